@@ -1,0 +1,100 @@
+"""Rows A3/A4: per-box depth statistic and depth-driven box scaling.
+
+Follows mmtrack/models/mot/ocsort_disparity.py:113-130 (bbox_postp_depth),
+:136-175 (extract_depth) and mmtrack/models/trackers/utils.py:58-73
+(scale_bbox).  Scalar typing follows the reference's pinned NumPy 1.x: the
+window bounds are Python floats (float64), d is float32, d*d is float32.
+"""
+import math
+
+import numpy as np
+
+MAX_DEPTH = 150      # ocsort_disparity.py:148
+MAX_BOX_W = 800      # ocsort_disparity.py:150
+
+
+def trunc_box(box):
+    """ocsort_disparity.py:141 ``box.astype(np.int)``: C truncation toward
+    zero; non-finite / out-of-range values give INT64_MIN as on x86-64."""
+    b = np.asarray(box, np.float32)
+    out = np.empty(4, np.int64)
+    for k in range(4):
+        v = float(b[k])
+        if not math.isfinite(v) or abs(v) >= 2.0 ** 63:
+            out[k] = np.iinfo(np.int64).min
+        else:
+            out[k] = int(v)
+    return out
+
+
+def _mean_f32(a):
+    """np.mean of a float32 array (float32 accumulation, NaN when empty)."""
+    a = np.asarray(a, np.float32)
+    if a.size == 0:
+        return np.float32(np.nan)
+    return np.float32(np.mean(a))
+
+
+def box_depth(depth, box):
+    """One box of extract_depth (:140-173).  Returns (d, scale): d is a
+    float32 (possibly NaN) or the int -1; scale a Python float."""
+    b = [int(v) for v in trunc_box(box)]
+    patch = depth[b[1]:b[3], b[0]:b[2]]
+    w = b[2] - b[0]
+    vals = patch[(patch < MAX_DEPTH) & (patch > 0)]
+    n = int(vals.size)
+    if n < 1 or w > MAX_BOX_W:
+        return -1, 1.0
+    srt = np.sort(vals, axis=None)
+    d_mid = srt[n // 2]
+    corners = np.asarray([
+        _mean_f32(depth[b[1]:b[1] + 2, b[0]:b[0] + 2]),
+        _mean_f32(depth[b[1]:b[1] + 2, b[2] - 2:b[2]]),
+        _mean_f32(depth[b[3] - 2:b[3], b[0]:b[0] + 2]),
+        _mean_f32(depth[b[3] - 2:b[3], b[2] - 2:b[2]])], np.float32)
+    with np.errstate(invalid='ignore'):
+        k = int(np.count_nonzero(corners > d_mid))
+    w_start = min(1 - k / 4, 0.4) * n
+    w_end = w_start + 0.6 * n
+    seg = srt[int(w_start):int(w_end)]
+    if seg.size == 0:
+        seg = srt[:-1]
+    d = _mean_f32(seg)
+    dd = float(np.float32(d * d))
+    # Python min/max keep the first argument when a comparison is False, so a
+    # NaN d gives a NaN scale (:171-172).
+    scale = min(dd, 3.0)
+    scale = max(scale, 1.0)
+    return d, scale
+
+
+def extract_depth(depth, bboxes):
+    """ocsort_disparity.py:136-175.  depth [H',W'] f32, bboxes [D,4] f32 xyxy.
+    Returns (d_values f32 [D] with -1 / NaN as in the reference, scales f32)."""
+    depth = np.asarray(depth, np.float32)
+    d_vals, scales = [], []
+    for box in np.asarray(bboxes, np.float32).reshape(-1, 4):
+        d, s = box_depth(depth, box)
+        d_vals.append(d)
+        scales.append(s)
+    return (np.asarray(d_vals, np.float32).reshape(-1),
+            np.asarray(scales, np.float32).reshape(-1))
+
+
+def scale_bbox(bboxes, scales):
+    """trackers/utils.py:58-73 in float32."""
+    b = np.asarray(bboxes, np.float32).reshape(-1, 4)
+    s = np.asarray(scales, np.float32)
+    two = np.float32(2)
+    cx = (b[:, 0] + b[:, 2]) / two
+    cy = (b[:, 1] + b[:, 3]) / two
+    w = (b[:, 2] - b[:, 0]) * s
+    h = (b[:, 3] - b[:, 1]) * s
+    return np.stack([cx - w / two, cy - h / two, cx + w / two, cy + h / two],
+                    -1).astype(np.float32)
+
+
+def bbox_postp_depth(depth, bboxes):
+    """ocsort_disparity.py:113-130: returns (inflated boxes, scales, d)."""
+    d, s = extract_depth(depth, bboxes)
+    return scale_bbox(bboxes, s), s, d

@@ -1,0 +1,87 @@
+"""Row A1: raw u16 disparity -> (mask, disparity px, depth m), resize, pad.
+
+Follows
+  mmtrack/datasets/transforms/loading_disparity.py:82-86,:129-134
+  mmtrack/datasets/transforms/transforms_disparity.py:52-70,:92-110 (nearest
+      resize through mmcv.imrescale == cv2.resize INTER_NEAREST)
+  mmtrack/datasets/transforms/transforms_disparity.py:177-194,:215-232 (pad)
+  mmtrack/models/mot/ocsort_disparity.py:132-134 (disp2depth)
+"""
+import numpy as np
+
+INVALID_RAW = 65535
+
+
+def load_postprocess(raw_u16):
+    """loading_disparity.py:82-83 (mask) and :129-134 (_post_processing_v2).
+
+    Returns (disp f32 [H,W] in pixels, mask u8 [H,W])."""
+    raw = np.asarray(raw_u16)
+    assert raw.dtype == np.uint16 and raw.ndim == 2
+    mask = (raw < INVALID_RAW).astype(np.uint8)
+    disp = raw.astype(np.float32)
+    disp[disp == INVALID_RAW] = 0
+    disp = disp / np.float32(16.0)
+    return disp, mask
+
+
+def rescale_size(h, w, scale):
+    """mmcv.image.geometric.rescale_size for a (a, b) tuple scale, keep_ratio.
+
+    transforms_disparity.py:55-60 passes results['scale'] = img_scale."""
+    long_edge, short_edge = max(scale), min(scale)
+    factor = min(long_edge / max(h, w), short_edge / min(h, w))
+    return int(h * float(factor) + 0.5), int(w * float(factor) + 0.5)
+
+
+def nearest_index(dst_n, src_n):
+    """cv2.resize(INTER_NEAREST) source index of every destination index:
+    min(floor(dst * (src/dst_n)), src-1), scale evaluated in float64."""
+    inv = 1.0 / (dst_n / float(src_n))
+    idx = np.floor(np.arange(dst_n, dtype=np.float64) * inv).astype(np.int64)
+    return np.minimum(idx, src_n - 1)
+
+
+def nearest_resize(img, new_h, new_w):
+    """transforms_disparity.py:52-70.  Values are NOT multiplied by the resize
+    factor (the reference does not either)."""
+    h, w = img.shape[:2]
+    if (new_h, new_w) == (h, w):
+        return img.copy()
+    return img[nearest_index(new_h, h)][:, nearest_index(new_w, w)]
+
+
+def pad_to_divisor(img, divisor=32, value=0):
+    """transforms_disparity.py:177-194: bottom/right constant pad."""
+    h, w = img.shape[:2]
+    ph = int(np.ceil(h / divisor)) * divisor
+    pw = int(np.ceil(w / divisor)) * divisor
+    out = np.full((ph, pw) + img.shape[2:], value, dtype=img.dtype)
+    out[:h, :w] = img
+    return out
+
+
+def disp2depth(disp, baseline=0.25, focal_length=640):
+    """ocsort_disparity.py:132-134: Z = B*f / (d + 1e-6) in float32.
+
+    torch evaluates ``python_scalar / tensor`` as ``tensor.reciprocal() *
+    scalar`` (Tensor.__rtruediv__), i.e. two float32 roundings."""
+    bf = np.float32(baseline * focal_length)
+    return (np.float32(1) / (np.asarray(disp, np.float32) + np.float32(1e-6))) * bf
+
+
+def preprocess(raw_u16, img_scale=None, size_divisor=32, baseline=0.25,
+               focal_length=640):
+    """Whole A1 chain for one frame.
+
+    Returns dict(disp [H',W'] f32, mask [H',W'] u8, depth [H',W'] f32)."""
+    disp, mask = load_postprocess(raw_u16)
+    h, w = disp.shape
+    if img_scale is not None:
+        nh, nw = rescale_size(h, w, img_scale)
+        disp = nearest_resize(disp, nh, nw)
+        mask = nearest_resize(mask, nh, nw)
+    disp = pad_to_divisor(disp, size_divisor, 0)
+    mask = pad_to_divisor(mask, size_divisor, 0)
+    return dict(disp=disp, mask=mask,
+                depth=disp2depth(disp, baseline, focal_length))

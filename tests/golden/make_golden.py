@@ -1,0 +1,214 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference
+modules (loaded from /root/reference through ``ref_shims.py``) on seeded
+synthetic inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Outputs (small .npz files next to this script):
+  ref_kf.npz          KalmanFilter.initiate/predict/update chains
+  ref_boxdepth.npz    OCSORT_Disparity.extract_depth / bbox_postp_depth /
+                      scale_bbox on random and edge-case boxes
+  ref_track_<name>.npz  OCSORT_Disparity.predict() over whole sequences:
+                      inputs (raw disparity, detections) and the reference's
+                      pred_track_instances + tracker state per frame
+The oracle (oracle/) is then checked against these files by
+tests/test_oracle_golden.py, and the CUDA path by tests/test_gpu_*.py.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_shims  # noqa: E402
+from oracle import disparity as odisp  # noqa: E402  (A1 preprocessing of inputs only)
+from stereotracking_b200.synthetic import SceneConfig, SyntheticStereo  # noqa: E402
+
+TRACKER_CFG = dict(obj_score_thr=0.3, init_track_thr=0.7,
+                   weight_iou_with_det_scores=False, match_iou_thr=0.1,
+                   num_tentatives=3, vel_consist_weight=0.2, vel_delta_t=3,
+                   num_frames_retain=30)
+
+
+def ragged(list_of_arrays, width, dtype):
+    n = max([len(a) for a in list_of_arrays] + [1])
+    shape = (len(list_of_arrays), n) + ((width,) if width else ())
+    out = np.zeros(shape, dtype)
+    cnt = np.zeros(len(list_of_arrays), np.int64)
+    for i, a in enumerate(list_of_arrays):
+        a = np.asarray(a, dtype).reshape((-1,) + ((width,) if width else ()))
+        out[i, :len(a)] = a
+        cnt[i] = len(a)
+    return out, cnt
+
+
+def make_kf(ns):
+    rng = np.random.default_rng(11)
+    kf = ns.KalmanFilter()
+    z0 = np.asarray([[300.5, 200.25, 0.8, 40.0], [15.0, 700.0, 1.3, 11.5]], np.float32)
+    means, covs, zs, ops = [], [], [], []
+    for z in z0:
+        m, c = kf.initiate(z)
+        means.append(m.copy()); covs.append(c.copy()); zs.append(z.astype(np.float64)); ops.append(0)
+        for step in range(12):
+            if rng.random() < 0.7:
+                m, c = kf.predict(m, c)
+                means.append(m.copy()); covs.append(c.copy()); zs.append(np.zeros(4)); ops.append(1)
+            zz = (m[:4] + rng.normal(0, [2, 2, 0.01, 1])).astype(np.float32)
+            m, c = kf.update(m, c, zz)
+            means.append(m.copy()); covs.append(c.copy()); zs.append(zz.astype(np.float64)); ops.append(2)
+    np.savez_compressed(os.path.join(HERE, 'ref_kf.npz'), mean=np.stack(means),
+                        cov=np.stack(covs), z=np.stack(zs), op=np.asarray(ops),
+                        chain_start=np.asarray([0, ops.index(0, 1)]))
+
+
+def edge_depth_map(rng, H=96, W=128):
+    raw = rng.integers(10, 900, (H, W)).astype(np.uint16)
+    raw[rng.random((H, W)) < 0.2] = 65535
+    raw[40:60, 50:80] = 320            # a constant-depth object
+    raw[0:8, 0:8] = 65535              # an all-invalid corner
+    raw[70:72, 90:92] = 400            # tiny valid island inside invalid area
+    raw[64:80, 84:100][raw[64:80, 84:100] != 400] = 65535
+    return raw
+
+
+def make_boxdepth(ns):
+    rng = np.random.default_rng(5)
+    model = ref_shims.build_model(ns, TRACKER_CFG)
+    raw = edge_depth_map(rng)
+    pre = odisp.preprocess(raw)
+    disp = torch.from_numpy(pre['disp'])[None, None].repeat(1, 3, 1, 1)
+    H, W = pre['depth'].shape
+    boxes = []
+    for _ in range(60):
+        x1, y1 = rng.uniform(-5, W - 4), rng.uniform(-5, H - 4)
+        boxes.append([x1, y1, x1 + rng.uniform(1, 60), y1 + rng.uniform(1, 60)])
+    boxes += [[50, 40, 80, 60], [52.3, 41.7, 77.9, 58.2], [0, 0, 8, 8], [0, 0, 3, 3],
+              [70, 70, 72, 72], [70.2, 70.9, 71.9, 71.1], [84, 64, 100, 80], [90, 70, 91, 71],
+              [-3.5, -2.5, 6, 7], [W - 3, H - 3, W + 5, H + 5], [W, H, W + 4, H + 4],
+              [10, 10, 10, 30], [10, 10, 30, 10], [1, 1, 2.5, 2.5], [0.5, 0.5, 1.9, 1.9],
+              [20, 20, 19, 40], [5, 90, 120, 96], [0, 0, W, H], [126.5, 3, 128, 9]]
+    boxes = torch.tensor(boxes, dtype=torch.float32)
+    depth_t = model.disp2depth(disp[:, 0:1])
+    d, s = model.extract_depth(depth_t, boxes)
+    inst = ns.InstanceData(bboxes=boxes.clone())
+    inst2, dv = model.bbox_postp_depth(inst, disp, None)
+    np.savez_compressed(
+        os.path.join(HERE, 'ref_boxdepth.npz'), raw=raw, boxes=boxes.numpy(),
+        depth_map=depth_t.numpy().squeeze(), d=np.asarray(d, np.float32),
+        scales=np.asarray(s, np.float32), inflated=inst2.bboxes.numpy(),
+        deflated=ns.scale_bbox(inst2.bboxes, 1 / inst2.scales).numpy(),
+        cxcyah=ns.bbox_xyxy_to_cxcyah(boxes).numpy(),
+        xyxy_back=ns.bbox_cxcyah_to_xyxy(ns.bbox_xyxy_to_cxcyah(boxes)).numpy())
+
+
+def synth_dets(gen, F, rng, jitter=0.6, miss=0.05, clutter=3, blackout=()):
+    """Noisy-GT detections per frame (what the detector would return)."""
+    boxes, vis, _ = gen.gt_boxes(0, F)
+    H, W = gen.cfg.height, gen.cfg.width
+    out = []
+    for f in range(F):
+        b, s = [], []
+        if f not in blackout:
+            for k in range(boxes.shape[2]):
+                if not vis[f, 0, k] or rng.random() < miss:
+                    continue
+                bb = boxes[f, 0, k].numpy() + rng.normal(0, jitter, 4)
+                bb[0::2] = np.clip(bb[0::2], 0, W); bb[1::2] = np.clip(bb[1::2], 0, H)
+                b.append(bb); s.append(rng.uniform(0.25, 0.98))
+            for _ in range(rng.integers(0, clutter + 1)):
+                x, y = rng.uniform(0, W - 30), rng.uniform(0, H - 30)
+                b.append([x, y, x + rng.uniform(4, 30), y + rng.uniform(4, 30)])
+                s.append(rng.uniform(0.05, 0.9))
+        b = np.asarray(b, np.float32).reshape(-1, 4)
+        s = np.asarray(s, np.float32)
+        o = np.argsort(-s, kind='stable')
+        out.append((b[o], s[o]))
+    return out
+
+
+def run_reference_sequence(ns, raws, dets):
+    model = ref_shims.build_model(ns, TRACKER_CFG)
+    frames = []
+    for f, (raw, (b, s)) in enumerate(zip(raws, dets)):
+        pre = odisp.preprocess(raw)
+        disp = torch.from_numpy(pre['disp'])[None, None, None].repeat(1, 1, 3, 1, 1)
+        mask = torch.from_numpy(pre['mask'])[None, None, None]
+        img = torch.zeros_like(disp)
+        model.detector.next = ns.InstanceData(
+            bboxes=torch.from_numpy(b.copy()), scores=torch.from_numpy(s.copy()),
+            labels=torch.zeros(len(b), dtype=torch.int64))
+        sample = ns.TrackDataSample(frame_id=f)
+        res = model.predict(dict(img=img, disp_postp=disp, disp_mask=mask), [sample])[0]
+        ti = res.pred_track_instances
+        trk = model.tracker
+        ids = list(trk.tracks.keys())
+        frames.append(dict(
+            bboxes=ti.bboxes.numpy(), ids=ti.instances_id.numpy(), scores=ti.scores.numpy(),
+            labels=ti.labels.numpy(), scales=ti.scales.numpy(),
+            depth=np.asarray(ti.depth, np.float32),
+            st_ids=np.asarray(ids, np.int64),
+            st_mean=np.stack([np.asarray(trk.tracks[i].mean, np.float64) for i in ids]) if ids else np.zeros((0, 8)),
+            st_cov=np.stack([trk.tracks[i].covariance for i in ids]) if ids else np.zeros((0, 8, 8)),
+            st_tent=np.asarray([bool(trk.tracks[i].tentative) for i in ids]),
+            st_tracked=np.asarray([bool(trk.tracks[i].tracked) for i in ids]),
+            st_vel=np.stack([trk.tracks[i].velocity.numpy().astype(np.float32) for i in ids]) if ids else np.zeros((0, 2), np.float32),
+            num_tracks=int(trk.num_tracks)))
+    return frames
+
+
+def save_sequence(name, raws, dets, frames):
+    pack = {}
+    pack['raw'] = np.stack(raws)
+    pack['det_boxes'], pack['det_count'] = ragged([d[0] for d in dets], 4, np.float32)
+    pack['det_scores'], _ = ragged([d[1] for d in dets], 0, np.float32)
+    for key, width, dt in [('bboxes', 4, np.float32), ('ids', 0, np.int64), ('scores', 0, np.float32),
+                           ('labels', 0, np.int64), ('scales', 0, np.float32), ('depth', 0, np.float32),
+                           ('st_ids', 0, np.int64), ('st_mean', 8, np.float64), ('st_tent', 0, np.bool_),
+                           ('st_tracked', 0, np.bool_), ('st_vel', 2, np.float32)]:
+        pack['out_' + key], cnt = ragged([fr[key] for fr in frames], width, dt)
+        if key == 'ids':
+            pack['out_count'] = cnt
+        if key == 'st_ids':
+            pack['st_count'] = cnt
+    n = pack['out_st_ids'].shape[1]
+    cov = np.zeros((len(frames), n, 8, 8))
+    for i, fr in enumerate(frames):
+        cov[i, :len(fr['st_cov'])] = fr['st_cov']
+    pack['out_st_cov'] = cov
+    pack['num_tracks'] = np.asarray([fr['num_tracks'] for fr in frames], np.int64)
+    np.savez_compressed(os.path.join(HERE, f'ref_track_{name}.npz'), **pack)
+    total = sum(len(fr['ids']) for fr in frames)
+    print(f'{name}: {len(frames)} frames, {total} track rows, max id {max(fr["num_tracks"] for fr in frames)}')
+
+
+def make_sequences(ns):
+    scen = {
+        'basic': dict(cfg=SceneConfig(160, 224, 5, 8, n_clutter=0), F=36, seed=3, miss=0.05, clutter=3, blackout=()),
+        'occlusion': dict(cfg=SceneConfig(160, 224, 6, 9, n_clutter=0), F=48, seed=4, miss=0.30, clutter=2,
+                          blackout=(20, 21, 33)),
+        'stress': dict(cfg=SceneConfig(192, 256, 8, 14, invalid_prob=0.30, n_clutter=0, heavy_ego=True),
+                       F=40, seed=5, miss=0.15, clutter=8, blackout=(0, 9)),
+    }
+    for name, sc in scen.items():
+        gen = SyntheticStereo(sc['cfg'], 1, sc['F'], seed=sc['seed'])
+        fr = gen.frames(0, sc['F'])
+        raws = [fr['raw'][f, 0].numpy() for f in range(sc['F'])]
+        rng = np.random.default_rng(sc['seed'] + 100)
+        dets = synth_dets(gen, sc['F'], rng, miss=sc['miss'], clutter=sc['clutter'],
+                          blackout=sc['blackout'])
+        frames = run_reference_sequence(ns, raws, dets)
+        save_sequence(name, raws, dets, frames)
+
+
+if __name__ == '__main__':
+    ns = ref_shims.load()
+    make_kf(ns)
+    make_boxdepth(ns)
+    make_sequences(ns)
+    print('golden fixtures written to', HERE)

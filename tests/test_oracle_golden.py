@@ -1,0 +1,74 @@
+"""The oracle against the fixtures produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import boxdepth, disparity, kalman
+from oracle.model import StereoTrackOracle
+from oracle.tracker import cxcyah_to_xyxy, xyxy_to_cxcyah
+
+
+def test_kalman_chain_matches_reference():
+    g = np.load(os.path.join(GOLDEN, 'ref_kf.npz'))
+    m = c = None
+    for i, op in enumerate(g['op']):
+        if op == 0:
+            m, c = kalman.initiate(g['z'][i].astype(np.float32))
+        elif op == 1:
+            m, c = kalman.predict(m, c)
+        else:
+            m, c = kalman.update(m, c, g['z'][i].astype(np.float32))
+        np.testing.assert_allclose(m, g['mean'][i], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(c, g['cov'][i], rtol=1e-11, atol=1e-13)
+
+
+def test_boxdepth_matches_reference():
+    g = np.load(os.path.join(GOLDEN, 'ref_boxdepth.npz'))
+    pre = disparity.preprocess(g['raw'])
+    np.testing.assert_array_equal(pre['depth'], g['depth_map'])
+    d, s = boxdepth.extract_depth(pre['depth'], g['boxes'])
+    np.testing.assert_array_equal(d, g['d'])          # NaN == NaN positions too
+    np.testing.assert_array_equal(s, g['scales'])
+    assert np.isnan(g['d']).any() and (g['d'] == -1).any()
+    infl = boxdepth.scale_bbox(g['boxes'], s)
+    np.testing.assert_array_equal(infl, g['inflated'])
+    with np.errstate(invalid='ignore', divide='ignore'):
+        defl = boxdepth.scale_bbox(infl, np.float32(1) / s)
+    np.testing.assert_array_equal(defl, g['deflated'])
+    with np.errstate(invalid='ignore', divide='ignore'):
+        cx = np.stack([xyxy_to_cxcyah(b) for b in g['boxes']])
+    np.testing.assert_array_equal(cx, g['cxcyah'])
+    np.testing.assert_array_equal(cxcyah_to_xyxy(cx), g['xyxy_back'])
+
+
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress'])
+def test_tracker_sequence_matches_reference(name):
+    g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
+    o = StereoTrackOracle()
+    lost_recovered = 0
+    for f in range(len(g['raw'])):
+        n = int(g['det_count'][f])
+        pre = o.depth_map(g['raw'][f])
+        r = o.step_from_dets(f, pre['depth'], g['det_boxes'][f, :n], g['det_scores'][f, :n],
+                             np.zeros(n, np.int64))
+        m = int(g['out_count'][f])
+        np.testing.assert_array_equal(r['instances_id'], g['out_ids'][f, :m], err_msg=f'frame {f}')
+        np.testing.assert_array_equal(r['bboxes'], g['out_bboxes'][f, :m])
+        np.testing.assert_array_equal(r['scores'], g['out_scores'][f, :m])
+        np.testing.assert_array_equal(r['scales'], g['out_scales'][f, :m])
+        np.testing.assert_array_equal(r['depth'], g['out_depth'][f, :m])
+        st = o.tracker.export_state()
+        k = int(g['st_count'][f])
+        np.testing.assert_array_equal(st['ids'], g['out_st_ids'][f, :k])
+        np.testing.assert_array_equal(st['tentative'], g['out_st_tent'][f, :k])
+        np.testing.assert_array_equal(st['tracked'], g['out_st_tracked'][f, :k])
+        np.testing.assert_allclose(st['mean'], g['out_st_mean'][f, :k], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(st['cov'], g['out_st_cov'][f, :k], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(st['velocity'], g['out_st_vel'][f, :k], rtol=1e-6, atol=1e-7)
+        assert st['num_tracks'] == g['num_tracks'][f]
+        lost_recovered += int((~g['out_st_tracked'][f, :k]).sum())
+    if name != 'basic':
+        assert lost_recovered > 0      # the scenario exercised lost tracks
