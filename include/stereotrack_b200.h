@@ -1,0 +1,170 @@
+/* stereotrack_b200.h - C ABI of the B200-native depth-guided tracking path.
+ *
+ * Drop-in boundary for the per-frame path of Superjie13/StereoTracking that
+ * runs after the detector backbone and around the disparity input
+ * (mmtrack/models/mot/ocsort_disparity.py:82-109 and everything it calls).
+ * The reference is pure Python, so there is no FFI in the reference to bind;
+ * these entry points are what the Python boundary classes in
+ * stereotracking_b200/ (same registry names and call signatures as the
+ * reference) call through ctypes.  INTEGRATION.md shows the reference-side
+ * binding.
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer into caller-owned memory unless the
+ *    parameter name ends in _host;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    never allocates or frees caller memory, never synchronises, and is safe to
+ *    capture in a CUDA graph (st_create / st_destroy / st_export_state excepted);
+ *  - return value: 0 = ok, < 0 = error (st_error_string); nothing throws;
+ *  - S = sequences processed in lockstep (one frame each per call); per-sequence
+ *    arrays are padded to a fixed capacity with a separate count array;
+ *  - overflow of a capacity never truncates silently: the per-sequence bit is
+ *    raised in the handle's status words (st_read_status).
+ */
+#ifndef STEREOTRACK_B200_H
+#define STEREOTRACK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST_ABI_VERSION 1
+
+enum {
+    ST_OK = 0,
+    ST_ERR_INVALID_ARG = -1,
+    ST_ERR_CUDA = -2,
+    ST_ERR_NO_DEVICE = -3,
+    ST_ERR_CAPACITY = -4,
+    ST_ERR_ALLOC = -5
+};
+
+/* per-sequence status bits written by the kernels (sticky until st_clear_status) */
+enum {
+    ST_STATUS_CAND_OVERFLOW = 1,   /* more post-threshold candidates than max_candidates */
+    ST_STATUS_DET_OVERFLOW = 2,    /* more detections than the tracker's max_dets        */
+    ST_STATUS_TRACK_OVERFLOW = 4,  /* more live tracks than max_tracks                   */
+    ST_STATUS_LAP_GUARD = 8        /* assignment solver hit its iteration guard          */
+};
+
+/* Tracker / model configuration.  Field names and defaults follow the
+ * reference constructors: OCSORTTracker_Disparity
+ * (mmtrack/models/trackers/ocsort_tracker_disparity.py:42-52), KalmanTrackerBase
+ * (kalman_tracker_base.py:33-47), BaseTracker (base_tracker.py:22-32),
+ * OCSORT_Disparity (mmtrack/models/mot/ocsort_disparity.py:30-40) and the
+ * detector test_cfg (configs/stereo_tracking/ocsort/
+ * yolox_s_mmyolo_mot_airdrone_disp.py:42). */
+typedef struct st_config {
+    int32_t max_sequences;      /* S capacity of the handle                    */
+    int32_t max_tracks;         /* live tracks per sequence (<= 1024)          */
+    int32_t max_dets;           /* detections per sequence per frame (<= 1024) */
+    int32_t max_candidates;     /* post-threshold candidates per frame         */
+    float obj_score_thr;        /* 0.3  */
+    float init_track_thr;       /* 0.7  */
+    int32_t weight_iou_with_det_scores; /* 0/1 */
+    double match_iou_thr;       /* 0.1 in the shipped config (ctor default 0.3); double:
+                                 * cost_limit = 1 - match_iou_thr is Python float math */
+    int32_t num_tentatives;     /* 3    */
+    float vel_consist_weight;   /* 0.2  */
+    int32_t vel_delta_t;        /* 3 (<= 15) */
+    int32_t num_frames_retain;  /* 30 in the shipped config (ctor default 10)   */
+    float baseline;             /* 0.25 m */
+    float focal_length;         /* 640 px */
+    float score_thr;            /* 0.01 */
+    float nms_iou_thr;          /* 0.5  */
+} st_config;
+
+typedef struct st_handle st_handle;   /* opaque: owns the SoA track state of S x max_tracks slots */
+
+int st_abi_version(void);
+const char *st_error_string(int code);
+void st_default_config(st_config *cfg);
+
+/* Replaces the Python object state of OCSORTTracker_Disparity
+ * (base_tracker.py:34-37 `reset`, self.tracks / self.num_tracks). */
+int st_create(const st_config *cfg, st_handle **out);
+int st_destroy(st_handle *h);
+/* reset every sequence whose byte in seq_mask is non-zero (NULL = all) */
+int st_reset(st_handle *h, const uint8_t *seq_mask, void *stream);
+int st_read_status(st_handle *h, int32_t *status_host, int S);   /* synchronises */
+int st_clear_status(st_handle *h, void *stream);
+
+/* K1 - replaces loading_disparity.py:82-86,:129-134 (mask, 65535->0, /16),
+ * transforms_disparity.py:52-70 (nearest resize to Hr x Wr), :177-194 (zero pad
+ * to Hp x Wp) and ocsort_disparity.py:132-134 (Z = B*f/(d+1e-6)).
+ * raw [S,H,W] u16 -> depth [S,Hp,Wp] f32; optional disp3 [S,3,Hp,Wp] f32 (the
+ * detector's disp_postp input) and mask [S,Hp,Wp] u8. */
+int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, int Wr, int Hp, int Wp,
+                  float *depth, float *disp3, uint8_t *mask,
+                  float baseline, float focal_length, void *stream);
+
+/* K2 - replaces the detector-head post-process invoked at
+ * mmtrack/models/detectors/yolo_detector_disparity_v1.py:121-122 (mmyolo
+ * YOLOv5Head.predict_by_feat + YOLOXBBoxCoder.decode, mmdet
+ * filter_scores_and_topk, mmcv batched_nms).  Level l has maps cls[l]
+ * [S,num_classes,h_l,w_l], bbox[l] [S,4,h_l,w_l], obj[l] [S,1,h_l,w_l] (NCHW f32).
+ * Outputs are padded to det_cap rows per sequence, in descending score order:
+ * boxes [S,det_cap,4], scores [S,det_cap], labels [S,det_cap] i64, prior_idx
+ * [S,det_cap] i32 (flattened prior index), keep_idx [S,det_cap] i32 (position
+ * in the score-sorted candidate list, what mmcv nms returns), counts [S] i32. */
+int st_decode_nms(st_handle *h, const float *const *cls_host, const float *const *bbox_host,
+                  const float *const *obj_host, int num_levels, const int32_t *level_h_host,
+                  const int32_t *level_w_host, const int32_t *strides_host, int S, int num_classes,
+                  float scale_w, float scale_h, int ori_h, int ori_w, int det_cap,
+                  float *boxes, float *scores, int64_t *labels, int32_t *prior_idx,
+                  int32_t *keep_idx, int32_t *counts, void *stream);
+
+/* K3 - replaces OCSORT_Disparity.extract_depth + bbox_postp_depth + scale_bbox
+ * (ocsort_disparity.py:113-130,:136-175; trackers/utils.py:58-73).
+ * depth [S,Hp,Wp]; boxes [S,cap,4] xyxy; counts [S].  Outputs d [S,cap] (value,
+ * -1, or NaN exactly as the reference), scale [S,cap], inflated [S,cap,4]
+ * (may be NULL). */
+int st_box_depth(const float *depth, int S, int Hp, int Wp, const float *boxes,
+                 const int32_t *counts, int cap, float *d, float *scale, float *inflated,
+                 void *stream);
+
+/* scale_bbox(boxes, 1/scales) (ocsort_disparity.py:96-97) or scale_bbox(boxes,
+ * scales) when invert == 0. */
+int st_scale_boxes(const float *boxes, const float *scales, const int32_t *counts, int S, int cap,
+                   int invert, float *out, void *stream);
+
+/* K4+K5 - replaces OCSORTTracker_Disparity.track
+ * (ocsort_tracker_disparity.py:345-618) including KalmanFilter
+ * predict/update (motion/kalman_filter.py:87-189), the three lap.lapjv
+ * associations and BaseTracker.update / pop_invalid_tracks.
+ * Inputs = pred_det_instances fields (boxes already inflated), padded to
+ * det_cap rows, det_counts [S]; frame_ids [S] i32.  Outputs = the returned
+ * InstanceData fields, padded to det_cap rows, out_counts [S]. */
+int st_track_step(st_handle *h, int S, const int32_t *frame_ids, const float *det_boxes,
+                  const float *det_scores, const int64_t *det_labels, const float *det_scales,
+                  const float *det_depth, const int32_t *det_counts, int det_cap,
+                  float *out_boxes, float *out_scores, int64_t *out_labels, float *out_scales,
+                  float *out_depth, int64_t *out_ids, int32_t *out_counts, void *stream);
+
+/* Debug / parity / checkpoint: copies the live tracks of sequence `seq` in
+ * dict order to HOST arrays sized max_tracks (synchronises).  mean [T,8] f64,
+ * cov [T,64] f64, velocity [T,2] f32, flags [T] u8 (bit0 tentative, bit1
+ * tracked), hits/last_frame [T] i32.  Returns the number of live tracks. */
+int st_export_state(st_handle *h, int seq, int64_t *ids_host, double *mean_host, double *cov_host,
+                    float *velocity_host, uint8_t *flags_host, int32_t *hits_host,
+                    int32_t *last_frame_host, int64_t *num_tracks_host);
+
+/* Batched Kalman primitives on caller arrays (KalmanFilter.initiate/predict/
+ * update of motion/kalman_filter.py:60-189), one warp per track: mean [n,8],
+ * cov [n,64] f64 in place, z [n,4] f32 (cx,cy,a,h). op: 0 initiate, 1 predict,
+ * 2 update. */
+int st_kalman_batch(int op, int n, double *mean, double *cov, const float *z, void *stream);
+
+/* Batched association (ocm/ocr cost is built by st_track_step; this entry
+ * exposes the assignment itself for parity tests): cost [B,R,C] f32 ->
+ * row2col [B,R], col2row [B,C] i32 (-1 = unmatched), lap.lapjv(extend_cost=True,
+ * cost_limit) semantics.  Uses the handle's scratch; R,C <= max_tracks/max_dets. */
+int st_lapjv_batch(st_handle *h, int B, int R, int C, const float *cost, double cost_limit,
+                   int32_t *row2col, int32_t *col2row, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEREOTRACK_B200_H */

@@ -38,9 +38,13 @@ def _mean_f32(a):
 def box_depth(depth, box):
     """One box of extract_depth (:140-173).  Returns (d, scale): d is a
     float32 (possibly NaN) or the int -1; scale a Python float."""
-    b = [int(v) for v in trunc_box(box)]
+    bi = trunc_box(box)                       # np.int64: arithmetic wraps like the reference's
+    with np.errstate(over='ignore'):
+        w = int(bi[2] - bi[0])
+        e = [int(bi[0] + np.int64(2)), int(bi[1] + np.int64(2)),
+             int(bi[2] - np.int64(2)), int(bi[3] - np.int64(2))]
+    b = [int(v) for v in bi]
     patch = depth[b[1]:b[3], b[0]:b[2]]
-    w = b[2] - b[0]
     vals = patch[(patch < MAX_DEPTH) & (patch > 0)]
     n = int(vals.size)
     if n < 1 or w > MAX_BOX_W:
@@ -48,10 +52,10 @@ def box_depth(depth, box):
     srt = np.sort(vals, axis=None)
     d_mid = srt[n // 2]
     corners = np.asarray([
-        _mean_f32(depth[b[1]:b[1] + 2, b[0]:b[0] + 2]),
-        _mean_f32(depth[b[1]:b[1] + 2, b[2] - 2:b[2]]),
-        _mean_f32(depth[b[3] - 2:b[3], b[0]:b[0] + 2]),
-        _mean_f32(depth[b[3] - 2:b[3], b[2] - 2:b[2]])], np.float32)
+        _mean_f32(depth[b[1]:e[1], b[0]:e[0]]),
+        _mean_f32(depth[b[1]:e[1], e[2]:b[2]]),
+        _mean_f32(depth[e[3]:b[3], b[0]:e[0]]),
+        _mean_f32(depth[e[3]:b[3], e[2]:b[2]])], np.float32)
     with np.errstate(invalid='ignore'):
         k = int(np.count_nonzero(corners > d_mid))
     w_start = min(1 - k / 4, 0.4) * n

@@ -1,0 +1,745 @@
+// K4 + K5: one frame of the OC-SORT tracker with depth-scaled boxes for S
+// sequences in lockstep, one CTA per sequence, the whole frame in one launch:
+//   detection filter -> Kalman predict of confirmed tracks (one warp per track)
+//   -> OCM cost (1 - IoU + velocity-direction term) -> LAPJV  (stage 1)
+//   -> tentative tracks vs leftovers                           (stage 2)
+//   -> observation-centric recovery on last observations       (stage 3)
+//   -> online smoothing, Kalman update / track birth, eviction, id allocation.
+// Replaces OCSORTTracker_Disparity.track and everything it calls:
+//   mmtrack/models/trackers/ocsort_tracker_disparity.py:105-185,:187-343,:345-618
+//   mmtrack/models/trackers/kalman_tracker_base.py:50-88
+//   mmtrack/models/trackers/base_tracker.py:34-121
+//   mmtrack/models/motion/kalman_filter.py:60-189
+// Track state lives in the handle as a structure of arrays; `order` keeps the
+// live slots in ascending-id order, which is the reference's dict order.
+#include <new>
+#include "st_common.cuh"
+#include "kalman.cuh"
+#include "lapjv.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+
+struct Params {
+    int T, D;                    // capacities
+    float obj_score_thr, init_track_thr, vel_w;
+    int weight_iou, num_tentatives, vel_dt, retain;
+    double lap_half;             // (1 - match_iou_thr) / 2
+};
+
+struct Smem {                    // carved from dynamic shared memory
+    stlap::Scratch lap;
+    double *kf;                  // [kWarps][kScratchDoubles]
+    float *row_box;              // [T,4] track boxes of the current stage (xyxy)
+    float *row_vel;              // [T,2]
+    float *row_kc;               // [T,2] centre of the k-step observation (cx, cy)
+    float *det_box;              // [D,4] boxes of the dets in the current column list
+    int *rows;                   // [T] slot of each row of the current stage
+    int *dets;                   // [D] input index of each column of the current stage
+    int *det_slot;               // [D] per INPUT det: matched slot or -1
+    int *out_src;                // [D] output order -> input det index
+    unsigned char *row_valid;    // [T]
+    unsigned char *det_stage;    // [D] per INPUT det: 0 dropped, 1..3 matched in stage, 4 leftover
+    unsigned char *slot_hit;     // [T] per ORDER position: matched this frame
+};
+
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+__host__ __device__ inline size_t smem_bytes(int T, int D) {
+    size_t b = stlap::scratch_bytes(T + D);
+    b += align16(sizeof(double) * kWarps * stkf::kScratchDoubles);
+    b += align16(sizeof(float) * T * 4) + align16(sizeof(float) * T * 2) * 2 + align16(sizeof(float) * D * 4);
+    b += align16(sizeof(int) * T) + align16(sizeof(int) * D) * 3;
+    b += align16(T) + align16(D) + align16(T);
+    return b;
+}
+
+__device__ inline Smem carve(unsigned char *p, int T, int D) {
+    Smem m;
+    m.lap = stlap::carve(p, T + D); p += stlap::scratch_bytes(T + D);
+    m.kf = reinterpret_cast<double *>(p); p += align16(sizeof(double) * kWarps * stkf::kScratchDoubles);
+    m.row_box = reinterpret_cast<float *>(p); p += align16(sizeof(float) * T * 4);
+    m.row_vel = reinterpret_cast<float *>(p); p += align16(sizeof(float) * T * 2);
+    m.row_kc = reinterpret_cast<float *>(p); p += align16(sizeof(float) * T * 2);
+    m.det_box = reinterpret_cast<float *>(p); p += align16(sizeof(float) * D * 4);
+    m.rows = reinterpret_cast<int *>(p); p += align16(sizeof(int) * T);
+    m.dets = reinterpret_cast<int *>(p); p += align16(sizeof(int) * D);
+    m.det_slot = reinterpret_cast<int *>(p); p += align16(sizeof(int) * D);
+    m.out_src = reinterpret_cast<int *>(p); p += align16(sizeof(int) * D);
+    m.row_valid = p; p += align16(T);
+    m.det_stage = p; p += align16(D);
+    m.slot_hit = p;
+    return m;
+}
+
+__device__ __forceinline__ float sum4(const float *b) {      // torch .sum() of 4 float32
+    return __fadd_rn(__fadd_rn(__fadd_rn(b[0], b[1]), b[2]), b[3]);
+}
+
+// k_step_observation (:173-185): the observation vel_delta_t steps before the
+// newest one if it exists and is not None, else the last non-None observation
+__device__ inline const float *k_step_obs(const TrackState &st, long long g, int vel_dt) {
+    const int n = st.num_obs[g];
+    if (n > vel_dt) {
+        const int r = (n - 1 - vel_dt) % ST_RING;
+        if (st.obs_valid[g * ST_RING + r]) return st.obs_ring + (g * ST_RING + r) * 4;
+    }
+    return st.last_obs + g * 4;
+}
+
+__device__ inline void push_obs(const TrackState &st, long long g, const float *box) {
+    const int n = st.num_obs[g];
+    const int r = n % ST_RING;
+    if (box) {
+        for (int k = 0; k < 4; ++k) { st.obs_ring[(g * ST_RING + r) * 4 + k] = box[k]; st.last_obs[g * 4 + k] = box[k]; }
+        st.obs_valid[g * ST_RING + r] = 1;
+        st.miss_run[g] = 0;
+    } else {
+        st.obs_valid[g * ST_RING + r] = 0;
+        st.miss_run[g] += 1;
+    }
+    st.num_obs[g] = n + 1;
+}
+
+// vel_direction (:148-156)
+__device__ inline void vel_direction(const float *b1, const float *b2, float *out) {
+    if (sum4(b1) < 0.f || sum4(b2) < 0.f) { out[0] = -1.f; out[1] = -1.f; return; }
+    const float cx1 = __fmul_rn(__fadd_rn(b1[0], b1[2]), 0.5f), cy1 = __fmul_rn(__fadd_rn(b1[1], b1[3]), 0.5f);
+    const float cx2 = __fmul_rn(__fadd_rn(b2[0], b2[2]), 0.5f), cy2 = __fmul_rn(__fadd_rn(b2[1], b2[3]), 0.5f);
+    const float sy = __fsub_rn(cy2, cy1), sx = __fsub_rn(cx2, cx1);
+    const float norm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(sy, sy), __fmul_rn(sx, sx))), 1e-6f);
+    out[0] = __fdiv_rn(sy, norm);
+    out[1] = __fdiv_rn(sx, norm);
+}
+
+// mmdet bbox_overlaps(mode='iou', eps=1e-6) for one pair, float32
+__device__ __forceinline__ float iou_pair(const float *a, const float *b) {
+    const float a1 = __fmul_rn(__fsub_rn(a[2], a[0]), __fsub_rn(a[3], a[1]));
+    const float a2 = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
+    float w = __fsub_rn(fminf(a[2], b[2]), fmaxf(a[0], b[0]));
+    float h = __fsub_rn(fminf(a[3], b[3]), fmaxf(a[1], b[1]));
+    w = w < 0.f ? 0.f : w;           // clamp(min=0) keeps NaN
+    h = h < 0.f ? 0.f : h;
+    const float inter = __fmul_rn(w, h);
+    float uni = __fsub_rn(__fadd_rn(a1, a2), inter);
+    uni = uni < 1e-6f ? 1e-6f : uni; // torch.max(union, eps) (NaN stays NaN)
+    return __fdiv_rn(inter, uni);
+}
+
+// ordered (stable) compaction of the indices i in [0,n) with flag(i) into dst;
+// executed by warp 0, returns the count to every thread of the block via *cnt_sh
+template <typename F>
+__device__ inline void compact_warp0(int n, F flag, int *dst, int *cnt_sh) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int total = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const bool f = i < n && flag(i);
+            const unsigned b = __ballot_sync(0xffffffffu, f);
+            if (f) dst[total + __popc(b & ((1u << lane) - 1u))] = i;
+            total += __popc(b);
+        }
+        if (lane == 0) *cnt_sh = total;
+    }
+    __syncthreads();
+}
+
+struct DetView {
+    const float *boxes, *scores, *scales, *depth;
+    const int64_t *labels;
+};
+
+// one association stage: rows = slots in sm.rows[0..R), cols = input dets in
+// sm.dets[0..C).  ocm = velocity-direction term on (stage 1/2); boxes of the
+// rows come from the Kalman mean (ocm) or the last observation (ocr).
+__device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long long sbase, int R, int C,
+                          bool ocm, const DetView &dv, float *cost, int stage_code, int32_t *status_word) {
+    if (R == 0 || C == 0) return;           // dists.size == 0 -> nothing matched (:263-265)
+    // ---- per-row data --------------------------------------------------------
+    for (int r = threadIdx.x; r < R; r += kThreads) {
+        const long long g = sbase + sm.rows[r];
+        if (ocm) {
+            // track_bboxes = cxcyah_to_xyxy(float32(mean[:4])) (:217-223)
+            const float cx = (float)st.mean[g * 8 + 0], cy = (float)st.mean[g * 8 + 1];
+            const float a = (float)st.mean[g * 8 + 2], h = (float)st.mean[g * 8 + 3];
+            const float hw = __fmul_rn(__fmul_rn(a, h), 0.5f), hh = __fmul_rn(h, 0.5f);
+            sm.row_box[r * 4 + 0] = __fsub_rn(cx, hw);
+            sm.row_box[r * 4 + 1] = __fsub_rn(cy, hh);
+            sm.row_box[r * 4 + 2] = __fadd_rn(cx, hw);
+            sm.row_box[r * 4 + 3] = __fadd_rn(cy, hh);
+            const float v0 = st.velocity[g * 2], v1 = st.velocity[g * 2 + 1];
+            sm.row_vel[r * 2] = v0;
+            sm.row_vel[r * 2 + 1] = v1;
+            const float *ko = k_step_obs(st, g, pr.vel_dt);
+            sm.row_kc[r * 2] = __fmul_rn(__fadd_rn(ko[0], ko[2]), 0.5f);
+            sm.row_kc[r * 2 + 1] = __fmul_rn(__fadd_rn(ko[1], ko[3]), 0.5f);
+            sm.row_valid[r] = (__fadd_rn(v0, v1) != -2.f) && (sum4(ko) != -4.f);
+        } else {
+            for (int k = 0; k < 4; ++k) sm.row_box[r * 4 + k] = st.last_obs[g * 4 + k];
+        }
+    }
+    for (int c = threadIdx.x; c < C; c += kThreads)
+        for (int k = 0; k < 4; ++k) sm.det_box[c * 4 + k] = dv.boxes[sm.dets[c] * 4 + k];
+    __syncthreads();
+    // ---- cost matrix -----------------------------------------------------------
+    const float kHalfPi = 1.57079637f, kPi = 3.14159274f;
+    for (int e = threadIdx.x; e < R * C; e += kThreads) {
+        const int r = e / C, c = e % C;
+        const float *tb = sm.row_box + r * 4, *db = sm.det_box + c * 4;
+        float iou = iou_pair(tb, db);
+        if (pr.weight_iou) iou = __fmul_rn(iou, dv.scores[sm.dets[c]]);
+        float dist = __fsub_rn(1.f, iou);
+        if (ocm) {
+            const float dcx = __fmul_rn(__fadd_rn(db[0], db[2]), 0.5f), dcy = __fmul_rn(__fadd_rn(db[1], db[3]), 0.5f);
+            float dy = __fsub_rn(dcy, sm.row_kc[r * 2 + 1]), dx = __fsub_rn(dcx, sm.row_kc[r * 2]);
+            const float norm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx))), 1e-6f);
+            dy = __fdiv_rn(dy, norm);
+            dx = __fdiv_rn(dx, norm);
+            float cs = __fadd_rn(__fmul_rn(dy, sm.row_vel[r * 2]), __fmul_rn(dx, sm.row_vel[r * 2 + 1]));
+            cs = cs < -1.f ? -1.f : (cs > 1.f ? 1.f : cs);
+            const float ang = st_acos_f32(cs);
+            const float na = __fdiv_rn(__fsub_rn(ang, kHalfPi), kPi);
+            const float term = __fmul_rn(na, sm.row_valid[r] ? 1.f : 0.f);
+            dist = __fadd_rn(dist, __fmul_rn(term, pr.vel_w));
+        }
+        cost[e] = dist;
+    }
+    __syncthreads();
+    // ---- assignment (warp 0) -----------------------------------------------------
+    if (threadIdx.x < 32) {
+        stlap::Problem P;
+        P.cost = cost; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
+        const bool ok = stlap::solve_warp(P, sm.lap);
+        if (!ok && threadIdx.x == 0) atomicOr(status_word, ST_STATUS_LAP_GUARD);
+    }
+    __syncthreads();
+    // col -> row; rows >= R are the solver's dummy rows (= unmatched)
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+        const int r = sm.lap.y[c];
+        if (r >= 0 && r < R) {
+            sm.det_slot[sm.dets[c]] = sm.rows[r];
+            sm.det_stage[sm.dets[c]] = (unsigned char)stage_code;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads)
+k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
+              const float *__restrict__ det_boxes, const float *__restrict__ det_scores,
+              const int64_t *__restrict__ det_labels, const float *__restrict__ det_scales,
+              const float *__restrict__ det_depth, const int32_t *__restrict__ det_counts, int det_cap,
+              float *__restrict__ cost_ws, float *__restrict__ out_boxes, float *__restrict__ out_scores,
+              int64_t *__restrict__ out_labels, float *__restrict__ out_scales,
+              float *__restrict__ out_depth, int64_t *__restrict__ out_ids,
+              int32_t *__restrict__ out_counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sh_cnt[4];
+    __shared__ int sh_nlive;
+    const int s = blockIdx.x;
+    const int T = pr.T, D = pr.D;
+    Smem sm = carve(smem_raw, T, D);
+    const long long sbase = (long long)s * T;
+    const int frame = frame_ids[s];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *kfws = sm.kf + warp * stkf::kScratchDoubles;
+    int32_t *order = st.order + sbase;
+    int32_t *free_slots = st.free_slots + sbase;
+    float *cost = cost_ws + (long long)s * T * D;
+    DetView dv;
+    dv.boxes = det_boxes + (long long)s * det_cap * 4;
+    dv.scores = det_scores + (long long)s * det_cap;
+    dv.labels = det_labels + (long long)s * det_cap;
+    dv.scales = det_scales + (long long)s * det_cap;
+    dv.depth = det_depth + (long long)s * det_cap;
+    int nd_in = det_counts[s];
+    if (nd_in > D) {
+        if (threadIdx.x == 0) atomicOr(&st.status[s], ST_STATUS_DET_OVERFLOW);
+        nd_in = D;
+    }
+    if (nd_in > det_cap) nd_in = det_cap;
+
+    // frame 0: reset() (:385-387)
+    if (frame == 0) {
+        for (int i = threadIdx.x; i < T; i += kThreads) free_slots[i] = T - 1 - i;
+        if (threadIdx.x == 0) { st.n_live[s] = 0; st.n_free[s] = T; st.next_id[s] = 0; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sh_nlive = st.n_live[s];
+    for (int i = threadIdx.x; i < nd_in; i += kThreads) { sm.det_slot[i] = -1; sm.det_stage[i] = 0; }
+    __syncthreads();
+    const int n_live = sh_nlive;
+    int n_out = 0;
+
+    if (n_live == 0 || nd_in == 0) {
+        // ---- init-only branch (:391-403): keep scores > init_track_thr, all new ids
+        compact_warp0(nd_in, [&](int i) { return dv.scores[i] > pr.init_track_thr; }, sm.out_src, &sh_cnt[0]);
+        n_out = sh_cnt[0];
+        for (int i = threadIdx.x; i < n_out; i += kThreads) sm.det_stage[sm.out_src[i]] = 4;
+        __syncthreads();
+    } else {
+        // ---- detection filter (:412-421)
+        compact_warp0(nd_in, [&](int i) {
+            const float *b = dv.boxes + i * 4;
+            const float area = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
+            return dv.scores[i] > pr.obj_score_thr && area > 100.f;
+        }, sm.dets, &sh_cnt[0]);
+        int C = sh_cnt[0];
+        for (int c = threadIdx.x; c < C; c += kThreads) sm.det_stage[sm.dets[c]] = 4;   // leftover unless matched
+        for (int p = threadIdx.x; p < n_live; p += kThreads) sm.slot_hit[p] = 0;
+        // ---- confirmed tracks: predict (:431-441)
+        compact_warp0(n_live, [&](int p) { return !st.tentative[sbase + order[p]]; }, sm.rows, &sh_cnt[1]);
+        int R = sh_cnt[1];
+        for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = order[sm.rows[r]];   // position -> slot
+        __syncthreads();
+        for (int r = warp; r < R; r += kWarps) {
+            const long long g = sbase + sm.rows[r];
+            if (st.last_frame[g] != frame - 1) { if (lane == 0) st.mean[g * 8 + 7] = 0.0; }
+            __syncwarp();
+            if (st.tracked[g]) {
+                for (int e = lane; e < 64; e += 32) st.saved_cov[g * 64 + e] = st.cov[g * 64 + e];
+                if (lane < 8) st.saved_mean[g * 8 + lane] = st.mean[g * 8 + lane];
+                if (lane == 0) st.has_saved[g] = 1;
+            }
+            __syncwarp();
+            stkf::predict(st.mean + g * 8, st.cov + g * 64, kfws);
+        }
+        __syncthreads();
+        // ---- stage 1: confirmed tracks vs filtered dets (:448-474)
+        associate(st, pr, sm, sbase, R, C, true, dv, cost, 1, &st.status[s]);
+        // ---- stage 2: tentative tracks vs leftovers (:476-503)
+        compact_warp0(nd_in, [&](int i) { return sm.det_stage[i] == 4; }, sm.dets, &sh_cnt[0]);
+        C = sh_cnt[0];
+        compact_warp0(n_live, [&](int p) { return st.tentative[sbase + order[p]] != 0; }, sm.rows, &sh_cnt[1]);
+        R = sh_cnt[1];
+        for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = order[sm.rows[r]];
+        __syncthreads();
+        associate(st, pr, sm, sbase, R, C, true, dv, cost, 2, &st.status[s]);
+        // ---- which tracks are matched so far
+        for (int i = threadIdx.x; i < nd_in; i += kThreads) {
+            const int slot = sm.det_slot[i];
+            if (slot >= 0)
+                for (int p = 0; p < n_live; ++p)
+                    if (order[p] == slot) { sm.slot_hit[p] = 1; break; }
+        }
+        __syncthreads();
+        // ---- stage 3: OCR, every unmatched track's last observation (:505-569)
+        compact_warp0(nd_in, [&](int i) { return sm.det_stage[i] == 4; }, sm.dets, &sh_cnt[0]);
+        C = sh_cnt[0];
+        compact_warp0(n_live, [&](int p) { return !sm.slot_hit[p]; }, sm.rows, &sh_cnt[1]);
+        R = sh_cnt[1];
+        for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = order[sm.rows[r]];
+        __syncthreads();
+        associate(st, pr, sm, sbase, R, C, false, dv, cost, 3, &st.status[s]);
+        for (int i = threadIdx.x; i < nd_in; i += kThreads) {
+            const int slot = sm.det_slot[i];
+            if (slot >= 0 && sm.det_stage[i] == 3)
+                for (int p = 0; p < n_live; ++p)
+                    if (order[p] == slot) { sm.slot_hit[p] = 1; break; }
+        }
+        __syncthreads();
+        // ---- online smoothing of re-found lost tracks (:571-577, :319-343)
+        for (int i = warp; i < nd_in; i += kWarps) {
+            const int slot = sm.det_slot[i];
+            if (slot < 0) continue;
+            const long long g = sbase + slot;
+            if (st.tracked[g]) continue;
+            const int miss = st.miss_run[g];
+            float last[4], shift[4];
+            const float denom = (float)(miss + 1);
+            for (int k = 0; k < 4; ++k) {
+                last[k] = st.last_obs[g * 4 + k];
+                shift[k] = __fdiv_rn(__fsub_rn(dv.boxes[i * 4 + k], last[k]), denom);
+            }
+            if (st.has_saved[g]) {
+                for (int e = lane; e < 64; e += 32) st.cov[g * 64 + e] = st.saved_cov[g * 64 + e];
+                if (lane < 8) st.mean[g * 8 + lane] = st.saved_mean[g * 8 + lane];
+            }
+            __syncwarp();
+            for (int t = 0; t < miss; ++t) {
+                float vb[4], zc[4];
+                double z[4];
+                for (int k = 0; k < 4; ++k) vb[k] = __fadd_rn(last[k], __fmul_rn((float)(t + 1), shift[k]));
+                stkf::xyxy_to_cxcyah(vb, zc);
+                for (int k = 0; k < 4; ++k) z[k] = (double)zc[k];
+                stkf::update(st.mean + g * 8, st.cov + g * 64, z, kfws);
+            }
+        }
+        __syncthreads();
+        // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582)
+        for (int p = threadIdx.x; p < n_live; p += kThreads)
+            if (!sm.slot_hit[p]) {
+                const long long g = sbase + order[p];
+                st.tracked[g] = 0;
+                push_obs(st, g, nullptr);
+            }
+        // ---- output order: stage 1, 2, 3 matches then leftovers (:584-596)
+        if (threadIdx.x < 32) {
+            int total = 0;
+            for (int code = 1; code <= 4; ++code)
+                for (int i0 = 0; i0 < nd_in; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool f = i < nd_in && sm.det_stage[i] == code;
+                    const unsigned b = __ballot_sync(0xffffffffu, f);
+                    if (f) sm.out_src[total + __popc(b & ((1u << lane) - 1u))] = i;
+                    total += __popc(b);
+                }
+            if (lane == 0) sh_cnt[0] = total;
+        }
+        __syncthreads();
+        n_out = sh_cnt[0];
+    }
+
+    // ---- ids + BaseTracker.update (:598-605, base_tracker.py:54-91) ------------
+    // new tracks are exactly the outputs without a slot; they are last in order
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int first_new = n_out;
+        for (int k = 0; k < n_out; ++k)
+            if (sm.det_slot[sm.out_src[k]] < 0) { first_new = k; break; }
+        sh_cnt[1] = first_new;
+    }
+    __syncthreads();
+    const int first_new = sh_cnt[1];
+    const int n_new = n_out - first_new;
+    const long long id0 = st.next_id[s];
+    const int n_free = st.n_free[s];
+    int n_create = n_new;
+    if (n_live + n_new > T) {
+        n_create = T - n_live;
+        if (threadIdx.x == 0) atomicOr(&st.status[s], ST_STATUS_TRACK_OVERFLOW);
+    }
+    __syncthreads();
+    for (int k = warp; k < n_out; k += kWarps) {
+        const int i = sm.out_src[k];
+        const float *box = dv.boxes + i * 4;
+        float zc[4];
+        stkf::xyxy_to_cxcyah(box, zc);
+        int slot = sm.det_slot[i];
+        long long id;
+        if (slot >= 0) {
+            // update_track (:128-146 + kalman_tracker_base.py:65-75)
+            const long long g = sbase + slot;
+            id = st.id[g];
+            double z[4];
+            for (int q = 0; q < 4; ++q) z[q] = (double)zc[q];
+            stkf::update(st.mean + g * 8, st.cov + g * 64, z, kfws);
+            if (lane == 0) {
+                st.hits[g] += 1;
+                st.last_frame[g] = frame;
+                if (st.tentative[g] && st.hits[g] >= pr.num_tentatives) st.tentative[g] = 0;
+                st.tracked[g] = 1;
+                push_obs(st, g, box);
+                vel_direction(k_step_obs(st, g, pr.vel_dt), box, st.velocity + g * 2);
+            }
+        } else {
+            const int r = k - first_new;
+            id = id0 + r;
+            if (r < n_create) {
+                // init_track (:105-126 + kalman_tracker_base.py:55-63)
+                slot = free_slots[n_free - 1 - r];
+                const long long g = sbase + slot;
+                stkf::initiate(st.mean + g * 8, st.cov + g * 64, zc);
+                if (lane == 0) {
+                    st.id[g] = id;
+                    st.hits[g] = 1;
+                    st.last_frame[g] = frame;
+                    st.tentative[g] = frame != 0;
+                    st.tracked[g] = 1;
+                    st.has_saved[g] = 0;
+                    st.num_obs[g] = 0;
+                    st.miss_run[g] = 0;
+                    push_obs(st, g, box);
+                    st.velocity[g * 2] = -1.f;
+                    st.velocity[g * 2 + 1] = -1.f;
+                    order[n_live + r] = slot;
+                }
+            }
+        }
+        if (lane == 0) {
+            const long long o = (long long)s * det_cap + k;
+            if (slot >= 0) {
+                const long long g = sbase + slot;
+                for (int q = 0; q < 4; ++q) st.last_box[g * 4 + q] = box[q];
+                st.last_score[g] = dv.scores[i];
+                st.last_scale[g] = dv.scales[i];
+                st.last_depth[g] = dv.depth[i];
+                st.last_label[g] = dv.labels[i];
+            }
+            for (int q = 0; q < 4; ++q) out_boxes[o * 4 + q] = box[q];
+            out_scores[o] = dv.scores[i];
+            out_labels[o] = dv.labels[i];
+            out_scales[o] = dv.scales[i];
+            out_depth[o] = dv.depth[i];
+            out_ids[o] = id;
+        }
+    }
+    __syncthreads();
+    // ---- pop_invalid_tracks (kalman_tracker_base.py:77-88) -------------------------
+    const int n_now = n_live + n_create;
+    if (threadIdx.x < 32) {
+        int kept = 0, freed = 0;
+        for (int p0 = 0; p0 < n_now; p0 += 32) {
+            const int p = p0 + lane;
+            int slot = -1;
+            bool dead = false;
+            if (p < n_now) {
+                slot = order[p];
+                const long long g = sbase + slot;
+                const int lf = st.last_frame[g];
+                dead = (frame - lf >= pr.retain) || (st.tentative[g] && lf != frame);
+            }
+            const unsigned alive_b = __ballot_sync(0xffffffffu, p < n_now && !dead);
+            const unsigned dead_b = __ballot_sync(0xffffffffu, p < n_now && dead);
+            __syncwarp();
+            if (p < n_now && !dead) order[kept + __popc(alive_b & ((1u << lane) - 1u))] = slot;
+            if (p < n_now && dead)
+                free_slots[(n_free - n_create) + freed + __popc(dead_b & ((1u << lane) - 1u))] = slot;
+            kept += __popc(alive_b);
+            freed += __popc(dead_b);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            st.n_live[s] = kept;
+            st.n_free[s] = n_free - n_create + freed;
+            st.next_id[s] = id0 + n_new;
+            out_counts[s] = n_out;
+        }
+    }
+}
+
+__global__ void k4_reset(TrackState st, int T, const uint8_t *__restrict__ mask) {
+    const int s = blockIdx.x;
+    if (mask && !mask[s]) return;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) st.free_slots[(long long)s * T + i] = T - 1 - i;
+    if (threadIdx.x == 0) { st.n_live[s] = 0; st.n_free[s] = T; st.next_id[s] = 0; }
+}
+
+__global__ void __launch_bounds__(32)
+k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int32_t *__restrict__ row2col,
+               int32_t *__restrict__ col2row, int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    stlap::Scratch sc = stlap::carve(smem_raw, R + C);
+    stlap::Problem P;
+    P.cost = cost + (long long)b * R * C; P.R = R; P.C = C; P.n = R + C; P.half = half;
+    if (R > 0 && C > 0) {
+        const bool ok = stlap::solve_warp(P, sc);
+        if (!ok && lane == 0) atomicOr(status, ST_STATUS_LAP_GUARD);
+        __syncwarp();
+    }
+    for (int i = lane; i < R; i += 32) {
+        int j = (R > 0 && C > 0) ? sc.x[i] : -1;
+        row2col[(long long)b * R + i] = (j >= 0 && j < C) ? j : -1;
+    }
+    for (int j = lane; j < C; j += 32) {
+        int i = (R > 0 && C > 0) ? sc.y[j] : -1;
+        col2row[(long long)b * C + j] = (i >= 0 && i < R) ? i : -1;
+    }
+}
+
+__global__ void k4_kalman_batch(int op, int n, double *mean, double *cov, const float *z) {
+    __shared__ double ws[4][stkf::kScratchDoubles];
+    const int warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * 4 + warp;
+    if (t >= n) return;
+    if (op == 0) stkf::initiate(mean + (long long)t * 8, cov + (long long)t * 64, z + (long long)t * 4);
+    else if (op == 1) stkf::predict(mean + (long long)t * 8, cov + (long long)t * 64, ws[warp]);
+    else {
+        double zz[4];
+        for (int k = 0; k < 4; ++k) zz[k] = (double)z[(long long)t * 4 + k];
+        stkf::update(mean + (long long)t * 8, cov + (long long)t * 64, zz, ws[warp]);
+    }
+}
+
+template <typename Tp>
+void take(Tp *&ptr, unsigned char *&cursor, size_t count) {
+    ptr = reinterpret_cast<Tp *>(cursor);
+    cursor += (sizeof(Tp) * count + 255) & ~(size_t)255;
+}
+
+// lays out every device array of the handle in one allocation; with base ==
+// nullptr only measures
+size_t layout(st_handle *h, unsigned char *base) {
+    const size_t S = h->cfg.max_sequences, T = h->cfg.max_tracks, D = h->cfg.max_dets;
+    const size_t N = h->cfg.max_candidates, W = (N + 63) / 64;
+    unsigned char *c = base;
+    TrackState &st = h->st;
+    take(st.n_live, c, S); take(st.next_id, c, S); take(st.order, c, S * T); take(st.free_slots, c, S * T);
+    take(st.n_free, c, S); take(st.status, c, S);
+    take(st.id, c, S * T); take(st.hits, c, S * T); take(st.last_frame, c, S * T);
+    take(st.tentative, c, S * T); take(st.tracked, c, S * T); take(st.has_saved, c, S * T);
+    take(st.mean, c, S * T * 8); take(st.cov, c, S * T * 64);
+    take(st.saved_mean, c, S * T * 8); take(st.saved_cov, c, S * T * 64);
+    take(st.velocity, c, S * T * 2); take(st.obs_ring, c, S * T * ST_RING * 4);
+    take(st.obs_valid, c, S * T * ST_RING); take(st.num_obs, c, S * T);
+    take(st.last_obs, c, S * T * 4); take(st.miss_run, c, S * T);
+    take(st.last_box, c, S * T * 4); take(st.last_score, c, S * T); take(st.last_scale, c, S * T);
+    take(st.last_depth, c, S * T); take(st.last_label, c, S * T);
+    take(h->cand_count, c, S); take(h->cand_score, c, S * N); take(h->cand_prior, c, S * N);
+    take(h->cand_label, c, S * N); take(h->sort_box, c, S * N * 4); take(h->sort_score, c, S * N);
+    take(h->sort_prior, c, S * N); take(h->sort_label, c, S * N); take(h->max_coord, c, S);
+    take(h->nms_mask, c, S * N * W);
+    take(h->cost, c, S * T * D);
+    return (size_t)(c - base);
+}
+
+}  // namespace
+
+extern "C" int st_abi_version(void) { return ST_ABI_VERSION; }
+
+extern "C" const char *st_error_string(int code) {
+    switch (code) {
+        case ST_OK: return "ok";
+        case ST_ERR_INVALID_ARG: return "invalid argument";
+        case ST_ERR_CUDA: return "CUDA runtime error";
+        case ST_ERR_NO_DEVICE: return "no CUDA device";
+        case ST_ERR_CAPACITY: return "capacity exceeded";
+        case ST_ERR_ALLOC: return "device allocation failed";
+        default: return "unknown error";
+    }
+}
+
+extern "C" void st_default_config(st_config *cfg) {
+    if (!cfg) return;
+    cfg->max_sequences = 1; cfg->max_tracks = 256; cfg->max_dets = 256; cfg->max_candidates = 2048;
+    // constructor defaults of the reference classes (see the header)
+    cfg->obj_score_thr = 0.3f; cfg->init_track_thr = 0.7f; cfg->weight_iou_with_det_scores = 1;
+    cfg->match_iou_thr = 0.3; cfg->num_tentatives = 3; cfg->vel_consist_weight = 0.2f;
+    cfg->vel_delta_t = 3; cfg->num_frames_retain = 10;
+    cfg->baseline = 0.25f; cfg->focal_length = 640.f; cfg->score_thr = 0.01f; cfg->nms_iou_thr = 0.5f;
+}
+
+extern "C" int st_create(const st_config *cfg, st_handle **out) {
+    if (!cfg || !out) return ST_ERR_INVALID_ARG;
+    if (cfg->max_sequences < 1 || cfg->max_tracks < 1 || cfg->max_tracks > 1024 || cfg->max_dets < 1 ||
+        cfg->max_dets > 1024 || cfg->max_candidates < 1 || cfg->vel_delta_t < 0 ||
+        cfg->vel_delta_t >= ST_RING || cfg->num_tentatives < 0)
+        return ST_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ST_ERR_NO_DEVICE;
+    st_handle *h = new (std::nothrow) st_handle();
+    if (!h) return ST_ERR_ALLOC;
+    h->cfg = *cfg;
+    cudaGetDevice(&h->device);
+    h->all_bytes = layout(h, nullptr);
+    if (cudaMalloc(&h->all_mem, h->all_bytes) != cudaSuccess) { delete h; return ST_ERR_ALLOC; }
+    layout(h, static_cast<unsigned char *>(h->all_mem));
+    if (cudaMemset(h->all_mem, 0, h->all_bytes) != cudaSuccess) { cudaFree(h->all_mem); delete h; return ST_ERR_CUDA; }
+    const size_t smem = smem_bytes(cfg->max_tracks, cfg->max_dets);
+    if (cudaFuncSetAttribute(k4_track_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k5_lapjv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)stlap::scratch_bytes(cfg->max_tracks + cfg->max_dets)) != cudaSuccess) {
+        cudaFree(h->all_mem); delete h; return ST_ERR_CAPACITY;
+    }
+    k4_reset<<<cfg->max_sequences, 128>>>(h->st, cfg->max_tracks, nullptr);
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(h->all_mem); delete h; return ST_ERR_CUDA; }
+    *out = h;
+    return ST_OK;
+}
+
+extern "C" int st_destroy(st_handle *h) {
+    if (!h) return ST_ERR_INVALID_ARG;
+    cudaFree(h->all_mem);
+    delete h;
+    return ST_OK;
+}
+
+extern "C" int st_reset(st_handle *h, const uint8_t *seq_mask, void *stream) {
+    if (!h) return ST_ERR_INVALID_ARG;
+    k4_reset<<<h->cfg.max_sequences, 128, 0, (cudaStream_t)stream>>>(h->st, h->cfg.max_tracks, seq_mask);
+    return st_last_launch();
+}
+
+extern "C" int st_read_status(st_handle *h, int32_t *status_host, int S) {
+    if (!h || !status_host || S < 0 || S > h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
+    ST_CUDA_OK(cudaMemcpy(status_host, h->st.status, sizeof(int32_t) * S, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+extern "C" int st_clear_status(st_handle *h, void *stream) {
+    if (!h) return ST_ERR_INVALID_ARG;
+    ST_CUDA_OK(cudaMemsetAsync(h->st.status, 0, sizeof(int32_t) * h->cfg.max_sequences, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+extern "C" int st_track_step(st_handle *h, int S, const int32_t *frame_ids, const float *det_boxes,
+                             const float *det_scores, const int64_t *det_labels, const float *det_scales,
+                             const float *det_depth, const int32_t *det_counts, int det_cap,
+                             float *out_boxes, float *out_scores, int64_t *out_labels, float *out_scales,
+                             float *out_depth, int64_t *out_ids, int32_t *out_counts, void *stream) {
+    if (!h || S < 0 || S > h->cfg.max_sequences || !frame_ids || !det_boxes || !det_scores || !det_labels ||
+        !det_scales || !det_depth || !det_counts || det_cap < 1 || !out_boxes || !out_scores || !out_labels ||
+        !out_scales || !out_depth || !out_ids || !out_counts)
+        return ST_ERR_INVALID_ARG;
+    if (S == 0) return ST_OK;
+    Params pr;
+    pr.T = h->cfg.max_tracks; pr.D = h->cfg.max_dets;
+    pr.obj_score_thr = h->cfg.obj_score_thr; pr.init_track_thr = h->cfg.init_track_thr;
+    pr.vel_w = h->cfg.vel_consist_weight; pr.weight_iou = h->cfg.weight_iou_with_det_scores;
+    pr.num_tentatives = h->cfg.num_tentatives; pr.vel_dt = h->cfg.vel_delta_t;
+    pr.retain = h->cfg.num_frames_retain;
+    // lap.lapjv(cost_limit = 1 - match_iou_thr): Python float arithmetic on the config value
+    pr.lap_half = (1.0 - h->cfg.match_iou_thr) / 2.0;
+    const size_t smem = smem_bytes(pr.T, pr.D);
+    k4_track_step<<<S, kThreads, smem, (cudaStream_t)stream>>>(
+        h->st, pr, frame_ids, det_boxes, det_scores, det_labels, det_scales, det_depth, det_counts, det_cap,
+        h->cost, out_boxes, out_scores, out_labels, out_scales, out_depth, out_ids, out_counts);
+    return st_last_launch();
+}
+
+extern "C" int st_export_state(st_handle *h, int seq, int64_t *ids_host, double *mean_host, double *cov_host,
+                               float *velocity_host, uint8_t *flags_host, int32_t *hits_host,
+                               int32_t *last_frame_host, int64_t *num_tracks_host) {
+    if (!h || seq < 0 || seq >= h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
+    ST_CUDA_OK(cudaDeviceSynchronize());
+    const int T = h->cfg.max_tracks;
+    int n_live = 0;
+    ST_CUDA_OK(cudaMemcpy(&n_live, h->st.n_live + seq, sizeof(int), cudaMemcpyDeviceToHost));
+    if (num_tracks_host)
+        ST_CUDA_OK(cudaMemcpy(num_tracks_host, h->st.next_id + seq, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (n_live < 0 || n_live > T) return ST_ERR_CUDA;
+    int32_t *order = new int32_t[T];
+    cudaMemcpy(order, h->st.order + (size_t)seq * T, sizeof(int32_t) * T, cudaMemcpyDeviceToHost);
+    int rc = ST_OK;
+    for (int p = 0; p < n_live && rc == ST_OK; ++p) {
+        const size_t g = (size_t)seq * T + order[p];
+        uint8_t tent = 0, trk = 0;
+        cudaError_t e = cudaSuccess;
+        if (ids_host) e = cudaMemcpy(ids_host + p, h->st.id + g, sizeof(int64_t), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && mean_host) e = cudaMemcpy(mean_host + p * 8, h->st.mean + g * 8, sizeof(double) * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && cov_host) e = cudaMemcpy(cov_host + p * 64, h->st.cov + g * 64, sizeof(double) * 64, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && velocity_host) e = cudaMemcpy(velocity_host + p * 2, h->st.velocity + g * 2, sizeof(float) * 2, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && hits_host) e = cudaMemcpy(hits_host + p, h->st.hits + g, sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && last_frame_host) e = cudaMemcpy(last_frame_host + p, h->st.last_frame + g, sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && flags_host) {
+            e = cudaMemcpy(&tent, h->st.tentative + g, 1, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(&trk, h->st.tracked + g, 1, cudaMemcpyDeviceToHost);
+            flags_host[p] = (uint8_t)((tent ? 1 : 0) | (trk ? 2 : 0));
+        }
+        if (e != cudaSuccess) rc = ST_ERR_CUDA;
+    }
+    delete[] order;
+    return rc == ST_OK ? n_live : rc;
+}
+
+extern "C" int st_kalman_batch(int op, int n, double *mean, double *cov, const float *z, void *stream) {
+    if (op < 0 || op > 2 || n < 0 || !mean || !cov || (op != 1 && !z)) return ST_ERR_INVALID_ARG;
+    if (n == 0) return ST_OK;
+    k4_kalman_batch<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(op, n, mean, cov, z);
+    return st_last_launch();
+}
+
+extern "C" int st_lapjv_batch(st_handle *h, int B, int R, int C, const float *cost, double cost_limit,
+                              int32_t *row2col, int32_t *col2row, void *stream) {
+    if (!h || B < 0 || R < 0 || C < 0 || R + C > h->cfg.max_tracks + h->cfg.max_dets || !row2col || !col2row ||
+        (R > 0 && C > 0 && !cost))
+        return ST_ERR_INVALID_ARG;
+    if (B == 0 || R + C == 0) return ST_OK;
+    k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C), (cudaStream_t)stream>>>(
+        R, C, cost, cost_limit / 2.0, row2col, col2row, h->st.status);
+    return st_last_launch();
+}

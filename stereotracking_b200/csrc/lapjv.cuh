@@ -1,0 +1,348 @@
+// Warp-cooperative dense Jonker-Volgenant assignment on the "extended" matrix
+// that lap.lapjv(extend_cost=True, cost_limit=L) builds, without materialising
+// it: ext[i][j] = cost[i][j] (i<R, j<C), 0 (i>=R, j>=C), L/2 otherwise.
+//
+// Replaces lap.lapjv at mmtrack/models/trackers/ocsort_tracker_disparity.py
+// :260-261 and :312-313.  The phase order and every scan order of the dense JV
+// solver are kept (column reduction with reverse sweep, reduction transfer, two
+// augmenting-row-reduction passes, shortest-path augmentation with
+// READY/SCAN/TODO lists) so that exact cost ties resolve as in the reference;
+// what is parallel is only what is order-independent: minima with index
+// tie-breaks, relaxations of disjoint columns, and detection of the columns a
+// sequential sweep would move (the moves themselves are replayed in order).
+#pragma once
+#include "st_common.cuh"
+
+namespace stlap {
+
+constexpr double kBig = 1.0e300;
+
+struct Scratch {          // all arrays have n = R + C entries, in shared memory
+    double *v;            // column potentials
+    double *d;            // shortest-path distances
+    int *cols, *pred, *x, *y, *free_rows;
+    unsigned *mask_a, *mask_b;   // (n+31)/32 words each
+    unsigned char *unique;
+};
+
+__host__ __device__ inline size_t scratch_bytes(int n) {
+    size_t words = (size_t)(n + 31) / 32;
+    size_t b = sizeof(double) * 2 * n + sizeof(int) * 5 * n + sizeof(unsigned) * 2 * words + n;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ inline Scratch carve(unsigned char *p, int n) {
+    Scratch s;
+    size_t words = (size_t)(n + 31) / 32;
+    s.v = reinterpret_cast<double *>(p); p += sizeof(double) * n;
+    s.d = reinterpret_cast<double *>(p); p += sizeof(double) * n;
+    s.cols = reinterpret_cast<int *>(p); p += sizeof(int) * n;
+    s.pred = reinterpret_cast<int *>(p); p += sizeof(int) * n;
+    s.x = reinterpret_cast<int *>(p); p += sizeof(int) * n;
+    s.y = reinterpret_cast<int *>(p); p += sizeof(int) * n;
+    s.free_rows = reinterpret_cast<int *>(p); p += sizeof(int) * n;
+    s.mask_a = reinterpret_cast<unsigned *>(p); p += sizeof(unsigned) * words;
+    s.mask_b = reinterpret_cast<unsigned *>(p); p += sizeof(unsigned) * words;
+    s.unique = p;
+    return s;
+}
+
+struct Problem {
+    const float *cost;    // R x C row-major (float32 as the reference's dists)
+    int R, C, n;
+    double half;          // cost_limit / 2
+    __device__ __forceinline__ double at(int i, int j) const {
+        if (i < R) return j < C ? (double)cost[(long long)i * C + j] : half;
+        return j < C ? half : 0.0;
+    }
+};
+
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_min_i(int v) {
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// (value, index) pairs ordered lexicographically; index < 0 = "none"
+__device__ __forceinline__ bool pair_less(double va, int ia, double vb, int ib) {
+    if (ib < 0) return ia >= 0;
+    if (ia < 0) return false;
+    return va < vb || (va == vb && ia < ib);
+}
+
+// Solve; on return s.x[i] (row->col) and s.y[j] (col->row) hold the extended
+// assignment.  Must be called by all 32 lanes of one warp.  Returns false when
+// an iteration guard fired (non-finite costs).
+__device__ bool solve_warp(const Problem &P, Scratch &s) {
+    const int lane = threadIdx.x & 31;
+    const int n = P.n;
+    bool ok = true;
+
+    // ---- column reduction -----------------------------------------------------
+    for (int i = lane; i < n; i += 32) { s.x[i] = -1; s.unique[i] = 1; }
+    for (int j = lane; j < n; j += 32) {
+        double best = kBig;
+        int arg = 0;
+        if (j < P.C) {
+            for (int i = 0; i < P.R; ++i) {
+                double c = (double)P.cost[(long long)i * P.C + j];
+                if (c < best) { best = c; arg = i; }
+            }
+            if (P.n > P.R && P.half < best) { best = P.half; arg = P.R; }
+        } else {
+            if (P.R > 0) { best = P.half; arg = 0; }
+            if (P.n > P.R && 0.0 < best) { best = 0.0; arg = P.R; }
+        }
+        s.v[j] = best;
+        s.y[j] = arg;
+    }
+    __syncwarp();
+    // reverse sweep: the highest column that elected a row keeps it
+    for (int j = lane; j < n; j += 32) atomicMax(&s.x[s.y[j]], j);
+    __syncwarp();
+    for (int j = lane; j < n; j += 32) {
+        int i = s.y[j];
+        if (s.x[i] != j) { s.unique[i] = 0; s.y[j] = -1; }
+    }
+    __syncwarp();
+
+    // ---- reduction transfer (row order matters: v[] feeds later rows) ----------
+    int nfree = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int ii = i0 + lane;
+        const int xi_l = ii < n ? s.x[ii] : 0;
+        const bool uq_l = ii < n ? (s.unique[ii] != 0) : false;
+        const unsigned freeb = __ballot_sync(0xffffffffu, ii < n && xi_l < 0);
+        const unsigned workb = __ballot_sync(0xffffffffu, ii < n && xi_l >= 0 && uq_l);
+        unsigned todo = freeb | workb;
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int i = i0 + b;
+            if ((freeb >> b) & 1u) {
+                if (lane == 0) s.free_rows[nfree] = i;
+                ++nfree;
+            } else {
+                const int j1 = __shfl_sync(0xffffffffu, xi_l, b);
+                double m = kBig;
+                for (int j2 = lane; j2 < n; j2 += 32)
+                    if (j2 != j1) m = fmin(m, P.at(i, j2) - s.v[j2]);
+                m = warp_min(m);
+                if (lane == 0) s.v[j1] -= m;
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- augmenting row reduction, two passes --------------------------------------
+    for (int pass = 0; pass < 2 && nfree > 0; ++pass) {
+        int cur = 0, nxt = 0;
+        unsigned long long visits = 0, guard = 0;
+        const unsigned long long guard_max = 64ull * (unsigned long long)n * (unsigned long long)n + 1024ull;
+        while (cur < nfree) {
+            if (++guard > guard_max) { ok = false; break; }
+            ++visits;
+            const int fr = s.free_rows[cur++];
+            // two smallest reduced costs, lowest index first on ties
+            double u1 = kBig, u2 = kBig;
+            int j1 = -1, j2 = -1;
+            for (int j = lane; j < n; j += 32) {
+                const double r = P.at(fr, j) - s.v[j];
+                if (pair_less(r, j, u1, j1)) { u2 = u1; j2 = j1; u1 = r; j1 = j; }
+                else if (pair_less(r, j, u2, j2)) { u2 = r; j2 = j; }
+            }
+            for (int o = 16; o; o >>= 1) {
+                const double ou1 = __shfl_xor_sync(0xffffffffu, u1, o), ou2 = __shfl_xor_sync(0xffffffffu, u2, o);
+                const int oj1 = __shfl_xor_sync(0xffffffffu, j1, o), oj2 = __shfl_xor_sync(0xffffffffu, j2, o);
+                if (pair_less(ou1, oj1, u1, j1)) {
+                    // other's best wins; second = min(my best, other's second)
+                    if (pair_less(u1, j1, ou2, oj2)) { u2 = u1; j2 = j1; } else { u2 = ou2; j2 = oj2; }
+                    u1 = ou1; j1 = oj1;
+                } else {
+                    if (pair_less(ou1, oj1, u2, j2)) { u2 = ou1; j2 = oj1; }
+                }
+            }
+            if (j2 < 0) u2 = kBig;
+            int i0 = s.y[j1];
+            const double vj1 = s.v[j1];
+            const double v1_new = vj1 - (u2 - u1);
+            const bool lowers = v1_new < vj1;
+            __syncwarp();
+            if (visits < (unsigned long long)cur * (unsigned long long)n) {
+                if (lowers) { if (lane == 0) s.v[j1] = v1_new; }
+                else if (i0 >= 0 && j2 >= 0) { j1 = j2; i0 = s.y[j2]; }
+                if (i0 >= 0) {
+                    if (lowers) { --cur; if (lane == 0) s.free_rows[cur] = i0; }
+                    else { if (lane == 0) s.free_rows[nxt] = i0; ++nxt; }
+                }
+            } else if (i0 >= 0) {
+                if (lane == 0) s.free_rows[nxt] = i0;
+                ++nxt;
+            }
+            if (lane == 0) { s.x[fr] = j1; s.y[j1] = fr; }
+            __syncwarp();
+        }
+        nfree = nxt;
+        if (!ok) break;
+    }
+
+    // ---- augmentation ----------------------------------------------------------
+    const int words = (n + 31) >> 5;
+    for (int f = 0; f < nfree && ok; ++f) {
+        const int start = s.free_rows[f];
+        for (int j = lane; j < n; j += 32) {
+            s.cols[j] = j;
+            s.pred[j] = start;
+            s.d[j] = P.at(start, j) - s.v[j];
+        }
+        __syncwarp();
+        int lo = 0, hi = 0, n_ready = 0, final_j = -1;
+        int guard = 0;
+        while (final_j == -1) {
+            if (++guard > 2 * n + 8) { ok = false; break; }
+            if (lo == hi) {
+                n_ready = lo;
+                // -- collect the columns of minimal d into SCAN, replaying the
+                //    sequential sweep's swaps (triggers found in parallel)
+                double run = s.d[s.cols[lo]];
+                for (int w = lane; w < words; w += 32) { s.mask_a[w] = 0u; s.mask_b[w] = 0u; }
+                __syncwarp();
+                for (int k0 = lo + 1; k0 < n; k0 += 32) {
+                    const int k = k0 + lane;
+                    const double dv = k < n ? s.d[s.cols[k]] : kBig;
+                    double inc = dv;                       // inclusive prefix min
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc = fmin(inc, t);
+                    }
+                    double exc = __shfl_up_sync(0xffffffffu, inc, 1);
+                    exc = lane == 0 ? run : fmin(exc, run);
+                    const unsigned strict = __ballot_sync(0xffffffffu, k < n && dv < exc);
+                    const unsigned equal = __ballot_sync(0xffffffffu, k < n && dv == exc);
+                    if (lane == 0) {
+                        // bits are relative to k0; store at bit offset k0 (may straddle words)
+                        const int w = k0 >> 5, sh = k0 & 31;
+                        s.mask_a[w] |= strict << sh;
+                        s.mask_b[w] |= equal << sh;
+                        if (sh && w + 1 < words) {
+                            s.mask_a[w + 1] |= strict >> (32 - sh);
+                            s.mask_b[w + 1] |= equal >> (32 - sh);
+                        }
+                    }
+                    run = fmin(run, __shfl_sync(0xffffffffu, inc, 31));
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    int h2 = lo + 1;
+                    for (int w = 0; w < words; ++w) {
+                        unsigned any = s.mask_a[w] | s.mask_b[w];
+                        while (any) {
+                            const int b = __ffs(any) - 1;
+                            any &= any - 1;
+                            const int k = (w << 5) + b;
+                            if ((s.mask_a[w] >> b) & 1u) h2 = lo;
+                            const int j = s.cols[k];
+                            s.cols[k] = s.cols[h2];
+                            s.cols[h2++] = j;
+                        }
+                    }
+                    s.mask_a[0] = (unsigned)h2;
+                }
+                __syncwarp();
+                hi = (int)s.mask_a[0];
+                __syncwarp();
+                // last unassigned column in SCAN order wins
+                int cand = -1;
+                for (int k = lo + lane; k < hi; k += 32)
+                    if (s.y[s.cols[k]] < 0) cand = k;
+                cand = warp_max_i(cand);
+                if (cand >= 0) final_j = s.cols[cand];
+            }
+            if (final_j == -1) {
+                // -- relax TODO columns from every SCAN column
+                while (lo != hi) {
+                    const int js = s.cols[lo++];
+                    const int i = s.y[js];
+                    const double mind = s.d[js];
+                    const double h = P.at(i, js) - s.v[js] - mind;
+                    for (int w = lane; w < words; w += 32) s.mask_a[w] = 0u;
+                    __syncwarp();
+                    int first_free = 0x7fffffff;
+                    for (int k0 = hi; k0 < n; k0 += 32) {
+                        const int k = k0 + lane;
+                        bool hit = false, freehit = false;
+                        if (k < n) {
+                            const int j = s.cols[k];
+                            const double r = P.at(i, j) - s.v[j] - h;
+                            if (r < s.d[j]) {
+                                s.d[j] = r;
+                                s.pred[j] = i;
+                                if (r == mind) { hit = true; freehit = s.y[j] < 0; }
+                            }
+                        }
+                        const unsigned hb = __ballot_sync(0xffffffffu, hit);
+                        const unsigned fb = __ballot_sync(0xffffffffu, freehit);
+                        if (fb && first_free == 0x7fffffff) first_free = k0 + __ffs(fb) - 1;
+                        if (lane == 0 && hb) {
+                            const int rel = k0 - hi;          // bit index relative to hi
+                            const int w = rel >> 5, sh = rel & 31;
+                            s.mask_a[w] |= hb << sh;
+                            if (sh && w + 1 < words) s.mask_a[w + 1] |= hb >> (32 - sh);
+                        }
+                    }
+                    __syncwarp();
+                    if (first_free != 0x7fffffff) { final_j = s.cols[first_free]; break; }
+                    if (lane == 0) {
+                        int h2 = hi;
+                        const int span = n - hi;
+                        for (int w = 0; w * 32 < span; ++w) {
+                            unsigned any = s.mask_a[w];
+                            while (any) {
+                                const int b = __ffs(any) - 1;
+                                any &= any - 1;
+                                const int k = hi + (w << 5) + b;
+                                const int j = s.cols[k];
+                                s.cols[k] = s.cols[h2];
+                                s.cols[h2++] = j;
+                            }
+                        }
+                        s.mask_b[0] = (unsigned)h2;
+                    }
+                    __syncwarp();
+                    hi = (int)s.mask_b[0];
+                    __syncwarp();
+                }
+                if (final_j != -1) lo = n_ready;      // caller's lo is unchanged by an early return
+            }
+        }
+        if (!ok) break;
+        {
+            const double mind = s.d[s.cols[lo]];
+            for (int k = lane; k < n_ready; k += 32) {
+                const int j = s.cols[k];
+                s.v[j] += s.d[j] - mind;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int i = -1, j = final_j, steps = 0;
+            while (i != start && steps++ <= n) {
+                i = s.pred[j];
+                s.y[j] = i;
+                const int t = j; j = s.x[i]; s.x[i] = t;
+            }
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+}  // namespace stlap

@@ -1,0 +1,266 @@
+"""Lockstep engine: S independent sequences advance one frame per call.
+
+Host side of the C ABI (include/stereotrack_b200.h).  PyTorch is used for
+device memory and streams only; every arithmetic step of the path runs in the
+CUDA library.  The per-frame pipeline mirrors OCSORT_Disparity.predict
+(mmtrack/models/mot/ocsort_disparity.py:79-109) after the detector backbone:
+
+  raw disparity --K1--> depth map
+  head maps     --K2--> detections (decode, threshold, NMS)
+  detections    --K3--> per-box depth, scale, inflated boxes      (:82-83)
+  inflated dets --K4/K5--> tracker.track                          (:88-93)
+  tracks        --scale_boxes(1/scale)--> deflated boxes          (:96-97)
+  deflated      --K3--> output depth                              (:100-104)
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+
+# the shipped tracker config: configs/stereo_tracking/ocsort/
+# yolox_s_mmyolo_mot_airdrone_disp.py:48-58 (ctor defaults differ, see _lib.StConfig)
+AIRDRONE_TRACKER = dict(obj_score_thr=0.3, init_track_thr=0.7, weight_iou_with_det_scores=False,
+                        match_iou_thr=0.1, num_tentatives=3, vel_consist_weight=0.2, vel_delta_t=3,
+                        num_frames_retain=30)
+
+
+@dataclass
+class EngineConfig:
+    n_seq: int = 1
+    max_tracks: int = 256
+    max_dets: int = 256
+    max_candidates: int = 2048
+    tracker: dict = field(default_factory=lambda: dict(AIRDRONE_TRACKER))
+    baseline: float = 0.25
+    focal_length: float = 640.0
+    score_thr: float = 0.01
+    nms_iou_thr: float = 0.5
+    strides: tuple = (8, 16, 32)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class StereoTrackEngine:
+    def __init__(self, cfg: EngineConfig = None, device='cuda:0', **kw):
+        cfg = cfg or EngineConfig(**kw)
+        if not torch.cuda.is_available():
+            raise _lib.StereoTrackError('StereoTrackEngine needs a CUDA device (no CPU fallback)')
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.lib = _lib.lib()
+        sc = _lib.StConfig()
+        self.lib.st_default_config(C.byref(sc))
+        sc.max_sequences, sc.max_tracks, sc.max_dets = cfg.n_seq, cfg.max_tracks, cfg.max_dets
+        sc.max_candidates = cfg.max_candidates
+        t = cfg.tracker
+        # constructor defaults of OCSORTTracker_Disparity when a key is absent
+        sc.obj_score_thr = t.get('obj_score_thr', 0.3)
+        sc.init_track_thr = t.get('init_track_thr', 0.7)
+        sc.weight_iou_with_det_scores = int(bool(t.get('weight_iou_with_det_scores', True)))
+        sc.match_iou_thr = float(t.get('match_iou_thr', 0.3))
+        sc.num_tentatives = t.get('num_tentatives', 3)
+        sc.vel_consist_weight = t.get('vel_consist_weight', 0.2)
+        sc.vel_delta_t = t.get('vel_delta_t', 3)
+        sc.num_frames_retain = t.get('num_frames_retain', 10)
+        if t.get('cmc') is not None:
+            raise NotImplementedError('camera-motion compensation (cmc) is a "next" row, see DESIGN.md')
+        sc.baseline, sc.focal_length = cfg.baseline, cfg.focal_length
+        sc.score_thr, sc.nms_iou_thr = cfg.score_thr, cfg.nms_iou_thr
+        self._sc = sc
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.st_create(C.byref(sc), C.byref(self._h)), 'st_create')
+        S, D = cfg.n_seq, cfg.max_dets
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        # detection buffers
+        self.det_boxes = torch.zeros(S, D, 4, **f32)
+        self.det_scores = torch.zeros(S, D, **f32)
+        self.det_labels = torch.zeros(S, D, dtype=torch.int64, device=dev)
+        self.det_prior = torch.zeros(S, D, dtype=torch.int32, device=dev)
+        self.det_keep = torch.zeros(S, D, dtype=torch.int32, device=dev)
+        self.det_counts = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.det_depth = torch.zeros(S, D, **f32)
+        self.det_scales = torch.zeros(S, D, **f32)
+        self.det_inflated = torch.zeros(S, D, 4, **f32)
+        # track outputs
+        self.trk_boxes = torch.zeros(S, D, 4, **f32)       # inflated (tracker space)
+        self.out_boxes = torch.zeros(S, D, 4, **f32)       # deflated (image space)
+        self.out_scores = torch.zeros(S, D, **f32)
+        self.out_labels = torch.zeros(S, D, dtype=torch.int64, device=dev)
+        self.out_scales = torch.zeros(S, D, **f32)
+        self.trk_depth = torch.zeros(S, D, **f32)          # depth carried through the tracker
+        self.out_depth = torch.zeros(S, D, **f32)          # recomputed on deflated boxes
+        self.out_scale2 = torch.zeros(S, D, **f32)
+        self.out_ids = torch.zeros(S, D, dtype=torch.int64, device=dev)
+        self.out_counts = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.frame_ids = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.depth_map = None
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self.lib.st_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers -------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, t, dtype):
+        assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype, t.is_contiguous())
+        return t
+
+    # ---- K1 ----------------------------------------------------------------------
+    def disp2depth(self, raw, resized_hw=None, size_divisor=32, want_disp3=False, want_mask=False, out=None):
+        """raw [S,H,W] uint16 -> depth [S,Hp,Wp] (+disp3 [S,3,Hp,Wp], mask [S,Hp,Wp])."""
+        self._dev(raw, torch.uint16)
+        S, H, W = raw.shape
+        Hr, Wr = resized_hw or (H, W)
+        Hp, Wp = -(-Hr // size_divisor) * size_divisor, -(-Wr // size_divisor) * size_divisor
+        depth = out if out is not None else torch.empty(S, Hp, Wp, dtype=torch.float32, device=raw.device)
+        disp3 = torch.empty(S, 3, Hp, Wp, dtype=torch.float32, device=raw.device) if want_disp3 else None
+        mask = torch.empty(S, Hp, Wp, dtype=torch.uint8, device=raw.device) if want_mask else None
+        _lib.check(self.lib.st_disp2depth(_ptr(raw), S, H, W, Hr, Wr, Hp, Wp, _ptr(depth), _ptr(disp3),
+                                          _ptr(mask), self.cfg.baseline, self.cfg.focal_length,
+                                          self._stream()), 'st_disp2depth')
+        return depth, disp3, mask
+
+    # ---- K2 ----------------------------------------------------------------------
+    def decode_nms(self, cls_l, bbox_l, obj_l, ori_hw, scale_factor=(1.0, 1.0)):
+        """Per-level head maps [S,C,h,w] -> fills det_* buffers; returns views."""
+        L = len(cls_l)
+        S = cls_l[0].shape[0]
+        nc = cls_l[0].shape[1]
+        for t in list(cls_l) + list(bbox_l) + list(obj_l):
+            self._dev(t, torch.float32)
+        arr = lambda ts: (C.c_void_p * L)(*[t.data_ptr() for t in ts])
+        ints = lambda vs: (C.c_int32 * L)(*vs)
+        _lib.check(self.lib.st_decode_nms(
+            self._h, arr(cls_l), arr(bbox_l), arr(obj_l), L, ints([t.shape[2] for t in cls_l]),
+            ints([t.shape[3] for t in cls_l]), ints(self.cfg.strides[:L]), S, nc,
+            float(scale_factor[0]), float(scale_factor[1]), int(ori_hw[0]), int(ori_hw[1]),
+            self.cfg.max_dets, _ptr(self.det_boxes), _ptr(self.det_scores), _ptr(self.det_labels),
+            _ptr(self.det_prior), _ptr(self.det_keep), _ptr(self.det_counts), self._stream()),
+            'st_decode_nms')
+        return self.det_boxes, self.det_scores, self.det_labels, self.det_counts
+
+    # ---- K3 ----------------------------------------------------------------------
+    def box_depth(self, depth, boxes, counts, d_out=None, scale_out=None, inflated_out=None):
+        S, Hp, Wp = depth.shape
+        cap = boxes.shape[1]
+        dev = depth.device
+        d_out = d_out if d_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
+        scale_out = scale_out if scale_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
+        _lib.check(self.lib.st_box_depth(_ptr(self._dev(depth, torch.float32)), S, Hp, Wp,
+                                         _ptr(self._dev(boxes, torch.float32)),
+                                         _ptr(self._dev(counts, torch.int32)), cap, _ptr(d_out),
+                                         _ptr(scale_out), _ptr(inflated_out), self._stream()), 'st_box_depth')
+        return d_out, scale_out, inflated_out
+
+    def scale_boxes(self, boxes, scales, counts, invert, out=None):
+        S, cap = scales.shape
+        out = out if out is not None else torch.empty_like(boxes)
+        _lib.check(self.lib.st_scale_boxes(_ptr(boxes), _ptr(scales), _ptr(counts), S, cap, int(invert),
+                                           _ptr(out), self._stream()), 'st_scale_boxes')
+        return out
+
+    # ---- K4/K5 -------------------------------------------------------------------
+    def track_step(self, frame_ids, boxes, scores, labels, scales, depth, counts):
+        """tracker.track for S sequences; inputs padded [S,cap,...]; fills trk_*/out_* buffers."""
+        S, cap = scores.shape
+        assert cap == self.cfg.max_dets, 'detection buffers must be padded to max_dets rows'
+        _lib.check(self.lib.st_track_step(
+            self._h, S, _ptr(self._dev(frame_ids, torch.int32)), _ptr(self._dev(boxes, torch.float32)),
+            _ptr(self._dev(scores, torch.float32)), _ptr(self._dev(labels, torch.int64)),
+            _ptr(self._dev(scales, torch.float32)), _ptr(self._dev(depth, torch.float32)),
+            _ptr(self._dev(counts, torch.int32)), cap, _ptr(self.trk_boxes), _ptr(self.out_scores),
+            _ptr(self.out_labels), _ptr(self.out_scales), _ptr(self.trk_depth), _ptr(self.out_ids),
+            _ptr(self.out_counts), self._stream()), 'st_track_step')
+        return dict(bboxes=self.trk_boxes, scores=self.out_scores, labels=self.out_labels,
+                    scales=self.out_scales, depth=self.trk_depth, instances_id=self.out_ids,
+                    counts=self.out_counts)
+
+    # ---- whole frame ---------------------------------------------------------------
+    def step_from_dets(self, depth_map, frame_ids=None):
+        """ocsort_disparity.py:82-109 given det_* buffers (detector output) and a depth map."""
+        fid = self.frame_ids if frame_ids is None else frame_ids
+        self.box_depth(depth_map, self.det_boxes, self.det_counts, self.det_depth, self.det_scales,
+                       self.det_inflated)
+        self.track_step(fid, self.det_inflated, self.det_scores, self.det_labels, self.det_scales,
+                        self.det_depth, self.det_counts)
+        self.scale_boxes(self.trk_boxes, self.out_scales, self.out_counts, True, self.out_boxes)
+        self.box_depth(depth_map, self.out_boxes, self.out_counts, self.out_depth, self.out_scale2, None)
+
+    def step(self, raw, cls_l, bbox_l, obj_l, frame_ids=None, resized_hw=None):
+        """One lockstep frame from raw inputs.  Results are left in the out_* buffers."""
+        S, H, W = raw.shape
+        if self.depth_map is None or self.depth_map.shape[0] != S:
+            Hr, Wr = resized_hw or (H, W)
+            Hp, Wp = -(-Hr // 32) * 32, -(-Wr // 32) * 32
+            self.depth_map = torch.empty(S, Hp, Wp, dtype=torch.float32, device=self.device)
+        self.disp2depth(raw, resized_hw, out=self.depth_map)
+        self.decode_nms(cls_l, bbox_l, obj_l, (H, W))
+        self.step_from_dets(self.depth_map, frame_ids)
+
+    def results(self):
+        """Host copies of the current outputs, one dict per sequence."""
+        n = self.out_counts.cpu().tolist()
+        pack = [t.cpu() for t in (self.out_boxes, self.out_ids, self.out_scores, self.out_labels,
+                                  self.out_scales, self.out_depth)]
+        out = []
+        for s, m in enumerate(n):
+            out.append(dict(bboxes=pack[0][s, :m].numpy(), instances_id=pack[1][s, :m].numpy(),
+                            scores=pack[2][s, :m].numpy(), labels=pack[3][s, :m].numpy(),
+                            scales=pack[4][s, :m].numpy(), depth=pack[5][s, :m].numpy()))
+        return out
+
+    # ---- state ----------------------------------------------------------------------
+    def reset(self, seq_mask=None):
+        m = None
+        if seq_mask is not None:
+            m = torch.as_tensor(seq_mask, dtype=torch.uint8, device=self.device).contiguous()
+        _lib.check(self.lib.st_reset(self._h, _ptr(m), self._stream()), 'st_reset')
+        if m is not None:
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def status(self):
+        import numpy as np
+        st = np.zeros(self.cfg.n_seq, np.int32)
+        _lib.check(self.lib.st_read_status(self._h, st.ctypes.data_as(C.c_void_p), self.cfg.n_seq))
+        return st
+
+    def export_state(self, seq):
+        import numpy as np
+        T = self.cfg.max_tracks
+        ids = np.zeros(T, np.int64); mean = np.zeros((T, 8)); cov = np.zeros((T, 64))
+        vel = np.zeros((T, 2), np.float32); flags = np.zeros(T, np.uint8)
+        hits = np.zeros(T, np.int32); last = np.zeros(T, np.int32); nt = np.zeros(1, np.int64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        n = _lib.check(self.lib.st_export_state(self._h, seq, p(ids), p(mean), p(cov), p(vel), p(flags),
+                                                p(hits), p(last), p(nt)), 'st_export_state')
+        return dict(ids=ids[:n], mean=mean[:n], cov=cov[:n].reshape(n, 8, 8), velocity=vel[:n],
+                    tentative=(flags[:n] & 1).astype(bool), tracked=(flags[:n] & 2).astype(bool),
+                    hits=hits[:n], last_frame=last[:n], num_tracks=int(nt[0]))
+
+    # ---- exposed primitives for parity tests -----------------------------------------
+    def kalman_batch(self, op, mean, cov, z=None):
+        n = mean.shape[0]
+        _lib.check(self.lib.st_kalman_batch(op, n, _ptr(mean), _ptr(cov), _ptr(z), self._stream()))
+
+    def lapjv_batch(self, cost, cost_limit):
+        B, R, Cc = cost.shape
+        x = torch.empty(B, R, dtype=torch.int32, device=cost.device)
+        y = torch.empty(B, Cc, dtype=torch.int32, device=cost.device)
+        _lib.check(self.lib.st_lapjv_batch(self._h, B, R, Cc, _ptr(self._dev(cost, torch.float32)),
+                                           float(cost_limit), _ptr(x), _ptr(y), self._stream()))
+        return x, y

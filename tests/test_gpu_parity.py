@@ -1,0 +1,294 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the
+fixtures produced by the unmodified reference.  Needs a GPU.
+
+Tolerances: indices, ids, counts, flags: bit-exact.  float32 outputs that only
+pass through +,-,*,/ (boxes, scales, inflated boxes): bit-exact.  Values with a
+float64 -> float32 rounding (scores, depths) or float64 state (Kalman): the
+tolerance BASELINE.json states, 1e-5 relative (asserted much tighter here).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def mods():
+    from oracle import boxdepth, disparity, head, kalman
+    from oracle.lapjv import lapjv
+    from oracle.model import StereoTrackOracle
+    from stereotracking_b200.engine import EngineConfig, StereoTrackEngine
+    from stereotracking_b200.synthetic import CONFIGS, SceneConfig, SyntheticStereo
+    import types
+    return types.SimpleNamespace(**locals())
+
+
+def cuda(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+# ---------------------------------------------------------------- K1 ------------
+@pytest.mark.parametrize('shape,scale', [((2, 96, 128), None), ((1, 720, 1280), None),
+                                         ((2, 61, 83), None), ((2, 120, 200), (90, 150)),
+                                         ((1, 97, 131), (160, 240))])
+def test_k1_disp2depth_bit_exact(mods, shape, scale):
+    rng = np.random.default_rng(1)
+    raw = rng.integers(0, 4000, shape).astype(np.uint16)
+    raw[rng.random(shape) < 0.2] = 65535
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=shape[0]))
+    rhw = mods.disparity.rescale_size(shape[1], shape[2], scale) if scale else None
+    depth, disp3, mask = eng.disp2depth(cuda(raw), resized_hw=rhw, want_disp3=True, want_mask=True)
+    for s in range(shape[0]):
+        ref = mods.disparity.preprocess(raw[s], img_scale=scale)
+        np.testing.assert_array_equal(depth[s].cpu().numpy(), ref['depth'])
+        np.testing.assert_array_equal(mask[s].cpu().numpy(), ref['mask'])
+        for c in range(3):
+            np.testing.assert_array_equal(disp3[s, c].cpu().numpy(), ref['disp'])
+    only_depth, none3, nonem = eng.disp2depth(cuda(raw), resized_hw=rhw)
+    assert none3 is None and nonem is None
+    assert torch.equal(only_depth, depth)
+
+
+# ---------------------------------------------------------------- K2 ------------
+def _head_case(mods, cfg_name, S, seed, frames=2):
+    cfg = mods.CONFIGS[cfg_name]
+    gen = mods.SyntheticStereo(cfg, S, frames, seed=seed)
+    return cfg, gen.frames(0, frames)
+
+
+@pytest.mark.parametrize('cfg_name,S,seed', [('C1', 3, 5), ('C4', 2, 6)])
+def test_k2_decode_nms_matches_oracle(mods, cfg_name, S, seed):
+    cfg, fr = _head_case(mods, cfg_name, S, seed)
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S, max_dets=512, max_candidates=4096))
+    for f in range(fr['raw'].shape[0]):
+        cls_l = [c[f].cuda().contiguous() for c in fr['cls']]
+        box_l = [c[f].cuda().contiguous() for c in fr['bbox']]
+        obj_l = [c[f].cuda().contiguous() for c in fr['obj']]
+        eng.decode_nms(cls_l, box_l, obj_l, (cfg.height, cfg.width))
+        counts = eng.det_counts.cpu().numpy()
+        assert eng.status().max() == 0
+        for s in range(S):
+            ref = mods.head.postprocess([c[f, s].numpy() for c in fr['cls']],
+                                        [c[f, s].numpy() for c in fr['bbox']],
+                                        [c[f, s].numpy() for c in fr['obj']], (cfg.height, cfg.width))
+            n = int(counts[s])
+            assert n == len(ref['keep']) and n > 0
+            np.testing.assert_array_equal(eng.det_keep[s, :n].cpu().numpy(), ref['keep'])
+            np.testing.assert_array_equal(eng.det_prior[s, :n].cpu().numpy(), ref['prior_idx'])
+            np.testing.assert_array_equal(eng.det_labels[s, :n].cpu().numpy(), ref['labels'])
+            np.testing.assert_allclose(eng.det_scores[s, :n].cpu().numpy(), ref['scores'], rtol=2e-7, atol=0)
+            np.testing.assert_allclose(eng.det_boxes[s, :n].cpu().numpy(), ref['bboxes'], rtol=1e-6, atol=1e-5)
+
+
+def test_k2_ties_multiclass_and_empty(mods):
+    rng = np.random.default_rng(3)
+    S, nc = 2, 3
+    lv = [(8, 12), (4, 6), (2, 3)]
+    cls = [rng.normal(0, 2, (S, nc, h, w)).astype(np.float32) for h, w in lv]
+    obj = [rng.normal(0, 2, (S, 1, h, w)).astype(np.float32) for h, w in lv]
+    box = [rng.normal(0, 0.7, (S, 4, h, w)).astype(np.float32) for h, w in lv]
+    # exact score ties: duplicate a few priors' logits and boxes
+    cls[0][0, :, 0, 1] = cls[0][0, :, 0, 0]; obj[0][0, :, 0, 1] = obj[0][0, :, 0, 0]
+    cls[0][0, :, 3, 3] = cls[0][0, :, 0, 0]; obj[0][0, :, 3, 3] = obj[0][0, :, 0, 0]
+    obj[0][1] = -30.0; obj[1][1] = -30.0; obj[2][1] = -30.0        # sequence 1: nothing passes
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S, max_dets=256, max_candidates=512))
+    eng.decode_nms([cuda(c) for c in cls], [cuda(c) for c in box], [cuda(c) for c in obj], (64, 96))
+    counts = eng.det_counts.cpu().numpy()
+    assert counts[1] == 0
+    ref = mods.head.postprocess([c[0] for c in cls], [c[0] for c in box], [c[0] for c in obj], (64, 96))
+    n = int(counts[0])
+    assert n == len(ref['keep'])
+    np.testing.assert_array_equal(eng.det_keep[0, :n].cpu().numpy(), ref['keep'])
+    np.testing.assert_array_equal(eng.det_prior[0, :n].cpu().numpy(), ref['prior_idx'])
+    np.testing.assert_array_equal(eng.det_labels[0, :n].cpu().numpy(), ref['labels'])
+    assert len(set(ref['labels'].tolist())) > 1
+
+
+def test_k2_candidate_overflow_is_flagged(mods):
+    S = 1
+    lv = [(8, 8), (4, 4), (2, 2)]
+    cls = [np.full((S, 1, h, w), 4.0, np.float32) for h, w in lv]
+    obj = [np.full((S, 1, h, w), 4.0, np.float32) for h, w in lv]
+    box = [np.zeros((S, 4, h, w), np.float32) for h, w in lv]
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S, max_dets=64, max_candidates=32))
+    eng.decode_nms([cuda(c) for c in cls], [cuda(c) for c in box], [cuda(c) for c in obj], (64, 64))
+    assert eng.status()[0] & 1
+
+
+# ---------------------------------------------------------------- K3 ------------
+def test_k3_box_depth_matches_reference_fixture(mods):
+    g = np.load(os.path.join(GOLDEN, 'ref_boxdepth.npz'))
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    depth, _, _ = eng.disp2depth(cuda(g['raw'][None]))
+    np.testing.assert_array_equal(depth[0].cpu().numpy(), g['depth_map'])
+    n = len(g['boxes'])
+    boxes = torch.zeros(1, n + 3, 4, device='cuda')
+    boxes[0, :n] = cuda(g['boxes'])
+    counts = torch.tensor([n], dtype=torch.int32, device='cuda')
+    infl = torch.zeros_like(boxes)
+    d, sc, _ = eng.box_depth(depth, boxes, counts, inflated_out=infl)
+    d, sc, infl = d[0, :n].cpu().numpy(), sc[0, :n].cpu().numpy(), infl[0, :n].cpu().numpy()
+    ref_d = g['d']
+    np.testing.assert_array_equal(np.isnan(d), np.isnan(ref_d))
+    np.testing.assert_array_equal(d == -1, ref_d == -1)
+    ok = ~np.isnan(ref_d)
+    np.testing.assert_allclose(d[ok], ref_d[ok], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(sc, g['scales'], rtol=2e-6, atol=0, equal_nan=True)
+    same = sc == g['scales']
+    np.testing.assert_array_equal(infl[same], g['inflated'][same])
+    defl = eng.scale_boxes(cuda(g['inflated'][None]), cuda(g['scales'][None]), counts, True)
+    np.testing.assert_array_equal(defl[0, :n].cpu().numpy(), g['deflated'])
+
+
+def test_k3_large_boxes_use_global_path(mods):
+    rng = np.random.default_rng(8)
+    H, W = 256, 1024
+    raw = rng.integers(20, 3000, (1, H, W)).astype(np.uint16)
+    raw[rng.random(raw.shape) < 0.3] = 65535
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    depth, _, _ = eng.disp2depth(cuda(raw))
+    b = np.asarray([[3.2, 1.1, 790.5, 250.7], [100, 10, 905, 200], [0, 0, 120.5, 90.2],
+                    [500.5, 3.3, 1023.9, 255.9], [10, 10, 400, 30]], np.float32)
+    boxes = cuda(b[None])
+    counts = torch.tensor([len(b)], dtype=torch.int32, device='cuda')
+    d, sc, _ = eng.box_depth(depth, boxes, counts)
+    rd, rs = mods.boxdepth.extract_depth(depth[0].cpu().numpy(), b)
+    assert rd[1] == -1                       # wider than 800 px
+    np.testing.assert_allclose(d[0].cpu().numpy(), rd, rtol=1e-6)
+    np.testing.assert_allclose(sc[0].cpu().numpy(), rs, rtol=2e-6)
+
+
+# ---------------------------------------------------------------- KF / LAP -------
+def test_kalman_batch_matches_reference_fixture(mods):
+    g = np.load(os.path.join(GOLDEN, 'ref_kf.npz'))
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    mean = torch.zeros(1, 8, dtype=torch.float64, device='cuda')
+    cov = torch.zeros(1, 64, dtype=torch.float64, device='cuda')
+    for i, op in enumerate(g['op']):
+        z = cuda(g['z'][i][None].astype(np.float32))
+        eng.kalman_batch(int(op), mean, cov, z)
+        np.testing.assert_allclose(mean[0].cpu().numpy(), g['mean'][i], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(cov[0].cpu().numpy().reshape(8, 8), g['cov'][i], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize('R,C,ties', [(1, 1, False), (7, 5, False), (5, 9, True), (40, 33, False),
+                                      (64, 64, True), (130, 120, False)])
+def test_lapjv_batch_matches_oracle(mods, R, C, ties):
+    rng = np.random.default_rng(R * 100 + C)
+    B = 24
+    if ties:
+        cost = (rng.integers(0, 5, (B, R, C)) * 0.25).astype(np.float32)
+    else:
+        cost = rng.uniform(0, 1.3, (B, R, C)).astype(np.float32)
+        cost[:, np.arange(min(R, C)), np.arange(min(R, C))] *= 0.2      # mostly matchable
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    x, y = eng.lapjv_batch(cuda(cost), 0.9)
+    assert eng.status().max() == 0
+    x, y = x.cpu().numpy(), y.cpu().numpy()
+    for b in range(B):
+        rx, ry = mods.lapjv(cost[b], 0.9)
+        np.testing.assert_array_equal(y[b], ry, err_msg=f'problem {b}')
+        np.testing.assert_array_equal(x[b], rx, err_msg=f'problem {b}')
+
+
+# ---------------------------------------------------------------- tracker ---------
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress'])
+def test_tracker_matches_reference_fixture(mods, name):
+    g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1, max_dets=64, max_tracks=128))
+    D = eng.cfg.max_dets
+    for f in range(len(g['raw'])):
+        n = int(g['det_count'][f])
+        depth, _, _ = eng.disp2depth(cuda(g['raw'][f][None]))
+        eng.det_boxes.zero_(); eng.det_scores.zero_(); eng.det_labels.zero_()
+        eng.det_boxes[0, :n] = cuda(g['det_boxes'][f, :n])
+        eng.det_scores[0, :n] = cuda(g['det_scores'][f, :n])
+        eng.det_counts[0] = n
+        eng.frame_ids[0] = f
+        eng.step_from_dets(depth)
+        r = eng.results()[0]
+        m = int(g['out_count'][f])
+        np.testing.assert_array_equal(r['instances_id'], g['out_ids'][f, :m], err_msg=f'frame {f}')
+        np.testing.assert_array_equal(r['scores'], g['out_scores'][f, :m])
+        np.testing.assert_allclose(r['scales'], g['out_scales'][f, :m], rtol=2e-6)
+        np.testing.assert_allclose(r['bboxes'], g['out_bboxes'][f, :m], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(r['depth'], g['out_depth'][f, :m], rtol=1e-5, equal_nan=True)
+        st = eng.export_state(0)
+        k = int(g['st_count'][f])
+        np.testing.assert_array_equal(st['ids'], g['out_st_ids'][f, :k])
+        np.testing.assert_array_equal(st['tentative'], g['out_st_tent'][f, :k])
+        np.testing.assert_array_equal(st['tracked'], g['out_st_tracked'][f, :k])
+        np.testing.assert_allclose(st['mean'], g['out_st_mean'][f, :k], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(st['cov'], g['out_st_cov'][f, :k], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(st['velocity'], g['out_st_vel'][f, :k], rtol=1e-5, atol=1e-6)
+        assert st['num_tracks'] == g['num_tracks'][f]
+    assert eng.status().max() == 0
+
+
+def _run_pipeline(mods, cfg, S, F, seed, max_dets=256, max_cand=4096, check_state=False):
+    gen = mods.SyntheticStereo(cfg, S, F, seed=seed)
+    fr = gen.frames(0, F)
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S, max_dets=max_dets, max_candidates=max_cand))
+    oracles = [mods.StereoTrackOracle() for _ in range(S)]
+    total = 0
+    for f in range(F):
+        eng.frame_ids.fill_(f)
+        eng.step(fr['raw'][f].cuda().contiguous(), [c[f].cuda().contiguous() for c in fr['cls']],
+                 [c[f].cuda().contiguous() for c in fr['bbox']], [c[f].cuda().contiguous() for c in fr['obj']])
+        res = eng.results()
+        for s in range(S):
+            ref = oracles[s].step(f, fr['raw'][f, s].numpy(), [c[f, s].numpy() for c in fr['cls']],
+                                  [c[f, s].numpy() for c in fr['bbox']], [c[f, s].numpy() for c in fr['obj']])
+            np.testing.assert_array_equal(res[s]['instances_id'], ref['instances_id'],
+                                          err_msg=f'frame {f} seq {s}')
+            np.testing.assert_allclose(res[s]['bboxes'], ref['bboxes'], rtol=1e-5, atol=1e-4)
+            np.testing.assert_allclose(res[s]['scores'], ref['scores'], rtol=2e-7)
+            np.testing.assert_allclose(res[s]['depth'], ref['depth'], rtol=1e-5, equal_nan=True)
+            total += len(ref['instances_id'])
+            if check_state and f % 7 == 0:
+                st, rs = eng.export_state(s), oracles[s].tracker.export_state()
+                np.testing.assert_array_equal(st['ids'], rs['ids'])
+                np.testing.assert_allclose(st['mean'], rs['mean'], rtol=1e-5, atol=1e-7)
+    assert eng.status().max() == 0
+    return total
+
+
+def test_full_pipeline_c1_matches_oracle(mods):
+    assert _run_pipeline(mods, mods.CONFIGS['C1'], S=3, F=40, seed=11, check_state=True) > 300
+
+
+def test_full_pipeline_stress_matches_oracle(mods):
+    cfg = mods.SceneConfig(360, 640, 5, 30, invalid_prob=0.30, n_clutter=200, heavy_ego=True)
+    assert _run_pipeline(mods, cfg, S=2, F=30, seed=12, max_dets=512) > 300
+
+
+def test_lockstep_batch_equals_single_sequences(mods):
+    """Sequences are independent: a batch of S equals S runs with n_seq=1."""
+    cfg = mods.SceneConfig(192, 256, 4, 8, n_clutter=10)
+    S, F = 4, 12
+    gen = mods.SyntheticStereo(cfg, S, F, seed=21)
+    fr = gen.frames(0, F)
+    batch = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S))
+    singles = [mods.StereoTrackEngine(mods.EngineConfig(n_seq=1)) for _ in range(S)]
+    for f in range(F):
+        batch.frame_ids.fill_(f)
+        batch.step(fr['raw'][f].cuda().contiguous(), [c[f].cuda().contiguous() for c in fr['cls']],
+                   [c[f].cuda().contiguous() for c in fr['bbox']], [c[f].cuda().contiguous() for c in fr['obj']])
+        rb = batch.results()
+        for s in range(S):
+            e = singles[s]
+            e.frame_ids.fill_(f)
+            e.step(fr['raw'][f, s:s + 1].cuda().contiguous(), [c[f, s:s + 1].cuda().contiguous() for c in fr['cls']],
+                   [c[f, s:s + 1].cuda().contiguous() for c in fr['bbox']],
+                   [c[f, s:s + 1].cuda().contiguous() for c in fr['obj']])
+            r1 = e.results()[0]
+            for k in rb[s]:
+                np.testing.assert_array_equal(rb[s][k], r1[k])
