@@ -90,6 +90,15 @@ int st_destroy(st_handle *h);
 int st_reset(st_handle *h, const uint8_t *seq_mask, void *stream);
 int st_read_status(st_handle *h, int32_t *status_host, int S);   /* synchronises */
 int st_clear_status(st_handle *h, void *stream);
+/* Diagnostics: 8 progress words per sequence written by the last st_track_step
+ * (phase, assignment rows/cols, solver sub-phase, ...).  Copied on a side
+ * stream, so it can be called while a step is still running. */
+int st_read_debug(st_handle *h, int32_t *debug_host, int S);
+/* Diagnostics: disable parts of st_track_step (bit0..2 assignment of stage 1..3,
+ * bit3 online smoothing, bit4 Kalman update, bit5 Kalman predict). 0 = normal. */
+int st_debug_set_skip(int mask);
+/* Diagnostics: the cost matrix of the last association of sequence `seq` (row-major R x C). */
+int st_debug_read_cost(st_handle *h, int seq, float *cost_host, int count);
 
 /* K1 - replaces loading_disparity.py:82-86,:129-134 (mask, 65535->0, /16),
  * transforms_disparity.py:52-70 (nearest resize to Hr x Wr), :177-194 (zero pad

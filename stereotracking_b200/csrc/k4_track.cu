@@ -22,6 +22,10 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 
+// diagnostics only (st_debug_set_skip): bit0..2 skip the assignment of stage
+// 1..3, bit3 skip online smoothing, bit4 skip Kalman update, bit5 skip predict
+__device__ int g_skip = 0;
+
 struct Params {
     int T, D;                    // capacities
     float obj_score_thr, init_track_thr, vel_w;
@@ -209,9 +213,13 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
     }
     __syncthreads();
     // ---- assignment (warp 0) -----------------------------------------------------
-    if (threadIdx.x < 32) {
+    if (threadIdx.x < 32 && (g_skip >> (stage_code - 1) & 1)) {
+        for (int c = threadIdx.x; c < C; c += 32) sm.lap.y[c] = -1;
+    } else if (threadIdx.x < 32) {
         stlap::Problem P;
         P.cost = cost; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
+        P.dbg = st.debug + (sbase / pr.T) * 8;
+        P.mark(0, stage_code); P.mark(1, R); P.mark(2, C);
         const bool ok = stlap::solve_warp(P, sm.lap);
         if (!ok && threadIdx.x == 0) atomicOr(status_word, ST_STATUS_LAP_GUARD);
     }
@@ -232,7 +240,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
               const float *__restrict__ det_boxes, const float *__restrict__ det_scores,
               const int64_t *__restrict__ det_labels, const float *__restrict__ det_scales,
               const float *__restrict__ det_depth, const int32_t *__restrict__ det_counts, int det_cap,
-              float *__restrict__ cost_ws, float *__restrict__ out_boxes, float *__restrict__ out_scores,
+              float *cost_ws /* written and re-read in this kernel: no __restrict__ */, float *__restrict__ out_boxes, float *__restrict__ out_scores,
               int64_t *__restrict__ out_labels, float *__restrict__ out_scales,
               float *__restrict__ out_depth, int64_t *__restrict__ out_ids,
               int32_t *__restrict__ out_counts) {
@@ -305,7 +313,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
                 if (lane == 0) st.has_saved[g] = 1;
             }
             __syncwarp();
-            stkf::predict(st.mean + g * 8, st.cov + g * 64, kfws);
+            if (!(g_skip & 32)) stkf::predict(st.mean + g * 8, st.cov + g * 64, kfws);
         }
         __syncthreads();
         // ---- stage 1: confirmed tracks vs filtered dets (:448-474)
@@ -341,12 +349,13 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
                     if (order[p] == slot) { sm.slot_hit[p] = 1; break; }
         }
         __syncthreads();
+        if (threadIdx.x == 0) st.debug[s * 8 + 7] = 8;
         // ---- online smoothing of re-found lost tracks (:571-577, :319-343)
         for (int i = warp; i < nd_in; i += kWarps) {
             const int slot = sm.det_slot[i];
             if (slot < 0) continue;
             const long long g = sbase + slot;
-            if (st.tracked[g]) continue;
+            if (st.tracked[g] || (g_skip & 8)) continue;
             const int miss = st.miss_run[g];
             float last[4], shift[4];
             const float denom = (float)(miss + 1);
@@ -369,6 +378,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             }
         }
         __syncthreads();
+        if (threadIdx.x == 0) st.debug[s * 8 + 7] = 9;
         // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582)
         for (int p = threadIdx.x; p < n_live; p += kThreads)
             if (!sm.slot_hit[p]) {
@@ -393,6 +403,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         n_out = sh_cnt[0];
     }
 
+    if (threadIdx.x == 0) st.debug[s * 8 + 7] = 10;
     // ---- ids + BaseTracker.update (:598-605, base_tracker.py:54-91) ------------
     // new tracks are exactly the outputs without a slot; they are last in order
     __syncthreads();
@@ -426,7 +437,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             id = st.id[g];
             double z[4];
             for (int q = 0; q < 4; ++q) z[q] = (double)zc[q];
-            stkf::update(st.mean + g * 8, st.cov + g * 64, z, kfws);
+            if (!(g_skip & 16)) stkf::update(st.mean + g * 8, st.cov + g * 64, z, kfws);
             if (lane == 0) {
                 st.hits[g] += 1;
                 st.last_frame[g] = frame;
@@ -478,6 +489,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) st.debug[s * 8 + 7] = 11;
     // ---- pop_invalid_tracks (kalman_tracker_base.py:77-88) -------------------------
     const int n_now = n_live + n_create;
     if (threadIdx.x < 32) {
@@ -507,6 +519,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             st.n_free[s] = n_free - n_create + freed;
             st.next_id[s] = id0 + n_new;
             out_counts[s] = n_out;
+            st.debug[s * 8 + 7] = 12;
         }
     }
 }
@@ -526,6 +539,7 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int32_
     stlap::Scratch sc = stlap::carve(smem_raw, R + C);
     stlap::Problem P;
     P.cost = cost + (long long)b * R * C; P.R = R; P.C = C; P.n = R + C; P.half = half;
+    P.dbg = nullptr;
     if (R > 0 && C > 0) {
         const bool ok = stlap::solve_warp(P, sc);
         if (!ok && lane == 0) atomicOr(status, ST_STATUS_LAP_GUARD);
@@ -569,7 +583,7 @@ size_t layout(st_handle *h, unsigned char *base) {
     unsigned char *c = base;
     TrackState &st = h->st;
     take(st.n_live, c, S); take(st.next_id, c, S); take(st.order, c, S * T); take(st.free_slots, c, S * T);
-    take(st.n_free, c, S); take(st.status, c, S);
+    take(st.n_free, c, S); take(st.status, c, S); take(st.debug, c, S * 8);
     take(st.id, c, S * T); take(st.hits, c, S * T); take(st.last_frame, c, S * T);
     take(st.tentative, c, S * T); take(st.tracked, c, S * T); take(st.has_saved, c, S * T);
     take(st.mean, c, S * T * 8); take(st.cov, c, S * T * 64);
@@ -657,6 +671,30 @@ extern "C" int st_reset(st_handle *h, const uint8_t *seq_mask, void *stream) {
 extern "C" int st_read_status(st_handle *h, int32_t *status_host, int S) {
     if (!h || !status_host || S < 0 || S > h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
     ST_CUDA_OK(cudaMemcpy(status_host, h->st.status, sizeof(int32_t) * S, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+extern "C" int st_read_debug(st_handle *h, int32_t *debug_host, int S) {
+    if (!h || !debug_host || S < 0 || S > h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
+    // a side stream so that the words can be read while a kernel is still running
+    cudaStream_t side;
+    ST_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    cudaError_t e = cudaMemcpyAsync(debug_host, h->st.debug, sizeof(int32_t) * 8 * S, cudaMemcpyDeviceToHost, side);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(side);
+    cudaStreamDestroy(side);
+    return e == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+}
+
+extern "C" int st_debug_read_cost(st_handle *h, int seq, float *cost_host, int count) {
+    if (!h || !cost_host || seq < 0 || seq >= h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
+    ST_CUDA_OK(cudaDeviceSynchronize());
+    ST_CUDA_OK(cudaMemcpy(cost_host, h->cost + (size_t)seq * h->cfg.max_tracks * h->cfg.max_dets,
+                          sizeof(float) * count, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+extern "C" int st_debug_set_skip(int mask) {
+    ST_CUDA_OK(cudaMemcpyToSymbol(g_skip, &mask, sizeof(int)));
     return ST_OK;
 }
 

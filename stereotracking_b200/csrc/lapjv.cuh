@@ -17,12 +17,16 @@ namespace stlap {
 
 constexpr double kBig = 1.0e300;
 
-struct Scratch {          // all arrays have n = R + C entries, in shared memory
-    double *v;            // column potentials
-    double *d;            // shortest-path distances
-    int *cols, *pred, *x, *y, *free_rows;
-    unsigned *mask_a, *mask_b;   // (n+31)/32 words each
-    unsigned char *unique;
+// All arrays have n = R + C entries and live in shared memory.  They are
+// volatile because lanes of one warp hand data to each other through them
+// between __syncwarp() calls (lane 0 replays serial list updates that the other
+// lanes then read).
+struct Scratch {
+    volatile double *v;            // column potentials
+    volatile double *d;            // shortest-path distances
+    volatile int *cols, *pred, *x, *y, *free_rows;
+    volatile unsigned *mask_a, *mask_b;   // (n+31)/32 words each
+    volatile unsigned char *unique;
 };
 
 __host__ __device__ inline size_t scratch_bytes(int n) {
@@ -34,15 +38,15 @@ __host__ __device__ inline size_t scratch_bytes(int n) {
 __device__ inline Scratch carve(unsigned char *p, int n) {
     Scratch s;
     size_t words = (size_t)(n + 31) / 32;
-    s.v = reinterpret_cast<double *>(p); p += sizeof(double) * n;
-    s.d = reinterpret_cast<double *>(p); p += sizeof(double) * n;
-    s.cols = reinterpret_cast<int *>(p); p += sizeof(int) * n;
-    s.pred = reinterpret_cast<int *>(p); p += sizeof(int) * n;
-    s.x = reinterpret_cast<int *>(p); p += sizeof(int) * n;
-    s.y = reinterpret_cast<int *>(p); p += sizeof(int) * n;
-    s.free_rows = reinterpret_cast<int *>(p); p += sizeof(int) * n;
-    s.mask_a = reinterpret_cast<unsigned *>(p); p += sizeof(unsigned) * words;
-    s.mask_b = reinterpret_cast<unsigned *>(p); p += sizeof(unsigned) * words;
+    s.v = reinterpret_cast<volatile double *>(p); p += sizeof(double) * n;
+    s.d = reinterpret_cast<volatile double *>(p); p += sizeof(double) * n;
+    s.cols = reinterpret_cast<volatile int *>(p); p += sizeof(int) * n;
+    s.pred = reinterpret_cast<volatile int *>(p); p += sizeof(int) * n;
+    s.x = reinterpret_cast<volatile int *>(p); p += sizeof(int) * n;
+    s.y = reinterpret_cast<volatile int *>(p); p += sizeof(int) * n;
+    s.free_rows = reinterpret_cast<volatile int *>(p); p += sizeof(int) * n;
+    s.mask_a = reinterpret_cast<volatile unsigned *>(p); p += sizeof(unsigned) * words;
+    s.mask_b = reinterpret_cast<volatile unsigned *>(p); p += sizeof(unsigned) * words;
     s.unique = p;
     return s;
 }
@@ -51,6 +55,10 @@ struct Problem {
     const float *cost;    // R x C row-major (float32 as the reference's dists)
     int R, C, n;
     double half;          // cost_limit / 2
+    int *dbg;             // optional [8] progress words (global), may be null
+    __device__ __forceinline__ void mark(int slot, int v) const {
+        if (dbg && (threadIdx.x & 31) == 0) ((volatile int *)dbg)[slot] = v;
+    }
     __device__ __forceinline__ double at(int i, int j) const {
         if (i < R) return j < C ? (double)cost[(long long)i * C + j] : half;
         return j < C ? half : 0.0;
@@ -80,11 +88,16 @@ __device__ __forceinline__ bool pair_less(double va, int ia, double vb, int ib) 
 // Solve; on return s.x[i] (row->col) and s.y[j] (col->row) hold the extended
 // assignment.  Must be called by all 32 lanes of one warp.  Returns false when
 // an iteration guard fired (non-finite costs).
-__device__ bool solve_warp(const Problem &P, Scratch &s) {
+// __noinline__ on purpose: with nvcc 12.9 the copies inlined into the fused
+// track kernel mis-executed the warp collectives of the augmentation loop on
+// inputs the stand-alone kernel solved (bisected on a B200); one
+// shared out-of-line body behaves identically at every call site.
+__device__ __noinline__ bool solve_warp(const Problem &P, Scratch &s) {
     const int lane = threadIdx.x & 31;
     const int n = P.n;
     bool ok = true;
 
+    P.mark(3, 1);
     // ---- column reduction -----------------------------------------------------
     for (int i = lane; i < n; i += 32) { s.x[i] = -1; s.unique[i] = 1; }
     for (int j = lane; j < n; j += 32) {
@@ -105,7 +118,7 @@ __device__ bool solve_warp(const Problem &P, Scratch &s) {
     }
     __syncwarp();
     // reverse sweep: the highest column that elected a row keeps it
-    for (int j = lane; j < n; j += 32) atomicMax(&s.x[s.y[j]], j);
+    for (int j = lane; j < n; j += 32) atomicMax(const_cast<int *>(&s.x[s.y[j]]), j);
     __syncwarp();
     for (int j = lane; j < n; j += 32) {
         int i = s.y[j];
@@ -113,6 +126,7 @@ __device__ bool solve_warp(const Problem &P, Scratch &s) {
     }
     __syncwarp();
 
+    P.mark(3, 2);
     // ---- reduction transfer (row order matters: v[] feeds later rows) ----------
     int nfree = 0;
     for (int i0 = 0; i0 < n; i0 += 32) {
@@ -142,6 +156,7 @@ __device__ bool solve_warp(const Problem &P, Scratch &s) {
     }
     __syncwarp();
 
+    P.mark(3, 3); P.mark(4, nfree);
     // ---- augmenting row reduction, two passes --------------------------------------
     for (int pass = 0; pass < 2 && nfree > 0; ++pass) {
         int cur = 0, nxt = 0;
@@ -195,6 +210,7 @@ __device__ bool solve_warp(const Problem &P, Scratch &s) {
     }
 
     // ---- augmentation ----------------------------------------------------------
+    P.mark(3, 4); P.mark(4, nfree);
     const int words = (n + 31) >> 5;
     for (int f = 0; f < nfree && ok; ++f) {
         const int start = s.free_rows[f];
@@ -217,7 +233,8 @@ __device__ bool solve_warp(const Problem &P, Scratch &s) {
                 __syncwarp();
                 for (int k0 = lo + 1; k0 < n; k0 += 32) {
                     const int k = k0 + lane;
-                    const double dv = k < n ? s.d[s.cols[k]] : kBig;
+                    double dv = 1.0e300;
+                    if (k < n) dv = s.d[s.cols[k]];
                     double inc = dv;                       // inclusive prefix min
                     for (int o = 1; o < 32; o <<= 1) {
                         const double t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -269,6 +286,7 @@ __device__ bool solve_warp(const Problem &P, Scratch &s) {
             if (final_j == -1) {
                 // -- relax TODO columns from every SCAN column
                 while (lo != hi) {
+                    if (lo < 0 || hi > n || lo > hi) { ok = false; final_j = -2; break; }
                     const int js = s.cols[lo++];
                     const int i = s.y[js];
                     const double mind = s.d[js];
@@ -323,7 +341,7 @@ __device__ bool solve_warp(const Problem &P, Scratch &s) {
                 if (final_j != -1) lo = n_ready;      // caller's lo is unchanged by an early return
             }
         }
-        if (!ok) break;
+        if (!ok || final_j < 0) { ok = false; break; }
         {
             const double mind = s.d[s.cols[lo]];
             for (int k = lane; k < n_ready; k += 32) {
@@ -342,6 +360,7 @@ __device__ bool solve_warp(const Problem &P, Scratch &s) {
         }
         __syncwarp();
     }
+    P.mark(3, ok ? 5 : -5);
     return ok;
 }
 

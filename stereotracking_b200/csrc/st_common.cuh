@@ -30,6 +30,7 @@ struct TrackState {
     int32_t *free_slots;    // [S, T] stack of unused slots
     int32_t *n_free;        // [S]
     int32_t *status;        // [S] sticky ST_STATUS_* bits
+    int32_t *debug;         // [S, 8] progress words of the last track step (diagnostics)
     // per slot
     int64_t *id;            // [S*T]
     int32_t *hits;          // len(track.bboxes)

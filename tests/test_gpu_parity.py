@@ -67,7 +67,7 @@ def _head_case(mods, cfg_name, S, seed, frames=2):
 @pytest.mark.parametrize('cfg_name,S,seed', [('C1', 3, 5), ('C4', 2, 6)])
 def test_k2_decode_nms_matches_oracle(mods, cfg_name, S, seed):
     cfg, fr = _head_case(mods, cfg_name, S, seed)
-    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S, max_dets=512, max_candidates=4096))
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S, max_dets=1024, max_candidates=4096))
     for f in range(fr['raw'].shape[0]):
         cls_l = [c[f].cuda().contiguous() for c in fr['cls']]
         box_l = [c[f].cuda().contiguous() for c in fr['bbox']]
