@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the depth-guided tracking path (BASELINE.json metric: tracked
+frames/sec with sequences batched in lockstep; % of HBM roofline; host-CPU
+reference beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A *step* is one lockstep frame of every sequence of the workload (S frames).
+Workload at every N: BASELINE.json configs[1] per GPU - 64 synthetic 1280x720
+stereo sequences (left image is not an input of this path; raw u16 disparity +
+YOLOX head maps are), up to 50 airborne objects per frame - so per-GPU work is
+fixed as N grows (weak scaling; sequences are independent, no collective on the
+data path).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = 'C2'
+SEQ_PER_GPU = 64
+METRIC = 'tracked_frames_per_sec'
+UNIT = 'frames/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--seq', type=int, default=SEQ_PER_GPU, help='sequences per GPU')
+    ap.add_argument('--workload', default=WORKLOAD)
+    ap.add_argument('--cpu-seqs', type=int, default=0, help='sequences of the CPU sample (0 = auto)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    return rank, world, local
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+# --------------------------------------------------------------------------- data
+def generate(cfg, S, n_frames, seed, device, chunk=2):
+    """Synthetic frames resident on `device`: raw [F,S,H,W] u16 and per-level head
+    maps [F,S,C,h,w] f32 (stereotracking_b200/synthetic.py)."""
+    from stereotracking_b200.synthetic import SyntheticStereo
+    gen = SyntheticStereo(cfg, S, n_frames, seed=seed, device=device)
+    parts = [gen.frames(f0, min(f0 + chunk, n_frames)) for f0 in range(0, n_frames, chunk)]
+    raw = torch.cat([p['raw'] for p in parts])
+    L = len(parts[0]['cls'])
+    cls = [torch.cat([p['cls'][l] for p in parts]) for l in range(L)]
+    box = [torch.cat([p['bbox'][l] for p in parts]) for l in range(L)]
+    obj = [torch.cat([p['obj'][l] for p in parts]) for l in range(L)]
+    return raw, cls, box, obj
+
+
+# --------------------------------------------------------------------------- CPU arm
+_CPU_DATA = {}
+
+
+def _cpu_worker(s):
+    """The oracle (CPU restatement of the reference tracker path) on one sequence."""
+    from oracle.model import StereoTrackOracle
+    torch.set_num_threads(1)
+    d = _CPU_DATA
+    o = StereoTrackOracle()
+    F = d['raw'].shape[0]
+    t0 = time.perf_counter()
+    rows = 0
+    for f in range(F):
+        r = o.step(f, d['raw'][f, s], [c[f, s] for c in d['cls']], [c[f, s] for c in d['box']],
+                   [c[f, s] for c in d['obj']])
+        rows += len(r['instances_id'])
+    return F, time.perf_counter() - t0, rows
+
+
+def _cpu_warm(_):
+    from oracle.model import StereoTrackOracle  # noqa: F401
+    from oracle.lapjv import lapjv
+    lapjv(np.zeros((1, 1), np.float32), 0.9)
+    time.sleep(0.05)
+    return 0
+
+
+def cpu_reference(raw, cls, box, obj, n_seqs, cores):
+    """frames/s of the oracle over `n_seqs` sequences, one process per core."""
+    import multiprocessing as mp
+    import warnings
+    warnings.simplefilter('ignore')
+    _CPU_DATA.update(raw=raw[:, :n_seqs].cpu().numpy(), cls=[c[:, :n_seqs].cpu().numpy() for c in cls],
+                     box=[c[:, :n_seqs].cpu().numpy() for c in box], obj=[c[:, :n_seqs].cpu().numpy() for c in obj])
+    cores = max(1, min(cores, n_seqs))
+    if cores == 1:
+        t0 = time.perf_counter()
+        res = [_cpu_worker(s) for s in range(n_seqs)]
+        wall = time.perf_counter() - t0
+    else:
+        with mp.get_context('fork').Pool(cores) as pool:
+            pool.map(_cpu_warm, range(cores), chunksize=1)     # imports + library load, untimed
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, range(n_seqs), chunksize=1)
+            wall = time.perf_counter() - t0
+    frames = sum(r[0] for r in res)
+    single = np.mean([r[0] / r[1] for r in res])
+    return frames / wall, cores, float(single), frames, sum(r[2] for r in res)
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    args = parse()
+    rank, world, local = dist_env()
+    from stereotracking_b200.synthetic import CONFIGS
+    cfg = CONFIGS[args.workload]
+    S, K, W = args.seq, args.steps, max(args.warmup, 0)
+    F = K + W
+    config = dict(workload=f'{args.workload}: {S} synthetic {cfg.width}x{cfg.height} stereo sequences per GPU in '
+                           f'lockstep, {cfg.k_min}-{cfg.k_max} objects/frame, {cfg.n_clutter} clutter priors, '
+                           f'{int(cfg.invalid_prob * 100)}% invalid disparity',
+                  sequences_per_gpu=S, frames_per_step=S * max(world, 1), priors_per_frame=cfg.num_priors,
+                  tracker='OCSORTTracker_Disparity (configs/stereo_tracking/ocsort/yolox_s_mmyolo_mot_airdrone_disp.py)',
+                  l2_policy='every step reads fresh frames (147 MB/step at C2) > 126 MB L2; no flush needed',
+                  parallelism=f'{world} x (sequence shard per GPU), no data-path collective')
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        # the reference's own CPU implementation of the path = the oracle port
+        # (the reference is pure Python and cannot be installed here: mmengine/
+        # mmcv/mmdet/mmyolo/lap are absent)
+        cores = os.cpu_count() or 1
+        n_seqs = args.cpu_seqs or max(2, min(S, cores))
+        frames_per_seq = min(F, 24)
+        dev = 'cuda' if torch.cuda.is_available() else 'cpu'
+        raw, cls, box, obj = generate(cfg, n_seqs, frames_per_seq, 20240604 + 1000, dev)
+        times = []
+        for _ in range(max(1, min(K, 3))):
+            fps, used, single, frames, rows = cpu_reference(raw, cls, box, obj, n_seqs, cores)
+            times.append(fps)
+        fps = float(np.median(times))
+        sample = f'{n_seqs} sequences x {frames_per_seq} frames of the same workload, one process per core'
+        line = dict(metric=METRIC, value=fps, unit=UNIT, n_gpus=args.gpus, steps=K, warmup=W,
+                    ms_per_step=1e3 * S * world / fps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f32 (f64 Kalman/assignment)', data='synthetic', config=config, impl='reference',
+                    cpu_baseline=dict(value=fps, unit=UNIT, cores=used, kind='port', sample=sample,
+                                      single_core=single),
+                    e2e=dict(value=fps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), 'bench.py needs a GPU for --impl b200 (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from stereotracking_b200.engine import EngineConfig, StereoTrackEngine
+
+    raw, cls, box, obj = generate(cfg, S, F, 20240604 + 1000 + rank, dev)
+    eng = StereoTrackEngine(EngineConfig(n_seq=S, max_dets=256, max_tracks=256, max_candidates=2048), device=dev)
+    io = eng.make_frame_io(raw.shape[1:], [c.shape[-2:] for c in cls])
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run_steps(f0, f1, events=None):
+        for f in range(f0, f1):
+            eng.frame_ids.fill_(f)
+            if events is None:
+                eng.frame_step(io, raw[f], [c[f] for c in cls], [c[f] for c in box], [c[f] for c in obj])
+            else:
+                # same launches, one C call per stage so that each stage can be bracketed by events
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+                ev[0].record(stream)
+                eng.disp2depth(raw[f], out=eng.depth_map); ev[1].record(stream)
+                eng.decode_nms([c[f] for c in cls], [c[f] for c in box], [c[f] for c in obj],
+                               (cfg.height, cfg.width)); ev[2].record(stream)
+                eng.box_depth(eng.depth_map, eng.det_boxes, eng.det_counts, eng.det_depth, eng.det_scales,
+                              eng.det_inflated); ev[3].record(stream)
+                eng.track_step(eng.frame_ids, eng.det_inflated, eng.det_scores, eng.det_labels, eng.det_scales,
+                               eng.det_depth, eng.det_counts); ev[4].record(stream)
+                eng.scale_boxes(eng.trk_boxes, eng.out_scales, eng.out_counts, True, eng.out_boxes)
+                ev[5].record(stream)
+                eng.box_depth(eng.depth_map, eng.out_boxes, eng.out_counts, eng.out_depth, eng.out_scale2, None)
+                ev[6].record(stream)
+                events.append(ev)
+
+    # ---- resident-input timing (value) -------------------------------------------
+    run_steps(0, W)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run_steps(W, F)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    status = eng.status()
+    tracked_rows = int(eng.out_counts.sum())
+
+    # ---- per-kernel timing (second pass over the same frames, same state reset by frame 0) ----
+    stage_events = []
+    run_steps(0, W)
+    barrier()
+    run_steps(W, F, stage_events)
+    barrier()
+    names = ['k1_disp2depth', 'k2_decode_nms(4 kernels)', 'k3_box_depth(dets)', 'k4_track_step',
+             'scale_boxes', 'k3_box_depth(tracks)']
+    stage_ms = np.array([[ev[i].elapsed_time(ev[i + 1]) for i in range(6)] for ev in stage_events])
+    stage_avg = stage_ms.mean(0)
+
+    # ---- end to end through the public call with HOST buffers ---------------------
+    host = dict(raw=raw.cpu().pin_memory(), cls=[c.cpu().pin_memory() for c in cls],
+                box=[c.cpu().pin_memory() for c in box], obj=[c.cpu().pin_memory() for c in obj])
+    d_raw = torch.empty_like(raw[0]); d_cls = [torch.empty_like(c[0]) for c in cls]
+    d_box = [torch.empty_like(c[0]) for c in box]; d_obj = [torch.empty_like(c[0]) for c in obj]
+    outs = [eng.out_boxes, eng.out_ids, eng.out_scores, eng.out_labels, eng.out_scales, eng.out_depth, eng.out_counts]
+    h_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs]
+    h2d = raw[0].numel() * 2 + sum(t[0].numel() * 4 for t in cls + box + obj)
+    d2h = sum(t.numel() * t.element_size() for t in outs)
+
+    def e2e_steps(f0, f1):
+        for f in range(f0, f1):
+            d_raw.copy_(host['raw'][f], non_blocking=True)
+            for l in range(len(cls)):
+                d_cls[l].copy_(host['cls'][l][f], non_blocking=True)
+                d_box[l].copy_(host['box'][l][f], non_blocking=True)
+                d_obj[l].copy_(host['obj'][l][f], non_blocking=True)
+            eng.frame_ids.fill_(f)
+            eng.frame_step(io, d_raw, d_cls, d_box, d_obj)
+            for t, h in zip(outs, h_out):
+                h.copy_(t, non_blocking=True)
+            stream.synchronize()          # the caller consumes this frame's tracks before the next frame
+
+    e2e_steps(0, W)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps(W, F)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks ------------------------------------------------------------
+    vals = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(vals[0]), float(vals[1])
+    frames = S * world * K
+    value = frames / (ms_total * 1e-3)
+    e2e_value = frames / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        Hp, Wp = cfg.padded_hw
+        k1_bytes = S * (2 * cfg.height * cfg.width + 4 * Hp * Wp)          # u16 read + f32 depth write
+        k1_gbs = k1_bytes / (stage_avg[0] * 1e-3) / 1e9
+        P = cfg.num_priors
+        k2_bytes = S * P * 8                                               # cls + obj logits of every prior
+        kernels = {n: dict(ms=float(stage_avg[i]), share=float(stage_avg[i] / stage_avg.sum()))
+                   for i, n in enumerate(names)}
+        kernels['k1_disp2depth'].update(algorithmic_bytes=k1_bytes, achieved_gbs=k1_gbs, frac=k1_gbs / peak)
+        kernels['k2_decode_nms(4 kernels)'].update(
+            algorithmic_bytes=k2_bytes, achieved_gbs=k2_bytes / (stage_avg[1] * 1e-3) / 1e9)
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            n_seqs = args.cpu_seqs or max(2, min(S, cores))
+            fsub = min(F, 24)
+            fps, used, single, nfr, rows = cpu_reference(raw[:fsub], [c[:fsub] for c in cls], [c[:fsub] for c in box],
+                                                         [c[:fsub] for c in obj], n_seqs, cores)
+            cpu = dict(value=fps, unit=UNIT, cores=used, kind='port', single_core=single,
+                       sample=f'first {n_seqs} sequences x {fsub} frames of this workload, oracle (NumPy/C port of '
+                              f'the reference tracker path), one process per core')
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
+            higher_is_better=True, scaling='weak', vs_baseline=None,
+            dtype='f32 (u16 disparity in, f64 Kalman state and assignment)', data='synthetic', config=config,
+            roofline=dict(kernel='k1_disp2depth_vec8', bound='hbm', achieved=k1_gbs, peak=peak, unit='GB/s',
+                          frac=k1_gbs / peak, traffic=None, peak_source=peak_src,
+                          note='HBM-bound kernel of the path (north_star); the per-stage table in "kernels" gives '
+                               'every stage\'s share of the step'),
+            kernels=kernels,
+            cpu_baseline=cpu,
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                     ms_per_step=e2e_ms / K),
+            gpu_launches=int(K * eng.KERNELS_PER_FRAME), clocks=clocks,
+            status_bits=int(status.max()), tracked_rows_last_step=tracked_rows)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

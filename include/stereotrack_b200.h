@@ -152,6 +152,35 @@ int st_track_step(st_handle *h, int S, const int32_t *frame_ids, const float *de
                   float *out_boxes, float *out_scores, int64_t *out_labels, float *out_scales,
                   float *out_depth, int64_t *out_ids, int32_t *out_counts, void *stream);
 
+/* All buffers of one lockstep frame (device pointers; host arrays where the name
+ * says so).  Capacities: every [S,cap,...] array has cap = st_config.max_dets. */
+typedef struct st_frame_io {
+    /* inputs */
+    const int32_t *frame_ids;          /* [S] */
+    const uint16_t *raw;               /* [S,H,W] or NULL when depth_map is already filled */
+    int32_t H, W, Hr, Wr, Hp, Wp;
+    const float *const *cls;           /* host arrays of num_levels device pointers, or NULL */
+    const float *const *bbox;          /*   when det_* already hold the detector output      */
+    const float *const *obj;
+    const int32_t *level_h, *level_w, *strides;   /* host */
+    int32_t num_levels, num_classes, ori_h, ori_w;
+    float scale_w, scale_h;
+    /* intermediates */
+    float *depth_map;                  /* [S,Hp,Wp] */
+    float *disp3;                      /* [S,3,Hp,Wp] or NULL */
+    uint8_t *mask;                     /* [S,Hp,Wp] or NULL */
+    float *det_boxes; float *det_scores; int64_t *det_labels; int32_t *det_prior; int32_t *det_keep;
+    int32_t *det_counts; float *det_depth; float *det_scales; float *det_inflated;
+    float *trk_boxes; float *trk_depth; float *out_scale2;
+    /* outputs = pred_track_instances fields */
+    float *out_boxes; float *out_scores; int64_t *out_labels; float *out_scales; float *out_depth;
+    int64_t *out_ids; int32_t *out_counts;
+} st_frame_io;
+
+/* The whole per-frame path for S sequences in one call (K1 -> K2 -> K3 -> K4/K5
+ * -> deflate -> K3); replaces ocsort_disparity.py:79-109 after the backbone. */
+int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *stream);
+
 /* Debug / parity / checkpoint: copies the live tracks of sequence `seq` in
  * dict order to HOST arrays sized max_tracks (synchronises).  mean [T,8] f64,
  * cov [T,64] f64, velocity [T,2] f32, flags [T] u8 (bit0 tentative, bit1

@@ -24,6 +24,21 @@ class StConfig(C.Structure):
         ('score_thr', C.c_float), ('nms_iou_thr', C.c_float)]
 
 
+class StFrameIO(C.Structure):
+    """st_frame_io of include/stereotrack_b200.h."""
+    _fields_ = (
+        [('frame_ids', C.c_void_p), ('raw', C.c_void_p)] +
+        [(n, C.c_int32) for n in ('H', 'W', 'Hr', 'Wr', 'Hp', 'Wp')] +
+        [(n, C.c_void_p) for n in ('cls', 'bbox', 'obj', 'level_h', 'level_w', 'strides')] +
+        [(n, C.c_int32) for n in ('num_levels', 'num_classes', 'ori_h', 'ori_w')] +
+        [('scale_w', C.c_float), ('scale_h', C.c_float)] +
+        [(n, C.c_void_p) for n in (
+            'depth_map', 'disp3', 'mask', 'det_boxes', 'det_scores', 'det_labels', 'det_prior',
+            'det_keep', 'det_counts', 'det_depth', 'det_scales', 'det_inflated', 'trk_boxes',
+            'trk_depth', 'out_scale2', 'out_boxes', 'out_scores', 'out_labels', 'out_scales',
+            'out_depth', 'out_ids', 'out_counts')])
+
+
 class StereoTrackError(RuntimeError):
     pass
 
@@ -48,6 +63,7 @@ _SIGNATURES = {
     'st_box_depth': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     'st_scale_boxes': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     'st_track_step': (_I, [_P, _I] + [_P] * 7 + [_I] + [_P] * 8),
+    'st_frame_step': (_I, [_P, _I, C.POINTER(StFrameIO), _P]),
     'st_export_state': (_I, [_P, _I] + [_P] * 8),
     'st_kalman_batch': (_I, [_I, _I, _P, _P, _P, _P]),
     'st_lapjv_batch': (_I, [_P, _I, _I, _I, _P, C.c_double, _P, _P, _P]),

@@ -212,6 +212,47 @@ class StereoTrackEngine:
         self.decode_nms(cls_l, bbox_l, obj_l, (H, W))
         self.step_from_dets(self.depth_map, frame_ids)
 
+    def make_frame_io(self, raw_shape, level_shapes, num_classes=1, resized_hw=None, scale_factor=(1.0, 1.0)):
+        """Prepare a reusable st_frame_io for inputs of the given shapes: raw
+        [S,H,W] and per-level head maps [S,C,h,w].  Pointers to the per-step inputs
+        are filled by ``frame_step``; everything else is bound once."""
+        S, H, W = raw_shape
+        Hr, Wr = resized_hw or (H, W)
+        Hp, Wp = -(-Hr // 32) * 32, -(-Wr // 32) * 32
+        if self.depth_map is None or tuple(self.depth_map.shape) != (S, Hp, Wp):
+            self.depth_map = torch.empty(S, Hp, Wp, dtype=torch.float32, device=self.device)
+        L = len(level_shapes)
+        io = _lib.StFrameIO()
+        keep = dict(cls=(C.c_void_p * L)(), bbox=(C.c_void_p * L)(), obj=(C.c_void_p * L)(),
+                    lh=(C.c_int32 * L)(*[s[0] for s in level_shapes]),
+                    lw=(C.c_int32 * L)(*[s[1] for s in level_shapes]),
+                    st=(C.c_int32 * L)(*self.cfg.strides[:L]))
+        io.frame_ids = self.frame_ids.data_ptr()
+        io.H, io.W, io.Hr, io.Wr, io.Hp, io.Wp = H, W, Hr, Wr, Hp, Wp
+        io.cls, io.bbox, io.obj = (C.cast(keep[k], C.c_void_p) for k in ('cls', 'bbox', 'obj'))
+        io.level_h, io.level_w, io.strides = (C.cast(keep[k], C.c_void_p) for k in ('lh', 'lw', 'st'))
+        io.num_levels, io.num_classes, io.ori_h, io.ori_w = L, num_classes, H, W
+        io.scale_w, io.scale_h = float(scale_factor[0]), float(scale_factor[1])
+        io.depth_map = self.depth_map.data_ptr()
+        for name in ('det_boxes', 'det_scores', 'det_labels', 'det_prior', 'det_keep', 'det_counts',
+                     'det_depth', 'det_scales', 'det_inflated', 'trk_boxes', 'trk_depth', 'out_scale2',
+                     'out_boxes', 'out_scores', 'out_labels', 'out_scales', 'out_depth', 'out_ids',
+                     'out_counts'):
+            setattr(io, name, getattr(self, name).data_ptr())
+        io._keep = keep
+        return io
+
+    def frame_step(self, io, raw, cls_l, bbox_l, obj_l):
+        """One lockstep frame through st_frame_step (a single C call, 9 kernel launches)."""
+        io.raw = raw.data_ptr()
+        for l in range(len(cls_l)):
+            io._keep['cls'][l] = cls_l[l].data_ptr()
+            io._keep['bbox'][l] = bbox_l[l].data_ptr()
+            io._keep['obj'][l] = obj_l[l].data_ptr()
+        _lib.check(self.lib.st_frame_step(self._h, raw.shape[0], C.byref(io), self._stream()), 'st_frame_step')
+
+    KERNELS_PER_FRAME = 9      # K1, K2 x4, K3, K4/K5, scale, K3
+
     def results(self):
         """Host copies of the current outputs, one dict per sequence."""
         n = self.out_counts.cpu().tolist()
