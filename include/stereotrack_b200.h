@@ -132,6 +132,7 @@ int st_decode_nms(st_handle *h, const float *const *cls_host, const float *const
  * (may be NULL). */
 int st_box_depth(const float *depth, int S, int Hp, int Wp, const float *boxes,
                  const int32_t *counts, int cap, float *d, float *scale, float *inflated,
+                 int32_t *workspace /* [2 + 2*S*cap] i32 scratch (worklist of large boxes) */,
                  void *stream);
 
 /* scale_bbox(boxes, 1/scales) (ocsort_disparity.py:96-97) or scale_bbox(boxes,
@@ -172,6 +173,7 @@ typedef struct st_frame_io {
     float *det_boxes; float *det_scores; int64_t *det_labels; int32_t *det_prior; int32_t *det_keep;
     int32_t *det_counts; float *det_depth; float *det_scales; float *det_inflated;
     float *trk_boxes; float *trk_depth; float *out_scale2;
+    int32_t *k3_workspace;             /* [2 + 2*S*cap] i32 scratch of st_box_depth */
     /* outputs = pred_track_instances fields */
     float *out_boxes; float *out_scores; int64_t *out_labels; float *out_scales; float *out_depth;
     int64_t *out_ids; int32_t *out_counts;

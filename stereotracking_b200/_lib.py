@@ -35,7 +35,7 @@ class StFrameIO(C.Structure):
         [(n, C.c_void_p) for n in (
             'depth_map', 'disp3', 'mask', 'det_boxes', 'det_scores', 'det_labels', 'det_prior',
             'det_keep', 'det_counts', 'det_depth', 'det_scales', 'det_inflated', 'trk_boxes',
-            'trk_depth', 'out_scale2', 'out_boxes', 'out_scores', 'out_labels', 'out_scales',
+            'trk_depth', 'out_scale2', 'k3_workspace', 'out_boxes', 'out_scores', 'out_labels', 'out_scales',
             'out_depth', 'out_ids', 'out_counts')])
 
 
@@ -60,7 +60,7 @@ _SIGNATURES = {
     'st_disp2depth': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_float, C.c_float, _P]),
     'st_decode_nms': (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, C.c_float, C.c_float, _I, _I, _I,
                            _P, _P, _P, _P, _P, _P, _P]),
-    'st_box_depth': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
+    'st_box_depth': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
     'st_scale_boxes': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     'st_track_step': (_I, [_P, _I] + [_P] * 7 + [_I] + [_P] * 8),
     'st_frame_step': (_I, [_P, _I, C.POINTER(StFrameIO), _P]),

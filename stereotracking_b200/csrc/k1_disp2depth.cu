@@ -24,87 +24,105 @@ __device__ __forceinline__ void st_stream_u2(uint2 *p, uint2 v) {
                  :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
+// Correctly rounded float32 reciprocal of x = raw/16 + 1e-6 without the XU
+// pipe (no MUFU): integer seed + four Newton steps in FMAs.  The input domain is
+// finite (raw in [0, 65534]); tests/test_k1_reciprocal.py checks every value
+// against IEEE division with exact rational arithmetic, and the GPU test feeds
+// all 65536 raw codes through the kernel.
+__device__ __forceinline__ float rcp_rn_fma(float x) {
+    float r = __uint_as_float(0x7EF311C7u - __float_as_uint(x));
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const float e = __fmaf_rn(-x, r, 1.0f);
+        r = __fmaf_rn(r, e, r);
+    }
+    return r;
+}
+
 // raw u16 -> (disp px, depth m, valid).  disp = raw/16 with 65535 -> 0
 // (loading_disparity.py:129-134); depth = reciprocal(disp + 1e-6) * (B*f),
 // torch's evaluation of `B*f / (disp + 1e-6)` (Tensor.__rtruediv__).
+// The u16 -> f32 conversion uses the 2^23 mantissa trick instead of I2F: the
+// profile of the first version showed the XU pipe (I2F + MUFU.RCP) 94 % busy.
 __device__ __forceinline__ void convert(uint32_t raw, float bf, float &disp, float &depth,
                                         uint32_t &valid) {
     valid = raw < 65535u;
-    disp = valid ? __fmul_rn((float)raw, 0.0625f) : 0.0f;
-    depth = __fmul_rn(__frcp_rn(__fadd_rn(disp, 1e-6f)), bf);
+    const float fr = __fsub_rn(__uint_as_float(0x4B000000u | raw), 8388608.0f);   // exact (float)raw
+    disp = valid ? __fmul_rn(fr, 0.0625f) : 0.0f;
+    depth = __fmul_rn(rcp_rn_fma(__fadd_rn(disp, 1e-6f)), bf);
 }
 
+constexpr int kUnroll = 4;    // independent 128-bit loads in flight per thread
+constexpr unsigned kChunk = 256 * kUnroll;   // work items per CTA iteration
+
 // Fast path: no resize, W and Wp multiples of 8, 16-byte aligned rows.
-// One work item = 8 consecutive pixels of one padded output row.
+// A work item is 8 consecutive pixels of a padded output row (one 128-bit
+// load, two 128-bit depth stores); a CTA iteration covers kChunk consecutive
+// items of one image, so consecutive threads touch consecutive 16-byte words.
+// All index arithmetic is 32-bit.
 template <bool kDisp3, bool kMask>
 __global__ void __launch_bounds__(256)
 k1_disp2depth_vec8(const uint16_t *__restrict__ raw, int S, int H, int W, int Hp, int Wp,
                    float *__restrict__ depth, float *__restrict__ disp3,
-                   uint8_t *__restrict__ mask, float bf) {
-    const int w8 = W >> 3, wp8 = Wp >> 3;
-    const long long items = (long long)S * Hp * wp8;
-    const long long plane = (long long)Hp * Wp;
-    const float pad_depth = __fmul_rn(__frcp_rn(1e-6f), bf);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    constexpr int U = 4;
-    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < items;
-         base += stride * U) {
-        uint4 v[U];
-        bool inside[U];
-        long long oidx[U];
-        int sidx[U];
+                   uint8_t *__restrict__ mask, float bf, unsigned long long div_magic) {
+    const unsigned w8 = W >> 3, wp8 = Wp >> 3;
+    const unsigned items = (unsigned)Hp * wp8;
+    const unsigned chunks_per_img = (items + kChunk - 1) / kChunk;
+    const unsigned total_chunks = (unsigned)S * chunks_per_img;
+    const size_t plane = (size_t)Hp * Wp;
+    const float pad_depth = __fmul_rn(rcp_rn_fma(1e-6f), bf);
+    for (unsigned chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+        const unsigned s = chunk / chunks_per_img;
+        const unsigned base = (chunk - s * chunks_per_img) * kChunk + threadIdx.x;
+        const uint16_t *src = raw + (size_t)s * H * W;
+        float *dst = depth + (size_t)s * plane;
+        {
+            uint4 v[kUnroll];
+            unsigned off[kUnroll];          // element offset inside the padded image
+            bool live[kUnroll], inside[kUnroll];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            long long it = base + u * stride;
-            inside[u] = false;
-            oidx[u] = -1;
-            if (it < items) {
-                int x8 = (int)(it % wp8);
-                long long t = it / wp8;
-                int y = (int)(t % Hp);
-                int s = (int)(t / Hp);
-                sidx[u] = s;
-                oidx[u] = ((long long)s * Hp + y) * Wp + (long long)x8 * 8;
-                inside[u] = (y < H) && (x8 < w8);
-                if (inside[u])
-                    v[u] = ld_stream_u4(reinterpret_cast<const uint4 *>(
-                        raw + ((long long)s * H + y) * W + (long long)x8 * 8));
+            for (int u = 0; u < kUnroll; ++u) {
+                const unsigned li = base + u * 256;
+                // li / wp8 as a multiply-high (exact for li < 2^24, wp8 < 2^16): no I2F/MUFU
+                const unsigned y = (unsigned)(((unsigned long long)li * div_magic) >> 40), x8 = li - y * wp8;
+                live[u] = li < items;
+                inside[u] = live[u] && y < (unsigned)H && x8 < w8;
+                off[u] = li * 8;
+                if (inside[u]) v[u] = ld_stream_u4(reinterpret_cast<const uint4 *>(src + (size_t)y * W + x8 * 8));
             }
-        }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (oidx[u] < 0) continue;
-            float dz[8], dp[8];
-            uint32_t mk[8];
-            if (inside[u]) {
-                uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            for (int u = 0; u < kUnroll; ++u) {
+                if (!live[u]) continue;
+                float dz[8], dp[8];
+                uint32_t mk[8];
+                if (inside[u]) {
+                    const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    convert(w[k] & 0xffffu, bf, dp[2 * k], dz[2 * k], mk[2 * k]);
-                    convert(w[k] >> 16, bf, dp[2 * k + 1], dz[2 * k + 1], mk[2 * k + 1]);
+                    for (int k = 0; k < 4; ++k) {
+                        convert(w[k] & 0xffffu, bf, dp[2 * k], dz[2 * k], mk[2 * k]);
+                        convert(w[k] >> 16, bf, dp[2 * k + 1], dz[2 * k + 1], mk[2 * k + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { dz[k] = pad_depth; dp[k] = 0.0f; mk[k] = 0; }
                 }
-            } else {
+                float4 *o = reinterpret_cast<float4 *>(dst + off[u]);
+                st_stream_f4(o, make_float4(dz[0], dz[1], dz[2], dz[3]));
+                st_stream_f4(o + 1, make_float4(dz[4], dz[5], dz[6], dz[7]));
+                if (kDisp3) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { dz[k] = pad_depth; dp[k] = 0.0f; mk[k] = 0; }
-            }
-            float4 *o = reinterpret_cast<float4 *>(depth + oidx[u]);
-            st_stream_f4(o, make_float4(dz[0], dz[1], dz[2], dz[3]));
-            st_stream_f4(o + 1, make_float4(dz[4], dz[5], dz[6], dz[7]));
-            if (kDisp3) {
-                long long pix = oidx[u] - (long long)sidx[u] * plane;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float4 *q = reinterpret_cast<float4 *>(
-                        disp3 + ((long long)sidx[u] * 3 + c) * plane + pix);
-                    st_stream_f4(q, make_float4(dp[0], dp[1], dp[2], dp[3]));
-                    st_stream_f4(q + 1, make_float4(dp[4], dp[5], dp[6], dp[7]));
+                    for (int c = 0; c < 3; ++c) {
+                        float4 *q = reinterpret_cast<float4 *>(disp3 + ((size_t)s * 3 + c) * plane + off[u]);
+                        st_stream_f4(q, make_float4(dp[0], dp[1], dp[2], dp[3]));
+                        st_stream_f4(q + 1, make_float4(dp[4], dp[5], dp[6], dp[7]));
+                    }
                 }
-            }
-            if (kMask) {
-                uint2 m;
-                m.x = mk[0] | (mk[1] << 8) | (mk[2] << 16) | (mk[3] << 24);
-                m.y = mk[4] | (mk[5] << 8) | (mk[6] << 16) | (mk[7] << 24);
-                st_stream_u2(reinterpret_cast<uint2 *>(mask + oidx[u]), m);
+                if (kMask) {
+                    uint2 m;
+                    m.x = mk[0] | (mk[1] << 8) | (mk[2] << 16) | (mk[3] << 24);
+                    m.y = mk[4] | (mk[5] << 8) | (mk[6] << 16) | (mk[7] << 24);
+                    st_stream_u2(reinterpret_cast<uint2 *>(mask + (size_t)s * plane + off[u]), m);
+                }
             }
         }
     }
@@ -143,15 +161,11 @@ k1_disp2depth_generic(const uint16_t *__restrict__ raw, int S, int H, int W, int
     }
 }
 
-int grid_for(long long threads_needed, int block) {
+int sm_count() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long blocks = (threads_needed + block - 1) / block;
-    long long cap = (long long)sms * 8;          // 8 resident CTAs of 256 threads per SM
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
+    return sms;
 }
 
 }  // namespace
@@ -167,21 +181,27 @@ extern "C" int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, i
     const bool aligned = ((uintptr_t)raw % 16 == 0) && ((uintptr_t)depth % 16 == 0) &&
                          (!disp3 || (uintptr_t)disp3 % 16 == 0) &&
                          (!mask || (uintptr_t)mask % 8 == 0);
-    if (Hr == H && Wr == W && (W % 8 == 0) && (Wp % 8 == 0) && aligned) {
-        long long items = (long long)S * Hp * (Wp / 8);
-        int grid = grid_for((items + 3) / 4, 256);
+    const bool small = (long long)Hp * (Wp / 8) < (1ll << 24) && Wp / 8 < 65536 && (long long)H * W < (1ll << 31);
+    const unsigned long long magic = ((1ull << 40) + (unsigned long long)(Wp / 8) - 1) / (unsigned long long)(Wp / 8);
+    if (Hr == H && Wr == W && (W % 8 == 0) && (Wp % 8 == 0) && aligned && small) {
+        const long long tiles = (long long)S * (((long long)Hp * (Wp / 8) + kChunk - 1) / kChunk);
+        // grid = a multiple of the SM count: 8 resident CTAs of 256 threads per SM
+        long long grid = (long long)sm_count() * 8;
+        if (grid > tiles) grid = tiles;
         if (disp3 && mask)
-            k1_disp2depth_vec8<true, true><<<grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf);
+            k1_disp2depth_vec8<true, true><<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf, magic);
         else if (disp3)
-            k1_disp2depth_vec8<true, false><<<grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf);
+            k1_disp2depth_vec8<true, false><<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf, magic);
         else if (mask)
-            k1_disp2depth_vec8<false, true><<<grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf);
+            k1_disp2depth_vec8<false, true><<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf, magic);
         else
-            k1_disp2depth_vec8<false, false><<<grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf);
+            k1_disp2depth_vec8<false, false><<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf, magic);
     } else {
-        long long total = (long long)S * Hp * Wp;
-        int grid = grid_for(total, 256);
-        k1_disp2depth_generic<<<grid, 256, 0, st>>>(raw, S, H, W, Hr, Wr, Hp, Wp, depth, disp3, mask, bf);
+        const long long total = (long long)S * Hp * Wp;
+        long long grid = (total + 255) / 256;
+        const long long cap = (long long)sm_count() * 8;
+        if (grid > cap) grid = cap;
+        k1_disp2depth_generic<<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hr, Wr, Hp, Wp, depth, disp3, mask, bf);
     }
     return st_last_launch();
 }

@@ -1,4 +1,4 @@
-// K3: per-box depth statistic + depth-driven box scale, one CTA per box.
+// K3: per-box depth statistic + depth-driven box scale, one WARP per box.
 // Replaces OCSORT_Disparity.extract_depth / bbox_postp_depth
 // (mmtrack/models/mot/ocsort_disparity.py:113-130,:136-175) and scale_bbox
 // (mmtrack/models/trackers/utils.py:58-73).
@@ -7,15 +7,19 @@
 // the sorted list whose position is voted by the four box corners.  Here the
 // three order statistics that define the result (median, first and last element
 // of the window) are found with an MSB-first radix select over the float bit
-// patterns using shared-memory histograms; the window sum is then one masked
-// pass (values strictly between the two boundary values, plus the boundary
-// values weighted by how many of their duplicates fall inside the window).
+// patterns using per-warp shared-memory histograms (8 bits per pass); the
+// window sum is then one masked pass (values strictly between the two boundary
+// values, plus the boundary values weighted by how many of their duplicates
+// fall inside the window).  Boxes are small (airborne objects), so a warp per
+// box with the valid depths staged in shared memory keeps every pass on-chip;
+// boxes with more valid pixels than the stage re-read the map (L1/L2).
 #include "st_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kStage = 4096;             // valid depths staged in shared memory
+constexpr int kWarps = 4;                // boxes per CTA
+constexpr int kStage = 2048;             // valid depths staged per warp
+constexpr int kSmallPix = 2048;          // boxes up to this many pixels: one warp; larger: one CTA
 
 struct Slice { int lo, hi; };            // hi <= lo means empty
 
@@ -60,22 +64,280 @@ struct BoxCtx {
     const float *dm;      // depth map of this sequence
     int Wp;
     Slice ys, xs;
-    int bw, bh, npix;
+    unsigned bw, npix;
     const float *staged;  // valid values in shared memory (when n_valid <= kStage)
     int n_valid;
     bool use_stage;
 };
 
+// visit every valid depth value of the box with the 32 lanes of the warp
+template <typename F>
+__device__ __forceinline__ void for_each_valid(const BoxCtx &c, int lane, F f) {
+    if (c.use_stage) {
+        for (int i = lane; i < c.n_valid; i += 32) f(c.staged[i]);
+    } else {
+        for (unsigned i = lane; i < c.npix; i += 32) {
+            const unsigned ry = i / c.bw, rx = i - ry * c.bw;
+            const float v = c.dm[(long long)(c.ys.lo + ry) * c.Wp + c.xs.lo + rx];
+            if (depth_valid(v)) f(v);
+        }
+    }
+}
+
+// Radix select of up to two ranks at once over positive-float bit patterns, one
+// warp.  value[k] = element of rank rank_in[k] (ascending), below[k] = number of
+// elements strictly smaller.  hist = 512 ints of this warp's shared memory.
+__device__ void radix_select2(const BoxCtx &c, int lane, int nsel, const int *rank_in, uint32_t *value,
+                              int *below, int *hist) {
+    uint32_t prefix[2] = {0u, 0u};
+    int rank[2] = {rank_in[0], nsel > 1 ? rank_in[1] : 0};
+    int less[2] = {0, 0};
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = lane; i < 512; i += 32) hist[i] = 0;
+        __syncwarp();
+        const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        const uint32_t p0 = prefix[0], p1 = prefix[1];
+        for_each_valid(c, lane, [&](float v) {
+            const uint32_t u = __float_as_uint(v);
+            // one shared-memory atomic per distinct bin among the active lanes
+            // (object pixels share one depth, so plain atomics would serialise)
+            int bin = -1;
+            if ((u & himask) == p0) bin = (u >> shift) & 255u;
+            else if (nsel > 1 && (u & himask) == p1) bin = 256 + ((u >> shift) & 255u);
+            const unsigned peers = __match_any_sync(__activemask(), bin);
+            if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+            if (nsel > 1 && bin >= 0 && bin < 256 && (u & himask) == p1) {
+                const int bin1 = 256 + ((u >> shift) & 255u);
+                atomicAdd(&hist[bin1], 1);
+            }
+        });
+        __syncwarp();
+        for (int k = 0; k < nsel; ++k) {
+            // lane owns bins [8*lane, 8*lane+8); exclusive scan of the lane totals
+            int local[8], tot = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { local[b] = hist[k * 256 + lane * 8 + b]; tot += local[b]; }
+            int inc = tot;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int acc = inc - tot;                 // elements in bins before this lane's
+            int found_bin = -1, found_acc = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (found_bin < 0 && acc + local[b] > rank[k]) { found_bin = lane * 8 + b; found_acc = acc; }
+                acc += local[b];
+            }
+            const unsigned who = __ballot_sync(0xffffffffu, found_bin >= 0);
+            const int src = __ffs(who) - 1;      // lowest lane that contains the rank
+            found_bin = __shfl_sync(0xffffffffu, found_bin, src);
+            found_acc = __shfl_sync(0xffffffffu, found_acc, src);
+            prefix[k] |= (uint32_t)found_bin << shift;
+            rank[k] -= found_acc;
+            less[k] += found_acc;
+        }
+        __syncwarp();
+    }
+    for (int k = 0; k < nsel; ++k) { value[k] = prefix[k]; below[k] = less[k]; }
+}
+
+// MSB-first binary search on the bit patterns of the staged values (one warp,
+// no histogram, no atomics): per bit one pass over shared memory and one
+// redux.  Same contract as radix_select2.
+__device__ void bit_select2(const float *staged, int n, int lane, int nsel, const int *rank_in,
+                            uint32_t *value, int *below) {
+    // bits above the highest differing bit are common to every value
+    uint32_t vor = 0u, vand = 0xffffffffu;
+    for (int i = lane; i < n; i += 32) { const uint32_t u = __float_as_uint(staged[i]); vor |= u; vand &= u; }
+    vor = __reduce_or_sync(0xffffffffu, vor);
+    vand = __reduce_and_sync(0xffffffffu, vand);
+    const uint32_t diff = vor ^ vand;
+    const int top = diff ? 31 - __clz(diff) : -1;          // highest bit that varies
+    const uint32_t common = top >= 31 ? 0u : (top < 0 ? vand : (vand & ~((2u << top) - 1u)));
+    uint32_t prefix[2] = {common, common};
+    int rank[2] = {rank_in[0], nsel > 1 ? rank_in[1] : 0};
+    int less[2] = {0, 0};
+    for (int bit = top; bit >= 0; --bit) {
+        const uint32_t hi = ~((2u << bit) - 1u);            // bits above `bit`
+        int c0 = 0, c1 = 0;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t u = __float_as_uint(staged[i]);
+            const bool zero = !((u >> bit) & 1u);
+            c0 += zero && ((u & hi) == prefix[0]);
+            c1 += zero && ((u & hi) == prefix[1]);
+        }
+        c0 = __reduce_add_sync(0xffffffffu, c0);
+        if (rank[0] >= c0) { rank[0] -= c0; less[0] += c0; prefix[0] |= 1u << bit; }
+        if (nsel > 1) {
+            c1 = __reduce_add_sync(0xffffffffu, c1);
+            if (rank[1] >= c1) { rank[1] -= c1; less[1] += c1; prefix[1] |= 1u << bit; }
+        }
+    }
+    for (int k = 0; k < nsel; ++k) { value[k] = prefix[k]; below[k] = less[k]; }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
+             const int32_t *__restrict__ counts, int cap, float *__restrict__ d_out,
+             float *__restrict__ scale_out, float *__restrict__ inflated, int32_t *__restrict__ worklist) {
+    __shared__ float staged_all[kWarps][kStage];
+    __shared__ int hist_all[kWarps][512];
+    const int s = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bi = blockIdx.x * kWarps + warp;
+    if (bi >= counts[s] || bi >= cap) return;          // warp-uniform
+    float *staged = staged_all[warp];
+    int *hist = hist_all[warp];
+
+    const long long o = (long long)s * cap + bi;
+    const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
+    const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
+    BoxCtx c;
+    c.dm = depth + (long long)s * Hp * Wp;
+    c.Wp = Wp;
+    c.ys = py_slice(b1, b3, Hp);
+    c.xs = py_slice(b0, b2, Wp);
+    c.bw = (unsigned)max(c.xs.hi - c.xs.lo, 0);
+    c.npix = c.bw * (unsigned)max(c.ys.hi - c.ys.lo, 0);
+    if (c.npix > (unsigned)kSmallPix) {                 // handled by k3_box_depth_large
+        if (lane == 0) {
+            const int slot = atomicAdd(&worklist[0], 1);
+            worklist[2 + 2 * slot] = s;
+            worklist[3 + 2 * slot] = bi;
+        }
+        return;
+    }
+    c.staged = staged;
+    c.use_stage = true;
+    // pass 0: count the valid values, staging them (npix <= kSmallPix = kStage always fits)
+    int n = 0;
+    for (unsigned i0 = 0; i0 < c.npix; i0 += 128) {
+        float v[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {              // four independent loads in flight
+            const unsigned i = i0 + u * 32 + lane;
+            v[u] = 0.f;
+            ok[u] = false;
+            if (i < c.npix) {
+                const unsigned ry = i / c.bw, rx = i - ry * c.bw;
+                v[u] = c.dm[(long long)(c.ys.lo + ry) * Wp + c.xs.lo + rx];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ok[u] = (i0 + u * 32 + lane < c.npix) && depth_valid(v[u]);
+            const unsigned m = __ballot_sync(0xffffffffu, ok[u]);
+            const int pos = n + __popc(m & ((1u << lane) - 1u));
+            if (ok[u] && pos < kStage) staged[pos] = v[u];
+            n += __popc(m);
+        }
+    }
+    __syncwarp();
+    c.n_valid = n;
+    if (n > kStage) c.use_stage = false;
+    // (box[2]-box[0]) > 800 in int64; wraps like NumPy for the INT64_MIN case
+    const long long wbox = wrap_add(b2, (long long)(0ull - (unsigned long long)b0));
+
+    float d = -1.f, scale = 1.f;
+    if (!(n < 1 || wbox > 800)) {
+        uint32_t val[2];
+        int below[2];
+        int rk[2] = {n / 2, 0};
+        if (c.use_stage) bit_select2(staged, n, lane, 1, rk, val, below);
+        else radix_select2(c, lane, 1, rk, val, below, hist);
+        const float d_mid = __uint_as_float(val[0]);
+        // corner votes on the unfiltered map (:157-160)
+        int k = 0;
+        {
+            Slice ytop = py_slice(b1, wrap_add(b1, 2), Hp), ybot = py_slice(wrap_add(b3, -2), b3, Hp);
+            Slice xl = py_slice(b0, wrap_add(b0, 2), Wp), xr = py_slice(wrap_add(b2, -2), b2, Wp);
+            k += corner_mean(c.dm, Wp, ytop, xl) > d_mid;
+            k += corner_mean(c.dm, Wp, ytop, xr) > d_mid;
+            k += corner_mean(c.dm, Wp, ybot, xl) > d_mid;
+            k += corner_mean(c.dm, Wp, ybot, xr) > d_mid;
+        }
+        // w_start = min(1 - k/4, 0.4) * len ; w_end = w_start + 0.6 * len   (float64)
+        const double frac = fmin(1.0 - (double)k / 4.0, 0.4);
+        const double w_start = __dmul_rn(frac, (double)n);
+        const double w_end = __dadd_rn(w_start, __dmul_rn(0.6, (double)n));
+        Slice seg = py_slice((long long)w_start, (long long)w_end, n);
+        if (seg.hi <= seg.lo) seg = py_slice(0, -1, n);       // d_sorted[:-1]
+        const int m = seg.hi - seg.lo;
+        if (m <= 0) {
+            d = __int_as_float(0x7fc00000);                    // mean of empty -> NaN
+        } else {
+            rk[0] = seg.lo; rk[1] = seg.hi - 1;
+            if (c.use_stage) bit_select2(staged, n, lane, 2, rk, val, below);
+            else radix_select2(c, lane, 2, rk, val, below, hist);
+            const uint32_t ua = val[0], ub = val[1];
+            double sum;
+            if (ua == ub) {
+                sum = (double)__uint_as_float(ua) * (double)m;
+            } else {
+                double part = 0.0;
+                int eq_a = 0;
+                for_each_valid(c, lane, [&](float v) {
+                    const uint32_t u = __float_as_uint(v);
+                    if (u > ua && u < ub) part += (double)v;
+                    eq_a += (u == ua);
+                });
+                sum = warp_sum(part);
+                const int n_eq_a = __reduce_add_sync(0xffffffffu, eq_a);
+                const int in_a = below[0] + n_eq_a - seg.lo;   // duplicates of s[lo] inside
+                const int in_b = seg.hi - below[1];            // duplicates of s[hi-1] inside
+                sum += (double)__uint_as_float(ua) * (double)in_a + (double)__uint_as_float(ub) * (double)in_b;
+            }
+            d = (float)(sum / (double)m);
+        }
+        // scale = max(min(d*d/1, 3.), 1.) with Python min/max NaN behaviour
+        const float dd = __fmul_rn(d, d);
+        scale = (dd != dd) ? dd : fmaxf(fminf(dd, 3.f), 1.f);
+    }
+    if (lane == 0) {
+        d_out[o] = d;
+        scale_out[o] = scale;
+        if (inflated) {
+            // scale_bbox (trackers/utils.py:58-73), float32, unfused
+            const float cx = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
+            const float cy = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
+            const float hw = __fmul_rn(__fmul_rn(__fsub_rn(box.z, box.x), scale), 0.5f);
+            const float hh = __fmul_rn(__fmul_rn(__fsub_rn(box.w, box.y), scale), 0.5f);
+            reinterpret_cast<float4 *>(inflated)[o] =
+                make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+        }
+    }
+}
+
+constexpr int kCtaThreads = 512;         // large boxes: one CTA per box
+constexpr int kCtaStage = 45056;         // floats of dynamic shared memory (176 KB, one CTA per SM)
+
 // visit every valid depth value of the box: f(value)
 template <typename F>
-__device__ __forceinline__ void for_each_valid(const BoxCtx &c, F f) {
+__device__ __forceinline__ void for_each_valid_cta(const BoxCtx &c, F f) {
     if (c.use_stage) {
-        for (int i = threadIdx.x; i < c.n_valid; i += kThreads) f(c.staged[i]);
+        for (int i = threadIdx.x; i < c.n_valid; i += kCtaThreads) f(c.staged[i]);
     } else {
-        for (int i = threadIdx.x; i < c.npix; i += kThreads) {
-            int y = c.ys.lo + i / c.bw, x = c.xs.lo + i % c.bw;
-            float v = c.dm[(long long)y * c.Wp + x];
-            if (depth_valid(v)) f(v);
+        for (unsigned i0 = threadIdx.x; i0 < c.npix; i0 += 4 * kCtaThreads) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {           // four independent loads in flight
+                const unsigned i = i0 + u * kCtaThreads;
+                v[u] = -1.f;
+                if (i < c.npix) {
+                    const unsigned ry = i / c.bw, rx = i - ry * c.bw;
+                    v[u] = c.dm[(long long)(c.ys.lo + ry) * c.Wp + c.xs.lo + rx];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (depth_valid(v[u])) f(v[u]);
         }
     }
 }
@@ -83,20 +345,30 @@ __device__ __forceinline__ void for_each_valid(const BoxCtx &c, F f) {
 // Radix select of up to two ranks at once over positive-float bit patterns.
 // On return value[k] is the element of rank rank[k] in ascending order and
 // below[k] the number of elements strictly smaller than it.
-__device__ void radix_select2(const BoxCtx &c, int nsel, const int *rank_in, uint32_t *value,
+__device__ void radix_select2_cta(const BoxCtx &c, int nsel, const int *rank_in, uint32_t *value,
                               int *below, int *hist /* [2*256] shared */, int *sh /* [8] shared */) {
     uint32_t prefix[2] = {0u, 0u};
     int rank[2] = {rank_in[0], nsel > 1 ? rank_in[1] : 0};
     int less[2] = {0, 0};
     for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 512; i += kThreads) hist[i] = 0;
+        for (int i = threadIdx.x; i < 512; i += kCtaThreads) hist[i] = 0;
         __syncthreads();
         const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
         const uint32_t p0 = prefix[0], p1 = prefix[1];
-        for_each_valid(c, [&](float v) {
-            uint32_t u = __float_as_uint(v);
-            if ((u & himask) == p0) atomicAdd(&hist[(u >> shift) & 255u], 1);
-            if (nsel > 1 && (u & himask) == p1) atomicAdd(&hist[256 + ((u >> shift) & 255u)], 1);
+        for_each_valid_cta(c, [&](float v) {
+            // one shared-memory atomic per distinct bin among the active lanes of a
+            // warp: object pixels share one depth and would serialise otherwise
+            const uint32_t u = __float_as_uint(v);
+            const int lane_ = threadIdx.x & 31;
+            const int bin0 = ((u & himask) == p0) ? (int)((u >> shift) & 255u) : -1;
+            const unsigned act = __activemask();
+            const unsigned peers0 = __match_any_sync(act, bin0);
+            if (bin0 >= 0 && lane_ == __ffs(peers0) - 1) atomicAdd(&hist[bin0], __popc(peers0));
+            if (nsel > 1) {
+                const int bin1 = ((u & himask) == p1) ? (int)((u >> shift) & 255u) : -1;
+                const unsigned peers1 = __match_any_sync(act, bin1);
+                if (bin1 >= 0 && lane_ == __ffs(peers1) - 1) atomicAdd(&hist[256 + bin1], __popc(peers1));
+            }
         });
         __syncthreads();
         if (threadIdx.x < nsel) {
@@ -121,13 +393,13 @@ __device__ void radix_select2(const BoxCtx &c, int nsel, const int *rank_in, uin
     for (int k = 0; k < nsel; ++k) { value[k] = prefix[k]; below[k] = less[k]; }
 }
 
-__device__ double block_sum(double v, double *red /* [kThreads/32] shared */) {
+__device__ double block_sum(double v, double *red /* [kCtaThreads/32] shared */) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double t = 0.0;
-    for (int w = 0; w < kThreads / 32; ++w) t += red[w];
+    for (int w = 0; w < kCtaThreads / 32; ++w) t += red[w];
     return t;
 }
 
@@ -137,21 +409,24 @@ __device__ int block_count(int v, int *red) {
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     int t = 0;
-    for (int w = 0; w < kThreads / 32; ++w) t += red[w];
+    for (int w = 0; w < kCtaThreads / 32; ++w) t += red[w];
     return t;
 }
 
-__global__ void __launch_bounds__(kThreads)
-k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
-             const int32_t *__restrict__ counts, int cap, float *__restrict__ d_out,
-             float *__restrict__ scale_out, float *__restrict__ inflated) {
-    const int s = blockIdx.y, bi = blockIdx.x;
-    if (bi >= counts[s]) return;
-    __shared__ float staged[kStage];
+__global__ void __launch_bounds__(kCtaThreads)
+k3_box_depth_large(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
+             int cap, float *__restrict__ d_out, float *__restrict__ scale_out,
+             float *__restrict__ inflated, const int32_t *__restrict__ worklist) {
+  const int n_work = worklist[0];
+  for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
+    __syncthreads();                                   // shared memory is reused across items
+    const int s = worklist[2 + 2 * item], bi = worklist[3 + 2 * item];
+    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) float staged[];    // [kCtaStage]
     __shared__ int hist[512];
     __shared__ int sh[8];
-    __shared__ int ired[kThreads / 32];
-    __shared__ double dred[kThreads / 32];
+    __shared__ int ired[kCtaThreads / 32];
+    __shared__ double dred[kCtaThreads / 32];
     __shared__ int stage_fill;
 
     const long long o = (long long)s * cap + bi;
@@ -162,39 +437,56 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
     c.Wp = Wp;
     c.ys = py_slice(b1, b3, Hp);
     c.xs = py_slice(b0, b2, Wp);
-    c.bw = max(c.xs.hi - c.xs.lo, 0);
-    c.bh = max(c.ys.hi - c.ys.lo, 0);
-    c.npix = c.bw * c.bh;
+    c.bw = (unsigned)max(c.xs.hi - c.xs.lo, 0);
+    c.npix = c.bw * (unsigned)max(c.ys.hi - c.ys.lo, 0);
     c.staged = staged;
     c.use_stage = false;
-    // pass 0: count valid values (and stage them when they fit)
-    int local = 0;
-    for (int i = threadIdx.x; i < c.npix; i += kThreads) {
-        int y = c.ys.lo + i / c.bw, x = c.xs.lo + i % c.bw;
-        local += depth_valid(c.dm[(long long)y * Wp + x]);
-    }
-    const int n = block_count(local, ired);
-    c.n_valid = n;
     // (box[2]-box[0]) > 800 in int64; wraps like NumPy for the INT64_MIN case
     const long long wbox = wrap_add(b2, (long long)(0ull - (unsigned long long)b0));
+    int n = 0;
+    if (!(wbox > 800)) {
+        // pass 0: count the valid values and stage the first kCtaStage of them
+        // (warp-aggregated append; the order inside the stage is irrelevant)
+        if (threadIdx.x == 0) stage_fill = 0;
+        __syncthreads();
+        for (unsigned i0 = threadIdx.x; i0 < c.npix; i0 += 4 * kCtaThreads) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned i = i0 + u * kCtaThreads;
+                v[u] = -1.f;
+                if (i < c.npix) {
+                    const unsigned ry = i / c.bw, rx = i - ry * c.bw;
+                    v[u] = c.dm[(long long)(c.ys.lo + ry) * Wp + c.xs.lo + rx];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = depth_valid(v[u]);
+                const unsigned act = __activemask();
+                const unsigned m = __ballot_sync(act, ok);
+                int base = 0;
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    if (lane == leader) base = atomicAdd(&stage_fill, __popc(m));
+                    base = __shfl_sync(act, base, leader);
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (ok && pos < kCtaStage) staged[pos] = v[u];
+                }
+            }
+        }
+        __syncthreads();
+        n = stage_fill;
+        c.use_stage = n <= kCtaStage;
+    }
+    c.n_valid = n;
 
     float d = -1.f, scale = 1.f;
     if (!(n < 1 || wbox > 800)) {
-        if (n <= kStage) {
-            if (threadIdx.x == 0) stage_fill = 0;
-            __syncthreads();
-            for (int i = threadIdx.x; i < c.npix; i += kThreads) {
-                int y = c.ys.lo + i / c.bw, x = c.xs.lo + i % c.bw;
-                float v = c.dm[(long long)y * Wp + x];
-                if (depth_valid(v)) staged[atomicAdd(&stage_fill, 1)] = v;
-            }
-            __syncthreads();
-            c.use_stage = true;
-        }
         uint32_t val[2];
         int below[2];
         int rk[2] = {n / 2, 0};
-        radix_select2(c, 1, rk, val, below, hist, sh);
+        radix_select2_cta(c, 1, rk, val, below, hist, sh);
         const float d_mid = __uint_as_float(val[0]);
         // corner votes on the unfiltered map (:157-160)
         int k = 0;
@@ -217,7 +509,7 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
             d = __int_as_float(0x7fc00000);                    // mean of empty -> NaN
         } else {
             rk[0] = seg.lo; rk[1] = seg.hi - 1;
-            radix_select2(c, 2, rk, val, below, hist, sh);
+            radix_select2_cta(c, 2, rk, val, below, hist, sh);
             const uint32_t ua = val[0], ub = val[1];
             double sum;
             if (ua == ub) {
@@ -225,7 +517,7 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
             } else {
                 double part = 0.0;
                 int eq_a = 0;
-                for_each_valid(c, [&](float v) {
+                for_each_valid_cta(c, [&](float v) {
                     uint32_t u = __float_as_uint(v);
                     if (u > ua && u < ub) part += (double)v;
                     eq_a += (u == ua);
@@ -255,6 +547,7 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
                 make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
         }
     }
+  }
 }
 
 __global__ void k3_scale_boxes(const float *__restrict__ boxes, const float *__restrict__ scales,
@@ -262,7 +555,7 @@ __global__ void k3_scale_boxes(const float *__restrict__ boxes, const float *__r
                                float *__restrict__ out) {
     const int s = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= counts[s]) return;
+    if (i >= counts[s] || i >= cap) return;
     const long long o = (long long)s * cap + i;
     const float4 b = reinterpret_cast<const float4 *>(boxes)[o];
     float sc = scales[o];
@@ -279,12 +572,24 @@ __global__ void k3_scale_boxes(const float *__restrict__ boxes, const float *__r
 
 extern "C" int st_box_depth(const float *depth, int S, int Hp, int Wp, const float *boxes,
                             const int32_t *counts, int cap, float *d, float *scale,
-                            float *inflated, void *stream) {
-    if (!depth || !boxes || !counts || !d || !scale || S < 0 || cap < 1 || Hp < 1 || Wp < 1)
+                            float *inflated, int32_t *workspace, void *stream) {
+    if (!depth || !boxes || !counts || !d || !scale || !workspace || S < 0 || cap < 1 || Hp < 1 || Wp < 1)
         return ST_ERR_INVALID_ARG;
     if (S == 0) return ST_OK;
-    k3_box_depth<<<dim3(cap, S), kThreads, 0, (cudaStream_t)stream>>>(depth, Hp, Wp, boxes, counts, cap, d,
-                                                                      scale, inflated);
+    ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 2, (cudaStream_t)stream));
+    k3_box_depth<<<dim3((cap + kWarps - 1) / kWarps, S), kWarps * 32, 0, (cudaStream_t)stream>>>(
+        depth, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace);
+    static bool smem_opt_in = false;
+    if (!smem_opt_in) {
+        ST_CUDA_OK(cudaFuncSetAttribute(k3_box_depth_large, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(float) * kCtaStage)));
+        smem_opt_in = true;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    // persistent: one CTA per SM (the stage takes most of its shared memory) loops over the worklist
+    k3_box_depth_large<<<sms > 0 ? sms : 148, kCtaThreads, sizeof(float) * kCtaStage, (cudaStream_t)stream>>>(
+        depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace);
     return st_last_launch();
 }
 

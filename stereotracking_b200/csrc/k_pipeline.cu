@@ -23,7 +23,7 @@ extern "C" int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *s
         if (rc != ST_OK) return rc;
     }
     rc = st_box_depth(io->depth_map, S, io->Hp, io->Wp, io->det_boxes, io->det_counts, cap, io->det_depth,
-                      io->det_scales, io->det_inflated, stream);
+                      io->det_scales, io->det_inflated, io->k3_workspace, stream);
     if (rc != ST_OK) return rc;
     rc = st_track_step(h, S, io->frame_ids, io->det_inflated, io->det_scores, io->det_labels, io->det_scales,
                        io->det_depth, io->det_counts, cap, io->trk_boxes, io->out_scores, io->out_labels,
@@ -32,5 +32,5 @@ extern "C" int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *s
     rc = st_scale_boxes(io->trk_boxes, io->out_scales, io->out_counts, S, cap, 1, io->out_boxes, stream);
     if (rc != ST_OK) return rc;
     return st_box_depth(io->depth_map, S, io->Hp, io->Wp, io->out_boxes, io->out_counts, cap, io->out_depth,
-                        io->out_scale2, nullptr, stream);
+                        io->out_scale2, nullptr, io->k3_workspace, stream);
 }

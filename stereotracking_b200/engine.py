@@ -99,6 +99,7 @@ class StereoTrackEngine:
         self.out_ids = torch.zeros(S, D, dtype=torch.int64, device=dev)
         self.out_counts = torch.zeros(S, dtype=torch.int32, device=dev)
         self.frame_ids = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.k3_workspace = torch.zeros(2 + 2 * S * D, dtype=torch.int32, device=dev)
         self.depth_map = None
 
     def close(self):
@@ -161,10 +162,14 @@ class StereoTrackEngine:
         dev = depth.device
         d_out = d_out if d_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
         scale_out = scale_out if scale_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
+        ws = self.k3_workspace
+        if ws.numel() < 2 + 2 * S * cap or ws.device != dev:
+            ws = self.k3_workspace = torch.zeros(2 + 2 * S * cap, dtype=torch.int32, device=dev)
         _lib.check(self.lib.st_box_depth(_ptr(self._dev(depth, torch.float32)), S, Hp, Wp,
                                          _ptr(self._dev(boxes, torch.float32)),
                                          _ptr(self._dev(counts, torch.int32)), cap, _ptr(d_out),
-                                         _ptr(scale_out), _ptr(inflated_out), self._stream()), 'st_box_depth')
+                                         _ptr(scale_out), _ptr(inflated_out), _ptr(ws), self._stream()),
+                   'st_box_depth')
         return d_out, scale_out, inflated_out
 
     def scale_boxes(self, boxes, scales, counts, invert, out=None):
@@ -236,6 +241,7 @@ class StereoTrackEngine:
         io.depth_map = self.depth_map.data_ptr()
         for name in ('det_boxes', 'det_scores', 'det_labels', 'det_prior', 'det_keep', 'det_counts',
                      'det_depth', 'det_scales', 'det_inflated', 'trk_boxes', 'trk_depth', 'out_scale2',
+                     'k3_workspace',
                      'out_boxes', 'out_scores', 'out_labels', 'out_scales', 'out_depth', 'out_ids',
                      'out_counts'):
             setattr(io, name, getattr(self, name).data_ptr())
@@ -251,7 +257,7 @@ class StereoTrackEngine:
             io._keep['obj'][l] = obj_l[l].data_ptr()
         _lib.check(self.lib.st_frame_step(self._h, raw.shape[0], C.byref(io), self._stream()), 'st_frame_step')
 
-    KERNELS_PER_FRAME = 9      # K1, K2 x4, K3, K4/K5, scale, K3
+    KERNELS_PER_FRAME = 11     # K1, K2 x4, K3 x2, K4/K5, scale, K3 x2
 
     def results(self):
         """Host copies of the current outputs, one dict per sequence."""

@@ -57,6 +57,17 @@ def test_k1_disp2depth_bit_exact(mods, shape, scale):
     assert torch.equal(only_depth, depth)
 
 
+def test_k1_every_raw_code_bit_exact(mods):
+    """The whole input domain of K1: all 65536 u16 codes (incl. 65535 = invalid)."""
+    raw = np.arange(65536, dtype=np.uint16).reshape(1, 256, 256)
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    depth, disp3, mask = eng.disp2depth(cuda(raw), want_disp3=True, want_mask=True)
+    ref = mods.disparity.preprocess(raw[0])
+    np.testing.assert_array_equal(depth[0].cpu().numpy(), ref['depth'])
+    np.testing.assert_array_equal(disp3[0, 1].cpu().numpy(), ref['disp'])
+    np.testing.assert_array_equal(mask[0].cpu().numpy(), ref['mask'])
+
+
 # ---------------------------------------------------------------- K2 ------------
 def _head_case(mods, cfg_name, S, seed, frames=2):
     cfg = mods.CONFIGS[cfg_name]
