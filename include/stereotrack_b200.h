@@ -200,8 +200,9 @@ int st_kalman_batch(int op, int n, double *mean, double *cov, const float *z, vo
 /* Batched association (ocm/ocr cost is built by st_track_step; this entry
  * exposes the assignment itself for parity tests): cost [B,R,C] f32 ->
  * row2col [B,R], col2row [B,C] i32 (-1 = unmatched), lap.lapjv(extend_cost=True,
- * cost_limit) semantics.  Uses the handle's scratch; R,C <= max_tracks/max_dets. */
+ * cost_limit) semantics.  Debug word 6 of sequence 0 counts exact-fallback solves.  Uses the handle's scratch; R,C <= max_tracks/max_dets. */
 int st_lapjv_batch(st_handle *h, int B, int R, int C, const float *cost, double cost_limit,
+                   int mode /* 0: certified fast path + exact fallback, 1: exact emulation only */,
                    int32_t *row2col, int32_t *col2row, void *stream);
 
 #ifdef __cplusplus

@@ -66,7 +66,7 @@ _SIGNATURES = {
     'st_frame_step': (_I, [_P, _I, C.POINTER(StFrameIO), _P]),
     'st_export_state': (_I, [_P, _I] + [_P] * 8),
     'st_kalman_batch': (_I, [_I, _I, _P, _P, _P, _P]),
-    'st_lapjv_batch': (_I, [_P, _I, _I, _I, _P, C.c_double, _P, _P, _P]),
+    'st_lapjv_batch': (_I, [_P, _I, _I, _I, _P, C.c_double, _I, _P, _P, _P]),
 }
 
 _lib = None

@@ -371,16 +371,27 @@ __device__ void radix_select2_cta(const BoxCtx &c, int nsel, const int *rank_in,
             }
         });
         __syncthreads();
-        if (threadIdx.x < nsel) {
-            const int k = threadIdx.x;
-            int acc = 0, b = 0;
-            for (; b < 256; ++b) {
-                int hcnt = hist[k * 256 + b];
-                if (acc + hcnt > rank[k]) break;
-                acc += hcnt;
+        if (threadIdx.x < 32) {
+            // warp 0 locates the bin holding each rank: 8 bins per lane + warp scan
+            const int lane_ = threadIdx.x;
+            for (int k = 0; k < nsel; ++k) {
+                int local[8], tot = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) { local[b] = hist[k * 256 + lane_ * 8 + b]; tot += local[b]; }
+                int inc = tot;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane_ >= o) inc += t;
+                }
+                int acc = inc - tot, found_bin = -1, found_acc = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (found_bin < 0 && acc + local[b] > rank[k]) { found_bin = lane_ * 8 + b; found_acc = acc; }
+                    acc += local[b];
+                }
+                const unsigned who = __ballot_sync(0xffffffffu, found_bin >= 0);
+                if (who && lane_ == __ffs(who) - 1) { sh[k * 2] = found_bin; sh[k * 2 + 1] = found_acc; }
             }
-            sh[k * 2] = b;
-            sh[k * 2 + 1] = acc;
         }
         __syncthreads();
         for (int k = 0; k < nsel; ++k) {

@@ -220,7 +220,9 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
         P.cost = cost; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
         P.dbg = st.debug + (sbase / pr.T) * 8;
         P.mark(0, stage_code); P.mark(1, R); P.mark(2, C);
-        const bool ok = stlap::solve_warp(P, sm.lap);
+        // debug words 5/6: assignments solved / solved by the exact fallback (this handle's lifetime)
+        if (threadIdx.x == 0) P.dbg[5] += 1;
+        const bool ok = stlap::assign_warp(P, sm.lap, P.dbg + 6);
         if (!ok && threadIdx.x == 0) atomicOr(status_word, ST_STATUS_LAP_GUARD);
     }
     __syncthreads();
@@ -532,8 +534,9 @@ __global__ void k4_reset(TrackState st, int T, const uint8_t *__restrict__ mask)
 }
 
 __global__ void __launch_bounds__(32)
-k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int32_t *__restrict__ row2col,
-               int32_t *__restrict__ col2row, int32_t *__restrict__ status) {
+k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mode,
+               int32_t *__restrict__ row2col, int32_t *__restrict__ col2row, int32_t *__restrict__ status,
+               int32_t *__restrict__ fallbacks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, lane = threadIdx.x;
     stlap::Scratch sc = stlap::carve(smem_raw, R + C);
@@ -541,7 +544,16 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int32_
     P.cost = cost + (long long)b * R * C; P.R = R; P.C = C; P.n = R + C; P.half = half;
     P.dbg = nullptr;
     if (R > 0 && C > 0) {
-        const bool ok = stlap::solve_warp(P, sc);
+        bool ok;
+        if (mode == 1) ok = stlap::solve_warp(P, sc);                 // exact emulation only
+        else {
+            ok = R + C <= 512 && stlap::fast_assign_warp(P, sc);       // certified fast path
+            if (!ok) {
+                if (lane == 0) atomicAdd(fallbacks, 1);
+                __syncwarp();
+                ok = stlap::solve_warp(P, sc);
+            }
+        }
         if (!ok && lane == 0) atomicOr(status, ST_STATUS_LAP_GUARD);
         __syncwarp();
     }
@@ -772,12 +784,12 @@ extern "C" int st_kalman_batch(int op, int n, double *mean, double *cov, const f
 }
 
 extern "C" int st_lapjv_batch(st_handle *h, int B, int R, int C, const float *cost, double cost_limit,
-                              int32_t *row2col, int32_t *col2row, void *stream) {
+                              int mode, int32_t *row2col, int32_t *col2row, void *stream) {
     if (!h || B < 0 || R < 0 || C < 0 || R + C > h->cfg.max_tracks + h->cfg.max_dets || !row2col || !col2row ||
         (R > 0 && C > 0 && !cost))
         return ST_ERR_INVALID_ARG;
     if (B == 0 || R + C == 0) return ST_OK;
     k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C), (cudaStream_t)stream>>>(
-        R, C, cost, cost_limit / 2.0, row2col, col2row, h->st.status);
+        R, C, cost, cost_limit / 2.0, mode, row2col, col2row, h->st.status, h->st.debug + 6);
     return st_last_launch();
 }

@@ -364,4 +364,229 @@ __device__ __noinline__ bool solve_warp(const Problem &P, Scratch &s) {
     return ok;
 }
 
+// ---------------------------------------------------------------------------------
+// Fast path.  The extended problem is equivalent to a maximum-weight bipartite
+// matching with "stay unmatched" options: minimise  sum_M c_ij + L/2 * (unmatched
+// rows + unmatched cols).  It is solved here as a rectangular assignment of the R
+// real rows to C real columns (cost c_ij - L/2) or to a private dummy column (cost
+// L/2) with the row-by-row shortest-augmenting-path (Hungarian) method, one warp,
+// float64 potentials.  Any exact solver returns the reference's assignment when the
+// optimum is unique, so the result is accepted only with a uniqueness certificate
+// from the optimal duals (u_i + v_j <= a_ij, v_j <= 0, v_j = 0 on free columns).
+// Every other optimal assignment uses tight edges only and keeps every column
+// with v_j < 0 occupied, so it differs from this one by re-routings along arcs
+// sigma(i) -> j (one per tight non-matching edge (i,j), dummy edges included):
+//   (1) a path from an occupied column that may be vacated (v_j >= -eps) to a
+//       free column, or
+//   (2) a directed cycle.
+// If neither exists (tolerance eps on tightness) the real part is unique and equals
+// the reference's.  Without the certificate -
+// exact cost ties such as duplicate boxes - the caller runs solve_warp, the literal
+// emulation of the reference's solver, so tie-breaks still match.
+// Rows whose best cost is >= L can never be matched: they are priced u_i = L/2
+// and skipped.
+// Scratch use: s.v = column potentials v_j (C real + R dummy columns), s.d =
+// minv, (s.cols,s.pred) reinterpreted as the R row potentials, s.x = p (column ->
+// row), s.y = way, s.unique = visited flags, s.free_rows = active row list.
+// On success s.y[j] (j < C) holds the row of column j or -1, s.x[i] the column of
+// row i or -1 - the same contract as solve_warp after truncation.
+constexpr double kFastEps = 1.0e-9;
+
+__device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
+    const int lane = threadIdx.x & 31;
+    const int R = P.R, C = P.C, m = R + C;
+    const double half = P.half, L = 2.0 * P.half;
+    volatile double *u = reinterpret_cast<volatile double *>(s.cols);   // [R] (cols,pred) = 2n ints
+    volatile double *v = s.v, *minv = s.d;
+    volatile int *p = s.x, *way = s.y, *active = s.free_rows;
+    volatile unsigned char *used = s.unique;
+    const double INF = 1.0e300;
+    // ---- row pruning + NaN screen ---------------------------------------------------
+    int n_active = 0;
+    bool bad = false;
+    for (int i0 = 0; i0 < R; i0 += 32) {
+        const int i = i0 + lane;
+        double best = INF;
+        bool nan = false;
+        if (i < R)
+            for (int j = 0; j < C; ++j) {
+                const double c = (double)P.cost[(long long)i * C + j];
+                nan |= !(c == c);
+                best = fmin(best, c);
+            }
+        bad |= __any_sync(0xffffffffu, nan) != 0;
+        const bool act = i < R && best < L;
+        if (i < R) u[i] = act ? 0.0 : half;
+        const unsigned mb = __ballot_sync(0xffffffffu, act);
+        if (act) active[n_active + __popc(mb & ((1u << lane) - 1u))] = i;
+        n_active += __popc(mb);
+    }
+    if (bad) return false;
+    for (int j = lane; j < m; j += 32) { v[j] = 0.0; p[j] = -1; }
+    __syncwarp();
+    // a(i, j): real column -> c_ij - half ; own dummy column C+i -> half ; else INF
+    auto a = [&](int i, int j) -> double {
+        if (j < C) return (double)P.cost[(long long)i * C + j] - half;
+        return (j - C == i) ? half : INF;
+    };
+    // ---- Hungarian, rows inserted one by one ---------------------------------------------
+    for (int t = 0; t < n_active; ++t) {
+        const int row = active[t];
+        for (int j = lane; j < m; j += 32) { minv[j] = INF; used[j] = 0; }
+        __syncwarp();
+        int j0 = m;                       // virtual start column holding `row`
+        int guard = 0;
+        while (true) {
+            if (++guard > m + 2) return false;
+            if (j0 < m && lane == 0) used[j0] = 1;
+            __syncwarp();
+            const int i0 = j0 == m ? row : p[j0];
+            const double ui0 = u[i0];
+            double delta = INF;
+            int j1 = -1;
+            for (int j = lane; j < m; j += 32) {
+                if (used[j]) continue;
+                // dummy columns of other rows are unreachable
+                if (j >= C && j - C != i0) {
+                    const double mv = minv[j];
+                    if (mv < delta) { delta = mv; j1 = j; }
+                    continue;
+                }
+                const double cur = a(i0, j) - ui0 - v[j];
+                double mv = minv[j];
+                if (cur < mv) { mv = cur; minv[j] = cur; way[j] = j0; }
+                if (mv < delta) { delta = mv; j1 = j; }
+            }
+            for (int o = 16; o; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, delta, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, j1, o);
+                if (pair_less(od, oj, delta, j1)) { delta = od; j1 = oj; }
+            }
+            if (j1 < 0 || !(delta < INF)) return false;
+            __syncwarp();
+            // dual update: visited columns (and the virtual one) move with their rows
+            for (int j = lane; j < m; j += 32) {
+                if (used[j]) { u[p[j]] += delta; v[j] -= delta; }
+                else minv[j] -= delta;
+            }
+            if (lane == 0) u[row] += delta;          // the virtual column's row
+            __syncwarp();
+            j0 = j1;
+            if (p[j0] < 0) break;
+        }
+        if (lane == 0) {
+            int steps = 0;
+            while (j0 != m && steps++ <= m) {       // flip the alternating path
+                const int jp = way[j0];
+                p[j0] = jp == m ? row : p[jp];
+                j0 = jp;
+            }
+        }
+        __syncwarp();
+    }
+    // ---- uniqueness certificate ---------------------------------------------------------
+    // sigma[i] = column of row i (own dummy C+i when unmatched); arcs sigma(i) -> j for
+    // every tight non-matching edge (i, j), dummy edges included.
+    volatile int *sigma = way;                         // `way` is dead after the solve
+    for (int i = lane; i < R; i += 32) sigma[i] = C + i;
+    __syncwarp();
+    for (int j = lane; j < C; j += 32) { const int r = p[j]; if (r >= 0) sigma[r] = j; }
+    __syncwarp();
+    volatile int *arc_from = reinterpret_cast<volatile int *>(s.d);     // s.d = 2n ints
+    volatile int *arc_to = arc_from + m;
+    int n_arcs = 0;
+    const int total_edges = R * C + R;                 // real edges, then one dummy edge per row
+    for (int e0 = 0; e0 < total_edges; e0 += 32) {
+        const int e = e0 + lane;
+        bool tight = false;
+        int from = 0, to = 0;
+        if (e < R * C) {
+            const int i = e / C, j = e - i * C;
+            if (p[j] != i) {
+                const double slack = ((double)P.cost[e] - half) - u[i] - v[j];
+                tight = slack <= kFastEps;
+                from = sigma[i]; to = j;
+            }
+        } else if (e < total_edges) {
+            const int i = e - R * C;
+            if (sigma[i] != C + i) {
+                tight = half - u[i] - v[C + i] <= kFastEps;
+                from = sigma[i]; to = C + i;
+            }
+        }
+        const unsigned tb = __ballot_sync(0xffffffffu, tight);
+        const int pos = n_arcs + __popc(tb & ((1u << lane) - 1u));
+        if (tight && pos < m) { arc_from[pos] = from; arc_to[pos] = to; }
+        n_arcs += __popc(tb);
+    }
+    if (n_arcs > m) return false;                       // more tight edges than the list holds
+    __syncwarp();
+    if (n_arcs > 0) {
+        // column flags live where the row potentials were (no longer needed)
+        volatile unsigned char *assigned = reinterpret_cast<volatile unsigned char *>(s.cols);
+        volatile unsigned char *reach = assigned + m, *alive = assigned + 2 * m, *has_out = assigned + 3 * m;
+        bool vac_l[16];
+        int cnt = 0;
+        for (int j = lane; j < m; j += 32, ++cnt) {
+            const bool asg = j < C ? p[j] >= 0 : sigma[j - C] == j;
+            if (cnt < 16) vac_l[cnt] = asg && v[j] >= -kFastEps;     // may be vacated at no cost
+            assigned[j] = asg; reach[j] = !asg; alive[j] = asg;
+        }
+        __syncwarp();
+        // (1) columns from which a free column is reachable along arcs
+        for (int round = 0; round <= m; ++round) {
+            bool changed = false;
+            for (int k = lane; k < n_arcs; k += 32)
+                if (reach[arc_to[k]] && !reach[arc_from[k]]) { reach[arc_from[k]] = 1; changed = true; }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        bool unsure = false;
+        cnt = 0;
+        for (int j = lane; j < m; j += 32, ++cnt)
+            if (cnt < 16 && vac_l[cnt] && reach[j]) unsure = true;   // a free re-routing exists
+        // (2) directed cycle among assigned columns (peel columns without live successors)
+        for (int round = 0; round <= m; ++round) {
+            for (int j = lane; j < m; j += 32) has_out[j] = 0;
+            __syncwarp();
+            for (int k = lane; k < n_arcs; k += 32)
+                if (alive[arc_from[k]] && alive[arc_to[k]]) has_out[arc_from[k]] = 1;
+            __syncwarp();
+            bool changed = false;
+            for (int j = lane; j < m; j += 32)
+                if (alive[j] && !has_out[j]) { alive[j] = 0; changed = true; }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        for (int j = lane; j < m; j += 32) unsure |= alive[j] != 0;    // survivors lie on a cycle
+        if (__any_sync(0xffffffffu, unsure)) return false;
+    }
+    __syncwarp();
+    // ---- publish in solve_warp's layout: y = col -> row, x = row -> col -------------------
+    // (p aliases s.x and way aliases s.y, so go through registers)
+    int colrow[16];                                   // m <= 512 per lane stride 32
+    int cnt = 0;
+    for (int j = lane; j < C && cnt < 16; j += 32) colrow[cnt++] = p[j];
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) s.x[i] = -1;
+    __syncwarp();
+    cnt = 0;
+    for (int j = lane; j < C; j += 32) {
+        const int r = cnt < 16 ? colrow[cnt] : -1;
+        ++cnt;
+        s.y[j] = r;
+        if (r >= 0) s.x[r] = j;
+    }
+    __syncwarp();
+    return true;
+}
+
+// Fast path with certified uniqueness, else the exact emulation of the reference's solver.
+__device__ inline bool assign_warp(const Problem &P, Scratch &s, int *fallback_counter) {
+    if (P.n <= 512 && fast_assign_warp(P, s)) return true;
+    if (fallback_counter && (threadIdx.x & 31) == 0) *fallback_counter += 1;
+    __syncwarp();
+    return solve_warp(P, s);
+}
+
 }  // namespace stlap

@@ -304,10 +304,17 @@ class StereoTrackEngine:
         n = mean.shape[0]
         _lib.check(self.lib.st_kalman_batch(op, n, _ptr(mean), _ptr(cov), _ptr(z), self._stream()))
 
-    def lapjv_batch(self, cost, cost_limit):
+    def debug_words(self):
+        """[S,8] diagnostic words: 5 = assignments solved, 6 = solved by the exact fallback."""
+        import numpy as np
+        a = np.zeros((self.cfg.n_seq, 8), np.int32)
+        _lib.check(self.lib.st_read_debug(self._h, a.ctypes.data_as(C.c_void_p), self.cfg.n_seq))
+        return a
+
+    def lapjv_batch(self, cost, cost_limit, mode=0):
         B, R, Cc = cost.shape
         x = torch.empty(B, R, dtype=torch.int32, device=cost.device)
         y = torch.empty(B, Cc, dtype=torch.int32, device=cost.device)
         _lib.check(self.lib.st_lapjv_batch(self._h, B, R, Cc, _ptr(self._dev(cost, torch.float32)),
-                                           float(cost_limit), _ptr(x), _ptr(y), self._stream()))
+                                           float(cost_limit), int(mode), _ptr(x), _ptr(y), self._stream()))
         return x, y

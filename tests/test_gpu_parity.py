@@ -201,13 +201,19 @@ def test_lapjv_batch_matches_oracle(mods, R, C, ties):
         cost = rng.uniform(0, 1.3, (B, R, C)).astype(np.float32)
         cost[:, np.arange(min(R, C)), np.arange(min(R, C))] *= 0.2      # mostly matchable
     eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
-    x, y = eng.lapjv_batch(cuda(cost), 0.9)
-    assert eng.status().max() == 0
-    x, y = x.cpu().numpy(), y.cpu().numpy()
-    for b in range(B):
-        rx, ry = mods.lapjv(cost[b], 0.9)
-        np.testing.assert_array_equal(y[b], ry, err_msg=f'problem {b}')
-        np.testing.assert_array_equal(x[b], rx, err_msg=f'problem {b}')
+    ref = [mods.lapjv(cost[b], 0.9) for b in range(B)]
+    for mode in (1, 0):        # exact emulation only; certified fast path + fallback
+        x, y = eng.lapjv_batch(cuda(cost), 0.9, mode=mode)
+        assert eng.status().max() == 0
+        x, y = x.cpu().numpy(), y.cpu().numpy()
+        for b in range(B):
+            np.testing.assert_array_equal(y[b], ref[b][1], err_msg=f'mode {mode} problem {b}')
+            np.testing.assert_array_equal(x[b], ref[b][0], err_msg=f'mode {mode} problem {b}')
+    fallbacks = int(eng.debug_words()[0, 6])
+    if not ties:
+        assert fallbacks == 0, 'tie-free problems must be certified by the fast path'
+    else:
+        assert fallbacks > 0, 'tie cases must go through the exact emulation'
 
 
 # ---------------------------------------------------------------- tracker ---------
