@@ -90,8 +90,9 @@ int st_destroy(st_handle *h);
 int st_reset(st_handle *h, const uint8_t *seq_mask, void *stream);
 int st_read_status(st_handle *h, int32_t *status_host, int S);   /* synchronises */
 int st_clear_status(st_handle *h, void *stream);
-/* Diagnostics: 8 progress words per sequence written by the last st_track_step
- * (phase, assignment rows/cols, solver sub-phase, ...).  Copied on a side
+/* Diagnostics: 16 words per sequence written by st_track_step: 0-4 solver progress,
+ * 5 assignments solved, 6 solved by the exact fallback, 7 phase, 8-13 SM cycles of
+ * the last step per phase (filter+predict, stage 1, 2, 3, smoothing+ordering, update).  Copied on a side
  * stream, so it can be called while a step is still running. */
 int st_read_debug(st_handle *h, int32_t *debug_host, int S);
 /* Diagnostics: disable parts of st_track_step (bit0..2 assignment of stage 1..3,
@@ -132,7 +133,7 @@ int st_decode_nms(st_handle *h, const float *const *cls_host, const float *const
  * (may be NULL). */
 int st_box_depth(const float *depth, int S, int Hp, int Wp, const float *boxes,
                  const int32_t *counts, int cap, float *d, float *scale, float *inflated,
-                 int32_t *workspace /* [2 + 2*S*cap] i32 scratch (worklist of large boxes) */,
+                 int32_t *workspace /* [2 + 4*S*cap] i32 scratch (worklists of large boxes) */,
                  void *stream);
 
 /* scale_bbox(boxes, 1/scales) (ocsort_disparity.py:96-97) or scale_bbox(boxes,
@@ -173,7 +174,7 @@ typedef struct st_frame_io {
     float *det_boxes; float *det_scores; int64_t *det_labels; int32_t *det_prior; int32_t *det_keep;
     int32_t *det_counts; float *det_depth; float *det_scales; float *det_inflated;
     float *trk_boxes; float *trk_depth; float *out_scale2;
-    int32_t *k3_workspace;             /* [2 + 2*S*cap] i32 scratch of st_box_depth */
+    int32_t *k3_workspace;             /* [2 + 4*S*cap] i32 scratch of st_box_depth */
     /* outputs = pred_track_instances fields */
     float *out_boxes; float *out_scores; int64_t *out_labels; float *out_scales; float *out_depth;
     int64_t *out_ids; int32_t *out_counts;

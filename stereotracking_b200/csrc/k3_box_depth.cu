@@ -20,6 +20,7 @@ namespace {
 constexpr int kWarps = 4;                // boxes per CTA
 constexpr int kStage = 2048;             // valid depths staged per warp
 constexpr int kSmallPix = 2048;          // boxes up to this many pixels: one warp; larger: one CTA
+constexpr int kMediumPix = 8192;         // CTA tiers: medium <= kMediumPix < huge
 
 struct Slice { int lo, hi; };            // hi <= lo means empty
 
@@ -185,7 +186,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(kWarps * 32)
 k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
              const int32_t *__restrict__ counts, int cap, float *__restrict__ d_out,
-             float *__restrict__ scale_out, float *__restrict__ inflated, int32_t *__restrict__ worklist) {
+             float *__restrict__ scale_out, float *__restrict__ inflated, int32_t *__restrict__ worklist,
+             int list_cap) {
     __shared__ float staged_all[kWarps][kStage];
     __shared__ int hist_all[kWarps][512];
     const int s = blockIdx.y;
@@ -207,6 +209,7 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
     c.npix = c.bw * (unsigned)max(c.ys.hi - c.ys.lo, 0);
     if (c.npix > (unsigned)kSmallPix) {                 // handled by k3_box_depth_large
         if (lane == 0) {
+            // worklist = [n_large, n_overflow, large items (s, box) x list_cap, overflow items x list_cap]
             const int slot = atomicAdd(&worklist[0], 1);
             worklist[2 + 2 * slot] = s;
             worklist[3 + 2 * slot] = bi;
@@ -315,20 +318,25 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
     }
 }
 
-constexpr int kCtaThreads = 512;         // large boxes: one CTA per box
-constexpr int kCtaStage = 45056;         // floats of dynamic shared memory (176 KB, one CTA per SM)
+// Boxes above kSmallPix pixels: one CTA per box, two tiers (both persistent over a
+// worklist written by the warp kernel):
+//   medium  <= kMediumPix pixels: 256 threads, 32 KB stage, several CTAs per SM
+//   huge     > kMediumPix pixels: 512 threads, 176 KB stage, one CTA per SM
+constexpr int kMediumThreads = 256, kMediumStage = 8192;
+constexpr int kHugeThreads = 512, kHugeStage = 45056;
+constexpr int kMaxCtaWarps = 16;
 
 // visit every valid depth value of the box: f(value)
 template <typename F>
 __device__ __forceinline__ void for_each_valid_cta(const BoxCtx &c, F f) {
     if (c.use_stage) {
-        for (int i = threadIdx.x; i < c.n_valid; i += kCtaThreads) f(c.staged[i]);
+        for (int i = threadIdx.x; i < c.n_valid; i += blockDim.x) f(c.staged[i]);
     } else {
-        for (unsigned i0 = threadIdx.x; i0 < c.npix; i0 += 4 * kCtaThreads) {
+        for (unsigned i0 = threadIdx.x; i0 < c.npix; i0 += 4 * blockDim.x) {
             float v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {           // four independent loads in flight
-                const unsigned i = i0 + u * kCtaThreads;
+                const unsigned i = i0 + u * blockDim.x;
                 v[u] = -1.f;
                 if (i < c.npix) {
                     const unsigned ry = i / c.bw, rx = i - ry * c.bw;
@@ -351,7 +359,7 @@ __device__ void radix_select2_cta(const BoxCtx &c, int nsel, const int *rank_in,
     int rank[2] = {rank_in[0], nsel > 1 ? rank_in[1] : 0};
     int less[2] = {0, 0};
     for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 512; i += kCtaThreads) hist[i] = 0;
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
         const uint32_t p0 = prefix[0], p1 = prefix[1];
@@ -404,13 +412,13 @@ __device__ void radix_select2_cta(const BoxCtx &c, int nsel, const int *rank_in,
     for (int k = 0; k < nsel; ++k) { value[k] = prefix[k]; below[k] = less[k]; }
 }
 
-__device__ double block_sum(double v, double *red /* [kCtaThreads/32] shared */) {
+__device__ double block_sum(double v, double *red /* [kMaxCtaWarps] shared */) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double t = 0.0;
-    for (int w = 0; w < kCtaThreads / 32; ++w) t += red[w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     return t;
 }
 
@@ -420,24 +428,25 @@ __device__ int block_count(int v, int *red) {
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     int t = 0;
-    for (int w = 0; w < kCtaThreads / 32; ++w) t += red[w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     return t;
 }
 
-__global__ void __launch_bounds__(kCtaThreads)
-k3_box_depth_large(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
+template <int kThreadsT, int kStageT>
+__global__ void __launch_bounds__(kThreadsT)
+k3_box_depth_cta(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
              int cap, float *__restrict__ d_out, float *__restrict__ scale_out,
-             float *__restrict__ inflated, const int32_t *__restrict__ worklist) {
-  const int n_work = worklist[0];
+             float *__restrict__ inflated, const int32_t *__restrict__ n_work_ptr, const int32_t *__restrict__ worklist) {
+  const int n_work = *n_work_ptr;
   for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
     __syncthreads();                                   // shared memory is reused across items
-    const int s = worklist[2 + 2 * item], bi = worklist[3 + 2 * item];
+    const int s = worklist[2 * item], bi = worklist[2 * item + 1];
     const int lane = threadIdx.x & 31;
-    extern __shared__ __align__(16) float staged[];    // [kCtaStage]
+    extern __shared__ __align__(16) float staged[];    // [kStageT]
     __shared__ int hist[512];
     __shared__ int sh[8];
-    __shared__ int ired[kCtaThreads / 32];
-    __shared__ double dred[kCtaThreads / 32];
+    __shared__ int ired[kMaxCtaWarps];
+    __shared__ double dred[kMaxCtaWarps];
     __shared__ int stage_fill;
 
     const long long o = (long long)s * cap + bi;
@@ -456,15 +465,15 @@ k3_box_depth_large(const float *__restrict__ depth, int Hp, int Wp, const float 
     const long long wbox = wrap_add(b2, (long long)(0ull - (unsigned long long)b0));
     int n = 0;
     if (!(wbox > 800)) {
-        // pass 0: count the valid values and stage the first kCtaStage of them
+        // pass 0: count the valid values and stage the first kStageT of them
         // (warp-aggregated append; the order inside the stage is irrelevant)
         if (threadIdx.x == 0) stage_fill = 0;
         __syncthreads();
-        for (unsigned i0 = threadIdx.x; i0 < c.npix; i0 += 4 * kCtaThreads) {
+        for (unsigned i0 = threadIdx.x; i0 < c.npix; i0 += 4 * blockDim.x) {
             float v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const unsigned i = i0 + u * kCtaThreads;
+                const unsigned i = i0 + u * blockDim.x;
                 v[u] = -1.f;
                 if (i < c.npix) {
                     const unsigned ry = i / c.bw, rx = i - ry * c.bw;
@@ -482,13 +491,13 @@ k3_box_depth_large(const float *__restrict__ depth, int Hp, int Wp, const float 
                     if (lane == leader) base = atomicAdd(&stage_fill, __popc(m));
                     base = __shfl_sync(act, base, leader);
                     const int pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (ok && pos < kCtaStage) staged[pos] = v[u];
+                    if (ok && pos < kStageT) staged[pos] = v[u];
                 }
             }
         }
         __syncthreads();
         n = stage_fill;
-        c.use_stage = n <= kCtaStage;
+        c.use_stage = n <= kStageT;
     }
     c.n_valid = n;
 
@@ -561,6 +570,175 @@ k3_box_depth_large(const float *__restrict__ depth, int Hp, int Wp, const float 
   }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Large boxes, main path: one pass over the pixels builds a shared-memory table of
+// the DISTINCT valid depth values with their multiplicities (open-addressing hash on
+// the float bit pattern, warp-aggregated inserts).  A depth map that comes from a
+// u16 disparity has few distinct values per box (one per object plus the
+// background ramp), so the table is tiny compared with the pixel count; the
+// order statistics and the window sum are then computed on the sorted table with
+// multiplicities - exactly the sorted-list semantics of the reference.  Boxes
+// with more distinct values than the table holds go to the overflow list and are
+// handled by the staged radix-select kernel below.
+constexpr int kTableSlots = 4096;        // hash slots (power of two)
+constexpr int kMaxDistinct = 3072;       // distinct values accepted before overflow
+constexpr int kTableThreads = 512;
+constexpr size_t kTableSmem = sizeof(uint32_t) * kTableSlots * 2 + sizeof(uint32_t) * kMaxDistinct * 5;
+
+__global__ void __launch_bounds__(kTableThreads)
+k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
+                   int cap, float *__restrict__ d_out, float *__restrict__ scale_out,
+                   float *__restrict__ inflated, int32_t *__restrict__ worklist, int list_cap) {
+    extern __shared__ __align__(16) uint32_t tsm[];
+    uint32_t *keys = tsm;                               // [kTableSlots] 0 = empty
+    int *cnts = reinterpret_cast<int *>(tsm + kTableSlots);
+    uint32_t *ukey = tsm + 2 * kTableSlots;             // [kMaxDistinct] unordered distinct values
+    int *ucnt = reinterpret_cast<int *>(ukey + kMaxDistinct);
+    float *sval = reinterpret_cast<float *>(ucnt + kMaxDistinct);    // sorted by value
+    int *scnt = reinterpret_cast<int *>(sval + kMaxDistinct);
+    int *sbelow = scnt + kMaxDistinct;                  // number of elements strictly smaller
+    __shared__ int n_distinct, n_dense, overflow, n_valid_sh, sel[2];
+    __shared__ double dred[kMaxCtaWarps];
+    const int lane = threadIdx.x & 31;
+    const int n_work = worklist[0];
+    for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
+        __syncthreads();
+        const int s = worklist[2 + 2 * item], bi = worklist[3 + 2 * item];
+        const long long o = (long long)s * cap + bi;
+        const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
+        const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
+        const float *dm = depth + (long long)s * Hp * Wp;
+        const Slice ys = py_slice(b1, b3, Hp), xs = py_slice(b0, b2, Wp);
+        const unsigned bw = (unsigned)max(xs.hi - xs.lo, 0);
+        const unsigned npix = bw * (unsigned)max(ys.hi - ys.lo, 0);
+        const long long wbox = wrap_add(b2, (long long)(0ull - (unsigned long long)b0));
+        float d = -1.f, scale = 1.f;
+        bool done = wbox > 800;                          // reference: d = -1, scale = 1 (:150)
+        if (!done) {
+            for (int i = threadIdx.x; i < kTableSlots; i += kTableThreads) { keys[i] = 0u; cnts[i] = 0; }
+            if (threadIdx.x == 0) { n_distinct = 0; n_dense = 0; overflow = 0; n_valid_sh = 0; }
+            __syncthreads();
+            for (unsigned i0 = threadIdx.x; i0 < npix; i0 += 4 * kTableThreads) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {           // four independent loads in flight
+                    const unsigned i = i0 + u * kTableThreads;
+                    v[u] = -1.f;
+                    if (i < npix) {
+                        const unsigned ry = i / bw, rx = i - ry * bw;
+                        v[u] = dm[(long long)(ys.lo + ry) * Wp + xs.lo + rx];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool ok = depth_valid(v[u]);
+                    const uint32_t key = ok ? __float_as_uint(v[u]) : 0u;     // valid depths are > 0: bits != 0
+                    const unsigned act = __activemask();
+                    const unsigned peers = __match_any_sync(act, key);
+                    if (ok && lane == __ffs(peers) - 1) {
+                        const int c = __popc(peers);
+                        uint32_t h = (key * 2654435761u) >> 20;               // top 12 bits -> 4096 slots
+                        for (int probe = 0; probe < kTableSlots; ++probe) {
+                            const uint32_t prev = atomicCAS(&keys[h], 0u, key);
+                            if (prev == 0u || prev == key) {
+                                atomicAdd(&cnts[h], c);
+                                if (prev == 0u && atomicAdd(&n_distinct, 1) >= kMaxDistinct) overflow = 1;
+                                break;
+                            }
+                            h = (h + 1) & (kTableSlots - 1);
+                        }
+                    }
+                }
+                if (overflow) break;                     // benign race: every thread leaves soon after
+            }
+            __syncthreads();
+            if (overflow) {
+                if (threadIdx.x == 0) {
+                    const int slot = atomicAdd(&worklist[1], 1);
+                    worklist[2 + 2 * list_cap + 2 * slot] = s;
+                    worklist[3 + 2 * list_cap + 2 * slot] = bi;
+                }
+                continue;                                // block-uniform
+            }
+            // dense (unordered) list of the distinct values
+            for (int i = threadIdx.x; i < kTableSlots; i += kTableThreads)
+                if (keys[i] != 0u) {
+                    const int k = atomicAdd(&n_dense, 1);
+                    ukey[k] = keys[i];
+                    ucnt[k] = cnts[i];
+                    atomicAdd(&n_valid_sh, cnts[i]);
+                }
+            __syncthreads();
+            const int T = n_dense, n = n_valid_sh;
+            if (n >= 1) {
+                // sort by value: position = number of smaller distinct values (keys are unique)
+                for (int e = threadIdx.x; e < T; e += kTableThreads) {
+                    const uint32_t ke = ukey[e];
+                    int pos = 0, below = 0;
+                    for (int f = 0; f < T; ++f) {
+                        const bool sm = ukey[f] < ke;
+                        pos += sm;
+                        below += sm ? ucnt[f] : 0;
+                    }
+                    sval[pos] = __uint_as_float(ke);
+                    scnt[pos] = ucnt[e];
+                    sbelow[pos] = below;
+                }
+                __syncthreads();
+                auto locate = [&](int rank, int which) {   // sorted[rank] -> sel[which] (entry index)
+                    for (int e = threadIdx.x; e < T; e += kTableThreads)
+                        if (sbelow[e] <= rank && rank < sbelow[e] + scnt[e]) sel[which] = e;
+                };
+                locate(n / 2, 0);
+                __syncthreads();
+                const float d_mid = sval[sel[0]];
+                int k = 0;
+                {
+                    Slice ytop = py_slice(b1, wrap_add(b1, 2), Hp), ybot = py_slice(wrap_add(b3, -2), b3, Hp);
+                    Slice xl = py_slice(b0, wrap_add(b0, 2), Wp), xr = py_slice(wrap_add(b2, -2), b2, Wp);
+                    k += corner_mean(dm, Wp, ytop, xl) > d_mid;
+                    k += corner_mean(dm, Wp, ytop, xr) > d_mid;
+                    k += corner_mean(dm, Wp, ybot, xl) > d_mid;
+                    k += corner_mean(dm, Wp, ybot, xr) > d_mid;
+                }
+                const double frac = fmin(1.0 - (double)k / 4.0, 0.4);
+                const double w_start = __dmul_rn(frac, (double)n);
+                const double w_end = __dadd_rn(w_start, __dmul_rn(0.6, (double)n));
+                Slice seg = py_slice((long long)w_start, (long long)w_end, n);
+                if (seg.hi <= seg.lo) seg = py_slice(0, -1, n);       // d_sorted[:-1]
+                const int m = seg.hi - seg.lo;
+                if (m <= 0) {
+                    d = __int_as_float(0x7fc00000);
+                } else {
+                    // window sum over the sorted multiset, fixed summation order
+                    double part = 0.0;
+                    for (int e = threadIdx.x; e < T; e += kTableThreads) {
+                        const int lo = max(sbelow[e], seg.lo), hi = min(sbelow[e] + scnt[e], seg.hi);
+                        if (hi > lo) part += (double)sval[e] * (double)(hi - lo);
+                    }
+                    const double sum = block_sum(part, dred);
+                    d = (float)(sum / (double)m);
+                }
+                const float dd = __fmul_rn(d, d);
+                scale = (dd != dd) ? dd : fmaxf(fminf(dd, 3.f), 1.f);
+            }
+        }
+        if (threadIdx.x == 0) {
+            d_out[o] = d;
+            scale_out[o] = scale;
+            if (inflated) {
+                const float cx = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
+                const float cy = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
+                const float hw = __fmul_rn(__fmul_rn(__fsub_rn(box.z, box.x), scale), 0.5f);
+                const float hh = __fmul_rn(__fmul_rn(__fsub_rn(box.w, box.y), scale), 0.5f);
+                reinterpret_cast<float4 *>(inflated)[o] =
+                    make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+            }
+        }
+    }
+}
+
 __global__ void k3_scale_boxes(const float *__restrict__ boxes, const float *__restrict__ scales,
                                const int32_t *__restrict__ counts, int cap, int invert,
                                float *__restrict__ out) {
@@ -588,19 +766,30 @@ extern "C" int st_box_depth(const float *depth, int S, int Hp, int Wp, const flo
         return ST_ERR_INVALID_ARG;
     if (S == 0) return ST_OK;
     ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 2, (cudaStream_t)stream));
+    const int list_cap = S * cap;
     k3_box_depth<<<dim3((cap + kWarps - 1) / kWarps, S), kWarps * 32, 0, (cudaStream_t)stream>>>(
-        depth, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace);
-    static bool smem_opt_in = false;
-    if (!smem_opt_in) {
-        ST_CUDA_OK(cudaFuncSetAttribute(k3_box_depth_large, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(float) * kCtaStage)));
-        smem_opt_in = true;
-    }
+        depth, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace, list_cap);
     static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    // persistent: one CTA per SM (the stage takes most of its shared memory) loops over the worklist
-    k3_box_depth_large<<<sms > 0 ? sms : 148, kCtaThreads, sizeof(float) * kCtaStage, (cudaStream_t)stream>>>(
-        depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace);
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+        ST_CUDA_OK(cudaFuncSetAttribute(k3_box_depth_cta<kHugeThreads, kHugeStage>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(float) * kHugeStage)));
+        ST_CUDA_OK(cudaFuncSetAttribute(k3_box_depth_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kTableSmem));
+    }
+    // persistent grids sized in multiples of the SM count, looping over the worklists:
+    // large boxes -> distinct-value table kernel; its overflow list -> staged radix select
+    long long tgrid = (long long)sms * 2;
+    if (tgrid > list_cap) tgrid = list_cap;
+    k3_box_depth_table<<<(int)tgrid, kTableThreads, kTableSmem, (cudaStream_t)stream>>>(
+        depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap);
+    k3_box_depth_cta<kHugeThreads, kHugeStage><<<sms, kHugeThreads, sizeof(float) * kHugeStage,
+                                                 (cudaStream_t)stream>>>(
+        depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace + 1, workspace + 2 + 2 * list_cap);
     return st_last_launch();
 }
 

@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
 // diagnostics only (st_debug_set_skip): bit0..2 skip the assignment of stage
@@ -218,7 +218,7 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
     } else if (threadIdx.x < 32) {
         stlap::Problem P;
         P.cost = cost; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
-        P.dbg = st.debug + (sbase / pr.T) * 8;
+        P.dbg = st.debug + (sbase / pr.T) * 16;
         P.mark(0, stage_code); P.mark(1, R); P.mark(2, C);
         // debug words 5/6: assignments solved / solved by the exact fallback (this handle's lifetime)
         if (threadIdx.x == 0) P.dbg[5] += 1;
@@ -251,6 +251,16 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
     __shared__ int sh_nlive;
     const int s = blockIdx.x;
     const int T = pr.T, D = pr.D;
+    // debug words 8..14: SM cycles the last step spent in each phase (thread 0's clock)
+    long long t_prev = clock64();
+#define ST_PHASE(idx)                                                         \
+    do {                                                                      \
+        if (threadIdx.x == 0) {                                               \
+            const long long t_now = clock64();                                \
+            st.debug[s * 16 + (idx)] = (int)(t_now - t_prev);                 \
+            t_prev = t_now;                                                   \
+        }                                                                     \
+    } while (0)
     Smem sm = carve(smem_raw, T, D);
     const long long sbase = (long long)s * T;
     const int frame = frame_ids[s];
@@ -318,8 +328,10 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             if (!(g_skip & 32)) stkf::predict(st.mean + g * 8, st.cov + g * 64, kfws);
         }
         __syncthreads();
+        ST_PHASE(8);
         // ---- stage 1: confirmed tracks vs filtered dets (:448-474)
         associate(st, pr, sm, sbase, R, C, true, dv, cost, 1, &st.status[s]);
+        ST_PHASE(9);
         // ---- stage 2: tentative tracks vs leftovers (:476-503)
         compact_warp0(nd_in, [&](int i) { return sm.det_stage[i] == 4; }, sm.dets, &sh_cnt[0]);
         C = sh_cnt[0];
@@ -328,6 +340,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = order[sm.rows[r]];
         __syncthreads();
         associate(st, pr, sm, sbase, R, C, true, dv, cost, 2, &st.status[s]);
+        ST_PHASE(10);
         // ---- which tracks are matched so far
         for (int i = threadIdx.x; i < nd_in; i += kThreads) {
             const int slot = sm.det_slot[i];
@@ -344,6 +357,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = order[sm.rows[r]];
         __syncthreads();
         associate(st, pr, sm, sbase, R, C, false, dv, cost, 3, &st.status[s]);
+        ST_PHASE(11);
         for (int i = threadIdx.x; i < nd_in; i += kThreads) {
             const int slot = sm.det_slot[i];
             if (slot >= 0 && sm.det_stage[i] == 3)
@@ -351,7 +365,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
                     if (order[p] == slot) { sm.slot_hit[p] = 1; break; }
         }
         __syncthreads();
-        if (threadIdx.x == 0) st.debug[s * 8 + 7] = 8;
+        if (threadIdx.x == 0) st.debug[s * 16 + 7] = 8;
         // ---- online smoothing of re-found lost tracks (:571-577, :319-343)
         for (int i = warp; i < nd_in; i += kWarps) {
             const int slot = sm.det_slot[i];
@@ -380,7 +394,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) st.debug[s * 8 + 7] = 9;
+        if (threadIdx.x == 0) st.debug[s * 16 + 7] = 9;
         // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582)
         for (int p = threadIdx.x; p < n_live; p += kThreads)
             if (!sm.slot_hit[p]) {
@@ -405,7 +419,8 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         n_out = sh_cnt[0];
     }
 
-    if (threadIdx.x == 0) st.debug[s * 8 + 7] = 10;
+    if (threadIdx.x == 0) st.debug[s * 16 + 7] = 10;
+    ST_PHASE(12);
     // ---- ids + BaseTracker.update (:598-605, base_tracker.py:54-91) ------------
     // new tracks are exactly the outputs without a slot; they are last in order
     __syncthreads();
@@ -491,7 +506,8 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) st.debug[s * 8 + 7] = 11;
+    if (threadIdx.x == 0) st.debug[s * 16 + 7] = 11;
+    ST_PHASE(13);
     // ---- pop_invalid_tracks (kalman_tracker_base.py:77-88) -------------------------
     const int n_now = n_live + n_create;
     if (threadIdx.x < 32) {
@@ -521,7 +537,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             st.n_free[s] = n_free - n_create + freed;
             st.next_id[s] = id0 + n_new;
             out_counts[s] = n_out;
-            st.debug[s * 8 + 7] = 12;
+            st.debug[s * 16 + 7] = 12;
         }
     }
 }
@@ -595,7 +611,7 @@ size_t layout(st_handle *h, unsigned char *base) {
     unsigned char *c = base;
     TrackState &st = h->st;
     take(st.n_live, c, S); take(st.next_id, c, S); take(st.order, c, S * T); take(st.free_slots, c, S * T);
-    take(st.n_free, c, S); take(st.status, c, S); take(st.debug, c, S * 8);
+    take(st.n_free, c, S); take(st.status, c, S); take(st.debug, c, S * 16);
     take(st.id, c, S * T); take(st.hits, c, S * T); take(st.last_frame, c, S * T);
     take(st.tentative, c, S * T); take(st.tracked, c, S * T); take(st.has_saved, c, S * T);
     take(st.mean, c, S * T * 8); take(st.cov, c, S * T * 64);
@@ -691,7 +707,7 @@ extern "C" int st_read_debug(st_handle *h, int32_t *debug_host, int S) {
     // a side stream so that the words can be read while a kernel is still running
     cudaStream_t side;
     ST_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    cudaError_t e = cudaMemcpyAsync(debug_host, h->st.debug, sizeof(int32_t) * 8 * S, cudaMemcpyDeviceToHost, side);
+    cudaError_t e = cudaMemcpyAsync(debug_host, h->st.debug, sizeof(int32_t) * 16 * S, cudaMemcpyDeviceToHost, side);
     if (e == cudaSuccess) e = cudaStreamSynchronize(side);
     cudaStreamDestroy(side);
     return e == cudaSuccess ? ST_OK : ST_ERR_CUDA;

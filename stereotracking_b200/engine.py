@@ -99,7 +99,7 @@ class StereoTrackEngine:
         self.out_ids = torch.zeros(S, D, dtype=torch.int64, device=dev)
         self.out_counts = torch.zeros(S, dtype=torch.int32, device=dev)
         self.frame_ids = torch.zeros(S, dtype=torch.int32, device=dev)
-        self.k3_workspace = torch.zeros(2 + 2 * S * D, dtype=torch.int32, device=dev)
+        self.k3_workspace = torch.zeros(2 + 4 * S * D, dtype=torch.int32, device=dev)
         self.depth_map = None
 
     def close(self):
@@ -163,8 +163,8 @@ class StereoTrackEngine:
         d_out = d_out if d_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
         scale_out = scale_out if scale_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
         ws = self.k3_workspace
-        if ws.numel() < 2 + 2 * S * cap or ws.device != dev:
-            ws = self.k3_workspace = torch.zeros(2 + 2 * S * cap, dtype=torch.int32, device=dev)
+        if ws.numel() < 2 + 4 * S * cap or ws.device != dev:
+            ws = self.k3_workspace = torch.zeros(2 + 4 * S * cap, dtype=torch.int32, device=dev)
         _lib.check(self.lib.st_box_depth(_ptr(self._dev(depth, torch.float32)), S, Hp, Wp,
                                          _ptr(self._dev(boxes, torch.float32)),
                                          _ptr(self._dev(counts, torch.int32)), cap, _ptr(d_out),
@@ -257,7 +257,19 @@ class StereoTrackEngine:
             io._keep['obj'][l] = obj_l[l].data_ptr()
         _lib.check(self.lib.st_frame_step(self._h, raw.shape[0], C.byref(io), self._stream()), 'st_frame_step')
 
-    KERNELS_PER_FRAME = 11     # K1, K2 x4, K3 x2, K4/K5, scale, K3 x2
+    def frame_step_ptrs(self, io, n_seq, frame_ids_ptr, raw_ptr, cls_ptrs, bbox_ptrs, obj_ptrs):
+        """frame_step with raw device addresses (ints) prepared ahead of time: no tensor
+        views or torch ops on the per-frame host path, one C call."""
+        io.frame_ids = frame_ids_ptr
+        io.raw = raw_ptr
+        k = io._keep
+        for l in range(len(cls_ptrs)):
+            k['cls'][l] = cls_ptrs[l]
+            k['bbox'][l] = bbox_ptrs[l]
+            k['obj'][l] = obj_ptrs[l]
+        _lib.check(self.lib.st_frame_step(self._h, n_seq, C.byref(io), self._stream()), 'st_frame_step')
+
+    KERNELS_PER_FRAME = 13     # K1, K2 x4, K3 x3, K4/K5, scale, K3 x3
 
     def results(self):
         """Host copies of the current outputs, one dict per sequence."""
@@ -305,9 +317,10 @@ class StereoTrackEngine:
         _lib.check(self.lib.st_kalman_batch(op, n, _ptr(mean), _ptr(cov), _ptr(z), self._stream()))
 
     def debug_words(self):
-        """[S,8] diagnostic words: 5 = assignments solved, 6 = solved by the exact fallback."""
+        """[S,16] diagnostic words: 5 = assignments solved, 6 = solved by the exact
+        fallback, 8..13 = SM cycles of the last track step per phase."""
         import numpy as np
-        a = np.zeros((self.cfg.n_seq, 8), np.int32)
+        a = np.zeros((self.cfg.n_seq, 16), np.int32)
         _lib.check(self.lib.st_read_debug(self._h, a.ctypes.data_as(C.c_void_p), self.cfg.n_seq))
         return a
 
@@ -318,3 +331,85 @@ class StereoTrackEngine:
         _lib.check(self.lib.st_lapjv_batch(self._h, B, R, Cc, _ptr(self._dev(cost, torch.float32)),
                                            float(cost_limit), int(mode), _ptr(x), _ptr(y), self._stream()))
         return x, y
+
+
+class LockstepGroups:
+    """S sequences split into G independent lockstep groups, one handle and one
+    CUDA stream per group.  Sequences never interact (the reference shards whole
+    videos across ranks, mmtrack/datasets/samplers/video_sampler.py:50-69), so the
+    latency-bound stages of one group (assignment, per-box depth of a few large
+    boxes) overlap with the bandwidth-bound stages of another instead of leaving
+    the GPU idle.  No cross-group synchronisation happens on the data path."""
+
+    def __init__(self, n_seq, n_groups=4, device='cuda:0', **cfg_kw):
+        n_groups = max(1, min(n_groups, n_seq))
+        base, extra = divmod(n_seq, n_groups)
+        self.sizes = [base + (1 if g < extra else 0) for g in range(n_groups)]
+        self.offsets = [sum(self.sizes[:g]) for g in range(n_groups)]
+        self.device = torch.device(device)
+        self.engines = [StereoTrackEngine(EngineConfig(n_seq=sz, **cfg_kw), device=device) for sz in self.sizes]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.sizes]
+        self.ios = None
+
+    def bind(self, raw_shape, level_shapes, num_classes=1):
+        _, H, W = raw_shape
+        self.ios = [e.make_frame_io((sz, H, W), level_shapes, num_classes) for e, sz in zip(self.engines, self.sizes)]
+
+    def frame_step(self, raw, cls_l, bbox_l, obj_l, frame_id, wait_event=None):
+        """Issue one lockstep frame of every group on its own stream.  Inputs are
+        full [S,...] device tensors (sliced per group, no copies)."""
+        for eng, io, st, a, sz in zip(self.engines, self.ios, self.streams, self.offsets, self.sizes):
+            with torch.cuda.stream(st):
+                if wait_event is not None:
+                    st.wait_event(wait_event)
+                eng.frame_ids.fill_(frame_id)
+                eng.frame_step(io, raw[a:a + sz], [c[a:a + sz] for c in cls_l], [c[a:a + sz] for c in bbox_l],
+                               [c[a:a + sz] for c in obj_l])
+
+    def plan(self, raw, cls_l, bbox_l, obj_l, first_frame_id=0):
+        """Precompute the device addresses of every (frame, group) slice of resident
+        inputs raw [F,S,H,W], heads [F,S,C,h,w] and of a frame-id table, so that
+        ``run_plan`` issues a frame with one C call per group and no torch ops."""
+        F = raw.shape[0]
+        self._fid = [torch.arange(first_frame_id, first_frame_id + F, dtype=torch.int32, device=self.device)
+                     [:, None].repeat(1, sz).contiguous() for sz in self.sizes]
+        plan = []
+        for f in range(F):
+            row = []
+            for g, (a, sz) in enumerate(zip(self.offsets, self.sizes)):
+                row.append((self._fid[g][f].data_ptr(), raw[f, a:a + sz].data_ptr(),
+                            [c[f, a:a + sz].data_ptr() for c in cls_l], [c[f, a:a + sz].data_ptr() for c in bbox_l],
+                            [c[f, a:a + sz].data_ptr() for c in obj_l]))
+            plan.append(row)
+        self._plan = plan
+        self._plan_keepalive = (raw, cls_l, bbox_l, obj_l)
+        return plan
+
+    def run_plan(self, f):
+        for eng, io, st, sz, args in zip(self.engines, self.ios, self.streams, self.sizes, self._plan[f]):
+            with torch.cuda.stream(st):
+                eng.frame_step_ptrs(io, sz, *args)
+
+    def join(self, stream=None):
+        stream = stream or torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            stream.wait_stream(st)
+
+    def fork(self, stream=None):
+        stream = stream or torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(stream)
+
+    def status(self):
+        import numpy as np
+        return np.concatenate([e.status() for e in self.engines])
+
+    def results(self):
+        out = []
+        for e in self.engines:
+            out.extend(e.results())
+        return out
+
+    @property
+    def kernels_per_frame(self):
+        return StereoTrackEngine.KERNELS_PER_FRAME * len(self.engines)
