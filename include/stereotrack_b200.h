@@ -110,6 +110,11 @@ int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, int Wr, int 
                   float *depth, float *disp3, uint8_t *mask,
                   float baseline, float focal_length, void *stream);
 
+/* disp2depth of OCSORT_Disparity (ocsort_disparity.py:132-134) on an already
+ * post-processed float disparity (`disp_postp[:, 0:1]`), n contiguous elements. */
+int st_disp_f32_to_depth(const float *disp, long long n, float *depth, float baseline,
+                         float focal_length, void *stream);
+
 /* K2 - replaces the detector-head post-process invoked at
  * mmtrack/models/detectors/yolo_detector_disparity_v1.py:121-122 (mmyolo
  * YOLOv5Head.predict_by_feat + YOLOXBBoxCoder.decode, mmdet

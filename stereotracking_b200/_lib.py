@@ -58,6 +58,7 @@ _SIGNATURES = {
     'st_debug_set_skip': (_I, [_I]),
     'st_debug_read_cost': (_I, [_P, _I, _P, _I]),
     'st_disp2depth': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_float, C.c_float, _P]),
+    'st_disp_f32_to_depth': (_I, [_P, C.c_longlong, _P, C.c_float, C.c_float, _P]),
     'st_decode_nms': (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, C.c_float, C.c_float, _I, _I, _I,
                            _P, _P, _P, _P, _P, _P, _P]),
     'st_box_depth': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),

@@ -161,6 +161,16 @@ k1_disp2depth_generic(const uint16_t *__restrict__ raw, int S, int H, int W, int
     }
 }
 
+// Depth from an already post-processed float disparity (the `disp_postp` tensor the
+// reference model receives, ocsort_disparity.py:115,:132-134).  Arbitrary floats, so
+// the IEEE reciprocal is used here (not the finite-domain FMA sequence above).
+__global__ void __launch_bounds__(256)
+k1_disp_f32_to_depth(const float *__restrict__ disp, long long n, float *__restrict__ depth, float bf) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        depth[i] = __fmul_rn(__frcp_rn(__fadd_rn(disp[i], 1e-6f)), bf);
+}
+
 int sm_count() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -203,5 +213,17 @@ extern "C" int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, i
         if (grid > cap) grid = cap;
         k1_disp2depth_generic<<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hr, Wr, Hp, Wp, depth, disp3, mask, bf);
     }
+    return st_last_launch();
+}
+
+extern "C" int st_disp_f32_to_depth(const float *disp, long long n, float *depth, float baseline,
+                                    float focal_length, void *stream) {
+    if (!disp || !depth || n < 0) return ST_ERR_INVALID_ARG;
+    if (n == 0) return ST_OK;
+    long long grid = (n + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    k1_disp_f32_to_depth<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(
+        disp, n, depth, (float)((double)baseline * (double)focal_length));
     return st_last_launch();
 }

@@ -392,6 +392,110 @@ __device__ __noinline__ bool solve_warp(const Problem &P, Scratch &s) {
 // row i or -1 - the same contract as solve_warp after truncation.
 constexpr double kFastEps = 1.0e-9;
 
+// Row-by-row Hungarian with the per-column state (minv, v, visited, way) held in
+// registers: lane l owns the real columns l, l+32, ... (KC per lane, C <= 32*KC).
+// The private dummy columns are not materialised: a row that joins the
+// alternating tree contributes the candidate "leave through my own dummy" with
+// slack L/2 - u_row, and all such slacks shrink together, so one warp-uniform
+// scalar (dmin, drow, dcol) tracks the best of them.  Real columns win ties
+// against dummies (lower index in the materialised formulation).
+// u (row potentials), p (column -> row) and way live in shared memory: they are
+// touched once per tree step, not per column.  Returns false on a guard.
+template <int KC>
+__device__ bool hungarian_regs(const Problem &P, volatile double *u, volatile double *v_out,
+                               volatile int *p, volatile int *way_sm, volatile int *active, int n_active) {
+    const int lane = threadIdx.x & 31;
+    const int R = P.R, C = P.C;
+    const double half = P.half, INF = 1.0e300;
+    const int VIRT = 1 << 30;                      // the virtual start column
+    double vv[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) vv[k] = 0.0;
+    for (int t = 0; t < n_active; ++t) {
+        const int row = active[t];
+        double minv[KC];
+        int way[KC];
+        unsigned used = 0u;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { minv[k] = INF; way[k] = VIRT; }
+        int j0 = VIRT, i0 = row;
+        double dmin = half - u[row];               // the new row's own dummy
+        int drow = row, dcol = VIRT;
+        bool to_dummy = false;
+        int guard = 0;
+        while (true) {
+            if (++guard > R + C + 2) return false;
+            const double ui0 = u[i0];
+            double best = INF;
+            int bj = -1;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int j = lane + 32 * k;
+                if (j < C && !((used >> k) & 1u)) {
+                    const double cur = ((double)P.cost[(long long)i0 * C + j] - half) - ui0 - vv[k];
+                    if (cur < minv[k]) { minv[k] = cur; way[k] = j0; }
+                    if (minv[k] < best) { best = minv[k]; bj = j; }
+                }
+            }
+            for (int o = 16; o; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (pair_less(ob, oj, best, bj)) { best = ob; bj = oj; }
+            }
+            to_dummy = bj < 0 || dmin < best;
+            const double delta = to_dummy ? dmin : best;
+            if (!(delta < INF)) return false;
+            // dual update
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int j = lane + 32 * k;
+                if (j < C) {
+                    if ((used >> k) & 1u) { u[p[j]] += delta; vv[k] -= delta; }
+                    else minv[k] -= delta;
+                }
+            }
+            if (lane == 0) u[row] += delta;
+            dmin -= delta;
+            __syncwarp();
+            if (to_dummy) break;
+            j0 = bj;
+            if ((j0 & 31) == lane) used |= 1u << (j0 >> 5);
+            i0 = p[j0];
+            if (i0 < 0) break;                     // free real column: augment
+            const double cand = half - u[i0];
+            if (cand < dmin) { dmin = cand; drow = i0; dcol = j0; }
+        }
+        // publish `way` and flip the alternating path (lane 0)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const int j = lane + 32 * k;
+            if (j < C) way_sm[j] = way[k];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int jc = to_dummy ? dcol : j0;         // column that receives a new row (VIRT: none)
+            if (to_dummy && dcol != VIRT) {
+                // drow leaves its column for its dummy; that column is re-filled along the path
+            }
+            int steps = 0;
+            while (jc != VIRT && steps++ <= R + C) {
+                const int jp = way_sm[jc];
+                p[jc] = jp == VIRT ? row : p[jp];
+                jc = jp;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int j = lane + 32 * k;
+        if (j < C) v_out[j] = vv[k];
+    }
+    for (int i = lane; i < R; i += 32) v_out[C + i] = 0.0;     // dummy columns keep v = 0
+    __syncwarp();
+    return true;
+}
+
 __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     const int lane = threadIdx.x & 31;
     const int R = P.R, C = P.C, m = R + C;
@@ -430,6 +534,17 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
         return (j - C == i) ? half : INF;
     };
     // ---- Hungarian, rows inserted one by one ---------------------------------------------
+    bool solved = false;
+    if (C <= 256) {
+        bool ok;
+        if (C <= 32) ok = hungarian_regs<1>(P, u, v, p, way, active, n_active);
+        else if (C <= 64) ok = hungarian_regs<2>(P, u, v, p, way, active, n_active);
+        else if (C <= 128) ok = hungarian_regs<4>(P, u, v, p, way, active, n_active);
+        else ok = hungarian_regs<8>(P, u, v, p, way, active, n_active);
+        if (!ok) return false;
+        solved = true;
+    }
+    if (!solved) {
     for (int t = 0; t < n_active; ++t) {
         const int row = active[t];
         for (int j = lane; j < m; j += 32) { minv[j] = INF; used[j] = 0; }
@@ -483,6 +598,7 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
             }
         }
         __syncwarp();
+    }
     }
     // ---- uniqueness certificate ---------------------------------------------------------
     // sigma[i] = column of row i (own dummy C+i when unmatched); arcs sigma(i) -> j for

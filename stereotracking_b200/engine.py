@@ -136,6 +136,14 @@ class StereoTrackEngine:
                                           self._stream()), 'st_disp2depth')
         return depth, disp3, mask
 
+    def disp_to_depth(self, disp, out=None):
+        """float disparity (any shape, contiguous) -> depth, ocsort_disparity.py:132-134."""
+        self._dev(disp, torch.float32)
+        out = out if out is not None else torch.empty_like(disp)
+        _lib.check(self.lib.st_disp_f32_to_depth(_ptr(disp), disp.numel(), _ptr(out), self.cfg.baseline,
+                                                 self.cfg.focal_length, self._stream()), 'st_disp_f32_to_depth')
+        return out
+
     # ---- K2 ----------------------------------------------------------------------
     def decode_nms(self, cls_l, bbox_l, obj_l, ori_hw, scale_factor=(1.0, 1.0)):
         """Per-level head maps [S,C,h,w] -> fills det_* buffers; returns views."""

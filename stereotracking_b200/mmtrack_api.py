@@ -1,0 +1,234 @@
+"""Drop-in classes for the reference's registry API (the boundary of the path).
+
+Same type names, constructor keywords, call signatures and error behaviour as
+
+  OCSORTTracker_Disparity  mmtrack/models/trackers/ocsort_tracker_disparity.py:20
+      ctor :42-52 (+ KalmanTrackerBase kalman_tracker_base.py:33-47, BaseTracker
+      base_tracker.py:22-32), track() :345-352, reset() base_tracker.py:34-37
+  OCSORT_Disparity         mmtrack/models/mot/ocsort_disparity.py:16
+      ctor :30-40, predict() :51-111, bbox_postp_depth :113-130
+  KalmanFilter             mmtrack/models/motion/kalman_filter.py:12
+
+so a config such as configs/stereo_tracking/ocsort/
+yolox_s_mmyolo_mot_airdrone_disp.py builds them through ``MODELS.build`` /
+``TASK_UTILS.build`` unchanged.  All arithmetic runs in the CUDA library through
+the C ABI (include/stereotrack_b200.h); there is no CPU or PyTorch fallback -
+constructing a tracker without the library or without a GPU raises.
+One tracker instance follows one sequence, as in the reference; the batched
+lockstep form is ``stereotracking_b200.engine``.
+"""
+import torch
+
+from . import _lib
+from .compat import MODELS, TASK_UTILS, InstanceData
+from .engine import EngineConfig, StereoTrackEngine
+
+
+@TASK_UTILS.register_module()
+class KalmanFilter:
+    """Constant-velocity Kalman filter on (cx, cy, a, h) (kalman_filter.py:12-58).
+
+    The tracker keeps its Kalman state on the device and never calls this object;
+    it exists so that ``motion=dict(type='KalmanFilter')`` keeps building and so
+    that user code calling initiate / predict / update gets the same numbers
+    (float64, computed by the CUDA kernels, one warp per track)."""
+    chi2inv95 = {1: 3.8415, 2: 5.9915, 3: 7.8147, 4: 9.4877, 5: 11.070, 6: 12.592, 7: 14.067, 8: 15.507, 9: 16.919}
+
+    def __init__(self, center_only: bool = False, use_nsa: bool = False):
+        if use_nsa:
+            raise NotImplementedError('use_nsa=True is not configured anywhere under configs/stereo_tracking')
+        self.center_only = center_only
+        self.gating_threshold = self.chi2inv95[2 if center_only else 4]
+        self.use_nsa = use_nsa
+        self._lib = _lib.lib()
+
+    def _run(self, op, mean, cov, z):
+        import ctypes as C
+        import numpy as np
+        if not torch.cuda.is_available():
+            raise _lib.StereoTrackError('KalmanFilter needs a CUDA device (no CPU fallback)')
+        m = torch.as_tensor(np.asarray(mean, np.float64).reshape(1, 8)).cuda().contiguous()
+        c = torch.as_tensor(np.asarray(cov, np.float64).reshape(1, 64)).cuda().contiguous()
+        zt = None if z is None else torch.as_tensor(np.asarray(z, np.float32).reshape(1, 4)).cuda().contiguous()
+        _lib.check(self._lib.st_kalman_batch(op, 1, C.c_void_p(m.data_ptr()), C.c_void_p(c.data_ptr()),
+                                             C.c_void_p(0 if zt is None else zt.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return m.cpu().numpy().reshape(8), c.cpu().numpy().reshape(8, 8)
+
+    def initiate(self, measurement):
+        import numpy as np
+        return self._run(0, np.zeros(8), np.zeros((8, 8)), measurement)
+
+    def predict(self, mean, covariance):
+        return self._run(1, mean, covariance, None)
+
+    def update(self, mean, covariance, measurement, bbox_score: float = 0.):
+        return self._run(2, mean, covariance, measurement)
+
+
+@MODELS.register_module()
+class OCSORTTracker_Disparity:
+    """OC-SORT tracker carrying per-detection ``scales`` / ``depth``."""
+
+    def __init__(self, obj_score_thr=0.3, init_track_thr=0.7, weight_iou_with_det_scores=True,
+                 match_iou_thr=0.3, num_tentatives=3, vel_consist_weight=0.2, vel_delta_t=3, cmc=None,
+                 reid=None, momentums=None, num_frames_retain=10, max_tracks=256, max_dets=256,
+                 device='cuda:0', **kwargs):
+        if kwargs:
+            raise TypeError(f'unexpected keyword arguments {sorted(kwargs)}')
+        if momentums is not None:
+            assert isinstance(momentums, dict), 'momentums must be a dict'   # base_tracker.py:26-27
+        method = cmc.get('method') if cmc is not None else None                # :63-76
+        if method not in (None, 'glme_affine'):
+            raise ValueError(f"Unknown cmc method '{method}', expected 'glme_affine' or None.")
+        if method is not None:
+            raise NotImplementedError("cmc=dict(method='glme_affine') is a 'next' row (DESIGN.md)")
+        self.obj_score_thr, self.init_track_thr = obj_score_thr, init_track_thr
+        self.weight_iou_with_det_scores, self.match_iou_thr = weight_iou_with_det_scores, match_iou_thr
+        self.num_tentatives, self.vel_consist_weight, self.vel_delta_t = num_tentatives, vel_consist_weight, vel_delta_t
+        self.num_frames_retain, self.momentums, self.reid, self.cmc_cfg = num_frames_retain, momentums, reid, cmc
+        self.fp16_enabled = False
+        self._engine = StereoTrackEngine(EngineConfig(
+            n_seq=1, max_tracks=max_tracks, max_dets=max_dets,
+            tracker=dict(obj_score_thr=obj_score_thr, init_track_thr=init_track_thr,
+                         weight_iou_with_det_scores=weight_iou_with_det_scores, match_iou_thr=match_iou_thr,
+                         num_tentatives=num_tentatives, vel_consist_weight=vel_consist_weight,
+                         vel_delta_t=vel_delta_t, num_frames_retain=num_frames_retain)), device=device)
+
+    # ---- BaseTracker surface (base_tracker.py:34-52) ---------------------------
+    @property
+    def with_cmc(self):
+        return False
+
+    def reset(self):
+        self._engine.reset()
+
+    def _state(self):
+        return self._engine.export_state(0)
+
+    @property
+    def num_tracks(self):
+        return self._state()['num_tracks']
+
+    @property
+    def empty(self):
+        return len(self._state()['ids']) == 0
+
+    @property
+    def ids(self):
+        return self._state()['ids'].tolist()
+
+    @property
+    def confirmed_ids(self):
+        st = self._state()
+        return st['ids'][~st['tentative']].tolist()
+
+    @property
+    def unconfirmed_ids(self):
+        st = self._state()
+        return st['ids'][st['tentative']].tolist()
+
+    # ---- track() (:345-618) -----------------------------------------------------
+    def track(self, model, img, feats, data_sample, data_preprocessor=None, rescale=False, **kwargs):
+        eng = self._engine
+        det = data_sample.pred_det_instances
+        frame_id = data_sample.metainfo.get('frame_id', -1)
+        n = int(det.bboxes.shape[0])
+        if n > eng.cfg.max_dets:
+            raise ValueError(f'{n} detections exceed max_dets={eng.cfg.max_dets}')
+        dev = eng.device
+        eng.det_inflated[0, :n] = det.bboxes.to(dev, torch.float32)
+        eng.det_scores[0, :n] = det.scores.to(dev, torch.float32)
+        eng.det_labels[0, :n] = det.labels.to(dev, torch.int64)
+        eng.det_scales[0, :n] = det.scales.to(dev, torch.float32)
+        eng.det_depth[0, :n] = det.depth.to(dev, torch.float32)
+        eng.det_counts.fill_(n)
+        eng.frame_ids.fill_(int(frame_id))
+        out = eng.track_step(eng.frame_ids, eng.det_inflated, eng.det_scores, eng.det_labels, eng.det_scales,
+                             eng.det_depth, eng.det_counts)
+        m = int(out['counts'][0])
+        status = int(eng.status()[0])
+        if status:
+            raise _lib.StereoTrackError(f'tracker capacity exceeded (status bits {status}); raise max_tracks / max_dets')
+        tgt = det.bboxes.device
+        res = InstanceData()
+        res.bboxes = out['bboxes'][0, :m].clone().to(tgt)
+        res.labels = out['labels'][0, :m].clone().to(tgt)
+        res.scores = out['scores'][0, :m].clone().to(tgt)
+        res.scales = out['scales'][0, :m].clone().to(tgt)
+        res.depth = out['depth'][0, :m].clone().to(tgt)
+        res.instances_id = out['instances_id'][0, :m].clone().to(tgt)
+        return res
+
+
+@MODELS.register_module()
+class OCSORT_Disparity:
+    """Model shell of the hot path: detector -> depth -> per-box depth/scale ->
+    tracker -> deflate -> output depth (ocsort_disparity.py:51-111).  ``detector``
+    may be any object with ``predict(data, data_samples)`` returning a list whose
+    first element has ``pred_instances`` (the reference PyTorch detector stays
+    the detector; it is not part of this path)."""
+
+    def __init__(self, detector=None, tracker=None, motion=None, data_preprocessor=None, init_cfg=None,
+                 baseline: float = 0.25, focal_length: int = 640):
+        self.detector = MODELS.build(detector) if isinstance(detector, dict) else detector
+        self.motion = TASK_UTILS.build(motion) if isinstance(motion, dict) else motion
+        self.tracker = MODELS.build(tracker) if isinstance(tracker, dict) else tracker
+        self.baseline, self.focal_length = baseline, focal_length
+        if self.tracker is not None:
+            self.tracker._engine.cfg.baseline = float(baseline)
+            self.tracker._engine.cfg.focal_length = float(focal_length)
+
+    def disp2depth(self, disp):
+        return self.tracker._engine.disp_to_depth(disp.contiguous().float())
+
+    def bbox_postp_depth(self, pred_instances, disp, gt_depth=None):
+        """:113-130 - returns (pred_instances with inflated bboxes / scales / depth, depth dict)."""
+        eng = self.tracker._engine
+        depth = self.disp2depth(disp[:, 0:1, :, :]).reshape(1, disp.shape[-2], disp.shape[-1])
+        boxes = pred_instances['bboxes']
+        n = int(boxes.shape[0])
+        cap = max(n, 1)
+        b = torch.zeros(1, cap, 4, dtype=torch.float32, device=eng.device)
+        b[0, :n] = boxes.to(eng.device, torch.float32)
+        cnt = torch.tensor([n], dtype=torch.int32, device=eng.device)
+        infl = torch.zeros_like(b)
+        d, sc, _ = eng.box_depth(depth, b, cnt, inflated_out=infl)
+        values = dict(d_values=d[0, :n].tolist())
+        if gt_depth is not None:
+            gd, _, _ = eng.box_depth(gt_depth.reshape(1, gt_depth.shape[-2], gt_depth.shape[-1]).contiguous().float(), b, cnt)
+            values['gt_d_values'] = gd[0, :n].tolist()
+        pred_instances['bboxes'] = infl[0, :n].to(boxes)
+        pred_instances['scales'] = sc[0, :n].to(boxes)
+        pred_instances['depth'] = d[0, :n].to(boxes)
+        return pred_instances, values
+
+    def predict(self, inputs, data_samples, **kwargs):
+        img, disp_postp, disp_mask = inputs['img'], inputs['disp_postp'], inputs['disp_mask']
+        depth_postp = inputs.get('depth_postp', None)
+        assert img.dim() == 5, 'The img must be 5D Tensor (N, T, C, H, W).'
+        assert img.size(0) == 1, 'OCSort inference only support 1 batch size per gpu for now.'
+        img, disp_postp, disp_mask = img[0], disp_postp[0], disp_mask[0]
+        if depth_postp is not None:
+            depth_postp = depth_postp[0]
+        assert len(data_samples) == 1, 'OCSort inference only support 1 batch size per gpu for now.'
+        sample = data_samples[0]
+        det_results = self.detector.predict(dict(img=img, disp_postp=disp_postp, disp_mask=disp_mask), data_samples)
+        assert len(det_results) == 1, 'Batch inference is not supported.'
+        scaled, _ = self.bbox_postp_depth(det_results[0].pred_instances.clone(), disp_postp, depth_postp)
+        sample.pred_det_instances = scaled
+        tracks = self.tracker.track(model=self, img=img, feats=None, data_sample=sample, **kwargs)
+        eng = self.tracker._engine
+        m = int(tracks.bboxes.shape[0])
+        cnt = torch.tensor([m], dtype=torch.int32, device=eng.device)
+        bb = torch.zeros(1, max(m, 1), 4, dtype=torch.float32, device=eng.device)
+        sc = torch.ones(1, max(m, 1), dtype=torch.float32, device=eng.device)
+        bb[0, :m] = tracks.bboxes.to(eng.device)
+        sc[0, :m] = tracks.scales.to(eng.device)
+        tracks.bboxes = eng.scale_boxes(bb, sc, cnt, True)[0, :m].to(tracks.scores)      # :96-97
+        _, depth = self.bbox_postp_depth(tracks.clone(), disp_postp, depth_postp)       # :100-101
+        tracks['depth'] = depth['d_values']
+        tracks['gt_depth'] = depth.get('gt_d_values', depth['d_values'])
+        sample.pred_det_instances = det_results[0].pred_instances.clone()
+        sample.pred_track_instances = tracks
+        return [sample]
