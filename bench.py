@@ -363,7 +363,7 @@ def main():
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
             higher_is_better=True, scaling='weak', vs_baseline=None,
             dtype='f32 (u16 disparity in, f64 Kalman state and assignment)', data='synthetic', config=config,
-            roofline=dict(kernel='k1_disp2depth_vec8', bound='hbm', achieved=k1_gbs, peak=peak, unit='GB/s',
+            roofline=dict(kernel='k1_disp2depth_flat', bound='hbm', achieved=k1_gbs, peak=peak, unit='GB/s',
                           frac=k1_gbs / peak, traffic=None, peak_source=peak_src,
                           note='HBM-bound kernel of the path (north_star), timed with CUDA events in a serial '
                                'single-stream pass over the same frames; "kernels" gives every stage of that pass'),

@@ -9,19 +9,14 @@
 
 namespace {
 
-__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ void st_stream_u2(uint2 *p, uint2 v) {
-    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};"
-                 :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2 *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
 }
 
 // Correctly rounded float32 reciprocal of x = raw/16 + 1e-6 without the XU
@@ -52,77 +47,113 @@ __device__ __forceinline__ void convert(uint32_t raw, float bf, float &disp, flo
     depth = __fmul_rn(rcp_rn_fma(__fadd_rn(disp, 1e-6f)), bf);
 }
 
-constexpr int kUnroll = 4;    // independent 128-bit loads in flight per thread
-constexpr unsigned kChunk = 256 * kUnroll;   // work items per CTA iteration
 
-// Fast path: no resize, W and Wp multiples of 8, 16-byte aligned rows.
-// A work item is 8 consecutive pixels of a padded output row (one 128-bit
-// load, two 128-bit depth stores); a CTA iteration covers kChunk consecutive
-// items of one image, so consecutive threads touch consecutive 16-byte words.
-// All index arithmetic is 32-bit.
+// The same arithmetic on the two u16 of one 32-bit word with the packed
+// float32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2 round each component
+// exactly like the scalar forms): half the issue slots per pixel - the kernel is
+// issue-limited, not DRAM-limited, until it is down to ~12 instructions per pixel.
+// fr * 0.0625 is exact, so fma(fr, 0.0625, 1e-6) == fadd(fmul(fr, 0.0625), 1e-6).
+// A pixel of raw 65535 gets disp 0 and therefore exactly the padding depth.
+// (A MUFU.RCP seed + one Newton step is also bit-exact on all 65536 codes on the
+// B200 and 17 % fewer instructions, but measured the same 67.7 us: after the
+// packed rewrite the kernel is no longer issue-limited, so the FMA-only form,
+// whose exactness tests/test_k1_reciprocal.py proves on the CPU, is kept.)
+__device__ __forceinline__ void convert2(uint32_t w, float2 bf2, float pad_depth, float2 &disp, float2 &depth,
+                                         uint32_t &valid_lo, uint32_t &valid_hi) {
+    const uint32_t lo = __byte_perm(w, 0x4B000000u, 0x7410), hi = __byte_perm(w, 0x4B000000u, 0x7432);
+    valid_lo = lo != 0x4B00FFFFu;
+    valid_hi = hi != 0x4B00FFFFu;
+    const float2 fr = __fadd2_rn(make_float2(__uint_as_float(lo), __uint_as_float(hi)),
+                                 make_float2(-8388608.0f, -8388608.0f));
+    disp = __fmul2_rn(fr, make_float2(0.0625f, 0.0625f));
+    const float2 x = __ffma2_rn(fr, make_float2(0.0625f, 0.0625f), make_float2(1e-6f, 1e-6f));
+    float2 r = make_float2(__uint_as_float(0x7EF311C7u - __float_as_uint(x.x)),
+                           __uint_as_float(0x7EF311C7u - __float_as_uint(x.y)));
+    const float2 nx = make_float2(-x.x, -x.y), one = make_float2(1.0f, 1.0f);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const float2 e = __ffma2_rn(nx, r, one);
+        r = __ffma2_rn(r, e, r);
+    }
+    depth = __fmul2_rn(r, bf2);
+    if (!valid_lo) { depth.x = pad_depth; disp.x = 0.0f; }     // 65535 -> disp 0 -> the padding depth
+    if (!valid_hi) { depth.y = pad_depth; disp.y = 0.0f; }
+}
+
+// Fast path: no resize, W == Wp (no column padding), W a multiple of 32, 8-byte
+// aligned images.  The padded output of all S images is one flat array of 4-pixel
+// items; a warp owns 64 consecutive items per step and each lane converts item
+// `lane` and item `lane + 32` of them: every warp-level access is one contiguous
+// run (two 256 B loads, two 512 B stores) and the index arithmetic is shared by 8
+// pixels.  (An earlier version gave each thread 8 consecutive pixels: its two
+// float4 stores sat 32 B apart, every store instruction filled half of each
+// 32-byte sector and the stores alone ran at 3.2 TB/s against 6.5 for a memset.)
+// Because W == Wp, item li of an image reads the raw words at the same linear
+// offset li while li < H * W / 4; the pad rows behave like invalid pixels (raw
+// 65535 gives exactly the padding depth, disp 0 and mask 0), so they need no branch.
+// The grid is the resident CTA count (SMs x occupancy) and strides over the
+// flat space, so every CTA gets the same share to within one step.
+// Measured on a B200 at the C2 shape (359 MB per launch, tools/bench_k1.py): 67.7 us =
+// 5.3 TB/s; a torch copy of the same byte count takes 61.4 us, a memset of the
+// written bytes alone 36.9 us, this kernel with its loads disabled 43 us and with
+// its stores disabled 33 us.
 template <bool kDisp3, bool kMask>
-__global__ void __launch_bounds__(256)
-k1_disp2depth_vec8(const uint16_t *__restrict__ raw, int S, int H, int W, int Hp, int Wp,
+__global__ void __launch_bounds__(256, (kDisp3 || kMask) ? 4 : 6)
+k1_disp2depth_flat(const uint16_t *__restrict__ raw, int S, int H, int Hp, int Wp,
                    float *__restrict__ depth, float *__restrict__ disp3,
-                   uint8_t *__restrict__ mask, float bf, unsigned long long div_magic) {
-    const unsigned w8 = W >> 3, wp8 = Wp >> 3;
-    const unsigned items = (unsigned)Hp * wp8;
-    const unsigned chunks_per_img = (items + kChunk - 1) / kChunk;
-    const unsigned total_chunks = (unsigned)S * chunks_per_img;
+                   uint8_t *__restrict__ mask, float bf, unsigned total_items) {
+    constexpr int kUnroll = (kDisp3 || kMask) ? 2 : 4;      // steps in flight: 2 x 64-bit loads each
+    const unsigned w4 = Wp >> 2;
+    const unsigned items = (unsigned)Hp * w4, valid_items = (unsigned)H * w4;
+    const unsigned stride = gridDim.x * 512u;                    // items per grid step
     const size_t plane = (size_t)Hp * Wp;
     const float pad_depth = __fmul_rn(rcp_rn_fma(1e-6f), bf);
-    for (unsigned chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
-        const unsigned s = chunk / chunks_per_img;
-        const unsigned base = (chunk - s * chunks_per_img) * kChunk + threadIdx.x;
-        const uint16_t *src = raw + (size_t)s * H * W;
-        float *dst = depth + (size_t)s * plane;
-        {
-            uint4 v[kUnroll];
-            unsigned off[kUnroll];          // element offset inside the padded image
-            bool live[kUnroll], inside[kUnroll];
+    const float2 bf2 = make_float2(bf, bf);
+    const unsigned ds = stride / items, dr = stride - ds * items;
+    // this lane's first item: warp w of the CTA owns items [512 b + 64 w, +64)
+    unsigned i = blockIdx.x * 512u + (threadIdx.x >> 5) * 64u + (threadIdx.x & 31u);
+    unsigned s = i / items, li = i - s * items;
+    const uint2 *src = reinterpret_cast<const uint2 *>(raw) + (size_t)s * valid_items + li;
+    const long long src_step = (long long)ds * valid_items + dr;
+    const long long src_wrap = (long long)valid_items - (long long)items;     // applied when li wraps
+    while (i < total_items) {
+        uint2 v[kUnroll][2];
+        unsigned sq[kUnroll], lq[kUnroll];
+        const unsigned i0 = i;
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const unsigned li = base + u * 256;
-                // li / wp8 as a multiply-high (exact for li < 2^24, wp8 < 2^16): no I2F/MUFU
-                const unsigned y = (unsigned)(((unsigned long long)li * div_magic) >> 40), x8 = li - y * wp8;
-                live[u] = li < items;
-                inside[u] = live[u] && y < (unsigned)H && x8 < w8;
-                off[u] = li * 8;
-                if (inside[u]) v[u] = ld_stream_u4(reinterpret_cast<const uint4 *>(src + (size_t)y * W + x8 * 8));
-            }
+        for (int u = 0; u < kUnroll; ++u) {
+            const bool live = i < total_items;
+            sq[u] = s; lq[u] = li;
+            v[u][0] = v[u][1] = make_uint2(0xffffffffu, 0xffffffffu);
+            if (live && li < valid_items) v[u][0] = ld_stream_u2(src);
+            if (live && li + 32u < valid_items) v[u][1] = ld_stream_u2(src + 32);
+            i += stride;
+            li += dr;
+            src += src_step;
+            if (li >= items) { li -= items; src += src_wrap; ++s; }
+            s += ds;
+        }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (!live[u]) continue;
-                float dz[8], dp[8];
-                uint32_t mk[8];
-                if (inside[u]) {
-                    const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        for (int u = 0; u < kUnroll; ++u) {
+            const unsigned iu = i0 + u * stride;
+            if (iu >= total_items) break;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        convert(w[k] & 0xffffu, bf, dp[2 * k], dz[2 * k], mk[2 * k]);
-                        convert(w[k] >> 16, bf, dp[2 * k + 1], dz[2 * k + 1], mk[2 * k + 1]);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { dz[k] = pad_depth; dp[k] = 0.0f; mk[k] = 0; }
-                }
-                float4 *o = reinterpret_cast<float4 *>(dst + off[u]);
-                st_stream_f4(o, make_float4(dz[0], dz[1], dz[2], dz[3]));
-                st_stream_f4(o + 1, make_float4(dz[4], dz[5], dz[6], dz[7]));
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                float2 dz[2], dp[2];
+                uint32_t mk[4];
+                convert2(v[u][hlf].x, bf2, pad_depth, dp[0], dz[0], mk[0], mk[1]);
+                convert2(v[u][hlf].y, bf2, pad_depth, dp[1], dz[1], mk[2], mk[3]);
+                float4 *o = reinterpret_cast<float4 *>(depth) + (size_t)iu + hlf * 32;
+                st_stream_f4(o, make_float4(dz[0].x, dz[0].y, dz[1].x, dz[1].y));
                 if (kDisp3) {
+                    const float4 d0 = make_float4(dp[0].x, dp[0].y, dp[1].x, dp[1].y);
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float4 *q = reinterpret_cast<float4 *>(disp3 + ((size_t)s * 3 + c) * plane + off[u]);
-                        st_stream_f4(q, make_float4(dp[0], dp[1], dp[2], dp[3]));
-                        st_stream_f4(q + 1, make_float4(dp[4], dp[5], dp[6], dp[7]));
-                    }
+                    for (int c = 0; c < 3; ++c)
+                        reinterpret_cast<float4 *>(disp3 + ((size_t)sq[u] * 3 + c) * plane)[lq[u] + hlf * 32] = d0;
                 }
-                if (kMask) {
-                    uint2 m;
-                    m.x = mk[0] | (mk[1] << 8) | (mk[2] << 16) | (mk[3] << 24);
-                    m.y = mk[4] | (mk[5] << 8) | (mk[6] << 16) | (mk[7] << 24);
-                    st_stream_u2(reinterpret_cast<uint2 *>(mask + (size_t)s * plane + off[u]), m);
-                }
+                if (kMask)
+                    reinterpret_cast<uint32_t *>(mask + (size_t)sq[u] * plane)[lq[u] + hlf * 32] =
+                        mk[0] | (mk[1] << 8) | (mk[2] << 16) | (mk[3] << 24);
             }
         }
     }
@@ -188,24 +219,29 @@ extern "C" int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, i
     if (S == 0) return ST_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const float bf = (float)((double)baseline * (double)focal_length);
-    const bool aligned = ((uintptr_t)raw % 16 == 0) && ((uintptr_t)depth % 16 == 0) &&
-                         (!disp3 || (uintptr_t)disp3 % 16 == 0) &&
-                         (!mask || (uintptr_t)mask % 8 == 0);
-    const bool small = (long long)Hp * (Wp / 8) < (1ll << 24) && Wp / 8 < 65536 && (long long)H * W < (1ll << 31);
-    const unsigned long long magic = ((1ull << 40) + (unsigned long long)(Wp / 8) - 1) / (unsigned long long)(Wp / 8);
-    if (Hr == H && Wr == W && (W % 8 == 0) && (Wp % 8 == 0) && aligned && small) {
-        const long long tiles = (long long)S * (((long long)Hp * (Wp / 8) + kChunk - 1) / kChunk);
-        // grid = a multiple of the SM count: 8 resident CTAs of 256 threads per SM
-        long long grid = (long long)sm_count() * 8;
-        if (grid > tiles) grid = tiles;
-        if (disp3 && mask)
-            k1_disp2depth_vec8<true, true><<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf, magic);
-        else if (disp3)
-            k1_disp2depth_vec8<true, false><<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf, magic);
-        else if (mask)
-            k1_disp2depth_vec8<false, true><<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf, magic);
-        else
-            k1_disp2depth_vec8<false, false><<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hp, Wp, depth, disp3, mask, bf, magic);
+    const bool aligned = ((uintptr_t)raw % 8 == 0) && ((uintptr_t)depth % 16 == 0) &&
+                         (!disp3 || (uintptr_t)disp3 % 16 == 0) && (!mask || (uintptr_t)mask % 4 == 0);
+    const long long total_items = (long long)S * Hp * (Wp / 4);
+    const bool small = total_items < (1ll << 31) - (1ll << 26);
+    if (Hr == H && Wr == W && W == Wp && (Wp % 4 == 0) && (((long long)Hp * (Wp / 4)) % 64 == 0) && aligned && small) {
+        // grid = the resident CTA count (SMs x occupancy of this instantiation), never more
+        auto launch = [&](auto kernel) {
+            static long long resident = 0;               // per instantiation; one device per process
+            if (!resident) {
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1)
+                    per_sm = 4;
+                resident = (long long)sm_count() * per_sm;
+            }
+            long long grid = resident;
+            const long long need = (total_items + 511) / 512;
+            if (grid > need) grid = need;
+            kernel<<<(int)grid, 256, 0, st>>>(raw, S, H, Hp, Wp, depth, disp3, mask, bf, (unsigned)total_items);
+        };
+        if (disp3 && mask) launch(k1_disp2depth_flat<true, true>);
+        else if (disp3) launch(k1_disp2depth_flat<true, false>);
+        else if (mask) launch(k1_disp2depth_flat<false, true>);
+        else launch(k1_disp2depth_flat<false, false>);
     } else {
         const long long total = (long long)S * Hp * Wp;
         long long grid = (total + 255) / 256;
