@@ -43,7 +43,8 @@ def parse():
     ap.add_argument('--workload', default=WORKLOAD)
     ap.add_argument('--cpu-seqs', type=int, default=0, help='sequences of the CPU sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--groups', type=int, default=4, help='independent lockstep groups (streams) per GPU')
+    ap.add_argument('--groups', type=int, default=1, help='independent lockstep groups (handles) per GPU')
+    ap.add_argument('--depth', type=int, default=3, help='frames in flight in the frame pipeline (1 = no overlap)')
     return ap.parse_args()
 
 
@@ -181,9 +182,10 @@ def main():
                   sequences_per_gpu=S, frames_per_step=S * max(world, 1), priors_per_frame=cfg.num_priors,
                   tracker='OCSORTTracker_Disparity (configs/stereo_tracking/ocsort/yolox_s_mmyolo_mot_airdrone_disp.py)',
                   l2_policy='every step reads fresh frames (147 MB/step at C2) > 126 MB L2; no flush needed',
-                  groups_per_gpu=args.groups,
-                  parallelism=f'{world} GPU(s) x {args.groups} lockstep groups (one stream each) x {S // max(args.groups, 1)} '
-                              f'sequences, no data-path collective')
+                  groups_per_gpu=args.groups, pipeline_depth=args.depth,
+                  parallelism=f'{world} GPU(s) x {args.groups} lockstep group(s) x {S // max(args.groups, 1)} '
+                              f'sequences, frame pipeline of depth {args.depth} (K1/K2/K3 of later frames overlap the '
+                              f'tracker of earlier ones), no data-path collective')
 
     if args.impl == 'reference':
         if rank != 0:
@@ -224,7 +226,8 @@ def main():
     eng = StereoTrackEngine(EngineConfig(n_seq=S, max_dets=256, max_tracks=256, max_candidates=2048), device=dev)
     io = eng.make_frame_io(raw.shape[1:], [c.shape[-2:] for c in cls])
     stream = torch.cuda.current_stream(dev)
-    groups = LockstepGroups(S, args.groups, device=dev, max_dets=256, max_tracks=256, max_candidates=2048)
+    groups = LockstepGroups(S, args.groups, device=dev, depth=args.depth, max_dets=256, max_tracks=256,
+                            max_candidates=2048)
     groups.bind(raw.shape[1:], [c.shape[-2:] for c in cls])
     groups.plan(raw, cls, box, obj)      # device addresses of every (frame, group) slice, computed once
 
@@ -236,7 +239,7 @@ def main():
     def run_steps(f0, f1, events=None):
         for f in range(f0, f1):
             if events is None:
-                # headline path: every group advances on its own stream, no cross-group sync
+                # headline path: one C call per group queues the frame on the frame pipeline
                 groups.run_plan(f)
                 continue
             eng.frame_ids.fill_(f)
@@ -276,7 +279,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     status = groups.status()
     dbg = np.concatenate([e.debug_words() for e in groups.engines])
-    tracked_rows = int(sum(int(e.out_counts.sum()) for e in groups.engines))
+    tracked_rows = int(sum(len(r['instances_id']) for r in groups.results()))
 
     # ---- per-kernel timing (second pass over the same frames, same state reset by frame 0) ----
     stage_events = []
@@ -290,36 +293,60 @@ def main():
     stage_avg = stage_ms.mean(0)
 
     # ---- end to end through the public call with HOST buffers ---------------------
+    # Per frame: pinned host -> device copy of the frame's inputs (copy stream), the
+    # frame on the group's frame pipeline, device -> pinned host copy of its tracks
+    # (read-back stream).  `depth` frames are in flight; the host consumes the
+    # tracks of frame f while frame f + depth - 1 is being copied in.
+    N = args.depth
     host = dict(raw=raw.cpu().pin_memory(), cls=[c.cpu().pin_memory() for c in cls],
                 box=[c.cpu().pin_memory() for c in box], obj=[c.cpu().pin_memory() for c in obj])
-    d_raw = torch.empty_like(raw[0]); d_cls = [torch.empty_like(c[0]) for c in cls]
-    d_box = [torch.empty_like(c[0]) for c in box]; d_obj = [torch.empty_like(c[0]) for c in obj]
-    def outs_of(e):
-        return [e.out_boxes, e.out_ids, e.out_scores, e.out_labels, e.out_scales, e.out_depth, e.out_counts]
-    h_out = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs_of(e)] for e in groups.engines]
+    fid_tab = torch.arange(F, dtype=torch.int32, device=dev)[:, None].repeat(1, S).contiguous()
+    d_in = [dict(raw=torch.empty_like(raw[0]), cls=[torch.empty_like(c[0]) for c in cls],
+                 box=[torch.empty_like(c[0]) for c in box], obj=[torch.empty_like(c[0]) for c in obj])
+            for _ in range(N)]
+    h_out = [[[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in b.outputs()] for b in p.slots]
+             for p in groups.pipes]
     h2d = raw[0].numel() * 2 + sum(t[0].numel() * 4 for t in cls + box + obj)
-    d2h = sum(t.numel() * t.element_size() for e in groups.engines for t in outs_of(e))
+    d2h = sum(t.numel() * t.element_size() for p in groups.pipes for t in p.slots[0].outputs())
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    G = len(groups.pipes)
+    mk = lambda: torch.cuda.Event()
+    ev_in = [mk() for _ in range(N)]
+    ev_done = [[mk() for _ in range(G)] for _ in range(N)]
+    ev_out = [mk() for _ in range(N)]
+    for e in ev_in + ev_out + [x for row in ev_done for x in row]:
+        e.record(stream)                   # materialise the CUDA events
+    torch.cuda.synchronize(dev)
 
     def e2e_steps(f0, f1):
-        """Per frame: pinned host -> device copy of each group's inputs, the group's
-        frame step, device -> pinned host copy of its tracks, all on the group's
-        stream; the host waits for every group before the next frame."""
-        for f in range(f0, f1):
-            for g, (e, io_g, st, a, sz) in enumerate(zip(groups.engines, groups.ios, groups.streams,
-                                                          groups.offsets, groups.sizes)):
-                with torch.cuda.stream(st):
-                    d_raw[a:a + sz].copy_(host['raw'][f, a:a + sz], non_blocking=True)
-                    for l in range(len(cls)):
-                        d_cls[l][a:a + sz].copy_(host['cls'][l][f, a:a + sz], non_blocking=True)
-                        d_box[l][a:a + sz].copy_(host['box'][l][f, a:a + sz], non_blocking=True)
-                        d_obj[l][a:a + sz].copy_(host['obj'][l][f, a:a + sz], non_blocking=True)
-                    e.frame_ids.fill_(f)
-                    e.frame_step(io_g, d_raw[a:a + sz], [c[a:a + sz] for c in d_cls], [c[a:a + sz] for c in d_box],
-                                 [c[a:a + sz] for c in d_obj])
-                    for t, h in zip(outs_of(e), h_out[g]):
-                        h.copy_(t, non_blocking=True)
-            for st in groups.streams:
-                st.synchronize()          # the caller consumes this frame's tracks before the next frame
+        consumed = 0
+        for k, f in enumerate(range(f0, f1)):
+            slot = groups.pipes[0].submitted % N
+            if k >= N:
+                ev_out[slot].synchronize()      # the caller has read the tracks of frame f - N
+                consumed += int(h_out[0][slot][6].sum())
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_out[slot])   # this slot's previous frame left the device
+                d = d_in[slot]
+                d['raw'].copy_(host['raw'][f], non_blocking=True)
+                for l in range(len(cls)):
+                    d['cls'][l].copy_(host['cls'][l][f], non_blocking=True)
+                    d['box'][l].copy_(host['box'][l][f], non_blocking=True)
+                    d['obj'][l].copy_(host['obj'][l][f], non_blocking=True)
+                ev_in[slot].record(s_in)
+            for g, (p, a, sz) in enumerate(zip(groups.pipes, groups.offsets, groups.sizes)):
+                p.submit(fid_tab[f, a:a + sz], d['raw'][a:a + sz], [c[a:a + sz] for c in d['cls']],
+                         [c[a:a + sz] for c in d['box']], [c[a:a + sz] for c in d['obj']],
+                         ready_event=ev_in[slot], done_event=ev_done[slot][g])
+            with torch.cuda.stream(s_out):
+                for g, p in enumerate(groups.pipes):
+                    s_out.wait_event(ev_done[slot][g])
+                    for t, hbuf in zip(p.slots[slot].outputs(), h_out[g][slot]):
+                        hbuf.copy_(t, non_blocking=True)
+                ev_out[slot].record(s_out)
+        for e in ev_out:
+            e.synchronize()                     # every frame's tracks are on the host
+        return consumed
 
     e2e_steps(0, W)
     barrier()

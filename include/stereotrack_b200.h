@@ -189,6 +189,24 @@ typedef struct st_frame_io {
  * -> deflate -> K3); replaces ocsort_disparity.py:79-109 after the backbone. */
 int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *stream);
 
+/* Software pipeline over consecutive frames of the same S sequences.  Only the
+ * tracker state couples frame f+1 to frame f (ocsort_tracker_disparity.py:345-618);
+ * K1, K2 and K3 on the detections of later frames and the deflate + K3 on the tracks
+ * of earlier frames run concurrently with it on three internal streams.  Results
+ * equal st_frame_step.  The caller owns `depth` complete st_frame_io buffer sets and
+ * passes set (k mod depth) with the k-th submit; inputs must stay valid until that
+ * frame is done.  inputs_ready / frame_done are cudaEvent_t (may be NULL): the first
+ * stage waits for inputs_ready, frame_done is recorded when every output of the
+ * frame is complete. */
+typedef struct st_pipeline st_pipeline;
+int st_pipeline_create(st_handle *h, int depth, st_pipeline **out);
+int st_pipeline_destroy(st_pipeline *p);
+int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, void *inputs_ready, void *frame_done);
+/* the pipeline's streams start after the work already queued on `stream` */
+int st_pipeline_fork(st_pipeline *p, void *stream);
+/* `stream` waits for every frame submitted so far */
+int st_pipeline_join(st_pipeline *p, void *stream);
+
 /* Debug / parity / checkpoint: copies the live tracks of sequence `seq` in
  * dict order to HOST arrays sized max_tracks (synchronises).  mean [T,8] f64,
  * cov [T,64] f64, velocity [T,2] f32, flags [T] u8 (bit0 tentative, bit1

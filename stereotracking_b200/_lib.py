@@ -65,6 +65,11 @@ _SIGNATURES = {
     'st_scale_boxes': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     'st_track_step': (_I, [_P, _I] + [_P] * 7 + [_I] + [_P] * 8),
     'st_frame_step': (_I, [_P, _I, C.POINTER(StFrameIO), _P]),
+    'st_pipeline_create': (_I, [_P, _I, C.POINTER(_P)]),
+    'st_pipeline_destroy': (_I, [_P]),
+    'st_pipeline_submit': (_I, [_P, _I, C.POINTER(StFrameIO), _P, _P]),
+    'st_pipeline_fork': (_I, [_P, _P]),
+    'st_pipeline_join': (_I, [_P, _P]),
     'st_export_state': (_I, [_P, _I] + [_P] * 8),
     'st_kalman_batch': (_I, [_I, _I, _P, _P, _P, _P]),
     'st_lapjv_batch': (_I, [_P, _I, _I, _I, _P, C.c_double, _I, _P, _P, _P]),

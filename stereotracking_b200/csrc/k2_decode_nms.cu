@@ -149,47 +149,58 @@ __device__ __forceinline__ bool suppresses(const float4 a, const float4 b, float
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
 }
 
+// grid (kMaskCtas, S): the CTAs of a sequence stride over the live upper-triangular
+// 64x64 tiles only (a (words, words, S) grid launched 65 536 CTAs at the default
+// capacity, nearly all of which found nothing to do: 45 us for ~10 live tiles).
+constexpr int kMaskCtas = 16;
+
 __global__ void __launch_bounds__(128)
 k2_nms_mask(int cap, int words, float iou_thr, int num_classes,
             const int32_t *__restrict__ cand_count, const float *__restrict__ sort_box,
             const int32_t *__restrict__ sort_label, const uint32_t *__restrict__ max_coord,
             unsigned long long *__restrict__ nms_mask) {
-    const int s = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
-    if (cb < rb) return;
+    const int s = blockIdx.y;
     const int n = min(cand_count[s], cap);
-    if (rb * 64 >= n || cb * 64 >= n) return;
+    const int nw = (n + 63) >> 6;
+    const int n_tiles = nw * (nw + 1) / 2;
     __shared__ float4 rows[64], cols[64];
     const long long base = (long long)s * cap;
     // batched_nms: boxes + label * (max_coordinate + 1) keeps classes apart
     const float off_unit = num_classes > 1 ? __fadd_rn(from_ordered_bits(max_coord[s]), 1.0f) : 0.f;
-    if (threadIdx.x < 64) {
-        int i = rb * 64 + threadIdx.x;
-        if (i < n) {
-            float4 b = reinterpret_cast<const float4 *>(sort_box)[base + i];
-            float o = num_classes > 1 ? __fmul_rn((float)sort_label[base + i], off_unit) : 0.f;
-            rows[threadIdx.x] = make_float4(__fadd_rn(b.x, o), __fadd_rn(b.y, o), __fadd_rn(b.z, o), __fadd_rn(b.w, o));
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int rb = 0, rem = t;                        // tile t -> (rb, cb), cb >= rb
+        while (rem >= nw - rb) { rem -= nw - rb; ++rb; }
+        const int cb = rb + rem;
+        __syncthreads();                            // rows / cols are reused across tiles
+        if (threadIdx.x < 64) {
+            int i = rb * 64 + threadIdx.x;
+            if (i < n) {
+                float4 b = reinterpret_cast<const float4 *>(sort_box)[base + i];
+                float o = num_classes > 1 ? __fmul_rn((float)sort_label[base + i], off_unit) : 0.f;
+                rows[threadIdx.x] = make_float4(__fadd_rn(b.x, o), __fadd_rn(b.y, o), __fadd_rn(b.z, o), __fadd_rn(b.w, o));
+            }
+        } else {
+            int tt = threadIdx.x - 64, j = cb * 64 + tt;
+            if (j < n) {
+                float4 b = reinterpret_cast<const float4 *>(sort_box)[base + j];
+                float o = num_classes > 1 ? __fmul_rn((float)sort_label[base + j], off_unit) : 0.f;
+                cols[tt] = make_float4(__fadd_rn(b.x, o), __fadd_rn(b.y, o), __fadd_rn(b.z, o), __fadd_rn(b.w, o));
+            }
         }
-    } else {
-        int t = threadIdx.x - 64, j = cb * 64 + t;
-        if (j < n) {
-            float4 b = reinterpret_cast<const float4 *>(sort_box)[base + j];
-            float o = num_classes > 1 ? __fmul_rn((float)sort_label[base + j], off_unit) : 0.f;
-            cols[t] = make_float4(__fadd_rn(b.x, o), __fadd_rn(b.y, o), __fadd_rn(b.z, o), __fadd_rn(b.w, o));
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int j0 = cb * 64 + lane, j1 = j0 + 32;
+        for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+            const int i = rb * 64 + r;
+            if (i >= n) break;                       // uniform across the warp
+            const float4 a = rows[r];
+            const bool p0 = (j0 < n) && (j0 > i) && suppresses(a, cols[lane], iou_thr);
+            const bool p1 = (j1 < n) && (j1 > i) && suppresses(a, cols[lane + 32], iou_thr);
+            const unsigned lo = __ballot_sync(0xffffffffu, p0);
+            const unsigned hi = __ballot_sync(0xffffffffu, p1);
+            if (lane == 0)
+                nms_mask[(base + i) * words + cb] = ((unsigned long long)hi << 32) | lo;
         }
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j0 = cb * 64 + lane, j1 = j0 + 32;
-    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-        const int i = rb * 64 + r;
-        if (i >= n) break;                       // uniform across the warp
-        const float4 a = rows[r];
-        const bool p0 = (j0 < n) && (j0 > i) && suppresses(a, cols[lane], iou_thr);
-        const bool p1 = (j1 < n) && (j1 > i) && suppresses(a, cols[lane + 32], iou_thr);
-        const unsigned lo = __ballot_sync(0xffffffffu, p0);
-        const unsigned hi = __ballot_sync(0xffffffffu, p1);
-        if (lane == 0)
-            nms_mask[(base + i) * words + cb] = ((unsigned long long)hi << 32) | lo;
     }
 }
 
@@ -303,7 +314,7 @@ extern "C" int st_decode_nms(st_handle *h, const float *const *cls_host, const f
     k2_rank_decode<<<dim3((cap + 127) / 128, S), 128, 0, st>>>(
         L, cap, scale_w, scale_h, h->cand_count, h->cand_score, h->cand_prior, h->cand_label,
         h->sort_box, h->sort_score, h->sort_prior, h->sort_label, h->max_coord, h->st.status);
-    k2_nms_mask<<<dim3(words, words, S), 128, 0, st>>>(
+    k2_nms_mask<<<dim3(kMaskCtas, S), 128, 0, st>>>(
         cap, words, h->cfg.nms_iou_thr, num_classes, h->cand_count, h->sort_box, h->sort_label,
         h->max_coord, h->nms_mask);
     k2_nms_scan<<<S, 256, sizeof(unsigned long long) * (words + 64), st>>>(

@@ -19,7 +19,9 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
+// cost matrices up to this many entries stay in shared memory (56 KB: two CTAs per SM fit)
+constexpr int kCostSmemFloats = 14336;
 constexpr int kWarps = kThreads / 32;
 
 // diagnostics only (st_debug_set_skip): bit0..2 skip the assignment of stage
@@ -47,6 +49,9 @@ struct Smem {                    // carved from dynamic shared memory
     unsigned char *row_valid;    // [T]
     unsigned char *det_stage;    // [D] per INPUT det: 0 dropped, 1..3 matched in stage, 4 leftover
     unsigned char *slot_hit;     // [T] per ORDER position: matched this frame
+    float *cost;                 // [cost_cap] cost matrix of the current stage when it fits
+    int cost_cap;
+    int *row_cnt, *col_cnt, *row_adm, *adm_misc;   // admissible-edge statistics (stlap::Problem)
 };
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -57,6 +62,8 @@ __host__ __device__ inline size_t smem_bytes(int T, int D) {
     b += align16(sizeof(float) * T * 4) + align16(sizeof(float) * T * 2) * 2 + align16(sizeof(float) * D * 4);
     b += align16(sizeof(int) * T) + align16(sizeof(int) * D) * 3;
     b += align16(T) + align16(D) + align16(T);
+    b += align16(sizeof(float) * (size_t)((long long)T * D < kCostSmemFloats ? T * D : kCostSmemFloats));
+    b += align16(sizeof(int) * T) * 2 + align16(sizeof(int) * D) + 16;
     return b;
 }
 
@@ -74,7 +81,13 @@ __device__ inline Smem carve(unsigned char *p, int T, int D) {
     m.out_src = reinterpret_cast<int *>(p); p += align16(sizeof(int) * D);
     m.row_valid = p; p += align16(T);
     m.det_stage = p; p += align16(D);
-    m.slot_hit = p;
+    m.slot_hit = p; p += align16(T);
+    m.cost_cap = (long long)T * D < kCostSmemFloats ? T * D : kCostSmemFloats;
+    m.cost = reinterpret_cast<float *>(p); p += align16(sizeof(float) * m.cost_cap);
+    m.row_cnt = reinterpret_cast<int *>(p); p += align16(sizeof(int) * T);
+    m.row_adm = reinterpret_cast<int *>(p); p += align16(sizeof(int) * T);
+    m.col_cnt = reinterpret_cast<int *>(p); p += align16(sizeof(int) * D);
+    m.adm_misc = reinterpret_cast<int *>(p);
     return m;
 }
 
@@ -160,8 +173,14 @@ struct DetView {
 // sm.dets[0..C).  ocm = velocity-direction term on (stage 1/2); boxes of the
 // rows come from the Kalman mean (ocm) or the last observation (ocr).
 __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long long sbase, int R, int C,
-                          bool ocm, const DetView &dv, float *cost, int stage_code, int32_t *status_word) {
+                          bool ocm, const DetView &dv, float *cost_global, int stage_code, int32_t *status_word) {
     if (R == 0 || C == 0) return;           // dists.size == 0 -> nothing matched (:263-265)
+    // the matrix lives in shared memory when it fits (every solver step reads a row of it)
+    float *cost = R * C <= sm.cost_cap ? sm.cost : cost_global;
+    const double lap_limit = 2.0 * pr.lap_half;
+    for (int r = threadIdx.x; r < R; r += kThreads) { sm.row_cnt[r] = 0; sm.row_adm[r] = -1; }
+    for (int c = threadIdx.x; c < C; c += kThreads) sm.col_cnt[c] = 0;
+    if (threadIdx.x == 0) sm.adm_misc[0] = 0;
     // ---- per-row data --------------------------------------------------------
     for (int r = threadIdx.x; r < R; r += kThreads) {
         const long long g = sbase + sm.rows[r];
@@ -210,8 +229,17 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
             dist = __fadd_rn(dist, __fmul_rn(term, pr.vel_w));
         }
         cost[e] = dist;
+        // admissible-edge statistics for the assignment fast path (lapjv.cuh)
+        if ((double)dist < lap_limit) {
+            atomicAdd(&sm.row_cnt[r], 1);
+            atomicAdd(&sm.col_cnt[c], 1);
+            sm.row_adm[r] = c;
+        }
+        if (dist != dist) sm.adm_misc[0] = 1;
     }
     __syncthreads();
+    if ((g_skip >> 6) & 1)                   // diagnostics: mirror the matrix for st_debug_read_cost
+        for (int e = threadIdx.x; e < R * C; e += kThreads) cost_global[e] = cost[e];
     // ---- assignment (warp 0) -----------------------------------------------------
     if (threadIdx.x < 32 && (g_skip >> (stage_code - 1) & 1)) {
         for (int c = threadIdx.x; c < C; c += 32) sm.lap.y[c] = -1;
@@ -219,6 +247,7 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
         stlap::Problem P;
         P.cost = cost; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
         P.dbg = st.debug + (sbase / pr.T) * 16;
+        P.row_cnt = sm.row_cnt; P.col_cnt = sm.col_cnt; P.row_adm = sm.row_adm; P.adm_misc = sm.adm_misc;
         P.mark(0, stage_code); P.mark(1, R); P.mark(2, C);
         // debug words 5/6: assignments solved / solved by the exact fallback (this handle's lifetime)
         if (threadIdx.x == 0) P.dbg[5] += 1;
@@ -559,7 +588,10 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
     stlap::Problem P;
     P.cost = cost + (long long)b * R * C; P.R = R; P.C = C; P.n = R + C; P.half = half;
     P.dbg = nullptr;
+    int *stats = reinterpret_cast<int *>(smem_raw + stlap::scratch_bytes(R + C));
+    P.row_cnt = stats; P.row_adm = stats + R; P.col_cnt = stats + 2 * R; P.adm_misc = stats + 2 * R + C;
     if (R > 0 && C > 0) {
+        stlap::count_admissible(P);
         bool ok;
         if (mode == 1) ok = stlap::solve_warp(P, sc);                 // exact emulation only
         else {
@@ -674,7 +706,8 @@ extern "C" int st_create(const st_config *cfg, st_handle **out) {
     const size_t smem = smem_bytes(cfg->max_tracks, cfg->max_dets);
     if (cudaFuncSetAttribute(k4_track_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(k5_lapjv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)stlap::scratch_bytes(cfg->max_tracks + cfg->max_dets)) != cudaSuccess) {
+                             (int)(stlap::scratch_bytes(cfg->max_tracks + cfg->max_dets) +
+                                   sizeof(int) * (2 * cfg->max_tracks + cfg->max_dets + 4))) != cudaSuccess) {
         cudaFree(h->all_mem); delete h; return ST_ERR_CAPACITY;
     }
     k4_reset<<<cfg->max_sequences, 128>>>(h->st, cfg->max_tracks, nullptr);
@@ -805,7 +838,7 @@ extern "C" int st_lapjv_batch(st_handle *h, int B, int R, int C, const float *co
         (R > 0 && C > 0 && !cost))
         return ST_ERR_INVALID_ARG;
     if (B == 0 || R + C == 0) return ST_OK;
-    k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C), (cudaStream_t)stream>>>(
+    k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C) + sizeof(int) * (2 * R + C + 4), (cudaStream_t)stream>>>(
         R, C, cost, cost_limit / 2.0, mode, row2col, col2row, h->st.status, h->st.debug + 6);
     return st_last_launch();
 }

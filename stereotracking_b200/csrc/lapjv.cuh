@@ -56,6 +56,12 @@ struct Problem {
     int R, C, n;
     double half;          // cost_limit / 2
     int *dbg;             // optional [8] progress words (global), may be null
+    // Admissible-edge statistics of the fast path (cost < L = 2 * half): number of
+    // admissible entries per row / column, one admissible column of each row, and
+    // adm_misc[0] != 0 when the matrix holds a NaN.  Filled by whoever wrote the
+    // matrix (the track kernel does it while it computes the costs) or by
+    // count_admissible().
+    int *row_cnt, *col_cnt, *row_adm, *adm_misc;
     __device__ __forceinline__ void mark(int slot, int v) const {
         if (dbg && (threadIdx.x & 31) == 0) ((volatile int *)dbg)[slot] = v;
     }
@@ -392,6 +398,47 @@ __device__ __noinline__ bool solve_warp(const Problem &P, Scratch &s) {
 // row i or -1 - the same contract as solve_warp after truncation.
 constexpr double kFastEps = 1.0e-9;
 
+// One warp fills the admissible-edge statistics of P (see Problem).
+__device__ inline void count_admissible(const Problem &P) {
+    const int lane = threadIdx.x & 31;
+    const double L = 2.0 * P.half;
+    for (int j = lane; j < P.C; j += 32) P.col_cnt[j] = 0;
+    if (lane == 0) P.adm_misc[0] = 0;
+    __syncwarp();
+    for (int i = lane; i < P.R; i += 32) {
+        int cnt = 0, adm = -1;
+        bool nan = false;
+        for (int j = 0; j < P.C; ++j) {
+            const double c = (double)P.cost[(long long)i * P.C + j];
+            nan |= !(c == c);
+            if (c < L) { ++cnt; adm = j; atomicAdd(&P.col_cnt[j], 1); }
+        }
+        P.row_cnt[i] = cnt;
+        P.row_adm[i] = adm;
+        if (nan) P.adm_misc[0] = 1;
+    }
+    __syncwarp();
+}
+
+// argmin over the warp of (value, index) pairs, lowest index among equal values,
+// index < 0 = "none"; three REDUX instead of a 5-level shuffle tree on 12 bytes.
+__device__ __forceinline__ void warp_argmin(double &val, int &idx) {
+    // order-preserving map of the double onto an unsigned 64-bit key; "none" sorts last
+    unsigned long long k = (unsigned long long)__double_as_longlong(val);
+    k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
+    if (idx < 0) k = ~0ull;
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const bool mine = hi == mhi && lo == mlo && idx >= 0;
+    const unsigned midx = __reduce_min_sync(0xffffffffu, mine ? (unsigned)idx : 0xffffffffu);
+    const unsigned who = __ballot_sync(0xffffffffu, mine && (unsigned)idx == midx);
+    if (who == 0u) { idx = -1; return; }
+    const int src = __ffs(who) - 1;
+    val = __shfl_sync(0xffffffffu, val, src);
+    idx = (int)midx;
+}
+
 // Row-by-row Hungarian with the per-column state (minv, v, visited, way) held in
 // registers: lane l owns the real columns l, l+32, ... (KC per lane, C <= 32*KC).
 // The private dummy columns are not materialised: a row that joins the
@@ -437,11 +484,7 @@ __device__ bool hungarian_regs(const Problem &P, volatile double *u, volatile do
                     if (minv[k] < best) { best = minv[k]; bj = j; }
                 }
             }
-            for (int o = 16; o; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                if (pair_less(ob, oj, best, bj)) { best = ob; bj = oj; }
-            }
+            warp_argmin(best, bj);
             to_dummy = bj < 0 || dmin < best;
             const double delta = to_dummy ? dmin : best;
             if (!(delta < INF)) return false;
@@ -505,28 +548,37 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     volatile int *p = s.x, *way = s.y, *active = s.free_rows;
     volatile unsigned char *used = s.unique;
     const double INF = 1.0e300;
-    // ---- row pruning + NaN screen ---------------------------------------------------
+    // ---- row pruning, NaN screen, isolated pairs ----------------------------------------
+    // Rows without an admissible entry (cost < L) can never be matched: u_i = L/2.
+    // A row whose only admissible column has no other admissible row is matched
+    // to it right away with u_i = a_ij, v_j = 0 - the state the row-by-row method
+    // reaches when it inserts that row first (every other entry of the row and of
+    // the column costs at least the dummy).  In tracking most pairs are of this
+    // kind, so the shortest-path search runs only for the crowded remainder.
+    if (P.adm_misc[0]) return false;
+    for (int j = lane; j < m; j += 32) { v[j] = 0.0; p[j] = -1; }
+    __syncwarp();
     int n_active = 0;
-    bool bad = false;
     for (int i0 = 0; i0 < R; i0 += 32) {
         const int i = i0 + lane;
-        double best = INF;
-        bool nan = false;
-        if (i < R)
-            for (int j = 0; j < C; ++j) {
-                const double c = (double)P.cost[(long long)i * C + j];
-                nan |= !(c == c);
-                best = fmin(best, c);
+        bool act = false;
+        if (i < R) {
+            const int cnt = P.row_cnt[i];
+            double ui = half;
+            if (cnt == 1 && P.col_cnt[P.row_adm[i]] == 1) {
+                const int j = P.row_adm[i];
+                p[j] = i;
+                ui = (double)P.cost[(long long)i * C + j] - half;
+            } else if (cnt > 0) {
+                act = true;
+                ui = 0.0;
             }
-        bad |= __any_sync(0xffffffffu, nan) != 0;
-        const bool act = i < R && best < L;
-        if (i < R) u[i] = act ? 0.0 : half;
+            u[i] = ui;
+        }
         const unsigned mb = __ballot_sync(0xffffffffu, act);
         if (act) active[n_active + __popc(mb & ((1u << lane) - 1u))] = i;
         n_active += __popc(mb);
     }
-    if (bad) return false;
-    for (int j = lane; j < m; j += 32) { v[j] = 0.0; p[j] = -1; }
     __syncwarp();
     // a(i, j): real column -> c_ij - half ; own dummy column C+i -> half ; else INF
     auto a = [&](int i, int j) -> double {

@@ -44,6 +44,56 @@ def _ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+class FrameBuffers:
+    """One set of per-frame device buffers (detections, tracker outputs, K3 scratch,
+    depth map): what one st_frame_io points at besides the inputs."""
+
+    def __init__(self, S, D, dev):
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        # detector output (K2) and per-detection depth / scale (K3)
+        self.det_boxes = torch.zeros(S, D, 4, **f32)
+        self.det_scores = torch.zeros(S, D, **f32)
+        self.det_labels = torch.zeros(S, D, **i64)
+        self.det_prior = torch.zeros(S, D, **i32)
+        self.det_keep = torch.zeros(S, D, **i32)
+        self.det_counts = torch.zeros(S, **i32)
+        self.det_depth = torch.zeros(S, D, **f32)
+        self.det_scales = torch.zeros(S, D, **f32)
+        self.det_inflated = torch.zeros(S, D, 4, **f32)
+        # track outputs
+        self.trk_boxes = torch.zeros(S, D, 4, **f32)       # inflated (tracker space)
+        self.out_boxes = torch.zeros(S, D, 4, **f32)       # deflated (image space)
+        self.out_scores = torch.zeros(S, D, **f32)
+        self.out_labels = torch.zeros(S, D, **i64)
+        self.out_scales = torch.zeros(S, D, **f32)
+        self.trk_depth = torch.zeros(S, D, **f32)          # depth carried through the tracker
+        self.out_depth = torch.zeros(S, D, **f32)          # recomputed on deflated boxes
+        self.out_scale2 = torch.zeros(S, D, **f32)
+        self.out_ids = torch.zeros(S, D, **i64)
+        self.out_counts = torch.zeros(S, **i32)
+        self.frame_ids = torch.zeros(S, **i32)
+        self.k3_workspace = torch.zeros(2 + 4 * S * D, **i32)
+        self.depth_map = None
+
+    def outputs(self):
+        return [self.out_boxes, self.out_ids, self.out_scores, self.out_labels, self.out_scales,
+                self.out_depth, self.out_counts]
+
+    def results(self):
+        """Host copies of the outputs, one dict per sequence."""
+        n = self.out_counts.cpu().tolist()
+        pack = [t.cpu() for t in (self.out_boxes, self.out_ids, self.out_scores, self.out_labels,
+                                  self.out_scales, self.out_depth)]
+        out = []
+        for s, m in enumerate(n):
+            out.append(dict(bboxes=pack[0][s, :m].numpy(), instances_id=pack[1][s, :m].numpy(),
+                            scores=pack[2][s, :m].numpy(), labels=pack[3][s, :m].numpy(),
+                            scales=pack[4][s, :m].numpy(), depth=pack[5][s, :m].numpy()))
+        return out
+
+
 class StereoTrackEngine:
     def __init__(self, cfg: EngineConfig = None, device='cuda:0', **kw):
         cfg = cfg or EngineConfig(**kw)
@@ -74,33 +124,9 @@ class StereoTrackEngine:
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.st_create(C.byref(sc), C.byref(self._h)), 'st_create')
-        S, D = cfg.n_seq, cfg.max_dets
-        dev = self.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        # detection buffers
-        self.det_boxes = torch.zeros(S, D, 4, **f32)
-        self.det_scores = torch.zeros(S, D, **f32)
-        self.det_labels = torch.zeros(S, D, dtype=torch.int64, device=dev)
-        self.det_prior = torch.zeros(S, D, dtype=torch.int32, device=dev)
-        self.det_keep = torch.zeros(S, D, dtype=torch.int32, device=dev)
-        self.det_counts = torch.zeros(S, dtype=torch.int32, device=dev)
-        self.det_depth = torch.zeros(S, D, **f32)
-        self.det_scales = torch.zeros(S, D, **f32)
-        self.det_inflated = torch.zeros(S, D, 4, **f32)
-        # track outputs
-        self.trk_boxes = torch.zeros(S, D, 4, **f32)       # inflated (tracker space)
-        self.out_boxes = torch.zeros(S, D, 4, **f32)       # deflated (image space)
-        self.out_scores = torch.zeros(S, D, **f32)
-        self.out_labels = torch.zeros(S, D, dtype=torch.int64, device=dev)
-        self.out_scales = torch.zeros(S, D, **f32)
-        self.trk_depth = torch.zeros(S, D, **f32)          # depth carried through the tracker
-        self.out_depth = torch.zeros(S, D, **f32)          # recomputed on deflated boxes
-        self.out_scale2 = torch.zeros(S, D, **f32)
-        self.out_ids = torch.zeros(S, D, dtype=torch.int64, device=dev)
-        self.out_counts = torch.zeros(S, dtype=torch.int32, device=dev)
-        self.frame_ids = torch.zeros(S, dtype=torch.int32, device=dev)
-        self.k3_workspace = torch.zeros(2 + 4 * S * D, dtype=torch.int32, device=dev)
-        self.depth_map = None
+        # the engine's own buffer set; its tensors are also attributes of the engine
+        self.buffers = FrameBuffers(cfg.n_seq, cfg.max_dets, self.device)
+        self.__dict__.update(vars(self.buffers))
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:
@@ -225,34 +251,40 @@ class StereoTrackEngine:
         self.decode_nms(cls_l, bbox_l, obj_l, (H, W))
         self.step_from_dets(self.depth_map, frame_ids)
 
-    def make_frame_io(self, raw_shape, level_shapes, num_classes=1, resized_hw=None, scale_factor=(1.0, 1.0)):
+    def make_frame_io(self, raw_shape, level_shapes, num_classes=1, resized_hw=None, scale_factor=(1.0, 1.0),
+                      bufs=None):
         """Prepare a reusable st_frame_io for inputs of the given shapes: raw
         [S,H,W] and per-level head maps [S,C,h,w].  Pointers to the per-step inputs
-        are filled by ``frame_step``; everything else is bound once."""
+        are filled by ``frame_step``; everything else is bound once to the buffer
+        set ``bufs`` (default: the engine's own)."""
         S, H, W = raw_shape
         Hr, Wr = resized_hw or (H, W)
         Hp, Wp = -(-Hr // 32) * 32, -(-Wr // 32) * 32
-        if self.depth_map is None or tuple(self.depth_map.shape) != (S, Hp, Wp):
-            self.depth_map = torch.empty(S, Hp, Wp, dtype=torch.float32, device=self.device)
+        own = bufs is None
+        bufs = self if own else bufs
+        if bufs.depth_map is None or tuple(bufs.depth_map.shape) != (S, Hp, Wp):
+            bufs.depth_map = torch.empty(S, Hp, Wp, dtype=torch.float32, device=self.device)
+            if own:
+                self.buffers.depth_map = bufs.depth_map
         L = len(level_shapes)
         io = _lib.StFrameIO()
         keep = dict(cls=(C.c_void_p * L)(), bbox=(C.c_void_p * L)(), obj=(C.c_void_p * L)(),
                     lh=(C.c_int32 * L)(*[s[0] for s in level_shapes]),
                     lw=(C.c_int32 * L)(*[s[1] for s in level_shapes]),
                     st=(C.c_int32 * L)(*self.cfg.strides[:L]))
-        io.frame_ids = self.frame_ids.data_ptr()
+        io.frame_ids = bufs.frame_ids.data_ptr()
         io.H, io.W, io.Hr, io.Wr, io.Hp, io.Wp = H, W, Hr, Wr, Hp, Wp
         io.cls, io.bbox, io.obj = (C.cast(keep[k], C.c_void_p) for k in ('cls', 'bbox', 'obj'))
         io.level_h, io.level_w, io.strides = (C.cast(keep[k], C.c_void_p) for k in ('lh', 'lw', 'st'))
         io.num_levels, io.num_classes, io.ori_h, io.ori_w = L, num_classes, H, W
         io.scale_w, io.scale_h = float(scale_factor[0]), float(scale_factor[1])
-        io.depth_map = self.depth_map.data_ptr()
+        io.depth_map = bufs.depth_map.data_ptr()
         for name in ('det_boxes', 'det_scores', 'det_labels', 'det_prior', 'det_keep', 'det_counts',
                      'det_depth', 'det_scales', 'det_inflated', 'trk_boxes', 'trk_depth', 'out_scale2',
                      'k3_workspace',
                      'out_boxes', 'out_scores', 'out_labels', 'out_scales', 'out_depth', 'out_ids',
                      'out_counts'):
-            setattr(io, name, getattr(self, name).data_ptr())
+            setattr(io, name, getattr(bufs, name).data_ptr())
         io._keep = keep
         return io
 
@@ -281,15 +313,7 @@ class StereoTrackEngine:
 
     def results(self):
         """Host copies of the current outputs, one dict per sequence."""
-        n = self.out_counts.cpu().tolist()
-        pack = [t.cpu() for t in (self.out_boxes, self.out_ids, self.out_scores, self.out_labels,
-                                  self.out_scales, self.out_depth)]
-        out = []
-        for s, m in enumerate(n):
-            out.append(dict(bboxes=pack[0][s, :m].numpy(), instances_id=pack[1][s, :m].numpy(),
-                            scores=pack[2][s, :m].numpy(), labels=pack[3][s, :m].numpy(),
-                            scales=pack[4][s, :m].numpy(), depth=pack[5][s, :m].numpy()))
-        return out
+        return self.buffers.results()
 
     # ---- state ----------------------------------------------------------------------
     def reset(self, seq_mask=None):
@@ -341,38 +365,91 @@ class StereoTrackEngine:
         return x, y
 
 
-class LockstepGroups:
-    """S sequences split into G independent lockstep groups, one handle and one
-    CUDA stream per group.  Sequences never interact (the reference shards whole
-    videos across ranks, mmtrack/datasets/samplers/video_sampler.py:50-69), so the
-    latency-bound stages of one group (assignment, per-box depth of a few large
-    boxes) overlap with the bandwidth-bound stages of another instead of leaving
-    the GPU idle.  No cross-group synchronisation happens on the data path."""
+class FramePipeline:
+    """Software pipeline over consecutive frames (st_pipeline_* of the C ABI): stage
+    A (K1, K2, K3 on detections) of frame f+2, stage B (tracker) of frame f+1 and
+    stage C (deflate, K3 on tracks) of frame f run concurrently on three library
+    streams.  ``depth`` complete buffer sets are cycled; frame k uses set k % depth
+    and its results stay readable until frame k + depth is submitted."""
 
-    def __init__(self, n_seq, n_groups=4, device='cuda:0', **cfg_kw):
+    def __init__(self, engine, raw_shape, level_shapes, depth=3, num_classes=1):
+        self.engine, self.depth = engine, depth
+        S = raw_shape[0]
+        self.n_seq = S
+        self.slots = [engine.buffers] + [FrameBuffers(S, engine.cfg.max_dets, engine.device) for _ in range(depth - 1)]
+        self.ios = [engine.make_frame_io(raw_shape, level_shapes, num_classes, bufs=None if i == 0 else b)
+                    for i, b in enumerate(self.slots)]
+        self._p = C.c_void_p()
+        with torch.cuda.device(engine.device):
+            _lib.check(engine.lib.st_pipeline_create(engine._h, depth, C.byref(self._p)), 'st_pipeline_create')
+        self.submitted = 0
+
+    def close(self):
+        if self._p.value:
+            self.engine.lib.st_pipeline_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit_ptrs(self, frame_ids_ptr, raw_ptr, cls_ptrs, bbox_ptrs, obj_ptrs, ready_event=None, done_event=None):
+        """Queue one frame given raw device addresses; returns the slot it uses."""
+        slot = self.submitted % self.depth
+        io = self.ios[slot]
+        io.frame_ids = frame_ids_ptr
+        io.raw = raw_ptr
+        k = io._keep
+        for l in range(len(cls_ptrs)):
+            k['cls'][l] = cls_ptrs[l]
+            k['bbox'][l] = bbox_ptrs[l]
+            k['obj'][l] = obj_ptrs[l]
+        ev = lambda e: C.c_void_p(0 if e is None else e.cuda_event)
+        _lib.check(self.engine.lib.st_pipeline_submit(self._p, self.n_seq, C.byref(io), ev(ready_event),
+                                                      ev(done_event)), 'st_pipeline_submit')
+        self.submitted += 1
+        return slot
+
+    def submit(self, frame_ids, raw, cls_l, bbox_l, obj_l, ready_event=None, done_event=None):
+        """Queue one frame given device tensors (frame_ids [S] int32, raw [S,H,W] u16,
+        heads [S,C,h,w] f32); they must stay alive and unchanged until the frame is done."""
+        return self.submit_ptrs(frame_ids.data_ptr(), raw.data_ptr(), [t.data_ptr() for t in cls_l],
+                                [t.data_ptr() for t in bbox_l], [t.data_ptr() for t in obj_l],
+                                ready_event, done_event)
+
+    def fork(self, stream=None):
+        stream = stream or torch.cuda.current_stream(self.engine.device)
+        _lib.check(self.engine.lib.st_pipeline_fork(self._p, C.c_void_p(stream.cuda_stream)), 'st_pipeline_fork')
+
+    def join(self, stream=None):
+        stream = stream or torch.cuda.current_stream(self.engine.device)
+        _lib.check(self.engine.lib.st_pipeline_join(self._p, C.c_void_p(stream.cuda_stream)), 'st_pipeline_join')
+
+
+class LockstepGroups:
+    """S sequences split into G independent lockstep groups (one handle each), every
+    group advancing through its own FramePipeline.  Sequences never interact (the
+    reference shards whole videos across ranks, mmtrack/datasets/samplers/
+    video_sampler.py:50-69), so no synchronisation between groups happens on the data
+    path.  One group per GPU is the default: the frame pipeline already overlaps the
+    latency-bound stages with the bandwidth-bound ones."""
+
+    def __init__(self, n_seq, n_groups=1, device='cuda:0', depth=3, **cfg_kw):
         n_groups = max(1, min(n_groups, n_seq))
         base, extra = divmod(n_seq, n_groups)
         self.sizes = [base + (1 if g < extra else 0) for g in range(n_groups)]
         self.offsets = [sum(self.sizes[:g]) for g in range(n_groups)]
         self.device = torch.device(device)
+        self.depth = depth
         self.engines = [StereoTrackEngine(EngineConfig(n_seq=sz, **cfg_kw), device=device) for sz in self.sizes]
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.sizes]
-        self.ios = None
+        self.pipes = None
 
     def bind(self, raw_shape, level_shapes, num_classes=1):
         _, H, W = raw_shape
-        self.ios = [e.make_frame_io((sz, H, W), level_shapes, num_classes) for e, sz in zip(self.engines, self.sizes)]
-
-    def frame_step(self, raw, cls_l, bbox_l, obj_l, frame_id, wait_event=None):
-        """Issue one lockstep frame of every group on its own stream.  Inputs are
-        full [S,...] device tensors (sliced per group, no copies)."""
-        for eng, io, st, a, sz in zip(self.engines, self.ios, self.streams, self.offsets, self.sizes):
-            with torch.cuda.stream(st):
-                if wait_event is not None:
-                    st.wait_event(wait_event)
-                eng.frame_ids.fill_(frame_id)
-                eng.frame_step(io, raw[a:a + sz], [c[a:a + sz] for c in cls_l], [c[a:a + sz] for c in bbox_l],
-                               [c[a:a + sz] for c in obj_l])
+        self.pipes = [FramePipeline(e, (sz, H, W), level_shapes, self.depth, num_classes)
+                      for e, sz in zip(self.engines, self.sizes)]
 
     def plan(self, raw, cls_l, bbox_l, obj_l, first_frame_id=0):
         """Precompute the device addresses of every (frame, group) slice of resident
@@ -393,29 +470,33 @@ class LockstepGroups:
         self._plan_keepalive = (raw, cls_l, bbox_l, obj_l)
         return plan
 
-    def run_plan(self, f):
-        for eng, io, st, sz, args in zip(self.engines, self.ios, self.streams, self.sizes, self._plan[f]):
-            with torch.cuda.stream(st):
-                eng.frame_step_ptrs(io, sz, *args)
+    def run_plan(self, f, ready_event=None, done_events=None):
+        """Queue planned frame f on every group's pipeline; returns the slot used."""
+        slot = 0
+        for g, (pipe, args) in enumerate(zip(self.pipes, self._plan[f])):
+            slot = pipe.submit_ptrs(*args, ready_event=ready_event,
+                                    done_event=None if done_events is None else done_events[g])
+        return slot
 
     def join(self, stream=None):
-        stream = stream or torch.cuda.current_stream(self.device)
-        for st in self.streams:
-            stream.wait_stream(st)
+        for p in self.pipes:
+            p.join(stream)
 
     def fork(self, stream=None):
-        stream = stream or torch.cuda.current_stream(self.device)
-        for st in self.streams:
-            st.wait_stream(stream)
+        for p in self.pipes:
+            p.fork(stream)
 
     def status(self):
         import numpy as np
         return np.concatenate([e.status() for e in self.engines])
 
-    def results(self):
+    def results(self, slot=None):
+        """Host copies of the outputs of the frame in ring slot ``slot`` (default: the
+        last submitted frame); call after ``join`` + synchronisation."""
         out = []
-        for e in self.engines:
-            out.extend(e.results())
+        for p in self.pipes:
+            k = (p.submitted - 1) % p.depth if slot is None else slot
+            out.extend(p.slots[k].results())
         return out
 
     @property

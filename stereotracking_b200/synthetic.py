@@ -116,6 +116,17 @@ class SyntheticStereo:
     def frames(self, f0, f1):
         """dict(raw [F,S,H,W] u16, cls/bbox/obj: per-level lists of
         [F,S,C,h,w] f32, gt_boxes, gt_visible) on ``self.device``."""
+        # clusters of neighbouring objects write the same head-map cells: indexed
+        # assignment with duplicate indices is only reproducible on CUDA in
+        # deterministic mode
+        prev = torch.are_deterministic_algorithms_enabled()
+        torch.use_deterministic_algorithms(True, warn_only=True)
+        try:
+            return self._frames(f0, f1)
+        finally:
+            torch.use_deterministic_algorithms(prev)
+
+    def _frames(self, f0, f1):
         cfg, dev = self.cfg, self.device
         S, K, H, W = self.S, cfg.k_max, cfg.height, cfg.width
         F = f1 - f0

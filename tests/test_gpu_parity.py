@@ -309,3 +309,55 @@ def test_lockstep_batch_equals_single_sequences(mods):
             r1 = e.results()[0]
             for k in rb[s]:
                 np.testing.assert_array_equal(rb[s][k], r1[k])
+
+
+def test_frame_pipeline_equals_sequential_steps(mods):
+    """st_pipeline_submit overlaps the stages of consecutive frames on three streams;
+    the results must equal the single-stream st_frame_step path frame by frame, both
+    with every frame in flight at once and with ring slots being reused."""
+    import torch
+    from stereotracking_b200.engine import FramePipeline
+    cfg = mods.SceneConfig(192, 256, 4, 8, n_clutter=10)
+    S, F = 3, 12
+    fr = mods.SyntheticStereo(cfg, S, F, seed=33).frames(0, F)
+    raw = fr['raw'].cuda().contiguous()
+    heads = [[c.cuda().contiguous() for c in fr[k]] for k in ('cls', 'bbox', 'obj')]
+    fid = torch.arange(F, dtype=torch.int32, device='cuda')[:, None].repeat(1, S).contiguous()
+    seq = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S))
+    want = []
+    for f in range(F):
+        seq.frame_ids.fill_(f)
+        seq.step(raw[f], [c[f] for c in heads[0]], [c[f] for c in heads[1]], [c[f] for c in heads[2]])
+        want.append(seq.results())
+    levels = [c.shape[-2:] for c in heads[0]]
+
+    def check(got, f):
+        for s in range(S):
+            for k in want[f][s]:
+                np.testing.assert_array_equal(got[s][k], want[f][s][k], err_msg=f'frame {f} seq {s} {k}')
+
+    # (a) every frame in flight, results read at the end
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S))
+    pipe = FramePipeline(eng, (S, cfg.height, cfg.width), levels, depth=F)
+    for f in range(F):
+        pipe.submit(fid[f], raw[f], [c[f] for c in heads[0]], [c[f] for c in heads[1]], [c[f] for c in heads[2]])
+    pipe.join()
+    torch.cuda.synchronize()
+    for f in range(F):
+        check(pipe.slots[f].results(), f)
+    # (b) two slots, reused; frame f is read while frame f + 1 is in flight
+    eng2 = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S))
+    pipe2 = FramePipeline(eng2, (S, cfg.height, cfg.width), levels, depth=2)
+    done = [torch.cuda.Event() for _ in range(2)]
+    for e in done:
+        e.record()
+    for f in range(F):
+        slot = pipe2.submit(fid[f], raw[f], [c[f] for c in heads[0]], [c[f] for c in heads[1]],
+                            [c[f] for c in heads[2]], done_event=done[f % 2])
+        assert slot == f % 2
+        if f >= 1:
+            done[(f - 1) % 2].synchronize()
+            check(pipe2.slots[(f - 1) % 2].results(), f - 1)
+    done[(F - 1) % 2].synchronize()
+    check(pipe2.slots[(F - 1) % 2].results(), F - 1)
+    assert eng.status().max() == 0 and eng2.status().max() == 0
