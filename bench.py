@@ -44,7 +44,7 @@ def parse():
     ap.add_argument('--cpu-seqs', type=int, default=0, help='sequences of the CPU sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--groups', type=int, default=1, help='independent lockstep groups (handles) per GPU')
-    ap.add_argument('--depth', type=int, default=3, help='frames in flight in the frame pipeline (1 = no overlap)')
+    ap.add_argument('--depth', type=int, default=5, help='frames in flight in the frame pipeline (1 = no overlap)')
     return ap.parse_args()
 
 

@@ -192,7 +192,8 @@ int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *stream);
 /* Software pipeline over consecutive frames of the same S sequences.  Only the
  * tracker state couples frame f+1 to frame f (ocsort_tracker_disparity.py:345-618);
  * K1, K2 and K3 on the detections of later frames and the deflate + K3 on the tracks
- * of earlier frames run concurrently with it on three internal streams.  Results
+ * of earlier frames run concurrently with it on five internal streams (K1 | K2 ->
+ * K3 on detections -> tracker -> deflate + K3 on tracks).  Results
  * equal st_frame_step.  The caller owns `depth` complete st_frame_io buffer sets and
  * passes set (k mod depth) with the k-th submit; inputs must stay valid until that
  * frame is done.  inputs_ready / frame_done are cudaEvent_t (may be NULL): the first

@@ -18,9 +18,10 @@
 namespace {
 
 constexpr int kWarps = 4;                // boxes per CTA
-constexpr int kStage = 2048;             // valid depths staged per warp
-constexpr int kSmallPix = 2048;          // boxes up to this many pixels: one warp; larger: one CTA
-constexpr int kMediumPix = 8192;         // CTA tiers: medium <= kMediumPix < huge
+constexpr int kStage = 512;              // valid depths staged per warp
+constexpr int kSmallPix = 512;           // boxes up to this many pixels: one warp; larger: one CTA
+// (2048 before: the warp kernel's longest box - ~27 bit passes over 2048 staged values - set its
+// duration at ~70 us; 512-2048 pixel boxes cost the table kernel's 512 threads a few microseconds)
 
 struct Slice { int lo, hi; };            // hi <= lo means empty
 
@@ -46,18 +47,27 @@ __device__ __forceinline__ long long wrap_add(long long a, long long b) {
 
 __device__ __forceinline__ bool depth_valid(float d) { return d < 150.f && d > 0.f; }
 
-// np.mean of depth[ys, xs] for a (<=2)x(<=2) patch: sequential float32 sum in
-// row-major order, then one float32 division; empty -> NaN
-__device__ float corner_mean(const float *__restrict__ dm, int Wp, Slice ys, Slice xs) {
-    int cnt = 0;
-    float acc = 0.f;
-    for (int y = ys.lo; y < ys.hi; ++y)
-        for (int x = xs.lo; x < xs.hi; ++x) {
-            float v = dm[(long long)y * Wp + x];
-            acc = cnt ? __fadd_rn(acc, v) : v;
-            ++cnt;
-        }
+// The four 2x2 corner patches of a box (:157-160): element e (0..3) of corner c
+// (0 tl, 1 tr, 2 bl, 3 br) in row-major order of the (<=2)x(<=2) patch that Python
+// slicing yields.  Returns false when the patch has no such element.
+__device__ __forceinline__ bool corner_elem(int c, int e, long long b0, long long b1, long long b2, long long b3,
+                                            int Hp, int Wp, int &y, int &x, int &cnt) {
+    const Slice ys = (c < 2) ? py_slice(b1, wrap_add(b1, 2), Hp) : py_slice(wrap_add(b3, -2), b3, Hp);
+    const Slice xs = (c & 1) ? py_slice(wrap_add(b2, -2), b2, Wp) : py_slice(b0, wrap_add(b0, 2), Wp);
+    const int ny = max(ys.hi - ys.lo, 0), nx = max(xs.hi - xs.lo, 0);
+    cnt = ny * nx;
+    if (e >= cnt) return false;
+    y = ys.lo + e / nx;
+    x = xs.lo + e % nx;
+    return true;
+}
+
+// np.mean of a corner patch from its prefetched elements v[0..cnt): sequential
+// float32 sum in row-major order, one float32 division; empty -> NaN
+__device__ __forceinline__ float corner_mean_of(const float *v, int cnt) {
     if (cnt == 0) return __int_as_float(0x7fc00000);
+    float acc = v[0];
+    for (int e = 1; e < cnt; ++e) acc = __fadd_rn(acc, v[e]);
     return __fdiv_rn(acc, (float)cnt);
 }
 
@@ -218,6 +228,16 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
     }
     c.staged = staged;
     c.use_stage = true;
+    // corner patches: lane 4c+e fetches element e of corner c now, so that the 16 loads
+    // are in flight together and hidden behind the staging pass (they were a chain of 16
+    // dependent loads after the median before)
+    float corner_val = 0.f;
+    int corner_cnt = 0;
+    if (lane < 16) {
+        int cy, cx;
+        if (corner_elem(lane >> 2, lane & 3, b0, b1, b2, b3, Hp, Wp, cy, cx, corner_cnt))
+            corner_val = c.dm[(long long)cy * Wp + cx];
+    }
     // pass 0: count the valid values, staging them (npix <= kSmallPix = kStage always fits)
     int n = 0;
     for (unsigned i0 = 0; i0 < c.npix; i0 += 128) {
@@ -256,15 +276,14 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
         if (c.use_stage) bit_select2(staged, n, lane, 1, rk, val, below);
         else radix_select2(c, lane, 1, rk, val, below, hist);
         const float d_mid = __uint_as_float(val[0]);
-        // corner votes on the unfiltered map (:157-160)
+        // corner votes on the unfiltered map (:157-160): lane 4c gathers the elements of corner c
         int k = 0;
         {
-            Slice ytop = py_slice(b1, wrap_add(b1, 2), Hp), ybot = py_slice(wrap_add(b3, -2), b3, Hp);
-            Slice xl = py_slice(b0, wrap_add(b0, 2), Wp), xr = py_slice(wrap_add(b2, -2), b2, Wp);
-            k += corner_mean(c.dm, Wp, ytop, xl) > d_mid;
-            k += corner_mean(c.dm, Wp, ytop, xr) > d_mid;
-            k += corner_mean(c.dm, Wp, ybot, xl) > d_mid;
-            k += corner_mean(c.dm, Wp, ybot, xr) > d_mid;
+            float cv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cv[e] = __shfl_sync(0xffffffffu, corner_val, (lane & 12) + e);
+            const bool vote = lane < 16 && (lane & 3) == 0 && corner_mean_of(cv, corner_cnt) > d_mid;
+            k = __popc(__ballot_sync(0xffffffffu, vote));
         }
         // w_start = min(1 - k/4, 0.4) * len ; w_end = w_start + 0.6 * len   (float64)
         const double frac = fmin(1.0 - (double)k / 4.0, 0.4);
@@ -322,7 +341,6 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
 // worklist written by the warp kernel):
 //   medium  <= kMediumPix pixels: 256 threads, 32 KB stage, several CTAs per SM
 //   huge     > kMediumPix pixels: 512 threads, 176 KB stage, one CTA per SM
-constexpr int kMediumThreads = 256, kMediumStage = 8192;
 constexpr int kHugeThreads = 512, kHugeStage = 45056;
 constexpr int kMaxCtaWarps = 16;
 
@@ -448,12 +466,20 @@ k3_box_depth_cta(const float *__restrict__ depth, int Hp, int Wp, const float *_
     __shared__ int ired[kMaxCtaWarps];
     __shared__ double dred[kMaxCtaWarps];
     __shared__ int stage_fill;
+    __shared__ float corner_sm[16];
+    __shared__ int corner_n[4];
 
     const long long o = (long long)s * cap + bi;
     const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
     const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
     BoxCtx c;
     c.dm = depth + (long long)s * Hp * Wp;
+    if (threadIdx.x < 16) {                 // corner patches, fetched up front (read after the barriers below)
+        int cy, cx, cn;
+        const bool has = corner_elem(threadIdx.x >> 2, threadIdx.x & 3, b0, b1, b2, b3, Hp, Wp, cy, cx, cn);
+        corner_sm[threadIdx.x] = has ? c.dm[(long long)cy * Wp + cx] : 0.f;
+        if ((threadIdx.x & 3) == 0) corner_n[threadIdx.x >> 2] = cn;
+    }
     c.Wp = Wp;
     c.ys = py_slice(b1, b3, Hp);
     c.xs = py_slice(b0, b2, Wp);
@@ -510,14 +536,8 @@ k3_box_depth_cta(const float *__restrict__ depth, int Hp, int Wp, const float *_
         const float d_mid = __uint_as_float(val[0]);
         // corner votes on the unfiltered map (:157-160)
         int k = 0;
-        {
-            Slice ytop = py_slice(b1, wrap_add(b1, 2), Hp), ybot = py_slice(wrap_add(b3, -2), b3, Hp);
-            Slice xl = py_slice(b0, wrap_add(b0, 2), Wp), xr = py_slice(wrap_add(b2, -2), b2, Wp);
-            k += corner_mean(c.dm, Wp, ytop, xl) > d_mid;
-            k += corner_mean(c.dm, Wp, ytop, xr) > d_mid;
-            k += corner_mean(c.dm, Wp, ybot, xl) > d_mid;
-            k += corner_mean(c.dm, Wp, ybot, xr) > d_mid;
-        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) k += corner_mean_of(corner_sm + 4 * cc, corner_n[cc]) > d_mid;
         // w_start = min(1 - k/4, 0.4) * len ; w_end = w_start + 0.6 * len   (float64)
         const double frac = fmin(1.0 - (double)k / 4.0, 0.4);
         const double w_start = __dmul_rn(frac, (double)n);
@@ -600,6 +620,8 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
     int *sbelow = scnt + kMaxDistinct;                  // number of elements strictly smaller
     __shared__ int n_distinct, n_dense, overflow, n_valid_sh, sel[2];
     __shared__ double dred[kMaxCtaWarps];
+    __shared__ float corner_sm[16];
+    __shared__ int corner_n[4];
     const int lane = threadIdx.x & 31;
     const int n_work = worklist[0];
     for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
@@ -616,6 +638,12 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
         float d = -1.f, scale = 1.f;
         bool done = wbox > 800;                          // reference: d = -1, scale = 1 (:150)
         if (!done) {
+            if (threadIdx.x < 16) {         // corner patches, fetched up front (read after the barriers below)
+                int cy, cx, cn;
+                const bool has = corner_elem(threadIdx.x >> 2, threadIdx.x & 3, b0, b1, b2, b3, Hp, Wp, cy, cx, cn);
+                corner_sm[threadIdx.x] = has ? dm[(long long)cy * Wp + cx] : 0.f;
+                if ((threadIdx.x & 3) == 0) corner_n[threadIdx.x >> 2] = cn;
+            }
             for (int i = threadIdx.x; i < kTableSlots; i += kTableThreads) { keys[i] = 0u; cnts[i] = 0; }
             if (threadIdx.x == 0) { n_distinct = 0; n_dense = 0; overflow = 0; n_valid_sh = 0; }
             __syncthreads();
@@ -694,14 +722,8 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
                 __syncthreads();
                 const float d_mid = sval[sel[0]];
                 int k = 0;
-                {
-                    Slice ytop = py_slice(b1, wrap_add(b1, 2), Hp), ybot = py_slice(wrap_add(b3, -2), b3, Hp);
-                    Slice xl = py_slice(b0, wrap_add(b0, 2), Wp), xr = py_slice(wrap_add(b2, -2), b2, Wp);
-                    k += corner_mean(dm, Wp, ytop, xl) > d_mid;
-                    k += corner_mean(dm, Wp, ytop, xr) > d_mid;
-                    k += corner_mean(dm, Wp, ybot, xl) > d_mid;
-                    k += corner_mean(dm, Wp, ybot, xr) > d_mid;
-                }
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) k += corner_mean_of(corner_sm + 4 * cc, corner_n[cc]) > d_mid;
                 const double frac = fmin(1.0 - (double)k / 4.0, 0.4);
                 const double w_start = __dmul_rn(frac, (double)n);
                 const double w_end = __dadd_rn(w_start, __dmul_rn(0.6, (double)n));

@@ -40,22 +40,27 @@ extern "C" int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *s
 // ---------------------------------------------------------------------------------
 // Software pipeline over consecutive frames.  Only the tracker state couples frame
 // f+1 to frame f; everything before the tracker (K1, K2, K3 on the detections) and
-// after it (deflate, K3 on the tracks) depends on that frame's inputs alone.  The
-// latency-bound stages (one CTA per sequence or per box, far fewer CTAs than SMs)
-// therefore overlap with the bandwidth-bound K1 of later frames instead of leaving
-// the GPU idle:
-//   stream A: K1 -> K2 -> K3(dets)   of frame f+2
-//   stream B: K4/K5 (tracker)        of frame f+1
-//   stream C: deflate -> K3(tracks)  of frame f
+// after it (deflate, K3 on the tracks) depends on that frame's inputs alone, and K1
+// and K2 do not depend on each other.  The latency-bound stages (one CTA per
+// sequence or per box, far fewer CTAs than SMs) therefore overlap with each other
+// and with the bandwidth-bound K1 of later frames instead of leaving the GPU idle.
+// Five streams, each processing the frames in order:
+//   stream 0: K1 (disparity -> depth)          stream 1: K2 (decode + NMS)
+//   stream 2: K3 on the detections (needs 0 and 1)
+//   stream 3: K4/K5, the tracker (needs 2; the only stage with cross-frame state)
+//   stream 4: deflate + K3 on the tracks (needs 3 and the frame's depth map)
 // Results are identical to st_frame_step: the same kernels run on the same data in
 // the same per-frame order; the ring of `depth` caller-owned buffer sets keeps the
-// intermediates of the frames in flight apart.
+// intermediates of the frames in flight apart (a set is reused when the frame that
+// last used it has left stream 4).
+constexpr int kStages = 5;
+
 struct st_pipeline {
     st_handle *h;
     int depth;
     long long submitted;
-    cudaStream_t sa, sb, sc;
-    cudaEvent_t *ev_a, *ev_b, *ev_c;   // [depth] stage completion of the frame in that slot
+    cudaStream_t st[kStages];
+    cudaEvent_t *ev;                   // [kStages][depth] stage completion of the frame in that slot
     cudaEvent_t fork_ev;
 };
 
@@ -64,27 +69,25 @@ extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
     st_pipeline *p = new (std::nothrow) st_pipeline();
     if (!p) return ST_ERR_ALLOC;
     p->h = h; p->depth = depth; p->submitted = 0;
-    p->ev_a = new (std::nothrow) cudaEvent_t[3 * depth];
-    if (!p->ev_a) { delete p; return ST_ERR_ALLOC; }
-    p->ev_b = p->ev_a + depth; p->ev_c = p->ev_b + depth;
-    bool ok = cudaStreamCreateWithFlags(&p->sa, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&p->sb, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&p->sc, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; ok && i < 3 * depth; ++i)
-        ok = cudaEventCreateWithFlags(&p->ev_a[i], cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) { delete[] p->ev_a; delete p; return ST_ERR_CUDA; }
+    p->ev = new (std::nothrow) cudaEvent_t[kStages * depth];
+    if (!p->ev) { delete p; return ST_ERR_ALLOC; }
+    bool ok = cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < kStages; ++i)
+        ok = cudaStreamCreateWithFlags(&p->st[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < kStages * depth; ++i)
+        ok = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { delete[] p->ev; delete p; return ST_ERR_CUDA; }
     *out = p;
     return ST_OK;
 }
 
 extern "C" int st_pipeline_destroy(st_pipeline *p) {
     if (!p) return ST_ERR_INVALID_ARG;
-    cudaStreamSynchronize(p->sa); cudaStreamSynchronize(p->sb); cudaStreamSynchronize(p->sc);
-    for (int i = 0; i < 3 * p->depth; ++i) cudaEventDestroy(p->ev_a[i]);
+    for (int i = 0; i < kStages; ++i) cudaStreamSynchronize(p->st[i]);
+    for (int i = 0; i < kStages * p->depth; ++i) cudaEventDestroy(p->ev[i]);
     cudaEventDestroy(p->fork_ev);
-    cudaStreamDestroy(p->sa); cudaStreamDestroy(p->sb); cudaStreamDestroy(p->sc);
-    delete[] p->ev_a;
+    for (int i = 0; i < kStages; ++i) cudaStreamDestroy(p->st[i]);
+    delete[] p->ev;
     delete p;
     return ST_OK;
 }
@@ -92,17 +95,14 @@ extern "C" int st_pipeline_destroy(st_pipeline *p) {
 extern "C" int st_pipeline_fork(st_pipeline *p, void *stream) {
     if (!p) return ST_ERR_INVALID_ARG;
     ST_CUDA_OK(cudaEventRecord(p->fork_ev, (cudaStream_t)stream));
-    ST_CUDA_OK(cudaStreamWaitEvent(p->sa, p->fork_ev, 0));
-    ST_CUDA_OK(cudaStreamWaitEvent(p->sb, p->fork_ev, 0));
-    ST_CUDA_OK(cudaStreamWaitEvent(p->sc, p->fork_ev, 0));
+    for (int i = 0; i < kStages; ++i) ST_CUDA_OK(cudaStreamWaitEvent(p->st[i], p->fork_ev, 0));
     return ST_OK;
 }
 
 extern "C" int st_pipeline_join(st_pipeline *p, void *stream) {
     if (!p) return ST_ERR_INVALID_ARG;
-    cudaStream_t all[3] = {p->sa, p->sb, p->sc};
-    for (int i = 0; i < 3; ++i) {
-        ST_CUDA_OK(cudaEventRecord(p->fork_ev, all[i]));
+    for (int i = 0; i < kStages; ++i) {
+        ST_CUDA_OK(cudaEventRecord(p->fork_ev, p->st[i]));
         ST_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, p->fork_ev, 0));
     }
     return ST_OK;
@@ -115,42 +115,52 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     st_handle *h = p->h;
     const int cap = h->cfg.max_dets;
     const int slot = (int)(p->submitted % p->depth);
+    auto ev = [&](int stage) { return p->ev[stage * p->depth + slot]; };
+    const bool reused = p->submitted >= p->depth;
     int rc;
-    // ---- stage A: the buffer set of this slot is free once frame (k - depth) left stage C
-    if (p->submitted >= p->depth) ST_CUDA_OK(cudaStreamWaitEvent(p->sa, p->ev_c[slot], 0));
-    if (inputs_ready) ST_CUDA_OK(cudaStreamWaitEvent(p->sa, (cudaEvent_t)inputs_ready, 0));
+    // ---- stream 0: K1.  The buffer set of this slot is free once its previous frame left stream 4.
+    if (reused) ST_CUDA_OK(cudaStreamWaitEvent(p->st[0], ev(4), 0));
+    if (inputs_ready) ST_CUDA_OK(cudaStreamWaitEvent(p->st[0], (cudaEvent_t)inputs_ready, 0));
     if (io->raw) {
         rc = st_disp2depth(io->raw, S, io->H, io->W, io->Hr, io->Wr, io->Hp, io->Wp, io->depth_map,
-                           io->disp3, io->mask, h->cfg.baseline, h->cfg.focal_length, p->sa);
+                           io->disp3, io->mask, h->cfg.baseline, h->cfg.focal_length, p->st[0]);
         if (rc != ST_OK) return rc;
     }
+    ST_CUDA_OK(cudaEventRecord(ev(0), p->st[0]));
+    // ---- stream 1: K2 (its det_* outputs were last read by stream 3 and 4 of the slot's previous frame)
+    if (reused) ST_CUDA_OK(cudaStreamWaitEvent(p->st[1], ev(4), 0));
+    if (inputs_ready) ST_CUDA_OK(cudaStreamWaitEvent(p->st[1], (cudaEvent_t)inputs_ready, 0));
     if (io->cls) {
         rc = st_decode_nms(h, io->cls, io->bbox, io->obj, io->num_levels, io->level_h, io->level_w,
                            io->strides, S, io->num_classes, io->scale_w, io->scale_h, io->ori_h, io->ori_w,
                            cap, io->det_boxes, io->det_scores, io->det_labels, io->det_prior, io->det_keep,
-                           io->det_counts, p->sa);
+                           io->det_counts, p->st[1]);
         if (rc != ST_OK) return rc;
     }
+    ST_CUDA_OK(cudaEventRecord(ev(1), p->st[1]));
+    // ---- stream 2: K3 on the detections
+    ST_CUDA_OK(cudaStreamWaitEvent(p->st[2], ev(0), 0));
+    ST_CUDA_OK(cudaStreamWaitEvent(p->st[2], ev(1), 0));
     rc = st_box_depth(io->depth_map, S, io->Hp, io->Wp, io->det_boxes, io->det_counts, cap, io->det_depth,
-                      io->det_scales, io->det_inflated, io->k3_workspace, p->sa);
+                      io->det_scales, io->det_inflated, io->k3_workspace, p->st[2]);
     if (rc != ST_OK) return rc;
-    ST_CUDA_OK(cudaEventRecord(p->ev_a[slot], p->sa));
-    // ---- stage B: the tracker, frames strictly in order on one stream
-    ST_CUDA_OK(cudaStreamWaitEvent(p->sb, p->ev_a[slot], 0));
+    ST_CUDA_OK(cudaEventRecord(ev(2), p->st[2]));
+    // ---- stream 3: the tracker, frames strictly in order
+    ST_CUDA_OK(cudaStreamWaitEvent(p->st[3], ev(2), 0));
     rc = st_track_step(h, S, io->frame_ids, io->det_inflated, io->det_scores, io->det_labels, io->det_scales,
                        io->det_depth, io->det_counts, cap, io->trk_boxes, io->out_scores, io->out_labels,
-                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, p->sb);
+                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, p->st[3]);
     if (rc != ST_OK) return rc;
-    ST_CUDA_OK(cudaEventRecord(p->ev_b[slot], p->sb));
-    // ---- stage C: deflate and the output depth
-    ST_CUDA_OK(cudaStreamWaitEvent(p->sc, p->ev_b[slot], 0));
-    rc = st_scale_boxes(io->trk_boxes, io->out_scales, io->out_counts, S, cap, 1, io->out_boxes, p->sc);
+    ST_CUDA_OK(cudaEventRecord(ev(3), p->st[3]));
+    // ---- stream 4: deflate and the output depth
+    ST_CUDA_OK(cudaStreamWaitEvent(p->st[4], ev(3), 0));
+    rc = st_scale_boxes(io->trk_boxes, io->out_scales, io->out_counts, S, cap, 1, io->out_boxes, p->st[4]);
     if (rc != ST_OK) return rc;
     rc = st_box_depth(io->depth_map, S, io->Hp, io->Wp, io->out_boxes, io->out_counts, cap, io->out_depth,
-                      io->out_scale2, nullptr, io->k3_workspace, p->sc);
+                      io->out_scale2, nullptr, io->k3_workspace, p->st[4]);
     if (rc != ST_OK) return rc;
-    ST_CUDA_OK(cudaEventRecord(p->ev_c[slot], p->sc));
-    if (frame_done) ST_CUDA_OK(cudaEventRecord((cudaEvent_t)frame_done, p->sc));
+    ST_CUDA_OK(cudaEventRecord(ev(4), p->st[4]));
+    if (frame_done) ST_CUDA_OK(cudaEventRecord((cudaEvent_t)frame_done, p->st[4]));
     p->submitted += 1;
     return ST_OK;
 }

@@ -366,13 +366,14 @@ class StereoTrackEngine:
 
 
 class FramePipeline:
-    """Software pipeline over consecutive frames (st_pipeline_* of the C ABI): stage
-    A (K1, K2, K3 on detections) of frame f+2, stage B (tracker) of frame f+1 and
-    stage C (deflate, K3 on tracks) of frame f run concurrently on three library
-    streams.  ``depth`` complete buffer sets are cycled; frame k uses set k % depth
-    and its results stay readable until frame k + depth is submitted."""
+    """Software pipeline over consecutive frames (st_pipeline_* of the C ABI): K1 and
+    K2 of a frame run side by side, then K3 on its detections, the tracker and the
+    deflate + K3 on its tracks, each on its own library stream, so up to five
+    consecutive frames are in different stages at once.  ``depth`` complete buffer
+    sets are cycled; frame k uses set k % depth and its results stay readable until
+    frame k + depth is submitted."""
 
-    def __init__(self, engine, raw_shape, level_shapes, depth=3, num_classes=1):
+    def __init__(self, engine, raw_shape, level_shapes, depth=5, num_classes=1):
         self.engine, self.depth = engine, depth
         S = raw_shape[0]
         self.n_seq = S
@@ -436,7 +437,7 @@ class LockstepGroups:
     path.  One group per GPU is the default: the frame pipeline already overlaps the
     latency-bound stages with the bandwidth-bound ones."""
 
-    def __init__(self, n_seq, n_groups=1, device='cuda:0', depth=3, **cfg_kw):
+    def __init__(self, n_seq, n_groups=1, device='cuda:0', depth=5, **cfg_kw):
         n_groups = max(1, min(n_groups, n_seq))
         base, extra = divmod(n_seq, n_groups)
         self.sizes = [base + (1 if g < extra else 0) for g in range(n_groups)]
