@@ -30,6 +30,10 @@ import torch  # noqa: E402
 WORKLOAD = 'C2'
 SEQ_PER_GPU = 64
 METRIC = 'tracked_frames_per_sec'
+# dram__bytes_read.sum + dram__bytes_write.sum of one k1_disp2depth_flat launch at the default
+# workload (64 x 1280x720), from the `ncu --set full` capture profiles/r01_k1_disp2depth_flat_full*
+# (118.0 MB read + 188.0 MB written; the rest of the 241 MB written is still in L2 at kernel end)
+K1_TRAFFIC_BYTES_C2_S64 = 117.98e6 + 188.03e6
 UNIT = 'frames/s'
 
 
@@ -222,7 +226,11 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     from stereotracking_b200.engine import EngineConfig, LockstepGroups, StereoTrackEngine
 
-    raw, cls, box, obj = generate(cfg, S, F, 20240604 + 1000 + rank, dev)
+    from stereotracking_b200 import shard
+    # whole sequences per rank (video_sampler.py:50-69): rank r owns sequences [first, first + S)
+    first_seq, n_own = shard.shard_sequences(S * world, world, rank)
+    assert n_own == S
+    raw, cls, box, obj = generate(cfg, S, F, 20240604 + 1000 + first_seq, dev)
     eng = StereoTrackEngine(EngineConfig(n_seq=S, max_dets=256, max_tracks=256, max_candidates=2048), device=dev)
     io = eng.make_frame_io(raw.shape[1:], [c.shape[-2:] for c in cls])
     stream = torch.cuda.current_stream(dev)
@@ -355,6 +363,10 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- host-side gather of the last frame's tracks (outside every timed region) -------
+    rows = shard.tracks_to_rows(groups.results(), F - 1, first_sequence=first_seq)
+    gathered = shard.gather_tracks(rows, dst=0)
+
     # ---- reduce over ranks ------------------------------------------------------------
     vals = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -391,7 +403,10 @@ def main():
             higher_is_better=True, scaling='weak', vs_baseline=None,
             dtype='f32 (u16 disparity in, f64 Kalman state and assignment)', data='synthetic', config=config,
             roofline=dict(kernel='k1_disp2depth_flat', bound='hbm', achieved=k1_gbs, peak=peak, unit='GB/s',
-                          frac=k1_gbs / peak, traffic=None, peak_source=peak_src,
+                          frac=k1_gbs / peak,
+                          traffic=K1_TRAFFIC_BYTES_C2_S64 if (args.workload == 'C2' and S == 64) else None,
+                          traffic_unit='bytes per launch (ncu --set full, profiles/r01_k1_disp2depth_flat_full_metrics.csv)',
+                          algorithmic_bytes_per_launch=k1_bytes, peak_source=peak_src,
                           note='HBM-bound kernel of the path (north_star), timed with CUDA events in a serial '
                                'single-stream pass over the same frames; "kernels" gives every stage of that pass'),
             kernels=kernels,
@@ -402,7 +417,8 @@ def main():
             host_issue_ms_per_step=issue_ms / K,
             k4_phase_cycles_median=dict(zip(['filter_predict', 'stage1', 'stage2', 'stage3', 'smooth_order', 'update'],
                                             [int(x) for x in np.median(dbg[:, 8:14], axis=0)])),
-            assignments=dict(solved=int(dbg[:, 5].sum()), exact_fallback=int(dbg[:, 6].sum())), status_bits=int(status.max()), tracked_rows_last_step=tracked_rows)
+            assignments=dict(solved=int(dbg[:, 5].sum()), exact_fallback=int(dbg[:, 6].sum())), status_bits=int(status.max()), tracked_rows_last_step=tracked_rows,
+            gathered_rows_all_ranks=int(len(gathered)))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

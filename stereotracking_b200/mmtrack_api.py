@@ -24,7 +24,7 @@ from .compat import MODELS, TASK_UTILS, InstanceData
 from .engine import EngineConfig, StereoTrackEngine
 
 
-@TASK_UTILS.register_module()
+@TASK_UTILS.register_module(force=True)      # replaces the reference class of the same name
 class KalmanFilter:
     """Constant-velocity Kalman filter on (cx, cy, a, h) (kalman_filter.py:12-58).
 
@@ -66,7 +66,7 @@ class KalmanFilter:
         return self._run(2, mean, covariance, measurement)
 
 
-@MODELS.register_module()
+@MODELS.register_module(force=True)
 class OCSORTTracker_Disparity:
     """OC-SORT tracker carrying per-detection ``scales`` / ``depth``."""
 
@@ -161,7 +161,7 @@ class OCSORTTracker_Disparity:
         return res
 
 
-@MODELS.register_module()
+@MODELS.register_module(force=True)
 class OCSORT_Disparity:
     """Model shell of the hot path: detector -> depth -> per-box depth/scale ->
     tracker -> deflate -> output depth (ocsort_disparity.py:51-111).  ``detector``

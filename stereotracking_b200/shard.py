@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing of the path: whole sequences per rank, no data-path collective.
+
+The reference splits whole videos across ranks with ``np.array_split``
+(mmtrack/datasets/samplers/video_sampler.py:50-69) and gathers per-sequence results
+on the host after the last frame (mmtrack/evaluation/metrics/mot_drone_metrics.py
+:336-345 ``all_gather_object(seq_info)``).  The same here: each rank owns a
+contiguous block of sequences and their track state for their whole life; the only
+communication is one ``gather_object`` of track rows at the end.  Host-side code,
+backend-agnostic (NCCL on the GPU box, gloo in the CPU tests).
+"""
+import numpy as np
+import torch.distributed as dist
+
+
+def shard_sequences(n_sequences, world_size, rank):
+    """(first, count) of the contiguous block of sequences rank ``rank`` owns:
+    ``np.array_split`` semantics (the first ``n % world`` ranks get one more),
+    video_sampler.py:59-66.  Raises like the reference when there are fewer
+    sequences than ranks (:55-57)."""
+    if n_sequences < world_size:
+        raise ValueError(f'only {n_sequences} videos loaded,but {world_size} gpus were given.')
+    if not 0 <= rank < world_size:
+        raise ValueError(f'rank {rank} outside world of {world_size}')
+    base, extra = divmod(n_sequences, world_size)
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def tracks_to_rows(results, frame_id, first_sequence=0):
+    """One lockstep frame of engine results (list of per-sequence dicts) -> float64
+    rows ``[sequence, frame, id, x1, y1, x2, y2, score, depth]``."""
+    rows = []
+    for s, r in enumerate(results):
+        n = len(r['instances_id'])
+        if n == 0:
+            continue
+        block = np.empty((n, 9), np.float64)
+        block[:, 0] = first_sequence + s
+        block[:, 1] = frame_id
+        block[:, 2] = r['instances_id']
+        block[:, 3:7] = r['bboxes']
+        block[:, 7] = r['scores']
+        block[:, 8] = r['depth']
+        rows.append(block)
+    return np.concatenate(rows) if rows else np.empty((0, 9), np.float64)
+
+
+def gather_tracks(rows, dst=0, group=None):
+    """Host-side gather of every rank's track rows on ``dst`` (None elsewhere), ordered
+    by (sequence, frame, position); single-process runs return ``rows``."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rows
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bucket = [None] * world if rank == dst else None
+    dist.gather_object(rows, bucket, dst=dst, group=group)
+    if rank != dst:
+        return None
+    parts = [b for b in bucket if b is not None and len(b)]
+    if not parts:
+        return np.empty((0, 9), np.float64)
+    out = np.concatenate(parts)
+    return out[np.lexsort((out[:, 1], out[:, 0]))]          # stable: keeps the per-frame output order
+
+
+def write_mot_txt(rows, sequence, path, depth_thr=None):
+    """MOTChallenge txt of one sequence as MOTDroneMetrics writes it
+    (mot_drone_metrics.py:195-207 depth-range filter ``depth_thr >= depth > 0``,
+    :231-236 line format; frame ids are 1-based)."""
+    sel = rows[rows[:, 0] == sequence]
+    if depth_thr is not None:
+        with np.errstate(invalid='ignore'):
+            sel = sel[(sel[:, 8] > 0) & (sel[:, 8] <= depth_thr)]
+    with open(path, 'wt') as f:
+        for r in sel:
+            f.write('%d,%d,%.3f,%.3f,%.3f,%.3f,%.3f,-1,-1,-1\n' %
+                    (r[1] + 1, r[2], r[3], r[4], r[5] - r[3], r[6] - r[4], r[7]))
+    return len(sel)

@@ -1,0 +1,110 @@
+"""The drop-in boundary on the GPU: the classes registered under the reference's names
+(OCSORT_Disparity / OCSORTTracker_Disparity / KalmanFilter), built through the registry
+from the keys of configs/stereo_tracking/ocsort/yolox_s_mmyolo_mot_airdrone_disp.py:29-58
+and driven exactly as the reference drives its own (model.predict on TrackDataSample),
+replay the fixtures produced by the unmodified reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+# model block of the shipped config (:29-58), detector replaced by a stand-in
+TRACKER_CFG = dict(type='OCSORTTracker_Disparity', obj_score_thr=0.3, init_track_thr=0.7,
+                   weight_iou_with_det_scores=False, match_iou_thr=0.1, num_tentatives=3,
+                   vel_consist_weight=0.2, vel_delta_t=3, num_frames_retain=30)
+
+
+class _Det:
+    """Stands where the reference PyTorch detector stays: returns the fixture's boxes."""
+
+    def __init__(self, api):
+        self.api, self.next = api, None
+
+    def predict(self, data, data_samples, **kw):
+        class R:
+            pass
+        r = R()
+        r.pred_instances = self.next
+        return [r]
+
+
+@pytest.fixture(scope='module')
+def api():
+    import torch
+    from stereotracking_b200 import compat, mmtrack_api
+    from oracle import disparity as odisp
+    return dict(torch=torch, compat=compat, api=mmtrack_api, odisp=odisp)
+
+
+@pytest.mark.parametrize('name', ['basic', 'occlusion'])
+def test_model_predict_replays_reference_fixture(api, name):
+    torch, compat = api['torch'], api['compat']
+    g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
+    det = _Det(api)
+    model = compat.MODELS.build(dict(type='OCSORT_Disparity', detector=det, motion=dict(type='KalmanFilter'),
+                                     tracker=dict(TRACKER_CFG, max_dets=64, max_tracks=128)))
+    assert type(model.tracker).__name__ == 'OCSORTTracker_Disparity' and model.tracker.empty
+    for f in range(len(g['raw'])):
+        n = int(g['det_count'][f])
+        pre = api['odisp'].preprocess(g['raw'][f])
+        disp = torch.from_numpy(pre['disp'])[None, None, None].repeat(1, 1, 3, 1, 1).cuda()
+        mask = torch.from_numpy(pre['mask'])[None, None, None].cuda()
+        det.next = compat.InstanceData(bboxes=torch.from_numpy(g['det_boxes'][f, :n].copy()).cuda(),
+                                       scores=torch.from_numpy(g['det_scores'][f, :n].copy()).cuda(),
+                                       labels=torch.zeros(n, dtype=torch.int64).cuda())
+        sample = compat.TrackDataSample(metainfo=dict(frame_id=f))
+        out = model.predict(dict(img=torch.zeros_like(disp), disp_postp=disp, disp_mask=mask), [sample])[0]
+        ti = out.pred_track_instances
+        m = int(g['out_count'][f])
+        assert ti.instances_id.dtype == torch.int64 and ti.bboxes.is_cuda
+        np.testing.assert_array_equal(ti.instances_id.cpu().numpy(), g['out_ids'][f, :m], err_msg=f'frame {f}')
+        np.testing.assert_array_equal(ti.labels.cpu().numpy(), g['out_labels'][f, :m])
+        np.testing.assert_array_equal(ti.scores.cpu().numpy(), g['out_scores'][f, :m])
+        np.testing.assert_allclose(ti.bboxes.cpu().numpy(), g['out_bboxes'][f, :m], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(ti.scales.cpu().numpy(), g['out_scales'][f, :m], rtol=2e-6)
+        np.testing.assert_allclose(np.asarray(ti['depth'], np.float32), g['out_depth'][f, :m], rtol=1e-5,
+                                   equal_nan=True)
+        assert ti['gt_depth'] == ti['depth']                       # ocsort_disparity.py:103-104 fallback
+        # raw detections are handed back untouched (:107)
+        np.testing.assert_array_equal(out.pred_det_instances.bboxes.cpu().numpy(), g['det_boxes'][f, :n])
+        # BaseTracker surface
+        k = int(g['st_count'][f])
+        assert model.tracker.ids == g['out_st_ids'][f, :k].tolist()
+        assert model.tracker.confirmed_ids == g['out_st_ids'][f, :k][~g['out_st_tent'][f, :k]].tolist()
+        assert model.tracker.num_tracks == int(g['num_tracks'][f])
+    model.tracker.reset()
+    assert model.tracker.empty and model.tracker.num_tracks == 0
+
+
+def test_kalman_filter_object_matches_reference_fixture(api):
+    g = np.load(os.path.join(GOLDEN, 'ref_kf.npz'))
+    kf = api['compat'].TASK_UTILS.build(dict(type='KalmanFilter'))
+    keys = set(g.files)
+    assert {'mean', 'cov', 'z', 'op'} <= keys, keys
+    mean, cov = None, None
+    for i in range(len(g['op'])):
+        op = int(g['op'][i])
+        if op == 0:
+            mean, cov = kf.initiate(g['z'][i].astype(np.float32))
+        elif op == 1:
+            mean, cov = kf.predict(mean, cov)
+        else:
+            mean, cov = kf.update(mean, cov, g['z'][i].astype(np.float32))
+        np.testing.assert_allclose(mean, g['mean'][i], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(cov, g['cov'][i], rtol=1e-9, atol=1e-12)
+
+
+def test_constructor_errors_follow_the_reference(api):
+    T = api['api'].OCSORTTracker_Disparity
+    with pytest.raises(ValueError):
+        T(cmc=dict(method='ecc'))                                  # :74-75
+    with pytest.raises(NotImplementedError):
+        T(cmc=dict(method='glme_affine'))
+    with pytest.raises(AssertionError):
+        T(momentums=[0.1])                                         # base_tracker.py:26-27
+    with pytest.raises(NotImplementedError):
+        api['api'].KalmanFilter(use_nsa=True)
