@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ST_ABI_VERSION 1
+#define ST_ABI_VERSION 2
 
 enum {
     ST_OK = 0,
@@ -140,6 +140,16 @@ int st_box_depth(const float *depth, int S, int Hp, int Wp, const float *boxes,
                  const int32_t *counts, int cap, float *d, float *scale, float *inflated,
                  int32_t *workspace /* [2 + 4*S*cap] i32 scratch (worklists of large boxes) */,
                  void *stream);
+/* Same, for the second call of a frame (ocsort_disparity.py:100-101, on the deflated
+ * track boxes): row r of `boxes` came from row prev_index[r] of prev_boxes (-1 = none),
+ * whose statistic prev_d was computed by an earlier call on the same depth map.  The
+ * statistic depends on a box only through its truncated corners (:141), so rows whose
+ * truncated corners equal those of their source row take prev_d; all others are
+ * computed.  Results are identical to st_box_depth. */
+int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, const float *boxes,
+                       const int32_t *counts, int cap, float *d, float *scale, float *inflated,
+                       int32_t *workspace, const float *prev_boxes, const int32_t *prev_index,
+                       const float *prev_d, void *stream);
 
 /* scale_bbox(boxes, 1/scales) (ocsort_disparity.py:96-97) or scale_bbox(boxes,
  * scales) when invert == 0. */
@@ -157,7 +167,9 @@ int st_track_step(st_handle *h, int S, const int32_t *frame_ids, const float *de
                   const float *det_scores, const int64_t *det_labels, const float *det_scales,
                   const float *det_depth, const int32_t *det_counts, int det_cap,
                   float *out_boxes, float *out_scores, int64_t *out_labels, float *out_scales,
-                  float *out_depth, int64_t *out_ids, int32_t *out_counts, void *stream);
+                  float *out_depth, int64_t *out_ids, int32_t *out_counts,
+                  int32_t *out_src /* [S,det_cap] input row of every output row, may be NULL */,
+                  void *stream);
 
 /* All buffers of one lockstep frame (device pointers; host arrays where the name
  * says so).  Capacities: every [S,cap,...] array has cap = st_config.max_dets. */
@@ -179,6 +191,7 @@ typedef struct st_frame_io {
     float *det_boxes; float *det_scores; int64_t *det_labels; int32_t *det_prior; int32_t *det_keep;
     int32_t *det_counts; float *det_depth; float *det_scales; float *det_inflated;
     float *trk_boxes; float *trk_depth; float *out_scale2;
+    int32_t *out_src;                  /* [S,cap] detection row of every track row */
     int32_t *k3_workspace;             /* [2 + 4*S*cap] i32 scratch of st_box_depth */
     /* outputs = pred_track_instances fields */
     float *out_boxes; float *out_scores; int64_t *out_labels; float *out_scales; float *out_depth;

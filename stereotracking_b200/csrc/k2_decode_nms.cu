@@ -1,14 +1,19 @@
-// K2: YOLOX head post-process for S frames in lockstep:
+// K2: YOLOX head post-process for S frames in lockstep, two kernels:
 //   k2_score_compact  prior grid, sigmoid(cls)*sigmoid(obj), max over classes,
-//                     score > thr, warp-aggregated compaction
-//   k2_rank_decode    stable rank by (score desc, prior index asc), box decode,
-//                     rescale, scatter into score order
-//   k2_nms_mask       64x64 tiles, warp-ballot suppression bitmask (upper triangle)
-//   k2_nms_scan       greedy keep scan in 64-box chunks, clamp, emit
+//                     score > thr, warp-aggregated compaction          (grid over priors)
+//   k2_sort_nms       one CTA per sequence, everything in shared memory: stable rank
+//                     by (score desc, prior index asc), box decode of the candidates
+//                     only, rescale, greedy NMS in 64-box chunks (warp-ballot bitmask
+//                     for the diagonal block, kept boxes of the chunk against all later
+//                     boxes), clamp, emit in descending score order
 // Replaces the third-party post-process the reference calls at
 // mmtrack/models/detectors/yolo_detector_disparity_v1.py:121-122 (mmyolo 0.2.0
 // YOLOv5Head.predict_by_feat / YOLOXBBoxCoder.decode, mmdet 3.0.0rc4
 // filter_scores_and_topk / _bbox_post_process, mmcv 2.0.0rc3 batched_nms).
+// (Round-1 history: rank/decode, a global N x N/64 suppression mask and the keep scan
+// were three more launches, 95 us of mostly launch and dependent-load latency for
+// ~200 candidates per frame.)
+#include <cmath>
 #include "st_common.cuh"
 
 namespace {
@@ -38,7 +43,7 @@ __device__ __forceinline__ float from_ordered_bits(uint32_t u) {
 }
 
 __global__ void __launch_bounds__(256)
-k2_score_compact(HeadLevels L, int P, int num_classes, float score_thr, int cap,
+k2_score_compact(HeadLevels L, int P, int num_classes, float score_thr, float logit_cut, int cap,
                  int32_t *__restrict__ cand_count, float *__restrict__ cand_score,
                  int32_t *__restrict__ cand_prior, int32_t *__restrict__ cand_label) {
     const int s = blockIdx.y;
@@ -50,15 +55,23 @@ k2_score_compact(HeadLevels L, int P, int num_classes, float score_thr, int cap,
         const int l = level_of(L, p);
         const int q = p - L.prior_off[l];
         const long long hw = (long long)L.h[l] * L.w[l];
-        const float so = st_sigmoid_f32(L.obj[l][(long long)s * hw + q]);
-        // scores = sigmoid(cls) * sigmoid(obj); max over classes, first max wins
-        float best = -1.f;
-        for (int c = 0; c < num_classes; ++c) {
-            float sc = __fmul_rn(st_sigmoid_f32(L.cls[l][((long long)s * num_classes + c) * hw + q]), so);
-            if (sc > best) { best = sc; label = c; }
+        // sigmoid(x) <= score_thr for x <= logit_cut and the other factor is <= 1, so a
+        // logit below the cut cannot pass `score > score_thr`: the float64 exp behind the
+        // correctly rounded sigmoid is only evaluated for the ~1 % of priors that may
+        const float lo = L.obj[l][(long long)s * hw + q];
+        if (lo > logit_cut) {
+            const float so = st_sigmoid_f32(lo);
+            // scores = sigmoid(cls) * sigmoid(obj); max over classes, first max wins
+            float best = -1.f;
+            for (int c = 0; c < num_classes; ++c) {
+                const float lc = L.cls[l][((long long)s * num_classes + c) * hw + q];
+                if (!(lc > logit_cut)) continue;
+                float sc = __fmul_rn(st_sigmoid_f32(lc), so);
+                if (sc > best) { best = sc; label = c; }
+            }
+            score = best;
+            pass = score > score_thr;
         }
-        score = best;
-        pass = score > score_thr;
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, pass);
     if (ballot == 0) return;
@@ -76,212 +89,215 @@ k2_score_compact(HeadLevels L, int P, int num_classes, float score_thr, int cap,
     }
 }
 
-__global__ void __launch_bounds__(128)
-k2_rank_decode(HeadLevels L, int cap, float scale_w, float scale_h,
-               const int32_t *__restrict__ cand_count, const float *__restrict__ cand_score,
-               const int32_t *__restrict__ cand_prior, const int32_t *__restrict__ cand_label,
-               float *__restrict__ sort_box, float *__restrict__ sort_score,
-               int32_t *__restrict__ sort_prior, int32_t *__restrict__ sort_label,
-               uint32_t *__restrict__ max_coord, int32_t *__restrict__ status) {
-    const int s = blockIdx.y;
-    int n = cand_count[s];
-    if (n > cap) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&status[s], ST_STATUS_CAND_OVERFLOW);
-        n = cap;
-    }
-    if (blockIdx.x * blockDim.x >= n) return;
-    __shared__ uint32_t t_key[128];
-    __shared__ int32_t t_pri[128];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    const long long base = (long long)s * cap;
-    uint32_t key = 0;
-    int pri = 0;
-    if (live) { key = __float_as_uint(cand_score[base + i]); pri = cand_prior[base + i]; }
-    // scores are positive floats, so their bit patterns order like the values
-    int rank = 0;
-    for (int t0 = 0; t0 < n; t0 += 128) {
-        int j = t0 + threadIdx.x;
-        __syncthreads();
-        if (j < n) { t_key[threadIdx.x] = __float_as_uint(cand_score[base + j]); t_pri[threadIdx.x] = cand_prior[base + j]; }
-        __syncthreads();
-        int m = min(128, n - t0);
-        if (live)
-            for (int k = 0; k < m; ++k)
-                rank += (t_key[k] > key) || (t_key[k] == key && t_pri[k] < pri);
-    }
-    float mx = -3.0e38f;
-    if (live) {
-        const int l = level_of(L, pri);
-        const int q = pri - L.prior_off[l];
-        const long long hw = (long long)L.h[l] * L.w[l];
-        const float *bp = L.bbox[l] + (long long)s * 4 * hw + q;
-        const float sf = (float)L.stride[l];
-        const float px = __fmul_rn((float)(q % L.w[l]), sf);
-        const float py = __fmul_rn((float)(q / L.w[l]), sf);
-        // YOLOXBBoxCoder.decode: xy = p*s + prior, wh = exp(p)*s, xyxy = xy -/+ wh/2
-        const float cx = __fadd_rn(__fmul_rn(bp[0], sf), px);
-        const float cy = __fadd_rn(__fmul_rn(bp[hw], sf), py);
-        const float hwid = __fmul_rn(__fmul_rn(st_exp_f32(bp[2 * hw]), sf), 0.5f);
-        const float hhei = __fmul_rn(__fmul_rn(st_exp_f32(bp[3 * hw]), sf), 0.5f);
-        float4 b;
-        b.x = __fdiv_rn(__fsub_rn(cx, hwid), scale_w);
-        b.y = __fdiv_rn(__fsub_rn(cy, hhei), scale_h);
-        b.z = __fdiv_rn(__fadd_rn(cx, hwid), scale_w);
-        b.w = __fdiv_rn(__fadd_rn(cy, hhei), scale_h);
-        reinterpret_cast<float4 *>(sort_box)[base + rank] = b;
-        sort_score[base + rank] = __uint_as_float(key);
-        sort_prior[base + rank] = pri;
-        sort_label[base + rank] = cand_label[base + i];
-        mx = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));
-    }
-    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx > -3.0e38f) atomicMax(&max_coord[s], ordered_bits(mx));
-}
-
-// mmcv nms criterion: inter / (Sa + Sb - inter) > thr, offset 0
+// mmcv nms criterion: inter / (Sa + Sb - inter) > thr, offset 0.
+// Boxes that do not overlap have inter = 0 and 0 / union (= +-0 or NaN) is never
+// > thr for thr >= 0, so the division is only evaluated for overlapping pairs -
+// nearly all of the N^2/2 pairs of a frame are disjoint.
 __device__ __forceinline__ bool suppresses(const float4 a, const float4 b, float thr) {
-    const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
-    const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+    const float wr = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    const float hr = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    if (thr >= 0.f && (!(wr > 0.f) || !(hr > 0.f))) return false;
+    const float w = fmaxf(wr, 0.f), h = fmaxf(hr, 0.f);
     const float inter = __fmul_rn(w, h);
     const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
     const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
 }
 
-// grid (kMaskCtas, S): the CTAs of a sequence stride over the live upper-triangular
-// 64x64 tiles only (a (words, words, S) grid launched 65 536 CTAs at the default
-// capacity, nearly all of which found nothing to do: 45 us for ~10 live tiles).
-constexpr int kMaskCtas = 16;
-
-__global__ void __launch_bounds__(128)
-k2_nms_mask(int cap, int words, float iou_thr, int num_classes,
-            const int32_t *__restrict__ cand_count, const float *__restrict__ sort_box,
-            const int32_t *__restrict__ sort_label, const uint32_t *__restrict__ max_coord,
-            unsigned long long *__restrict__ nms_mask) {
-    const int s = blockIdx.y;
-    const int n = min(cand_count[s], cap);
-    const int nw = (n + 63) >> 6;
-    const int n_tiles = nw * (nw + 1) / 2;
-    __shared__ float4 rows[64], cols[64];
-    const long long base = (long long)s * cap;
-    // batched_nms: boxes + label * (max_coordinate + 1) keeps classes apart
-    const float off_unit = num_classes > 1 ? __fadd_rn(from_ordered_bits(max_coord[s]), 1.0f) : 0.f;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        int rb = 0, rem = t;                        // tile t -> (rb, cb), cb >= rb
-        while (rem >= nw - rb) { rem -= nw - rb; ++rb; }
-        const int cb = rb + rem;
-        __syncthreads();                            // rows / cols are reused across tiles
-        if (threadIdx.x < 64) {
-            int i = rb * 64 + threadIdx.x;
-            if (i < n) {
-                float4 b = reinterpret_cast<const float4 *>(sort_box)[base + i];
-                float o = num_classes > 1 ? __fmul_rn((float)sort_label[base + i], off_unit) : 0.f;
-                rows[threadIdx.x] = make_float4(__fadd_rn(b.x, o), __fadd_rn(b.y, o), __fadd_rn(b.z, o), __fadd_rn(b.w, o));
-            }
-        } else {
-            int tt = threadIdx.x - 64, j = cb * 64 + tt;
-            if (j < n) {
-                float4 b = reinterpret_cast<const float4 *>(sort_box)[base + j];
-                float o = num_classes > 1 ? __fmul_rn((float)sort_label[base + j], off_unit) : 0.f;
-                cols[tt] = make_float4(__fadd_rn(b.x, o), __fadd_rn(b.y, o), __fadd_rn(b.z, o), __fadd_rn(b.w, o));
-            }
-        }
-        __syncthreads();
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int j0 = cb * 64 + lane, j1 = j0 + 32;
-        for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-            const int i = rb * 64 + r;
-            if (i >= n) break;                       // uniform across the warp
-            const float4 a = rows[r];
-            const bool p0 = (j0 < n) && (j0 > i) && suppresses(a, cols[lane], iou_thr);
-            const bool p1 = (j1 < n) && (j1 > i) && suppresses(a, cols[lane + 32], iou_thr);
-            const unsigned lo = __ballot_sync(0xffffffffu, p0);
-            const unsigned hi = __ballot_sync(0xffffffffu, p1);
-            if (lane == 0)
-                nms_mask[(base + i) * words + cb] = ((unsigned long long)hi << 32) | lo;
-        }
-    }
-}
-
 __device__ __forceinline__ float clamp_like_torch(float x, float lo, float hi) {
     return (x != x) ? x : fminf(fmaxf(x, lo), hi);
 }
 
-// One CTA per sequence.  Boxes are visited in chunks of 64: the 64x64 diagonal
-// block is resolved serially from shared memory, then the rows of the kept
-// boxes are OR-ed into the remaining words in parallel.
-__global__ void __launch_bounds__(256)
-k2_nms_scan(int cap, int words, int det_cap, float ori_w, float ori_h,
-            const int32_t *__restrict__ cand_count, const float *__restrict__ sort_box,
-            const float *__restrict__ sort_score, const int32_t *__restrict__ sort_prior,
-            const int32_t *__restrict__ sort_label, const unsigned long long *__restrict__ nms_mask,
-            float *__restrict__ boxes, float *__restrict__ scores, int64_t *__restrict__ labels,
-            int32_t *__restrict__ prior_idx, int32_t *__restrict__ keep_idx,
+constexpr int kNmsThreads = 1024;
+
+__host__ __device__ inline size_t sort_nms_smem(int cap) {
+    // box (score order), 64-bit sort key, label + rank (candidate order), score / prior / label
+    // (score order), removed bits, diagonal block, kept list
+    return (size_t)cap * (16 + 8 + 4 + 4 + 4 + 4 + 4) + (size_t)((cap + 63) / 64) * 8 + 64 * 8 + 64 * 4 + 64;
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+k2_sort_nms(HeadLevels L, int cap, int num_classes, float scale_w, float scale_h, float iou_thr, int det_cap,
+            float ori_w, float ori_h, const int32_t *__restrict__ cand_count,
+            const float *__restrict__ cand_score, const int32_t *__restrict__ cand_prior,
+            const int32_t *__restrict__ cand_label, float *__restrict__ boxes, float *__restrict__ scores,
+            int64_t *__restrict__ labels, int32_t *__restrict__ prior_idx, int32_t *__restrict__ keep_idx,
             int32_t *__restrict__ counts, int32_t *__restrict__ status) {
-    extern __shared__ unsigned long long smem_u64[];
-    unsigned long long *remv = smem_u64;            // [words]
-    unsigned long long *diag = smem_u64 + words;    // [64]
+    extern __shared__ __align__(16) unsigned char k2_smem[];
+    float4 *sbox = reinterpret_cast<float4 *>(k2_smem);                    // [cap] score order
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(sbox + cap);   // [cap] candidate order
+    int32_t *lab = reinterpret_cast<int32_t *>(skey + cap);                // [cap] candidate order
+    int32_t *rnk = lab + cap;                                              // [cap] candidate order
+    float *sscore = reinterpret_cast<float *>(rnk + cap);                  // [cap] score order
+    int32_t *sprior = reinterpret_cast<int32_t *>(sscore + cap);
+    int32_t *slabel = sprior + cap;
+    unsigned long long *remv = reinterpret_cast<unsigned long long *>(slabel + cap);   // [(cap+63)/64]
+    unsigned long long *diag = remv + (cap + 63) / 64;                     // [64]
+    int32_t *klist = reinterpret_cast<int32_t *>(diag + 64);               // [64] kept rows of the chunk
     __shared__ unsigned long long keepbits;
-    __shared__ int kept_total;
+    __shared__ uint32_t max_bits;
+    __shared__ int chunk_base, n_kept_chunk;
+
     const int s = blockIdx.x;
-    const int n = min(cand_count[s], cap);
-    const int nw = (n + 63) >> 6;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n = cand_count[s];
+    if (n > cap) {
+        if (tid == 0) atomicOr(&status[s], ST_STATUS_CAND_OVERFLOW);
+        n = cap;
+    }
     const long long base = (long long)s * cap;
-    for (int w = threadIdx.x; w < nw; w += blockDim.x) remv[w] = 0ull;
-    if (threadIdx.x == 0) kept_total = 0;
+    const int nw = (n + 63) >> 6;
+    // sort key: score bits (positive floats order like their bit patterns) above the
+    // inverted prior index, so that "greater key" = higher score, then lower prior index
+    for (int i = tid; i < n; i += kNmsThreads) {
+        skey[i] = ((unsigned long long)__float_as_uint(cand_score[base + i]) << 32) |
+                  (unsigned long long)(0xffffffffu - (uint32_t)cand_prior[base + i]);
+        lab[i] = cand_label[base + i];
+        rnk[i] = 0;
+    }
+    for (int w = tid; w < nw; w += kNmsThreads) remv[w] = 0ull;
+    if (tid == 0) max_bits = 0u;
     __syncthreads();
+    // ---- stable rank: every thread counts the greater keys of one slice of the list ------
+    if (n > 0) {
+        const int parts = max(1, kNmsThreads / n);              // slices per candidate
+        const int slice = (n + parts - 1) / parts;
+        for (int t = tid; t < n * parts; t += kNmsThreads) {
+            const int i = t % n, part = t / n;
+            const unsigned long long k = skey[i];
+            const int j0 = part * slice, j1 = min(n, j0 + slice);
+            int cnt = 0;
+#pragma unroll 4
+            for (int j = j0; j < j1; ++j) cnt += skey[j] > k;
+            if (cnt) atomicAdd(&rnk[i], cnt);
+        }
+    }
+    __syncthreads();
+    // ---- decode, scatter into score order -------------------------------------------------
+    float mx = -3.0e38f;
+    for (int i = tid; i < n; i += kNmsThreads) {
+        const unsigned long long k = skey[i];
+        const int p = (int)(0xffffffffu - (uint32_t)k);
+        const int rank = rnk[i];
+        const int l = level_of(L, p);
+        const int q = p - L.prior_off[l];
+        const long long hw = (long long)L.h[l] * L.w[l];
+        const float *bp = L.bbox[l] + (long long)s * 4 * hw + q;
+        const float r0 = bp[0], r1 = bp[hw], r2 = bp[2 * hw], r3 = bp[3 * hw];
+        const float sf = (float)L.stride[l];
+        const float px = __fmul_rn((float)(q % L.w[l]), sf);
+        const float py = __fmul_rn((float)(q / L.w[l]), sf);
+        // YOLOXBBoxCoder.decode: xy = p*s + prior, wh = exp(p)*s, xyxy = xy -/+ wh/2
+        const float cx = __fadd_rn(__fmul_rn(r0, sf), px);
+        const float cy = __fadd_rn(__fmul_rn(r1, sf), py);
+        const float hwid = __fmul_rn(__fmul_rn(st_exp_f32(r2), sf), 0.5f);
+        const float hhei = __fmul_rn(__fmul_rn(st_exp_f32(r3), sf), 0.5f);
+        float4 b;
+        b.x = __fdiv_rn(__fsub_rn(cx, hwid), scale_w);
+        b.y = __fdiv_rn(__fsub_rn(cy, hhei), scale_h);
+        b.z = __fdiv_rn(__fadd_rn(cx, hwid), scale_w);
+        b.w = __fdiv_rn(__fadd_rn(cy, hhei), scale_h);
+        sbox[rank] = b;
+        sscore[rank] = __uint_as_float((uint32_t)(k >> 32));
+        sprior[rank] = p;
+        slabel[rank] = lab[i];
+        mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+    }
+    if (num_classes > 1) {
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0 && mx > -3.0e38f) atomicMax(&max_bits, ordered_bits(mx));
+    }
+    __syncthreads();
+    // batched_nms: boxes + label * (max_coordinate + 1) keeps classes apart
+    const float off_unit = num_classes > 1 ? __fadd_rn(from_ordered_bits(max_bits), 1.0f) : 0.f;
+    auto nms_box = [&](int i) {
+        float4 b = sbox[i];
+        if (num_classes > 1) {
+            const float o = __fmul_rn((float)slabel[i], off_unit);
+            b = make_float4(__fadd_rn(b.x, o), __fadd_rn(b.y, o), __fadd_rn(b.z, o), __fadd_rn(b.w, o));
+        }
+        return b;
+    };
+    // ---- greedy NMS in 64-box chunks (two barriers per chunk) ---------------------------------
+    int kept_total = 0;                       // thread 0 only
     for (int c = 0; c < nw; ++c) {
-        const int rows_here = min(64, n - c * 64);
-        if (threadIdx.x < 64)
-            diag[threadIdx.x] = threadIdx.x < rows_here
-                                    ? nms_mask[(base + c * 64 + threadIdx.x) * words + c] : 0ull;
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        const int r0 = c * 64, rows_here = min(64, n - r0);
+        // (a) suppression bitmask of the chunk against itself (upper triangle), two rows per warp
+        for (int r = warp; r < rows_here; r += kNmsThreads / 32) {
+            const int i = r0 + r;
+            const float4 a = nms_box(i);
+            const int j0 = r0 + lane, j1 = j0 + 32;
+            const bool p0 = j0 < n && j0 > i && suppresses(a, nms_box(j0), iou_thr);
+            const bool p1 = j1 < n && j1 > i && suppresses(a, nms_box(j1), iou_thr);
+            const unsigned lo = __ballot_sync(0xffffffffu, p0);
+            const unsigned hi = __ballot_sync(0xffffffffu, p1);
+            if (lane == 0) diag[r] = ((unsigned long long)hi << 32) | lo;
+        }
+        __syncthreads();          // diag complete; every thread has finished step (c) of the previous chunk
+        // (b) serial resolution of the chunk: visit only the rows that are still alive
+        if (tid == 0) {
+            const unsigned long long live = rows_here == 64 ? ~0ull : ((1ull << rows_here) - 1ull);
             unsigned long long cur = remv[c], kb = 0ull;
-            for (int r = 0; r < rows_here; ++r) {
-                if (!((cur >> r) & 1ull)) { kb |= 1ull << r; cur |= diag[r]; }
+            int nk = 0;
+            while (true) {
+                const unsigned long long todo = ~cur & live & ~kb;
+                if (!todo) break;
+                const int r = __ffsll((long long)todo) - 1;
+                kb |= 1ull << r;
+                cur |= diag[r];               // diag[r] has only bits above r
+                klist[nk++] = r0 + r;
             }
             keepbits = kb;
+            n_kept_chunk = nk;
+            chunk_base = kept_total;
+            kept_total += nk;
         }
         __syncthreads();
         const unsigned long long kb = keepbits;
-        const int rest = nw - (c + 1);
-        for (int idx = threadIdx.x; idx < rows_here * rest; idx += blockDim.x) {
-            const int r = idx / rest, w = c + 1 + idx % rest;
-            if ((kb >> r) & 1ull) {
-                unsigned long long m = nms_mask[(base + c * 64 + r) * words + w];
-                if (m) atomicOr(&remv[w], m);
-            }
+        const int nk = n_kept_chunk;
+        // (c) the kept boxes of the chunk against every later box
+        for (int j = r0 + 64 + tid; j < n; j += kNmsThreads) {
+            if ((remv[j >> 6] >> (j & 63)) & 1ull) continue;
+            const float4 bj = nms_box(j);
+            for (int t = 0; t < nk; ++t)
+                if (suppresses(nms_box(klist[t]), bj, iou_thr)) {
+                    atomicOr(&remv[j >> 6], 1ull << (j & 63));
+                    break;
+                }
         }
-        // emit the kept boxes of this chunk in order
-        if (threadIdx.x < 64 && ((kb >> threadIdx.x) & 1ull)) {
-            const int pos = kept_total + __popcll(kb & ((1ull << threadIdx.x) - 1ull));
-            const int i = c * 64 + threadIdx.x;
+        // (d) emit the kept boxes of this chunk in order
+        if (tid < 64 && ((kb >> tid) & 1ull)) {
+            const int pos = chunk_base + __popcll(kb & ((1ull << tid) - 1ull));
+            const int i = r0 + tid;
             if (pos < det_cap) {
-                const float4 b = reinterpret_cast<const float4 *>(sort_box)[base + i];
+                const float4 b = sbox[i];
                 const long long o = (long long)s * det_cap + pos;
                 // results.bboxes[:, 0::2].clamp_(0, ori_w); [:, 1::2].clamp_(0, ori_h)
                 reinterpret_cast<float4 *>(boxes)[o] =
                     make_float4(clamp_like_torch(b.x, 0.f, ori_w), clamp_like_torch(b.y, 0.f, ori_h),
                                 clamp_like_torch(b.z, 0.f, ori_w), clamp_like_torch(b.w, 0.f, ori_h));
-                scores[o] = sort_score[base + i];
-                labels[o] = (int64_t)sort_label[base + i];
-                prior_idx[o] = sort_prior[base + i];
+                scores[o] = sscore[i];
+                labels[o] = (int64_t)slabel[i];
+                prior_idx[o] = sprior[i];
                 keep_idx[o] = i;
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) kept_total += __popcll(kb);
-        __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         if (kept_total > det_cap) { atomicOr(&status[s], ST_STATUS_DET_OVERFLOW); kept_total = det_cap; }
         counts[s] = kept_total;
     }
 }
 
 }  // namespace
+
+// called by st_create: opt in to the dynamic shared memory k2_sort_nms needs at this capacity
+int st_k2_configure(int max_candidates) {
+    const size_t need = sort_nms_smem(max_candidates);
+    if (need > 220 * 1024) return ST_ERR_CAPACITY;
+    return cudaFuncSetAttribute(k2_sort_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) == cudaSuccess
+               ? ST_OK : ST_ERR_CUDA;
+}
 
 extern "C" int st_decode_nms(st_handle *h, const float *const *cls_host, const float *const *bbox_host,
                              const float *const *obj_host, int num_levels, const int32_t *level_h_host,
@@ -306,20 +322,16 @@ extern "C" int st_decode_nms(st_handle *h, const float *const *cls_host, const f
     }
     L.prior_off[num_levels] = P;
     const int cap = h->cfg.max_candidates;
-    const int words = (cap + 63) / 64;
+    // sigmoid(x) <= thr  <=>  x <= log(thr / (1 - thr)); a small margin keeps the cut conservative
+    const double thr = (double)h->cfg.score_thr;
+    const float logit_cut = (thr > 0.0 && thr < 1.0) ? (float)(log(thr / (1.0 - thr)) - 1e-3) : -3.0e38f;
     ST_CUDA_OK(cudaMemsetAsync(h->cand_count, 0, sizeof(int32_t) * S, st));
-    ST_CUDA_OK(cudaMemsetAsync(h->max_coord, 0, sizeof(uint32_t) * S, st));
     k2_score_compact<<<dim3((P + 255) / 256, S), 256, 0, st>>>(
-        L, P, num_classes, h->cfg.score_thr, cap, h->cand_count, h->cand_score, h->cand_prior, h->cand_label);
-    k2_rank_decode<<<dim3((cap + 127) / 128, S), 128, 0, st>>>(
-        L, cap, scale_w, scale_h, h->cand_count, h->cand_score, h->cand_prior, h->cand_label,
-        h->sort_box, h->sort_score, h->sort_prior, h->sort_label, h->max_coord, h->st.status);
-    k2_nms_mask<<<dim3(kMaskCtas, S), 128, 0, st>>>(
-        cap, words, h->cfg.nms_iou_thr, num_classes, h->cand_count, h->sort_box, h->sort_label,
-        h->max_coord, h->nms_mask);
-    k2_nms_scan<<<S, 256, sizeof(unsigned long long) * (words + 64), st>>>(
-        cap, words, det_cap, (float)ori_w, (float)ori_h, h->cand_count, h->sort_box, h->sort_score,
-        h->sort_prior, h->sort_label, h->nms_mask, boxes, scores, labels, prior_idx, keep_idx,
-        counts, h->st.status);
+        L, P, num_classes, h->cfg.score_thr, logit_cut, cap, h->cand_count, h->cand_score, h->cand_prior,
+        h->cand_label);
+    k2_sort_nms<<<S, kNmsThreads, sort_nms_smem(cap), st>>>(
+        L, cap, num_classes, scale_w, scale_h, h->cfg.nms_iou_thr, det_cap, (float)ori_w, (float)ori_h,
+        h->cand_count, h->cand_score, h->cand_prior, h->cand_label, boxes, scores, labels, prior_idx,
+        keep_idx, counts, h->st.status);
     return st_last_launch();
 }

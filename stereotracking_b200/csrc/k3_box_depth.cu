@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(kWarps * 32)
 k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
              const int32_t *__restrict__ counts, int cap, float *__restrict__ d_out,
              float *__restrict__ scale_out, float *__restrict__ inflated, int32_t *__restrict__ worklist,
-             int list_cap) {
+             int list_cap, const float *__restrict__ prev_boxes, const int32_t *__restrict__ prev_index,
+             const float *__restrict__ prev_d) {
     __shared__ float staged_all[kWarps][kStage];
     __shared__ int hist_all[kWarps][512];
     const int s = blockIdx.y;
@@ -210,6 +211,35 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
     const long long o = (long long)s * cap + bi;
     const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
     const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
+    // Reuse: the statistic depends on the box only through its truncated corners.  The
+    // second call of a frame (ocsort_disparity.py:100-101) runs on the deflated track
+    // boxes, which are the inflated-then-deflated detection boxes: whenever the
+    // truncated corners equal those of the detection the row came from, the value of
+    // the first call is the value of this one.
+    if (prev_index) {
+        const int pi = prev_index[o];
+        if (pi >= 0 && pi < cap) {
+            const float4 pb = reinterpret_cast<const float4 *>(prev_boxes)[(long long)s * cap + pi];
+            if (trunc_i64(pb.x) == b0 && trunc_i64(pb.y) == b1 && trunc_i64(pb.z) == b2 && trunc_i64(pb.w) == b3) {
+                if (lane == 0) {
+                    const float d = prev_d[(long long)s * cap + pi];
+                    const float dd = __fmul_rn(d, d);
+                    d_out[o] = d;
+                    scale_out[o] = (dd != dd) ? dd : fmaxf(fminf(dd, 3.f), 1.f);
+                    if (inflated) {
+                        const float scale = scale_out[o];
+                        const float cx = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
+                        const float cy = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
+                        const float hw = __fmul_rn(__fmul_rn(__fsub_rn(box.z, box.x), scale), 0.5f);
+                        const float hh = __fmul_rn(__fmul_rn(__fsub_rn(box.w, box.y), scale), 0.5f);
+                        reinterpret_cast<float4 *>(inflated)[o] =
+                            make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+                    }
+                }
+                return;
+            }
+        }
+    }
     BoxCtx c;
     c.dm = depth + (long long)s * Hp * Wp;
     c.Wp = Wp;
@@ -784,13 +814,22 @@ __global__ void k3_scale_boxes(const float *__restrict__ boxes, const float *__r
 extern "C" int st_box_depth(const float *depth, int S, int Hp, int Wp, const float *boxes,
                             const int32_t *counts, int cap, float *d, float *scale,
                             float *inflated, int32_t *workspace, void *stream) {
+    return st_box_depth_reuse(depth, S, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace, nullptr,
+                              nullptr, nullptr, stream);
+}
+
+extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, const float *boxes,
+                                  const int32_t *counts, int cap, float *d, float *scale, float *inflated,
+                                  int32_t *workspace, const float *prev_boxes, const int32_t *prev_index,
+                                  const float *prev_d, void *stream) {
     if (!depth || !boxes || !counts || !d || !scale || !workspace || S < 0 || cap < 1 || Hp < 1 || Wp < 1)
         return ST_ERR_INVALID_ARG;
+    if (prev_index && (!prev_boxes || !prev_d)) return ST_ERR_INVALID_ARG;
     if (S == 0) return ST_OK;
     ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 2, (cudaStream_t)stream));
     const int list_cap = S * cap;
     k3_box_depth<<<dim3((cap + kWarps - 1) / kWarps, S), kWarps * 32, 0, (cudaStream_t)stream>>>(
-        depth, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace, list_cap);
+        depth, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace, list_cap, prev_boxes, prev_index, prev_d);
     static int sms = 0;
     if (!sms) {
         int dev = 0;

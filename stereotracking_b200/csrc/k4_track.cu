@@ -274,7 +274,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
               float *cost_ws /* written and re-read in this kernel: no __restrict__ */, float *__restrict__ out_boxes, float *__restrict__ out_scores,
               int64_t *__restrict__ out_labels, float *__restrict__ out_scales,
               float *__restrict__ out_depth, int64_t *__restrict__ out_ids,
-              int32_t *__restrict__ out_counts) {
+              int32_t *__restrict__ out_counts, int32_t *__restrict__ out_src /* may be null */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int sh_cnt[4];
     __shared__ int sh_nlive;
@@ -532,6 +532,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             out_scales[o] = dv.scales[i];
             out_depth[o] = dv.depth[i];
             out_ids[o] = id;
+            if (out_src) out_src[o] = i;
         }
     }
     __syncthreads();
@@ -639,7 +640,7 @@ void take(Tp *&ptr, unsigned char *&cursor, size_t count) {
 // nullptr only measures
 size_t layout(st_handle *h, unsigned char *base) {
     const size_t S = h->cfg.max_sequences, T = h->cfg.max_tracks, D = h->cfg.max_dets;
-    const size_t N = h->cfg.max_candidates, W = (N + 63) / 64;
+    const size_t N = h->cfg.max_candidates;
     unsigned char *c = base;
     TrackState &st = h->st;
     take(st.n_live, c, S); take(st.next_id, c, S); take(st.order, c, S * T); take(st.free_slots, c, S * T);
@@ -654,9 +655,7 @@ size_t layout(st_handle *h, unsigned char *base) {
     take(st.last_box, c, S * T * 4); take(st.last_score, c, S * T); take(st.last_scale, c, S * T);
     take(st.last_depth, c, S * T); take(st.last_label, c, S * T);
     take(h->cand_count, c, S); take(h->cand_score, c, S * N); take(h->cand_prior, c, S * N);
-    take(h->cand_label, c, S * N); take(h->sort_box, c, S * N * 4); take(h->sort_score, c, S * N);
-    take(h->sort_prior, c, S * N); take(h->sort_label, c, S * N); take(h->max_coord, c, S);
-    take(h->nms_mask, c, S * N * W);
+    take(h->cand_label, c, S * N);
     take(h->cost, c, S * T * D);
     return (size_t)(c - base);
 }
@@ -704,6 +703,7 @@ extern "C" int st_create(const st_config *cfg, st_handle **out) {
     layout(h, static_cast<unsigned char *>(h->all_mem));
     if (cudaMemset(h->all_mem, 0, h->all_bytes) != cudaSuccess) { cudaFree(h->all_mem); delete h; return ST_ERR_CUDA; }
     const size_t smem = smem_bytes(cfg->max_tracks, cfg->max_dets);
+    if (st_k2_configure(cfg->max_candidates) != ST_OK) { cudaFree(h->all_mem); delete h; return ST_ERR_CAPACITY; }
     if (cudaFuncSetAttribute(k4_track_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(k5_lapjv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(stlap::scratch_bytes(cfg->max_tracks + cfg->max_dets) +
@@ -769,7 +769,8 @@ extern "C" int st_track_step(st_handle *h, int S, const int32_t *frame_ids, cons
                              const float *det_scores, const int64_t *det_labels, const float *det_scales,
                              const float *det_depth, const int32_t *det_counts, int det_cap,
                              float *out_boxes, float *out_scores, int64_t *out_labels, float *out_scales,
-                             float *out_depth, int64_t *out_ids, int32_t *out_counts, void *stream) {
+                             float *out_depth, int64_t *out_ids, int32_t *out_counts, int32_t *out_src,
+                             void *stream) {
     if (!h || S < 0 || S > h->cfg.max_sequences || !frame_ids || !det_boxes || !det_scores || !det_labels ||
         !det_scales || !det_depth || !det_counts || det_cap < 1 || !out_boxes || !out_scores || !out_labels ||
         !out_scales || !out_depth || !out_ids || !out_counts)
@@ -786,7 +787,7 @@ extern "C" int st_track_step(st_handle *h, int S, const int32_t *frame_ids, cons
     const size_t smem = smem_bytes(pr.T, pr.D);
     k4_track_step<<<S, kThreads, smem, (cudaStream_t)stream>>>(
         h->st, pr, frame_ids, det_boxes, det_scores, det_labels, det_scales, det_depth, det_counts, det_cap,
-        h->cost, out_boxes, out_scores, out_labels, out_scales, out_depth, out_ids, out_counts);
+        h->cost, out_boxes, out_scores, out_labels, out_scales, out_depth, out_ids, out_counts, out_src);
     return st_last_launch();
 }
 

@@ -28,12 +28,14 @@ extern "C" int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *s
     if (rc != ST_OK) return rc;
     rc = st_track_step(h, S, io->frame_ids, io->det_inflated, io->det_scores, io->det_labels, io->det_scales,
                        io->det_depth, io->det_counts, cap, io->trk_boxes, io->out_scores, io->out_labels,
-                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, stream);
+                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, io->out_src, stream);
     if (rc != ST_OK) return rc;
     rc = st_scale_boxes(io->trk_boxes, io->out_scales, io->out_counts, S, cap, 1, io->out_boxes, stream);
     if (rc != ST_OK) return rc;
-    return st_box_depth(io->depth_map, S, io->Hp, io->Wp, io->out_boxes, io->out_counts, cap, io->out_depth,
-                        io->out_scale2, nullptr, io->k3_workspace, stream);
+    // rows whose truncated corners equal those of their detection take its statistic (st_box_depth_reuse)
+    return st_box_depth_reuse(io->depth_map, S, io->Hp, io->Wp, io->out_boxes, io->out_counts, cap, io->out_depth,
+                              io->out_scale2, nullptr, io->k3_workspace, io->out_src ? io->det_boxes : nullptr,
+                              io->out_src, io->out_src ? io->det_depth : nullptr, stream);
 }
 
 
@@ -149,15 +151,16 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     ST_CUDA_OK(cudaStreamWaitEvent(p->st[3], ev(2), 0));
     rc = st_track_step(h, S, io->frame_ids, io->det_inflated, io->det_scores, io->det_labels, io->det_scales,
                        io->det_depth, io->det_counts, cap, io->trk_boxes, io->out_scores, io->out_labels,
-                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, p->st[3]);
+                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, io->out_src, p->st[3]);
     if (rc != ST_OK) return rc;
     ST_CUDA_OK(cudaEventRecord(ev(3), p->st[3]));
     // ---- stream 4: deflate and the output depth
     ST_CUDA_OK(cudaStreamWaitEvent(p->st[4], ev(3), 0));
     rc = st_scale_boxes(io->trk_boxes, io->out_scales, io->out_counts, S, cap, 1, io->out_boxes, p->st[4]);
     if (rc != ST_OK) return rc;
-    rc = st_box_depth(io->depth_map, S, io->Hp, io->Wp, io->out_boxes, io->out_counts, cap, io->out_depth,
-                      io->out_scale2, nullptr, io->k3_workspace, p->st[4]);
+    rc = st_box_depth_reuse(io->depth_map, S, io->Hp, io->Wp, io->out_boxes, io->out_counts, cap, io->out_depth,
+                            io->out_scale2, nullptr, io->k3_workspace, io->out_src ? io->det_boxes : nullptr,
+                            io->out_src, io->out_src ? io->det_depth : nullptr, p->st[4]);
     if (rc != ST_OK) return rc;
     ST_CUDA_OK(cudaEventRecord(ev(4), p->st[4]));
     if (frame_done) ST_CUDA_OK(cudaEventRecord((cudaEvent_t)frame_done, p->st[4]));

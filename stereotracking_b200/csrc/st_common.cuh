@@ -15,6 +15,8 @@
         if (e__ != cudaSuccess) return ST_ERR_CUDA;   \
     } while (0)
 
+int st_k2_configure(int max_candidates);    // k2_decode_nms.cu
+
 static inline int st_last_launch() {
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
@@ -64,12 +66,6 @@ struct st_handle {
     float *cand_score;      // [S, N]
     int32_t *cand_prior;    // [S, N]
     int32_t *cand_label;    // [S, N]
-    float *sort_box;        // [S, N, 4]
-    float *sort_score;      // [S, N]
-    int32_t *sort_prior;    // [S, N]
-    int32_t *sort_label;    // [S, N]
-    uint32_t *max_coord;    // [S] ordered-uint encoding of max box coordinate
-    unsigned long long *nms_mask;   // [S, N, N/64]
     // K4/K5 workspace
     float *cost;            // [S, T*D]
     void *all_mem;          // single allocation backing everything above

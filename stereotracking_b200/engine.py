@@ -73,6 +73,7 @@ class FrameBuffers:
         self.out_scale2 = torch.zeros(S, D, **f32)
         self.out_ids = torch.zeros(S, D, **i64)
         self.out_counts = torch.zeros(S, **i32)
+        self.out_src = torch.zeros(S, D, **i32)            # detection row of every track row
         self.frame_ids = torch.zeros(S, **i32)
         self.k3_workspace = torch.zeros(2 + 4 * S * D, **i32)
         self.depth_map = None
@@ -224,7 +225,7 @@ class StereoTrackEngine:
             _ptr(self._dev(scales, torch.float32)), _ptr(self._dev(depth, torch.float32)),
             _ptr(self._dev(counts, torch.int32)), cap, _ptr(self.trk_boxes), _ptr(self.out_scores),
             _ptr(self.out_labels), _ptr(self.out_scales), _ptr(self.trk_depth), _ptr(self.out_ids),
-            _ptr(self.out_counts), self._stream()), 'st_track_step')
+            _ptr(self.out_counts), _ptr(self.out_src), self._stream()), 'st_track_step')
         return dict(bboxes=self.trk_boxes, scores=self.out_scores, labels=self.out_labels,
                     scales=self.out_scales, depth=self.trk_depth, instances_id=self.out_ids,
                     counts=self.out_counts)
@@ -281,7 +282,7 @@ class StereoTrackEngine:
         io.depth_map = bufs.depth_map.data_ptr()
         for name in ('det_boxes', 'det_scores', 'det_labels', 'det_prior', 'det_keep', 'det_counts',
                      'det_depth', 'det_scales', 'det_inflated', 'trk_boxes', 'trk_depth', 'out_scale2',
-                     'k3_workspace',
+                     'out_src', 'k3_workspace',
                      'out_boxes', 'out_scores', 'out_labels', 'out_scales', 'out_depth', 'out_ids',
                      'out_counts'):
             setattr(io, name, getattr(bufs, name).data_ptr())
