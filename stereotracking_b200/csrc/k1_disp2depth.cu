@@ -159,6 +159,128 @@ k1_disp2depth_flat(const uint16_t *__restrict__ raw, int S, int H, int Hp, int W
     }
 }
 
+// ---- resize / column-padded path: source rows staged by the bulk-copy engine ---------------
+// Nearest resize (cv2 INTER_NEAREST index rule, float64: src = min(floor(dst * (1 / (dst_n /
+// src_n))), src_n - 1)) and images whose width is not a multiple of 32.  An output row
+// reads ONE source row, at gather positions that are not coalescible; so a CTA walks
+// output rows, and one elected thread has the TMA unit copy the source row into shared
+// memory (cp.async.bulk, global -> shared, completion on an mbarrier) for the row after
+// the one being converted (two-stage ring).  All threads then gather from shared memory
+// through a per-CTA column table and write coalesced float4 / uchar4 outputs.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "K1_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra K1_DONE;\n"
+        "bra K1_WAIT;\n"
+        "K1_DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+constexpr int kRowThreads = 256;
+
+__host__ __device__ inline size_t resize_smem_bytes(int W, int Wp) {
+    const size_t row = ((size_t)W * 2 + 15) & ~(size_t)15;
+    return 2 * row + (((size_t)Wp * 2 + 15) & ~(size_t)15) + 16;
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+k1_disp2depth_rows_tma(const uint16_t *__restrict__ raw, int S, int H, int W, int Hr, int Wr, int Hp, int Wp,
+                       float *__restrict__ depth, float *__restrict__ disp3, uint8_t *__restrict__ mask, float bf) {
+    extern __shared__ __align__(16) unsigned char k1_smem[];
+    const size_t row_bytes = ((size_t)W * 2 + 15) & ~(size_t)15;
+    uint16_t *rowbuf[2] = {reinterpret_cast<uint16_t *>(k1_smem), reinterpret_cast<uint16_t *>(k1_smem + row_bytes)};
+    uint16_t *sx = reinterpret_cast<uint16_t *>(k1_smem + 2 * row_bytes);          // [Wp] source column, 0xffff = pad
+    uint64_t *bars = reinterpret_cast<uint64_t *>(k1_smem + 2 * row_bytes + (((size_t)Wp * 2 + 15) & ~(size_t)15));
+    const int tid = threadIdx.x;
+    const double inv_x = 1.0 / ((double)Wr / (double)W);
+    const double inv_y = 1.0 / ((double)Hr / (double)H);
+    const float pad_depth = __fmul_rn(rcp_rn_fma(1e-6f), bf);
+    for (int x = tid; x < Wp; x += kRowThreads)
+        sx[x] = x < Wr ? (uint16_t)min((int)floor(__dmul_rn((double)x, inv_x)), W - 1) : (uint16_t)0xffffu;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long total_rows = (long long)S * Hp;
+    const size_t plane = (size_t)Hp * Wp;
+    // source row of output row r (or -1 for a pad row)
+    auto src_row = [&](long long r) -> long long {
+        const int y = (int)(r % Hp);
+        if (y >= Hr) return -1;
+        const int sy = min((int)floor(__dmul_rn((double)y, inv_y)), H - 1);
+        return (r / Hp) * H + sy;
+    };
+    unsigned phase[2] = {0u, 0u};
+    long long r = blockIdx.x;
+    if (r < total_rows && tid == 0) {
+        const long long sr = src_row(r);
+        if (sr >= 0) {
+            mbar_expect_tx(&bars[0], (unsigned)row_bytes);
+            bulk_g2s(rowbuf[0], raw + sr * W, (unsigned)row_bytes, &bars[0]);
+        }
+    }
+    int stage = 0;
+    for (; r < total_rows; r += gridDim.x, stage ^= 1) {
+        // prefetch the next row of this CTA into the other stage (its previous reader finished
+        // before the __syncthreads at the end of the previous iteration)
+        const long long rn = r + gridDim.x;
+        if (rn < total_rows && tid == 0) {
+            const long long srn = src_row(rn);
+            if (srn >= 0) {
+                mbar_expect_tx(&bars[stage ^ 1], (unsigned)row_bytes);
+                bulk_g2s(rowbuf[stage ^ 1], raw + srn * W, (unsigned)row_bytes, &bars[stage ^ 1]);
+            }
+        }
+        const bool has_src = src_row(r) >= 0;
+        if (has_src) {
+            mbar_wait(&bars[stage], phase[stage]);
+            phase[stage] ^= 1u;
+        }
+        const uint16_t *row = rowbuf[stage];
+        const int s = (int)(r / Hp);
+        const size_t out0 = (size_t)r * Wp;                     // == (s * Hp + y) * Wp
+        const size_t pix0 = out0 - (size_t)s * plane;            // offset inside the image plane
+        for (int x = 4 * tid; x < Wp; x += 4 * kRowThreads) {
+            float dz[4], dp[4];
+            uint32_t mk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t c = has_src ? sx[x + k] : 0xffffu;
+                if (c != 0xffffu) convert(row[c], bf, dp[k], dz[k], mk[k]);
+                else { dz[k] = pad_depth; dp[k] = 0.0f; mk[k] = 0u; }
+            }
+            st_stream_f4(reinterpret_cast<float4 *>(depth + out0 + x), make_float4(dz[0], dz[1], dz[2], dz[3]));
+            if (disp3) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    *reinterpret_cast<float4 *>(disp3 + ((size_t)s * 3 + c) * plane + pix0 + x) =
+                        make_float4(dp[0], dp[1], dp[2], dp[3]);
+            }
+            if (mask)
+                *reinterpret_cast<uint32_t *>(mask + out0 + x) = mk[0] | (mk[1] << 8) | (mk[2] << 16) | (mk[3] << 24);
+        }
+        __syncthreads();            // every thread is done with rowbuf[stage] before it is refilled
+    }
+}
+
 // General path: nearest resize (cv2 INTER_NEAREST index rule: src =
 // min(floor(dst * (1/(dst_n/src_n))), src_n-1), float64) and arbitrary sizes.
 __global__ void __launch_bounds__(256)
@@ -242,6 +364,24 @@ extern "C" int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, i
         else if (disp3) launch(k1_disp2depth_flat<true, false>);
         else if (mask) launch(k1_disp2depth_flat<false, true>);
         else launch(k1_disp2depth_flat<false, false>);
+    } else if ((W % 8 == 0) && (Wp % 4 == 0) && W <= 32768 && Wp <= 65534 && ((uintptr_t)raw % 16 == 0) &&
+               ((uintptr_t)depth % 16 == 0) && (!disp3 || (uintptr_t)disp3 % 16 == 0) &&
+               (!mask || (uintptr_t)mask % 4 == 0)) {
+        // resize and / or column padding: TMA-staged source rows
+        const size_t smem = resize_smem_bytes(W, Wp);
+        static size_t configured = 0;
+        if (smem > configured) {
+            ST_CUDA_OK(cudaFuncSetAttribute(k1_disp2depth_rows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_disp2depth_rows_tma, kRowThreads, smem) != cudaSuccess ||
+            per_sm < 1)
+            per_sm = 1;
+        long long grid = (long long)sm_count() * per_sm;
+        const long long rows = (long long)S * Hp;
+        if (grid > rows) grid = rows;
+        k1_disp2depth_rows_tma<<<(int)grid, kRowThreads, smem, st>>>(raw, S, H, W, Hr, Wr, Hp, Wp, depth, disp3, mask, bf);
     } else {
         const long long total = (long long)S * Hp * Wp;
         long long grid = (total + 255) / 256;

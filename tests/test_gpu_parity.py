@@ -38,7 +38,11 @@ def cuda(a, dtype=None):
 # ---------------------------------------------------------------- K1 ------------
 @pytest.mark.parametrize('shape,scale', [((2, 96, 128), None), ((1, 720, 1280), None),
                                          ((2, 61, 83), None), ((2, 120, 200), (90, 150)),
-                                         ((1, 97, 131), (160, 240))])
+                                         ((1, 97, 131), (160, 240)),
+                                         # W % 8 == 0: rows staged by the TMA bulk-copy kernel (column
+                                         # padding only / downscale / upscale / several CTAs per image)
+                                         ((2, 100, 136), None), ((1, 180, 320), (135, 240)),
+                                         ((3, 90, 160), (180, 320)), ((2, 360, 640), (200, 300))])
 def test_k1_disp2depth_bit_exact(mods, shape, scale):
     rng = np.random.default_rng(1)
     raw = rng.integers(0, 4000, shape).astype(np.uint16)
