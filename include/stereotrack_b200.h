@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ST_ABI_VERSION 2
+#define ST_ABI_VERSION 3
 
 enum {
     ST_OK = 0,
@@ -169,6 +169,10 @@ int st_track_step(st_handle *h, int S, const int32_t *frame_ids, const float *de
                   float *out_boxes, float *out_scores, int64_t *out_labels, float *out_scales,
                   float *out_depth, int64_t *out_ids, int32_t *out_counts,
                   int32_t *out_src /* [S,det_cap] input row of every output row, may be NULL */,
+                  const float *warp /* [S,6] row-major 2x3 camera-motion affine per sequence applied to
+                                       the confirmed tracks after predict (cmc=dict(method='glme_affine'),
+                                       ocsort_tracker_disparity.py:428-445, trackers/gmc.py:20-45); a NaN
+                                       first entry = no warp for that sequence; NULL = cmc disabled */,
                   void *stream);
 
 /* All buffers of one lockstep frame (device pointers; host arrays where the name
@@ -196,6 +200,7 @@ typedef struct st_frame_io {
     /* outputs = pred_track_instances fields */
     float *out_boxes; float *out_scores; int64_t *out_labels; float *out_scales; float *out_depth;
     int64_t *out_ids; int32_t *out_counts;
+    const float *warp;                 /* [S,6] camera-motion affine of this frame or NULL (st_track_step) */
 } st_frame_io;
 
 /* The whole per-frame path for S sequences in one call (K1 -> K2 -> K3 -> K4/K5

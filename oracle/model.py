@@ -36,10 +36,11 @@ class StereoTrackOracle:
                                 strides=self.strides, score_thr=self.score_thr,
                                 iou_thr=self.nms_iou)
 
-    def step_from_dets(self, frame_id, depth, det_bboxes, det_scores, det_labels):
-        """ocsort_disparity.py:82-109 given the detector output."""
+    def step_from_dets(self, frame_id, depth, det_bboxes, det_scores, det_labels, warp=None):
+        """ocsort_disparity.py:82-109 given the detector output (``warp``: the frame's
+        camera-motion affine when cmc is configured, else None)."""
         infl, scales, d = boxdepth.bbox_postp_depth(depth, det_bboxes)
-        trk = self.tracker.track(frame_id, infl, det_scores, det_labels, scales, d)
+        trk = self.tracker.track(frame_id, infl, det_scores, det_labels, scales, d, warp=warp)
         with np.errstate(divide='ignore', invalid='ignore'):
             inv = (np.float32(1) / trk['scales']).astype(np.float32)
         out_boxes = boxdepth.scale_bbox(trk['bboxes'], inv)

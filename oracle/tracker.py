@@ -232,8 +232,34 @@ class OCSortDisparityOracle:
             t.mean, t.cov = kalman.update(t.mean, t.cov, xyxy_to_cxcyah(virt))
 
     # ---- one frame (:345-618) ------------------------------------------------
-    def track(self, frame_id, bboxes, scores, labels, scales, depth, debug=None):
-        """Inputs are the pred_det_instances fields (boxes already inflated).
+    def apply_gmc(self, ids, warp):
+        """apply_gmc_to_tracks_cxcyah (mmtrack/models/trackers/gmc.py:20-45): the 2x3
+        background affine moves the persistent Kalman state of the given tracks:
+        centre and its velocity through R (+ t), h and vh by s = sqrt(max(det R,
+        1e-12)), covariance through the same linear map A P A^T."""
+        warp = np.asarray(warp)
+        R = warp[:2, :2].astype(np.float64)
+        t = warp[:2, 2].astype(np.float64)
+        s = float(np.sqrt(max(np.linalg.det(R), 1e-12)))
+        A = np.eye(8, dtype=float)
+        A[0:2, 0:2] = R
+        A[4:6, 4:6] = R
+        A[3, 3] = s
+        A[7, 7] = s
+        for i in ids:
+            tr = self.tracks[i]
+            mean = tr.mean.copy()
+            mean[0:2] = R.dot(mean[0:2]) + t
+            mean[3] *= s
+            mean[4:6] = R.dot(mean[4:6])
+            mean[7] *= s
+            tr.mean = mean
+            tr.cov = A.dot(tr.cov).dot(A.T)
+
+    def track(self, frame_id, bboxes, scores, labels, scales, depth, debug=None, warp=None):
+        """Inputs are the pred_det_instances fields (boxes already inflated); ``warp`` is
+        the 2x3 camera-motion affine of this frame or None (ocsort_tracker_disparity.py
+        :428-445, cmc=dict(method='glme_affine')).
         Returns dict(bboxes, labels, scores, scales, depth, instances_id)."""
         bboxes = np.asarray(bboxes, F32).reshape(-1, 4)
         scores = np.asarray(scores, F32).reshape(-1)
@@ -265,6 +291,8 @@ class OCSortDisparityOracle:
                 if t.tracked:
                     t.saved = (t.mean, t.cov)
                 t.mean, t.cov = kalman.predict(t.mean, t.cov)
+            if warp is not None:                      # :443-445
+                self.apply_gmc(confirmed, warp)
 
             # stage 1: confirmed tracks (:448-474)
             c1 = self.ocm_cost(confirmed, bboxes[det], scores[det])

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libstereotrack_b200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ST_STATUS = dict(CAND_OVERFLOW=1, DET_OVERFLOW=2, TRACK_OVERFLOW=4, LAP_GUARD=8)
 
@@ -36,7 +36,7 @@ class StFrameIO(C.Structure):
             'depth_map', 'disp3', 'mask', 'det_boxes', 'det_scores', 'det_labels', 'det_prior',
             'det_keep', 'det_counts', 'det_depth', 'det_scales', 'det_inflated', 'trk_boxes',
             'trk_depth', 'out_scale2', 'out_src', 'k3_workspace', 'out_boxes', 'out_scores', 'out_labels', 'out_scales',
-            'out_depth', 'out_ids', 'out_counts')])
+            'out_depth', 'out_ids', 'out_counts', 'warp')])
 
 
 class StereoTrackError(RuntimeError):
@@ -64,7 +64,7 @@ _SIGNATURES = {
     'st_box_depth': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
     'st_scale_boxes': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     'st_box_depth_reuse': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
-    'st_track_step': (_I, [_P, _I] + [_P] * 7 + [_I] + [_P] * 9),
+    'st_track_step': (_I, [_P, _I] + [_P] * 7 + [_I] + [_P] * 10),
     'st_frame_step': (_I, [_P, _I, C.POINTER(StFrameIO), _P]),
     'st_pipeline_create': (_I, [_P, _I, C.POINTER(_P)]),
     'st_pipeline_destroy': (_I, [_P]),

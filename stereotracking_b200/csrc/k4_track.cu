@@ -274,7 +274,8 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
               float *cost_ws /* written and re-read in this kernel: no __restrict__ */, float *__restrict__ out_boxes, float *__restrict__ out_scores,
               int64_t *__restrict__ out_labels, float *__restrict__ out_scales,
               float *__restrict__ out_depth, int64_t *__restrict__ out_ids,
-              int32_t *__restrict__ out_counts, int32_t *__restrict__ out_src /* may be null */) {
+              int32_t *__restrict__ out_counts, int32_t *__restrict__ out_src /* may be null */,
+              const float *__restrict__ cmc_warp /* [S,6] camera-motion affine, may be null */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int sh_cnt[4];
     __shared__ int sh_nlive;
@@ -357,6 +358,48 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             if (!(g_skip & 32)) stkf::predict(st.mean + g * 8, st.cov + g * 64, kfws);
         }
         __syncthreads();
+        // ---- camera-motion compensation of the confirmed tracks (:443-445, gmc.py:20-45):
+        // centre and its velocity through R (+ t), h and vh by s = sqrt(max(det R, 1e-12)),
+        // covariance A P A^T with A = diag-blocks (R, 1, s, R, 1, s).  A NaN first entry
+        // means "no warp this frame" (the reference's estimator returned None).
+        if (cmc_warp != nullptr && cmc_warp[s * 6] == cmc_warp[s * 6]) {
+            const float *wm = cmc_warp + s * 6;
+            const double r00 = (double)wm[0], r01 = (double)wm[1], t0 = (double)wm[2];
+            const double r10 = (double)wm[3], r11 = (double)wm[4], t1 = (double)wm[5];
+            const double sc = sqrt(fmax(__dsub_rn(__dmul_rn(r00, r11), __dmul_rn(r01, r10)), 1e-12));
+            for (int r = warp; r < R; r += kWarps) {
+                const long long g = sbase + sm.rows[r];
+                double *P = kfws, *X = kfws + 64, *m = kfws + 128;
+                for (int e = lane; e < 64; e += 32) P[e] = st.cov[g * 64 + e];
+                if (lane < 8) m[lane] = st.mean[g * 8 + lane];
+                __syncwarp();
+                // row map: 0,1 and 4,5 mix through R; 3 and 7 scale; 2 and 6 stay
+                auto mix = [&](const double *src, int i, int j, bool rows) -> double {
+                    const int k = rows ? i : j;              // index being transformed
+                    auto at = [&](int q) { return rows ? src[q * 8 + j] : src[i * 8 + q]; };
+                    const int base = k & 4;                  // 0 or 4
+                    switch (k & 3) {
+                        case 0: return __dadd_rn(__dmul_rn(r00, at(base)), __dmul_rn(r01, at(base + 1)));
+                        case 1: return __dadd_rn(__dmul_rn(r10, at(base)), __dmul_rn(r11, at(base + 1)));
+                        case 3: return __dmul_rn(sc, at(k));
+                        default: return at(k);
+                    }
+                };
+                for (int e = lane; e < 64; e += 32) X[e] = mix(P, e >> 3, e & 7, true);      // X = A P
+                __syncwarp();
+                for (int e = lane; e < 64; e += 32) st.cov[g * 64 + e] = mix(X, e >> 3, e & 7, false);   // X A^T
+                if (lane == 0) {
+                    st.mean[g * 8 + 0] = __dadd_rn(__dadd_rn(__dmul_rn(r00, m[0]), __dmul_rn(r01, m[1])), t0);
+                    st.mean[g * 8 + 1] = __dadd_rn(__dadd_rn(__dmul_rn(r10, m[0]), __dmul_rn(r11, m[1])), t1);
+                    st.mean[g * 8 + 3] = __dmul_rn(m[3], sc);
+                    st.mean[g * 8 + 4] = __dadd_rn(__dmul_rn(r00, m[4]), __dmul_rn(r01, m[5]));
+                    st.mean[g * 8 + 5] = __dadd_rn(__dmul_rn(r10, m[4]), __dmul_rn(r11, m[5]));
+                    st.mean[g * 8 + 7] = __dmul_rn(m[7], sc);
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+        }
         ST_PHASE(8);
         // ---- stage 1: confirmed tracks vs filtered dets (:448-474)
         associate(st, pr, sm, sbase, R, C, true, dv, cost, 1, &st.status[s]);
@@ -770,7 +813,7 @@ extern "C" int st_track_step(st_handle *h, int S, const int32_t *frame_ids, cons
                              const float *det_depth, const int32_t *det_counts, int det_cap,
                              float *out_boxes, float *out_scores, int64_t *out_labels, float *out_scales,
                              float *out_depth, int64_t *out_ids, int32_t *out_counts, int32_t *out_src,
-                             void *stream) {
+                             const float *warp, void *stream) {
     if (!h || S < 0 || S > h->cfg.max_sequences || !frame_ids || !det_boxes || !det_scores || !det_labels ||
         !det_scales || !det_depth || !det_counts || det_cap < 1 || !out_boxes || !out_scores || !out_labels ||
         !out_scales || !out_depth || !out_ids || !out_counts)
@@ -787,7 +830,7 @@ extern "C" int st_track_step(st_handle *h, int S, const int32_t *frame_ids, cons
     const size_t smem = smem_bytes(pr.T, pr.D);
     k4_track_step<<<S, kThreads, smem, (cudaStream_t)stream>>>(
         h->st, pr, frame_ids, det_boxes, det_scores, det_labels, det_scales, det_depth, det_counts, det_cap,
-        h->cost, out_boxes, out_scores, out_labels, out_scales, out_depth, out_ids, out_counts, out_src);
+        h->cost, out_boxes, out_scores, out_labels, out_scales, out_depth, out_ids, out_counts, out_src, warp);
     return st_last_launch();
 }
 

@@ -28,7 +28,7 @@ extern "C" int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *s
     if (rc != ST_OK) return rc;
     rc = st_track_step(h, S, io->frame_ids, io->det_inflated, io->det_scores, io->det_labels, io->det_scales,
                        io->det_depth, io->det_counts, cap, io->trk_boxes, io->out_scores, io->out_labels,
-                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, io->out_src, stream);
+                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, io->out_src, io->warp, stream);
     if (rc != ST_OK) return rc;
     rc = st_scale_boxes(io->trk_boxes, io->out_scales, io->out_counts, S, cap, 1, io->out_boxes, stream);
     if (rc != ST_OK) return rc;
@@ -151,7 +151,7 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     ST_CUDA_OK(cudaStreamWaitEvent(p->st[3], ev(2), 0));
     rc = st_track_step(h, S, io->frame_ids, io->det_inflated, io->det_scores, io->det_labels, io->det_scales,
                        io->det_depth, io->det_counts, cap, io->trk_boxes, io->out_scores, io->out_labels,
-                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, io->out_src, p->st[3]);
+                       io->out_scales, io->trk_depth, io->out_ids, io->out_counts, io->out_src, io->warp, p->st[3]);
     if (rc != ST_OK) return rc;
     ST_CUDA_OK(cudaEventRecord(ev(3), p->st[3]));
     // ---- stream 4: deflate and the output depth

@@ -117,8 +117,6 @@ class StereoTrackEngine:
         sc.vel_consist_weight = t.get('vel_consist_weight', 0.2)
         sc.vel_delta_t = t.get('vel_delta_t', 3)
         sc.num_frames_retain = t.get('num_frames_retain', 10)
-        if t.get('cmc') is not None:
-            raise NotImplementedError('camera-motion compensation (cmc) is a "next" row, see DESIGN.md')
         sc.baseline, sc.focal_length = cfg.baseline, cfg.focal_length
         sc.score_thr, sc.nms_iou_thr = cfg.score_thr, cfg.nms_iou_thr
         self._sc = sc
@@ -215,8 +213,12 @@ class StereoTrackEngine:
         return out
 
     # ---- K4/K5 -------------------------------------------------------------------
-    def track_step(self, frame_ids, boxes, scores, labels, scales, depth, counts):
-        """tracker.track for S sequences; inputs padded [S,cap,...]; fills trk_*/out_* buffers."""
+    def track_step(self, frame_ids, boxes, scores, labels, scales, depth, counts, warp=None):
+        """tracker.track for S sequences; inputs padded [S,cap,...]; fills trk_*/out_* buffers.
+        ``warp``: [S,6] float32 camera-motion affines (NaN row = none) when cmc is on."""
+        if warp is not None:
+            self._dev(warp, torch.float32)
+            assert warp.shape == (scores.shape[0], 6)
         S, cap = scores.shape
         assert cap == self.cfg.max_dets, 'detection buffers must be padded to max_dets rows'
         _lib.check(self.lib.st_track_step(
@@ -225,19 +227,19 @@ class StereoTrackEngine:
             _ptr(self._dev(scales, torch.float32)), _ptr(self._dev(depth, torch.float32)),
             _ptr(self._dev(counts, torch.int32)), cap, _ptr(self.trk_boxes), _ptr(self.out_scores),
             _ptr(self.out_labels), _ptr(self.out_scales), _ptr(self.trk_depth), _ptr(self.out_ids),
-            _ptr(self.out_counts), _ptr(self.out_src), self._stream()), 'st_track_step')
+            _ptr(self.out_counts), _ptr(self.out_src), _ptr(warp), self._stream()), 'st_track_step')
         return dict(bboxes=self.trk_boxes, scores=self.out_scores, labels=self.out_labels,
                     scales=self.out_scales, depth=self.trk_depth, instances_id=self.out_ids,
                     counts=self.out_counts)
 
     # ---- whole frame ---------------------------------------------------------------
-    def step_from_dets(self, depth_map, frame_ids=None):
+    def step_from_dets(self, depth_map, frame_ids=None, warp=None):
         """ocsort_disparity.py:82-109 given det_* buffers (detector output) and a depth map."""
         fid = self.frame_ids if frame_ids is None else frame_ids
         self.box_depth(depth_map, self.det_boxes, self.det_counts, self.det_depth, self.det_scales,
                        self.det_inflated)
         self.track_step(fid, self.det_inflated, self.det_scores, self.det_labels, self.det_scales,
-                        self.det_depth, self.det_counts)
+                        self.det_depth, self.det_counts, warp=warp)
         self.scale_boxes(self.trk_boxes, self.out_scales, self.out_counts, True, self.out_boxes)
         self.box_depth(depth_map, self.out_boxes, self.out_counts, self.out_depth, self.out_scale2, None)
 
@@ -397,12 +399,15 @@ class FramePipeline:
         except Exception:
             pass
 
-    def submit_ptrs(self, frame_ids_ptr, raw_ptr, cls_ptrs, bbox_ptrs, obj_ptrs, ready_event=None, done_event=None):
-        """Queue one frame given raw device addresses; returns the slot it uses."""
+    def submit_ptrs(self, frame_ids_ptr, raw_ptr, cls_ptrs, bbox_ptrs, obj_ptrs, ready_event=None, done_event=None,
+                    warp_ptr=0):
+        """Queue one frame given raw device addresses; returns the slot it uses.
+        ``warp_ptr``: address of the frame's [S,6] camera-motion affines, 0 = cmc off."""
         slot = self.submitted % self.depth
         io = self.ios[slot]
         io.frame_ids = frame_ids_ptr
         io.raw = raw_ptr
+        io.warp = warp_ptr
         k = io._keep
         for l in range(len(cls_ptrs)):
             k['cls'][l] = cls_ptrs[l]
@@ -414,12 +419,13 @@ class FramePipeline:
         self.submitted += 1
         return slot
 
-    def submit(self, frame_ids, raw, cls_l, bbox_l, obj_l, ready_event=None, done_event=None):
+    def submit(self, frame_ids, raw, cls_l, bbox_l, obj_l, ready_event=None, done_event=None, warp=None):
         """Queue one frame given device tensors (frame_ids [S] int32, raw [S,H,W] u16,
-        heads [S,C,h,w] f32); they must stay alive and unchanged until the frame is done."""
+        heads [S,C,h,w] f32, optional warp [S,6] f32); they must stay alive and unchanged
+        until the frame is done."""
         return self.submit_ptrs(frame_ids.data_ptr(), raw.data_ptr(), [t.data_ptr() for t in cls_l],
                                 [t.data_ptr() for t in bbox_l], [t.data_ptr() for t in obj_l],
-                                ready_event, done_event)
+                                ready_event, done_event, 0 if warp is None else warp.data_ptr())
 
     def fork(self, stream=None):
         stream = stream or torch.cuda.current_stream(self.engine.device)

@@ -24,6 +24,36 @@ from .compat import MODELS, TASK_UTILS, InstanceData
 from .engine import EngineConfig, StereoTrackEngine
 
 
+def _mesh_affine(curr_img, prev_img, metainfo, step=16, winsize=31, ransac_thr=5.0, min_inlier_ratio=0.3):
+    """Host-side camera-motion estimator with the reference's parameters
+    (trackers/utils.py:6-55 GLME_affine): both frames as 255x255 equalised grey
+    thumbnails, Farneback flow (pyr 0.5, 5 levels, 3 iterations, poly 5 / 1.2), the
+    median flow of every step x step cell scaled back to image pixels, and a RANSAC
+    4-DoF affine through the cell centres.  Returns the float32 2x3 matrix or None."""
+    import cv2
+    import numpy as np
+    h0, w0 = metainfo['img_shape'][:2]
+
+    def thumb(t):
+        a = t.detach().cpu().numpy()[0].transpose(1, 2, 0).astype(np.uint8)[:h0, :w0, :3][:, :, ::-1]
+        a = cv2.resize(np.ascontiguousarray(a), (255, 255))
+        return cv2.equalizeHist(cv2.cvtColor(a, cv2.COLOR_RGB2GRAY))
+
+    cur, prev = thumb(curr_img), thumb(prev_img)
+    fx, fy = w0 / 255, h0 / 255
+    flow = cv2.calcOpticalFlowFarneback(prev, cur, None, pyr_scale=0.5, levels=5, winsize=winsize, iterations=3,
+                                        poly_n=5, poly_sigma=1.2, flags=0) * np.array([fx, fy])
+    gh, gw = cur.shape[0] // step, cur.shape[1] // step
+    mesh = np.median(flow[:gh * step, :gw * step].reshape(gh, step, gw, step, 2), axis=(1, 3)).reshape(-1, 2)
+    ys, xs = np.mgrid[0:gh, 0:gw]
+    src = np.stack([(xs + 0.5) * step * fx, (ys + 0.5) * step * fy], -1).reshape(-1, 2).astype(np.float32)
+    dst = (src + mesh).astype(np.float32)
+    mat, inl = cv2.estimateAffinePartial2D(src, dst, method=cv2.RANSAC, ransacReprojThreshold=ransac_thr)
+    if mat is None or inl is None or float(inl.sum()) / len(src) < min_inlier_ratio:
+        return None
+    return mat.astype(np.float32)
+
+
 @TASK_UTILS.register_module(force=True)      # replaces the reference class of the same name
 class KalmanFilter:
     """Constant-velocity Kalman filter on (cx, cy, a, h) (kalman_filter.py:12-58).
@@ -81,8 +111,8 @@ class OCSORTTracker_Disparity:
         method = cmc.get('method') if cmc is not None else None                # :63-76
         if method not in (None, 'glme_affine'):
             raise ValueError(f"Unknown cmc method '{method}', expected 'glme_affine' or None.")
-        if method is not None:
-            raise NotImplementedError("cmc=dict(method='glme_affine') is a 'next' row (DESIGN.md)")
+        self.cmc_mode = None if method is None else 'mesh_affine'
+        self.prev_cmc_img = None
         self.obj_score_thr, self.init_track_thr = obj_score_thr, init_track_thr
         self.weight_iou_with_det_scores, self.match_iou_thr = weight_iou_with_det_scores, match_iou_thr
         self.num_tentatives, self.vel_consist_weight, self.vel_delta_t = num_tentatives, vel_consist_weight, vel_delta_t
@@ -98,7 +128,21 @@ class OCSORTTracker_Disparity:
     # ---- BaseTracker surface (base_tracker.py:34-52) ---------------------------
     @property
     def with_cmc(self):
-        return False
+        return self.cmc_mode is not None
+
+    def reset_cmc(self):
+        self.prev_cmc_img = None
+
+    def estimate_camera_motion(self, img, metainfo):
+        """The frame's 2x3 background affine or None (:87-97).  The estimator itself
+        (dense Farneback flow -> per-cell median -> RANSAC partial affine,
+        trackers/utils.py:6-55) is host-side OpenCV on a 255x255 thumbnail and stays on
+        the host; only its application to the Kalman states runs in the tracker kernel."""
+        warp = None
+        if self.cmc_mode == 'mesh_affine' and self.prev_cmc_img is not None:
+            warp = _mesh_affine(img, self.prev_cmc_img, metainfo, **(self.cmc_cfg.get('glme', None) or {}))
+        self.prev_cmc_img = img
+        return warp
 
     def reset(self):
         self._engine.reset()
@@ -144,8 +188,17 @@ class OCSORTTracker_Disparity:
         eng.det_depth[0, :n] = det.depth.to(dev, torch.float32)
         eng.det_counts.fill_(n)
         eng.frame_ids.fill_(int(frame_id))
+        warp = None
+        if frame_id == 0:
+            self.reset_cmc()                                                   # :385-387
+        if self.with_cmc:
+            # the reference estimates only in the association branch (:391, :428-429)
+            w = self.estimate_camera_motion(img, data_sample.metainfo) if (n > 0 and not self.empty) else None
+            warp = torch.full((1, 6), float('nan'), dtype=torch.float32, device=dev)
+            if w is not None:
+                warp[0] = torch.as_tensor(w, dtype=torch.float32).reshape(6).to(dev)
         out = eng.track_step(eng.frame_ids, eng.det_inflated, eng.det_scores, eng.det_labels, eng.det_scales,
-                             eng.det_depth, eng.det_counts)
+                             eng.det_depth, eng.det_counts, warp=warp)
         m = int(out['counts'][0])
         status = int(eng.status()[0])
         if status:
@@ -159,6 +212,49 @@ class OCSORTTracker_Disparity:
         res.depth = out['depth'][0, :m].clone().to(tgt)
         res.instances_id = out['instances_id'][0, :m].clone().to(tgt)
         return res
+
+
+@MODELS.register_module(force=True)
+class OCSORTTracker(OCSORTTracker_Disparity):
+    """RGB-only OC-SORT tracker (mmtrack/models/trackers/ocsort_tracker.py:21): the same
+    tracker without the per-detection ``scales`` / ``depth`` fields - its diff against
+    the disparity tracker is only those two fields - so it runs on the same kernels
+    with scales = 1 and depth = 0 and returns bboxes / labels / scores / instances_id."""
+
+    def track(self, model, img, feats, data_sample, data_preprocessor=None, rescale=False, **kwargs):
+        det = data_sample.pred_det_instances
+        n = int(det.bboxes.shape[0])
+        det.scales = torch.ones(n, dtype=torch.float32, device=det.bboxes.device)
+        det.depth = torch.zeros(n, dtype=torch.float32, device=det.bboxes.device)
+        full = super().track(model, img, feats, data_sample, data_preprocessor, rescale, **kwargs)
+        res = InstanceData()
+        res.bboxes, res.labels, res.scores, res.instances_id = full.bboxes, full.labels, full.scores, full.instances_id
+        return res
+
+
+@MODELS.register_module(force=True)
+class OCSORT:
+    """RGB-only model shell (mmtrack/models/mot/ocsort.py:13, predict :71-114): detector ->
+    tracker, no depth stage."""
+
+    def __init__(self, detector=None, tracker=None, motion=None, data_preprocessor=None, init_cfg=None):
+        self.detector = MODELS.build(detector) if isinstance(detector, dict) else detector
+        self.motion = TASK_UTILS.build(motion) if isinstance(motion, dict) else motion
+        self.tracker = MODELS.build(tracker) if isinstance(tracker, dict) else tracker
+
+    def predict(self, inputs, data_samples, **kwargs):
+        img = inputs['img']
+        assert img.dim() == 5, 'The img must be 5D Tensor (N, T, C, H, W).'
+        assert img.size(0) == 1, 'OCSort inference only support 1 batch size per gpu for now.'
+        img = img[0]
+        assert len(data_samples) == 1, 'OCSort inference only support 1 batch size per gpu for now.'
+        sample = data_samples[0]
+        det_results = self.detector.predict(img, data_samples)
+        assert len(det_results) == 1, 'Batch inference is not supported.'
+        sample.pred_det_instances = det_results[0].pred_instances.clone()
+        sample.pred_track_instances = self.tracker.track(model=self, img=img, feats=None, data_sample=sample,
+                                                         **kwargs)
+        return [sample]
 
 
 @MODELS.register_module(force=True)

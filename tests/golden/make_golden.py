@@ -132,8 +132,40 @@ def synth_dets(gen, F, rng, jitter=0.6, miss=0.05, clutter=3, blackout=()):
     return out
 
 
-def run_reference_sequence(ns, raws, dets):
-    model = ref_shims.build_model(ns, TRACKER_CFG)
+def ego_warps(gen, F):
+    """Frame-to-frame background affine of a heavy_ego scene: the generator maps a
+    static scene point u0 to u_t = s_t R_t (u0 - c) + c + T_t, so u_t = A u_{t-1} + b with
+    A = s_t R_t (s_{t-1} R_{t-1})^-1 and b = c + T_t - A (c + T_{t-1}).  Every fifth
+    frame has no warp (the reference's estimator returns None when RANSAC fails)."""
+    import math
+    cfg = gen.cfg
+    c = np.array([cfg.width / 2.0, cfg.height / 2.0])
+    fr = np.arange(F, dtype=np.float64)
+    sc = 1 + 0.02 * np.sin(fr / 7)
+    ang = math.radians(0.5) * np.sin(fr / 11)
+    M = [sc[t] * np.array([[math.cos(ang[t]), -math.sin(ang[t])], [math.sin(ang[t]), math.cos(ang[t])]]) for t in range(F)]
+    T = gen.ego_t[0].numpy()
+    warps = [None]
+    for t in range(1, F):
+        if t % 5 == 4:
+            warps.append(None)
+            continue
+        A = M[t] @ np.linalg.inv(M[t - 1])
+        b = c + T[t] - A @ (c + T[t - 1])
+        warps.append(np.concatenate([A, b[:, None]], axis=1).astype(np.float32))
+    return warps
+
+
+def run_reference_sequence(ns, raws, dets, warps=None):
+    cfg = dict(TRACKER_CFG)
+    if warps is not None:
+        cfg['cmc'] = dict(method='glme_affine')
+    model = ref_shims.build_model(ns, cfg)
+    if warps is not None:
+        # the estimator (Farneback flow + RANSAC on the images, trackers/utils.py:6-55) is
+        # host-side OpenCV and out of scope; the track() code path and
+        # apply_gmc_to_tracks_cxcyah (gmc.py:20-45) run unmodified on scripted warps
+        model.tracker.estimate_camera_motion = lambda img, metainfo: warps[metainfo['frame_id']]
     frames = []
     for f, (raw, (b, s)) in enumerate(zip(raws, dets)):
         pre = odisp.preprocess(raw)
@@ -162,8 +194,14 @@ def run_reference_sequence(ns, raws, dets):
     return frames
 
 
-def save_sequence(name, raws, dets, frames):
+def save_sequence(name, raws, dets, frames, warps=None):
     pack = {}
+    if warps is not None:
+        w = np.full((len(warps), 6), np.nan, np.float32)
+        for i, m in enumerate(warps):
+            if m is not None:
+                w[i] = np.asarray(m, np.float32).reshape(6)
+        pack['warp'] = w
     pack['raw'] = np.stack(raws)
     pack['det_boxes'], pack['det_count'] = ragged([d[0] for d in dets], 4, np.float32)
     pack['det_scores'], _ = ragged([d[1] for d in dets], 0, np.float32)
@@ -194,6 +232,9 @@ def make_sequences(ns):
                           blackout=(20, 21, 33)),
         'stress': dict(cfg=SceneConfig(192, 256, 8, 14, invalid_prob=0.30, n_clutter=0, heavy_ego=True),
                        F=40, seed=5, miss=0.15, clutter=8, blackout=(0, 9)),
+        # camera-motion compensation on (cmc=dict(method='glme_affine')), scripted warps
+        'cmc': dict(cfg=SceneConfig(192, 256, 6, 10, n_clutter=0, heavy_ego=True),
+                    F=40, seed=6, miss=0.20, clutter=3, blackout=(17,), cmc=True),
     }
     for name, sc in scen.items():
         gen = SyntheticStereo(sc['cfg'], 1, sc['F'], seed=sc['seed'])
@@ -202,8 +243,9 @@ def make_sequences(ns):
         rng = np.random.default_rng(sc['seed'] + 100)
         dets = synth_dets(gen, sc['F'], rng, miss=sc['miss'], clutter=sc['clutter'],
                           blackout=sc['blackout'])
-        frames = run_reference_sequence(ns, raws, dets)
-        save_sequence(name, raws, dets, frames)
+        warps = ego_warps(gen, sc['F']) if sc.get('cmc') else None
+        frames = run_reference_sequence(ns, raws, dets, warps)
+        save_sequence(name, raws, dets, frames, warps)
 
 
 if __name__ == '__main__':

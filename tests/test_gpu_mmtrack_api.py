@@ -40,14 +40,21 @@ def api():
     return dict(torch=torch, compat=compat, api=mmtrack_api, odisp=odisp)
 
 
-@pytest.mark.parametrize('name', ['basic', 'occlusion'])
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'cmc'])
 def test_model_predict_replays_reference_fixture(api, name):
     torch, compat = api['torch'], api['compat']
     g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
     det = _Det(api)
+    extra = dict(cmc=dict(method='glme_affine')) if name == 'cmc' else {}
     model = compat.MODELS.build(dict(type='OCSORT_Disparity', detector=det, motion=dict(type='KalmanFilter'),
-                                     tracker=dict(TRACKER_CFG, max_dets=64, max_tracks=128)))
+                                     tracker=dict(TRACKER_CFG, max_dets=64, max_tracks=128, **extra)))
     assert type(model.tracker).__name__ == 'OCSORTTracker_Disparity' and model.tracker.empty
+    if name == 'cmc':
+        # as in the fixture: the host-side estimator is replaced by the scripted warps, the
+        # tracker applies them (with_cmc path of track())
+        assert model.tracker.with_cmc
+        model.tracker.estimate_camera_motion = lambda img, meta: (
+            None if np.isnan(g['warp'][meta['frame_id'], 0]) else g['warp'][meta['frame_id']].reshape(2, 3))
     for f in range(len(g['raw'])):
         n = int(g['det_count'][f])
         pre = api['odisp'].preprocess(g['raw'][f])
@@ -102,9 +109,37 @@ def test_constructor_errors_follow_the_reference(api):
     T = api['api'].OCSORTTracker_Disparity
     with pytest.raises(ValueError):
         T(cmc=dict(method='ecc'))                                  # :74-75
-    with pytest.raises(NotImplementedError):
-        T(cmc=dict(method='glme_affine'))
+    assert T(cmc=dict(method='glme_affine')).with_cmc and not T().with_cmc
     with pytest.raises(AssertionError):
         T(momentums=[0.1])                                         # base_tracker.py:26-27
     with pytest.raises(NotImplementedError):
         api['api'].KalmanFilter(use_nsa=True)
+
+
+def test_rgb_only_ocsort_matches_oracle_tracker(api):
+    """OCSORT / OCSORTTracker (the RGB-only pair, ocsort.py / ocsort_tracker.py): the
+    same association with scales = 1, against the oracle tracker on jittered boxes."""
+    torch, compat = api['torch'], api['compat']
+    from oracle.tracker import OCSortDisparityOracle
+    g = np.load(os.path.join(GOLDEN, 'ref_track_occlusion.npz'))
+    cfg = {k: v for k, v in TRACKER_CFG.items() if k != 'type'}
+    det = _Det(api)
+    model = compat.MODELS.build(dict(type='OCSORT', detector=det, motion=dict(type='KalmanFilter'),
+                                     tracker=dict(type='OCSORTTracker', max_dets=64, max_tracks=128, **cfg)))
+    ref = OCSortDisparityOracle(**cfg)
+    rows = 0
+    for f in range(len(g['raw'])):
+        n = int(g['det_count'][f])
+        boxes, scores = g['det_boxes'][f, :n].copy(), g['det_scores'][f, :n].copy()
+        det.next = compat.InstanceData(bboxes=torch.from_numpy(boxes).cuda(), scores=torch.from_numpy(scores).cuda(),
+                                       labels=torch.zeros(n, dtype=torch.int64).cuda())
+        sample = compat.TrackDataSample(metainfo=dict(frame_id=f))
+        out = model.predict(dict(img=torch.zeros(1, 1, 3, 32, 32).cuda()), [sample])[0].pred_track_instances
+        want = ref.track(f, boxes, scores, np.zeros(n, np.int64), np.ones(n, np.float32), np.zeros(n, np.float32))
+        assert sorted(out.keys()) == ['bboxes', 'instances_id', 'labels', 'scores']
+        np.testing.assert_array_equal(out.instances_id.cpu().numpy(), want['instances_id'], err_msg=f'frame {f}')
+        np.testing.assert_array_equal(out.bboxes.cpu().numpy(), want['bboxes'])
+        np.testing.assert_array_equal(out.scores.cpu().numpy(), want['scores'])
+        rows += len(want['instances_id'])
+    assert rows > 100
+

@@ -221,7 +221,7 @@ def test_lapjv_batch_matches_oracle(mods, R, C, ties):
 
 
 # ---------------------------------------------------------------- tracker ---------
-@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress'])
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress', 'cmc'])
 def test_tracker_matches_reference_fixture(mods, name):
     g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
     eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1, max_dets=64, max_tracks=128))
@@ -234,7 +234,8 @@ def test_tracker_matches_reference_fixture(mods, name):
         eng.det_scores[0, :n] = cuda(g['det_scores'][f, :n])
         eng.det_counts[0] = n
         eng.frame_ids[0] = f
-        eng.step_from_dets(depth)
+        # 'cmc': camera-motion compensation on, scripted 2x3 affines (NaN row = no warp)
+        eng.step_from_dets(depth, warp=cuda(g['warp'][f][None]) if 'warp' in g.files else None)
         r = eng.results()[0]
         m = int(g['out_count'][f])
         np.testing.assert_array_equal(r['instances_id'], g['out_ids'][f, :m], err_msg=f'frame {f}')

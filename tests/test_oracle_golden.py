@@ -44,7 +44,7 @@ def test_boxdepth_matches_reference():
     np.testing.assert_array_equal(cxcyah_to_xyxy(cx), g['xyxy_back'])
 
 
-@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress'])
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress', 'cmc'])
 def test_tracker_sequence_matches_reference(name):
     g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
     o = StereoTrackOracle()
@@ -52,8 +52,12 @@ def test_tracker_sequence_matches_reference(name):
     for f in range(len(g['raw'])):
         n = int(g['det_count'][f])
         pre = o.depth_map(g['raw'][f])
+        # 'cmc': the scripted camera-motion affine of the frame (NaN row = the estimator returned None)
+        warp = None
+        if 'warp' in g.files and not np.isnan(g['warp'][f, 0]):
+            warp = g['warp'][f].reshape(2, 3)
         r = o.step_from_dets(f, pre['depth'], g['det_boxes'][f, :n], g['det_scores'][f, :n],
-                             np.zeros(n, np.int64))
+                             np.zeros(n, np.int64), warp=warp)
         m = int(g['out_count'][f])
         np.testing.assert_array_equal(r['instances_id'], g['out_ids'][f, :m], err_msg=f'frame {f}')
         np.testing.assert_array_equal(r['bboxes'], g['out_bboxes'][f, :m])
