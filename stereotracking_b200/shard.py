@@ -29,21 +29,22 @@ def shard_sequences(n_sequences, world_size, rank):
 
 def tracks_to_rows(results, frame_id, first_sequence=0):
     """One lockstep frame of engine results (list of per-sequence dicts) -> float64
-    rows ``[sequence, frame, id, x1, y1, x2, y2, score, depth]``."""
+    rows ``[sequence, frame, id, x1, y1, x2, y2, score, depth, label]``."""
     rows = []
     for s, r in enumerate(results):
         n = len(r['instances_id'])
         if n == 0:
             continue
-        block = np.empty((n, 9), np.float64)
+        block = np.empty((n, 10), np.float64)
         block[:, 0] = first_sequence + s
         block[:, 1] = frame_id
         block[:, 2] = r['instances_id']
         block[:, 3:7] = r['bboxes']
         block[:, 7] = r['scores']
         block[:, 8] = r['depth']
+        block[:, 9] = r['labels']
         rows.append(block)
-    return np.concatenate(rows) if rows else np.empty((0, 9), np.float64)
+    return np.concatenate(rows) if rows else np.empty((0, 10), np.float64)
 
 
 def gather_tracks(rows, dst=0, group=None):
@@ -58,7 +59,7 @@ def gather_tracks(rows, dst=0, group=None):
         return None
     parts = [b for b in bucket if b is not None and len(b)]
     if not parts:
-        return np.empty((0, 9), np.float64)
+        return np.empty((0, 10), np.float64)
     out = np.concatenate(parts)
     return out[np.lexsort((out[:, 1], out[:, 0]))]          # stable: keeps the per-frame output order
 
@@ -75,4 +76,21 @@ def write_mot_txt(rows, sequence, path, depth_thr=None):
         for r in sel:
             f.write('%d,%d,%.3f,%.3f,%.3f,%.3f,%.3f,-1,-1,-1\n' %
                     (r[1] + 1, r[2], r[3], r[4], r[5] - r[3], r[6] - r[4], r[7]))
+    return len(sel)
+
+
+def write_results_csv(rows, sequence, path, gt_depth=None):
+    """``results.csv`` of one sequence as the reference's ``@save_prediction_results``
+    decorator appends it per frame (mmtrack/utils/collect_results.py:25-37): header
+    frame,id,label,tl_x,tl_y,br_x,br_y,depth,gt_depth,score; ``gt_depth`` falls back to
+    the predicted depth as in ocsort_disparity.py:103-104."""
+    import csv
+    sel = rows[rows[:, 0] == sequence]
+    with open(path, 'w', newline='') as f:
+        w = csv.writer(f)
+        w.writerow(['frame', 'id', 'label', 'tl_x', 'tl_y', 'br_x', 'br_y', 'depth', 'gt_depth', 'score'])
+        for k, r in enumerate(sel):
+            gd = r[8] if gt_depth is None else gt_depth[k]
+            w.writerow([int(r[1]), int(r[2]), int(r[9]), np.float32(r[3]), np.float32(r[4]), np.float32(r[5]),
+                        np.float32(r[6]), np.float32(r[8]), np.float32(gd), np.float32(r[7])])
     return len(sel)

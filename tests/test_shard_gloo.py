@@ -91,5 +91,16 @@ def test_two_ranks_equal_one_rank(tmp_path):
 
 
 def test_gather_is_identity_without_process_group():
-    rows = np.arange(18, dtype=np.float64).reshape(2, 9)
+    rows = np.arange(20, dtype=np.float64).reshape(2, 10)
     assert shard.gather_tracks(rows) is rows
+
+
+def test_results_csv_has_the_reference_columns(tmp_path):
+    rows = np.array([[3, 0, 7, 10.5, 20.25, 30, 40, 0.9, 12.5, 0],
+                     [3, 1, 7, 11.5, 21.25, 31, 41, 0.8, np.nan, 0],
+                     [4, 0, 1, 0, 0, 5, 5, 0.5, 3.0, 0]], np.float64)
+    assert shard.write_results_csv(rows, 3, tmp_path / 'results.csv') == 2
+    lines = open(tmp_path / 'results.csv').read().strip().splitlines()
+    assert lines[0] == 'frame,id,label,tl_x,tl_y,br_x,br_y,depth,gt_depth,score'   # collect_results.py:36
+    assert lines[1] == '0,7,0,10.5,20.25,30.0,40.0,12.5,12.5,0.9'
+    assert lines[2].split(',')[7] == 'nan' and len(lines) == 3
