@@ -345,17 +345,23 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         int R = sh_cnt[1];
         for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = order[sm.rows[r]];   // position -> slot
         __syncthreads();
-        for (int r = warp; r < R; r += kWarps) {
-            const long long g = sbase + sm.rows[r];
-            if (st.last_frame[g] != frame - 1) { if (lane == 0) st.mean[g * 8 + 7] = 0.0; }
-            __syncwarp();
-            if (st.tracked[g]) {
-                for (int e = lane; e < 64; e += 32) st.saved_cov[g * 64 + e] = st.cov[g * 64 + e];
-                if (lane < 8) st.saved_mean[g * 8 + lane] = st.mean[g * 8 + lane];
-                if (lane == 0) st.has_saved[g] = 1;
+        // four tracks per warp (kalman.cuh, 8-lane groups, state in registers)
+        for (int r0 = warp * 4; r0 < R; r0 += kWarps * 4) {
+            const int r = r0 + (lane >> 3), gl = lane & 7;
+            const bool active = r < R;
+            const long long g = active ? sbase + sm.rows[r] : 0;
+            stkf::Row8 row = stkf::load8(st.mean + g * 8, st.cov + g * 64, gl, active);
+            if (active) {
+                if (st.last_frame[g] != frame - 1 && gl == 7) row.m = 0.0;        // lost last frame: vh = 0
+                if (st.tracked[g]) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) st.saved_cov[g * 64 + gl * 8 + j] = row.p[j];
+                    st.saved_mean[g * 8 + gl] = row.m;
+                    if (gl == 0) st.has_saved[g] = 1;
+                }
             }
-            __syncwarp();
-            if (!(g_skip & 32)) stkf::predict(st.mean + g * 8, st.cov + g * 64, kfws);
+            if (!(g_skip & 32)) stkf::predict8(row, gl);
+            stkf::store8(row, st.mean + g * 8, st.cov + g * 64, gl, active);
         }
         __syncthreads();
         // ---- camera-motion compensation of the confirmed tracks (:443-445, gmc.py:20-45):
@@ -513,21 +519,27 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         if (threadIdx.x == 0) atomicOr(&st.status[s], ST_STATUS_TRACK_OVERFLOW);
     }
     __syncthreads();
-    for (int k = warp; k < n_out; k += kWarps) {
-        const int i = sm.out_src[k];
+    // four output rows per warp: 8-lane groups run the Kalman update / track birth of their row
+    for (int k0 = warp * 4; k0 < n_out; k0 += kWarps * 4) {
+        const int k = k0 + (lane >> 3), gl = lane & 7;
+        const bool active = k < n_out;
+        const int i = active ? sm.out_src[k] : 0;
         const float *box = dv.boxes + i * 4;
         float zc[4];
         stkf::xyxy_to_cxcyah(box, zc);
-        int slot = sm.det_slot[i];
-        long long id;
-        if (slot >= 0) {
-            // update_track (:128-146 + kalman_tracker_base.py:65-75)
-            const long long g = sbase + slot;
-            id = st.id[g];
+        int slot = active ? sm.det_slot[i] : -1;
+        long long id = 0;
+        const bool upd = active && slot >= 0;
+        {
+            // update_track (:128-146 + kalman_tracker_base.py:65-75); every lane runs the shuffles
+            const long long g = upd ? sbase + slot : 0;
             double z[4];
             for (int q = 0; q < 4; ++q) z[q] = (double)zc[q];
-            if (!(g_skip & 16)) stkf::update(st.mean + g * 8, st.cov + g * 64, z, kfws);
-            if (lane == 0) {
+            stkf::Row8 row = stkf::load8(st.mean + g * 8, st.cov + g * 64, gl, upd);
+            if (!(g_skip & 16)) stkf::update8(row, z, gl);
+            stkf::store8(row, st.mean + g * 8, st.cov + g * 64, gl, upd);
+            if (upd) id = st.id[g];
+            if (upd && gl == 0) {
                 st.hits[g] += 1;
                 st.last_frame[g] = frame;
                 if (st.tentative[g] && st.hits[g] >= pr.num_tentatives) st.tentative[g] = 0;
@@ -535,15 +547,16 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
                 push_obs(st, g, box);
                 vel_direction(k_step_obs(st, g, pr.vel_dt), box, st.velocity + g * 2);
             }
-        } else {
+        }
+        if (active && !upd) {
             const int r = k - first_new;
             id = id0 + r;
             if (r < n_create) {
                 // init_track (:105-126 + kalman_tracker_base.py:55-63)
                 slot = free_slots[n_free - 1 - r];
                 const long long g = sbase + slot;
-                stkf::initiate(st.mean + g * 8, st.cov + g * 64, zc);
-                if (lane == 0) {
+                stkf::initiate8(st.mean + g * 8, st.cov + g * 64, zc, gl);
+                if (gl == 0) {
                     st.id[g] = id;
                     st.hits[g] = 1;
                     st.last_frame[g] = frame;
@@ -559,7 +572,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
                 }
             }
         }
-        if (lane == 0) {
+        if (active && gl == 0) {
             const long long o = (long long)s * det_cap + k;
             if (slot >= 0) {
                 const long long g = sbase + slot;
@@ -660,17 +673,23 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
 }
 
 __global__ void k4_kalman_batch(int op, int n, double *mean, double *cov, const float *z) {
-    __shared__ double ws[4][stkf::kScratchDoubles];
-    const int warp = threadIdx.x >> 5;
-    const int t = blockIdx.x * 4 + warp;
-    if (t >= n) return;
-    if (op == 0) stkf::initiate(mean + (long long)t * 8, cov + (long long)t * 64, z + (long long)t * 4);
-    else if (op == 1) stkf::predict(mean + (long long)t * 8, cov + (long long)t * 64, ws[warp]);
+    // 4 warps per CTA, 4 tracks per warp (the 8-lane-group filter of kalman.cuh)
+    const int lane = threadIdx.x & 31, gl = lane & 7;
+    const int t = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+    const bool active = t < n;
+    const long long g = active ? t : 0;
+    if (op == 0) {
+        if (active) stkf::initiate8(mean + g * 8, cov + g * 64, z + g * 4, gl);
+        return;
+    }
+    stkf::Row8 row = stkf::load8(mean + g * 8, cov + g * 64, gl, active);
+    if (op == 1) stkf::predict8(row, gl);
     else {
         double zz[4];
-        for (int k = 0; k < 4; ++k) zz[k] = (double)z[(long long)t * 4 + k];
-        stkf::update(mean + (long long)t * 8, cov + (long long)t * 64, zz, ws[warp]);
+        for (int k = 0; k < 4; ++k) zz[k] = active ? (double)z[g * 4 + k] : 0.0;
+        stkf::update8(row, zz, gl);
     }
+    stkf::store8(row, mean + g * 8, cov + g * 64, gl, active);
 }
 
 template <typename Tp>
@@ -872,7 +891,7 @@ extern "C" int st_export_state(st_handle *h, int seq, int64_t *ids_host, double 
 extern "C" int st_kalman_batch(int op, int n, double *mean, double *cov, const float *z, void *stream) {
     if (op < 0 || op > 2 || n < 0 || !mean || !cov || (op != 1 && !z)) return ST_ERR_INVALID_ARG;
     if (n == 0) return ST_OK;
-    k4_kalman_batch<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(op, n, mean, cov, z);
+    k4_kalman_batch<<<(n + 15) / 16, 128, 0, (cudaStream_t)stream>>>(op, n, mean, cov, z);
     return st_last_launch();
 }
 
