@@ -19,7 +19,10 @@
 
 namespace {
 
-constexpr int kThreads = 512;
+#ifndef ST_K4_THREADS
+#define ST_K4_THREADS 512
+#endif
+constexpr int kThreads = ST_K4_THREADS;
 // cost matrices up to this many entries stay in shared memory (56 KB: two CTAs per SM fit)
 constexpr int kCostSmemFloats = 14336;
 constexpr int kWarps = kThreads / 32;

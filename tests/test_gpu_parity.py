@@ -366,3 +366,52 @@ def test_frame_pipeline_equals_sequential_steps(mods):
     done[(F - 1) % 2].synchronize()
     check(pipe2.slots[(F - 1) % 2].results(), F - 1)
     assert eng.status().max() == 0 and eng2.status().max() == 0
+
+
+def test_capacity_overflow_raises_status_bits_not_silent_truncation(mods):
+    """More detections than max_dets / more live tracks than max_tracks never truncate
+    silently: the sticky per-sequence status bits are raised (include/stereotrack_b200.h)."""
+    from stereotracking_b200 import _lib
+    S = 2
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S, max_dets=16, max_tracks=8))
+    depth = torch.full((S, 64, 64), 20.0, dtype=torch.float32, device='cuda')
+    rng = np.random.default_rng(5)
+    n = 12
+    xy = rng.uniform(0, 30, (S, n, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + 14.0], -1)                   # area 196 > 100
+    eng.det_boxes[:, :n] = cuda(boxes)
+    eng.det_scores[:, :n] = 0.9
+    eng.det_counts.fill_(n)
+    eng.det_counts[1] = 4                                          # sequence 1 stays within capacity
+    eng.frame_ids.fill_(0)
+    eng.step_from_dets(depth)
+    st = eng.status()
+    assert st[0] & _lib.ST_STATUS['TRACK_OVERFLOW'] and st[1] == 0
+    assert int(eng.out_counts[1]) == 4 and len(eng.export_state(1)['ids']) == 4
+    assert len(eng.export_state(0)['ids']) == 8                    # capped at max_tracks, flagged
+    # the mmtrack facade turns the bit into an exception
+    import ctypes as C
+    assert eng.lib.st_clear_status(eng._h, C.c_void_p(0)) == 0
+    torch.cuda.synchronize()
+    assert eng.status().max() == 0
+
+
+def test_c_abi_rejects_invalid_arguments(mods):
+    import ctypes as C
+    from stereotracking_b200 import _lib
+    lib = _lib.lib()
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    null = C.c_void_p(0)
+    assert lib.st_disp2depth(null, 1, 8, 8, 8, 8, 32, 32, null, null, null, 0.25, 640.0, null) == -1
+    assert lib.st_box_depth(null, 1, 32, 32, null, null, 4, null, null, null, null, null) == -1
+    assert lib.st_track_step(eng._h, 2, *([null] * 7), 4, *([null] * 10)) == -1       # S > max_sequences
+    assert lib.st_kalman_batch(7, 1, null, null, null, null) == -1
+    assert lib.st_pipeline_create(null, 3, C.byref(C.c_void_p())) == -1
+    assert lib.st_error_string(-1) == b'invalid argument'
+    bad = _lib.StConfig()
+    lib.st_default_config(C.byref(bad))
+    bad.max_tracks = 5000
+    h = C.c_void_p()
+    assert lib.st_create(C.byref(bad), C.byref(h)) == -1
+    bad.max_tracks, bad.max_candidates = 64, 100000                  # K2 shared-memory capacity
+    assert lib.st_create(C.byref(bad), C.byref(h)) == -4
