@@ -22,7 +22,7 @@ class StereoTrackOracle:
     def __init__(self, tracker_cfg=None, baseline=0.25, focal_length=640,
                  img_scale=None, size_divisor=32, score_thr=0.01, nms_iou=0.5,
                  strides=(8, 16, 32)):
-        self.tracker = OCSortDisparityOracle(**(tracker_cfg or self.DEFAULT_TRACKER))
+        self.tracker = OCSortDisparityOracle(**(self.DEFAULT_TRACKER if tracker_cfg is None else tracker_cfg))
         self.baseline, self.focal_length = baseline, focal_length
         self.img_scale, self.size_divisor = img_scale, size_divisor
         self.score_thr, self.nms_iou, self.strides = score_thr, nms_iou, strides

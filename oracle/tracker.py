@@ -83,7 +83,7 @@ class OCSortDisparityOracle:
                  weight_iou_with_det_scores=True, match_iou_thr=0.3,
                  num_tentatives=3, vel_consist_weight=0.2, vel_delta_t=3,
                  num_frames_retain=10, cmc=None, **_ignored):
-        assert cmc is None, 'camera-motion compensation is a "next" row'
+        self.cmc = cmc        # the warp itself is passed to track(); estimation is host-side OpenCV
         self.obj_score_thr = obj_score_thr
         self.init_track_thr = init_track_thr
         self.weight_iou_with_det_scores = weight_iou_with_det_scores

@@ -156,8 +156,8 @@ def ego_warps(gen, F):
     return warps
 
 
-def run_reference_sequence(ns, raws, dets, warps=None):
-    cfg = dict(TRACKER_CFG)
+def run_reference_sequence(ns, raws, dets, warps=None, tracker_cfg=None):
+    cfg = dict(TRACKER_CFG if tracker_cfg is None else tracker_cfg)
     if warps is not None:
         cfg['cmc'] = dict(method='glme_affine')
     model = ref_shims.build_model(ns, cfg)
@@ -232,6 +232,10 @@ def make_sequences(ns):
                           blackout=(20, 21, 33)),
         'stress': dict(cfg=SceneConfig(192, 256, 8, 14, invalid_prob=0.30, n_clutter=0, heavy_ego=True),
                        F=40, seed=5, miss=0.15, clutter=8, blackout=(0, 9)),
+        # constructor defaults of OCSORTTracker_Disparity (:42-52) instead of the AirDrone config:
+        # weight_iou_with_det_scores=True, match_iou_thr=0.3, num_frames_retain=10
+        'defaults': dict(cfg=SceneConfig(160, 224, 6, 9, n_clutter=0), F=40, seed=7, miss=0.25, clutter=3,
+                         blackout=(12, 13), tracker_cfg={}),
         # camera-motion compensation on (cmc=dict(method='glme_affine')), scripted warps
         'cmc': dict(cfg=SceneConfig(192, 256, 6, 10, n_clutter=0, heavy_ego=True),
                     F=40, seed=6, miss=0.20, clutter=3, blackout=(17,), cmc=True),
@@ -244,7 +248,7 @@ def make_sequences(ns):
         dets = synth_dets(gen, sc['F'], rng, miss=sc['miss'], clutter=sc['clutter'],
                           blackout=sc['blackout'])
         warps = ego_warps(gen, sc['F']) if sc.get('cmc') else None
-        frames = run_reference_sequence(ns, raws, dets, warps)
+        frames = run_reference_sequence(ns, raws, dets, warps, sc.get('tracker_cfg'))
         save_sequence(name, raws, dets, frames, warps)
 
 

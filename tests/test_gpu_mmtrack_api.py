@@ -40,14 +40,15 @@ def api():
     return dict(torch=torch, compat=compat, api=mmtrack_api, odisp=odisp)
 
 
-@pytest.mark.parametrize('name', ['basic', 'occlusion', 'cmc'])
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'cmc', 'defaults'])
 def test_model_predict_replays_reference_fixture(api, name):
     torch, compat = api['torch'], api['compat']
     g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
     det = _Det(api)
     extra = dict(cmc=dict(method='glme_affine')) if name == 'cmc' else {}
+    base = dict(type='OCSORTTracker_Disparity') if name == 'defaults' else TRACKER_CFG     # ctor defaults
     model = compat.MODELS.build(dict(type='OCSORT_Disparity', detector=det, motion=dict(type='KalmanFilter'),
-                                     tracker=dict(TRACKER_CFG, max_dets=64, max_tracks=128, **extra)))
+                                     tracker=dict(base, max_dets=64, max_tracks=128, **extra)))
     assert type(model.tracker).__name__ == 'OCSORTTracker_Disparity' and model.tracker.empty
     if name == 'cmc':
         # as in the fixture: the host-side estimator is replaced by the scripted warps, the

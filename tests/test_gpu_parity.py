@@ -221,10 +221,13 @@ def test_lapjv_batch_matches_oracle(mods, R, C, ties):
 
 
 # ---------------------------------------------------------------- tracker ---------
-@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress', 'cmc'])
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress', 'cmc', 'defaults'])
 def test_tracker_matches_reference_fixture(mods, name):
     g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
-    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1, max_dets=64, max_tracks=128))
+    # 'defaults': constructor defaults of OCSORTTracker_Disparity (weight_iou_with_det_scores=True,
+    # match_iou_thr=0.3, num_frames_retain=10) instead of the AirDrone config
+    cfg = dict(tracker={}) if name == 'defaults' else {}
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1, max_dets=64, max_tracks=128, **cfg))
     D = eng.cfg.max_dets
     for f in range(len(g['raw'])):
         n = int(g['det_count'][f])

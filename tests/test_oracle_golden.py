@@ -44,10 +44,11 @@ def test_boxdepth_matches_reference():
     np.testing.assert_array_equal(cxcyah_to_xyxy(cx), g['xyxy_back'])
 
 
-@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress', 'cmc'])
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress', 'cmc', 'defaults'])
 def test_tracker_sequence_matches_reference(name):
     g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
-    o = StereoTrackOracle()
+    # 'defaults': the constructor defaults of OCSORTTracker_Disparity, not the AirDrone config
+    o = StereoTrackOracle(tracker_cfg={}) if name == 'defaults' else StereoTrackOracle()
     lost_recovered = 0
     for f in range(len(g['raw'])):
         n = int(g['det_count'][f])
