@@ -227,6 +227,7 @@ def main():
     from stereotracking_b200.engine import EngineConfig, LockstepGroups, StereoTrackEngine
 
     from stereotracking_b200 import shard
+    numa = shard.bind_to_gpu_numa(local) if world > 1 else dict(bound=False, reason='single process')
     # whole sequences per rank (video_sampler.py:50-69): rank r owns sequences [first, first + S)
     first_seq, n_own = shard.shard_sequences(S * world, world, rank)
     assert n_own == S
@@ -435,7 +436,7 @@ def main():
             k4_phase_cycles_median=dict(zip(['filter_predict', 'stage1', 'stage2', 'stage3', 'smooth_order', 'update'],
                                             [int(x) for x in np.median(dbg[:, 8:14], axis=0)])),
             assignments=dict(solved=int(dbg[:, 5].sum()), exact_fallback=int(dbg[:, 6].sum())), status_bits=int(status.max()), tracked_rows_last_step=tracked_rows,
-            gathered_rows_all_ranks=int(len(gathered)))
+            gathered_rows_all_ranks=int(len(gathered)), numa_rank0=numa)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -12,6 +12,44 @@ import numpy as np
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index):
+    """Best effort: restrict this process to the CPUs of the NUMA node its GPU hangs off,
+    before any pinned host buffer is allocated (first-touch places the pages there), so
+    that with one process per GPU the host<->device copies of all ranks do not cross the
+    socket interconnect.  Returns a small report dict; never raises."""
+    import os
+    try:
+        bus = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',')[device_index])
+                                                  if os.environ.get('CUDA_VISIBLE_DEVICES') else device_index)
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        except Exception:
+            import torch
+            pr = torch.cuda.get_device_properties(device_index)
+            bus = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        bus = bus.lower()
+        if len(bus.split(':')[0]) == 8:                 # nvml prints an 8-digit domain
+            bus = bus[4:]
+        node = int(open(f'/sys/bus/pci/devices/{bus}/numa_node').read())
+        if node < 0:
+            return dict(bound=False, reason='numa_node=-1', bus=bus)
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return dict(bound=False, reason='no allowed cpu on the node', node=node, bus=bus)
+        os.sched_setaffinity(0, allowed)
+        return dict(bound=True, node=node, cpus=len(allowed), bus=bus)
+    except Exception as e:                              # containers may hide sysfs / NVML
+        return dict(bound=False, reason=f'{type(e).__name__}: {e}')
+
+
 def shard_sequences(n_sequences, world_size, rank):
     """(first, count) of the contiguous block of sequences rank ``rank`` owns:
     ``np.array_split`` semantics (the first ``n % world`` ranks get one more),
