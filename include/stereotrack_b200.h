@@ -225,6 +225,12 @@ int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, void *input
 int st_pipeline_fork(st_pipeline *p, void *stream);
 /* `stream` waits for every frame submitted so far */
 int st_pipeline_join(st_pipeline *p, void *stream);
+/* Timeline (tracing aid; the reference has no per-stage timers, utils/benchmark.py:195-231
+ * times whole test_steps): time-stamp begin and end of the five stages of the next n_frames
+ * submitted frames; read_trace synchronises and fills ms_host[frame][stage][begin,end] in
+ * milliseconds since tracing was switched on, returning the number of traced frames. */
+int st_pipeline_trace(st_pipeline *p, int n_frames);
+int st_pipeline_read_trace(st_pipeline *p, float *ms_host, int max_frames);
 
 /* Debug / parity / checkpoint: copies the live tracks of sequence `seq` in
  * dict order to HOST arrays sized max_tracks (synchronises).  mean [T,8] f64,

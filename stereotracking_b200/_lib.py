@@ -71,6 +71,8 @@ _SIGNATURES = {
     'st_pipeline_submit': (_I, [_P, _I, C.POINTER(StFrameIO), _P, _P]),
     'st_pipeline_fork': (_I, [_P, _P]),
     'st_pipeline_join': (_I, [_P, _P]),
+    'st_pipeline_trace': (_I, [_P, _I]),
+    'st_pipeline_read_trace': (_I, [_P, _P, _I]),
     'st_export_state': (_I, [_P, _I] + [_P] * 8),
     'st_kalman_batch': (_I, [_I, _I, _P, _P, _P, _P]),
     'st_lapjv_batch': (_I, [_P, _I, _I, _I, _P, C.c_double, _I, _P, _P, _P]),

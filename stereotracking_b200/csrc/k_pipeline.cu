@@ -64,6 +64,11 @@ struct st_pipeline {
     cudaStream_t st[kStages];
     cudaEvent_t *ev;                   // [kStages][depth] stage completion of the frame in that slot
     cudaEvent_t fork_ev;
+    // optional timeline (st_pipeline_trace): begin / end timing events of every stage of the
+    // first trace_cap frames submitted after tracing was switched on
+    cudaEvent_t *trace_ev;             // [trace_cap][kStages][2]
+    cudaEvent_t trace_origin;
+    int trace_cap, trace_n;
 };
 
 extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
@@ -71,6 +76,7 @@ extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
     st_pipeline *p = new (std::nothrow) st_pipeline();
     if (!p) return ST_ERR_ALLOC;
     p->h = h; p->depth = depth; p->submitted = 0;
+    p->trace_ev = nullptr; p->trace_cap = 0; p->trace_n = 0;
     p->ev = new (std::nothrow) cudaEvent_t[kStages * depth];
     if (!p->ev) { delete p; return ST_ERR_ALLOC; }
     bool ok = cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming) == cudaSuccess;
@@ -88,6 +94,11 @@ extern "C" int st_pipeline_destroy(st_pipeline *p) {
     for (int i = 0; i < kStages; ++i) cudaStreamSynchronize(p->st[i]);
     for (int i = 0; i < kStages * p->depth; ++i) cudaEventDestroy(p->ev[i]);
     cudaEventDestroy(p->fork_ev);
+    if (p->trace_ev) {
+        for (int i = 0; i < p->trace_cap * kStages * 2; ++i) cudaEventDestroy(p->trace_ev[i]);
+        cudaEventDestroy(p->trace_origin);
+        delete[] p->trace_ev;
+    }
     for (int i = 0; i < kStages; ++i) cudaStreamDestroy(p->st[i]);
     delete[] p->ev;
     delete p;
@@ -119,19 +130,26 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     const int slot = (int)(p->submitted % p->depth);
     auto ev = [&](int stage) { return p->ev[stage * p->depth + slot]; };
     const bool reused = p->submitted >= p->depth;
+    const bool traced = p->trace_ev && p->trace_n < p->trace_cap;
+    auto mark = [&](int stage, int end) {            // timeline event on the stage's stream
+        if (traced) cudaEventRecord(p->trace_ev[(p->trace_n * kStages + stage) * 2 + end], p->st[stage]);
+    };
     int rc;
     // ---- stream 0: K1.  The buffer set of this slot is free once its previous frame left stream 4.
     if (reused) ST_CUDA_OK(cudaStreamWaitEvent(p->st[0], ev(4), 0));
     if (inputs_ready) ST_CUDA_OK(cudaStreamWaitEvent(p->st[0], (cudaEvent_t)inputs_ready, 0));
+    mark(0, 0);
     if (io->raw) {
         rc = st_disp2depth(io->raw, S, io->H, io->W, io->Hr, io->Wr, io->Hp, io->Wp, io->depth_map,
                            io->disp3, io->mask, h->cfg.baseline, h->cfg.focal_length, p->st[0]);
         if (rc != ST_OK) return rc;
     }
+    mark(0, 1);
     ST_CUDA_OK(cudaEventRecord(ev(0), p->st[0]));
     // ---- stream 1: K2 (its det_* outputs were last read by stream 3 and 4 of the slot's previous frame)
     if (reused) ST_CUDA_OK(cudaStreamWaitEvent(p->st[1], ev(4), 0));
     if (inputs_ready) ST_CUDA_OK(cudaStreamWaitEvent(p->st[1], (cudaEvent_t)inputs_ready, 0));
+    mark(1, 0);
     if (io->cls) {
         rc = st_decode_nms(h, io->cls, io->bbox, io->obj, io->num_levels, io->level_h, io->level_w,
                            io->strides, S, io->num_classes, io->scale_w, io->scale_h, io->ori_h, io->ori_w,
@@ -139,31 +157,71 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
                            io->det_counts, p->st[1]);
         if (rc != ST_OK) return rc;
     }
+    mark(1, 1);
     ST_CUDA_OK(cudaEventRecord(ev(1), p->st[1]));
     // ---- stream 2: K3 on the detections
     ST_CUDA_OK(cudaStreamWaitEvent(p->st[2], ev(0), 0));
     ST_CUDA_OK(cudaStreamWaitEvent(p->st[2], ev(1), 0));
+    mark(2, 0);
     rc = st_box_depth(io->depth_map, S, io->Hp, io->Wp, io->det_boxes, io->det_counts, cap, io->det_depth,
                       io->det_scales, io->det_inflated, io->k3_workspace, p->st[2]);
     if (rc != ST_OK) return rc;
+    mark(2, 1);
     ST_CUDA_OK(cudaEventRecord(ev(2), p->st[2]));
     // ---- stream 3: the tracker, frames strictly in order
     ST_CUDA_OK(cudaStreamWaitEvent(p->st[3], ev(2), 0));
+    mark(3, 0);
     rc = st_track_step(h, S, io->frame_ids, io->det_inflated, io->det_scores, io->det_labels, io->det_scales,
                        io->det_depth, io->det_counts, cap, io->trk_boxes, io->out_scores, io->out_labels,
                        io->out_scales, io->trk_depth, io->out_ids, io->out_counts, io->out_src, io->warp, p->st[3]);
     if (rc != ST_OK) return rc;
+    mark(3, 1);
     ST_CUDA_OK(cudaEventRecord(ev(3), p->st[3]));
     // ---- stream 4: deflate and the output depth
     ST_CUDA_OK(cudaStreamWaitEvent(p->st[4], ev(3), 0));
+    mark(4, 0);
     rc = st_scale_boxes(io->trk_boxes, io->out_scales, io->out_counts, S, cap, 1, io->out_boxes, p->st[4]);
     if (rc != ST_OK) return rc;
     rc = st_box_depth_reuse(io->depth_map, S, io->Hp, io->Wp, io->out_boxes, io->out_counts, cap, io->out_depth,
                             io->out_scale2, nullptr, io->k3_workspace, io->out_src ? io->det_boxes : nullptr,
                             io->out_src, io->out_src ? io->det_depth : nullptr, p->st[4]);
     if (rc != ST_OK) return rc;
+    mark(4, 1);
+    if (traced) p->trace_n += 1;
     ST_CUDA_OK(cudaEventRecord(ev(4), p->st[4]));
     if (frame_done) ST_CUDA_OK(cudaEventRecord((cudaEvent_t)frame_done, p->st[4]));
     p->submitted += 1;
     return ST_OK;
+}
+
+// Timeline of the pipeline (tracing aid): after st_pipeline_trace(p, n) the begin and end
+// of every stage of the next n submitted frames are time-stamped with CUDA events on the
+// stage's own stream; st_pipeline_read_trace synchronises and returns, per traced frame
+// and stage, {begin, end} in milliseconds since tracing was switched on.
+extern "C" int st_pipeline_trace(st_pipeline *p, int n_frames) {
+    if (!p || n_frames < 0 || n_frames > 4096) return ST_ERR_INVALID_ARG;
+    if (p->trace_ev) {
+        for (int i = 0; i < p->trace_cap * kStages * 2; ++i) cudaEventDestroy(p->trace_ev[i]);
+        cudaEventDestroy(p->trace_origin);
+        delete[] p->trace_ev;
+        p->trace_ev = nullptr;
+    }
+    p->trace_cap = n_frames; p->trace_n = 0;
+    if (n_frames == 0) return ST_OK;
+    p->trace_ev = new (std::nothrow) cudaEvent_t[(size_t)n_frames * kStages * 2];
+    if (!p->trace_ev) { p->trace_cap = 0; return ST_ERR_ALLOC; }
+    for (int i = 0; i < n_frames * kStages * 2; ++i) ST_CUDA_OK(cudaEventCreate(&p->trace_ev[i]));
+    ST_CUDA_OK(cudaEventCreate(&p->trace_origin));
+    ST_CUDA_OK(cudaEventRecord(p->trace_origin, p->st[0]));
+    return ST_OK;
+}
+
+extern "C" int st_pipeline_read_trace(st_pipeline *p, float *ms_host, int max_frames) {
+    if (!p || !ms_host || max_frames < 0) return ST_ERR_INVALID_ARG;
+    if (!p->trace_ev) return 0;
+    for (int i = 0; i < kStages; ++i) ST_CUDA_OK(cudaStreamSynchronize(p->st[i]));
+    const int n = p->trace_n < max_frames ? p->trace_n : max_frames;
+    for (int i = 0; i < n * kStages * 2; ++i)
+        ST_CUDA_OK(cudaEventElapsedTime(&ms_host[i], p->trace_origin, p->trace_ev[i]));
+    return n;
 }

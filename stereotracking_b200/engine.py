@@ -427,6 +427,20 @@ class FramePipeline:
                                 [t.data_ptr() for t in bbox_l], [t.data_ptr() for t in obj_l],
                                 ready_event, done_event, 0 if warp is None else warp.data_ptr())
 
+    STAGES = ('k1_disp2depth', 'k2_decode_nms', 'k3_box_depth_dets', 'k4_track_step', 'deflate_k3_tracks')
+
+    def trace(self, n_frames):
+        """Time-stamp the stages of the next ``n_frames`` submitted frames (0 = off)."""
+        _lib.check(self.engine.lib.st_pipeline_trace(self._p, int(n_frames)), 'st_pipeline_trace')
+
+    def read_trace(self, max_frames=4096):
+        """[frames, 5 stages, (begin, end)] milliseconds since ``trace`` (synchronises)."""
+        import numpy as np
+        a = np.zeros((max_frames, 5, 2), np.float32)
+        n = _lib.check(self.engine.lib.st_pipeline_read_trace(self._p, a.ctypes.data_as(C.c_void_p), max_frames),
+                       'st_pipeline_read_trace')
+        return a[:n]
+
     def fork(self, stream=None):
         stream = stream or torch.cuda.current_stream(self.engine.device)
         _lib.check(self.engine.lib.st_pipeline_fork(self._p, C.c_void_p(stream.cuda_stream)), 'st_pipeline_fork')

@@ -418,3 +418,28 @@ def test_c_abi_rejects_invalid_arguments(mods):
     assert lib.st_create(C.byref(bad), C.byref(h)) == -1
     bad.max_tracks, bad.max_candidates = 64, 100000                  # K2 shared-memory capacity
     assert lib.st_create(C.byref(bad), C.byref(h)) == -4
+
+
+def test_pipeline_trace_reports_ordered_stage_times(mods):
+    """st_pipeline_trace: begin <= end per stage, and the stages of a frame follow their
+    dependencies (K1, K2 -> K3 on detections -> tracker -> deflate + K3 on tracks)."""
+    from stereotracking_b200.engine import FramePipeline
+    cfg = mods.SceneConfig(192, 256, 4, 8, n_clutter=10)
+    S, F = 2, 6
+    fr = mods.SyntheticStereo(cfg, S, F, seed=34).frames(0, F)
+    raw = fr['raw'].cuda().contiguous()
+    heads = [[c.cuda().contiguous() for c in fr[k]] for k in ('cls', 'bbox', 'obj')]
+    fid = torch.arange(F, dtype=torch.int32, device='cuda')[:, None].repeat(1, S).contiguous()
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S))
+    pipe = FramePipeline(eng, (S, cfg.height, cfg.width), [c.shape[-2:] for c in heads[0]], depth=3)
+    pipe.trace(4)
+    for f in range(F):
+        pipe.submit(fid[f], raw[f], [c[f] for c in heads[0]], [c[f] for c in heads[1]], [c[f] for c in heads[2]])
+    tr = pipe.read_trace()
+    assert tr.shape == (4, 5, 2)                       # only the first 4 frames after trace() are stamped
+    assert (tr[:, :, 1] >= tr[:, :, 0]).all() and (tr >= 0).all()
+    assert (tr[:, 2, 0] >= tr[:, 0, 1]).all() and (tr[:, 2, 0] >= tr[:, 1, 1]).all()
+    assert (tr[:, 3, 0] >= tr[:, 2, 1]).all() and (tr[:, 4, 0] >= tr[:, 3, 1]).all()
+    assert (tr[1:, 3, 0] >= tr[:-1, 3, 1]).all()       # the tracker takes the frames in order
+    pipe.trace(0)
+    assert len(pipe.read_trace()) == 0
