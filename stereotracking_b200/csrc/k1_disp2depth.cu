@@ -5,6 +5,7 @@
 //   mmtrack/datasets/transforms/loading_disparity.py:82-86,:129-134
 //   mmtrack/datasets/transforms/transforms_disparity.py:52-70,:177-194
 //   mmtrack/models/mot/ocsort_disparity.py:132-134
+#include <cstdlib>
 #include "st_common.cuh"
 
 namespace {
@@ -353,6 +354,7 @@ extern "C" int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, i
                 int per_sm = 0;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1)
                     per_sm = 4;
+                if (const char *e = getenv("ST_K1_CTAS_PER_SM")) { const int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }
                 resident = (long long)sm_count() * per_sm;
             }
             long long grid = resident;

@@ -13,6 +13,7 @@
 // fall inside the window).  Boxes are small (airborne objects), so a warp per
 // box with the valid depths staged in shared memory keeps every pass on-chip;
 // boxes with more valid pixels than the stage re-read the map (L1/L2).
+#include <cstdlib>
 #include "st_common.cuh"
 
 namespace {
@@ -844,7 +845,9 @@ extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, con
     }
     // persistent grids sized in multiples of the SM count, looping over the worklists:
     // large boxes -> distinct-value table kernel; its overflow list -> staged radix select
-    long long tgrid = (long long)sms * 2;
+    static int table_per_sm = 0;
+    if (!table_per_sm) { const char *e = getenv("ST_K3_TABLE_CTAS_PER_SM"); table_per_sm = e ? atoi(e) : 2; }
+    long long tgrid = (long long)sms * table_per_sm;
     if (tgrid > list_cap) tgrid = list_cap;
     k3_box_depth_table<<<(int)tgrid, kTableThreads, kTableSmem, (cudaStream_t)stream>>>(
         depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap);

@@ -3,6 +3,7 @@
 // between them, no synchronisation).  Mirrors OCSORT_Disparity.predict between
 // the detector backbone and the return value
 // (mmtrack/models/mot/ocsort_disparity.py:79-109).
+#include <cstdlib>
 #include <new>
 #include "st_common.cuh"
 
@@ -80,8 +81,17 @@ extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
     p->ev = new (std::nothrow) cudaEvent_t[kStages * depth];
     if (!p->ev) { delete p; return ST_ERR_ALLOC; }
     bool ok = cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; ok && i < kStages; ++i)
-        ok = cudaStreamCreateWithFlags(&p->st[i], cudaStreamNonBlocking) == cudaSuccess;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const char *pe = getenv("ST_PIPE_PRIO");
+    const int prio_mode = pe ? atoi(pe) : 0;
+    for (int i = 0; ok && i < kStages; ++i) {
+        // prio_mode 1: the tracker (the serial stage) above everything else; 2: K1 below everything else
+        int prio = prio_lo;
+        if (prio_mode == 1 && i == 3) prio = prio_hi;
+        if (prio_mode == 2) prio = i == 0 ? prio_lo : prio_hi;
+        ok = cudaStreamCreateWithPriority(&p->st[i], cudaStreamNonBlocking, prio_mode ? prio : 0) == cudaSuccess;
+    }
     for (int i = 0; ok && i < kStages * depth; ++i)
         ok = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { delete[] p->ev; delete p; return ST_ERR_CUDA; }
