@@ -148,8 +148,12 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     // ---- stream 0: K1.  The buffer set of this slot is free once its previous frame left stream 4.
     if (reused) ST_CUDA_OK(cudaStreamWaitEvent(p->st[0], ev(4), 0));
     if (inputs_ready) ST_CUDA_OK(cudaStreamWaitEvent(p->st[0], (cudaEvent_t)inputs_ready, 0));
+    // diagnostics only (ST_PIPE_SKIP, bit i = leave stage i's kernels out; results are then stale):
+    // shows which stage slows which in the overlapped regime (tools/pipeline_timeline.py)
+    static int skip = -1;
+    if (skip < 0) { const char *e = getenv("ST_PIPE_SKIP"); skip = e ? atoi(e) : 0; }
     mark(0, 0);
-    if (io->raw) {
+    if (io->raw && !(skip & 1)) {
         rc = st_disp2depth(io->raw, S, io->H, io->W, io->Hr, io->Wr, io->Hp, io->Wp, io->depth_map,
                            io->disp3, io->mask, h->cfg.baseline, h->cfg.focal_length, p->st[0]);
         if (rc != ST_OK) return rc;
@@ -160,7 +164,7 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     if (reused) ST_CUDA_OK(cudaStreamWaitEvent(p->st[1], ev(4), 0));
     if (inputs_ready) ST_CUDA_OK(cudaStreamWaitEvent(p->st[1], (cudaEvent_t)inputs_ready, 0));
     mark(1, 0);
-    if (io->cls) {
+    if (io->cls && !(skip & 2)) {
         rc = st_decode_nms(h, io->cls, io->bbox, io->obj, io->num_levels, io->level_h, io->level_w,
                            io->strides, S, io->num_classes, io->scale_w, io->scale_h, io->ori_h, io->ori_w,
                            cap, io->det_boxes, io->det_scores, io->det_labels, io->det_prior, io->det_keep,
@@ -173,8 +177,9 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     ST_CUDA_OK(cudaStreamWaitEvent(p->st[2], ev(0), 0));
     ST_CUDA_OK(cudaStreamWaitEvent(p->st[2], ev(1), 0));
     mark(2, 0);
-    rc = st_box_depth(io->depth_map, S, io->Hp, io->Wp, io->det_boxes, io->det_counts, cap, io->det_depth,
-                      io->det_scales, io->det_inflated, io->k3_workspace, p->st[2]);
+    rc = (skip & 4) ? ST_OK
+                    : st_box_depth(io->depth_map, S, io->Hp, io->Wp, io->det_boxes, io->det_counts, cap, io->det_depth,
+                                   io->det_scales, io->det_inflated, io->k3_workspace, p->st[2]);
     if (rc != ST_OK) return rc;
     mark(2, 1);
     ST_CUDA_OK(cudaEventRecord(ev(2), p->st[2]));
