@@ -144,3 +144,36 @@ def test_rgb_only_ocsort_matches_oracle_tracker(api):
         rows += len(want['instances_id'])
     assert rows > 100
 
+
+
+def test_predict_with_gt_depth_map_fills_gt_depth(api):
+    """inputs['depth_postp'] (a ground-truth depth map, ocsort_disparity.py:56-59,:100-104):
+    gt_depth of every track is the same box statistic taken from that map."""
+    torch, compat = api['torch'], api['compat']
+    from oracle import boxdepth
+    g = np.load(os.path.join(GOLDEN, 'ref_track_basic.npz'))
+    det = _Det(api)
+    model = compat.MODELS.build(dict(type='OCSORT_Disparity', detector=det, motion=dict(type='KalmanFilter'),
+                                     tracker=dict(TRACKER_CFG, max_dets=64, max_tracks=128)))
+    rng = np.random.default_rng(9)
+    checked = 0
+    for f in range(6):
+        n = int(g['det_count'][f])
+        pre = api['odisp'].preprocess(g['raw'][f])
+        gt_map = rng.uniform(1.0, 120.0, pre['depth'].shape).astype(np.float32)
+        disp = torch.from_numpy(pre['disp'])[None, None, None].repeat(1, 1, 3, 1, 1).cuda()
+        det.next = compat.InstanceData(bboxes=torch.from_numpy(g['det_boxes'][f, :n].copy()).cuda(),
+                                       scores=torch.from_numpy(g['det_scores'][f, :n].copy()).cuda(),
+                                       labels=torch.zeros(n, dtype=torch.int64).cuda())
+        sample = compat.TrackDataSample(metainfo=dict(frame_id=f))
+        out = model.predict(dict(img=torch.zeros_like(disp), disp_postp=disp,
+                                 disp_mask=torch.ones(1, 1, 1, *pre['depth'].shape).cuda(),
+                                 depth_postp=torch.from_numpy(gt_map)[None, None, None].cuda()), [sample])[0]
+        ti = out.pred_track_instances
+        want, _ = boxdepth.extract_depth(gt_map, ti.bboxes.cpu().numpy())
+        np.testing.assert_allclose(np.asarray(ti['gt_depth'], np.float32), np.asarray(want, np.float32), rtol=1e-5,
+                                   equal_nan=True)
+        m = int(g['out_count'][f])
+        np.testing.assert_allclose(np.asarray(ti['depth'], np.float32), g['out_depth'][f, :m], rtol=1e-5, equal_nan=True)
+        checked += m
+    assert checked > 20
