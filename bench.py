@@ -435,7 +435,9 @@ def main():
             host_issue_ms_per_step=issue_ms / K,
             k4_phase_cycles_median=dict(zip(['filter_predict', 'stage1', 'stage2', 'stage3', 'smooth_order', 'update'],
                                             [int(x) for x in np.median(dbg[:, 8:14], axis=0)])),
-            assignments=dict(solved=int(dbg[:, 5].sum()), exact_fallback=int(dbg[:, 6].sum())), status_bits=int(status.max()), tracked_rows_last_step=tracked_rows,
+            assignments=dict(solved=int(dbg[:, 5].sum()), exact_fallback=int(dbg[:, 6].sum()),
+                             last_search_cycles_median=int(np.median(dbg[:, 14])),
+                             last_certificate_cycles_median=int(np.median(dbg[:, 15]))), status_bits=int(status.max()), tracked_rows_last_step=tracked_rows,
             gathered_rows_all_ranks=int(len(gathered)), numa_rank0=numa)
         print(json.dumps(line))
     if world > 1:

@@ -55,6 +55,13 @@ struct Smem {                    // carved from dynamic shared memory
     float *cost;                 // [cost_cap] cost matrix of the current stage when it fits
     int cost_cap;
     int *row_cnt, *col_cnt, *row_adm, *adm_misc;   // admissible-edge statistics (stlap::Problem)
+    // the frame's working set, fetched once (every later phase is a chain of dependent reads)
+    int *ord_slot;               // [T] order[p]
+    int *slot_pos;               // [T] slot -> order position (live slots only)
+    unsigned char *ord_tent;     // [T] tentative flag per order position
+    unsigned char *ord_tracked;  // [T] tracked flag per order position (as of the start of the frame)
+    float *in_box;               // [D,4] detection boxes
+    float *in_score;             // [D]
 };
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -67,6 +74,7 @@ __host__ __device__ inline size_t smem_bytes(int T, int D) {
     b += align16(T) + align16(D) + align16(T);
     b += align16(sizeof(float) * (size_t)((long long)T * D < kCostSmemFloats ? T * D : kCostSmemFloats));
     b += align16(sizeof(int) * T) * 2 + align16(sizeof(int) * D) + 16;
+    b += align16(sizeof(int) * T) * 2 + align16(T) * 2 + align16(sizeof(float) * D * 4) + align16(sizeof(float) * D);
     return b;
 }
 
@@ -90,7 +98,13 @@ __device__ inline Smem carve(unsigned char *p, int T, int D) {
     m.row_cnt = reinterpret_cast<int *>(p); p += align16(sizeof(int) * T);
     m.row_adm = reinterpret_cast<int *>(p); p += align16(sizeof(int) * T);
     m.col_cnt = reinterpret_cast<int *>(p); p += align16(sizeof(int) * D);
-    m.adm_misc = reinterpret_cast<int *>(p);
+    m.adm_misc = reinterpret_cast<int *>(p); p += 16;
+    m.ord_slot = reinterpret_cast<int *>(p); p += align16(sizeof(int) * T);
+    m.slot_pos = reinterpret_cast<int *>(p); p += align16(sizeof(int) * T);
+    m.ord_tent = p; p += align16(T);
+    m.ord_tracked = p; p += align16(T);
+    m.in_box = reinterpret_cast<float *>(p); p += align16(sizeof(float) * D * 4);
+    m.in_score = reinterpret_cast<float *>(p);
     return m;
 }
 
@@ -183,7 +197,7 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
     const double lap_limit = 2.0 * pr.lap_half;
     for (int r = threadIdx.x; r < R; r += kThreads) { sm.row_cnt[r] = 0; sm.row_adm[r] = -1; }
     for (int c = threadIdx.x; c < C; c += kThreads) sm.col_cnt[c] = 0;
-    if (threadIdx.x == 0) sm.adm_misc[0] = 0;
+    if (threadIdx.x == 0) { sm.adm_misc[0] = 0; sm.adm_misc[1] = 0; }
     // ---- per-row data --------------------------------------------------------
     for (int r = threadIdx.x; r < R; r += kThreads) {
         const long long g = sbase + sm.rows[r];
@@ -208,7 +222,7 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
         }
     }
     for (int c = threadIdx.x; c < C; c += kThreads)
-        for (int k = 0; k < 4; ++k) sm.det_box[c * 4 + k] = dv.boxes[sm.dets[c] * 4 + k];
+        for (int k = 0; k < 4; ++k) sm.det_box[c * 4 + k] = sm.in_box[sm.dets[c] * 4 + k];
     __syncthreads();
     // ---- cost matrix -----------------------------------------------------------
     const float kHalfPi = 1.57079637f, kPi = 3.14159274f;
@@ -216,7 +230,7 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
         const int r = e / C, c = e % C;
         const float *tb = sm.row_box + r * 4, *db = sm.det_box + c * 4;
         float iou = iou_pair(tb, db);
-        if (pr.weight_iou) iou = __fmul_rn(iou, dv.scores[sm.dets[c]]);
+        if (pr.weight_iou) iou = __fmul_rn(iou, sm.in_score[sm.dets[c]]);
         float dist = __fsub_rn(1.f, iou);
         if (ocm) {
             const float dcx = __fmul_rn(__fadd_rn(db[0], db[2]), 0.5f), dcy = __fmul_rn(__fadd_rn(db[1], db[3]), 0.5f);
@@ -239,6 +253,7 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
             sm.row_adm[r] = c;
         }
         if (dist != dist) sm.adm_misc[0] = 1;
+        if (fabs((double)dist - lap_limit) <= 2.0e-9) sm.adm_misc[1] = 1;
     }
     __syncthreads();
     if ((g_skip >> 6) & 1)                   // diagnostics: mirror the matrix for st_debug_read_cost
@@ -322,31 +337,45 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
     }
     __syncthreads();
     if (threadIdx.x == 0) sh_nlive = st.n_live[s];
-    for (int i = threadIdx.x; i < nd_in; i += kThreads) { sm.det_slot[i] = -1; sm.det_stage[i] = 0; }
+    for (int i = threadIdx.x; i < nd_in; i += kThreads) {
+        sm.det_slot[i] = -1;
+        sm.det_stage[i] = 0;
+        const float4 b = reinterpret_cast<const float4 *>(dv.boxes)[i];
+        sm.in_box[i * 4 + 0] = b.x; sm.in_box[i * 4 + 1] = b.y; sm.in_box[i * 4 + 2] = b.z; sm.in_box[i * 4 + 3] = b.w;
+        sm.in_score[i] = dv.scores[i];
+    }
     __syncthreads();
     const int n_live = sh_nlive;
+    for (int p = threadIdx.x; p < n_live; p += kThreads) {
+        const int slot = order[p];
+        sm.ord_slot[p] = slot;
+        sm.slot_pos[slot] = p;
+        sm.ord_tent[p] = st.tentative[sbase + slot];
+        sm.ord_tracked[p] = st.tracked[sbase + slot];
+    }
+    __syncthreads();
     int n_out = 0;
 
     if (n_live == 0 || nd_in == 0) {
         // ---- init-only branch (:391-403): keep scores > init_track_thr, all new ids
-        compact_warp0(nd_in, [&](int i) { return dv.scores[i] > pr.init_track_thr; }, sm.out_src, &sh_cnt[0]);
+        compact_warp0(nd_in, [&](int i) { return sm.in_score[i] > pr.init_track_thr; }, sm.out_src, &sh_cnt[0]);
         n_out = sh_cnt[0];
         for (int i = threadIdx.x; i < n_out; i += kThreads) sm.det_stage[sm.out_src[i]] = 4;
         __syncthreads();
     } else {
         // ---- detection filter (:412-421)
         compact_warp0(nd_in, [&](int i) {
-            const float *b = dv.boxes + i * 4;
+            const float *b = sm.in_box + i * 4;
             const float area = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
-            return dv.scores[i] > pr.obj_score_thr && area > 100.f;
+            return sm.in_score[i] > pr.obj_score_thr && area > 100.f;
         }, sm.dets, &sh_cnt[0]);
         int C = sh_cnt[0];
         for (int c = threadIdx.x; c < C; c += kThreads) sm.det_stage[sm.dets[c]] = 4;   // leftover unless matched
         for (int p = threadIdx.x; p < n_live; p += kThreads) sm.slot_hit[p] = 0;
         // ---- confirmed tracks: predict (:431-441)
-        compact_warp0(n_live, [&](int p) { return !st.tentative[sbase + order[p]]; }, sm.rows, &sh_cnt[1]);
+        compact_warp0(n_live, [&](int p) { return !sm.ord_tent[p]; }, sm.rows, &sh_cnt[1]);
         int R = sh_cnt[1];
-        for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = order[sm.rows[r]];   // position -> slot
+        for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = sm.ord_slot[sm.rows[r]];   // position -> slot
         __syncthreads();
         // four tracks per warp (kalman.cuh, 8-lane groups, state in registers)
         for (int r0 = warp * 4; r0 < R; r0 += kWarps * 4) {
@@ -416,18 +445,16 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         // ---- stage 2: tentative tracks vs leftovers (:476-503)
         compact_warp0(nd_in, [&](int i) { return sm.det_stage[i] == 4; }, sm.dets, &sh_cnt[0]);
         C = sh_cnt[0];
-        compact_warp0(n_live, [&](int p) { return st.tentative[sbase + order[p]] != 0; }, sm.rows, &sh_cnt[1]);
+        compact_warp0(n_live, [&](int p) { return sm.ord_tent[p] != 0; }, sm.rows, &sh_cnt[1]);
         R = sh_cnt[1];
-        for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = order[sm.rows[r]];
+        for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = sm.ord_slot[sm.rows[r]];
         __syncthreads();
         associate(st, pr, sm, sbase, R, C, true, dv, cost, 2, &st.status[s]);
         ST_PHASE(10);
         // ---- which tracks are matched so far
         for (int i = threadIdx.x; i < nd_in; i += kThreads) {
             const int slot = sm.det_slot[i];
-            if (slot >= 0)
-                for (int p = 0; p < n_live; ++p)
-                    if (order[p] == slot) { sm.slot_hit[p] = 1; break; }
+            if (slot >= 0) sm.slot_hit[sm.slot_pos[slot]] = 1;
         }
         __syncthreads();
         // ---- stage 3: OCR, every unmatched track's last observation (:505-569)
@@ -435,15 +462,13 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         C = sh_cnt[0];
         compact_warp0(n_live, [&](int p) { return !sm.slot_hit[p]; }, sm.rows, &sh_cnt[1]);
         R = sh_cnt[1];
-        for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = order[sm.rows[r]];
+        for (int r = threadIdx.x; r < R; r += kThreads) sm.rows[r] = sm.ord_slot[sm.rows[r]];
         __syncthreads();
         associate(st, pr, sm, sbase, R, C, false, dv, cost, 3, &st.status[s]);
         ST_PHASE(11);
         for (int i = threadIdx.x; i < nd_in; i += kThreads) {
             const int slot = sm.det_slot[i];
-            if (slot >= 0 && sm.det_stage[i] == 3)
-                for (int p = 0; p < n_live; ++p)
-                    if (order[p] == slot) { sm.slot_hit[p] = 1; break; }
+            if (slot >= 0 && sm.det_stage[i] == 3) sm.slot_hit[sm.slot_pos[slot]] = 1;
         }
         __syncthreads();
         if (threadIdx.x == 0) st.debug[s * 16 + 7] = 8;
@@ -452,7 +477,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             const int slot = sm.det_slot[i];
             if (slot < 0) continue;
             const long long g = sbase + slot;
-            if (st.tracked[g] || (g_skip & 8)) continue;
+            if (sm.ord_tracked[sm.slot_pos[slot]] || (g_skip & 8)) continue;      // tracked flags only change in the update below
             const int miss = st.miss_run[g];
             float last[4], shift[4];
             const float denom = (float)(miss + 1);
@@ -479,7 +504,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582)
         for (int p = threadIdx.x; p < n_live; p += kThreads)
             if (!sm.slot_hit[p]) {
-                const long long g = sbase + order[p];
+                const long long g = sbase + sm.ord_slot[p];
                 st.tracked[g] = 0;
                 push_obs(st, g, nullptr);
             }

@@ -58,7 +58,8 @@ struct Problem {
     int *dbg;             // optional [8] progress words (global), may be null
     // Admissible-edge statistics of the fast path (cost < L = 2 * half): number of
     // admissible entries per row / column, one admissible column of each row, and
-    // adm_misc[0] != 0 when the matrix holds a NaN.  Filled by whoever wrote the
+    // adm_misc[0] != 0 when the matrix holds a NaN, adm_misc[1] != 0 when a cost lies within
+    // 2e-9 of L.  Filled by whoever wrote the
     // matrix (the track kernel does it while it computes the costs) or by
     // count_admissible().
     int *row_cnt, *col_cnt, *row_adm, *adm_misc;
@@ -403,7 +404,7 @@ __device__ inline void count_admissible(const Problem &P) {
     const int lane = threadIdx.x & 31;
     const double L = 2.0 * P.half;
     for (int j = lane; j < P.C; j += 32) P.col_cnt[j] = 0;
-    if (lane == 0) P.adm_misc[0] = 0;
+    if (lane == 0) { P.adm_misc[0] = 0; P.adm_misc[1] = 0; }
     __syncwarp();
     for (int i = lane; i < P.R; i += 32) {
         int cnt = 0, adm = -1;
@@ -411,6 +412,7 @@ __device__ inline void count_admissible(const Problem &P) {
         for (int j = 0; j < P.C; ++j) {
             const double c = (double)P.cost[(long long)i * P.C + j];
             nan |= !(c == c);
+            if (fabs(c - L) <= 2.0e-9) P.adm_misc[1] = 1;
             if (c < L) { ++cnt; adm = j; atomicAdd(&P.col_cnt[j], 1); }
         }
         P.row_cnt[i] = cnt;
@@ -555,7 +557,7 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     // reaches when it inserts that row first (every other entry of the row and of
     // the column costs at least the dummy).  In tracking most pairs are of this
     // kind, so the shortest-path search runs only for the crowded remainder.
-    if (P.adm_misc[0]) return false;
+    if (P.adm_misc[0] || P.adm_misc[1]) return false;      // NaN, or a cost within 2e-9 of L (tie with the dummies)
     for (int j = lane; j < m; j += 32) { v[j] = 0.0; p[j] = -1; }
     __syncwarp();
     int n_active = 0;
@@ -586,6 +588,7 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
         return (j - C == i) ? half : INF;
     };
     // ---- Hungarian, rows inserted one by one ---------------------------------------------
+    const long long t_h0 = clock64();
     bool solved = false;
     if (C <= 256) {
         bool ok;
@@ -652,6 +655,7 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
         __syncwarp();
     }
     }
+    const long long t_h1 = clock64();
     // ---- uniqueness certificate ---------------------------------------------------------
     // sigma[i] = column of row i (own dummy C+i when unmatched); arcs sigma(i) -> j for
     // every tight non-matching edge (i, j), dummy edges included.
@@ -663,20 +667,24 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     volatile int *arc_from = reinterpret_cast<volatile int *>(s.d);     // s.d = 2n ints
     volatile int *arc_to = arc_from + m;
     int n_arcs = 0;
-    const int total_edges = R * C + R;                 // real edges, then one dummy edge per row
+    // Only the rows the search handled can have a tight non-matching real edge: a row without
+    // admissible entries has u = L/2 and an isolated pair keeps u = a_ij < L/2, so every other
+    // entry of such a row has slack >= (cost - L) > eps (no cost lies within 2e-9 of L:
+    // adm_misc[1], checked above).  The real edges of the active rows, then one dummy edge per row:
+    const int real_edges = n_active * C, total_edges = real_edges + R;
     for (int e0 = 0; e0 < total_edges; e0 += 32) {
         const int e = e0 + lane;
         bool tight = false;
         int from = 0, to = 0;
-        if (e < R * C) {
-            const int i = e / C, j = e - i * C;
+        if (e < real_edges) {
+            const int t = e / C, j = e - t * C, i = active[t];
             if (p[j] != i) {
-                const double slack = ((double)P.cost[e] - half) - u[i] - v[j];
+                const double slack = ((double)P.cost[(long long)i * C + j] - half) - u[i] - v[j];
                 tight = slack <= kFastEps;
                 from = sigma[i]; to = j;
             }
         } else if (e < total_edges) {
-            const int i = e - R * C;
+            const int i = e - real_edges;
             if (sigma[i] != C + i) {
                 tight = half - u[i] - v[C + i] <= kFastEps;
                 from = sigma[i]; to = C + i;
@@ -730,6 +738,8 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
         if (__any_sync(0xffffffffu, unsure)) return false;
     }
     __syncwarp();
+    // diagnostics (debug words 14 / 15): cycles of the search and of the certificate, last call
+    if (P.dbg && lane == 0) { P.dbg[14] = (int)(t_h1 - t_h0); P.dbg[15] = (int)(clock64() - t_h1); }
     // ---- publish in solve_warp's layout: y = col -> row, x = row -> col -------------------
     // (p aliases s.x and way aliases s.y, so go through registers)
     int colrow[16];                                   // m <= 512 per lane stride 32
