@@ -96,64 +96,6 @@ __device__ __forceinline__ void for_each_valid(const BoxCtx &c, int lane, F f) {
     }
 }
 
-// Radix select of up to two ranks at once over positive-float bit patterns, one
-// warp.  value[k] = element of rank rank_in[k] (ascending), below[k] = number of
-// elements strictly smaller.  hist = 512 ints of this warp's shared memory.
-__device__ void radix_select2(const BoxCtx &c, int lane, int nsel, const int *rank_in, uint32_t *value,
-                              int *below, int *hist) {
-    uint32_t prefix[2] = {0u, 0u};
-    int rank[2] = {rank_in[0], nsel > 1 ? rank_in[1] : 0};
-    int less[2] = {0, 0};
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = lane; i < 512; i += 32) hist[i] = 0;
-        __syncwarp();
-        const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-        const uint32_t p0 = prefix[0], p1 = prefix[1];
-        for_each_valid(c, lane, [&](float v) {
-            const uint32_t u = __float_as_uint(v);
-            // one shared-memory atomic per distinct bin among the active lanes
-            // (object pixels share one depth, so plain atomics would serialise)
-            int bin = -1;
-            if ((u & himask) == p0) bin = (u >> shift) & 255u;
-            else if (nsel > 1 && (u & himask) == p1) bin = 256 + ((u >> shift) & 255u);
-            const unsigned peers = __match_any_sync(__activemask(), bin);
-            if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
-            if (nsel > 1 && bin >= 0 && bin < 256 && (u & himask) == p1) {
-                const int bin1 = 256 + ((u >> shift) & 255u);
-                atomicAdd(&hist[bin1], 1);
-            }
-        });
-        __syncwarp();
-        for (int k = 0; k < nsel; ++k) {
-            // lane owns bins [8*lane, 8*lane+8); exclusive scan of the lane totals
-            int local[8], tot = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) { local[b] = hist[k * 256 + lane * 8 + b]; tot += local[b]; }
-            int inc = tot;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            int acc = inc - tot;                 // elements in bins before this lane's
-            int found_bin = -1, found_acc = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                if (found_bin < 0 && acc + local[b] > rank[k]) { found_bin = lane * 8 + b; found_acc = acc; }
-                acc += local[b];
-            }
-            const unsigned who = __ballot_sync(0xffffffffu, found_bin >= 0);
-            const int src = __ffs(who) - 1;      // lowest lane that contains the rank
-            found_bin = __shfl_sync(0xffffffffu, found_bin, src);
-            found_acc = __shfl_sync(0xffffffffu, found_acc, src);
-            prefix[k] |= (uint32_t)found_bin << shift;
-            rank[k] -= found_acc;
-            less[k] += found_acc;
-        }
-        __syncwarp();
-    }
-    for (int k = 0; k < nsel; ++k) { value[k] = prefix[k]; below[k] = less[k]; }
-}
-
 // MSB-first binary search on the bit patterns of the staged values (one warp,
 // no histogram, no atomics): per bit one pass over shared memory and one
 // redux.  Same contract as radix_select2.
@@ -194,53 +136,74 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
-k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
-             const int32_t *__restrict__ counts, int cap, float *__restrict__ d_out,
-             float *__restrict__ scale_out, float *__restrict__ inflated, int32_t *__restrict__ worklist,
-             int list_cap, const float *__restrict__ prev_boxes, const int32_t *__restrict__ prev_index,
-             const float *__restrict__ prev_d) {
-    __shared__ float staged_all[kWarps][kStage];
-    __shared__ int hist_all[kWarps][512];
-    const int s = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bi = blockIdx.x * kWarps + warp;
-    if (bi >= counts[s] || bi >= cap) return;          // warp-uniform
-    float *staged = staged_all[warp];
-    int *hist = hist_all[warp];
+// Workspace layout (int32): [0] number of large boxes, [1] number of table overflows, [2] cursor
+// of the table kernel, [3] number of small boxes, then three lists of (sequence, row) pairs with
+// list_cap = S * cap entries each: large boxes, table overflows, small boxes.
+__device__ __forceinline__ int32_t *large_list(int32_t *ws) { return ws + 4; }
+__device__ __forceinline__ int32_t *overflow_list(int32_t *ws, int list_cap) { return ws + 4 + 2 * list_cap; }
+__device__ __forceinline__ int32_t *small_list(int32_t *ws, int list_cap) { return ws + 4 + 4 * list_cap; }
 
+// One thread per box slot: rows that can reuse the statistic of their source row are finished
+// here; the others are sorted into the dense small-box and large-box lists, so that the warp
+// kernel and the table kernel get balanced work and can run side by side.
+//
+// Reuse: the statistic depends on the box only through its truncated corners.  The second call
+// of a frame (ocsort_disparity.py:100-101) runs on the deflated track boxes, which are the
+// inflated-then-deflated detection boxes: whenever the truncated corners equal those of the
+// detection the row came from, the value of the first call is the value of this one.
+__global__ void __launch_bounds__(256)
+k3_classify(int S, int Hp, int Wp, const float *__restrict__ boxes, const int32_t *__restrict__ counts, int cap,
+            float *__restrict__ d_out, float *__restrict__ scale_out, float *__restrict__ inflated,
+            int32_t *__restrict__ worklist, int list_cap, const float *__restrict__ prev_boxes,
+            const int32_t *__restrict__ prev_index, const float *__restrict__ prev_d) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= (long long)S * cap) return;
+    const int s = (int)(o / cap), bi = (int)(o - (long long)s * cap);
+    const int cnt = counts[s];
+    const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
+    const int pi = prev_index ? prev_index[o] : -1;
+    if (bi >= cnt) return;
+    const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
+    if (pi >= 0 && pi < cap) {
+        const float4 pb = reinterpret_cast<const float4 *>(prev_boxes)[(long long)s * cap + pi];
+        if (trunc_i64(pb.x) == b0 && trunc_i64(pb.y) == b1 && trunc_i64(pb.z) == b2 && trunc_i64(pb.w) == b3) {
+            const float d = prev_d[(long long)s * cap + pi];
+            const float dd = __fmul_rn(d, d);
+            const float scale = (dd != dd) ? dd : fmaxf(fminf(dd, 3.f), 1.f);
+            d_out[o] = d;
+            scale_out[o] = scale;
+            if (inflated) {
+                const float cx = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
+                const float cy = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
+                const float hw = __fmul_rn(__fmul_rn(__fsub_rn(box.z, box.x), scale), 0.5f);
+                const float hh = __fmul_rn(__fmul_rn(__fsub_rn(box.w, box.y), scale), 0.5f);
+                reinterpret_cast<float4 *>(inflated)[o] =
+                    make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+            }
+            return;
+        }
+    }
+    const Slice ys = py_slice(b1, b3, Hp), xs = py_slice(b0, b2, Wp);
+    const unsigned npix = (unsigned)max(xs.hi - xs.lo, 0) * (unsigned)max(ys.hi - ys.lo, 0);
+    if (npix > (unsigned)kSmallPix) {
+        const int slot = atomicAdd(&worklist[0], 1);
+        large_list(worklist)[2 * slot] = s;
+        large_list(worklist)[2 * slot + 1] = bi;
+    } else {
+        const int slot = atomicAdd(&worklist[3], 1);
+        small_list(worklist, list_cap)[2 * slot] = s;
+        small_list(worklist, list_cap)[2 * slot + 1] = bi;
+    }
+}
+
+// one small box by one warp; `staged` is the warp's shared-memory stage
+__device__ void k3_box_one(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
+                           const int s, const int bi, int cap, float *__restrict__ d_out,
+                           float *__restrict__ scale_out, float *__restrict__ inflated, float *staged,
+                           const int lane) {
     const long long o = (long long)s * cap + bi;
     const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
     const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
-    // Reuse: the statistic depends on the box only through its truncated corners.  The
-    // second call of a frame (ocsort_disparity.py:100-101) runs on the deflated track
-    // boxes, which are the inflated-then-deflated detection boxes: whenever the
-    // truncated corners equal those of the detection the row came from, the value of
-    // the first call is the value of this one.
-    if (prev_index) {
-        const int pi = prev_index[o];
-        if (pi >= 0 && pi < cap) {
-            const float4 pb = reinterpret_cast<const float4 *>(prev_boxes)[(long long)s * cap + pi];
-            if (trunc_i64(pb.x) == b0 && trunc_i64(pb.y) == b1 && trunc_i64(pb.z) == b2 && trunc_i64(pb.w) == b3) {
-                if (lane == 0) {
-                    const float d = prev_d[(long long)s * cap + pi];
-                    const float dd = __fmul_rn(d, d);
-                    d_out[o] = d;
-                    scale_out[o] = (dd != dd) ? dd : fmaxf(fminf(dd, 3.f), 1.f);
-                    if (inflated) {
-                        const float scale = scale_out[o];
-                        const float cx = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
-                        const float cy = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
-                        const float hw = __fmul_rn(__fmul_rn(__fsub_rn(box.z, box.x), scale), 0.5f);
-                        const float hh = __fmul_rn(__fmul_rn(__fsub_rn(box.w, box.y), scale), 0.5f);
-                        reinterpret_cast<float4 *>(inflated)[o] =
-                            make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
-                    }
-                }
-                return;
-            }
-        }
-    }
     BoxCtx c;
     c.dm = depth + (long long)s * Hp * Wp;
     c.Wp = Wp;
@@ -248,15 +211,6 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
     c.xs = py_slice(b0, b2, Wp);
     c.bw = (unsigned)max(c.xs.hi - c.xs.lo, 0);
     c.npix = c.bw * (unsigned)max(c.ys.hi - c.ys.lo, 0);
-    if (c.npix > (unsigned)kSmallPix) {                 // handled by k3_box_depth_large
-        if (lane == 0) {
-            // worklist = [n_large, n_overflow, large items (s, box) x list_cap, overflow items x list_cap]
-            const int slot = atomicAdd(&worklist[0], 1);
-            worklist[2 + 2 * slot] = s;
-            worklist[3 + 2 * slot] = bi;
-        }
-        return;
-    }
     c.staged = staged;
     c.use_stage = true;
     // corner patches: lane 4c+e fetches element e of corner c now, so that the 16 loads
@@ -304,8 +258,7 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
         uint32_t val[2];
         int below[2];
         int rk[2] = {n / 2, 0};
-        if (c.use_stage) bit_select2(staged, n, lane, 1, rk, val, below);
-        else radix_select2(c, lane, 1, rk, val, below, hist);
+        bit_select2(staged, n, lane, 1, rk, val, below);
         const float d_mid = __uint_as_float(val[0]);
         // corner votes on the unfiltered map (:157-160): lane 4c gathers the elements of corner c
         int k = 0;
@@ -327,8 +280,7 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
             d = __int_as_float(0x7fc00000);                    // mean of empty -> NaN
         } else {
             rk[0] = seg.lo; rk[1] = seg.hi - 1;
-            if (c.use_stage) bit_select2(staged, n, lane, 2, rk, val, below);
-            else radix_select2(c, lane, 2, rk, val, below, hist);
+            bit_select2(staged, n, lane, 2, rk, val, below);
             const uint32_t ua = val[0], ub = val[1];
             double sum;
             if (ua == ub) {
@@ -365,6 +317,22 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
             reinterpret_cast<float4 *>(inflated)[o] =
                 make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
         }
+    }
+}
+
+// Small boxes: a resident wave of 4-warp CTAs, warps stride over the dense small-box list.
+__global__ void __launch_bounds__(kWarps * 32)
+k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes, int cap,
+             float *__restrict__ d_out, float *__restrict__ scale_out, float *__restrict__ inflated,
+             const int32_t *__restrict__ worklist, int list_cap) {
+    __shared__ float staged_all[kWarps][kStage];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = worklist[3];
+    const int32_t *list = worklist + 4 + 4 * list_cap;
+    for (int idx = blockIdx.x * kWarps + warp; idx < n; idx += gridDim.x * kWarps) {
+        k3_box_one(depth, Hp, Wp, boxes, list[2 * idx], list[2 * idx + 1], cap, d_out, scale_out, inflated,
+                   staged_all[warp], lane);
+        __syncwarp();
     }
 }
 
@@ -655,9 +623,16 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
     __shared__ int corner_n[4];
     const int lane = threadIdx.x & 31;
     const int n_work = worklist[0];
-    for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
+    __shared__ int next_item;
+    // items are fetched from a shared cursor: boxes range from 513 to 65 000+ pixels, and with a
+    // static stride one CTA could draw several of the largest while others idled
+    while (true) {
         __syncthreads();
-        const int s = worklist[2 + 2 * item], bi = worklist[3 + 2 * item];
+        if (threadIdx.x == 0) next_item = atomicAdd(&worklist[2], 1);
+        __syncthreads();
+        const int item = next_item;
+        if (item >= n_work) break;
+        const int s = worklist[4 + 2 * item], bi = worklist[5 + 2 * item];
         const long long o = (long long)s * cap + bi;
         const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
         const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
@@ -715,8 +690,8 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
             if (overflow) {
                 if (threadIdx.x == 0) {
                     const int slot = atomicAdd(&worklist[1], 1);
-                    worklist[2 + 2 * list_cap + 2 * slot] = s;
-                    worklist[3 + 2 * list_cap + 2 * slot] = bi;
+                    worklist[4 + 2 * list_cap + 2 * slot] = s;
+                    worklist[5 + 2 * list_cap + 2 * slot] = bi;
                 }
                 continue;                                // block-uniform
             }
@@ -827,11 +802,20 @@ extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, con
         return ST_ERR_INVALID_ARG;
     if (prev_index && (!prev_boxes || !prev_d)) return ST_ERR_INVALID_ARG;
     if (S == 0) return ST_OK;
-    ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 2, (cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 4, st));
     const int list_cap = S * cap;
-    k3_box_depth<<<dim3((cap + kWarps - 1) / kWarps, S), kWarps * 32, 0, (cudaStream_t)stream>>>(
-        depth, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace, list_cap, prev_boxes, prev_index, prev_d);
-    static int sms = 0;
+    // one-time setup: SM count, shared-memory opt-ins, resident grid of the warp kernel, and an
+    // auxiliary stream with a ring of events for the fork / join below (calls are serialised by
+    // the caller, see the header)
+    static int sms = 0, warp_ctas = 0, table_per_sm = 0;
+    // one auxiliary stream per caller stream (a shared one would order the large-box kernels of
+    // independent callers - the two K3 stages of the frame pipeline - behind each other)
+    constexpr int kMaxCallers = 16;
+    static cudaStream_t caller[kMaxCallers], aux_of[kMaxCallers];
+    static int n_callers = 0;
+    static cudaEvent_t ev_ring[64];
+    static unsigned ev_next = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -842,18 +826,45 @@ extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, con
                                         (int)(sizeof(float) * kHugeStage)));
         ST_CUDA_OK(cudaFuncSetAttribute(k3_box_depth_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)kTableSmem));
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_box_depth, kWarps * 32, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 8;
+        warp_ctas = sms * per_sm;
+        const char *e = getenv("ST_K3_TABLE_CTAS_PER_SM");
+        table_per_sm = e ? atoi(e) : 2;
+        for (int i = 0; i < 64; ++i) ST_CUDA_OK(cudaEventCreateWithFlags(&ev_ring[i], cudaEventDisableTiming));
     }
-    // persistent grids sized in multiples of the SM count, looping over the worklists:
-    // large boxes -> distinct-value table kernel; its overflow list -> staged radix select
-    static int table_per_sm = 0;
-    if (!table_per_sm) { const char *e = getenv("ST_K3_TABLE_CTAS_PER_SM"); table_per_sm = e ? atoi(e) : 2; }
+    cudaStream_t aux = nullptr;
+    for (int i = 0; i < n_callers; ++i)
+        if (caller[i] == st) aux = aux_of[i];
+    if (!aux) {
+        const int slot = n_callers < kMaxCallers ? n_callers++ : (int)(ev_next % kMaxCallers);   // recycle when full
+        if (aux_of[slot]) cudaStreamDestroy(aux_of[slot]);     // static storage: null until first used
+        ST_CUDA_OK(cudaStreamCreateWithFlags(&aux_of[slot], cudaStreamNonBlocking));
+        caller[slot] = st;
+        aux = aux_of[slot];
+    }
+    const long long slots = (long long)S * cap;
+    k3_classify<<<(int)((slots + 255) / 256), 256, 0, st>>>(S, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace,
+                                                           list_cap, prev_boxes, prev_index, prev_d);
+    // fork: the large boxes (table kernel, then its overflow list) on the auxiliary stream,
+    // the small boxes on the caller's stream; join before returning to the caller's order
+    cudaEvent_t ev_fork = ev_ring[ev_next++ & 63], ev_join = ev_ring[ev_next++ & 63];
+    ST_CUDA_OK(cudaEventRecord(ev_fork, st));
+    ST_CUDA_OK(cudaStreamWaitEvent(aux, ev_fork, 0));
     long long tgrid = (long long)sms * table_per_sm;
     if (tgrid > list_cap) tgrid = list_cap;
-    k3_box_depth_table<<<(int)tgrid, kTableThreads, kTableSmem, (cudaStream_t)stream>>>(
+    k3_box_depth_table<<<(int)tgrid, kTableThreads, kTableSmem, aux>>>(
         depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap);
-    k3_box_depth_cta<kHugeThreads, kHugeStage><<<sms, kHugeThreads, sizeof(float) * kHugeStage,
-                                                 (cudaStream_t)stream>>>(
-        depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace + 1, workspace + 2 + 2 * list_cap);
+    k3_box_depth_cta<kHugeThreads, kHugeStage><<<sms, kHugeThreads, sizeof(float) * kHugeStage, aux>>>(
+        depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace + 1, workspace + 4 + 2 * list_cap);
+    ST_CUDA_OK(cudaEventRecord(ev_join, aux));
+    {
+        long long grid = (slots + kWarps - 1) / kWarps;
+        if (grid > warp_ctas) grid = warp_ctas;
+        k3_box_depth<<<(int)grid, kWarps * 32, 0, st>>>(depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap);
+    }
+    ST_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
     return st_last_launch();
 }
 
