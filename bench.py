@@ -435,6 +435,9 @@ def main():
             host_issue_ms_per_step=issue_ms / K,
             k4_phase_cycles_median=dict(zip(['filter_predict', 'stage1', 'stage2', 'stage3', 'smooth_order', 'update'],
                                             [int(x) for x in np.median(dbg[:, 8:14], axis=0)])),
+            k4_phase_cycles_slowest_sequence=dict(zip(
+                ['filter_predict', 'stage1', 'stage2', 'stage3', 'smooth_order', 'update'],
+                [int(x) for x in dbg[int(np.argmax(dbg[:, 8:14].sum(1))), 8:14]])),
             assignments=dict(solved=int(dbg[:, 5].sum()), exact_fallback=int(dbg[:, 6].sum()),
                              last_search_cycles_median=int(np.median(dbg[:, 14])),
                              last_certificate_cycles_median=int(np.median(dbg[:, 15]))), status_bits=int(status.max()), tracked_rows_last_step=tracked_rows,

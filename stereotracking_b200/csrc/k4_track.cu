@@ -485,19 +485,23 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
                 last[k] = st.last_obs[g * 4 + k];
                 shift[k] = __fdiv_rn(__fsub_rn(dv.boxes[i * 4 + k], last[k]), denom);
             }
-            if (st.has_saved[g]) {
-                for (int e = lane; e < 64; e += 32) st.cov[g * 64 + e] = st.saved_cov[g * 64 + e];
-                if (lane < 8) st.mean[g * 8 + lane] = st.saved_mean[g * 8 + lane];
-            }
-            __syncwarp();
+            // The chain of `miss` virtual updates runs on the register-resident filter: state
+            // loaded once, stored once (it was a global load + store of the 8x8 covariance per
+            // virtual update: 90k cycles for a track lost for 29 frames, the longest path of the
+            // whole kernel).  The four 8-lane groups of the warp compute the same track.
+            const int gl = lane & 7;
+            const bool saved = st.has_saved[g] != 0;
+            stkf::Row8 row = stkf::load8(saved ? st.saved_mean + g * 8 : st.mean + g * 8,
+                                         saved ? st.saved_cov + g * 64 : st.cov + g * 64, gl, true);
             for (int t = 0; t < miss; ++t) {
                 float vb[4], zc[4];
                 double z[4];
                 for (int k = 0; k < 4; ++k) vb[k] = __fadd_rn(last[k], __fmul_rn((float)(t + 1), shift[k]));
                 stkf::xyxy_to_cxcyah(vb, zc);
                 for (int k = 0; k < 4; ++k) z[k] = (double)zc[k];
-                stkf::update(st.mean + g * 8, st.cov + g * 64, z, kfws);
+                stkf::update8(row, z, gl);
             }
+            stkf::store8(row, st.mean + g * 8, st.cov + g * 64, gl, lane < 8);
         }
         __syncthreads();
         if (threadIdx.x == 0) st.debug[s * 16 + 7] = 9;
