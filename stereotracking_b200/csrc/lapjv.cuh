@@ -739,7 +739,10 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     }
     __syncwarp();
     // diagnostics (debug words 14 / 15): cycles of the search and of the certificate, last call
-    if (P.dbg && lane == 0) { P.dbg[14] = (int)(t_h1 - t_h0); P.dbg[15] = (int)(clock64() - t_h1); }
+    if (P.dbg && lane == 0 && P.dbg[0] == 1) {          // stage 1 of the track step only
+        P.dbg[14] = (int)(t_h1 - t_h0); P.dbg[15] = (int)(clock64() - t_h1);
+        P.dbg[3] = n_active; P.dbg[4] = R * 1000 + C;
+    }
     // ---- publish in solve_warp's layout: y = col -> row, x = row -> col -------------------
     // (p aliases s.x and way aliases s.y, so go through registers)
     int colrow[16];                                   // m <= 512 per lane stride 32
