@@ -441,8 +441,9 @@ def main():
             assignments=dict(solved=int(dbg[:, 5].sum()), exact_fallback=int(dbg[:, 6].sum()),
                              stage1_search_cycles_median=int(np.median(dbg[:, 14])),
                              stage1_certificate_cycles_median=int(np.median(dbg[:, 15])),
-                             stage1_slowest=dict(zip(['active_rows', 'rows_x1000_plus_cols', 'search_cycles', 'certificate_cycles'],
-                                                     [int(v) for v in dbg[int(np.argmax(dbg[:, 9])), [3, 4, 14, 15]]]))), status_bits=int(status.max()), tracked_rows_last_step=tracked_rows,
+                             stage1_slowest=dict(zip(['active_rows', 'rows_x1000_plus_cols', 'search_cycles', 'certificate_cycles',
+                                                      'cert_scan', 'cert_reach', 'cert_cycle', 'arcs'],
+                                                     [int(v) for v in dbg[int(np.argmax(dbg[:, 9])), [3, 4, 14, 15, 16, 17, 18, 19]]]))), status_bits=int(status.max()), tracked_rows_last_step=tracked_rows,
             gathered_rows_all_ranks=int(len(gathered)), numa_rank0=numa)
         print(json.dumps(line))
     if world > 1:

@@ -90,11 +90,12 @@ int st_destroy(st_handle *h);
 int st_reset(st_handle *h, const uint8_t *seq_mask, void *stream);
 int st_read_status(st_handle *h, int32_t *status_host, int S);   /* synchronises */
 int st_clear_status(st_handle *h, void *stream);
-/* Diagnostics: 16 words per sequence written by st_track_step: 0-2 stage / rows / columns of
+/* Diagnostics: 32 words per sequence written by st_track_step: 0-2 stage / rows / columns of
  * the last association, 3-4 active rows and rows*1000+columns of the last stage-1 fast solve,
  * 5 assignments solved, 6 solved by the exact fallback, 7 phase, 8-13 SM cycles of the last
  * step per phase (filter+predict, stage 1, 2, 3, smoothing+ordering, update), 14-15 cycles of
- * the search and of the uniqueness certificate of the last stage-1 solve.  Copied on a side
+ * the search and of the uniqueness certificate of the last stage-1 solve, 16-19 cycles of the
+ * certificate's edge scan / reach rounds / cycle rounds and its arc count.  Copied on a side
  * stream, so it can be called while a step is still running. */
 int st_read_debug(st_handle *h, int32_t *debug_host, int S);
 /* Diagnostics: disable parts of st_track_step (bit0..2 assignment of stage 1..3,

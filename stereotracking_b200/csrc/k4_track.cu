@@ -264,7 +264,7 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
     } else if (threadIdx.x < 32) {
         stlap::Problem P;
         P.cost = cost; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
-        P.dbg = st.debug + (sbase / pr.T) * 16;
+        P.dbg = st.debug + (sbase / pr.T) * ST_DEBUG_WORDS;
         P.row_cnt = sm.row_cnt; P.col_cnt = sm.col_cnt; P.row_adm = sm.row_adm; P.adm_misc = sm.adm_misc;
         P.mark(0, stage_code); P.mark(1, R); P.mark(2, C);
         // debug words 5/6: assignments solved / solved by the exact fallback (this handle's lifetime)
@@ -305,7 +305,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
     do {                                                                      \
         if (threadIdx.x == 0) {                                               \
             const long long t_now = clock64();                                \
-            st.debug[s * 16 + (idx)] = (int)(t_now - t_prev);                 \
+            st.debug[s * ST_DEBUG_WORDS + (idx)] = (int)(t_now - t_prev);                 \
             t_prev = t_now;                                                   \
         }                                                                     \
     } while (0)
@@ -471,7 +471,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             if (slot >= 0 && sm.det_stage[i] == 3) sm.slot_hit[sm.slot_pos[slot]] = 1;
         }
         __syncthreads();
-        if (threadIdx.x == 0) st.debug[s * 16 + 7] = 8;
+        if (threadIdx.x == 0) st.debug[s * ST_DEBUG_WORDS + 7] = 8;
         // ---- online smoothing of re-found lost tracks (:571-577, :319-343)
         for (int i = warp; i < nd_in; i += kWarps) {
             const int slot = sm.det_slot[i];
@@ -504,7 +504,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             stkf::store8(row, st.mean + g * 8, st.cov + g * 64, gl, lane < 8);
         }
         __syncthreads();
-        if (threadIdx.x == 0) st.debug[s * 16 + 7] = 9;
+        if (threadIdx.x == 0) st.debug[s * ST_DEBUG_WORDS + 7] = 9;
         // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582)
         for (int p = threadIdx.x; p < n_live; p += kThreads)
             if (!sm.slot_hit[p]) {
@@ -529,7 +529,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         n_out = sh_cnt[0];
     }
 
-    if (threadIdx.x == 0) st.debug[s * 16 + 7] = 10;
+    if (threadIdx.x == 0) st.debug[s * ST_DEBUG_WORDS + 7] = 10;
     ST_PHASE(12);
     // ---- ids + BaseTracker.update (:598-605, base_tracker.py:54-91) ------------
     // new tracks are exactly the outputs without a slot; they are last in order
@@ -624,7 +624,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) st.debug[s * 16 + 7] = 11;
+    if (threadIdx.x == 0) st.debug[s * ST_DEBUG_WORDS + 7] = 11;
     ST_PHASE(13);
     // ---- pop_invalid_tracks (kalman_tracker_base.py:77-88) -------------------------
     const int n_now = n_live + n_create;
@@ -655,7 +655,7 @@ k4_track_step(TrackState st, Params pr, const int32_t *__restrict__ frame_ids,
             st.n_free[s] = n_free - n_create + freed;
             st.next_id[s] = id0 + n_new;
             out_counts[s] = n_out;
-            st.debug[s * 16 + 7] = 12;
+            st.debug[s * ST_DEBUG_WORDS + 7] = 12;
         }
     }
 }
@@ -738,7 +738,7 @@ size_t layout(st_handle *h, unsigned char *base) {
     unsigned char *c = base;
     TrackState &st = h->st;
     take(st.n_live, c, S); take(st.next_id, c, S); take(st.order, c, S * T); take(st.free_slots, c, S * T);
-    take(st.n_free, c, S); take(st.status, c, S); take(st.debug, c, S * 16);
+    take(st.n_free, c, S); take(st.status, c, S); take(st.debug, c, S * ST_DEBUG_WORDS);
     take(st.id, c, S * T); take(st.hits, c, S * T); take(st.last_frame, c, S * T);
     take(st.tentative, c, S * T); take(st.tracked, c, S * T); take(st.has_saved, c, S * T);
     take(st.mean, c, S * T * 8); take(st.cov, c, S * T * 64);
@@ -834,7 +834,7 @@ extern "C" int st_read_debug(st_handle *h, int32_t *debug_host, int S) {
     // a side stream so that the words can be read while a kernel is still running
     cudaStream_t side;
     ST_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    cudaError_t e = cudaMemcpyAsync(debug_host, h->st.debug, sizeof(int32_t) * 16 * S, cudaMemcpyDeviceToHost, side);
+    cudaError_t e = cudaMemcpyAsync(debug_host, h->st.debug, sizeof(int32_t) * ST_DEBUG_WORDS * S, cudaMemcpyDeviceToHost, side);
     if (e == cudaSuccess) e = cudaStreamSynchronize(side);
     cudaStreamDestroy(side);
     return e == cudaSuccess ? ST_OK : ST_ERR_CUDA;

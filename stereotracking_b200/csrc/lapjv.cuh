@@ -671,33 +671,91 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     // admissible entries has u = L/2 and an isolated pair keeps u = a_ij < L/2, so every other
     // entry of such a row has slack >= (cost - L) > eps (no cost lies within 2e-9 of L:
     // adm_misc[1], checked above).  The real edges of the active rows, then one dummy edge per row:
-    const int real_edges = n_active * C, total_edges = real_edges + R;
-    for (int e0 = 0; e0 < total_edges; e0 += 32) {
-        const int e = e0 + lane;
+    // one active row per lane, all lanes stepping through the columns together.  The test runs
+    // in float32 first (dependent float64 operations cost ~50 cycles each on this part, and
+    // nearly every edge is far from tight): the float32 slack differs from the float64 one by
+    // < 1e-6, so only edges within 1e-4 are re-evaluated exactly.  The float32 copy of the
+    // column potentials sits behind the R row potentials in the (cols, pred) region (n doubles).
+    // (plain pointer: the __syncwarp() below orders the writes before the reads, and a volatile
+    // generic access to shared memory costs far more than an ordinary one)
+    float *vf = reinterpret_cast<float *>(const_cast<double *>(u + R));
+    for (int j = lane; j < C; j += 32) vf[j] = (float)v[j];
+    __syncwarp();
+    for (int t0 = 0; t0 < n_active; t0 += 32) {
+        const int t = t0 + lane;
+        const bool hv = t < n_active;
+        const int i = hv ? active[t] : 0;
+        const double ui = hv ? u[i] : 0.0;
+        const float hu = (float)(half + ui);
+        const int si = hv ? sigma[i] : -1;
+        const float *crow = P.cost + (long long)i * C;
+        for (int j = 0; j < C; ++j) {
+            bool tight = hv && j != si && (crow[j] - hu) - vf[j] <= 1.0e-4f;
+            if (tight) tight = ((double)crow[j] - half) - ui - v[j] <= kFastEps;
+            const unsigned tb = __ballot_sync(0xffffffffu, tight);
+            if (tb == 0u) continue;
+            const int pos = n_arcs + __popc(tb & ((1u << lane) - 1u));
+            if (tight && pos < m) { arc_from[pos] = si; arc_to[pos] = j; }
+            n_arcs += __popc(tb);
+        }
+    }
+    for (int i0 = 0; i0 < R; i0 += 32) {               // the dummy edge of every matched row
+        const int i = i0 + lane;
         bool tight = false;
-        int from = 0, to = 0;
-        if (e < real_edges) {
-            const int t = e / C, j = e - t * C, i = active[t];
-            if (p[j] != i) {
-                const double slack = ((double)P.cost[(long long)i * C + j] - half) - u[i] - v[j];
-                tight = slack <= kFastEps;
-                from = sigma[i]; to = j;
-            }
-        } else if (e < total_edges) {
-            const int i = e - real_edges;
-            if (sigma[i] != C + i) {
-                tight = half - u[i] - v[C + i] <= kFastEps;
-                from = sigma[i]; to = C + i;
-            }
+        int from = 0;
+        if (i < R) {
+            from = sigma[i];
+            if (from != C + i) tight = half - u[i] - v[C + i] <= kFastEps;
         }
         const unsigned tb = __ballot_sync(0xffffffffu, tight);
         const int pos = n_arcs + __popc(tb & ((1u << lane) - 1u));
-        if (tight && pos < m) { arc_from[pos] = from; arc_to[pos] = to; }
+        if (tight && pos < m) { arc_from[pos] = from; arc_to[pos] = C + i; }
         n_arcs += __popc(tb);
     }
     if (n_arcs > m) return false;                       // more tight edges than the list holds
     __syncwarp();
-    if (n_arcs > 0) {
+    const long long t_c1 = clock64();
+    long long t_c2 = t_c1;
+    if (n_arcs > 0 && n_arcs <= 32) {
+        // few arcs (the usual case): one arc per lane, fixpoints by shuffles, no shared memory.
+        // `from` is always an assigned column (sigma of a row); only columns that occur in arcs matter.
+        __syncwarp();
+        const bool have = lane < n_arcs;
+        const int from = have ? arc_from[lane] : -1, to = have ? arc_to[lane] : -2;
+        bool to_assigned = false, from_vac = false;
+        if (have) {
+            to_assigned = to < C ? p[to] >= 0 : sigma[to - C] == to;
+            from_vac = v[from] >= -kFastEps;                     // may be vacated at no cost
+        }
+        // (1) a free column reachable from a vacatable one
+        bool reach = have && !to_assigned;
+        for (int round = 0; round <= n_arcs; ++round) {
+            bool changed = false;
+            for (int k = 0; k < n_arcs; ++k) {
+                const int f = __shfl_sync(0xffffffffu, from, k);
+                const bool r = __shfl_sync(0xffffffffu, (int)reach, k) != 0;
+                if (have && !reach && r && f == to) { reach = true; changed = true; }
+            }
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        t_c2 = clock64();
+        bool unsure = reach && from_vac;
+        // (2) a directed cycle: an arc stays alive while its head has an alive outgoing arc
+        bool alive = have && to_assigned;
+        for (int round = 0; round <= n_arcs; ++round) {
+            bool has_next = false;
+            for (int k = 0; k < n_arcs; ++k) {
+                const int f = __shfl_sync(0xffffffffu, from, k);
+                const bool al = __shfl_sync(0xffffffffu, (int)alive, k) != 0;
+                has_next |= al && f == to;
+            }
+            const bool drop = alive && !has_next;
+            if (drop) alive = false;
+            if (!__any_sync(0xffffffffu, drop)) break;
+        }
+        unsure |= alive;
+        if (__any_sync(0xffffffffu, unsure)) return false;
+    } else if (n_arcs > 0) {
         // column flags live where the row potentials were (no longer needed)
         volatile unsigned char *assigned = reinterpret_cast<volatile unsigned char *>(s.cols);
         volatile unsigned char *reach = assigned + m, *alive = assigned + 2 * m, *has_out = assigned + 3 * m;
@@ -717,6 +775,7 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
             __syncwarp();
             if (!__any_sync(0xffffffffu, changed)) break;
         }
+        t_c2 = clock64();
         bool unsure = false;
         cnt = 0;
         for (int j = lane; j < m; j += 32, ++cnt)
@@ -741,6 +800,8 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     // diagnostics (debug words 14 / 15): cycles of the search and of the certificate, last call
     if (P.dbg && lane == 0 && P.dbg[0] == 1) {          // stage 1 of the track step only
         P.dbg[14] = (int)(t_h1 - t_h0); P.dbg[15] = (int)(clock64() - t_h1);
+        P.dbg[16] = (int)(t_c1 - t_h1); P.dbg[17] = (int)(t_c2 - t_c1); P.dbg[18] = (int)(clock64() - t_c2);
+        P.dbg[19] = n_arcs;
         P.dbg[3] = n_active; P.dbg[4] = R * 1000 + C;
     }
     // ---- publish in solve_warp's layout: y = col -> row, x = row -> col -------------------

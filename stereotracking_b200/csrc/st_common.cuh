@@ -8,6 +8,7 @@
 
 #define ST_RING 16            // observation ring capacity (vel_delta_t <= 15)
 #define ST_MAX_LEVELS 8
+#define ST_DEBUG_WORDS 32     // diagnostic words per sequence (st_read_debug)
 
 #define ST_CUDA_OK(expr)                              \
     do {                                              \
@@ -32,7 +33,7 @@ struct TrackState {
     int32_t *free_slots;    // [S, T] stack of unused slots
     int32_t *n_free;        // [S]
     int32_t *status;        // [S] sticky ST_STATUS_* bits
-    int32_t *debug;         // [S, 8] progress words of the last track step (diagnostics)
+    int32_t *debug;         // [S, ST_DEBUG_WORDS] diagnostics of the last track step (st_read_debug)
     // per slot
     int64_t *id;            // [S*T]
     int32_t *hits;          // len(track.bboxes)

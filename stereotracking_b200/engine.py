@@ -352,10 +352,10 @@ class StereoTrackEngine:
         _lib.check(self.lib.st_kalman_batch(op, n, _ptr(mean), _ptr(cov), _ptr(z), self._stream()))
 
     def debug_words(self):
-        """[S,16] diagnostic words: 5 = assignments solved, 6 = solved by the exact
+        """[S,32] diagnostic words: 5 = assignments solved, 6 = solved by the exact
         fallback, 8..13 = SM cycles of the last track step per phase."""
         import numpy as np
-        a = np.zeros((self.cfg.n_seq, 16), np.int32)
+        a = np.zeros((self.cfg.n_seq, 32), np.int32)
         _lib.check(self.lib.st_read_debug(self._h, a.ctypes.data_as(C.c_void_p), self.cfg.n_seq))
         return a
 
