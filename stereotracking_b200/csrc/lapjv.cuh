@@ -681,6 +681,28 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     float *vf = reinterpret_cast<float *>(const_cast<double *>(u + R));
     for (int j = lane; j < C; j += 32) vf[j] = (float)v[j];
     __syncwarp();
+    // Two traversals of the same edge set: with few active rows, row by row with the lanes over
+    // the columns (cost ~ rows x ceil(C / 32) steps); with many, one row per lane and all lanes
+    // stepping through the columns together (cost ~ C steps per 32 rows).
+    if (n_active * ((C + 31) / 32) * 2 < C) {
+        for (int t = 0; t < n_active; ++t) {
+            const int i = active[t];
+            const double ui = u[i];
+            const float hu = (float)(half + ui);
+            const int si = sigma[i];
+            const float *crow = P.cost + (long long)i * C;
+            for (int j0 = 0; j0 < C; j0 += 32) {
+                const int j = j0 + lane;
+                bool tight = j < C && j != si && (crow[j] - hu) - vf[j] <= 1.0e-4f;
+                if (tight) tight = ((double)crow[j] - half) - ui - v[j] <= kFastEps;
+                const unsigned tb = __ballot_sync(0xffffffffu, tight);
+                if (tb == 0u) continue;
+                const int pos = n_arcs + __popc(tb & ((1u << lane) - 1u));
+                if (tight && pos < m) { arc_from[pos] = si; arc_to[pos] = j; }
+                n_arcs += __popc(tb);
+            }
+        }
+    } else
     for (int t0 = 0; t0 < n_active; t0 += 32) {
         const int t = t0 + lane;
         const bool hv = t < n_active;
