@@ -711,14 +711,29 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
         const float hu = (float)(half + ui);
         const int si = hv ? sigma[i] : -1;
         const float *crow = P.cost + (long long)i * C;
-        for (int j = 0; j < C; ++j) {
-            bool tight = hv && j != si && (crow[j] - hu) - vf[j] <= 1.0e-4f;
-            if (tight) tight = ((double)crow[j] - half) - ui - v[j] <= kFastEps;
-            const unsigned tb = __ballot_sync(0xffffffffu, tight);
-            if (tb == 0u) continue;
-            const int pos = n_arcs + __popc(tb & ((1u << lane) - 1u));
-            if (tight && pos < m) { arc_from[pos] = si; arc_to[pos] = j; }
-            n_arcs += __popc(tb);
+        // four columns per step: one vote decides whether any of them needs a closer look (the
+        // loop-carried vote + branch, not the loads, set the pace of a one-column step)
+        for (int j4 = 0; j4 < C; j4 += 4) {
+            bool near[4];
+            bool any_near = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j4 + q;
+                near[q] = hv && j < C && j != si && (crow[j < C ? j : 0] - hu) - vf[j < C ? j : 0] <= 1.0e-4f;
+                any_near |= near[q];
+            }
+            if (!__any_sync(0xffffffffu, any_near)) continue;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j4 + q;
+                bool tight = near[q];
+                if (tight) tight = ((double)crow[j] - half) - ui - v[j] <= kFastEps;
+                const unsigned tb = __ballot_sync(0xffffffffu, tight);
+                if (tb == 0u) continue;
+                const int pos = n_arcs + __popc(tb & ((1u << lane) - 1u));
+                if (tight && pos < m) { arc_from[pos] = si; arc_to[pos] = j; }
+                n_arcs += __popc(tb);
+            }
         }
     }
     for (int i0 = 0; i0 < R; i0 += 32) {               // the dummy edge of every matched row
