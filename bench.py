@@ -233,7 +233,7 @@ def main():
     assert n_own == S
     raw, cls, box, obj = generate(cfg, S, F, 20240604 + 1000 + first_seq, dev)
     eng = StereoTrackEngine(EngineConfig(n_seq=S, max_dets=256, max_tracks=256, max_candidates=2048), device=dev)
-    io = eng.make_frame_io(raw.shape[1:], [c.shape[-2:] for c in cls])
+    eng.make_frame_io(raw.shape[1:], [c.shape[-2:] for c in cls])      # allocates eng.depth_map
     stream = torch.cuda.current_stream(dev)
     groups = LockstepGroups(S, args.groups, device=dev, depth=args.depth, max_dets=256, max_tracks=256,
                             max_candidates=2048)
@@ -251,23 +251,22 @@ def main():
                 # headline path: one C call per group queues the frame on the frame pipeline
                 groups.run_plan(f)
                 continue
+            # same launches, one C call per stage so that each stage can be bracketed by events
             eng.frame_ids.fill_(f)
-            if True:
-                # same launches, one C call per stage so that each stage can be bracketed by events
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
-                ev[0].record(stream)
-                eng.disp2depth(raw[f], out=eng.depth_map); ev[1].record(stream)
-                eng.decode_nms([c[f] for c in cls], [c[f] for c in box], [c[f] for c in obj],
-                               (cfg.height, cfg.width)); ev[2].record(stream)
-                eng.box_depth(eng.depth_map, eng.det_boxes, eng.det_counts, eng.det_depth, eng.det_scales,
-                              eng.det_inflated); ev[3].record(stream)
-                eng.track_step(eng.frame_ids, eng.det_inflated, eng.det_scores, eng.det_labels, eng.det_scales,
-                               eng.det_depth, eng.det_counts); ev[4].record(stream)
-                eng.scale_boxes(eng.trk_boxes, eng.out_scales, eng.out_counts, True, eng.out_boxes)
-                ev[5].record(stream)
-                eng.box_depth(eng.depth_map, eng.out_boxes, eng.out_counts, eng.out_depth, eng.out_scale2, None)
-                ev[6].record(stream)
-                events.append(ev)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            ev[0].record(stream)
+            eng.disp2depth(raw[f], out=eng.depth_map); ev[1].record(stream)
+            eng.decode_nms([c[f] for c in cls], [c[f] for c in box], [c[f] for c in obj],
+                           (cfg.height, cfg.width)); ev[2].record(stream)
+            eng.box_depth(eng.depth_map, eng.det_boxes, eng.det_counts, eng.det_depth, eng.det_scales,
+                          eng.det_inflated); ev[3].record(stream)
+            eng.track_step(eng.frame_ids, eng.det_inflated, eng.det_scores, eng.det_labels, eng.det_scales,
+                           eng.det_depth, eng.det_counts); ev[4].record(stream)
+            eng.scale_boxes(eng.trk_boxes, eng.out_scales, eng.out_counts, True, eng.out_boxes)
+            ev[5].record(stream)
+            eng.box_depth(eng.depth_map, eng.out_boxes, eng.out_counts, eng.out_depth, eng.out_scale2, None)
+            ev[6].record(stream)
+            events.append(ev)
 
     # ---- resident-input timing (value) -------------------------------------------
     run_steps(0, W)
