@@ -79,22 +79,27 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
-    def stop(self):
+    def stop(self, windows=None):
+        """Summary of the samples received inside the (t0, t1) perf_counter windows (the timed
+        regions; a sample is kept when it arrives up to 30 ms after a window closes)."""
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
+        rows = [r for t, r in self.rows if windows is None or any(a <= t <= b + 0.03 for a, b in windows)]
+        if not rows:                      # regions shorter than one sampling period: nearest samples
+            rows = [r for _, r in self.rows][-3:]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -278,13 +283,14 @@ def main():
     e0.record(stream)
     groups.fork(stream)                 # group streams start after e0 ...
     t_issue = time.perf_counter()
+    clock_windows = []
     run_steps(W, F)
     issue_ms = (time.perf_counter() - t_issue) * 1e3     # host time to issue the K steps (no sync inside)
     groups.join(stream)                 # ... and e1 is recorded after all of them finished
     e1.record(stream)
     barrier()
+    clock_windows.append((t_issue, time.perf_counter()))
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     status = groups.status()
     dbg = np.concatenate([e.debug_words() for e in groups.engines])
     tracked_rows = int(sum(len(r['instances_id']) for r in groups.results()))
@@ -377,6 +383,8 @@ def main():
     e2e_steps(W, F)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clock_windows.append((t0, t0 + e2e_s))
+    clocks = sampler.stop(clock_windows) if rank == 0 else None      # samples of both timed regions
 
     # ---- host-side gather of the last frame's tracks (outside every timed region) -------
     rows = shard.tracks_to_rows(groups.results(), F - 1, first_sequence=first_seq)
