@@ -603,6 +603,7 @@ k3_box_depth_cta(const float *__restrict__ depth, int Hp, int Wp, const float *_
 constexpr int kTableSlots = 4096;        // hash slots (power of two)
 constexpr int kMaxDistinct = 3072;       // distinct values accepted before overflow
 constexpr int kTableThreads = 512;
+constexpr int kTablePerThread = 8;      // pixel loads in flight per thread (the pass is latency-bound)
 constexpr size_t kTableSmem = sizeof(uint32_t) * kTableSlots * 2 + sizeof(uint32_t) * kMaxDistinct * 5;
 
 __global__ void __launch_bounds__(kTableThreads)
@@ -653,10 +654,10 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
             for (int i = threadIdx.x; i < kTableSlots; i += kTableThreads) { keys[i] = 0u; cnts[i] = 0; }
             if (threadIdx.x == 0) { n_distinct = 0; n_dense = 0; overflow = 0; n_valid_sh = 0; }
             __syncthreads();
-            for (unsigned i0 = threadIdx.x; i0 < npix; i0 += 4 * kTableThreads) {
-                float v[4];
+            for (unsigned i0 = threadIdx.x; i0 < npix; i0 += kTablePerThread * kTableThreads) {
+                float v[kTablePerThread];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {           // four independent loads in flight
+                for (int u = 0; u < kTablePerThread; ++u) {   // independent loads in flight
                     const unsigned i = i0 + u * kTableThreads;
                     v[u] = -1.f;
                     if (i < npix) {
@@ -665,7 +666,7 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kTablePerThread; ++u) {
                     const bool ok = depth_valid(v[u]);
                     const uint32_t key = ok ? __float_as_uint(v[u]) : 0u;     // valid depths are > 0: bits != 0
                     const unsigned act = __activemask();
