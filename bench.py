@@ -405,7 +405,7 @@ def main():
         k1_bytes = S * (2 * cfg.height * cfg.width + 4 * Hp * Wp)          # u16 read + f32 depth write
         k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
         P = cfg.num_priors
-        k2_bytes = S * P * 8                                               # cls + obj logits of every prior
+        k2_bytes = S * P * 4                                               # objectness logit of every prior (class logits lazily)
         kernels = {n: dict(ms=float(stage_avg[i]), share=float(stage_avg[i] / stage_avg.sum()))
                    for i, n in enumerate(names)}
         kernels['k1_disp2depth'].update(algorithmic_bytes=k1_bytes, ms_back_to_back=k1_ms, achieved_gbs=k1_gbs,
