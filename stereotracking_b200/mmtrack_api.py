@@ -174,18 +174,22 @@ class OCSORTTracker_Disparity:
 
     # ---- track() (:345-618) -----------------------------------------------------
     def track(self, model, img, feats, data_sample, data_preprocessor=None, rescale=False, **kwargs):
-        eng = self._engine
         det = data_sample.pred_det_instances
-        frame_id = data_sample.metainfo.get('frame_id', -1)
-        n = int(det.bboxes.shape[0])
+        return self._track(img, data_sample.metainfo, det.bboxes, det.scores, det.labels, det.scales, det.depth)
+
+    def _track(self, img, metainfo, bboxes, scores, labels, scales, depth):
+        """One frame given the pred_det_instances fields as tensors (any device)."""
+        eng = self._engine
+        frame_id = metainfo.get('frame_id', -1)
+        n = int(bboxes.shape[0])
         if n > eng.cfg.max_dets:
             raise ValueError(f'{n} detections exceed max_dets={eng.cfg.max_dets}')
         dev = eng.device
-        eng.det_inflated[0, :n] = det.bboxes.to(dev, torch.float32)
-        eng.det_scores[0, :n] = det.scores.to(dev, torch.float32)
-        eng.det_labels[0, :n] = det.labels.to(dev, torch.int64)
-        eng.det_scales[0, :n] = det.scales.to(dev, torch.float32)
-        eng.det_depth[0, :n] = det.depth.to(dev, torch.float32)
+        eng.det_inflated[0, :n] = bboxes.to(dev, torch.float32)
+        eng.det_scores[0, :n] = scores.to(dev, torch.float32)
+        eng.det_labels[0, :n] = labels.to(dev, torch.int64)
+        eng.det_scales[0, :n] = scales.to(dev, torch.float32)
+        eng.det_depth[0, :n] = depth.to(dev, torch.float32)
         eng.det_counts.fill_(n)
         eng.frame_ids.fill_(int(frame_id))
         warp = None
@@ -193,7 +197,7 @@ class OCSORTTracker_Disparity:
             self.reset_cmc()                                                   # :385-387
         if self.with_cmc:
             # the reference estimates only in the association branch (:391, :428-429)
-            w = self.estimate_camera_motion(img, data_sample.metainfo) if (n > 0 and not self.empty) else None
+            w = self.estimate_camera_motion(img, metainfo) if (n > 0 and not self.empty) else None
             warp = torch.full((1, 6), float('nan'), dtype=torch.float32, device=dev)
             if w is not None:
                 warp[0] = torch.as_tensor(w, dtype=torch.float32).reshape(6).to(dev)
@@ -203,7 +207,7 @@ class OCSORTTracker_Disparity:
         status = int(eng.status()[0])
         if status:
             raise _lib.StereoTrackError(f'tracker capacity exceeded (status bits {status}); raise max_tracks / max_dets')
-        tgt = det.bboxes.device
+        tgt = bboxes.device
         res = InstanceData()
         res.bboxes = out['bboxes'][0, :m].clone().to(tgt)
         res.labels = out['labels'][0, :m].clone().to(tgt)
@@ -222,11 +226,10 @@ class OCSORTTracker(OCSORTTracker_Disparity):
     with scales = 1 and depth = 0 and returns bboxes / labels / scores / instances_id."""
 
     def track(self, model, img, feats, data_sample, data_preprocessor=None, rescale=False, **kwargs):
-        det = data_sample.pred_det_instances
+        det = data_sample.pred_det_instances                 # left untouched: no scales / depth fields here
         n = int(det.bboxes.shape[0])
-        det.scales = torch.ones(n, dtype=torch.float32, device=det.bboxes.device)
-        det.depth = torch.zeros(n, dtype=torch.float32, device=det.bboxes.device)
-        full = super().track(model, img, feats, data_sample, data_preprocessor, rescale, **kwargs)
+        ones = torch.ones(n, dtype=torch.float32, device=det.bboxes.device)
+        full = self._track(img, data_sample.metainfo, det.bboxes, det.scores, det.labels, ones, torch.zeros_like(ones))
         res = InstanceData()
         res.bboxes, res.labels, res.scores, res.instances_id = full.bboxes, full.labels, full.scores, full.instances_id
         return res
