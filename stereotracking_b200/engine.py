@@ -413,7 +413,12 @@ class FramePipeline:
             k['cls'][l] = cls_ptrs[l]
             k['bbox'][l] = bbox_ptrs[l]
             k['obj'][l] = obj_ptrs[l]
-        ev = lambda e: C.c_void_p(0 if e is None else e.cuda_event)
+        def ev(e):
+            if e is None:
+                return C.c_void_p(0)
+            if not e.cuda_event:          # torch creates the CUDA event lazily at its first record
+                e.record(torch.cuda.current_stream(self.engine.device))
+            return C.c_void_p(e.cuda_event)
         _lib.check(self.engine.lib.st_pipeline_submit(self._p, self.n_seq, C.byref(io), ev(ready_event),
                                                       ev(done_event)), 'st_pipeline_submit')
         self.submitted += 1
