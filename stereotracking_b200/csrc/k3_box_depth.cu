@@ -1,18 +1,23 @@
-// K3: per-box depth statistic + depth-driven box scale, one WARP per box.
+// K3: per-box depth statistic + depth-driven box scale.
 // Replaces OCSORT_Disparity.extract_depth / bbox_postp_depth
 // (mmtrack/models/mot/ocsort_disparity.py:113-130,:136-175) and scale_bbox
 // (mmtrack/models/trackers/utils.py:58-73).
 //
 // The reference sorts the valid depths of the box and averages a 60 % window of
-// the sorted list whose position is voted by the four box corners.  Here the
-// three order statistics that define the result (median, first and last element
-// of the window) are found with an MSB-first radix select over the float bit
-// patterns using per-warp shared-memory histograms (8 bits per pass); the
-// window sum is then one masked pass (values strictly between the two boundary
-// values, plus the boundary values weighted by how many of their duplicates
-// fall inside the window).  Boxes are small (airborne objects), so a warp per
-// box with the valid depths staged in shared memory keeps every pass on-chip;
-// boxes with more valid pixels than the stage re-read the map (L1/L2).
+// the sorted list whose position is voted by the four box corners.  Kernels:
+//   k3_classify         one thread per box slot: rows that may reuse an earlier statistic
+//                       are finished, the rest go to a dense small-box or large-box list
+//   k3_box_depth        one WARP per box of <= 512 pixels (airborne objects are small): valid
+//                       depths staged in shared memory; the three order statistics that define
+//                       the result (median, first and last element of the window) by an
+//                       MSB-first bit-wise select (one pass + one REDUX per bit); the window sum
+//                       as one masked pass with the boundary duplicates weighted exactly
+//   k3_box_depth_table  one CTA per larger box, on an auxiliary stream beside the warp kernel:
+//                       shared-memory hash table of the DISTINCT depth values with their
+//                       multiplicities, ranked; order statistics and window sum from the
+//                       sorted multiset
+//   k3_box_depth_cta    overflow of the table (> 3072 distinct values): staged radix select
+//                       with shared-memory histograms, 8 bits per pass
 #include <cstdlib>
 #include "st_common.cuh"
 
