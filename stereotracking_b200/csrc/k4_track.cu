@@ -1,6 +1,7 @@
 // K4 + K5: one frame of the OC-SORT tracker with depth-scaled boxes for S
 // sequences in lockstep, one CTA per sequence, the whole frame in one launch:
-//   detection filter -> Kalman predict of confirmed tracks (one warp per track)
+//   detection filter -> Kalman predict of confirmed tracks (8-lane groups, four tracks per
+//   warp, state in registers) -> optional camera-motion compensation
 //   -> OCM cost (1 - IoU + velocity-direction term) -> LAPJV  (stage 1)
 //   -> tentative tracks vs leftovers                           (stage 2)
 //   -> observation-centric recovery on last observations       (stage 3)
