@@ -846,7 +846,9 @@ extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, con
     if (!aux) {
         const int slot = n_callers < kMaxCallers ? n_callers++ : (int)(ev_next % kMaxCallers);   // recycle when full
         if (aux_of[slot]) cudaStreamDestroy(aux_of[slot]);     // static storage: null until first used
-        ST_CUDA_OK(cudaStreamCreateWithFlags(&aux_of[slot], cudaStreamNonBlocking));
+        int prio = 0;                                            // the auxiliary stream inherits the caller's priority
+        cudaStreamGetPriority(st, &prio);
+        ST_CUDA_OK(cudaStreamCreateWithPriority(&aux_of[slot], cudaStreamNonBlocking, prio));
         caller[slot] = st;
         aux = aux_of[slot];
     }
