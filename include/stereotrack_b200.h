@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ST_ABI_VERSION 4
+#define ST_ABI_VERSION 5
 
 enum {
     ST_OK = 0,
@@ -153,6 +153,24 @@ int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, const float *b
                        const int32_t *counts, int cap, float *d, float *scale, float *inflated,
                        int32_t *workspace, const float *prev_boxes, const int32_t *prev_index,
                        const float *prev_d, void *stream);
+
+/* The ablation reducers of mmtrack/models/mot/depth_extraction_comparison.py (decorators that
+ * replace extract_depth in comparison runs): same patch, validity filter and -1 rule, another
+ * statistic, scale = clip(d*d/400, 1, 3).  ST_DEPTH_WINDOW is st_box_depth (scale = clip(d*d, 1, 3)).
+ * ST_DEPTH_CENTER reads the unfiltered map at the integer box centre with NumPy indexing; where
+ * the reference raises IndexError (:141, centre outside the map) d = NaN, scale = 1 and oob[s]
+ * (may be NULL; [S] i32, zeroed by the call) counts such boxes of sequence s.  `workspace` is
+ * only used by ST_DEPTH_WINDOW (may be NULL otherwise). */
+enum st_depth_mode {
+    ST_DEPTH_WINDOW = 0,          /* ocsort_disparity.py:136-175 */
+    ST_DEPTH_TRUNCATED_MEAN = 1,  /* depth_extraction_comparison.py:5-46 */
+    ST_DEPTH_MEAN = 2,            /* :49-80 */
+    ST_DEPTH_MEDIAN = 3,          /* :83-115 */
+    ST_DEPTH_CENTER = 4           /* :117-150 */
+};
+int st_box_depth_mode(const float *depth, int S, int Hp, int Wp, const float *boxes,
+                      const int32_t *counts, int cap, int mode, float *d, float *scale,
+                      float *inflated, int32_t *oob, int32_t *workspace, void *stream);
 
 /* scale_bbox(boxes, 1/scales) (ocsort_disparity.py:96-97) or scale_bbox(boxes,
  * scales) when invert == 0. */

@@ -85,6 +85,61 @@ def extract_depth(depth, bboxes):
             np.asarray(scales, np.float32).reshape(-1))
 
 
+# --- ablation reducers (mmtrack/models/mot/depth_extraction_comparison.py) -----------------
+ABLATION_MODES = ('truncated_mean', 'mean', 'median', 'center')
+ABLATION_SCALE_DIV = 400     # depth_extraction_comparison.py:41,:75,:110,:145
+
+
+def box_depth_ablation(depth, box, mode):
+    """One box of the decorators truncated_mean (:5-46), mean (:49-80), median (:83-115)
+    and center (:117-150).  Same patch, validity filter and ``-1`` rule as extract_depth;
+    the statistic differs and the scale is ``clip(d*d/400, 1, 3)``.  ``center`` reads the
+    unfiltered map at the integer box centre with NumPy indexing (negative indices wrap,
+    out of range raises IndexError as in the reference)."""
+    bi = trunc_box(box)
+    with np.errstate(over='ignore'):
+        w = int(bi[2] - bi[0])
+        cx = int((bi[0] + bi[2]) // 2)
+        cy = int((bi[1] + bi[3]) // 2)
+    b = [int(v) for v in bi]
+    patch = depth[b[1]:b[3], b[0]:b[2]]
+    vals = patch[(patch < MAX_DEPTH) & (patch > 0)]
+    n = int(vals.size)
+    if n < 1 or w > MAX_BOX_W:
+        return -1, 1.0
+    if mode == 'truncated_mean':
+        srt = np.sort(vals, axis=None)
+        seg = srt[int(0.1 * n):int((1 - 0.1) * n)]
+        if seg.size == 0:
+            seg = srt[:-1]
+        d = _mean_f32(seg)
+    elif mode == 'mean':
+        d = _mean_f32(vals)
+    elif mode == 'median':
+        d = np.float32(np.median(vals))
+    elif mode == 'center':
+        d = depth[cy, cx]
+    else:
+        raise ValueError(f'unknown depth reducer {mode!r}')
+    with np.errstate(over='ignore'):
+        dd = float(np.float32(d * d)) / ABLATION_SCALE_DIV
+    scale = min(dd, 3.0)
+    scale = max(scale, 1.0)
+    return d, scale
+
+
+def extract_depth_ablation(depth, bboxes, mode):
+    """The decorated ``extract_depth`` over all boxes: (d_values f32, scales f32)."""
+    depth = np.asarray(depth, np.float32)
+    d_vals, scales = [], []
+    for box in np.asarray(bboxes, np.float32).reshape(-1, 4):
+        d, s = box_depth_ablation(depth, box, mode)
+        d_vals.append(d)
+        scales.append(s)
+    return (np.asarray(d_vals, np.float32).reshape(-1),
+            np.asarray(scales, np.float32).reshape(-1))
+
+
 def scale_bbox(bboxes, scales):
     """trackers/utils.py:58-73 in float32."""
     b = np.asarray(bboxes, np.float32).reshape(-1, 4)

@@ -21,7 +21,10 @@ class StereoTrackOracle:
 
     def __init__(self, tracker_cfg=None, baseline=0.25, focal_length=640,
                  img_scale=None, size_divisor=32, score_thr=0.01, nms_iou=0.5,
-                 strides=(8, 16, 32)):
+                 strides=(8, 16, 32), depth_reducer=None):
+        # depth_reducer: None = extract_depth (:136-175); 'truncated_mean' | 'mean' | 'median' | 'center'
+        # = extract_depth decorated as in mmtrack/models/mot/depth_extraction_comparison.py
+        self.depth_reducer = depth_reducer
         self.tracker = OCSortDisparityOracle(**(self.DEFAULT_TRACKER if tracker_cfg is None else tracker_cfg))
         self.baseline, self.focal_length = baseline, focal_length
         self.img_scale, self.size_divisor = img_scale, size_divisor
@@ -39,12 +42,15 @@ class StereoTrackOracle:
     def step_from_dets(self, frame_id, depth, det_bboxes, det_scores, det_labels, warp=None):
         """ocsort_disparity.py:82-109 given the detector output (``warp``: the frame's
         camera-motion affine when cmc is configured, else None)."""
-        infl, scales, d = boxdepth.bbox_postp_depth(depth, det_bboxes)
+        extract = boxdepth.extract_depth if self.depth_reducer is None else (
+            lambda dm, bb: boxdepth.extract_depth_ablation(dm, bb, self.depth_reducer))
+        d, scales = extract(depth, det_bboxes)
+        infl = boxdepth.scale_bbox(det_bboxes, scales)                      # bbox_postp_depth (:113-130)
         trk = self.tracker.track(frame_id, infl, det_scores, det_labels, scales, d, warp=warp)
         with np.errstate(divide='ignore', invalid='ignore'):
             inv = (np.float32(1) / trk['scales']).astype(np.float32)
         out_boxes = boxdepth.scale_bbox(trk['bboxes'], inv)
-        d_out, _ = boxdepth.extract_depth(depth, out_boxes)
+        d_out, _ = extract(depth, out_boxes)
         res = dict(trk)
         res.update(bboxes=out_boxes, depth=d_out, gt_depth=d_out,
                    det_inflated=infl, det_scales=scales, det_depth=d)

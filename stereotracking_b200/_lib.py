@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libstereotrack_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ST_STATUS = dict(CAND_OVERFLOW=1, DET_OVERFLOW=2, TRACK_OVERFLOW=4, LAP_GUARD=8)
 
@@ -63,6 +63,7 @@ _SIGNATURES = {
                            _P, _P, _P, _P, _P, _P, _P]),
     'st_box_depth': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
     'st_scale_boxes': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    'st_box_depth_mode': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     'st_box_depth_reuse': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'st_track_step': (_I, [_P, _I] + [_P] * 7 + [_I] + [_P] * 10),
     'st_frame_step': (_I, [_P, _I, C.POINTER(StFrameIO), _P]),

@@ -773,6 +773,123 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Ablation reducers (mmtrack/models/mot/depth_extraction_comparison.py:5-150): the same
+// patch, validity filter and -1 rule as extract_depth, another statistic of the valid
+// depths, and scale = clip(d*d/400, 1, 3).  One CTA per box, values read in place
+// (these variants are for comparison runs, not for the frame pipeline):
+//   1 truncated mean  mean(sorted[int(0.1 n) : int(0.9 n)]), sorted[:-1] when empty (:29-36)
+//   2 mean            mean of the valid depths (:71)
+//   3 median          np.median: sorted[n/2], or the mean of the two middle elements (:106)
+//   4 centre          the UNFILTERED map at ((b1+b3)//2, (b0+b2)//2) with NumPy indexing:
+//                     negative indices wrap; out of range raises IndexError in the
+//                     reference (:141) -> d = NaN, scale = 1 and oob[s] is incremented
+constexpr int kAblationThreads = 256;
+
+__global__ void __launch_bounds__(kAblationThreads)
+k3_box_depth_ablation(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
+                      const int32_t *__restrict__ counts, int cap, int mode, float *__restrict__ d_out,
+                      float *__restrict__ scale_out, float *__restrict__ inflated, int32_t *__restrict__ oob) {
+    __shared__ int hist[512];
+    __shared__ int sh[8];
+    __shared__ int ired[kMaxCtaWarps];
+    __shared__ double dred[kMaxCtaWarps];
+    const int s = blockIdx.y;
+    const int n_box = min(counts[s], cap);
+    for (int bi = blockIdx.x; bi < n_box; bi += gridDim.x) {
+        __syncthreads();                               // shared memory is reused across boxes
+        const long long o = (long long)s * cap + bi;
+        const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
+        const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
+        BoxCtx c;
+        c.dm = depth + (long long)s * Hp * Wp;
+        c.Wp = Wp;
+        c.ys = py_slice(b1, b3, Hp);
+        c.xs = py_slice(b0, b2, Wp);
+        c.bw = (unsigned)max(c.xs.hi - c.xs.lo, 0);
+        c.npix = c.bw * (unsigned)max(c.ys.hi - c.ys.lo, 0);
+        c.staged = nullptr;
+        c.use_stage = false;
+        c.n_valid = 0;
+        const long long wbox = wrap_add(b2, (long long)(0ull - (unsigned long long)b0));
+        int n = 0;
+        if (!(wbox > 800)) {
+            int mine = 0;
+            for_each_valid_cta(c, [&](float) { ++mine; });
+            n = block_count(mine, ired);
+        }
+        c.n_valid = n;
+        float d = -1.f, scale = 1.f;
+        bool outside = false;
+        if (!(n < 1 || wbox > 800)) {
+            if (mode == 4) {
+                // (box[0] + box[2]) // 2 in int64: wrapping add, floor division
+                long long cx = wrap_add(b0, b2) >> 1, cy = wrap_add(b1, b3) >> 1;
+                if (cx < 0) cx += Wp;
+                if (cy < 0) cy += Hp;
+                outside = cx < 0 || cx >= Wp || cy < 0 || cy >= Hp;
+                d = outside ? __int_as_float(0x7fc00000) : c.dm[cy * Wp + cx];
+            } else {
+                Slice seg;
+                if (mode == 1) {
+                    seg = py_slice((long long)__dmul_rn(0.1, (double)n), (long long)__dmul_rn(1.0 - 0.1, (double)n), n);
+                    if (seg.hi <= seg.lo) seg = py_slice(0, -1, n);   // d_sorted[:-1]
+                } else if (mode == 2) {
+                    seg.lo = 0; seg.hi = n;
+                } else {
+                    seg.lo = (n - 1) / 2; seg.hi = n / 2 + 1;
+                }
+                const int m = seg.hi - seg.lo;
+                if (m <= 0) {
+                    d = __int_as_float(0x7fc00000);                   // mean of empty -> NaN
+                } else {
+                    uint32_t val[2];
+                    int below[2];
+                    int rk[2] = {seg.lo, seg.hi - 1};
+                    radix_select2_cta(c, 2, rk, val, below, hist, sh);
+                    const uint32_t ua = val[0], ub = val[1];
+                    double sum;
+                    if (ua == ub) {
+                        sum = (double)__uint_as_float(ua) * (double)m;
+                    } else {
+                        double part = 0.0;
+                        int eq_a = 0;
+                        for_each_valid_cta(c, [&](float v) {
+                            const uint32_t u = __float_as_uint(v);
+                            if (u > ua && u < ub) part += (double)v;
+                            eq_a += (u == ua);
+                        });
+                        sum = block_sum(part, dred);
+                        const int n_eq_a = block_count(eq_a, ired);
+                        const int in_a = below[0] + n_eq_a - seg.lo;  // duplicates of s[lo] inside
+                        const int in_b = seg.hi - below[1];           // duplicates of s[hi-1] inside
+                        sum += (double)__uint_as_float(ua) * (double)in_a + (double)__uint_as_float(ub) * (double)in_b;
+                    }
+                    d = (float)(sum / (double)m);
+                }
+            }
+            if (!outside) {
+                // scale = max(min(d*d/400, 3.), 1.) with Python min/max NaN behaviour
+                const float dd = __fdiv_rn(__fmul_rn(d, d), 400.f);
+                scale = (dd != dd) ? dd : fmaxf(fminf(dd, 3.f), 1.f);
+            }
+        }
+        if (threadIdx.x == 0) {
+            d_out[o] = d;
+            scale_out[o] = scale;
+            if (outside && oob) atomicAdd(&oob[s], 1);
+            if (inflated) {
+                const float cx = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
+                const float cy = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
+                const float hw = __fmul_rn(__fmul_rn(__fsub_rn(box.z, box.x), scale), 0.5f);
+                const float hh = __fmul_rn(__fmul_rn(__fsub_rn(box.w, box.y), scale), 0.5f);
+                reinterpret_cast<float4 *>(inflated)[o] =
+                    make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+            }
+        }
+    }
+}
+
 __global__ void k3_scale_boxes(const float *__restrict__ boxes, const float *__restrict__ scales,
                                const int32_t *__restrict__ counts, int cap, int invert,
                                float *__restrict__ out) {
@@ -873,6 +990,25 @@ extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, con
         k3_box_depth<<<(int)grid, kWarps * 32, 0, st>>>(depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap);
     }
     ST_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
+    return st_last_launch();
+}
+
+extern "C" int st_box_depth_mode(const float *depth, int S, int Hp, int Wp, const float *boxes,
+                                 const int32_t *counts, int cap, int mode, float *d, float *scale,
+                                 float *inflated, int32_t *oob, int32_t *workspace, void *stream) {
+    if (mode == ST_DEPTH_WINDOW) {
+        if (oob && S > 0) ST_CUDA_OK(cudaMemsetAsync(oob, 0, sizeof(int32_t) * S, (cudaStream_t)stream));
+        return st_box_depth_reuse(depth, S, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace, nullptr,
+                                  nullptr, nullptr, stream);
+    }
+    if (!depth || !boxes || !counts || !d || !scale || S < 0 || cap < 1 || Hp < 1 || Wp < 1 ||
+        mode < ST_DEPTH_TRUNCATED_MEAN || mode > ST_DEPTH_CENTER)
+        return ST_ERR_INVALID_ARG;
+    if (S == 0) return ST_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (oob) ST_CUDA_OK(cudaMemsetAsync(oob, 0, sizeof(int32_t) * S, st));
+    k3_box_depth_ablation<<<dim3(cap < 64 ? cap : 64, S), kAblationThreads, 0, st>>>(
+        depth, Hp, Wp, boxes, counts, cap, mode, d, scale, inflated, oob);
     return st_last_launch();
 }
 

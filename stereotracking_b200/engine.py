@@ -189,7 +189,15 @@ class StereoTrackEngine:
         return self.det_boxes, self.det_scores, self.det_labels, self.det_counts
 
     # ---- K3 ----------------------------------------------------------------------
-    def box_depth(self, depth, boxes, counts, d_out=None, scale_out=None, inflated_out=None):
+    DEPTH_MODES = dict(window=0, truncated_mean=1, mean=2, median=3, center=4)
+
+    def box_depth(self, depth, boxes, counts, d_out=None, scale_out=None, inflated_out=None, mode='window'):
+        """``mode``: 'window' = extract_depth (ocsort_disparity.py:136-175); 'truncated_mean',
+        'mean', 'median', 'center' = the ablation reducers of depth_extraction_comparison.py
+        (scale = clip(d*d/400, 1, 3)).  For 'center', ``self.depth_oob`` [S] int32 counts the boxes
+        whose centre pixel lies outside the map (the reference raises IndexError there)."""
+        if mode not in self.DEPTH_MODES:
+            raise ValueError(f'unknown depth reducer {mode!r}')
         S, Hp, Wp = depth.shape
         cap = boxes.shape[1]
         dev = depth.device
@@ -198,11 +206,21 @@ class StereoTrackEngine:
         ws = self.k3_workspace
         if ws.numel() < 4 + 6 * S * cap or ws.device != dev:
             ws = self.k3_workspace = torch.zeros(4 + 6 * S * cap, dtype=torch.int32, device=dev)
-        _lib.check(self.lib.st_box_depth(_ptr(self._dev(depth, torch.float32)), S, Hp, Wp,
-                                         _ptr(self._dev(boxes, torch.float32)),
-                                         _ptr(self._dev(counts, torch.int32)), cap, _ptr(d_out),
-                                         _ptr(scale_out), _ptr(inflated_out), _ptr(ws), self._stream()),
-                   'st_box_depth')
+        if mode == 'window':
+            _lib.check(self.lib.st_box_depth(_ptr(self._dev(depth, torch.float32)), S, Hp, Wp,
+                                             _ptr(self._dev(boxes, torch.float32)),
+                                             _ptr(self._dev(counts, torch.int32)), cap, _ptr(d_out),
+                                             _ptr(scale_out), _ptr(inflated_out), _ptr(ws), self._stream()),
+                       'st_box_depth')
+        else:
+            self.depth_oob = torch.empty(S, dtype=torch.int32, device=dev)
+            _lib.check(self.lib.st_box_depth_mode(_ptr(self._dev(depth, torch.float32)), S, Hp, Wp,
+                                                  _ptr(self._dev(boxes, torch.float32)),
+                                                  _ptr(self._dev(counts, torch.int32)), cap,
+                                                  self.DEPTH_MODES[mode], _ptr(d_out), _ptr(scale_out),
+                                                  _ptr(inflated_out), _ptr(self.depth_oob), _ptr(ws),
+                                                  self._stream()),
+                       'st_box_depth_mode')
         return d_out, scale_out, inflated_out
 
     def scale_boxes(self, boxes, scales, counts, invert, out=None):

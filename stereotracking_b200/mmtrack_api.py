@@ -269,7 +269,13 @@ class OCSORT_Disparity:
     the detector; it is not part of this path)."""
 
     def __init__(self, detector=None, tracker=None, motion=None, data_preprocessor=None, init_cfg=None,
-                 baseline: float = 0.25, focal_length: int = 640):
+                 baseline: float = 0.25, focal_length: int = 640, depth_reducer: str = 'window'):
+        # depth_reducer: 'window' = extract_depth (:136-175); 'truncated_mean' | 'mean' | 'median' |
+        # 'center' = what decorating extract_depth with depth_extraction_comparison.py's
+        # *_decorator does in the reference's ablation runs
+        if depth_reducer not in StereoTrackEngine.DEPTH_MODES:
+            raise ValueError(f'unknown depth_reducer {depth_reducer!r}')
+        self.depth_reducer = depth_reducer
         self.detector = MODELS.build(detector) if isinstance(detector, dict) else detector
         self.motion = TASK_UTILS.build(motion) if isinstance(motion, dict) else motion
         self.tracker = MODELS.build(tracker) if isinstance(tracker, dict) else tracker
@@ -280,6 +286,11 @@ class OCSORT_Disparity:
 
     def disp2depth(self, disp):
         return self.tracker._engine.disp_to_depth(disp.contiguous().float())
+
+    def _check_center(self, eng):
+        # depth_extraction_comparison.py:141 ``depth[cy, cx]``: NumPy raises when the box centre is off the map
+        if self.depth_reducer == 'center' and int(eng.depth_oob.sum()) > 0:
+            raise IndexError('box centre outside the depth map')
 
     def bbox_postp_depth(self, pred_instances, disp, gt_depth=None):
         """:113-130 - returns (pred_instances with inflated bboxes / scales / depth, depth dict)."""
@@ -292,10 +303,13 @@ class OCSORT_Disparity:
         b[0, :n] = boxes.to(eng.device, torch.float32)
         cnt = torch.tensor([n], dtype=torch.int32, device=eng.device)
         infl = torch.zeros_like(b)
-        d, sc, _ = eng.box_depth(depth, b, cnt, inflated_out=infl)
+        d, sc, _ = eng.box_depth(depth, b, cnt, inflated_out=infl, mode=self.depth_reducer)
+        self._check_center(eng)
         values = dict(d_values=d[0, :n].tolist())
         if gt_depth is not None:
-            gd, _, _ = eng.box_depth(gt_depth.reshape(1, gt_depth.shape[-2], gt_depth.shape[-1]).contiguous().float(), b, cnt)
+            gd, _, _ = eng.box_depth(gt_depth.reshape(1, gt_depth.shape[-2], gt_depth.shape[-1]).contiguous().float(), b, cnt,
+                                     mode=self.depth_reducer)
+            self._check_center(eng)
             values['gt_d_values'] = gd[0, :n].tolist()
         pred_instances['bboxes'] = infl[0, :n].to(boxes)
         pred_instances['scales'] = sc[0, :n].to(boxes)

@@ -8,6 +8,7 @@ Outputs (small .npz files next to this script):
   ref_kf.npz          KalmanFilter.initiate/predict/update chains
   ref_boxdepth.npz    OCSORT_Disparity.extract_depth / bbox_postp_depth /
                       scale_bbox on random and edge-case boxes
+  ref_boxdepth_ablation.npz  the four ablation reducers of depth_extraction_comparison.py
   ref_track_<name>.npz  OCSORT_Disparity.predict() over whole sequences:
                       inputs (raw disparity, detections) and the reference's
                       pred_track_instances + tracker state per frame
@@ -107,6 +108,50 @@ def make_boxdepth(ns):
         xyxy_back=ns.bbox_cxcyah_to_xyxy(ns.bbox_xyxy_to_cxcyah(boxes)).numpy())
 
 
+def make_boxdepth_ablation(ns):
+    """The four ablation reducers of mmtrack/models/mot/depth_extraction_comparison.py on the
+    inputs of ref_boxdepth.npz plus a larger map with bigger boxes.  The decorators replace
+    ``extract_depth`` (they ignore the wrapped function) and are called box by box so that an
+    IndexError of ``center`` (centre pixel outside the map) can be recorded per box."""
+    import sys as _sys
+    mod = _sys.modules['mmtrack.models.mot.depth_extraction_comparison']
+    base = np.load(os.path.join(HERE, 'ref_boxdepth.npz'))
+    rng = np.random.default_rng(17)
+    raw2 = rng.integers(8, 700, (200, 320)).astype(np.uint16)
+    raw2 //= 4                                   # many duplicates, few distinct values
+    raw2[raw2 < 2] = 2
+    raw2[rng.random(raw2.shape) < 0.25] = 65535
+    raw2[60:140, 100:220] = 96
+    boxes2 = []
+    for _ in range(40):
+        x1, y1 = rng.uniform(-20, 300), rng.uniform(-20, 190)
+        boxes2.append([x1, y1, x1 + rng.uniform(2, 200), y1 + rng.uniform(2, 150)])
+    boxes2 += [[0, 0, 320, 200], [100, 60, 220, 140], [310, 190, 400, 260], [-50, -40, 30, 20],
+               [150, 100, 151, 101], [150, 100, 152, 101], [150, 100, 152, 102], [10, 10, 13, 11]]
+    out = {}
+    for tag, raw, boxes in (('a', base['raw'], base['boxes']), ('b', raw2, np.asarray(boxes2, np.float32))):
+        depth = odisp.preprocess(raw)['depth']
+        depth_t = torch.from_numpy(depth)[None, None]
+        out[f'raw_{tag}'] = raw
+        out[f'boxes_{tag}'] = np.asarray(boxes, np.float32)
+        for mode in ('truncated_mean', 'mean', 'median', 'center'):
+            fn = getattr(mod, mode + '_decorator')(lambda *a, **k: None)
+            d = np.full(len(boxes), np.nan, np.float32)
+            sc = np.ones(len(boxes), np.float32)
+            err = np.zeros(len(boxes), np.int32)
+            for i, b in enumerate(boxes):
+                try:
+                    with np.errstate(all='ignore'):
+                        dv, sv = fn(None, depth_t, torch.tensor(np.asarray(b, np.float32)[None]))
+                    d[i], sc[i] = dv[0], sv[0]
+                except IndexError:
+                    err[i] = 1
+            out[f'd_{mode}_{tag}'], out[f'scale_{mode}_{tag}'], out[f'oob_{mode}_{tag}'] = d, sc, err
+    np.savez_compressed(os.path.join(HERE, 'ref_boxdepth_ablation.npz'), **out)
+    print('ablation:', {k: (int(np.isnan(v).sum()) if v.dtype.kind == 'f' else int(v.sum()))
+                        for k, v in out.items() if k.startswith(('oob_',))})
+
+
 def synth_dets(gen, F, rng, jitter=0.6, miss=0.05, clutter=3, blackout=()):
     """Noisy-GT detections per frame (what the detector would return)."""
     boxes, vis, _ = gen.gt_boxes(0, F)
@@ -156,11 +201,16 @@ def ego_warps(gen, F):
     return warps
 
 
-def run_reference_sequence(ns, raws, dets, warps=None, tracker_cfg=None):
+def run_reference_sequence(ns, raws, dets, warps=None, tracker_cfg=None, reducer=None):
     cfg = dict(TRACKER_CFG if tracker_cfg is None else tracker_cfg)
     if warps is not None:
         cfg['cmc'] = dict(method='glme_affine')
     model = ref_shims.build_model(ns, cfg)
+    if reducer is not None:
+        # an ablation run: extract_depth decorated with depth_extraction_comparison.py's <reducer>_decorator
+        import types
+        dec = getattr(sys.modules['mmtrack.models.mot.depth_extraction_comparison'], reducer + '_decorator')
+        model.extract_depth = types.MethodType(dec(type(model).extract_depth), model)
     if warps is not None:
         # the estimator (Farneback flow + RANSAC on the images, trackers/utils.py:6-55) is
         # host-side OpenCV and out of scope; the track() code path and
@@ -225,7 +275,7 @@ def save_sequence(name, raws, dets, frames, warps=None):
     print(f'{name}: {len(frames)} frames, {total} track rows, max id {max(fr["num_tracks"] for fr in frames)}')
 
 
-def make_sequences(ns):
+def make_sequences(ns, only=None):
     scen = {
         'basic': dict(cfg=SceneConfig(160, 224, 5, 8, n_clutter=0), F=36, seed=3, miss=0.05, clutter=3, blackout=()),
         'occlusion': dict(cfg=SceneConfig(160, 224, 6, 9, n_clutter=0), F=48, seed=4, miss=0.30, clutter=2,
@@ -239,8 +289,13 @@ def make_sequences(ns):
         # camera-motion compensation on (cmc=dict(method='glme_affine')), scripted warps
         'cmc': dict(cfg=SceneConfig(192, 256, 6, 10, n_clutter=0, heavy_ego=True),
                     F=40, seed=6, miss=0.20, clutter=3, blackout=(17,), cmc=True),
+        # ablation run: extract_depth replaced by the median reducer, scale = clip(d*d/400, 1, 3)
+        'median': dict(cfg=SceneConfig(160, 224, 6, 9, n_clutter=0), F=36, seed=8, miss=0.15, clutter=3,
+                       blackout=(14,), reducer='median'),
     }
     for name, sc in scen.items():
+        if only is not None and name not in only:
+            continue
         gen = SyntheticStereo(sc['cfg'], 1, sc['F'], seed=sc['seed'])
         fr = gen.frames(0, sc['F'])
         raws = [fr['raw'][f, 0].numpy() for f in range(sc['F'])]
@@ -248,13 +303,18 @@ def make_sequences(ns):
         dets = synth_dets(gen, sc['F'], rng, miss=sc['miss'], clutter=sc['clutter'],
                           blackout=sc['blackout'])
         warps = ego_warps(gen, sc['F']) if sc.get('cmc') else None
-        frames = run_reference_sequence(ns, raws, dets, warps, sc.get('tracker_cfg'))
+        frames = run_reference_sequence(ns, raws, dets, warps, sc.get('tracker_cfg'), sc.get('reducer'))
         save_sequence(name, raws, dets, frames, warps)
 
 
 if __name__ == '__main__':
     ns = ref_shims.load()
+    if sys.argv[1:] == ['ablation']:             # only the ablation fixtures (reads ref_boxdepth.npz)
+        make_boxdepth_ablation(ns)
+        make_sequences(ns, only=('median',))
+        sys.exit(0)
     make_kf(ns)
     make_boxdepth(ns)
+    make_boxdepth_ablation(ns)
     make_sequences(ns)
     print('golden fixtures written to', HERE)

@@ -40,15 +40,18 @@ def api():
     return dict(torch=torch, compat=compat, api=mmtrack_api, odisp=odisp)
 
 
-@pytest.mark.parametrize('name', ['basic', 'occlusion', 'cmc', 'defaults'])
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'cmc', 'defaults', 'median'])
 def test_model_predict_replays_reference_fixture(api, name):
     torch, compat = api['torch'], api['compat']
     g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
     det = _Det(api)
     extra = dict(cmc=dict(method='glme_affine')) if name == 'cmc' else {}
     base = dict(type='OCSORTTracker_Disparity') if name == 'defaults' else TRACKER_CFG     # ctor defaults
+    # 'median': the reference run had extract_depth decorated with median_decorator
+    # (mmtrack/models/mot/depth_extraction_comparison.py:83-115)
+    shell = dict(depth_reducer='median') if name == 'median' else {}
     model = compat.MODELS.build(dict(type='OCSORT_Disparity', detector=det, motion=dict(type='KalmanFilter'),
-                                     tracker=dict(base, max_dets=64, max_tracks=128, **extra)))
+                                     tracker=dict(base, max_dets=64, max_tracks=128, **extra), **shell))
     assert type(model.tracker).__name__ == 'OCSORTTracker_Disparity' and model.tracker.empty
     if name == 'cmc':
         # as in the fixture: the host-side estimator is replaced by the scripted warps, the
@@ -115,6 +118,8 @@ def test_constructor_errors_follow_the_reference(api):
         T(momentums=[0.1])                                         # base_tracker.py:26-27
     with pytest.raises(NotImplementedError):
         api['api'].KalmanFilter(use_nsa=True)
+    with pytest.raises(ValueError):
+        api['api'].OCSORT_Disparity(depth_reducer='mode')           # not one of depth_extraction_comparison.py's
 
 
 def test_rgb_only_ocsort_matches_oracle_tracker(api):

@@ -181,6 +181,82 @@ def test_k3_large_boxes_use_global_path(mods):
     np.testing.assert_allclose(sc[0].cpu().numpy(), rs, rtol=2e-6)
 
 
+@pytest.mark.parametrize('mode', ['truncated_mean', 'mean', 'median', 'center'])
+def test_k3_ablation_reducers_match_reference_fixture(mods, mode):
+    """depth_extraction_comparison.py's reducers: the golden values of the unmodified reference
+    (median / centre bit-exact, the two means within float32 summation order), -1 / NaN rows at
+    the same places, and the centre-off-the-map rows (reference: IndexError) counted in depth_oob."""
+    g = np.load(os.path.join(GOLDEN, 'ref_boxdepth_ablation.npz'))
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    for tag in 'ab':
+        depth, _, _ = eng.disp2depth(cuda(g[f'raw_{tag}'][None]))
+        b = g[f'boxes_{tag}']
+        n = len(b)
+        boxes = torch.zeros(1, n + 2, 4, device='cuda')
+        boxes[0, :n] = cuda(b)
+        counts = torch.tensor([n], dtype=torch.int32, device='cuda')
+        infl = torch.zeros_like(boxes)
+        d, sc, _ = eng.box_depth(depth, boxes, counts, inflated_out=infl, mode=mode)
+        d, sc, infl = d[0, :n].cpu().numpy(), sc[0, :n].cpu().numpy(), infl[0, :n].cpu().numpy()
+        oob = g[f'oob_{mode}_{tag}'].astype(bool)
+        assert int(eng.depth_oob[0]) == int(oob.sum())
+        assert np.isnan(d[oob]).all() and (sc[oob] == 1).all()
+        ref_d, ref_s = g[f'd_{mode}_{tag}'][~oob], g[f'scale_{mode}_{tag}'][~oob]
+        np.testing.assert_array_equal(np.isnan(d[~oob]), np.isnan(ref_d))
+        np.testing.assert_array_equal(d[~oob] == -1, ref_d == -1)
+        if mode in ('median', 'center'):
+            np.testing.assert_array_equal(d[~oob], ref_d)
+            np.testing.assert_array_equal(sc[~oob], ref_s)
+        else:
+            np.testing.assert_allclose(d[~oob], ref_d, rtol=1e-6, atol=0, equal_nan=True)
+            np.testing.assert_allclose(sc[~oob], ref_s, rtol=2e-6, atol=0, equal_nan=True)
+        np.testing.assert_array_equal(infl, mods.boxdepth.scale_bbox(b, sc))
+
+
+def test_k3_ablation_reducers_large_boxes_and_batches(mods):
+    """Boxes up to the 800 px limit on a 736x1280 map, several sequences with ragged counts."""
+    rng = np.random.default_rng(21)
+    S, H, W = 3, 736, 1280
+    raw = (rng.integers(30, 4000, (S, H, W)) // 8 * 8).astype(np.uint16)
+    raw[rng.random(raw.shape) < 0.3] = 65535
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S))
+    depth, _, _ = eng.disp2depth(cuda(raw))
+    dm = depth.cpu().numpy()
+    cap = 12
+    b = np.zeros((S, cap, 4), np.float32)
+    cnt = np.asarray([12, 0, 7], np.int32)
+    for s in range(S):
+        for i in range(cnt[s]):
+            x1, y1 = rng.uniform(-30, W - 40), rng.uniform(-30, H - 40)
+            b[s, i] = [x1, y1, x1 + rng.uniform(2, 820), y1 + rng.uniform(2, 700)]
+    b[0, 0] = [0.5, 0.5, 799.5, 735.5]
+    for mode in ('truncated_mean', 'mean', 'median', 'center'):
+        d, sc, _ = eng.box_depth(depth, cuda(b), cuda(cnt), mode=mode)
+        d, sc = d.cpu().numpy(), sc.cpu().numpy()
+        oob = eng.depth_oob.cpu().numpy()
+        for s in range(S):
+            n_oob = 0
+            for i in range(cnt[s]):
+                try:
+                    with np.errstate(all='ignore'):
+                        rd, rs = mods.boxdepth.box_depth_ablation(dm[s], b[s, i], mode)
+                except IndexError:
+                    n_oob += 1
+                    assert np.isnan(d[s, i]) and sc[s, i] == 1
+                    continue
+                np.testing.assert_allclose(d[s, i], np.float32(rd), rtol=2e-6, atol=0, equal_nan=True,
+                                           err_msg=f'{mode} seq {s} box {i}')
+                np.testing.assert_allclose(sc[s, i], np.float32(rs), rtol=4e-6, atol=0, equal_nan=True)
+            assert oob[s] == n_oob
+    # mode 0 through the same entry point is st_box_depth
+    d0, s0, _ = eng.box_depth(depth, cuda(b), cuda(cnt))
+    assert mods.StereoTrackEngine.DEPTH_MODES['window'] == 0
+    with pytest.raises(ValueError):
+        eng.box_depth(depth, cuda(b), cuda(cnt), mode='mode')
+    assert eng.lib.st_box_depth_mode(depth.data_ptr(), S, H, W, cuda(b).data_ptr(), cuda(cnt).data_ptr(), cap, 9,
+                                     d0.data_ptr(), s0.data_ptr(), None, None, None, None) != 0
+
+
 # ---------------------------------------------------------------- KF / LAP -------
 def test_kalman_batch_matches_reference_fixture(mods):
     g = np.load(os.path.join(GOLDEN, 'ref_kf.npz'))

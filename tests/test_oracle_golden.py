@@ -44,11 +44,39 @@ def test_boxdepth_matches_reference():
     np.testing.assert_array_equal(cxcyah_to_xyxy(cx), g['xyxy_back'])
 
 
-@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress', 'cmc', 'defaults'])
+@pytest.mark.parametrize('mode', boxdepth.ABLATION_MODES)
+def test_boxdepth_ablation_matches_reference(mode):
+    """The four reducers of depth_extraction_comparison.py, box by box (center raises
+    IndexError exactly where the reference did)."""
+    g = np.load(os.path.join(GOLDEN, 'ref_boxdepth_ablation.npz'))
+    seen = dict(minus1=0, nan=0, oob=0, clipped=0)
+    for tag in 'ab':
+        depth = disparity.preprocess(g[f'raw_{tag}'])['depth']
+        for i, box in enumerate(g[f'boxes_{tag}']):
+            if g[f'oob_{mode}_{tag}'][i]:
+                with pytest.raises(IndexError):
+                    boxdepth.box_depth_ablation(depth, box, mode)
+                seen['oob'] += 1
+                continue
+            with np.errstate(all='ignore'):
+                d, s = boxdepth.box_depth_ablation(depth, box, mode)
+            np.testing.assert_array_equal(np.float32(d), g[f'd_{mode}_{tag}'][i], err_msg=f'{tag}{i}')
+            np.testing.assert_array_equal(np.float32(s), g[f'scale_{mode}_{tag}'][i], err_msg=f'{tag}{i}')
+            seen['minus1'] += int(d == -1)
+            seen['nan'] += int(np.isnan(np.float32(d)))
+            seen['clipped'] += int(np.float32(s) == 3)
+    assert seen['minus1'] > 0 and (seen['clipped'] > 0 or mode == 'median')
+    assert (seen['oob'] > 0) == (mode == 'center')
+    assert (seen['nan'] > 0) == (mode == 'truncated_mean')     # n == 1: d_sorted[:-1] is empty
+
+
+@pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress', 'cmc', 'defaults', 'median'])
 def test_tracker_sequence_matches_reference(name):
     g = np.load(os.path.join(GOLDEN, f'ref_track_{name}.npz'))
     # 'defaults': the constructor defaults of OCSORTTracker_Disparity, not the AirDrone config
-    o = StereoTrackOracle(tracker_cfg={}) if name == 'defaults' else StereoTrackOracle()
+    # 'median': an ablation run, extract_depth decorated with median_decorator
+    o = StereoTrackOracle(tracker_cfg={}) if name == 'defaults' else StereoTrackOracle(
+        depth_reducer='median' if name == 'median' else None)
     lost_recovered = 0
     for f in range(len(g['raw'])):
         n = int(g['det_count'][f])
