@@ -113,6 +113,19 @@ int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, int Wr, int 
                   float *depth, float *disp3, uint8_t *mask,
                   float baseline, float focal_length, void *stream);
 
+/* K1b - the RGB half of the detector input from the decoded u8 frame, for the test pipeline of
+ * configs/stereo_tracking/ocsort/yolox_s_mmyolo_mot_airdrone_disp.py:104-116 at resize factor 1:
+ * Pad_Disparity._pad_img (transforms_disparity.py:243; bottom/right pad of the u8 image with
+ * pad_val['img']), PackTrackInputs_Disparity HWC -> CHW (formatting_disparity.py:166-176) and
+ * TrackDataPreprocessor_Disparity_V1.forward (data_preprocessor_disparity_v1.py:38-52: optional
+ * channel swap, .float(), optional (img - mean) / std, stack_batch to the padded size).
+ * img [S,H,W,3] u8 (device) -> out [S,3,Hp,Wp] f32 (device).  pad_val_host [3] u8 in INPUT channel
+ * order (NULL = 0); mean_host / std_host [3] f32 in OUTPUT channel order, both or neither
+ * (NULL = no normalisation, as in the shipped config); swap_rb != 0 = bgr_to_rgb / rgb_to_bgr. */
+int st_pack_image(const uint8_t *img, int S, int H, int W, int Hp, int Wp,
+                  const uint8_t *pad_val_host, const float *mean_host, const float *std_host,
+                  int swap_rb, float *out, void *stream);
+
 /* disp2depth of OCSORT_Disparity (ocsort_disparity.py:132-134) on an already
  * post-processed float disparity (`disp_postp[:, 0:1]`), n contiguous elements. */
 int st_disp_f32_to_depth(const float *disp, long long n, float *depth, float baseline,

@@ -85,3 +85,29 @@ def preprocess(raw_u16, img_scale=None, size_divisor=32, baseline=0.25,
     mask = pad_to_divisor(mask, size_divisor, 0)
     return dict(disp=disp, mask=mask,
                 depth=disp2depth(disp, baseline, focal_length))
+
+
+def pack_image(img, size_divisor=32, pad_val=(114, 114, 114), mean=None, std=None, swap_rb=False):
+    """The RGB half of the detector input at resize factor 1: Pad_Disparity._pad_img
+    (transforms_disparity.py:243 -> mmdet Pad: bottom/right pad of the HWC u8 image to a multiple
+    of ``size_divisor`` with pad_val['img']), PackTrackInputs_Disparity HWC -> CHW
+    (formatting_disparity.py:166-176), TrackDataPreprocessor_Disparity_V1.forward
+    (data_preprocessor_disparity_v1.py:38-52): channel swap, float32, (img - mean) / std with
+    mean / std in the swapped order, stack_batch (already at the padded size).
+    img [H,W,3] u8 -> [3,H',W'] float32."""
+    img = np.asarray(img, np.uint8)
+    H, W = img.shape[:2]
+    Hp = -(-H // size_divisor) * size_divisor
+    Wp = -(-W // size_divisor) * size_divisor
+    padded = np.empty((Hp, Wp, 3), np.uint8)
+    padded[:] = np.asarray(pad_val, np.float64).astype(np.uint8)
+    padded[:H, :W] = img
+    chw = padded.transpose(2, 0, 1)
+    if swap_rb:
+        chw = chw[[2, 1, 0]]
+    out = chw.astype(np.float32)
+    if mean is not None:
+        m = np.asarray(mean, np.float32).reshape(3, 1, 1)
+        sd = np.asarray(std, np.float32).reshape(3, 1, 1)
+        out = (out - m) / sd
+    return np.ascontiguousarray(out, np.float32)

@@ -63,6 +63,7 @@ _SIGNATURES = {
                            _P, _P, _P, _P, _P, _P, _P]),
     'st_box_depth': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
     'st_scale_boxes': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    'st_pack_image': (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     'st_box_depth_mode': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     'st_box_depth_reuse': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'st_track_step': (_I, [_P, _I] + [_P] * 7 + [_I] + [_P] * 10),

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libstereotrack_b200.so')
-SOURCES = ['k1_disp2depth.cu', 'k2_decode_nms.cu', 'k3_box_depth.cu', 'k4_track.cu', 'k_pipeline.cu']
+SOURCES = ['k1_disp2depth.cu', 'k1b_pack_image.cu', 'k2_decode_nms.cu', 'k3_box_depth.cu', 'k4_track.cu', 'k_pipeline.cu']
 HEADERS = ['st_common.cuh', 'kalman.cuh', 'lapjv.cuh', os.path.join('..', '..', 'include', 'stereotrack_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-fmad=false', '--extended-lambda', '-Xcompiler', '-fPIC', '-shared']

@@ -1,0 +1,129 @@
+// K1b: the RGB half of the detector input, produced on the device from the decoded u8 frame.
+// Replaces, for the test pipeline of configs/stereo_tracking/ocsort/yolox_s_mmyolo_mot_airdrone_disp.py
+// (:104-116) at resize factor 1:
+//   Pad_Disparity._pad_img        bottom/right pad of the HWC u8 image to a multiple of 32 with
+//                                 pad_val['img'] = 114 (transforms_disparity.py:243 -> mmdet Pad / mmcv.impad)
+//   PackTrackInputs_Disparity     HWC -> CHW (formatting_disparity.py:166-176)
+//   TrackDataPreprocessor_Disparity_V1.forward   optional channel swap, .float(), optional
+//                                 (img - mean) / std, stack_batch to the /32 size
+//                                 (data_preprocessor_disparity_v1.py:38-52, utils/misc.py:13-64)
+// so that a frame crosses PCIe as 3 bytes per pixel instead of 12.  Pure streaming:
+// 3*H*W bytes read, 12*Hp*Wp bytes written per frame; HBM-bound.
+#include "st_common.cuh"
+
+namespace {
+
+struct PackParams {
+    float mean[3], std[3];       // indexed by OUTPUT channel (after the swap), as the reference's buffers
+    unsigned char pad[3];        // indexed by INPUT channel: the pad happens on the u8 image
+    int swap_rb, normalise;
+};
+
+template <typename T>
+__device__ __forceinline__ T pick3(const T *a, int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
+
+__device__ __forceinline__ float convert(unsigned b, int co, const PackParams &p) {
+    const float f = (float)b;
+    // torch: (img - mean) / std in float32, true division, un-fused
+    return p.normalise ? __fdiv_rn(__fsub_rn(f, pick3(p.mean, co)), pick3(p.std, co)) : f;
+}
+
+// Four pixels per item: three aligned 32-bit loads (12 interleaved bytes), one 128-bit store per
+// output plane; consecutive lanes write consecutive 16-byte pieces of each plane.
+// blockIdx.y = sequence, so that the index math inside a frame is 32-bit.
+__global__ void __launch_bounds__(256)
+k1b_pack_image_v4(const unsigned char *__restrict__ img, int H, int W, int Hp, int Wp,
+                  PackParams p, float *__restrict__ out) {
+    const unsigned wq = (unsigned)Wp >> 2, n_items = wq * (unsigned)Hp;
+    const long long plane = (long long)Hp * Wp;
+    const long long s = blockIdx.y;
+    for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+        const int y = (int)(it / wq);
+        const int x = (int)(it - (unsigned)y * wq) << 2;
+        uint32_t w[3];
+        if (y < H && x < W) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(img + ((s * H + y) * W + x) * 3);
+            w[0] = __ldg(src); w[1] = __ldg(src + 1); w[2] = __ldg(src + 2);
+        } else {
+            const uint32_t a = p.pad[0], b = p.pad[1], c = p.pad[2];
+            w[0] = a | (b << 8) | (c << 16) | (a << 24);
+            w[1] = b | (c << 8) | (a << 16) | (b << 24);
+            w[2] = c | (a << 8) | (b << 16) | (c << 24);
+        }
+        float v[3][4];
+#pragma unroll
+        for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int k = 3 * px + c;
+                const unsigned b = (w[k >> 2] >> (8 * (k & 3))) & 255u;
+                const int co = p.swap_rb ? 2 - c : c;
+                v[c][px] = convert(b, co, p);                     // indexed by input channel (static)
+            }
+        float *dst = out + s * 3 * plane + (long long)y * Wp + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int co = p.swap_rb ? 2 - c : c;
+            *reinterpret_cast<float4 *>(dst + co * plane) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+        }
+    }
+}
+
+// Any width / alignment: one output element per thread step.
+__global__ void __launch_bounds__(256)
+k1b_pack_image_generic(const unsigned char *__restrict__ img, long long n_out, int H, int W, int Hp, int Wp,
+                       PackParams p, float *__restrict__ out) {
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_out;
+         o += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(o % Wp);
+        long long r = o / Wp;
+        const int y = (int)(r % Hp);
+        r /= Hp;
+        const int co = (int)(r % 3);
+        const long long s = r / 3;
+        const int c = p.swap_rb ? 2 - co : co;
+        const unsigned b = (y < H && x < W) ? img[((s * H + y) * W + x) * 3 + c] : pick3(p.pad, c);
+        out[o] = convert(b, co, p);
+    }
+}
+
+}  // namespace
+
+extern "C" int st_pack_image(const uint8_t *img, int S, int H, int W, int Hp, int Wp,
+                             const uint8_t *pad_val_host, const float *mean_host, const float *std_host,
+                             int swap_rb, float *out, void *stream) {
+    if (!img || !out || S < 0 || H < 1 || W < 1 || Hp < H || Wp < W || ((mean_host == nullptr) != (std_host == nullptr)))
+        return ST_ERR_INVALID_ARG;
+    if (S == 0) return ST_OK;
+    PackParams p;
+    for (int c = 0; c < 3; ++c) {
+        p.pad[c] = pad_val_host ? pad_val_host[c] : 0;
+        p.mean[c] = mean_host ? mean_host[c] : 0.f;
+        p.std[c] = std_host ? std_host[c] : 1.f;
+    }
+    p.swap_rb = swap_rb != 0;
+    p.normalise = mean_host != nullptr;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (W % 4 == 0) && (Wp % 4 == 0) && ((uintptr_t)img % 4 == 0) && ((uintptr_t)out % 16 == 0) &&
+                     (long long)Hp * Wp < (1ll << 31) && S <= 65535;
+    if (vec) {
+        const long long per_seq = (long long)Hp * (Wp / 4);
+        long long gx = (per_seq + 255) / 256;
+        const long long share = ((long long)sms * 8 + S - 1) / S;       // about one resident wave in total
+        if (gx > share) gx = share;
+        k1b_pack_image_v4<<<dim3((unsigned)gx, (unsigned)S), 256, 0, st>>>(img, H, W, Hp, Wp, p, out);
+    } else {
+        const long long n_out = (long long)S * 3 * Hp * Wp;
+        long long grid = (n_out + 255) / 256;
+        if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+        k1b_pack_image_generic<<<(int)grid, 256, 0, st>>>(img, n_out, H, W, Hp, Wp, p, out);
+    }
+    return st_last_launch();
+}

@@ -9,6 +9,7 @@ Outputs (small .npz files next to this script):
   ref_boxdepth.npz    OCSORT_Disparity.extract_depth / bbox_postp_depth /
                       scale_bbox on random and edge-case boxes
   ref_boxdepth_ablation.npz  the four ablation reducers of depth_extraction_comparison.py
+  ref_frontend.npz    pad + HWC->CHW + TrackDataPreprocessor_Disparity_V1 lines + stack_batch on u8 images
   ref_track_<name>.npz  OCSORT_Disparity.predict() over whole sequences:
                       inputs (raw disparity, detections) and the reference's
                       pred_track_instances + tracker state per frame
@@ -150,6 +151,44 @@ def make_boxdepth_ablation(ns):
     np.savez_compressed(os.path.join(HERE, 'ref_boxdepth_ablation.npz'), **out)
     print('ablation:', {k: (int(np.isnan(v).sum()) if v.dtype.kind == 'f' else int(v.sum()))
                         for k, v in out.items() if k.startswith(('oob_',))})
+
+
+def make_frontend(ns):
+    """RGB half of the detector input: the reference's own lines of
+    TrackDataPreprocessor_Disparity_V1.forward (data_preprocessor_disparity_v1.py:38-52, executed
+    here statement by statement on torch tensors - the class itself needs mmengine) and the
+    reference's ``stack_batch`` (mmtrack/utils/misc.py:13-64, loaded from /root/reference), after
+    the u8 pad of mmdet's Pad (third-party, restated as a NumPy bottom/right pad with 114) and
+    PackTrackInputs_Disparity's HWC -> CHW transpose (formatting_disparity.py:166-176)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('mmtrack.utils.misc', os.path.join(ref_shims.REF, 'mmtrack', 'utils', 'misc.py'))
+    misc = importlib.util.module_from_spec(spec)
+    misc.__package__ = 'mmtrack.utils'
+    spec.loader.exec_module(misc)
+    rng = np.random.default_rng(23)
+    out = {}
+    for tag, (H, W) in (('a', (40, 52)), ('b', (30, 45))):
+        img = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+        Hp, Wp = -(-H // 32) * 32, -(-W // 32) * 32
+        padded = np.full((Hp, Wp, 3), 114, np.uint8)           # mmcv.impad(img, shape=..., pad_val=(114.0,)*3)
+        padded[:H, :W] = img
+        packed = torch.from_numpy(np.ascontiguousarray(padded[None].transpose(0, 3, 1, 2)))   # (T=1,C,H,W)
+        out[f'img_{tag}'] = img
+        for name, (mean, std, swap) in (('plain', (None, None, False)),
+                                       ('norm', ((123.675, 116.28, 103.53), (58.395, 57.12, 57.375), True))):
+            imgs = [packed]
+            if swap:
+                imgs = [_img[:, [2, 1, 0], ...] for _img in imgs]                              # :44-45
+            imgs = [_img.float() for _img in imgs]                                             # :47
+            if mean is not None:
+                m = torch.tensor(mean).view(1, -1, 1, 1)                                       # data_preprocessor.py:77-80
+                sd = torch.tensor(std).view(1, -1, 1, 1)
+                imgs = [(_img - m) / sd for _img in imgs]                                      # :49
+            res = misc.stack_batch(imgs, 32, 0)                                                # :51-52
+            assert res.shape == (1, 1, 3, Hp, Wp)
+            out[f'out_{name}_{tag}'] = res[0, 0].numpy()
+    np.savez_compressed(os.path.join(HERE, 'ref_frontend.npz'), **out)
+    print('frontend:', {k: v.shape for k, v in out.items()})
 
 
 def synth_dets(gen, F, rng, jitter=0.6, miss=0.05, clutter=3, blackout=()):
@@ -313,8 +352,12 @@ if __name__ == '__main__':
         make_boxdepth_ablation(ns)
         make_sequences(ns, only=('median',))
         sys.exit(0)
+    if sys.argv[1:] == ['frontend']:
+        make_frontend(ns)
+        sys.exit(0)
     make_kf(ns)
     make_boxdepth(ns)
     make_boxdepth_ablation(ns)
+    make_frontend(ns)
     make_sequences(ns)
     print('golden fixtures written to', HERE)

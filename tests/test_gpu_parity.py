@@ -73,6 +73,29 @@ def test_k1_every_raw_code_bit_exact(mods):
 
 
 # ---------------------------------------------------------------- K2 ------------
+def test_k1b_pack_image_bit_exact(mods):
+    """RGB half of the detector input: reference-generated fixture (vector and generic kernels),
+    then a C2-sized batch against the oracle."""
+    g = np.load(os.path.join(GOLDEN, 'ref_frontend.npz'))
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    norm = dict(mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375), swap_rb=True)
+    for tag in 'ab':
+        img = cuda(g[f'img_{tag}'][None])
+        np.testing.assert_array_equal(eng.pack_image(img)[0].cpu().numpy(), g[f'out_plain_{tag}'])
+        np.testing.assert_array_equal(eng.pack_image(img, **norm)[0].cpu().numpy(), g[f'out_norm_{tag}'])
+    rng = np.random.default_rng(31)
+    big = rng.integers(0, 256, (3, 720, 1280, 3)).astype(np.uint8)
+    out = eng.pack_image(cuda(big), **norm)
+    assert out.shape == (3, 3, 736, 1280)
+    for s in range(3):
+        np.testing.assert_array_equal(out[s].cpu().numpy(), mods.disparity.pack_image(big[s], **norm))
+    out = eng.pack_image(cuda(big[:, :, :1279]), pad_val=(1, 2, 3))           # odd width: generic kernel
+    np.testing.assert_array_equal(out[2].cpu().numpy(), mods.disparity.pack_image(big[2, :, :1279], pad_val=(1, 2, 3)))
+    with pytest.raises(AssertionError):
+        eng.pack_image(cuda(big), mean=(1, 2, 3))
+    assert eng.lib.st_pack_image(None, 1, 8, 8, 8, 8, None, None, None, 0, out.data_ptr(), None) != 0
+
+
 def _head_case(mods, cfg_name, S, seed, frames=2):
     cfg = mods.CONFIGS[cfg_name]
     gen = mods.SyntheticStereo(cfg, S, frames, seed=seed)

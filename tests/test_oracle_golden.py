@@ -44,6 +44,17 @@ def test_boxdepth_matches_reference():
     np.testing.assert_array_equal(cxcyah_to_xyxy(cx), g['xyxy_back'])
 
 
+def test_pack_image_matches_reference_lines():
+    """RGB half of the detector input (pad 114, HWC->CHW, swap, float, normalise, stack_batch)."""
+    g = np.load(os.path.join(GOLDEN, 'ref_frontend.npz'))
+    for tag in 'ab':
+        np.testing.assert_array_equal(disparity.pack_image(g[f'img_{tag}']), g[f'out_plain_{tag}'])
+        np.testing.assert_array_equal(
+            disparity.pack_image(g[f'img_{tag}'], mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375),
+                                 swap_rb=True), g[f'out_norm_{tag}'])
+    assert (g['out_plain_a'][:, 40:, :] == 114).all() and (g['out_plain_a'][:, :, 52:] == 114).all()
+
+
 @pytest.mark.parametrize('mode', boxdepth.ABLATION_MODES)
 def test_boxdepth_ablation_matches_reference(mode):
     """The four reducers of depth_extraction_comparison.py, box by box (center raises
