@@ -279,6 +279,16 @@ int st_export_state(st_handle *h, int seq, int64_t *ids_host, double *mean_host,
  * cov [n,64] f64 in place, z [n,4] f32 (cx,cy,a,h). op: 0 initiate, 1 predict,
  * 2 update. */
 int st_kalman_batch(int op, int n, double *mean, double *cov, const float *z, void *stream);
+/* KalmanFilter.project (kalman_filter.py:121-152, use_nsa=False): pmean [n,4], pcov [n,16] f64
+ * (either may be NULL). */
+int st_kalman_project(int n, const double *mean, const double *cov, double *pmean, double *pcov,
+                      void *stream);
+/* KalmanFilter.gating_distance (kalman_filter.py:190-234) of n states against the same m
+ * measurements meas [m,4] f64 (cx,cy,a,h): dist [n,m] f64 squared Mahalanobis distances;
+ * only_position != 0 uses (cx,cy) only.  A projected covariance that is not positive definite
+ * gives NaN (NumPy raises LinAlgError). */
+int st_kalman_gating(int n, const double *mean, const double *cov, int m, const double *meas,
+                     int only_position, double *dist, void *stream);
 
 /* Batched association (ocm/ocr cost is built by st_track_step; this entry
  * exposes the assignment itself for parity tests): cost [B,R,C] f32 ->

@@ -44,3 +44,14 @@ def update(mean, cov, z):
     gain = scipy.linalg.cho_solve(chol, (cov @ H.T).T, check_finite=False).T
     innov = np.asarray(z, np.float64) - pm
     return mean + innov @ gain.T, cov - np.linalg.multi_dot((gain, pc, gain.T))
+
+
+def gating_distance(mean, cov, measurements, only_position=False):
+    """kalman_filter.py:190-234: squared Mahalanobis distance of each measurement (N,4)."""
+    pm, pc = project(mean, cov)
+    z = np.asarray(measurements, np.float64)
+    if only_position:
+        pm, pc, z = pm[:2], pc[:2, :2], z[:, :2]
+    chol = np.linalg.cholesky(pc)
+    y = scipy.linalg.solve_triangular(chol, (z - pm).T, lower=True, check_finite=False)
+    return np.sum(y * y, axis=0)

@@ -725,6 +725,66 @@ __global__ void k4_kalman_batch(int op, int n, double *mean, double *cov, const 
     stkf::store8(row, mean + g * 8, cov + g * 64, gl, active);
 }
 
+// KalmanFilter.project (kalman_filter.py:121-152) and gating_distance (:190-234) for n states,
+// one thread per state: S = H P H^T + diag((h/20)^2, (h/20)^2, 1e-1^2, (h/20)^2) is the upper-left
+// 4x4 block of P plus the diagonal (H selects, so the products are exact); the squared Mahalanobis
+// distance of every measurement through the lower Cholesky factor and a forward substitution.
+__global__ void k4_kalman_project(int n, const double *__restrict__ mean, const double *__restrict__ cov,
+                                  double *__restrict__ pmean, double *__restrict__ pcov, int m,
+                                  const double *__restrict__ meas, int only_position, double *__restrict__ dist) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double *mu = mean + (long long)t * 8, *P = cov + (long long)t * 64;
+    const double sp = __dmul_rn(1.0 / 20, mu[3]);
+    const double r[4] = {__dmul_rn(sp, sp), __dmul_rn(sp, sp), __dmul_rn(1e-1, 1e-1), __dmul_rn(sp, sp)};
+    double A[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) A[i][j] = __dadd_rn(P[i * 8 + j], i == j ? r[i] : 0.0);
+    if (pmean)
+        for (int i = 0; i < 4; ++i) pmean[(long long)t * 4 + i] = mu[i];
+    if (pcov)
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) pcov[(long long)t * 16 + i * 4 + j] = A[i][j];
+    if (!dist) return;
+    const int nd = only_position ? 2 : 4;
+    double L[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < nd) {
+            double acc = A[j][j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < j) acc = __dsub_rn(acc, __dmul_rn(L[j][k], L[j][k]));
+            L[j][j] = sqrt(acc);                          // not positive definite -> NaN (NumPy raises LinAlgError)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i > j && i < nd) {
+                    double a = A[i][j];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < j) a = __dsub_rn(a, __dmul_rn(L[i][k], L[j][k]));
+                    L[i][j] = __ddiv_rn(a, L[j][j]);
+                }
+        }
+    }
+    for (int q = 0; q < m; ++q) {
+        double z[4], acc2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < nd) {
+                double a = __dsub_rn(meas[(long long)q * 4 + i], mu[i]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < i) a = __dsub_rn(a, __dmul_rn(L[i][k], z[k]));
+                z[i] = __ddiv_rn(a, L[i][i]);
+                acc2 = __dadd_rn(acc2, __dmul_rn(z[i], z[i]));
+            }
+        dist[(long long)t * m + q] = acc2;
+    }
+}
+
 template <typename Tp>
 void take(Tp *&ptr, unsigned char *&cursor, size_t count) {
     ptr = reinterpret_cast<Tp *>(cursor);
@@ -925,6 +985,24 @@ extern "C" int st_kalman_batch(int op, int n, double *mean, double *cov, const f
     if (op < 0 || op > 2 || n < 0 || !mean || !cov || (op != 1 && !z)) return ST_ERR_INVALID_ARG;
     if (n == 0) return ST_OK;
     k4_kalman_batch<<<(n + 15) / 16, 128, 0, (cudaStream_t)stream>>>(op, n, mean, cov, z);
+    return st_last_launch();
+}
+
+extern "C" int st_kalman_project(int n, const double *mean, const double *cov, double *pmean, double *pcov,
+                                 void *stream) {
+    if (n < 0 || !mean || !cov || (!pmean && !pcov)) return ST_ERR_INVALID_ARG;
+    if (n == 0) return ST_OK;
+    k4_kalman_project<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, mean, cov, pmean, pcov, 0, nullptr, 0,
+                                                                       nullptr);
+    return st_last_launch();
+}
+
+extern "C" int st_kalman_gating(int n, const double *mean, const double *cov, int m, const double *meas,
+                                int only_position, double *dist, void *stream) {
+    if (n < 0 || m < 0 || !mean || !cov || !dist || (m > 0 && !meas)) return ST_ERR_INVALID_ARG;
+    if (n == 0 || m == 0) return ST_OK;
+    k4_kalman_project<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, mean, cov, nullptr, nullptr, m, meas,
+                                                                       only_position != 0, dist);
     return st_last_launch();
 }
 

@@ -95,6 +95,54 @@ class KalmanFilter:
     def update(self, mean, covariance, measurement, bbox_score: float = 0.):
         return self._run(2, mean, covariance, measurement)
 
+    def _states(self, mean, covariance):
+        import numpy as np
+        if not torch.cuda.is_available():
+            raise _lib.StereoTrackError('KalmanFilter needs a CUDA device (no CPU fallback)')
+        m = torch.as_tensor(np.asarray(mean, np.float64).reshape(-1, 8)).cuda().contiguous()
+        c = torch.as_tensor(np.asarray(covariance, np.float64).reshape(-1, 64)).cuda().contiguous()
+        return m, c
+
+    def project(self, mean, covariance, bbox_score: float = 0.):
+        """kalman_filter.py:121-152 (``bbox_score`` only matters with use_nsa)."""
+        m, c = self._states(mean, covariance)
+        pm = torch.empty(m.shape[0], 4, dtype=torch.float64, device='cuda')
+        pc = torch.empty(m.shape[0], 16, dtype=torch.float64, device='cuda')
+        _lib.check(self._lib.st_kalman_project(m.shape[0], m.data_ptr(), c.data_ptr(), pm.data_ptr(), pc.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), 'st_kalman_project')
+        return pm.cpu().numpy().reshape(4), pc.cpu().numpy().reshape(4, 4)
+
+    def gating_distance(self, mean, covariance, measurements, only_position: bool = False):
+        """kalman_filter.py:190-234: squared Mahalanobis distance of each measurement (N,4)."""
+        import numpy as np
+        m, c = self._states(mean, covariance)
+        z = torch.as_tensor(np.asarray(measurements, np.float64).reshape(-1, 4)).cuda().contiguous()
+        out = torch.empty(z.shape[0], dtype=torch.float64, device='cuda')
+        _lib.check(self._lib.st_kalman_gating(1, m.data_ptr(), c.data_ptr(), z.shape[0], z.data_ptr(),
+                                              int(bool(only_position)), out.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), 'st_kalman_gating')
+        return out.cpu().numpy()
+
+    def track(self, tracks, bboxes):
+        """kalman_filter.py:236-260: predict every track, gate the boxes (N,4 cxcyah) against it;
+        distances above ``gating_threshold`` become NaN.  One predict and one gating launch for
+        all tracks."""
+        import numpy as np
+        ids = list(tracks.keys())
+        m, c = self._states(np.stack([tracks[i].mean for i in ids]), np.stack([tracks[i].covariance for i in ids]))
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self._lib.st_kalman_batch(1, len(ids), m.data_ptr(), c.data_ptr(), None, st), 'st_kalman_batch')
+        z = torch.as_tensor(bboxes.detach().cpu().numpy().astype(np.float64).reshape(-1, 4)).cuda().contiguous()
+        out = torch.empty(len(ids), z.shape[0], dtype=torch.float64, device='cuda')
+        _lib.check(self._lib.st_kalman_gating(len(ids), m.data_ptr(), c.data_ptr(), z.shape[0], z.data_ptr(),
+                                              int(bool(self.center_only)), out.data_ptr(), st), 'st_kalman_gating')
+        mh, ch = m.cpu().numpy(), c.cpu().numpy()
+        for k, i in enumerate(ids):
+            tracks[i].mean, tracks[i].covariance = mh[k].copy(), ch[k].reshape(8, 8).copy()
+        costs = out.cpu().numpy()
+        costs[costs > self.gating_threshold] = np.nan
+        return tracks, costs
+
 
 @MODELS.register_module(force=True)
 class OCSORTTracker_Disparity:

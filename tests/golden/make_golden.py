@@ -6,6 +6,7 @@ synthetic inputs.  Run in the build container only:
 
 Outputs (small .npz files next to this script):
   ref_kf.npz          KalmanFilter.initiate/predict/update chains
+  ref_kf_gating.npz   KalmanFilter.project / gating_distance / track on states of ref_kf.npz
   ref_boxdepth.npz    OCSORT_Disparity.extract_depth / bbox_postp_depth /
                       scale_bbox on random and edge-case boxes
   ref_boxdepth_ablation.npz  the four ablation reducers of depth_extraction_comparison.py
@@ -67,6 +68,35 @@ def make_kf(ns):
     np.savez_compressed(os.path.join(HERE, 'ref_kf.npz'), mean=np.stack(means),
                         cov=np.stack(covs), z=np.stack(zs), op=np.asarray(ops),
                         chain_start=np.asarray([0, ops.index(0, 1)]))
+
+
+def make_kf_gating(ns):
+    """KalmanFilter.project / gating_distance / track of the unmodified reference on the states
+    of ref_kf.npz."""
+    import types
+    g = np.load(os.path.join(HERE, 'ref_kf.npz'))
+    rng = np.random.default_rng(13)
+    kf = ns.KalmanFilterRaw()
+    idx = np.arange(0, len(g['op']), 3)
+    pm, pc, meas, d4, d2 = [], [], [], [], []
+    for i in idx:
+        m, c = g['mean'][i], g['cov'][i]
+        a, b = kf.project(m, c)
+        pm.append(a); pc.append(b)
+        z = (m[:4] + rng.normal(0, [6, 6, 0.05, 4], (5, 4))).astype(np.float32)
+        meas.append(z)
+        d4.append(kf.gating_distance(m, c, z))
+        d2.append(kf.gating_distance(m, c, z, only_position=True))
+    tracks = {7: types.SimpleNamespace(mean=g['mean'][5].copy(), covariance=g['cov'][5].copy()),
+              9: types.SimpleNamespace(mean=g['mean'][30].copy(), covariance=g['cov'][30].copy())}
+    boxes = torch.from_numpy(np.concatenate([meas[1][:3], meas[10][:3]]))
+    _, costs = kf.track(tracks, boxes)
+    np.savez_compressed(os.path.join(HERE, 'ref_kf_gating.npz'), idx=idx, pmean=np.stack(pm), pcov=np.stack(pc),
+                        meas=np.stack(meas), dist4=np.stack(d4), dist2=np.stack(d2),
+                        track_in=np.asarray([5, 30]), track_boxes=boxes.numpy(), track_costs=costs,
+                        track_mean=np.stack([tracks[7].mean, tracks[9].mean]),
+                        track_cov=np.stack([tracks[7].covariance, tracks[9].covariance]))
+    print('kf gating:', len(idx), 'states; track costs NaN', int(np.isnan(costs).sum()), 'of', costs.size)
 
 
 def edge_depth_map(rng, H=96, W=128):
@@ -355,7 +385,11 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['frontend']:
         make_frontend(ns)
         sys.exit(0)
+    if sys.argv[1:] == ['kf_gating']:
+        make_kf_gating(ns)
+        sys.exit(0)
     make_kf(ns)
+    make_kf_gating(ns)
     make_boxdepth(ns)
     make_boxdepth_ablation(ns)
     make_frontend(ns)

@@ -109,6 +109,31 @@ def test_kalman_filter_object_matches_reference_fixture(api):
         np.testing.assert_allclose(cov, g['cov'][i], rtol=1e-9, atol=1e-12)
 
 
+def test_kalman_filter_project_gating_track_match_reference_fixture(api):
+    """KalmanFilter.project / gating_distance / track (kalman_filter.py:121-152,:190-260)."""
+    import types
+    g = np.load(os.path.join(GOLDEN, 'ref_kf_gating.npz'))
+    k = np.load(os.path.join(GOLDEN, 'ref_kf.npz'))
+    kf = api['compat'].TASK_UTILS.build(dict(type='KalmanFilter'))
+    for n, i in enumerate(g['idx']):
+        pm, pc = kf.project(k['mean'][i], k['cov'][i])
+        np.testing.assert_array_equal(pm, g['pmean'][n])
+        np.testing.assert_allclose(pc, g['pcov'][n], rtol=1e-15, atol=0)
+        np.testing.assert_allclose(kf.gating_distance(k['mean'][i], k['cov'][i], g['meas'][n]), g['dist4'][n],
+                                   rtol=1e-10)
+        np.testing.assert_allclose(kf.gating_distance(k['mean'][i], k['cov'][i], g['meas'][n], only_position=True),
+                                   g['dist2'][n], rtol=1e-10)
+    a, b = (int(v) for v in g['track_in'])
+    tracks = {7: types.SimpleNamespace(mean=k['mean'][a].copy(), covariance=k['cov'][a].copy()),
+              9: types.SimpleNamespace(mean=k['mean'][b].copy(), covariance=k['cov'][b].copy())}
+    out, costs = kf.track(tracks, api['torch'].from_numpy(g['track_boxes']).cuda())
+    np.testing.assert_array_equal(np.isnan(costs), np.isnan(g['track_costs']))
+    np.testing.assert_allclose(costs, g['track_costs'], rtol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(np.stack([out[7].mean, out[9].mean]), g['track_mean'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np.stack([out[7].covariance, out[9].covariance]), g['track_cov'], rtol=1e-11, atol=1e-13)
+    assert not np.isnan(g['track_costs']).all() and np.isnan(g['track_costs']).any()
+
+
 def test_constructor_errors_follow_the_reference(api):
     T = api['api'].OCSORTTracker_Disparity
     with pytest.raises(ValueError):

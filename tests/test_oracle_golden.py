@@ -25,6 +25,19 @@ def test_kalman_chain_matches_reference():
         np.testing.assert_allclose(c, g['cov'][i], rtol=1e-11, atol=1e-13)
 
 
+def test_kalman_project_and_gating_match_reference():
+    g = np.load(os.path.join(GOLDEN, 'ref_kf_gating.npz'))
+    k = np.load(os.path.join(GOLDEN, 'ref_kf.npz'))
+    for n, i in enumerate(g['idx']):
+        pm, pc = kalman.project(k['mean'][i], k['cov'][i])
+        np.testing.assert_array_equal(pm, g['pmean'][n])
+        np.testing.assert_allclose(pc, g['pcov'][n], rtol=1e-15, atol=0)
+        np.testing.assert_allclose(kalman.gating_distance(k['mean'][i], k['cov'][i], g['meas'][n]), g['dist4'][n],
+                                   rtol=1e-12)
+        np.testing.assert_allclose(kalman.gating_distance(k['mean'][i], k['cov'][i], g['meas'][n], True),
+                                   g['dist2'][n], rtol=1e-12)
+
+
 def test_boxdepth_matches_reference():
     g = np.load(os.path.join(GOLDEN, 'ref_boxdepth.npz'))
     pre = disparity.preprocess(g['raw'])
