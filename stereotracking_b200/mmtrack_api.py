@@ -144,6 +144,16 @@ class KalmanFilter:
         return tracks, costs
 
 
+class compat_dict(dict):
+    """addict.Dict stand-in for ``memo``: items also readable as attributes."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
 @MODELS.register_module(force=True)
 class OCSORTTracker_Disparity:
     """OC-SORT tracker carrying per-detection ``scales`` / ``depth``."""
@@ -151,7 +161,10 @@ class OCSORTTracker_Disparity:
     def __init__(self, obj_score_thr=0.3, init_track_thr=0.7, weight_iou_with_det_scores=True,
                  match_iou_thr=0.3, num_tentatives=3, vel_consist_weight=0.2, vel_delta_t=3, cmc=None,
                  reid=None, momentums=None, num_frames_retain=10, max_tracks=256, max_dets=256,
-                 device='cuda:0', **kwargs):
+                 device='cuda:0', keep_memo=True, **kwargs):
+        # keep_memo: keep every frame's output rows for ``memo`` / ``get`` (base_tracker.py:120-177;
+        # grows without bound like the reference's per-track lists - switch off for endless streams)
+        self.keep_memo, self._frames = bool(keep_memo), []
         if kwargs:
             raise TypeError(f'unexpected keyword arguments {sorted(kwargs)}')
         if momentums is not None:
@@ -194,6 +207,56 @@ class OCSORTTracker_Disparity:
 
     def reset(self):
         self._engine.reset()
+        self._frames = []
+
+    # memo items in the order of the reference's update(...) call (:598-605)
+    MEMO_ITEMS = ('ids', 'bboxes', 'scores', 'labels', 'scales', 'depth', 'frame_ids')
+
+    def _buffers(self, ids):
+        """Per-track lists of the memo items as BaseTracker.update builds them
+        (base_tracker.py:54-91,:102-118: one ``v[None]`` entry per frame the track was output in),
+        for the live tracks ``ids``, rebuilt from the kept per-frame outputs."""
+        if not self.keep_memo:
+            raise RuntimeError('memo / get need keep_memo=True')
+        want = {int(i) for i in ids}
+        buf = {i: {k: [] for k in self.MEMO_ITEMS} for i in want}
+        for frame_id, rows in self._frames:
+            for r, tid in enumerate(rows['ids'].tolist()):
+                if tid in want:
+                    for k in self.MEMO_ITEMS:
+                        buf[tid][k].append(torch.tensor([frame_id]) if k == 'frame_ids' else rows[k][r][None])
+        return buf
+
+    @property
+    def memo(self):
+        """base_tracker.py:120-139: the latest entry of every memo item for all live tracks."""
+        live = self.ids
+        buf = self._buffers(live)
+        outs = compat_dict()
+        for k in self.MEMO_ITEMS:
+            outs[k] = torch.cat([buf[i][k][-1] for i in live], dim=0)
+        return outs
+
+    def get(self, item, ids=None, num_samples=None, behavior=None):
+        """base_tracker.py:141-177."""
+        if ids is None:
+            ids = self.ids
+        buf = self._buffers(ids)
+        outs = []
+        for i in ids:
+            out = buf[int(i)][item]
+            if num_samples is not None:
+                out = torch.cat(out[-num_samples:], dim=0)
+                if behavior == 'mean':
+                    out = out.mean(dim=0, keepdim=True)
+                elif behavior is None:
+                    out = out[None]
+                else:
+                    raise NotImplementedError()
+            else:
+                out = out[-1]
+            outs.append(out)
+        return torch.cat(outs, dim=0)
 
     def _state(self):
         return self._engine.export_state(0)
@@ -243,6 +306,7 @@ class OCSORTTracker_Disparity:
         warp = None
         if frame_id == 0:
             self.reset_cmc()                                                   # :385-387
+            self._frames = []
         if self.with_cmc:
             # the reference estimates only in the association branch (:391, :428-429)
             w = self.estimate_camera_motion(img, metainfo) if (n > 0 and not self.empty) else None
@@ -263,6 +327,9 @@ class OCSORTTracker_Disparity:
         res.scales = out['scales'][0, :m].clone().to(tgt)
         res.depth = out['depth'][0, :m].clone().to(tgt)
         res.instances_id = out['instances_id'][0, :m].clone().to(tgt)
+        if self.keep_memo:
+            self._frames.append((int(frame_id), dict(ids=res.instances_id, bboxes=res.bboxes, scores=res.scores,
+                                                     labels=res.labels, scales=res.scales, depth=res.depth)))
         return res
 
 
@@ -272,6 +339,8 @@ class OCSORTTracker(OCSORTTracker_Disparity):
     tracker without the per-detection ``scales`` / ``depth`` fields - its diff against
     the disparity tracker is only those two fields - so it runs on the same kernels
     with scales = 1 and depth = 0 and returns bboxes / labels / scores / instances_id."""
+
+    MEMO_ITEMS = ('ids', 'bboxes', 'scores', 'labels', 'frame_ids')          # ocsort_tracker.py update(...) call
 
     def track(self, model, img, feats, data_sample, data_preprocessor=None, rescale=False, **kwargs):
         det = data_sample.pred_det_instances                 # left untouched: no scales / depth fields here

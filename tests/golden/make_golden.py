@@ -11,6 +11,7 @@ Outputs (small .npz files next to this script):
                       scale_bbox on random and edge-case boxes
   ref_boxdepth_ablation.npz  the four ablation reducers of depth_extraction_comparison.py
   ref_frontend.npz    pad + HWC->CHW + TrackDataPreprocessor_Disparity_V1 lines + stack_batch on u8 images
+  ref_memo_occlusion.npz  BaseTracker.memo / get while replaying ref_track_occlusion.npz
   ref_track_<name>.npz  OCSORT_Disparity.predict() over whole sequences:
                       inputs (raw disparity, detections) and the reference's
                       pred_track_instances + tracker state per frame
@@ -270,7 +271,7 @@ def ego_warps(gen, F):
     return warps
 
 
-def run_reference_sequence(ns, raws, dets, warps=None, tracker_cfg=None, reducer=None):
+def run_reference_sequence(ns, raws, dets, warps=None, tracker_cfg=None, reducer=None, probe=None):
     cfg = dict(TRACKER_CFG if tracker_cfg is None else tracker_cfg)
     if warps is not None:
         cfg['cmc'] = dict(method='glme_affine')
@@ -298,6 +299,8 @@ def run_reference_sequence(ns, raws, dets, warps=None, tracker_cfg=None, reducer
         res = model.predict(dict(img=img, disp_postp=disp, disp_mask=mask), [sample])[0]
         ti = res.pred_track_instances
         trk = model.tracker
+        if probe is not None:
+            probe(f, trk)
         ids = list(trk.tracks.keys())
         frames.append(dict(
             bboxes=ti.bboxes.numpy(), ids=ti.instances_id.numpy(), scores=ti.scores.numpy(),
@@ -344,6 +347,39 @@ def save_sequence(name, raws, dets, frames, warps=None):
     print(f'{name}: {len(frames)} frames, {total} track rows, max id {max(fr["num_tracks"] for fr in frames)}')
 
 
+def make_memo(ns):
+    """BaseTracker.memo / get (base_tracker.py:120-177) of the unmodified reference tracker while
+    it replays the inputs of ref_track_occlusion.npz."""
+    g = np.load(os.path.join(HERE, 'ref_track_occlusion.npz'))
+    F = len(g['raw'])
+    raws = [g['raw'][f] for f in range(F)]
+    dets = [(g['det_boxes'][f, :g['det_count'][f]], g['det_scores'][f, :g['det_count'][f]]) for f in range(F)]
+    pack = {}
+    probes = (6, 25, F - 1)
+
+    def probe(f, trk):
+        if f not in probes:
+            return
+        memo = trk.memo
+        for k in ('ids', 'bboxes', 'scores', 'labels', 'scales', 'depth', 'frame_ids'):
+            pack[f'memo_{k}_{f}'] = memo[k].numpy()
+        pack[f'get_bboxes_mean3_{f}'] = trk.get('bboxes', num_samples=3, behavior='mean').numpy()
+        pack[f'get_scores_last_{f}'] = trk.get('scores').numpy()
+        two = trk.ids[:2]
+        pack[f'get_two_{f}'] = np.asarray(two, np.int64)
+        # tracks with >= 2 entries each, so that the (1, n, 4) pieces can be concatenated
+        full = [i for i in trk.ids if len(trk.tracks[i]['bboxes']) >= 2][:2]
+        pack[f'get_full_{f}'] = np.asarray(full, np.int64)
+        if full:
+            pack[f'get_bboxes_none2_{f}'] = trk.get('bboxes', ids=full, num_samples=2).numpy()
+    frames = run_reference_sequence(ns, raws, dets, probe=probe)
+    for f in range(F):       # the replay is the stored run
+        assert np.array_equal(frames[f]['ids'], g['out_ids'][f, :g['out_count'][f]])
+    pack['probes'] = np.asarray(probes)
+    np.savez_compressed(os.path.join(HERE, 'ref_memo_occlusion.npz'), **pack)
+    print('memo:', {k: v.shape for k, v in pack.items() if k.startswith('memo_ids')})
+
+
 def make_sequences(ns, only=None):
     scen = {
         'basic': dict(cfg=SceneConfig(160, 224, 5, 8, n_clutter=0), F=36, seed=3, miss=0.05, clutter=3, blackout=()),
@@ -385,6 +421,9 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['frontend']:
         make_frontend(ns)
         sys.exit(0)
+    if sys.argv[1:] == ['memo']:
+        make_memo(ns)
+        sys.exit(0)
     if sys.argv[1:] == ['kf_gating']:
         make_kf_gating(ns)
         sys.exit(0)
@@ -394,4 +433,5 @@ if __name__ == '__main__':
     make_boxdepth_ablation(ns)
     make_frontend(ns)
     make_sequences(ns)
+    make_memo(ns)
     print('golden fixtures written to', HERE)

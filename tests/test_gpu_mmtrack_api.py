@@ -91,6 +91,49 @@ def test_model_predict_replays_reference_fixture(api, name):
     assert model.tracker.empty and model.tracker.num_tracks == 0
 
 
+def test_tracker_memo_and_get_match_reference_fixture(api):
+    """BaseTracker.memo / get (base_tracker.py:120-177) while replaying the occlusion fixture."""
+    torch, compat = api['torch'], api['compat']
+    g = np.load(os.path.join(GOLDEN, 'ref_track_occlusion.npz'))
+    mm = np.load(os.path.join(GOLDEN, 'ref_memo_occlusion.npz'))
+    det = _Det(api)
+    model = compat.MODELS.build(dict(type='OCSORT_Disparity', detector=det, motion=dict(type='KalmanFilter'),
+                                     tracker=dict(TRACKER_CFG, max_dets=64, max_tracks=128)))
+    probes = set(int(v) for v in mm['probes'])
+    for f in range(len(g['raw'])):
+        n = int(g['det_count'][f])
+        pre = api['odisp'].preprocess(g['raw'][f])
+        disp = torch.from_numpy(pre['disp'])[None, None, None].repeat(1, 1, 3, 1, 1).cuda()
+        mask = torch.from_numpy(pre['mask'])[None, None, None].cuda()
+        det.next = compat.InstanceData(bboxes=torch.from_numpy(g['det_boxes'][f, :n].copy()).cuda(),
+                                       scores=torch.from_numpy(g['det_scores'][f, :n].copy()).cuda(),
+                                       labels=torch.zeros(n, dtype=torch.int64).cuda())
+        model.predict(dict(img=torch.zeros_like(disp), disp_postp=disp, disp_mask=mask),
+                      [compat.TrackDataSample(metainfo=dict(frame_id=f))])
+        if f not in probes:
+            continue
+        trk = model.tracker
+        memo = trk.memo
+        for k in ('ids', 'labels', 'frame_ids'):
+            np.testing.assert_array_equal(memo[k].cpu().numpy(), mm[f'memo_{k}_{f}'], err_msg=f'{k} frame {f}')
+        np.testing.assert_array_equal(memo.scores.cpu().numpy(), mm[f'memo_scores_{f}'])
+        np.testing.assert_allclose(memo['bboxes'].cpu().numpy(), mm[f'memo_bboxes_{f}'], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(memo['scales'].cpu().numpy(), mm[f'memo_scales_{f}'], rtol=2e-6)
+        np.testing.assert_allclose(memo['depth'].cpu().numpy(), mm[f'memo_depth_{f}'], rtol=1e-5, equal_nan=True)
+        np.testing.assert_allclose(trk.get('bboxes', num_samples=3, behavior='mean').cpu().numpy(),
+                                   mm[f'get_bboxes_mean3_{f}'], rtol=1e-5, atol=1e-4)
+        np.testing.assert_array_equal(trk.get('scores').cpu().numpy(), mm[f'get_scores_last_{f}'])
+        full = mm[f'get_full_{f}'].tolist()
+        if full:
+            got = trk.get('bboxes', ids=full, num_samples=2)
+            assert tuple(got.shape) == mm[f'get_bboxes_none2_{f}'].shape
+            np.testing.assert_allclose(got.cpu().numpy(), mm[f'get_bboxes_none2_{f}'], rtol=1e-5, atol=1e-4)
+        with pytest.raises(NotImplementedError):
+            trk.get('bboxes', num_samples=2, behavior='median')
+    model.tracker.reset()
+    assert model.tracker._frames == []
+
+
 def test_kalman_filter_object_matches_reference_fixture(api):
     g = np.load(os.path.join(GOLDEN, 'ref_kf.npz'))
     kf = api['compat'].TASK_UTILS.build(dict(type='KalmanFilter'))
