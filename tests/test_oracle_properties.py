@@ -71,3 +71,61 @@ def test_shards_partition_the_sequences(n, world):
         assert a + ca == b                                                # contiguous, disjoint, in rank order
     sizes = [c for _, c in blocks]
     assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(8, 40), st.integers(8, 40))
+def test_depth_reducers_are_order_statistics_of_the_valid_patch(seed, H, W):
+    """extract_depth and its four ablation reducers: -1 exactly when the patch has no valid depth
+    (or the box is wider than 800 px); otherwise every statistic but `center` lies between the
+    smallest and largest valid depth of the patch, min <= median <= max, and scale in [1, 3]."""
+    from oracle import boxdepth
+    rng = np.random.default_rng(seed)
+    depth = rng.uniform(0.5, 220, (H, W)).astype(np.float32)
+    depth[rng.random((H, W)) < 0.2] = np.float32(1.6e8)          # invalid disparity -> huge depth
+    x1, y1 = rng.uniform(-3, W - 2), rng.uniform(-3, H - 2)
+    box = np.asarray([x1, y1, x1 + rng.uniform(0.5, W), y1 + rng.uniform(0.5, H)], np.float32)
+    b = boxdepth.trunc_box(box)
+    patch = depth[b[1]:b[3], b[0]:b[2]]
+    valid = patch[(patch < 150) & (patch > 0)]
+    with np.errstate(all='ignore'):
+        results = {'window': boxdepth.box_depth(depth, box)}
+        for mode in boxdepth.ABLATION_MODES:
+            try:
+                results[mode] = boxdepth.box_depth_ablation(depth, box, mode)
+            except IndexError:
+                assert mode == 'center'
+    for mode, (d, s) in results.items():
+        if valid.size == 0:
+            assert d == -1 and s == 1.0
+            continue
+        assert d != -1
+        if np.isnan(np.float32(d)):
+            assert valid.size == 1 and mode in ('window', 'truncated_mean')       # sorted[:-1] of one element
+            continue
+        assert 1.0 <= s <= 3.0
+        if mode != 'center':
+            assert valid.min() <= d <= valid.max()
+    if valid.size:
+        assert results['median'][0] == np.float32(np.median(valid))
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 70), st.integers(1, 70), st.booleans())
+def test_pack_image_layout(seed, H, W, swap):
+    """K1b's oracle: padded to /32, the image region is the (optionally channel-swapped) transpose,
+    the pad is the pad value, normalisation is affine per channel."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+    out = disparity.pack_image(img, pad_val=(7, 8, 9), swap_rb=swap)
+    assert out.dtype == np.float32 and out.shape[1] % 32 == 0 and out.shape[2] % 32 == 0
+    assert out.shape[1] - H < 32 and out.shape[2] - W < 32
+    src = img[..., ::-1] if swap else img
+    assert np.array_equal(out[:, :H, :W], src.transpose(2, 0, 1).astype(np.float32))
+    pad = (9, 8, 7) if swap else (7, 8, 9)
+    for c in range(3):
+        assert (out[c, H:, :] == pad[c]).all() and (out[c, :, W:] == pad[c]).all()
+    mean, std = (10.0, 20.0, 30.0), (2.0, 4.0, 8.0)
+    norm = disparity.pack_image(img, pad_val=(7, 8, 9), mean=mean, std=std, swap_rb=swap)
+    for c in range(3):
+        assert np.array_equal(norm[c], (out[c] - np.float32(mean[c])) / np.float32(std[c]))
