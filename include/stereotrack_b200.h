@@ -274,6 +274,16 @@ int st_export_state(st_handle *h, int seq, int64_t *ids_host, double *mean_host,
                     float *velocity_host, uint8_t *flags_host, int32_t *hits_host,
                     int32_t *last_frame_host, int64_t *num_tracks_host);
 
+/* Checkpoint / resume of the whole tracker state of a handle (the reference never checkpoints
+ * its tracker: it restarts at frame_id == 0, ocsort_tracker_disparity.py:385-387).  A snapshot
+ * is a HOST buffer of st_snapshot_bytes(h) bytes; save and load synchronise `stream`; no step
+ * may be in flight on another stream.  Loading needs a handle created with the same
+ * max_sequences / max_tracks / max_dets / max_candidates (else ST_ERR_INVALID_ARG); the
+ * tracker thresholds of the loading handle stay its own. */
+long long st_snapshot_bytes(st_handle *h);
+int st_snapshot_save(st_handle *h, void *buf_host, long long bytes, void *stream);
+int st_snapshot_load(st_handle *h, const void *buf_host, long long bytes, void *stream);
+
 /* Batched Kalman primitives on caller arrays (KalmanFilter.initiate/predict/
  * update of motion/kalman_filter.py:60-189), one warp per track: mean [n,8],
  * cov [n,64] f64 in place, z [n,4] f32 (cx,cy,a,h). op: 0 initiate, 1 predict,

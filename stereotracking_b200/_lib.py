@@ -77,6 +77,9 @@ _SIGNATURES = {
     'st_pipeline_read_trace': (_I, [_P, _P, _I]),
     'st_export_state': (_I, [_P, _I] + [_P] * 8),
     'st_kalman_batch': (_I, [_I, _I, _P, _P, _P, _P]),
+    'st_snapshot_bytes': (C.c_longlong, [_P]),
+    'st_snapshot_save': (_I, [_P, _P, C.c_longlong, _P]),
+    'st_snapshot_load': (_I, [_P, _P, C.c_longlong, _P]),
     'st_kalman_project': (_I, [_I, _P, _P, _P, _P, _P]),
     'st_kalman_gating': (_I, [_I, _P, _P, _I, _P, _I, _P, _P]),
     'st_lapjv_batch': (_I, [_P, _I, _I, _I, _P, C.c_double, _I, _P, _P, _P]),

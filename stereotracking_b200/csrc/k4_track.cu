@@ -14,6 +14,7 @@
 // Track state lives in the handle as a structure of arrays; `order` keeps the
 // live slots in ascending-id order, which is the reference's dict order.
 #include <new>
+#include <cstring>
 #include "st_common.cuh"
 #include "kalman.cuh"
 #include "lapjv.cuh"
@@ -882,6 +883,51 @@ extern "C" int st_reset(st_handle *h, const uint8_t *seq_mask, void *stream) {
     if (!h) return ST_ERR_INVALID_ARG;
     k4_reset<<<h->cfg.max_sequences, 128, 0, (cudaStream_t)stream>>>(h->st, h->cfg.max_tracks, seq_mask);
     return st_last_launch();
+}
+
+// ---- checkpoint / resume ----------------------------------------------------------------
+// Every device array of a handle lives in one allocation (layout()), so a snapshot is that
+// allocation behind a small header; loading checks that the capacities that determine the
+// layout are the same.  The thresholds of the loading handle stay its own.
+namespace {
+struct SnapshotHeader {
+    uint32_t magic, abi;
+    int32_t max_sequences, max_tracks, max_dets, max_candidates;
+    uint64_t payload;
+};
+constexpr uint32_t kSnapshotMagic = 0x4b525453u;       // "STRK"
+}  // namespace
+
+extern "C" long long st_snapshot_bytes(st_handle *h) {
+    return h ? (long long)(sizeof(SnapshotHeader) + h->all_bytes) : (long long)ST_ERR_INVALID_ARG;
+}
+
+extern "C" int st_snapshot_save(st_handle *h, void *buf_host, long long bytes, void *stream) {
+    if (!h || !buf_host || bytes < st_snapshot_bytes(h)) return ST_ERR_INVALID_ARG;
+    SnapshotHeader hd{kSnapshotMagic, (uint32_t)ST_ABI_VERSION, h->cfg.max_sequences, h->cfg.max_tracks,
+                      h->cfg.max_dets, h->cfg.max_candidates, (uint64_t)h->all_bytes};
+    memcpy(buf_host, &hd, sizeof(hd));
+    cudaStream_t st = (cudaStream_t)stream;
+    ST_CUDA_OK(cudaMemcpyAsync(static_cast<unsigned char *>(buf_host) + sizeof(hd), h->all_mem, h->all_bytes,
+                               cudaMemcpyDeviceToHost, st));
+    ST_CUDA_OK(cudaStreamSynchronize(st));
+    return ST_OK;
+}
+
+extern "C" int st_snapshot_load(st_handle *h, const void *buf_host, long long bytes, void *stream) {
+    if (!h || !buf_host || bytes < (long long)sizeof(SnapshotHeader)) return ST_ERR_INVALID_ARG;
+    SnapshotHeader hd;
+    memcpy(&hd, buf_host, sizeof(hd));
+    if (hd.magic != kSnapshotMagic || hd.abi != (uint32_t)ST_ABI_VERSION || hd.max_sequences != h->cfg.max_sequences ||
+        hd.max_tracks != h->cfg.max_tracks || hd.max_dets != h->cfg.max_dets ||
+        hd.max_candidates != h->cfg.max_candidates || hd.payload != (uint64_t)h->all_bytes ||
+        bytes < (long long)(sizeof(hd) + hd.payload))
+        return ST_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    ST_CUDA_OK(cudaMemcpyAsync(h->all_mem, static_cast<const unsigned char *>(buf_host) + sizeof(hd), h->all_bytes,
+                               cudaMemcpyHostToDevice, st));
+    ST_CUDA_OK(cudaStreamSynchronize(st));
+    return ST_OK;
 }
 
 extern "C" int st_read_status(st_handle *h, int32_t *status_host, int S) {

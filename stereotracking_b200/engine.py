@@ -372,6 +372,24 @@ class StereoTrackEngine:
         _lib.check(self.lib.st_read_status(self._h, st.ctypes.data_as(C.c_void_p), self.cfg.n_seq))
         return st
 
+    def save_state(self):
+        """Snapshot of the whole tracker state (all sequences) as a uint8 NumPy array
+        (st_snapshot_save); join any frame pipeline first."""
+        import numpy as np
+        n = int(self.lib.st_snapshot_bytes(self._h))
+        if n < 0:
+            _lib.check(n, 'st_snapshot_bytes')
+        buf = np.empty(n, np.uint8)
+        _lib.check(self.lib.st_snapshot_save(self._h, buf.ctypes.data, n, self._stream()), 'st_snapshot_save')
+        return buf
+
+    def load_state(self, buf):
+        """Restore a snapshot taken by ``save_state`` on an engine of the same capacities."""
+        import numpy as np
+        buf = np.ascontiguousarray(np.frombuffer(buf, np.uint8) if isinstance(buf, (bytes, bytearray)) else buf,
+                                   dtype=np.uint8)
+        _lib.check(self.lib.st_snapshot_load(self._h, buf.ctypes.data, buf.size, self._stream()), 'st_snapshot_load')
+
     def export_state(self, seq):
         import numpy as np
         T = self.cfg.max_tracks

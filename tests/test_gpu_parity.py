@@ -357,6 +357,55 @@ def test_tracker_matches_reference_fixture(mods, name):
     assert eng.status().max() == 0
 
 
+def test_snapshot_resume_continues_identically(mods):
+    """Checkpoint / resume: a snapshot taken at frame 20 of the occlusion fixture, restored into the
+    same engine and into a fresh one, continues with the same outputs and state as the
+    uninterrupted run (which test_tracker_matches_reference_fixture pins to the reference)."""
+    g = np.load(os.path.join(GOLDEN, 'ref_track_occlusion.npz'))
+    F, cut = len(g['raw']), 20
+
+    def run(eng, frames):
+        outs = []
+        for f in frames:
+            n = int(g['det_count'][f])
+            depth, _, _ = eng.disp2depth(cuda(g['raw'][f][None]))
+            eng.det_boxes.zero_(); eng.det_scores.zero_(); eng.det_labels.zero_()
+            eng.det_boxes[0, :n] = cuda(g['det_boxes'][f, :n])
+            eng.det_scores[0, :n] = cuda(g['det_scores'][f, :n])
+            eng.det_counts[0] = n
+            eng.frame_ids[0] = f
+            eng.step_from_dets(depth)
+            r = eng.results()[0]
+            outs.append({k: np.array(r[k]) for k in ('instances_id', 'bboxes', 'scores', 'scales', 'depth')})
+        return outs, eng.export_state(0)
+
+    def same(a, b):
+        for x, y in zip(a[0], b[0]):
+            for k in x:
+                np.testing.assert_array_equal(x[k], y[k])
+        for k in ('ids', 'tentative', 'tracked', 'mean', 'cov', 'velocity'):
+            np.testing.assert_array_equal(a[1][k], b[1][k])
+        assert a[1]['num_tracks'] == b[1]['num_tracks']
+
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1, max_dets=64, max_tracks=128))
+    run(eng, range(cut))
+    snap = eng.save_state()
+    first = run(eng, range(cut, F))
+    m = int(g['out_count'][F - 1])
+    np.testing.assert_array_equal(first[0][-1]['instances_id'], g['out_ids'][F - 1, :m])
+    eng.load_state(snap)
+    same(first, run(eng, range(cut, F)))
+    other = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1, max_dets=64, max_tracks=128))
+    other.load_state(snap.tobytes())
+    same(first, run(other, range(cut, F)))
+    small = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1, max_dets=64, max_tracks=64))
+    from stereotracking_b200._lib import StereoTrackError
+    with pytest.raises(StereoTrackError):
+        small.load_state(snap)                           # other capacities: refused, state untouched
+    with pytest.raises(StereoTrackError):
+        eng.load_state(snap[:100])
+
+
 def _run_pipeline(mods, cfg, S, F, seed, max_dets=256, max_cand=4096, check_state=False):
     gen = mods.SyntheticStereo(cfg, S, F, seed=seed)
     fr = gen.frames(0, F)
