@@ -25,6 +25,7 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get('GOLDEN_OUT', HERE)       # where the fixtures are written (and re-read by later steps)
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
@@ -66,7 +67,7 @@ def make_kf(ns):
             zz = (m[:4] + rng.normal(0, [2, 2, 0.01, 1])).astype(np.float32)
             m, c = kf.update(m, c, zz)
             means.append(m.copy()); covs.append(c.copy()); zs.append(zz.astype(np.float64)); ops.append(2)
-    np.savez_compressed(os.path.join(HERE, 'ref_kf.npz'), mean=np.stack(means),
+    np.savez_compressed(os.path.join(OUT, 'ref_kf.npz'), mean=np.stack(means),
                         cov=np.stack(covs), z=np.stack(zs), op=np.asarray(ops),
                         chain_start=np.asarray([0, ops.index(0, 1)]))
 
@@ -75,7 +76,7 @@ def make_kf_gating(ns):
     """KalmanFilter.project / gating_distance / track of the unmodified reference on the states
     of ref_kf.npz."""
     import types
-    g = np.load(os.path.join(HERE, 'ref_kf.npz'))
+    g = np.load(os.path.join(OUT, 'ref_kf.npz'))
     rng = np.random.default_rng(13)
     kf = ns.KalmanFilterRaw()
     idx = np.arange(0, len(g['op']), 3)
@@ -92,7 +93,7 @@ def make_kf_gating(ns):
               9: types.SimpleNamespace(mean=g['mean'][30].copy(), covariance=g['cov'][30].copy())}
     boxes = torch.from_numpy(np.concatenate([meas[1][:3], meas[10][:3]]))
     _, costs = kf.track(tracks, boxes)
-    np.savez_compressed(os.path.join(HERE, 'ref_kf_gating.npz'), idx=idx, pmean=np.stack(pm), pcov=np.stack(pc),
+    np.savez_compressed(os.path.join(OUT, 'ref_kf_gating.npz'), idx=idx, pmean=np.stack(pm), pcov=np.stack(pc),
                         meas=np.stack(meas), dist4=np.stack(d4), dist2=np.stack(d2),
                         track_in=np.asarray([5, 30]), track_boxes=boxes.numpy(), track_costs=costs,
                         track_mean=np.stack([tracks[7].mean, tracks[9].mean]),
@@ -132,7 +133,7 @@ def make_boxdepth(ns):
     inst = ns.InstanceData(bboxes=boxes.clone())
     inst2, dv = model.bbox_postp_depth(inst, disp, None)
     np.savez_compressed(
-        os.path.join(HERE, 'ref_boxdepth.npz'), raw=raw, boxes=boxes.numpy(),
+        os.path.join(OUT, 'ref_boxdepth.npz'), raw=raw, boxes=boxes.numpy(),
         depth_map=depth_t.numpy().squeeze(), d=np.asarray(d, np.float32),
         scales=np.asarray(s, np.float32), inflated=inst2.bboxes.numpy(),
         deflated=ns.scale_bbox(inst2.bboxes, 1 / inst2.scales).numpy(),
@@ -147,7 +148,7 @@ def make_boxdepth_ablation(ns):
     IndexError of ``center`` (centre pixel outside the map) can be recorded per box."""
     import sys as _sys
     mod = _sys.modules['mmtrack.models.mot.depth_extraction_comparison']
-    base = np.load(os.path.join(HERE, 'ref_boxdepth.npz'))
+    base = np.load(os.path.join(OUT, 'ref_boxdepth.npz'))
     rng = np.random.default_rng(17)
     raw2 = rng.integers(8, 700, (200, 320)).astype(np.uint16)
     raw2 //= 4                                   # many duplicates, few distinct values
@@ -179,7 +180,7 @@ def make_boxdepth_ablation(ns):
                 except IndexError:
                     err[i] = 1
             out[f'd_{mode}_{tag}'], out[f'scale_{mode}_{tag}'], out[f'oob_{mode}_{tag}'] = d, sc, err
-    np.savez_compressed(os.path.join(HERE, 'ref_boxdepth_ablation.npz'), **out)
+    np.savez_compressed(os.path.join(OUT, 'ref_boxdepth_ablation.npz'), **out)
     print('ablation:', {k: (int(np.isnan(v).sum()) if v.dtype.kind == 'f' else int(v.sum()))
                         for k, v in out.items() if k.startswith(('oob_',))})
 
@@ -218,7 +219,7 @@ def make_frontend(ns):
             res = misc.stack_batch(imgs, 32, 0)                                                # :51-52
             assert res.shape == (1, 1, 3, Hp, Wp)
             out[f'out_{name}_{tag}'] = res[0, 0].numpy()
-    np.savez_compressed(os.path.join(HERE, 'ref_frontend.npz'), **out)
+    np.savez_compressed(os.path.join(OUT, 'ref_frontend.npz'), **out)
     print('frontend:', {k: v.shape for k, v in out.items()})
 
 
@@ -342,7 +343,7 @@ def save_sequence(name, raws, dets, frames, warps=None):
         cov[i, :len(fr['st_cov'])] = fr['st_cov']
     pack['out_st_cov'] = cov
     pack['num_tracks'] = np.asarray([fr['num_tracks'] for fr in frames], np.int64)
-    np.savez_compressed(os.path.join(HERE, f'ref_track_{name}.npz'), **pack)
+    np.savez_compressed(os.path.join(OUT, f'ref_track_{name}.npz'), **pack)
     total = sum(len(fr['ids']) for fr in frames)
     print(f'{name}: {len(frames)} frames, {total} track rows, max id {max(fr["num_tracks"] for fr in frames)}')
 
@@ -350,7 +351,7 @@ def save_sequence(name, raws, dets, frames, warps=None):
 def make_memo(ns):
     """BaseTracker.memo / get (base_tracker.py:120-177) of the unmodified reference tracker while
     it replays the inputs of ref_track_occlusion.npz."""
-    g = np.load(os.path.join(HERE, 'ref_track_occlusion.npz'))
+    g = np.load(os.path.join(OUT, 'ref_track_occlusion.npz'))
     F = len(g['raw'])
     raws = [g['raw'][f] for f in range(F)]
     dets = [(g['det_boxes'][f, :g['det_count'][f]], g['det_scores'][f, :g['det_count'][f]]) for f in range(F)]
@@ -376,7 +377,7 @@ def make_memo(ns):
     for f in range(F):       # the replay is the stored run
         assert np.array_equal(frames[f]['ids'], g['out_ids'][f, :g['out_count'][f]])
     pack['probes'] = np.asarray(probes)
-    np.savez_compressed(os.path.join(HERE, 'ref_memo_occlusion.npz'), **pack)
+    np.savez_compressed(os.path.join(OUT, 'ref_memo_occlusion.npz'), **pack)
     print('memo:', {k: v.shape for k, v in pack.items() if k.startswith('memo_ids')})
 
 
@@ -434,4 +435,4 @@ if __name__ == '__main__':
     make_frontend(ns)
     make_sequences(ns)
     make_memo(ns)
-    print('golden fixtures written to', HERE)
+    print('golden fixtures written to', OUT)
