@@ -13,8 +13,11 @@
  *  - every data pointer is a DEVICE pointer into caller-owned memory unless the
  *    parameter name ends in _host;
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
- *    never allocates or frees caller memory, never synchronises, and is safe to
- *    capture in a CUDA graph (st_create / st_destroy / st_export_state excepted);
+ *    never allocates or frees caller memory and never synchronises (st_create /
+ *    st_destroy / st_export_state / st_read_* / st_snapshot_* excepted).  The per-frame
+ *    calls consist of kernel launches, memsets and event fork/join on streams the
+ *    library owns, i.e. the stream-capturable subset, but capture into a CUDA graph
+ *    is not exercised by the tests of this round;
  *  - return value: 0 = ok, < 0 = error (st_error_string); nothing throws;
  *  - S = sequences processed in lockstep (one frame each per call); per-sequence
  *    arrays are padded to a fixed capacity with a separate count array;
