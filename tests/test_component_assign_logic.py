@@ -10,7 +10,7 @@ import numpy as np
 from hypothesis import given, settings, strategies as st
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
-from emulate_components import component_assign, label_components  # noqa: E402
+from emulate_components import component_assign, component_assign_lanes, label_components  # noqa: E402
 from oracle.lapjv import lapjv  # noqa: E402
 
 
@@ -30,6 +30,28 @@ def test_certified_results_equal_the_jv_restatement(seed, R, C, density):
     if ok:
         rx, ry = lapjv(cost, 0.9)
         assert np.array_equal(x, rx) and np.array_equal(y, ry)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 40), st.integers(1, 40), st.sampled_from([0.02, 0.05, 0.1]))
+def test_lane_formulation_agrees_with_the_set_formulation(seed, R, C, density):
+    """The warp-shaped restatement (bitmask closure, base-(c+1) codes, per-lane best / runner-up)
+    certifies exactly the problems the straightforward one certifies (unless more than 32 rows are
+    active), with the same result."""
+    rng = np.random.default_rng(seed)
+    cost = _sparse_cost(rng, R, C, density)
+    if seed % 3 == 0 and R > 1:
+        cost[1] = cost[0]                               # sprinkle exact ties
+    x, y, ok = component_assign(cost, 0.9)
+    lx, ly, lok = component_assign_lanes(cost, 0.9)
+    if lok:
+        assert ok and np.array_equal(x, lx) and np.array_equal(y, ly)
+        rx, ry = lapjv(cost, 0.9)
+        assert np.array_equal(lx, rx) and np.array_equal(ly, ry)
+    elif ok:
+        adm = cost < 0.9
+        iso = [(adm[i].sum() == 1 and adm[:, np.nonzero(adm[i])[0][-1]].sum() == 1) for i in range(R)]
+        assert sum(adm[i].any() and not iso[i] for i in range(R)) > 32
 
 
 @settings(max_examples=60, deadline=None)

@@ -79,3 +79,87 @@ def component_assign(cost, limit, max_side=4, eps=1e-9):
         for i, j in match.items():
             x[i], y[j] = j, i
     return x, y, True
+
+
+def component_assign_lanes(cost, limit, max_side=4, eps=1e-9):
+    """The same algorithm in the form one warp would run it (the transcription target for
+    lapjv.cuh): lane t owns the t-th ACTIVE row (rows that are neither edgeless nor an isolated
+    pair) and its admissibility bitmask; closure of the masks by shuffles; one leader per
+    component; the component's partial matchings enumerated as base-(c+1) codes, code
+    `lane + 32 k` on lane `lane`; best / runner-up reduced over the warp."""
+    cost = np.asarray(cost, np.float32)
+    R, C = cost.shape
+    x, y = np.full(R, -1, np.int32), np.full(C, -1, np.int32)
+    if R == 0 or C == 0:
+        return x, y, True
+    c64 = cost.astype(np.float64)
+    if np.isnan(c64).any() or (np.abs(c64 - limit) <= 2 * eps).any():
+        return x, y, False
+    adm = cost < limit
+    row_cnt, col_cnt = adm.sum(1), adm.sum(0)
+    active = []
+    for i in range(R):
+        if row_cnt[i] == 1 and col_cnt[np.nonzero(adm[i])[0][-1]] == 1:
+            j = int(np.nonzero(adm[i])[0][-1])
+            x[i], y[j] = j, i
+        elif row_cnt[i] > 0:
+            active.append(i)
+    n = len(active)
+    if n > 32:
+        return x, y, False
+    mask = [sum(1 << int(j) for j in np.nonzero(adm[i])[0]) for i in active]
+    while True:                                   # closure: in-place, lane k broadcasts in turn
+        changed = False
+        for k in range(n):
+            mk = mask[k]
+            for t in range(n):
+                if mask[t] & mk and mask[t] | mk != mask[t]:
+                    mask[t] |= mk
+                    changed = True
+        if not changed:
+            break
+    done = [False] * n
+    while not all(done):
+        leader = done.index(False)
+        lanes = [t for t in range(n) if mask[t] == mask[leader]]
+        rows = [active[t] for t in lanes]
+        cols = [j for j in range(C) if mask[leader] >> j & 1]
+        for t in lanes:
+            done[t] = True
+        r, c = len(rows), len(cols)
+        if r > max_side or c > max_side:
+            return x, y, False
+        base, n_codes = c + 1, (c + 1) ** r
+        lane_best = [(np.inf, -1)] * 32
+        lane_second = [np.inf] * 32
+        for code in range(n_codes):
+            lane = code % 32
+            used, total, ok, rest = 0, 0.0, True, code
+            for k in range(r):
+                d, rest = rest % base, rest // base
+                if d == 0:
+                    continue
+                j = cols[d - 1]
+                if not adm[rows[k], j] or used >> j & 1:
+                    ok = False
+                    break
+                used |= 1 << j
+                total += c64[rows[k], j] - limit
+            if not ok:
+                continue
+            if total < lane_best[lane][0]:
+                lane_second[lane] = lane_best[lane][0]
+                lane_best[lane] = (total, code)
+            elif total < lane_second[lane]:
+                lane_second[lane] = total
+        win = min(range(32), key=lambda q: (lane_best[q][0], q))
+        best, code = lane_best[win]
+        second = min([lane_second[q] for q in range(32)] + [lane_best[q][0] for q in range(32) if q != win])
+        if not second - best > eps:
+            return x, y, False
+        rest = code
+        for k in range(r):
+            d, rest = rest % base, rest // base
+            if d:
+                x[rows[k]], y[cols[d - 1]] = cols[d - 1], rows[k]
+    return x, y, True
