@@ -60,7 +60,7 @@ def main():
         R, C = dists.shape
         if dists.size:
             limit = 1 - self.match_iou_thr
-            adm = dists < limit
+            adm = dists.astype(np.float64) < limit
             comps = components(adm)
             nontrivial = [c for c in comps if not (len(c[0]) == 1 and len(c[1]) == 1)]
             stats['problems'] += 1

@@ -41,7 +41,7 @@ def solve_component(cost, rows, cols, limit, eps):
     """Enumerate every partial matching of the component on admissible edges.
     Returns (assignment dict row->col, unique)."""
     best, second, arg = 0.0, np.inf, ()              # the empty matching
-    options = [[None] + [j for j in cols if cost[i, j] < limit] for i in rows]
+    options = [[None] + [j for j in cols if float(cost[i, j]) < limit] for i in rows]
     first = True
     for pick in itertools.product(*options):
         used = [j for j in pick if j is not None]
@@ -66,7 +66,7 @@ def component_assign(cost, limit, max_side=4, eps=1e-9):
         return x, y, True
     if (np.abs(cost.astype(np.float64) - limit) <= 2 * eps).any():
         return x, y, False
-    adm = cost < limit
+    adm = cost.astype(np.float64) < limit              # float64 like the kernel (NumPy 2 would compare in float32)
     row_label, col_label, _ = label_components(adm)
     for root in np.unique(row_label[row_label >= 0]):
         rows = np.nonzero(row_label == root)[0].tolist()
@@ -95,7 +95,7 @@ def component_assign_lanes(cost, limit, max_side=4, eps=1e-9):
     c64 = cost.astype(np.float64)
     if np.isnan(c64).any() or (np.abs(c64 - limit) <= 2 * eps).any():
         return x, y, False
-    adm = cost < limit
+    adm = c64 < limit                                  # float64 like the kernel
     row_cnt, col_cnt = adm.sum(1), adm.sum(0)
     active = []
     for i in range(R):
