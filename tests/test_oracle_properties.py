@@ -129,3 +129,14 @@ def test_pack_image_layout(seed, H, W, swap):
     norm = disparity.pack_image(img, pad_val=(7, 8, 9), mean=mean, std=std, swap_rb=swap)
     for c in range(3):
         assert np.array_equal(norm[c], (out[c] - np.float32(mean[c])) / np.float32(std[c]))
+
+
+def test_depth_is_strictly_decreasing_in_the_raw_code():
+    """Basis of the round-2 plan to take K3's order statistics on the 16-bit raw codes: over all
+    valid codes the float32 depth Z = f*B / (raw/16 + 1e-6) is strictly decreasing, so sorting by
+    depth is sorting by code in reverse, and equal depths are equal codes."""
+    raw = np.arange(1, 65535, dtype=np.uint16)[None, :]
+    depth = disparity.preprocess(raw, size_divisor=1)['depth'][0, :65534]
+    assert depth.dtype == np.float32 and np.all(np.diff(depth) < 0)
+    valid = (depth < 150) & (depth > 0)
+    assert valid.sum() == 65534 - 17 and not valid[:17].any()       # raw codes 1..17 are deeper than 150 m
