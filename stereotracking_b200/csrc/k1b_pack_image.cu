@@ -103,12 +103,15 @@ extern "C" int st_pack_image(const uint8_t *img, int S, int H, int W, int Hp, in
     }
     p.swap_rb = swap_rb != 0;
     p.normalise = mean_host != nullptr;
-    static int sms = 0;
+    static int sms = 0, resident_v4 = 0;
     if (!sms) {
-        int dev = 0;
+        int dev = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1b_pack_image_v4, 256, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 8;
+        resident_v4 = sms * per_sm;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (W % 4 == 0) && (Wp % 4 == 0) && ((uintptr_t)img % 4 == 0) && ((uintptr_t)out % 16 == 0) &&
@@ -116,7 +119,9 @@ extern "C" int st_pack_image(const uint8_t *img, int S, int H, int W, int Hp, in
     if (vec) {
         const long long per_seq = (long long)Hp * (Wp / 4);
         long long gx = (per_seq + 255) / 256;
-        const long long share = ((long long)sms * 8 + S - 1) / S;       // about one resident wave in total
+        // one resident wave in total, rounded DOWN: every CTA has the same share of a frame, so
+        // CTAs beyond the resident count would run as a second, nearly empty wave
+        const long long share = resident_v4 / S > 0 ? resident_v4 / S : 1;
         if (gx > share) gx = share;
         k1b_pack_image_v4<<<dim3((unsigned)gx, (unsigned)S), 256, 0, st>>>(img, H, W, Hp, Wp, p, out);
     } else {
