@@ -41,8 +41,12 @@ def test_b200_arm_fails_loudly_without_cuda():
 def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
     """The driver launches the reference arm like the B200 arm (torchrun, N ranks): rank 0 alone
     measures and prints, the other ranks exit 0 without work."""
+    import socket
+    with socket.socket() as sock:                        # a free rendezvous port
+        sock.bind(('127.0.0.1', 0))
+        port = sock.getsockname()[1]
     res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-                          '--master-addr', '127.0.0.1', '--master-port', '29541', os.path.join(ROOT, 'bench.py'),
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'bench.py'),
                           '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '1', '--cpu-seqs', '2'],
                          capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
