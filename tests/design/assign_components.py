@@ -4,7 +4,7 @@ rows of the stage-1 cost matrix split into connected components of the ADMISSIBL
 assignment, so each component is an independent small LAP that a separate warp could solve.
 Runs the oracle (test infrastructure) - this is an analysis tool, not part of the product.
 
-    python tools/assign_components.py [n_sequences] [n_frames] [C2|C3|C4]
+    python tests/design/assign_components.py [n_sequences] [n_frames] [C2|C3|C4]
 """
 import collections
 import os
@@ -12,7 +12,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import tracker as otracker  # noqa: E402
 from oracle.model import StereoTrackOracle  # noqa: E402
 from stereotracking_b200.synthetic import CONFIGS, SyntheticStereo  # noqa: E402

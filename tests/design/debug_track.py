@@ -1,6 +1,6 @@
 """Drive st_track_step alone with synthetic detections and compare with the oracle tracker."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, ctypes as C
 from stereotracking_b200.engine import EngineConfig, StereoTrackEngine
 from oracle.tracker import OCSortDisparityOracle

@@ -1,7 +1,7 @@
 """Python emulation of csrc/lapjv.cuh solve_warp (same parallel formulation),
 used to debug the device algorithm offline against oracle/lapjv."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 BIG = 1e300
 

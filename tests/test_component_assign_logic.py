@@ -1,4 +1,4 @@
-"""Soundness of the component-wise assignment planned for K4 (tools/emulate_components.py, a CPU
+"""Soundness of the component-wise assignment planned for K4 (tests/design/emulate_components.py, a CPU
 restatement; the kernel of this round does not use it yet): whenever it certifies a result, the
 result equals the oracle's lap.lapjv restatement - on random sparse problems, on problems with
 duplicated rows/columns (exact ties must be refused, not guessed), and on the stage-1/2/3 cost
@@ -9,7 +9,7 @@ import sys
 import numpy as np
 from hypothesis import given, settings, strategies as st
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'design'))
 from emulate_components import component_assign, component_assign_lanes, label_components  # noqa: E402
 from oracle.lapjv import lapjv  # noqa: E402
 
