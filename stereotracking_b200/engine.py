@@ -351,7 +351,7 @@ class StereoTrackEngine:
             k['obj'][l] = obj_ptrs[l]
         _lib.check(self.lib.st_frame_step(self._h, n_seq, C.byref(io), self._stream()), 'st_frame_step')
 
-    KERNELS_PER_FRAME = 13     # K1, K2 x4, K3 x3, K4/K5, scale, K3 x3
+    KERNELS_PER_FRAME = 13     # K1, K2 x2 (score, sort+NMS), K3 x4 (classify, warp, table, overflow), K4, deflate, K3 x4
 
     def results(self):
         """Host copies of the current outputs, one dict per sequence."""
