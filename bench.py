@@ -35,6 +35,11 @@ METRIC = 'tracked_frames_per_sec'
 # (118.0 MB read + 188.0 MB written; the rest of the 241 MB written is still in L2 at kernel end)
 K1_TRAFFIC_BYTES_C2_S64 = 117.98e6 + 188.03e6
 UNIT = 'frames/s'
+# engine capacities per workload (tracks / detections / post-threshold candidates per sequence)
+CAPS = dict(C1=dict(max_dets=256, max_tracks=256, max_candidates=2048),
+            C2=dict(max_dets=256, max_tracks=256, max_candidates=2048),
+            C3=dict(max_dets=512, max_tracks=512, max_candidates=4096),
+            C4=dict(max_dets=1024, max_tracks=512, max_candidates=4096))
 
 
 def parse():
@@ -49,6 +54,13 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--groups', type=int, default=1, help='independent lockstep groups (handles) per GPU')
     ap.add_argument('--depth', type=int, default=5, help='frames in flight in the frame pipeline (1 = no overlap)')
+    ap.add_argument('--depth-source', default='raw', choices=['raw', 'map'],
+                    help="headline mode: 'raw' = K3 gathers from the raw u16 frame, no depth map is written; "
+                         "'map' = K1 writes the float32 depth map and K3 gathers from it.  Both are measured.")
+    ap.add_argument('--reps', type=int, default=5, help='repetitions of the K-step timed region (median reported)')
+    ap.add_argument('--e2e-reps', type=int, default=3)
+    ap.add_argument('--graph', type=int, default=1, help='replay each frame as a CUDA graph (0 = stream launches)')
+    ap.add_argument('--parity-seqs', type=int, default=4, help='sequences replayed through the oracle after the timed regions')
     return ap.parse_args()
 
 
@@ -229,78 +241,121 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
-    from stereotracking_b200.engine import EngineConfig, LockstepGroups, StereoTrackEngine
+    from stereotracking_b200.engine import EngineConfig, FrameBuffers, FrameInputs, LockstepGroups, StereoTrackEngine
 
     from stereotracking_b200 import shard
+    # bind to the GPU's NUMA node BEFORE any pinned host allocation (first touch places the pages)
     numa = shard.bind_to_gpu_numa(local) if world > 1 else dict(bound=False, reason='single process')
     # whole sequences per rank (video_sampler.py:50-69): rank r owns sequences [first, first + S)
     first_seq, n_own = shard.shard_sequences(S * world, world, rank)
     assert n_own == S
     raw, cls, box, obj = generate(cfg, S, F, 20240604 + 1000 + first_seq, dev)
-    eng = StereoTrackEngine(EngineConfig(n_seq=S, max_dets=256, max_tracks=256, max_candidates=2048), device=dev)
-    eng.make_frame_io(raw.shape[1:], [c.shape[-2:] for c in cls])      # allocates eng.depth_map
+    level_hw = [c.shape[-2:] for c in cls]
+    caps = CAPS.get(args.workload, CAPS['C2'])
+    eng = StereoTrackEngine(EngineConfig(n_seq=S, **caps), device=dev)
+    eng.make_frame_io(raw.shape[1:], level_hw)      # allocates eng.depth_map
     stream = torch.cuda.current_stream(dev)
-    groups = LockstepGroups(S, args.groups, device=dev, depth=args.depth, max_dets=256, max_tracks=256,
-                            max_candidates=2048)
-    groups.bind(raw.shape[1:], [c.shape[-2:] for c in cls])
-    groups.plan(raw, cls, box, obj)      # device addresses of every (frame, group) slice, computed once
+    modes = [args.depth_source, 'map' if args.depth_source == 'raw' else 'raw']
+    groups_of = {}
+    for mode in modes:
+        g = LockstepGroups(S, args.groups, device=dev, depth=args.depth, depth_source=mode, **caps)
+        g.bind(raw.shape[1:], level_hw)
+        g.plan(raw, cls, box, obj)      # device addresses of every (frame, group) slice, computed once
+        if args.graph:
+            g.use_graphs(True)
+        groups_of[mode] = g
+    groups = groups_of[modes[0]]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def run_steps(f0, f1, events=None):
+    def run_stages(f0, f1, events, mode):
+        """the same launches as the pipeline, one C call per stage on ONE stream so that each stage
+        can be bracketed by events (launch gaps of an idle stream included)"""
+        Hp, Wp = cfg.padded_hw
         for f in range(f0, f1):
-            if events is None:
-                # headline path: one C call per group queues the frame on the frame pipeline
-                groups.run_plan(f)
-                continue
-            # same launches, one C call per stage so that each stage can be bracketed by events
             eng.frame_ids.fill_(f)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
             ev[0].record(stream)
-            eng.disp2depth(raw[f], out=eng.depth_map); ev[1].record(stream)
+            if mode == 'map':
+                eng.disp2depth(raw[f], out=eng.depth_map)
+            ev[1].record(stream)
             eng.decode_nms([c[f] for c in cls], [c[f] for c in box], [c[f] for c in obj],
                            (cfg.height, cfg.width)); ev[2].record(stream)
-            eng.box_depth(eng.depth_map, eng.det_boxes, eng.det_counts, eng.det_depth, eng.det_scales,
-                          eng.det_inflated); ev[3].record(stream)
+            if mode == 'map':
+                eng.box_depth(eng.depth_map, eng.det_boxes, eng.det_counts, eng.det_depth, eng.det_scales,
+                              eng.det_inflated)
+            else:
+                eng.box_depth_raw(raw[f], (Hp, Wp), eng.det_boxes, eng.det_counts, eng.det_depth, eng.det_scales,
+                                  eng.det_inflated)
+            ev[3].record(stream)
             eng.track_step(eng.frame_ids, eng.det_inflated, eng.det_scores, eng.det_labels, eng.det_scales,
                            eng.det_depth, eng.det_counts); ev[4].record(stream)
             eng.scale_boxes(eng.trk_boxes, eng.out_scales, eng.out_counts, True, eng.out_boxes)
             ev[5].record(stream)
-            eng.box_depth(eng.depth_map, eng.out_boxes, eng.out_counts, eng.out_depth, eng.out_scale2, None)
+            if mode == 'map':
+                eng.box_depth(eng.depth_map, eng.out_boxes, eng.out_counts, eng.out_depth, eng.out_scale2, None)
+            else:
+                eng.box_depth_raw(raw[f], (Hp, Wp), eng.out_boxes, eng.out_counts, eng.out_depth, eng.out_scale2, None,
+                                  prev_boxes=eng.det_boxes, prev_index=eng.out_src, prev_d=eng.det_depth)
             ev[6].record(stream)
-            events.append(ev)
+            if events is not None:
+                events.append(ev)
 
-    # ---- resident-input timing (value) -------------------------------------------
-    run_steps(0, W)
-    barrier()
+    # ---- resident-input timing (value): `reps` repetitions of [W warm-up steps, K timed steps] ----
+    # every repetition replays frames 0 .. F-1 (frame 0 resets the trackers); the K timed steps are
+    # bracketed by barrier + synchronize and CUDA events on the launching stream (fork / join)
+    clock_windows = []
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    groups.fork(stream)                 # group streams start after e0 ...
-    t_issue = time.perf_counter()
-    clock_windows = []
-    run_steps(W, F)
-    issue_ms = (time.perf_counter() - t_issue) * 1e3     # host time to issue the K steps (no sync inside)
-    groups.join(stream)                 # ... and e1 is recorded after all of them finished
-    e1.record(stream)
-    barrier()
-    clock_windows.append((t_issue, time.perf_counter()))
-    ms_total = e0.elapsed_time(e1)
+
+    def timed_pass(g):
+        for f in range(0, W):
+            g.run_plan(f)
+        g.join(stream)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        g.fork(stream)                 # the pipeline streams start after e0 ...
+        for f in range(W, F):
+            g.run_plan(f)              # one C call per group queues the frame
+        issue = (time.perf_counter() - t0) * 1e3       # host time to issue the K steps (no sync inside)
+        g.join(stream)                 # ... and e1 is recorded after all of them finished
+        e1.record(stream)
+        barrier()
+        clock_windows.append((t0, time.perf_counter()))
+        return e0.elapsed_time(e1), issue
+
+    timing = {}
+    for mode in modes:
+        g = groups_of[mode]
+        timed_pass(g)                                   # one untimed repetition (graph instantiation, caches)
+        reps = [timed_pass(g) for _ in range(max(1, args.reps))]
+        ms = torch.tensor([r[0] for r in reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # per repetition: the slowest rank
+        timing[mode] = dict(ms=ms.cpu().numpy(), issue=float(np.median([r[1] for r in reps])))
     status = groups.status()
     dbg = np.concatenate([e.debug_words() for e in groups.engines])
-    tracked_rows = int(sum(len(r['instances_id']) for r in groups.results()))
+    last = {mode: groups_of[mode].results() for mode in modes}
+    tracked_rows = int(sum(len(r['instances_id']) for r in last[modes[0]]))
+    # both depth sources must give the same tracks (bit for bit) - checked on the last frame of all sequences
+    modes_identical = all(np.array_equal(a[k], b[k], equal_nan=a[k].dtype.kind == 'f')
+                          for a, b in zip(last[modes[0]], last[modes[1]]) for k in a)
 
-    # ---- per-kernel timing (second pass over the same frames, same state reset by frame 0) ----
-    stage_events = []
-    run_steps(0, W, [])
-    barrier()
-    run_steps(W, F, stage_events)
-    barrier()
+    # ---- per-kernel timing (serial single-stream passes over the same frames) -------------------
+    stage_avg = {}
+    for mode in modes:
+        evs = []
+        run_stages(0, W, None, mode)
+        barrier()
+        run_stages(W, F, evs, mode)
+        barrier()
+        stage_avg[mode] = np.array([[ev[i].elapsed_time(ev[i + 1]) for i in range(6)] for ev in evs]).mean(0)
     # K1 alone, back to back over the timed frames (fresh 118 MB read per launch, 241 MB written to
     # alternating maps): the launch queue stays full, so the average is the kernel's own duration;
     # the per-stage events above also contain the launch gap of an idle stream (~8 us per stage)
@@ -308,35 +363,35 @@ def main():
     for f in range(min(W, 3)):
         eng.disp2depth(raw[f], out=k1_out[f % 2])
     barrier()
-    k0, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record(stream)
-    for f in range(W, F):
-        eng.disp2depth(raw[f], out=k1_out[f % 2])
-    k1e.record(stream)
-    barrier()
-    k1_ms = k0.elapsed_time(k1e) / K
+    k1_reps = []
+    for _ in range(3):
+        k0, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for f in range(W, F):
+            eng.disp2depth(raw[f], out=k1_out[f % 2])
+        k1e.record(stream)
+        barrier()
+        k1_reps.append(k0.elapsed_time(k1e) / K)
+    k1_ms = float(np.median(k1_reps))
     del k1_out
-    names = ['k1_disp2depth', 'k2_decode_nms(2 kernels)', 'k3_box_depth(dets)', 'k4_track_step',
-             'scale_boxes', 'k3_box_depth(tracks)']
-    stage_ms = np.array([[ev[i].elapsed_time(ev[i + 1]) for i in range(6)] for ev in stage_events])
-    stage_avg = stage_ms.mean(0)
 
     # ---- end to end through the public call with HOST buffers ---------------------
-    # Per frame: pinned host -> device copy of the frame's inputs (copy stream), the
-    # frame on the group's frame pipeline, device -> pinned host copy of its tracks
-    # (read-back stream).  `depth` frames are in flight; the host consumes the
-    # tracks of frame f while frame f + depth - 1 is being copied in.
+    # Per frame: ONE pinned host -> device copy of the frame's inputs (frame ids, raw disparity and
+    # all head maps are one staging record, engine.FrameInputs) on the copy stream, the frame on the
+    # frame pipeline, ONE device -> pinned host copy of its tracks (FrameBuffers.out_block) on the
+    # read-back stream.  `depth` frames are in flight; the host consumes the tracks of frame f
+    # while frame f + depth - 1 is being copied in.
     N = args.depth
-    host = dict(raw=raw.cpu().pin_memory(), cls=[c.cpu().pin_memory() for c in cls],
-                box=[c.cpu().pin_memory() for c in box], obj=[c.cpu().pin_memory() for c in obj])
-    fid_tab = torch.arange(F, dtype=torch.int32, device=dev)[:, None].repeat(1, S).contiguous()
-    d_in = [dict(raw=torch.empty_like(raw[0]), cls=[torch.empty_like(c[0]) for c in cls],
-                 box=[torch.empty_like(c[0]) for c in box], obj=[torch.empty_like(c[0]) for c in obj])
-            for _ in range(N)]
-    h_out = [[[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in b.outputs()] for b in p.slots]
-             for p in groups.pipes]
-    h2d = raw[0].numel() * 2 + sum(t[0].numel() * 4 for t in cls + box + obj)
-    d2h = sum(t.numel() * t.element_size() for p in groups.pipes for t in p.slots[0].outputs())
+    H_, W_ = cfg.height, cfg.width
+    host = [FrameInputs(S, H_, W_, level_hw, device='cpu', pin=True).fill(
+        f, raw[f].cpu(), [c[f].cpu() for c in cls], [c[f].cpu() for c in box], [c[f].cpu() for c in obj])
+        for f in range(F)]
+    d_in = [FrameInputs(S, H_, W_, level_hw, device=dev) for _ in range(N)]
+    pipe = groups.pipes[0]
+    assert len(groups.pipes) == 1 or not args.graph, 'one lockstep group per GPU in the end-to-end region'
+    h_out = [[torch.empty_like(b.out_block, device='cpu').pin_memory() for b in p.slots] for p in groups.pipes]
+    h2d = host[0].nbytes
+    d2h = sum(p.slots[0].out_block.numel() for p in groups.pipes)
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     G = len(groups.pipes)
     mk = lambda: torch.cuda.Event()
@@ -347,55 +402,113 @@ def main():
         e.record(stream)                   # materialise the CUDA events
     torch.cuda.synchronize(dev)
 
-    def e2e_steps(f0, f1):
+    def e2e_steps(f0, f1, collect=None):
+        """frames f0 .. f1-1 from host staging records to host track rows; ``collect``: list that
+        receives (frame, results of the sequences in parity_seqs) for every frame"""
         consumed = 0
+
+        def consume(slot, f):
+            nonlocal consumed
+            ev_out[slot].synchronize()          # the tracks of frame f are on the host
+            for g_, p in enumerate(groups.pipes):
+                v = FrameBuffers.unpack(h_out[g_][slot], p.slots[slot].out_layout)
+                consumed += int(v['out_counts'].sum())
+            if collect is not None:
+                res = []
+                for g_, p in enumerate(groups.pipes):
+                    res.extend(p.slots[slot].results(h_out[g_][slot].clone()))
+                collect.append((f, [res[s] for s in parity_seqs]))
+
         for k, f in enumerate(range(f0, f1)):
             slot = groups.pipes[0].submitted % N
             if k >= N:
-                ev_out[slot].synchronize()      # the caller has read the tracks of frame f - N
-                consumed += int(h_out[0][slot][6].sum())
+                consume(slot, f - N)            # the caller has read the tracks of frame f - N
             with torch.cuda.stream(s_in):
                 s_in.wait_event(ev_out[slot])   # this slot's previous frame left the device
                 d = d_in[slot]
-                d['raw'].copy_(host['raw'][f], non_blocking=True)
-                for l in range(len(cls)):
-                    d['cls'][l].copy_(host['cls'][l][f], non_blocking=True)
-                    d['box'][l].copy_(host['box'][l][f], non_blocking=True)
-                    d['obj'][l].copy_(host['obj'][l][f], non_blocking=True)
+                d.block.copy_(host[f].block, non_blocking=True)       # one cudaMemcpyAsync per frame
                 ev_in[slot].record(s_in)
-            for g, (p, a, sz) in enumerate(zip(groups.pipes, groups.offsets, groups.sizes)):
-                p.submit(fid_tab[f, a:a + sz], d['raw'][a:a + sz], [c[a:a + sz] for c in d['cls']],
-                         [c[a:a + sz] for c in d['box']], [c[a:a + sz] for c in d['obj']],
-                         ready_event=ev_in[slot], done_event=ev_done[slot][g])
+            for g_, (p, a, sz) in enumerate(zip(groups.pipes, groups.offsets, groups.sizes)):
+                p.submit(d.frame_ids[a:a + sz], d.raw[a:a + sz], [c[a:a + sz] for c in d.cls],
+                         [c[a:a + sz] for c in d.bbox], [c[a:a + sz] for c in d.obj],
+                         ready_event=ev_in[slot], done_event=ev_done[slot][g_])
             with torch.cuda.stream(s_out):
-                for g, p in enumerate(groups.pipes):
-                    s_out.wait_event(ev_done[slot][g])
-                    for t, hbuf in zip(p.slots[slot].outputs(), h_out[g][slot]):
-                        hbuf.copy_(t, non_blocking=True)
+                for g_, p in enumerate(groups.pipes):
+                    s_out.wait_event(ev_done[slot][g_])
+                    h_out[g_][slot].copy_(p.slots[slot].out_block, non_blocking=True)   # one copy per frame
                 ev_out[slot].record(s_out)
-        for e in ev_out:
-            e.synchronize()                     # every frame's tracks are on the host
+        n_frames = f1 - f0
+        for k in range(max(n_frames - N, 0), n_frames):
+            consume((groups.pipes[0].submitted - n_frames + k) % N, f0 + k)
         return consumed
 
-    e2e_steps(0, W)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps(W, F)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clock_windows.append((t0, t0 + e2e_s))
-    clocks = sampler.stop(clock_windows) if rank == 0 else None      # samples of both timed regions
+    parity_seqs = sorted({int(round(i * (S - 1) / max(args.parity_seqs - 1, 1))) for i in range(args.parity_seqs)}) \
+        if args.parity_seqs > 0 else []
+    e2e_steps(0, F)                             # untimed: graph instantiation for the staging addresses, caches
+    e2e_ms_reps = []
+    for _ in range(max(1, args.e2e_reps)):
+        e2e_steps(0, W)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps(W, F)
+        torch.cuda.synchronize(dev)
+        mine = (time.perf_counter() - t0) * 1e3
+        barrier()
+        clock_windows.append((t0, time.perf_counter()))
+        e2e_ms_reps.append(mine)
+    clocks = sampler.stop(clock_windows) if rank == 0 else None      # samples of all timed regions
+
+    # ---- parity of the timed workload: the oracle replays some of this rank's sequences ----------
+    parity = None
+    if parity_seqs:
+        got = []
+        e2e_steps(0, F, collect=got)
+        got.sort(key=lambda t: t[0])
+        from oracle.model import StereoTrackOracle
+        mism = rows = 0
+        first_bad = None
+        for k, s_ in enumerate(parity_seqs):
+            o = StereoTrackOracle()
+            for f, res in got:
+                ref = o.step(f, host[f].raw[s_].numpy(), [c[s_].numpy() for c in host[f].cls],
+                             [c[s_].numpy() for c in host[f].bbox], [c[s_].numpy() for c in host[f].obj])
+                r = res[k]
+                ok = (np.array_equal(r['instances_id'], ref['instances_id']) and
+                      np.array_equal(r['labels'], ref['labels']) and
+                      np.allclose(r['bboxes'], ref['bboxes'], rtol=1e-5, atol=1e-4) and
+                      np.allclose(r['scores'], ref['scores'], rtol=1e-5) and
+                      np.allclose(r['depth'], ref['depth'], rtol=1e-5, equal_nan=True))
+                rows += len(ref['instances_id'])
+                if not ok:
+                    mism += 1
+                    first_bad = first_bad or dict(sequence=first_seq + s_, frame=f)
+        parity = dict(sequences=[first_seq + s_ for s_ in parity_seqs], frames=F, rows=rows, mismatches=mism,
+                      first_mismatch=first_bad, depth_sources_identical=bool(modes_identical),
+                      checked='ids / labels bit-exact, boxes / scores / depths 1e-5 relative, every frame, against '
+                              'the oracle (CPU restatement of the reference) on the same inputs')
 
     # ---- host-side gather of the last frame's tracks (outside every timed region) -------
     rows = shard.tracks_to_rows(groups.results(), F - 1, first_sequence=first_seq)
     gathered = shard.gather_tracks(rows, dst=0)
 
     # ---- reduce over ranks ------------------------------------------------------------
-    vals = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor(e2e_ms_reps, dtype=torch.float64, device=dev)
+    per_rank_e2e = [e2e_t.cpu().numpy()]
+    per_rank_numa = [numa]
+    bad = torch.tensor([0 if parity is None else parity['mismatches'] + (0 if modes_identical else 1)],
+                       dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(vals[0]), float(vals[1])
+        all_e2e = [torch.zeros_like(e2e_t) for _ in range(world)]
+        dist.all_gather(all_e2e, e2e_t)
+        per_rank_e2e = [t.cpu().numpy() for t in all_e2e]
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)          # per repetition: the slowest rank
+        dist.all_reduce(bad, op=dist.ReduceOp.SUM)
+        per_rank_numa = [None] * world
+        dist.all_gather_object(per_rank_numa, numa)
+    e2e_ms = float(np.median(e2e_t.cpu().numpy()))
     frames = S * world * K
+    ms_all = timing[modes[0]]['ms']
+    ms_total = float(np.median(ms_all))
     value = frames / (ms_total * 1e-3)
     e2e_value = frames / (e2e_ms * 1e-3)
 
@@ -406,55 +519,89 @@ def main():
         k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
         P = cfg.num_priors
         k2_bytes = S * P * 4                                               # objectness logit of every prior (class logits lazily)
-        kernels = {n: dict(ms=float(stage_avg[i]), share=float(stage_avg[i] / stage_avg.sum()))
-                   for i, n in enumerate(names)}
-        kernels['k1_disp2depth'].update(algorithmic_bytes=k1_bytes, ms_back_to_back=k1_ms, achieved_gbs=k1_gbs,
-                                        frac=k1_gbs / peak)
-        kernels['k2_decode_nms(2 kernels)'].update(
-            algorithmic_bytes=k2_bytes, achieved_gbs=k2_bytes / (stage_avg[1] * 1e-3) / 1e9)
+        names = ['k1_disp2depth', 'k2_decode_nms(2 kernels)', 'k3_box_depth(dets)', 'k4_track_step',
+                 'scale_boxes', 'k3_box_depth(tracks)']
+        kernels = {}
+        for mode in modes:
+            sa = stage_avg[mode]
+            kernels[mode] = {n: dict(ms=float(sa[i]), share=float(sa[i] / sa.sum())) for i, n in enumerate(names)
+                             if not (mode == 'raw' and i == 0)}
+        kernels['map']['k1_disp2depth'].update(algorithmic_bytes=k1_bytes, ms_back_to_back=k1_ms, achieved_gbs=k1_gbs,
+                                               frac=k1_gbs / peak)
+        for mode in modes:
+            kernels[mode]['k2_decode_nms(2 kernels)'].update(
+                algorithmic_bytes=k2_bytes, achieved_gbs=k2_bytes / (stage_avg[mode][1] * 1e-3) / 1e9)
+        # bytes one step of the pipeline moves through HBM, by depth source (algorithmic: the raw
+        # frame or the map, the objectness plane of the head maps; box / track rows are < 1 MB)
+        step_bytes = dict(map=k1_bytes + k2_bytes, raw=k2_bytes,
+                          note='raw: K3 gathers ~2 bytes per box pixel from the u16 frame (about 4 MB per step at '
+                               'this workload) instead of K1 streaming the frame into a float32 map')
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             n_seqs = args.cpu_seqs or max(2, min(S, cores))
             fsub = min(F, 24)
-            fps, used, single, nfr, rows = cpu_reference(raw[:fsub], [c[:fsub] for c in cls], [c[:fsub] for c in box],
-                                                         [c[:fsub] for c in obj], n_seqs, cores)
+            fps, used, single, nfr, rows_ = cpu_reference(raw[:fsub], [c[:fsub] for c in cls], [c[:fsub] for c in box],
+                                                          [c[:fsub] for c in obj], n_seqs, cores)
             cpu = dict(value=fps, unit=UNIT, cores=used, kind='port', single_core=single,
                        sample=f'first {n_seqs} sequences x {fsub} frames of this workload, oracle (NumPy/C port of '
                               f'the reference tracker path), one process per core')
+        config.update(depth_source=modes[0], cuda_graph=bool(args.graph), value_repetitions=int(len(ms_all)),
+                      e2e_repetitions=int(len(e2e_ms_reps)))
+        other = modes[1]
+        oms = float(np.median(timing[other]['ms']))
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
             higher_is_better=True, scaling='weak', vs_baseline=None,
             dtype='f32 (u16 disparity in, f64 Kalman state and assignment)', data='synthetic', config=config,
+            value_stats=dict(median_ms_per_step=ms_total / K, min_ms_per_step=float(ms_all.min()) / K,
+                             max_ms_per_step=float(ms_all.max()) / K, repetitions=int(len(ms_all)),
+                             note='median over repetitions of the K-step region, each the max over ranks'),
+            modes={modes[0]: dict(value=value, ms_per_step=ms_total / K, host_issue_ms_per_step=timing[modes[0]]['issue'] / K,
+                                  hbm_bytes_per_step=step_bytes[modes[0]]),
+                   other: dict(value=frames / (oms * 1e-3), ms_per_step=oms / K,
+                               host_issue_ms_per_step=timing[other]['issue'] / K,
+                               hbm_bytes_per_step=step_bytes[other],
+                               min_ms_per_step=float(timing[other]['ms'].min()) / K,
+                               max_ms_per_step=float(timing[other]['ms'].max()) / K),
+                   'note': step_bytes['note']},
             roofline=dict(kernel='k1_disp2depth_flat', bound='hbm', achieved=k1_gbs, peak=peak, unit='GB/s',
                           frac=k1_gbs / peak,
                           traffic=K1_TRAFFIC_BYTES_C2_S64 if (args.workload == 'C2' and S == 64) else None,
                           traffic_unit='bytes per launch (ncu --set full, profiles/r01_k1_disp2depth_flat_full_metrics.csv)',
                           algorithmic_bytes_per_launch=k1_bytes, peak_source=peak_src,
-                          note='HBM-bound kernel of the path (north_star): average duration of K launches issued '
-                               'back to back on one stream over the timed frames (CUDA events); "kernels" gives '
-                               'every stage of a serial single-stream pass, launch gaps included'),
+                          whole_step_map_mode=dict(bytes=step_bytes['map'], ms=(ms_total if modes[0] == 'map' else oms) / K,
+                                                   frac=step_bytes['map'] / ((ms_total if modes[0] == 'map' else oms) / K * 1e-3) / 1e9 / peak),
+                          note='HBM-bound kernel of the path (north_star kernel 1): average duration of K launches '
+                               'issued back to back on one stream over the timed frames (CUDA events, median of 3 '
+                               'passes).  In depth_source=map it is a stage of every step; in depth_source=raw the '
+                               'step no longer writes the map (K3 converts the box pixels on the fly) and the step '
+                               'is latency-bound: "modes" gives both, "kernels" every stage of a serial pass'),
             kernels=kernels,
             cpu_baseline=cpu,
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                     ms_per_step=e2e_ms / K),
+                     ms_per_step=e2e_ms / K, h2d_copies_per_step=1, d2h_copies_per_step=G,
+                     repetitions_ms_per_step=[float(v) / K for v in e2e_t.cpu().numpy()],
+                     per_rank=[dict(rank=r, ms_per_step=float(np.median(v)) / K,
+                                    h2d_gbs=h2d / (float(np.median(v)) / K * 1e-3) / 1e9, numa=per_rank_numa[r])
+                               for r, v in enumerate(per_rank_e2e)]),
+            parity=parity,
             gpu_launches=int(K * groups.kernels_per_frame), clocks=clocks,
-            host_issue_ms_per_step=issue_ms / K,
+            host_issue_ms_per_step=timing[modes[0]]['issue'] / K,
             k4_phase_cycles_median=dict(zip(['filter_predict', 'stage1', 'stage2', 'stage3', 'smooth_order', 'update'],
                                             [int(x) for x in np.median(dbg[:, 8:14], axis=0)])),
             k4_phase_cycles_slowest_sequence=dict(zip(
                 ['filter_predict', 'stage1', 'stage2', 'stage3', 'smooth_order', 'update'],
                 [int(x) for x in dbg[int(np.argmax(dbg[:, 8:14].sum(1))), 8:14]])),
-            assignments=dict(solved=int(dbg[:, 5].sum()), exact_fallback=int(dbg[:, 6].sum()),
-                             stage1_search_cycles_median=int(np.median(dbg[:, 14])),
-                             stage1_certificate_cycles_median=int(np.median(dbg[:, 15])),
-                             stage1_slowest=dict(zip(['active_rows', 'rows_x1000_plus_cols', 'search_cycles', 'certificate_cycles',
-                                                      'cert_scan', 'cert_reach', 'cert_cycle', 'arcs'],
-                                                     [int(v) for v in dbg[int(np.argmax(dbg[:, 9])), [3, 4, 14, 15, 16, 17, 18, 19]]]))), status_bits=int(status.max()), tracked_rows_last_step=tracked_rows,
-            gathered_rows_all_ranks=int(len(gathered)), numa_rank0=numa)
+            assignments=dict(solved=int(dbg[:, 5].sum()), exact_fallback=int(dbg[:, 6].sum())),
+            status_bits=int(status.max()), tracked_rows_last_step=tracked_rows,
+            gathered_rows_all_ranks=int(len(gathered)))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if float(bad[0]) != 0:
+        sys.stderr.write('PARITY MISMATCH: the timed workload differs from the oracle (see "parity")\n')
+        sys.exit(3)
 
 
 if __name__ == '__main__':

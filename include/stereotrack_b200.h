@@ -16,8 +16,12 @@
  *    never allocates or frees caller memory and never synchronises (st_create /
  *    st_destroy / st_export_state / st_read_* / st_snapshot_* excepted).  The per-frame
  *    calls consist of kernel launches, memsets and event fork/join on streams the
- *    library owns, i.e. the stream-capturable subset, but capture into a CUDA graph
- *    is not exercised by the tests of this round;
+ *    library owns, i.e. the stream-capturable subset; st_pipeline_* can replay a frame
+ *    as a CUDA graph (st_pipeline_use_graphs);
+ *  - a handle belongs to the CUDA device that was current at st_create; every call that
+ *    takes a handle makes that device current for its duration.  Lazily initialised
+ *    library state (occupancy-derived grids, auxiliary streams, events) is kept per
+ *    device and is safe to touch from several host threads;
  *  - return value: 0 = ok, < 0 = error (st_error_string); nothing throws;
  *  - S = sequences processed in lockstep (one frame each per call); per-sequence
  *    arrays are padded to a fixed capacity with a separate count array;
@@ -33,7 +37,7 @@
 extern "C" {
 #endif
 
-#define ST_ABI_VERSION 5
+#define ST_ABI_VERSION 6
 
 enum {
     ST_OK = 0,
@@ -91,7 +95,10 @@ int st_create(const st_config *cfg, st_handle **out);
 int st_destroy(st_handle *h);
 /* reset every sequence whose byte in seq_mask is non-zero (NULL = all) */
 int st_reset(st_handle *h, const uint8_t *seq_mask, void *stream);
-int st_read_status(st_handle *h, int32_t *status_host, int S);   /* synchronises */
+int st_read_status(st_handle *h, int32_t *status_host, int S);   /* waits for ALL work on the device, then reads */
+/* number of live tracks of every sequence (len(self.tracks), base_tracker.py:39-41 `empty`):
+ * one copy on `stream`, which is synchronised */
+int st_read_live_counts(st_handle *h, int32_t *live_host, int S, void *stream);
 int st_clear_status(st_handle *h, void *stream);
 /* Diagnostics: 32 words per sequence written by st_track_step: 0-2 stage / rows / columns of
  * the last association, 3-4 active rows and rows*1000+columns of the last stage-1 fast solve,
@@ -170,6 +177,18 @@ int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, const float *b
                        int32_t *workspace, const float *prev_boxes, const int32_t *prev_index,
                        const float *prev_d, void *stream);
 
+/* K3 on the RAW u16 frame, no depth map in between: the same call as st_box_depth_reuse on the map
+ * st_disp2depth(raw, S, H, W, H, W, Hp, Wp, ..., baseline, focal_length) would write (resize
+ * factor 1, i.e. Hr == H and Wr == W as in every shipped config), with bit-identical results.
+ * Replaces ocsort_disparity.py:132-134 + :136-175 for the boxes only: depth is monotone in the raw
+ * code, so the order statistics are taken on 16-bit codes (shared-memory histograms) and only the
+ * window sum evaluates Z = B f / (d + 1e-6).  prev_* as in st_box_depth_reuse (NULL = none). */
+int st_box_depth_raw(const uint16_t *raw, int S, int H, int W, int Hp, int Wp, float baseline,
+                     float focal_length, const float *boxes, const int32_t *counts, int cap,
+                     float *d, float *scale, float *inflated, int32_t *workspace,
+                     const float *prev_boxes, const int32_t *prev_index, const float *prev_d,
+                     void *stream);
+
 /* The ablation reducers of mmtrack/models/mot/depth_extraction_comparison.py (decorators that
  * replace extract_depth in comparison runs): same patch, validity filter and -1 rule, another
  * statistic, scale = clip(d*d/400, 1, 3).  ST_DEPTH_WINDOW is st_box_depth (scale = clip(d*d, 1, 3)).
@@ -226,7 +245,7 @@ typedef struct st_frame_io {
     int32_t num_levels, num_classes, ori_h, ori_w;
     float scale_w, scale_h;
     /* intermediates */
-    float *depth_map;                  /* [S,Hp,Wp] */
+    float *depth_map;                  /* [S,Hp,Wp]; may be NULL when depth_from_raw != 0 */
     float *disp3;                      /* [S,3,Hp,Wp] or NULL */
     uint8_t *mask;                     /* [S,Hp,Wp] or NULL */
     float *det_boxes; float *det_scores; int64_t *det_labels; int32_t *det_prior; int32_t *det_keep;
@@ -238,6 +257,9 @@ typedef struct st_frame_io {
     float *out_boxes; float *out_scores; int64_t *out_labels; float *out_scales; float *out_depth;
     int64_t *out_ids; int32_t *out_counts;
     const float *warp;                 /* [S,6] camera-motion affine of this frame or NULL (st_track_step) */
+    int32_t depth_from_raw;            /* != 0: both K3 calls gather from `raw` (st_box_depth_raw; needs raw,
+                                        * Hr == H, Wr == W); K1 then only runs when the caller wants the map
+                                        * (depth_map != NULL), so the 4 Hp Wp byte write leaves the path */
 } st_frame_io;
 
 /* The whole per-frame path for S sequences in one call (K1 -> K2 -> K3 -> K4/K5
@@ -247,9 +269,9 @@ int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *stream);
 /* Software pipeline over consecutive frames of the same S sequences.  Only the
  * tracker state couples frame f+1 to frame f (ocsort_tracker_disparity.py:345-618);
  * K1, K2 and K3 on the detections of later frames and the deflate + K3 on the tracks
- * of earlier frames run concurrently with it on five internal streams (K1 | K2 ->
- * K3 on detections -> tracker -> deflate + K3 on tracks).  Results
- * equal st_frame_step.  The caller owns `depth` complete st_frame_io buffer sets and
+ * of earlier frames run concurrently with it on internal streams: a "pre" segment per
+ * ring slot (K1 | K2 -> K3 on detections), the tracker on one stream in frame order, a
+ * "post" segment (deflate + K3 on tracks).  Results equal st_frame_step.  The caller owns `depth` complete st_frame_io buffer sets and
  * passes set (k mod depth) with the k-th submit; inputs must stay valid until that
  * frame is done.  inputs_ready / frame_done are cudaEvent_t (may be NULL): the first
  * stage waits for inputs_ready, frame_done is recorded when every output of the
@@ -258,6 +280,15 @@ typedef struct st_pipeline st_pipeline;
 int st_pipeline_create(st_handle *h, int depth, st_pipeline **out);
 int st_pipeline_destroy(st_pipeline *p);
 int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, void *inputs_ready, void *frame_done);
+/* Replay frames as CUDA graphs: from a ring slot's second use on, its pre
+ * and post segments are stream-captured once and relaunched with cudaGraphLaunch; the tracker
+ * kernel stays a plain launch between them (it carries the cross-frame dependency in stream
+ * order).  The frame's input pointers (raw, head maps) are read by the kernels from a per-slot
+ * device table that follows st_frame_io, so replaying on new inputs needs no graph update; a
+ * change of any other st_frame_io field - buffers, sizes - re-captures the slot.  Identical
+ * results; st_pipeline_stats reports how many frames were replayed and how many captures ran. */
+int st_pipeline_use_graphs(st_pipeline *p, int enable);
+int st_pipeline_stats(st_pipeline *p, long long *graph_frames, long long *captures);
 /* the pipeline's streams start after the work already queued on `stream` */
 int st_pipeline_fork(st_pipeline *p, void *stream);
 /* `stream` waits for every frame submitted so far */
@@ -296,6 +327,14 @@ int st_kalman_batch(int op, int n, double *mean, double *cov, const float *z, vo
  * (either may be NULL). */
 int st_kalman_project(int n, const double *mean, const double *cov, double *pmean, double *pcov,
                       void *stream);
+/* KalmanFilter(use_nsa=True) (kalman_filter.py:38,:144-145): project / update with every
+ * measurement std scaled by noise_scale[i] = 1 - bbox_score of state i ([n] f64; NULL = 1, the
+ * plain calls above).  The OC-SORT trackers never pass a bbox_score (kalman_tracker_base.py:74-75,
+ * ocsort_tracker_disparity.py:342-343), so inside st_track_step use_nsa is the identity. */
+int st_kalman_project_scored(int n, const double *mean, const double *cov, const double *noise_scale,
+                             double *pmean, double *pcov, void *stream);
+int st_kalman_batch_scored(int op, int n, double *mean, double *cov, const float *z,
+                           const double *noise_scale, void *stream);
 /* KalmanFilter.gating_distance (kalman_filter.py:190-234) of n states against the same m
  * measurements meas [m,4] f64 (cx,cy,a,h): dist [n,m] f64 squared Mahalanobis distances;
  * only_position != 0 uses (cx,cy) only.  A projected covariance that is not positive definite

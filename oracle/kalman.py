@@ -32,14 +32,17 @@ def predict(mean, cov):
     return F @ mean, np.linalg.multi_dot((F, cov, F.T)) + np.diag(std * std)
 
 
-def project(mean, cov):
+def project(mean, cov, bbox_score=0., use_nsa=False):
     h = mean[3]
-    std = np.array([W_POS * h, W_POS * h, 1e-1, W_POS * h])
+    std = [W_POS * h, W_POS * h, 1e-1, W_POS * h]
+    if use_nsa:                                   # kalman_filter.py:144-145
+        std = [(1 - bbox_score) * x for x in std]
+    std = np.array(std)
     return H @ mean, np.linalg.multi_dot((H, cov, H.T)) + np.diag(std * std)
 
 
-def update(mean, cov, z):
-    pm, pc = project(mean, cov)
+def update(mean, cov, z, bbox_score=0., use_nsa=False):
+    pm, pc = project(mean, cov, bbox_score, use_nsa)
     chol = scipy.linalg.cho_factor(pc, lower=True, check_finite=False)
     gain = scipy.linalg.cho_solve(chol, (cov @ H.T).T, check_finite=False).T
     innov = np.asarray(z, np.float64) - pm

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libstereotrack_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 ST_STATUS = dict(CAND_OVERFLOW=1, DET_OVERFLOW=2, TRACK_OVERFLOW=4, LAP_GUARD=8)
 
@@ -36,7 +36,8 @@ class StFrameIO(C.Structure):
             'depth_map', 'disp3', 'mask', 'det_boxes', 'det_scores', 'det_labels', 'det_prior',
             'det_keep', 'det_counts', 'det_depth', 'det_scales', 'det_inflated', 'trk_boxes',
             'trk_depth', 'out_scale2', 'out_src', 'k3_workspace', 'out_boxes', 'out_scores', 'out_labels', 'out_scales',
-            'out_depth', 'out_ids', 'out_counts', 'warp')])
+            'out_depth', 'out_ids', 'out_counts', 'warp')] +
+        [('depth_from_raw', C.c_int32)])
 
 
 class StereoTrackError(RuntimeError):
@@ -53,6 +54,7 @@ _SIGNATURES = {
     'st_destroy': (_I, [_P]),
     'st_reset': (_I, [_P, _P, _P]),
     'st_read_status': (_I, [_P, _P, _I]),
+    'st_read_live_counts': (_I, [_P, _P, _I, _P]),
     'st_clear_status': (_I, [_P, _P]),
     'st_read_debug': (_I, [_P, _P, _I]),
     'st_debug_set_skip': (_I, [_I]),
@@ -66,11 +68,14 @@ _SIGNATURES = {
     'st_pack_image': (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     'st_box_depth_mode': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     'st_box_depth_reuse': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'st_box_depth_raw': (_I, [_P, _I, _I, _I, _I, _I, C.c_float, C.c_float, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'st_track_step': (_I, [_P, _I] + [_P] * 7 + [_I] + [_P] * 10),
     'st_frame_step': (_I, [_P, _I, C.POINTER(StFrameIO), _P]),
     'st_pipeline_create': (_I, [_P, _I, C.POINTER(_P)]),
     'st_pipeline_destroy': (_I, [_P]),
     'st_pipeline_submit': (_I, [_P, _I, C.POINTER(StFrameIO), _P, _P]),
+    'st_pipeline_use_graphs': (_I, [_P, _I]),
+    'st_pipeline_stats': (_I, [_P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     'st_pipeline_fork': (_I, [_P, _P]),
     'st_pipeline_join': (_I, [_P, _P]),
     'st_pipeline_trace': (_I, [_P, _I]),
@@ -81,6 +86,8 @@ _SIGNATURES = {
     'st_snapshot_save': (_I, [_P, _P, C.c_longlong, _P]),
     'st_snapshot_load': (_I, [_P, _P, C.c_longlong, _P]),
     'st_kalman_project': (_I, [_I, _P, _P, _P, _P, _P]),
+    'st_kalman_project_scored': (_I, [_I, _P, _P, _P, _P, _P, _P]),
+    'st_kalman_batch_scored': (_I, [_I, _I, _P, _P, _P, _P, _P]),
     'st_kalman_gating': (_I, [_I, _P, _P, _I, _P, _I, _P, _P]),
     'st_lapjv_batch': (_I, [_P, _I, _I, _I, _P, C.c_double, _I, _P, _P, _P]),
 }

@@ -107,3 +107,65 @@ except Exception:  # ImportError or version asserts of mmtrack/__init__.py:62-73
         @property
         def frame_id(self):
             return self._metainfo.get('frame_id', -1)
+
+
+def model_shell_base():
+    """Base class of the model shells (OCSORT / OCSORT_Disparity).  With mmtrack installed it is the
+    reference's own ``BaseMultiObjectTracker(mmengine.model.BaseModel)`` (mmtrack/models/mot/base.py:12,
+    :68-112), so a shell built by a Runner has ``data_preprocessor``, ``.to()``, ``.eval()``,
+    ``test_step`` and ``forward(mode=...)``.  Without it, a stand-in with the same surface for
+    stand-alone use and the tests."""
+    if HAVE_MMTRACK:
+        from mmtrack.models.mot.base import BaseMultiObjectTracker  # type: ignore
+        return BaseMultiObjectTracker
+
+    class BaseMultiObjectTracker:
+        """mmengine BaseModel / mmtrack BaseMultiObjectTracker surface used at inference."""
+
+        def __init__(self, data_preprocessor=None, init_cfg=None):
+            if isinstance(data_preprocessor, dict):
+                data_preprocessor = MODELS.build(data_preprocessor)
+            self.data_preprocessor, self.init_cfg = data_preprocessor, init_cfg
+            self.training = False
+
+        def to(self, *args, **kwargs):
+            return self
+
+        cuda = cpu = to
+
+        def eval(self):
+            self.training = False
+            return self
+
+        def init_weights(self):
+            pass
+
+        def forward(self, inputs, data_samples=None, mode='predict', **kwargs):       # base.py:68-112
+            if mode == 'loss':
+                return self.loss(inputs, data_samples, **kwargs)
+            if mode == 'predict':
+                return self.predict(inputs, data_samples, **kwargs)
+            if mode == 'tensor':
+                return self._forward(inputs, data_samples, **kwargs)
+            raise RuntimeError(f'Invalid mode "{mode}". Only supports loss, predict and tensor mode')
+
+        def test_step(self, data):                                                    # mmengine BaseModel.test_step
+            if self.data_preprocessor is not None:
+                data = self.data_preprocessor(data, False)
+            return self.forward(**data, mode='predict') if isinstance(data, dict) else self.forward(*data, mode='predict')
+
+        val_step = test_step
+
+        @property
+        def with_detector(self):
+            return getattr(self, 'detector', None) is not None
+
+        @property
+        def with_motion(self):
+            return getattr(self, 'motion', None) is not None
+
+        @property
+        def with_tracker(self):
+            return getattr(self, 'tracker', None) is not None
+
+    return BaseMultiObjectTracker

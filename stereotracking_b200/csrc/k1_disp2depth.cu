@@ -100,9 +100,10 @@ __device__ __forceinline__ void convert2(uint32_t w, float2 bf2, float pad_depth
 // its stores disabled 33 us.
 template <bool kDisp3, bool kMask>
 __global__ void __launch_bounds__(256, (kDisp3 || kMask) ? 4 : 6)
-k1_disp2depth_flat(const uint16_t *__restrict__ raw, int S, int H, int Hp, int Wp,
+k1_disp2depth_flat(const uint16_t *__restrict__ raw, const StFrameInputs *__restrict__ tab, int S, int H, int Hp, int Wp,
                    float *__restrict__ depth, float *__restrict__ disp3,
                    uint8_t *__restrict__ mask, float bf, unsigned total_items) {
+    if (tab) raw = tab->raw;                                 // replayed frame: the input lives where the table says
     constexpr int kUnroll = (kDisp3 || kMask) ? 2 : 4;      // steps in flight: 2 x 64-bit loads each
     const unsigned w4 = Wp >> 2;
     const unsigned items = (unsigned)Hp * w4, valid_items = (unsigned)H * w4;
@@ -201,8 +202,10 @@ __host__ __device__ inline size_t resize_smem_bytes(int W, int Wp) {
 }
 
 __global__ void __launch_bounds__(kRowThreads)
-k1_disp2depth_rows_tma(const uint16_t *__restrict__ raw, int S, int H, int W, int Hr, int Wr, int Hp, int Wp,
+k1_disp2depth_rows_tma(const uint16_t *__restrict__ raw, const StFrameInputs *__restrict__ tab, int S, int H, int W,
+                       int Hr, int Wr, int Hp, int Wp,
                        float *__restrict__ depth, float *__restrict__ disp3, uint8_t *__restrict__ mask, float bf) {
+    if (tab) raw = tab->raw;
     extern __shared__ __align__(16) unsigned char k1_smem[];
     const size_t row_bytes = ((size_t)W * 2 + 15) & ~(size_t)15;
     uint16_t *rowbuf[2] = {reinterpret_cast<uint16_t *>(k1_smem), reinterpret_cast<uint16_t *>(k1_smem + row_bytes)};
@@ -285,9 +288,11 @@ k1_disp2depth_rows_tma(const uint16_t *__restrict__ raw, int S, int H, int W, in
 // General path: nearest resize (cv2 INTER_NEAREST index rule: src =
 // min(floor(dst * (1/(dst_n/src_n))), src_n-1), float64) and arbitrary sizes.
 __global__ void __launch_bounds__(256)
-k1_disp2depth_generic(const uint16_t *__restrict__ raw, int S, int H, int W, int Hr, int Wr,
+k1_disp2depth_generic(const uint16_t *__restrict__ raw, const StFrameInputs *__restrict__ tab, int S, int H, int W,
+                      int Hr, int Wr,
                       int Hp, int Wp, float *__restrict__ depth, float *__restrict__ disp3,
                       uint8_t *__restrict__ mask, float bf) {
+    if (tab) raw = tab->raw;
     const long long total = (long long)S * Hp * Wp;
     const long long plane = (long long)Hp * Wp;
     const double inv_x = 1.0 / ((double)Wr / (double)W);
@@ -325,18 +330,21 @@ k1_disp_f32_to_depth(const float *__restrict__ disp, long long n, float *__restr
         depth[i] = __fmul_rn(__frcp_rn(__fadd_rn(disp[i], 1e-6f)), bf);
 }
 
-int sm_count() {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms;
-}
+int sm_count() { return st_ctx_sms(); }
 
 }  // namespace
 
 extern "C" int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, int Wr, int Hp,
                              int Wp, float *depth, float *disp3, uint8_t *mask, float baseline,
                              float focal_length, void *stream) {
+    return st_disp2depth_tab(raw, nullptr, S, H, W, Hr, Wr, Hp, Wp, depth, disp3, mask, baseline, focal_length, stream);
+}
+
+// `raw` selects the kernel variant (alignment); with a table the kernels read tab->raw instead,
+// which must have the same alignment class
+int st_disp2depth_tab(const uint16_t *raw, const StFrameInputs *tab, int S, int H, int W, int Hr, int Wr, int Hp,
+                      int Wp, float *depth, float *disp3, uint8_t *mask, float baseline,
+                      float focal_length, void *stream) {
     if (!raw || !depth || S < 0 || H <= 0 || W <= 0 || Hr <= 0 || Wr <= 0 || Hp < Hr || Wp < Wr)
         return ST_ERR_INVALID_ARG;
     if (S == 0) return ST_OK;
@@ -349,18 +357,20 @@ extern "C" int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, i
     if (Hr == H && Wr == W && W == Wp && (Wp % 4 == 0) && (((long long)Hp * (Wp / 4)) % 64 == 0) && aligned && small) {
         // grid = the resident CTA count (SMs x occupancy of this instantiation), never more
         auto launch = [&](auto kernel) {
-            static long long resident = 0;               // per instantiation; one device per process
-            if (!resident) {
+            struct Dev { long long resident; };
+            static StPerDevice<Dev> per_device;          // per instantiation and per CUDA device
+            const Dev *dv = per_device.get([&](Dev &v) {
                 int per_sm = 0;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1)
                     per_sm = 4;
-                if (const char *e = getenv("ST_K1_CTAS_PER_SM")) { const int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }
-                resident = (long long)sm_count() * per_sm;
-            }
-            long long grid = resident;
+                if (const char *e = getenv("ST_K1_CTAS_PER_SM")) { const int c = atoi(e); if (c > 0 && c < per_sm) per_sm = c; }
+                v.resident = (long long)st_ctx_sms() * per_sm;
+                return true;
+            });
+            long long grid = dv ? dv->resident : 148;
             const long long need = (total_items + 511) / 512;
             if (grid > need) grid = need;
-            kernel<<<(int)grid, 256, 0, st>>>(raw, S, H, Hp, Wp, depth, disp3, mask, bf, (unsigned)total_items);
+            kernel<<<(int)grid, 256, 0, st>>>(raw, tab, S, H, Hp, Wp, depth, disp3, mask, bf, (unsigned)total_items);
         };
         if (disp3 && mask) launch(k1_disp2depth_flat<true, true>);
         else if (disp3) launch(k1_disp2depth_flat<true, false>);
@@ -371,11 +381,8 @@ extern "C" int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, i
                (!mask || (uintptr_t)mask % 4 == 0)) {
         // resize and / or column padding: TMA-staged source rows
         const size_t smem = resize_smem_bytes(W, Wp);
-        static size_t configured = 0;
-        if (smem > configured) {
-            ST_CUDA_OK(cudaFuncSetAttribute(k1_disp2depth_rows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        // the opt-in is per device and cheap: set it for the size this call needs
+        ST_CUDA_OK(cudaFuncSetAttribute(k1_disp2depth_rows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_disp2depth_rows_tma, kRowThreads, smem) != cudaSuccess ||
             per_sm < 1)
@@ -383,13 +390,13 @@ extern "C" int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, i
         long long grid = (long long)sm_count() * per_sm;
         const long long rows = (long long)S * Hp;
         if (grid > rows) grid = rows;
-        k1_disp2depth_rows_tma<<<(int)grid, kRowThreads, smem, st>>>(raw, S, H, W, Hr, Wr, Hp, Wp, depth, disp3, mask, bf);
+        k1_disp2depth_rows_tma<<<(int)grid, kRowThreads, smem, st>>>(raw, tab, S, H, W, Hr, Wr, Hp, Wp, depth, disp3, mask, bf);
     } else {
         const long long total = (long long)S * Hp * Wp;
         long long grid = (total + 255) / 256;
         const long long cap = (long long)sm_count() * 8;
         if (grid > cap) grid = cap;
-        k1_disp2depth_generic<<<(int)grid, 256, 0, st>>>(raw, S, H, W, Hr, Wr, Hp, Wp, depth, disp3, mask, bf);
+        k1_disp2depth_generic<<<(int)grid, 256, 0, st>>>(raw, tab, S, H, W, Hr, Wr, Hp, Wp, depth, disp3, mask, bf);
     }
     return st_last_launch();
 }

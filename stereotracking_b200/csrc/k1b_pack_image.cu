@@ -103,16 +103,18 @@ extern "C" int st_pack_image(const uint8_t *img, int S, int H, int W, int Hp, in
     }
     p.swap_rb = swap_rb != 0;
     p.normalise = mean_host != nullptr;
-    static int sms = 0, resident_v4 = 0;
-    if (!sms) {
-        int dev = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    struct Dev { int sms, resident_v4; };
+    static StPerDevice<Dev> per_device;                  // mutex-guarded, one entry per CUDA device
+    const Dev *dv = per_device.get([](Dev &v) {
+        int per_sm = 0;
+        v.sms = st_ctx_sms();
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1b_pack_image_v4, 256, 0) != cudaSuccess || per_sm < 1)
             per_sm = 8;
-        resident_v4 = sms * per_sm;
-    }
+        v.resident_v4 = v.sms * per_sm;
+        return true;
+    });
+    if (!dv) return ST_ERR_CUDA;
+    const int sms = dv->sms, resident_v4 = dv->resident_v4;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (W % 4 == 0) && (Wp % 4 == 0) && ((uintptr_t)img % 4 == 0) && ((uintptr_t)out % 16 == 0) &&
                      (long long)Hp * Wp < (1ll << 31) && S <= 65535;

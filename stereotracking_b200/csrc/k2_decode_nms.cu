@@ -27,6 +27,12 @@ struct HeadLevels {
     int n;
 };
 
+// head-map pointers of level l: from the frame's input table when the launch carries one (a
+// replayed CUDA graph), else the ones passed with the launch
+#define K2_CLS(l) (tab ? tab->cls[l] : L.cls[l])
+#define K2_BBOX(l) (tab ? tab->bbox[l] : L.bbox[l])
+#define K2_OBJ(l) (tab ? tab->obj[l] : L.obj[l])
+
 __device__ __forceinline__ int level_of(const HeadLevels &L, int p) {
     int l = 0;
     while (l + 1 < L.n && p >= L.prior_off[l + 1]) ++l;
@@ -43,7 +49,7 @@ __device__ __forceinline__ float from_ordered_bits(uint32_t u) {
 }
 
 __global__ void __launch_bounds__(256)
-k2_score_compact(HeadLevels L, int P, int num_classes, float score_thr, float logit_cut, int cap,
+k2_score_compact(HeadLevels L, const StFrameInputs *__restrict__ tab, int P, int num_classes, float score_thr, float logit_cut, int cap,
                  int32_t *__restrict__ cand_count, float *__restrict__ cand_score,
                  int32_t *__restrict__ cand_prior, int32_t *__restrict__ cand_label) {
     const int s = blockIdx.y;
@@ -58,13 +64,13 @@ k2_score_compact(HeadLevels L, int P, int num_classes, float score_thr, float lo
         // sigmoid(x) <= score_thr for x <= logit_cut and the other factor is <= 1, so a
         // logit below the cut cannot pass `score > score_thr`: the float64 exp behind the
         // correctly rounded sigmoid is only evaluated for the ~1 % of priors that may
-        const float lo = L.obj[l][(long long)s * hw + q];
+        const float lo = K2_OBJ(l)[(long long)s * hw + q];
         if (lo > logit_cut) {
             const float so = st_sigmoid_f32(lo);
             // scores = sigmoid(cls) * sigmoid(obj); max over classes, first max wins
             float best = -1.f;
             for (int c = 0; c < num_classes; ++c) {
-                const float lc = L.cls[l][((long long)s * num_classes + c) * hw + q];
+                const float lc = K2_CLS(l)[((long long)s * num_classes + c) * hw + q];
                 if (!(lc > logit_cut)) continue;
                 float sc = __fmul_rn(st_sigmoid_f32(lc), so);
                 if (sc > best) { best = sc; label = c; }
@@ -103,7 +109,7 @@ k2_score_compact(HeadLevels L, int P, int num_classes, float score_thr, float lo
 constexpr int kScoreWarps = 8;
 
 __global__ void __launch_bounds__(kScoreWarps * 32)
-k2_score_compact_v4(HeadLevels L, int S, int P, int num_classes, float score_thr, float logit_cut, int cap,
+k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, int P, int num_classes, float score_thr, float logit_cut, int cap,
                     int32_t *__restrict__ cand_count, float *__restrict__ cand_score,
                     int32_t *__restrict__ cand_prior, int32_t *__restrict__ cand_label) {
     __shared__ int32_t queue_all[kScoreWarps][128];
@@ -124,7 +130,7 @@ k2_score_compact_v4(HeadLevels L, int S, int P, int num_classes, float score_thr
             const int l = level_of(L, j * 4);
             asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                          : "=f"(o4s[u].x), "=f"(o4s[u].y), "=f"(o4s[u].z), "=f"(o4s[u].w)
-                         : "l"(L.obj[l] + (long long)s * L.h[l] * L.w[l] + (j * 4 - L.prior_off[l])));
+                         : "l"(K2_OBJ(l) + (long long)s * L.h[l] * L.w[l] + (j * 4 - L.prior_off[l])));
         }
     }
 #pragma unroll
@@ -141,7 +147,7 @@ k2_score_compact_v4(HeadLevels L, int S, int P, int num_classes, float score_thr
         if (lo[0] > logit_cut || lo[1] > logit_cut || lo[2] > logit_cut || lo[3] > logit_cut) {
             float mc[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};     // max class logit
             for (int c = 0; c < num_classes; ++c) {
-                const float4 c4 = *reinterpret_cast<const float4 *>(L.cls[l] + ((long long)s * num_classes + c) * hw + q);
+                const float4 c4 = *reinterpret_cast<const float4 *>(K2_CLS(l) + ((long long)s * num_classes + c) * hw + q);
                 mc[0] = fmaxf(mc[0], c4.x); mc[1] = fmaxf(mc[1], c4.y);
                 mc[2] = fmaxf(mc[2], c4.z); mc[3] = fmaxf(mc[3], c4.w);
             }
@@ -175,11 +181,11 @@ k2_score_compact_v4(HeadLevels L, int S, int P, int num_classes, float score_thr
             const int l = level_of(L, p);
             const int q = p - L.prior_off[l];
             const long long hw = (long long)L.h[l] * L.w[l];
-            const float so = st_sigmoid_f32(L.obj[l][(long long)s * hw + q]);
+            const float so = st_sigmoid_f32(K2_OBJ(l)[(long long)s * hw + q]);
             // scores = sigmoid(cls) * sigmoid(obj); max over classes, first max wins
             float best = -1.f;
             for (int c = 0; c < num_classes; ++c) {
-                const float lc = L.cls[l][((long long)s * num_classes + c) * hw + q];
+                const float lc = K2_CLS(l)[((long long)s * num_classes + c) * hw + q];
                 if (!(lc > logit_cut)) continue;
                 const float v = __fmul_rn(st_sigmoid_f32(lc), so);
                 if (v > best) { best = v; label = c; }
@@ -233,7 +239,7 @@ __host__ __device__ inline size_t sort_nms_smem(int cap) {
 }
 
 __global__ void __launch_bounds__(kNmsThreads)
-k2_sort_nms(HeadLevels L, int cap, int num_classes, float scale_w, float scale_h, float iou_thr, int det_cap,
+k2_sort_nms(HeadLevels L, const StFrameInputs *__restrict__ tab, int cap, int num_classes, float scale_w, float scale_h, float iou_thr, int det_cap,
             float ori_w, float ori_h, const int32_t *__restrict__ cand_count,
             const float *__restrict__ cand_score, const int32_t *__restrict__ cand_prior,
             const int32_t *__restrict__ cand_label, float *__restrict__ boxes, float *__restrict__ scores,
@@ -298,7 +304,7 @@ k2_sort_nms(HeadLevels L, int cap, int num_classes, float scale_w, float scale_h
         const int l = level_of(L, p);
         const int q = p - L.prior_off[l];
         const long long hw = (long long)L.h[l] * L.w[l];
-        const float *bp = L.bbox[l] + (long long)s * 4 * hw + q;
+        const float *bp = K2_BBOX(l) + (long long)s * 4 * hw + q;
         const float r0 = bp[0], r1 = bp[hw], r2 = bp[2 * hw], r3 = bp[3 * hw];
         const float sf = (float)L.stride[l];
         const float px = __fmul_rn((float)(q % L.w[l]), sf);
@@ -421,11 +427,25 @@ extern "C" int st_decode_nms(st_handle *h, const float *const *cls_host, const f
                              int num_classes, float scale_w, float scale_h, int ori_h, int ori_w,
                              int det_cap, float *boxes, float *scores, int64_t *labels,
                              int32_t *prior_idx, int32_t *keep_idx, int32_t *counts, void *stream) {
+    return st_decode_nms_ws(h, cls_host, bbox_host, obj_host, nullptr, nullptr, num_levels, level_h_host, level_w_host,
+                            strides_host, S, num_classes, scale_w, scale_h, ori_h, ori_w, det_cap, boxes, scores,
+                            labels, prior_idx, keep_idx, counts, stream);
+}
+
+// tab: the kernels read the head-map pointers from it (cls/bbox/obj_host then only select the
+// kernel variant by their alignment); ws: candidate scratch of this frame (nullptr = the handle's)
+int st_decode_nms_ws(st_handle *h, const float *const *cls_host, const float *const *bbox_host,
+                     const float *const *obj_host, const StFrameInputs *tab, const StK2Scratch *ws, int num_levels,
+                     const int32_t *level_h_host, const int32_t *level_w_host, const int32_t *strides_host, int S,
+                     int num_classes, float scale_w, float scale_h, int ori_h, int ori_w, int det_cap, float *boxes,
+                     float *scores, int64_t *labels, int32_t *prior_idx, int32_t *keep_idx, int32_t *counts,
+                     void *stream) {
     if (!h || !cls_host || !bbox_host || !obj_host || num_levels < 1 || num_levels > ST_MAX_LEVELS ||
         S < 0 || S > h->cfg.max_sequences || num_classes < 1 || det_cap < 1 || !boxes || !scores ||
         !labels || !prior_idx || !keep_idx || !counts)
         return ST_ERR_INVALID_ARG;
     if (S == 0) return ST_OK;
+    StDeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     HeadLevels L;
     L.n = num_levels;
@@ -441,7 +461,10 @@ extern "C" int st_decode_nms(st_handle *h, const float *const *cls_host, const f
     // sigmoid(x) <= thr  <=>  x <= log(thr / (1 - thr)); a small margin keeps the cut conservative
     const double thr = (double)h->cfg.score_thr;
     const float logit_cut = (thr > 0.0 && thr < 1.0) ? (float)(log(thr / (1.0 - thr)) - 1e-3) : -3.0e38f;
-    ST_CUDA_OK(cudaMemsetAsync(h->cand_count, 0, sizeof(int32_t) * S, st));
+    StK2Scratch own;
+    own.count = h->cand_count; own.score = h->cand_score; own.prior = h->cand_prior; own.label = h->cand_label;
+    if (!ws) ws = &own;
+    ST_CUDA_OK(cudaMemsetAsync(ws->count, 0, sizeof(int32_t) * S, st));
     bool vec4 = true;
     for (int l = 0; l < num_levels; ++l)
         vec4 = vec4 && (level_h_host[l] * level_w_host[l]) % 4 == 0 && ((uintptr_t)cls_host[l] % 16 == 0) &&
@@ -449,16 +472,14 @@ extern "C" int st_decode_nms(st_handle *h, const float *const *cls_host, const f
     if (vec4) {
         const int items_pad = ((P >> 2) + 31) & ~31;
         k2_score_compact_v4<<<dim3((items_pad + kScoreWarps * 64 - 1) / (kScoreWarps * 64), S), kScoreWarps * 32, 0, st>>>(
-            L, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, h->cand_count, h->cand_score, h->cand_prior,
-            h->cand_label);
+            L, tab, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
     } else {
         k2_score_compact<<<dim3((P + 255) / 256, S), 256, 0, st>>>(
-            L, P, num_classes, h->cfg.score_thr, logit_cut, cap, h->cand_count, h->cand_score, h->cand_prior,
-            h->cand_label);
+            L, tab, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
     }
     k2_sort_nms<<<S, kNmsThreads, sort_nms_smem(cap), st>>>(
-        L, cap, num_classes, scale_w, scale_h, h->cfg.nms_iou_thr, det_cap, (float)ori_w, (float)ori_h,
-        h->cand_count, h->cand_score, h->cand_prior, h->cand_label, boxes, scores, labels, prior_idx,
+        L, tab, cap, num_classes, scale_w, scale_h, h->cfg.nms_iou_thr, det_cap, (float)ori_w, (float)ori_h,
+        ws->count, ws->score, ws->prior, ws->label, boxes, scores, labels, prior_idx,
         keep_idx, counts, h->st.status);
     return st_last_launch();
 }

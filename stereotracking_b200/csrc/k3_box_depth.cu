@@ -19,7 +19,9 @@
 //   k3_box_depth_cta    overflow of the table (> 3072 distinct values): staged radix select
 //                       with shared-memory histograms, 8 bits per pass
 #include <cstdlib>
-#include "st_common.cuh"
+#include <map>
+#include <mutex>
+#include "k3_select.cuh"
 
 namespace {
 
@@ -29,55 +31,9 @@ constexpr int kSmallPix = 512;           // boxes up to this many pixels: one wa
 // (2048 before: the warp kernel's longest box - ~27 bit passes over 2048 staged values - set its
 // duration at ~70 us; 512-2048 pixel boxes cost the table kernel's 512 threads a few microseconds)
 
-struct Slice { int lo, hi; };            // hi <= lo means empty
+using namespace stk3;
 
-// Python slice semantics of a[start:stop] on an axis of length n (step 1)
-__device__ __forceinline__ Slice py_slice(long long start, long long stop, int n) {
-    if (start < 0) { start += n; if (start < 0) start = 0; } else if (start > n) start = n;
-    if (stop < 0) { stop += n; if (stop < 0) stop = 0; } else if (stop > n) stop = n;
-    Slice s; s.lo = (int)start; s.hi = (int)stop;
-    return s;
-}
-
-// astype(np.int64) of a float32 on x86-64: truncation toward zero, INT64_MIN
-// for NaN / out-of-range
-__device__ __forceinline__ long long trunc_i64(float v) {
-    if (!(fabsf(v) < 9.2233720368547758e18f)) return (long long)0x8000000000000000ull;
-    return (long long)v;
-}
-
-// int64 arithmetic that wraps like NumPy's (no signed-overflow UB)
-__device__ __forceinline__ long long wrap_add(long long a, long long b) {
-    return (long long)((unsigned long long)a + (unsigned long long)b);
-}
-
-__device__ __forceinline__ bool depth_valid(float d) { return d < 150.f && d > 0.f; }
-
-// The four 2x2 corner patches of a box (:157-160): element e (0..3) of corner c
-// (0 tl, 1 tr, 2 bl, 3 br) in row-major order of the (<=2)x(<=2) patch that Python
-// slicing yields.  Returns false when the patch has no such element.
-__device__ __forceinline__ bool corner_elem(int c, int e, long long b0, long long b1, long long b2, long long b3,
-                                            int Hp, int Wp, int &y, int &x, int &cnt) {
-    const Slice ys = (c < 2) ? py_slice(b1, wrap_add(b1, 2), Hp) : py_slice(wrap_add(b3, -2), b3, Hp);
-    const Slice xs = (c & 1) ? py_slice(wrap_add(b2, -2), b2, Wp) : py_slice(b0, wrap_add(b0, 2), Wp);
-    const int ny = max(ys.hi - ys.lo, 0), nx = max(xs.hi - xs.lo, 0);
-    cnt = ny * nx;
-    if (e >= cnt) return false;
-    y = ys.lo + e / nx;
-    x = xs.lo + e % nx;
-    return true;
-}
-
-// np.mean of a corner patch from its prefetched elements v[0..cnt): sequential
-// float32 sum in row-major order, one float32 division; empty -> NaN
-__device__ __forceinline__ float corner_mean_of(const float *v, int cnt) {
-    if (cnt == 0) return __int_as_float(0x7fc00000);
-    float acc = v[0];
-    for (int e = 1; e < cnt; ++e) acc = __fadd_rn(acc, v[e]);
-    return __fdiv_rn(acc, (float)cnt);
-}
-
-struct BoxCtx {
+struct WarpCtx {
     const float *dm;      // depth map of this sequence
     int Wp;
     Slice ys, xs;
@@ -89,7 +45,7 @@ struct BoxCtx {
 
 // visit every valid depth value of the box with the 32 lanes of the warp
 template <typename F>
-__device__ __forceinline__ void for_each_valid(const BoxCtx &c, int lane, F f) {
+__device__ __forceinline__ void for_each_valid(const WarpCtx &c, int lane, F f) {
     if (c.use_stage) {
         for (int i = lane; i < c.n_valid; i += 32) f(c.staged[i]);
     } else {
@@ -141,66 +97,6 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Workspace layout (int32): [0] number of large boxes, [1] number of table overflows, [2] cursor
-// of the table kernel, [3] number of small boxes, then three lists of (sequence, row) pairs with
-// list_cap = S * cap entries each: large boxes, table overflows, small boxes.
-__device__ __forceinline__ int32_t *large_list(int32_t *ws) { return ws + 4; }
-__device__ __forceinline__ int32_t *overflow_list(int32_t *ws, int list_cap) { return ws + 4 + 2 * list_cap; }
-__device__ __forceinline__ int32_t *small_list(int32_t *ws, int list_cap) { return ws + 4 + 4 * list_cap; }
-
-// One thread per box slot: rows that can reuse the statistic of their source row are finished
-// here; the others are sorted into the dense small-box and large-box lists, so that the warp
-// kernel and the table kernel get balanced work and can run side by side.
-//
-// Reuse: the statistic depends on the box only through its truncated corners.  The second call
-// of a frame (ocsort_disparity.py:100-101) runs on the deflated track boxes, which are the
-// inflated-then-deflated detection boxes: whenever the truncated corners equal those of the
-// detection the row came from, the value of the first call is the value of this one.
-__global__ void __launch_bounds__(256)
-k3_classify(int S, int Hp, int Wp, const float *__restrict__ boxes, const int32_t *__restrict__ counts, int cap,
-            float *__restrict__ d_out, float *__restrict__ scale_out, float *__restrict__ inflated,
-            int32_t *__restrict__ worklist, int list_cap, const float *__restrict__ prev_boxes,
-            const int32_t *__restrict__ prev_index, const float *__restrict__ prev_d) {
-    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= (long long)S * cap) return;
-    const int s = (int)(o / cap), bi = (int)(o - (long long)s * cap);
-    const int cnt = counts[s];
-    const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
-    const int pi = prev_index ? prev_index[o] : -1;
-    if (bi >= cnt) return;
-    const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
-    if (pi >= 0 && pi < cap) {
-        const float4 pb = reinterpret_cast<const float4 *>(prev_boxes)[(long long)s * cap + pi];
-        if (trunc_i64(pb.x) == b0 && trunc_i64(pb.y) == b1 && trunc_i64(pb.z) == b2 && trunc_i64(pb.w) == b3) {
-            const float d = prev_d[(long long)s * cap + pi];
-            const float dd = __fmul_rn(d, d);
-            const float scale = (dd != dd) ? dd : fmaxf(fminf(dd, 3.f), 1.f);
-            d_out[o] = d;
-            scale_out[o] = scale;
-            if (inflated) {
-                const float cx = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
-                const float cy = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
-                const float hw = __fmul_rn(__fmul_rn(__fsub_rn(box.z, box.x), scale), 0.5f);
-                const float hh = __fmul_rn(__fmul_rn(__fsub_rn(box.w, box.y), scale), 0.5f);
-                reinterpret_cast<float4 *>(inflated)[o] =
-                    make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
-            }
-            return;
-        }
-    }
-    const Slice ys = py_slice(b1, b3, Hp), xs = py_slice(b0, b2, Wp);
-    const unsigned npix = (unsigned)max(xs.hi - xs.lo, 0) * (unsigned)max(ys.hi - ys.lo, 0);
-    if (npix > (unsigned)kSmallPix) {
-        const int slot = atomicAdd(&worklist[0], 1);
-        large_list(worklist)[2 * slot] = s;
-        large_list(worklist)[2 * slot + 1] = bi;
-    } else {
-        const int slot = atomicAdd(&worklist[3], 1);
-        small_list(worklist, list_cap)[2 * slot] = s;
-        small_list(worklist, list_cap)[2 * slot + 1] = bi;
-    }
-}
-
 // one small box by one warp; `staged` is the warp's shared-memory stage
 __device__ void k3_box_one(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
                            const int s, const int bi, int cap, float *__restrict__ d_out,
@@ -209,7 +105,7 @@ __device__ void k3_box_one(const float *__restrict__ depth, int Hp, int Wp, cons
     const long long o = (long long)s * cap + bi;
     const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
     const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
-    BoxCtx c;
+    WarpCtx c;
     c.dm = depth + (long long)s * Hp * Wp;
     c.Wp = Wp;
     c.ys = py_slice(b1, b3, Hp);
@@ -340,260 +236,6 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
         __syncwarp();
     }
 }
-
-// Boxes above kSmallPix pixels: one CTA per box, two tiers (both persistent over a
-// worklist written by the warp kernel):
-//   medium  <= kMediumPix pixels: 256 threads, 32 KB stage, several CTAs per SM
-//   huge     > kMediumPix pixels: 512 threads, 176 KB stage, one CTA per SM
-constexpr int kHugeThreads = 512, kHugeStage = 45056;
-constexpr int kMaxCtaWarps = 16;
-
-// visit every valid depth value of the box: f(value)
-template <typename F>
-__device__ __forceinline__ void for_each_valid_cta(const BoxCtx &c, F f) {
-    if (c.use_stage) {
-        for (int i = threadIdx.x; i < c.n_valid; i += blockDim.x) f(c.staged[i]);
-    } else {
-        for (unsigned i0 = threadIdx.x; i0 < c.npix; i0 += 4 * blockDim.x) {
-            float v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {           // four independent loads in flight
-                const unsigned i = i0 + u * blockDim.x;
-                v[u] = -1.f;
-                if (i < c.npix) {
-                    const unsigned ry = i / c.bw, rx = i - ry * c.bw;
-                    v[u] = c.dm[(long long)(c.ys.lo + ry) * c.Wp + c.xs.lo + rx];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (depth_valid(v[u])) f(v[u]);
-        }
-    }
-}
-
-// Radix select of up to two ranks at once over positive-float bit patterns.
-// On return value[k] is the element of rank rank[k] in ascending order and
-// below[k] the number of elements strictly smaller than it.
-__device__ void radix_select2_cta(const BoxCtx &c, int nsel, const int *rank_in, uint32_t *value,
-                              int *below, int *hist /* [2*256] shared */, int *sh /* [8] shared */) {
-    uint32_t prefix[2] = {0u, 0u};
-    int rank[2] = {rank_in[0], nsel > 1 ? rank_in[1] : 0};
-    int less[2] = {0, 0};
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
-        const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-        const uint32_t p0 = prefix[0], p1 = prefix[1];
-        for_each_valid_cta(c, [&](float v) {
-            // one shared-memory atomic per distinct bin among the active lanes of a
-            // warp: object pixels share one depth and would serialise otherwise
-            const uint32_t u = __float_as_uint(v);
-            const int lane_ = threadIdx.x & 31;
-            const int bin0 = ((u & himask) == p0) ? (int)((u >> shift) & 255u) : -1;
-            const unsigned act = __activemask();
-            const unsigned peers0 = __match_any_sync(act, bin0);
-            if (bin0 >= 0 && lane_ == __ffs(peers0) - 1) atomicAdd(&hist[bin0], __popc(peers0));
-            if (nsel > 1) {
-                const int bin1 = ((u & himask) == p1) ? (int)((u >> shift) & 255u) : -1;
-                const unsigned peers1 = __match_any_sync(act, bin1);
-                if (bin1 >= 0 && lane_ == __ffs(peers1) - 1) atomicAdd(&hist[256 + bin1], __popc(peers1));
-            }
-        });
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            // warp 0 locates the bin holding each rank: 8 bins per lane + warp scan
-            const int lane_ = threadIdx.x;
-            for (int k = 0; k < nsel; ++k) {
-                int local[8], tot = 0;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) { local[b] = hist[k * 256 + lane_ * 8 + b]; tot += local[b]; }
-                int inc = tot;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane_ >= o) inc += t;
-                }
-                int acc = inc - tot, found_bin = -1, found_acc = 0;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    if (found_bin < 0 && acc + local[b] > rank[k]) { found_bin = lane_ * 8 + b; found_acc = acc; }
-                    acc += local[b];
-                }
-                const unsigned who = __ballot_sync(0xffffffffu, found_bin >= 0);
-                if (who && lane_ == __ffs(who) - 1) { sh[k * 2] = found_bin; sh[k * 2 + 1] = found_acc; }
-            }
-        }
-        __syncthreads();
-        for (int k = 0; k < nsel; ++k) {
-            prefix[k] |= (uint32_t)sh[k * 2] << shift;
-            rank[k] -= sh[k * 2 + 1];
-            less[k] += sh[k * 2 + 1];
-        }
-        __syncthreads();
-    }
-    for (int k = 0; k < nsel; ++k) { value[k] = prefix[k]; below[k] = less[k]; }
-}
-
-__device__ double block_sum(double v, double *red /* [kMaxCtaWarps] shared */) {
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    return t;
-}
-
-__device__ int block_count(int v, int *red) {
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int t = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    return t;
-}
-
-template <int kThreadsT, int kStageT>
-__global__ void __launch_bounds__(kThreadsT)
-k3_box_depth_cta(const float *__restrict__ depth, int Hp, int Wp, const float *__restrict__ boxes,
-             int cap, float *__restrict__ d_out, float *__restrict__ scale_out,
-             float *__restrict__ inflated, const int32_t *__restrict__ n_work_ptr, const int32_t *__restrict__ worklist) {
-  const int n_work = *n_work_ptr;
-  for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
-    __syncthreads();                                   // shared memory is reused across items
-    const int s = worklist[2 * item], bi = worklist[2 * item + 1];
-    const int lane = threadIdx.x & 31;
-    extern __shared__ __align__(16) float staged[];    // [kStageT]
-    __shared__ int hist[512];
-    __shared__ int sh[8];
-    __shared__ int ired[kMaxCtaWarps];
-    __shared__ double dred[kMaxCtaWarps];
-    __shared__ int stage_fill;
-    __shared__ float corner_sm[16];
-    __shared__ int corner_n[4];
-
-    const long long o = (long long)s * cap + bi;
-    const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
-    const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
-    BoxCtx c;
-    c.dm = depth + (long long)s * Hp * Wp;
-    if (threadIdx.x < 16) {                 // corner patches, fetched up front (read after the barriers below)
-        int cy, cx, cn;
-        const bool has = corner_elem(threadIdx.x >> 2, threadIdx.x & 3, b0, b1, b2, b3, Hp, Wp, cy, cx, cn);
-        corner_sm[threadIdx.x] = has ? c.dm[(long long)cy * Wp + cx] : 0.f;
-        if ((threadIdx.x & 3) == 0) corner_n[threadIdx.x >> 2] = cn;
-    }
-    c.Wp = Wp;
-    c.ys = py_slice(b1, b3, Hp);
-    c.xs = py_slice(b0, b2, Wp);
-    c.bw = (unsigned)max(c.xs.hi - c.xs.lo, 0);
-    c.npix = c.bw * (unsigned)max(c.ys.hi - c.ys.lo, 0);
-    c.staged = staged;
-    c.use_stage = false;
-    // (box[2]-box[0]) > 800 in int64; wraps like NumPy for the INT64_MIN case
-    const long long wbox = wrap_add(b2, (long long)(0ull - (unsigned long long)b0));
-    int n = 0;
-    if (!(wbox > 800)) {
-        // pass 0: count the valid values and stage the first kStageT of them
-        // (warp-aggregated append; the order inside the stage is irrelevant)
-        if (threadIdx.x == 0) stage_fill = 0;
-        __syncthreads();
-        for (unsigned i0 = threadIdx.x; i0 < c.npix; i0 += 4 * blockDim.x) {
-            float v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned i = i0 + u * blockDim.x;
-                v[u] = -1.f;
-                if (i < c.npix) {
-                    const unsigned ry = i / c.bw, rx = i - ry * c.bw;
-                    v[u] = c.dm[(long long)(c.ys.lo + ry) * Wp + c.xs.lo + rx];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const bool ok = depth_valid(v[u]);
-                const unsigned act = __activemask();
-                const unsigned m = __ballot_sync(act, ok);
-                int base = 0;
-                if (m) {
-                    const int leader = __ffs(m) - 1;
-                    if (lane == leader) base = atomicAdd(&stage_fill, __popc(m));
-                    base = __shfl_sync(act, base, leader);
-                    const int pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (ok && pos < kStageT) staged[pos] = v[u];
-                }
-            }
-        }
-        __syncthreads();
-        n = stage_fill;
-        c.use_stage = n <= kStageT;
-    }
-    c.n_valid = n;
-
-    float d = -1.f, scale = 1.f;
-    if (!(n < 1 || wbox > 800)) {
-        uint32_t val[2];
-        int below[2];
-        int rk[2] = {n / 2, 0};
-        radix_select2_cta(c, 1, rk, val, below, hist, sh);
-        const float d_mid = __uint_as_float(val[0]);
-        // corner votes on the unfiltered map (:157-160)
-        int k = 0;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) k += corner_mean_of(corner_sm + 4 * cc, corner_n[cc]) > d_mid;
-        // w_start = min(1 - k/4, 0.4) * len ; w_end = w_start + 0.6 * len   (float64)
-        const double frac = fmin(1.0 - (double)k / 4.0, 0.4);
-        const double w_start = __dmul_rn(frac, (double)n);
-        const double w_end = __dadd_rn(w_start, __dmul_rn(0.6, (double)n));
-        Slice seg = py_slice((long long)w_start, (long long)w_end, n);
-        if (seg.hi <= seg.lo) seg = py_slice(0, -1, n);       // d_sorted[:-1]
-        const int m = seg.hi - seg.lo;
-        if (m <= 0) {
-            d = __int_as_float(0x7fc00000);                    // mean of empty -> NaN
-        } else {
-            rk[0] = seg.lo; rk[1] = seg.hi - 1;
-            radix_select2_cta(c, 2, rk, val, below, hist, sh);
-            const uint32_t ua = val[0], ub = val[1];
-            double sum;
-            if (ua == ub) {
-                sum = (double)__uint_as_float(ua) * (double)m;
-            } else {
-                double part = 0.0;
-                int eq_a = 0;
-                for_each_valid_cta(c, [&](float v) {
-                    uint32_t u = __float_as_uint(v);
-                    if (u > ua && u < ub) part += (double)v;
-                    eq_a += (u == ua);
-                });
-                sum = block_sum(part, dred);
-                const int n_eq_a = block_count(eq_a, ired);
-                const int in_a = below[0] + n_eq_a - seg.lo;   // duplicates of s[lo] inside
-                const int in_b = seg.hi - below[1];            // duplicates of s[hi-1] inside
-                sum += (double)__uint_as_float(ua) * (double)in_a + (double)__uint_as_float(ub) * (double)in_b;
-            }
-            d = (float)(sum / (double)m);
-        }
-        // scale = max(min(d*d/1, 3.), 1.) with Python min/max NaN behaviour
-        const float dd = __fmul_rn(d, d);
-        scale = (dd != dd) ? dd : fmaxf(fminf(dd, 3.f), 1.f);
-    }
-    if (threadIdx.x == 0) {
-        d_out[o] = d;
-        scale_out[o] = scale;
-        if (inflated) {
-            // scale_bbox (trackers/utils.py:58-73), float32, unfused
-            const float cx = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
-            const float cy = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
-            const float hw = __fmul_rn(__fmul_rn(__fsub_rn(box.z, box.x), scale), 0.5f);
-            const float hh = __fmul_rn(__fmul_rn(__fsub_rn(box.w, box.y), scale), 0.5f);
-            reinterpret_cast<float4 *>(inflated)[o] =
-                make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
-        }
-    }
-  }
-}
-
 
 // ---------------------------------------------------------------------------------
 // Large boxes, main path: one pass over the pixels builds a shared-memory table of
@@ -801,9 +443,9 @@ k3_box_depth_ablation(const float *__restrict__ depth, int Hp, int Wp, const flo
         const long long o = (long long)s * cap + bi;
         const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
         const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
-        BoxCtx c;
-        c.dm = depth + (long long)s * Hp * Wp;
-        c.Wp = Wp;
+        BoxCtx<MapSrc> c;
+        c.src.dm = depth + (long long)s * Hp * Wp;
+        c.src.Wp = Wp;
         c.ys = py_slice(b1, b3, Hp);
         c.xs = py_slice(b0, b2, Wp);
         c.bw = (unsigned)max(c.xs.hi - c.xs.lo, 0);
@@ -828,7 +470,7 @@ k3_box_depth_ablation(const float *__restrict__ depth, int Hp, int Wp, const flo
                 if (cx < 0) cx += Wp;
                 if (cy < 0) cy += Hp;
                 outside = cx < 0 || cx >= Wp || cy < 0 || cy >= Hp;
-                d = outside ? __int_as_float(0x7fc00000) : c.dm[cy * Wp + cx];
+                d = outside ? __int_as_float(0x7fc00000) : c.src.at((int)cy, (int)cx);
             } else {
                 Slice seg;
                 if (mode == 1) {
@@ -908,6 +550,9 @@ __global__ void k3_scale_boxes(const float *__restrict__ boxes, const float *__r
         make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
 }
 
+struct K3Dev { int sms, warp_ctas, table_per_sm; };
+StPerDevice<K3Dev> g_k3dev;
+
 }  // namespace
 
 extern "C" int st_box_depth(const float *depth, int S, int Hp, int Wp, const float *boxes,
@@ -928,65 +573,45 @@ extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, con
     cudaStream_t st = (cudaStream_t)stream;
     ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 4, st));
     const int list_cap = S * cap;
-    // one-time setup: SM count, shared-memory opt-ins, resident grid of the warp kernel, and an
-    // auxiliary stream with a ring of events for the fork / join below (calls are serialised by
-    // the caller, see the header)
-    static int sms = 0, warp_ctas = 0, table_per_sm = 0;
-    // one auxiliary stream per caller stream (a shared one would order the large-box kernels of
-    // independent callers - the two K3 stages of the frame pipeline - behind each other)
-    constexpr int kMaxCallers = 16;
-    static cudaStream_t caller[kMaxCallers], aux_of[kMaxCallers];
-    static int n_callers = 0;
-    static cudaEvent_t ev_ring[64];
-    static unsigned ev_next = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-        ST_CUDA_OK(cudaFuncSetAttribute(k3_box_depth_cta<kHugeThreads, kHugeStage>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(float) * kHugeStage)));
-        ST_CUDA_OK(cudaFuncSetAttribute(k3_box_depth_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)kTableSmem));
+    // once per device: shared-memory opt-ins, resident grid of the warp kernel
+    const K3Dev *dv = g_k3dev.get([](K3Dev &v) {
+        v.sms = st_ctx_sms();
+        if (cudaFuncSetAttribute(k3_box_depth_cta<kHugeThreads, kHugeStage, MakeMapSrc>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(float) * kHugeStage)) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(k3_box_depth_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kTableSmem) != cudaSuccess) return false;
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_box_depth, kWarps * 32, 0) != cudaSuccess || per_sm < 1)
             per_sm = 8;
-        warp_ctas = sms * per_sm;
+        v.warp_ctas = v.sms * per_sm;
         const char *e = getenv("ST_K3_TABLE_CTAS_PER_SM");
-        table_per_sm = e ? atoi(e) : 2;
-        for (int i = 0; i < 64; ++i) ST_CUDA_OK(cudaEventCreateWithFlags(&ev_ring[i], cudaEventDisableTiming));
-    }
-    cudaStream_t aux = nullptr;
-    for (int i = 0; i < n_callers; ++i)
-        if (caller[i] == st) aux = aux_of[i];
-    if (!aux) {
-        const int slot = n_callers < kMaxCallers ? n_callers++ : (int)(ev_next % kMaxCallers);   // recycle when full
-        if (aux_of[slot]) cudaStreamDestroy(aux_of[slot]);     // static storage: null until first used
-        int prio = 0;                                            // the auxiliary stream inherits the caller's priority
-        cudaStreamGetPriority(st, &prio);
-        ST_CUDA_OK(cudaStreamCreateWithPriority(&aux_of[slot], cudaStreamNonBlocking, prio));
-        caller[slot] = st;
-        aux = aux_of[slot];
-    }
+        v.table_per_sm = e ? atoi(e) : 2;
+        return true;
+    });
+    if (!dv) return ST_ERR_CUDA;
+    // the large boxes (table kernel, then its overflow list) run on the auxiliary stream paired
+    // with the caller's, the small boxes on the caller's stream; join before returning
+    cudaStream_t aux;
+    cudaEvent_t ev_fork, ev_join;
+    if (st_ctx_aux(st, &aux, &ev_fork, &ev_join) != ST_OK) return ST_ERR_CUDA;
     const long long slots = (long long)S * cap;
     k3_classify<<<(int)((slots + 255) / 256), 256, 0, st>>>(S, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace,
-                                                           list_cap, prev_boxes, prev_index, prev_d);
-    // fork: the large boxes (table kernel, then its overflow list) on the auxiliary stream,
-    // the small boxes on the caller's stream; join before returning to the caller's order
-    cudaEvent_t ev_fork = ev_ring[ev_next++ & 63], ev_join = ev_ring[ev_next++ & 63];
+                                                           list_cap, prev_boxes, prev_index, prev_d, (unsigned)kSmallPix);
     ST_CUDA_OK(cudaEventRecord(ev_fork, st));
     ST_CUDA_OK(cudaStreamWaitEvent(aux, ev_fork, 0));
-    long long tgrid = (long long)sms * table_per_sm;
+    long long tgrid = (long long)dv->sms * dv->table_per_sm;
     if (tgrid > list_cap) tgrid = list_cap;
     k3_box_depth_table<<<(int)tgrid, kTableThreads, kTableSmem, aux>>>(
         depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap);
-    k3_box_depth_cta<kHugeThreads, kHugeStage><<<sms, kHugeThreads, sizeof(float) * kHugeStage, aux>>>(
-        depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace + 1, workspace + 4 + 2 * list_cap);
+    MakeMapSrc mk;
+    mk.depth = depth; mk.Hp = Hp; mk.Wp = Wp;
+    k3_box_depth_cta<kHugeThreads, kHugeStage, MakeMapSrc><<<dv->sms, kHugeThreads, sizeof(float) * kHugeStage, aux>>>(
+        mk, Hp, Wp, boxes, cap, d, scale, inflated, workspace + 1, workspace + 4 + 2 * list_cap);
     ST_CUDA_OK(cudaEventRecord(ev_join, aux));
     {
         long long grid = (slots + kWarps - 1) / kWarps;
-        if (grid > warp_ctas) grid = warp_ctas;
+        if (grid > dv->warp_ctas) grid = dv->warp_ctas;
         k3_box_depth<<<(int)grid, kWarps * 32, 0, st>>>(depth, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap);
     }
     ST_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));

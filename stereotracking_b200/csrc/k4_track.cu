@@ -706,7 +706,8 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
     }
 }
 
-__global__ void k4_kalman_batch(int op, int n, double *mean, double *cov, const float *z) {
+__global__ void k4_kalman_batch(int op, int n, double *mean, double *cov, const float *z,
+                                const double *__restrict__ noise_scale /* [n] 1 - bbox_score, or null */) {
     // 4 warps per CTA, 4 tracks per warp (the 8-lane-group filter of kalman.cuh)
     const int lane = threadIdx.x & 31, gl = lane & 7;
     const int t = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 4 + (lane >> 3);
@@ -721,7 +722,7 @@ __global__ void k4_kalman_batch(int op, int n, double *mean, double *cov, const 
     else {
         double zz[4];
         for (int k = 0; k < 4; ++k) zz[k] = active ? (double)z[g * 4 + k] : 0.0;
-        stkf::update8(row, zz, gl);
+        stkf::update8(row, zz, gl, (active && noise_scale) ? noise_scale[g] : 1.0);
     }
     stkf::store8(row, mean + g * 8, cov + g * 64, gl, active);
 }
@@ -732,12 +733,14 @@ __global__ void k4_kalman_batch(int op, int n, double *mean, double *cov, const 
 // distance of every measurement through the lower Cholesky factor and a forward substitution.
 __global__ void k4_kalman_project(int n, const double *__restrict__ mean, const double *__restrict__ cov,
                                   double *__restrict__ pmean, double *__restrict__ pcov, int m,
-                                  const double *__restrict__ meas, int only_position, double *__restrict__ dist) {
+                                  const double *__restrict__ meas, int only_position, double *__restrict__ dist,
+                                  const double *__restrict__ noise_scale /* [n] 1 - bbox_score (use_nsa), or null */) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const double *mu = mean + (long long)t * 8, *P = cov + (long long)t * 64;
-    const double sp = __dmul_rn(1.0 / 20, mu[3]);
-    const double r[4] = {__dmul_rn(sp, sp), __dmul_rn(sp, sp), __dmul_rn(1e-1, 1e-1), __dmul_rn(sp, sp)};
+    const double ns = noise_scale ? noise_scale[t] : 1.0;          // x * 1.0 is exact
+    const double sp = __dmul_rn(ns, __dmul_rn(1.0 / 20, mu[3])), sa = __dmul_rn(ns, 1e-1);
+    const double r[4] = {__dmul_rn(sp, sp), __dmul_rn(sp, sp), __dmul_rn(sa, sa), __dmul_rn(sp, sp)};
     double A[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -874,6 +877,7 @@ extern "C" int st_create(const st_config *cfg, st_handle **out) {
 
 extern "C" int st_destroy(st_handle *h) {
     if (!h) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     cudaFree(h->all_mem);
     delete h;
     return ST_OK;
@@ -881,6 +885,7 @@ extern "C" int st_destroy(st_handle *h) {
 
 extern "C" int st_reset(st_handle *h, const uint8_t *seq_mask, void *stream) {
     if (!h) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     k4_reset<<<h->cfg.max_sequences, 128, 0, (cudaStream_t)stream>>>(h->st, h->cfg.max_tracks, seq_mask);
     return st_last_launch();
 }
@@ -904,6 +909,7 @@ extern "C" long long st_snapshot_bytes(st_handle *h) {
 
 extern "C" int st_snapshot_save(st_handle *h, void *buf_host, long long bytes, void *stream) {
     if (!h || !buf_host || bytes < st_snapshot_bytes(h)) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     SnapshotHeader hd{kSnapshotMagic, (uint32_t)ST_ABI_VERSION, h->cfg.max_sequences, h->cfg.max_tracks,
                       h->cfg.max_dets, h->cfg.max_candidates, (uint64_t)h->all_bytes};
     memcpy(buf_host, &hd, sizeof(hd));
@@ -916,6 +922,7 @@ extern "C" int st_snapshot_save(st_handle *h, void *buf_host, long long bytes, v
 
 extern "C" int st_snapshot_load(st_handle *h, const void *buf_host, long long bytes, void *stream) {
     if (!h || !buf_host || bytes < (long long)sizeof(SnapshotHeader)) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     SnapshotHeader hd;
     memcpy(&hd, buf_host, sizeof(hd));
     if (hd.magic != kSnapshotMagic || hd.abi != (uint32_t)ST_ABI_VERSION || hd.max_sequences != h->cfg.max_sequences ||
@@ -932,12 +939,26 @@ extern "C" int st_snapshot_load(st_handle *h, const void *buf_host, long long by
 
 extern "C" int st_read_status(st_handle *h, int32_t *status_host, int S) {
     if (!h || !status_host || S < 0 || S > h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
+    // the steps run on non-blocking streams the legacy default stream does not order against:
+    // wait for everything in flight on the device, then read
+    ST_CUDA_OK(cudaDeviceSynchronize());
     ST_CUDA_OK(cudaMemcpy(status_host, h->st.status, sizeof(int32_t) * S, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+extern "C" int st_read_live_counts(st_handle *h, int32_t *live_host, int S, void *stream) {
+    if (!h || !live_host || S < 0 || S > h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ST_CUDA_OK(cudaMemcpyAsync(live_host, h->st.n_live, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, st));
+    ST_CUDA_OK(cudaStreamSynchronize(st));
     return ST_OK;
 }
 
 extern "C" int st_read_debug(st_handle *h, int32_t *debug_host, int S) {
     if (!h || !debug_host || S < 0 || S > h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     // a side stream so that the words can be read while a kernel is still running
     cudaStream_t side;
     ST_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
@@ -949,6 +970,7 @@ extern "C" int st_read_debug(st_handle *h, int32_t *debug_host, int S) {
 
 extern "C" int st_debug_read_cost(st_handle *h, int seq, float *cost_host, int count) {
     if (!h || !cost_host || seq < 0 || seq >= h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     ST_CUDA_OK(cudaDeviceSynchronize());
     ST_CUDA_OK(cudaMemcpy(cost_host, h->cost + (size_t)seq * h->cfg.max_tracks * h->cfg.max_dets,
                           sizeof(float) * count, cudaMemcpyDeviceToHost));
@@ -962,6 +984,7 @@ extern "C" int st_debug_set_skip(int mask) {
 
 extern "C" int st_clear_status(st_handle *h, void *stream) {
     if (!h) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     ST_CUDA_OK(cudaMemsetAsync(h->st.status, 0, sizeof(int32_t) * h->cfg.max_sequences, (cudaStream_t)stream));
     return ST_OK;
 }
@@ -976,6 +999,7 @@ extern "C" int st_track_step(st_handle *h, int S, const int32_t *frame_ids, cons
         !det_scales || !det_depth || !det_counts || det_cap < 1 || !out_boxes || !out_scores || !out_labels ||
         !out_scales || !out_depth || !out_ids || !out_counts)
         return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     if (S == 0) return ST_OK;
     Params pr;
     pr.T = h->cfg.max_tracks; pr.D = h->cfg.max_dets;
@@ -996,6 +1020,7 @@ extern "C" int st_export_state(st_handle *h, int seq, int64_t *ids_host, double 
                                float *velocity_host, uint8_t *flags_host, int32_t *hits_host,
                                int32_t *last_frame_host, int64_t *num_tracks_host) {
     if (!h || seq < 0 || seq >= h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     ST_CUDA_OK(cudaDeviceSynchronize());
     const int T = h->cfg.max_tracks;
     int n_live = 0;
@@ -1028,18 +1053,28 @@ extern "C" int st_export_state(st_handle *h, int seq, int64_t *ids_host, double 
 }
 
 extern "C" int st_kalman_batch(int op, int n, double *mean, double *cov, const float *z, void *stream) {
+    return st_kalman_batch_scored(op, n, mean, cov, z, nullptr, stream);
+}
+
+extern "C" int st_kalman_batch_scored(int op, int n, double *mean, double *cov, const float *z,
+                                      const double *noise_scale, void *stream) {
     if (op < 0 || op > 2 || n < 0 || !mean || !cov || (op != 1 && !z)) return ST_ERR_INVALID_ARG;
     if (n == 0) return ST_OK;
-    k4_kalman_batch<<<(n + 15) / 16, 128, 0, (cudaStream_t)stream>>>(op, n, mean, cov, z);
+    k4_kalman_batch<<<(n + 15) / 16, 128, 0, (cudaStream_t)stream>>>(op, n, mean, cov, z, noise_scale);
     return st_last_launch();
 }
 
 extern "C" int st_kalman_project(int n, const double *mean, const double *cov, double *pmean, double *pcov,
                                  void *stream) {
+    return st_kalman_project_scored(n, mean, cov, nullptr, pmean, pcov, stream);
+}
+
+extern "C" int st_kalman_project_scored(int n, const double *mean, const double *cov, const double *noise_scale,
+                                        double *pmean, double *pcov, void *stream) {
     if (n < 0 || !mean || !cov || (!pmean && !pcov)) return ST_ERR_INVALID_ARG;
     if (n == 0) return ST_OK;
     k4_kalman_project<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, mean, cov, pmean, pcov, 0, nullptr, 0,
-                                                                       nullptr);
+                                                                       nullptr, noise_scale);
     return st_last_launch();
 }
 
@@ -1048,7 +1083,7 @@ extern "C" int st_kalman_gating(int n, const double *mean, const double *cov, in
     if (n < 0 || m < 0 || !mean || !cov || !dist || (m > 0 && !meas)) return ST_ERR_INVALID_ARG;
     if (n == 0 || m == 0) return ST_OK;
     k4_kalman_project<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, mean, cov, nullptr, nullptr, m, meas,
-                                                                       only_position != 0, dist);
+                                                                       only_position != 0, dist, nullptr);
     return st_last_launch();
 }
 
@@ -1057,6 +1092,7 @@ extern "C" int st_lapjv_batch(st_handle *h, int B, int R, int C, const float *co
     if (!h || B < 0 || R < 0 || C < 0 || R + C > h->cfg.max_tracks + h->cfg.max_dets || !row2col || !col2row ||
         (R > 0 && C > 0 && !cost))
         return ST_ERR_INVALID_ARG;
+    StDeviceGuard guard(h->device);
     if (B == 0 || R + C == 0) return ST_OK;
     k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C) + sizeof(int) * (2 * R + C + 4), (cudaStream_t)stream>>>(
         R, C, cost, cost_limit / 2.0, mode, row2col, col2row, h->st.status, h->st.debug + 6);

@@ -81,8 +81,10 @@ __device__ __forceinline__ void predict8(Row8 &r, int gl) {
     r.m = gl < 4 ? r.m + mv : r.m;
 }
 
-// z = measurement (cx, cy, a, h) promoted to float64, the same in all lanes of the group
-__device__ __forceinline__ void update8(Row8 &r, const double *z, int gl) {
+// z = measurement (cx, cy, a, h) promoted to float64, the same in all lanes of the group.
+// nsa = 1 - bbox_score when the filter was built with use_nsa=True (kalman_filter.py:144-145
+// scales every measurement std by it), else 1 (x * 1.0 is exact, so the default path is unchanged).
+__device__ __forceinline__ void update8(Row8 &r, const double *z, int gl, double nsa = 1.0) {
     const double h = shfl8(r.m, 3);
     // S = H P H^T + R, replicated in every lane
     double S[4][4];
@@ -92,7 +94,7 @@ __device__ __forceinline__ void update8(Row8 &r, const double *z, int gl) {
         for (int q = 0; q < 4; ++q) {
             double v = shfl8(r.p[q], a);
             if (a == q) {
-                const double sd = a == 2 ? 1e-1 : kWPos * h;
+                const double sd = nsa * (a == 2 ? 1e-1 : kWPos * h);
                 v += sd * sd;
             }
             S[a][q] = v;

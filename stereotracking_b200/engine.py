@@ -62,17 +62,31 @@ class FrameBuffers:
         self.det_depth = torch.zeros(S, D, **f32)
         self.det_scales = torch.zeros(S, D, **f32)
         self.det_inflated = torch.zeros(S, D, 4, **f32)
-        # track outputs
+        # track outputs.  The rows a caller reads back (pred_track_instances fields + counts) are
+        # views of ONE allocation, so a frame's results cross PCIe as a single copy (out_block).
         self.trk_boxes = torch.zeros(S, D, 4, **f32)       # inflated (tracker space)
-        self.out_boxes = torch.zeros(S, D, 4, **f32)       # deflated (image space)
-        self.out_scores = torch.zeros(S, D, **f32)
-        self.out_labels = torch.zeros(S, D, **i64)
-        self.out_scales = torch.zeros(S, D, **f32)
+        fields = [('out_boxes', (S, D, 4), torch.float32), ('out_ids', (S, D), torch.int64),
+                  ('out_scores', (S, D), torch.float32), ('out_labels', (S, D), torch.int64),
+                  ('out_scales', (S, D), torch.float32), ('out_depth', (S, D), torch.float32),
+                  ('out_counts', (S,), torch.int32)]
+        offs, total = [], 0
+        for _, shape, dt in fields:
+            offs.append(total)
+            n = 1
+            for v in shape:
+                n *= v
+            total += -(-n * torch.empty(0, dtype=dt).element_size() // 256) * 256
+        self.out_block = torch.zeros(total, dtype=torch.uint8, device=dev)
+        self.out_layout = []
+        for (name, shape, dt), o in zip(fields, offs):
+            n = 1
+            for v in shape:
+                n *= v
+            nbytes = n * torch.empty(0, dtype=dt).element_size()
+            setattr(self, name, self.out_block[o:o + nbytes].view(dt).view(*shape))
+            self.out_layout.append((name, o, shape, dt))
         self.trk_depth = torch.zeros(S, D, **f32)          # depth carried through the tracker
-        self.out_depth = torch.zeros(S, D, **f32)          # recomputed on deflated boxes
         self.out_scale2 = torch.zeros(S, D, **f32)
-        self.out_ids = torch.zeros(S, D, **i64)
-        self.out_counts = torch.zeros(S, **i32)
         self.out_src = torch.zeros(S, D, **i32)            # detection row of every track row
         self.frame_ids = torch.zeros(S, **i32)
         self.k3_workspace = torch.zeros(4 + 6 * S * D, **i32)
@@ -82,17 +96,73 @@ class FrameBuffers:
         return [self.out_boxes, self.out_ids, self.out_scores, self.out_labels, self.out_scales,
                 self.out_depth, self.out_counts]
 
-    def results(self):
-        """Host copies of the outputs, one dict per sequence."""
-        n = self.out_counts.cpu().tolist()
-        pack = [t.cpu() for t in (self.out_boxes, self.out_ids, self.out_scores, self.out_labels,
-                                  self.out_scales, self.out_depth)]
+    @staticmethod
+    def unpack(block, layout):
+        """The output tensors as views of a (host or device) copy of ``out_block``."""
+        out = {}
+        for name, o, shape, dt in layout:
+            n = 1
+            for v in shape:
+                n *= v
+            out[name] = block[o:o + n * torch.empty(0, dtype=dt).element_size()].view(dt).view(*shape)
+        return out
+
+    def results(self, host_block=None):
+        """Host copies of the outputs, one dict per sequence (``host_block``: a host copy of
+        ``out_block`` that was already transferred)."""
+        blk = self.out_block.cpu() if host_block is None else host_block
+        v = self.unpack(blk, self.out_layout)
+        n = v['out_counts'].tolist()
+        pack = [v[k] for k in ('out_boxes', 'out_ids', 'out_scores', 'out_labels', 'out_scales', 'out_depth')]
         out = []
         for s, m in enumerate(n):
             out.append(dict(bboxes=pack[0][s, :m].numpy(), instances_id=pack[1][s, :m].numpy(),
                             scores=pack[2][s, :m].numpy(), labels=pack[3][s, :m].numpy(),
                             scales=pack[4][s, :m].numpy(), depth=pack[5][s, :m].numpy()))
         return out
+
+
+class FrameInputs:
+    """One lockstep frame's inputs - frame ids [S] i32, raw disparity [S,H,W] u16, head maps per
+    level cls [S,C,h,w] / bbox [S,4,h,w] / obj [S,1,h,w] f32 - as views of ONE allocation
+    (``block``, uint8; fields 256-byte aligned), on the host (optionally pinned) or a device: a
+    frame crosses PCIe as a single ``cudaMemcpyAsync`` (``dst.block.copy_(src.block)``) and lands
+    at fixed device addresses, so the frame's graph needs no pointer update."""
+
+    def __init__(self, S, H, W, level_shapes, num_classes=1, device='cpu', pin=False):
+        fields = [('frame_ids', (S,), torch.int32), ('raw', (S, H, W), torch.uint16)]
+        for l, (h, w) in enumerate(level_shapes):
+            fields += [(f'cls{l}', (S, num_classes, h, w), torch.float32), (f'bbox{l}', (S, 4, h, w), torch.float32),
+                       (f'obj{l}', (S, 1, h, w), torch.float32)]
+        offs, total = [], 0
+        for _, shape, dt in fields:
+            offs.append(total)
+            n = 1
+            for v in shape:
+                n *= v
+            total += -(-n * torch.empty(0, dtype=dt).element_size() // 256) * 256
+        self.block = torch.zeros(total, dtype=torch.uint8, device=device)
+        if pin:
+            self.block = self.block.pin_memory()
+        v = {}
+        for (name, shape, dt), o in zip(fields, offs):
+            n = 1
+            for k in shape:
+                n *= k
+            v[name] = self.block[o:o + n * torch.empty(0, dtype=dt).element_size()].view(dt).view(*shape)
+        L = len(level_shapes)
+        self.frame_ids, self.raw = v['frame_ids'], v['raw']
+        self.cls = [v[f'cls{l}'] for l in range(L)]
+        self.bbox = [v[f'bbox{l}'] for l in range(L)]
+        self.obj = [v[f'obj{l}'] for l in range(L)]
+        self.nbytes = total
+
+    def fill(self, frame_id, raw, cls_l, bbox_l, obj_l):
+        self.frame_ids.fill_(int(frame_id))
+        self.raw.copy_(raw)
+        for dst, src in zip(self.cls + self.bbox + self.obj, list(cls_l) + list(bbox_l) + list(obj_l)):
+            dst.copy_(src)
+        return self
 
 
 class StereoTrackEngine:
@@ -244,6 +314,28 @@ class StereoTrackEngine:
                        'st_box_depth_mode')
         return d_out, scale_out, inflated_out
 
+    def box_depth_raw(self, raw, padded_hw, boxes, counts, d_out=None, scale_out=None, inflated_out=None,
+                      prev_boxes=None, prev_index=None, prev_d=None):
+        """extract_depth (ocsort_disparity.py:136-175) straight from the raw u16 frames [S,H,W]:
+        bit-identical to ``box_depth`` on the map ``disp2depth(raw)`` writes (resize factor 1),
+        without that map (st_box_depth_raw).  ``prev_*``: reuse of an earlier call's values as
+        in st_box_depth_reuse."""
+        S, H, W = raw.shape
+        Hp, Wp = padded_hw
+        cap = boxes.shape[1]
+        dev = raw.device
+        d_out = d_out if d_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
+        scale_out = scale_out if scale_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
+        ws = self.k3_workspace
+        if ws.numel() < 4 + 6 * S * cap or ws.device != dev:
+            ws = self.k3_workspace = torch.zeros(4 + 6 * S * cap, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.st_box_depth_raw(_ptr(self._dev(raw, torch.uint16)), S, H, W, Hp, Wp, self.cfg.baseline,
+                                             self.cfg.focal_length, _ptr(self._dev(boxes, torch.float32)),
+                                             _ptr(self._dev(counts, torch.int32)), cap, _ptr(d_out), _ptr(scale_out),
+                                             _ptr(inflated_out), _ptr(ws), _ptr(prev_boxes), _ptr(prev_index),
+                                             _ptr(prev_d), self._stream()), 'st_box_depth_raw')
+        return d_out, scale_out, inflated_out
+
     def scale_boxes(self, boxes, scales, counts, invert, out=None):
         S, cap = scales.shape
         out = out if out is not None else torch.empty_like(boxes)
@@ -285,26 +377,32 @@ class StereoTrackEngine:
     def step(self, raw, cls_l, bbox_l, obj_l, frame_ids=None, resized_hw=None):
         """One lockstep frame from raw inputs.  Results are left in the out_* buffers."""
         S, H, W = raw.shape
-        if self.depth_map is None or self.depth_map.shape[0] != S:
-            Hr, Wr = resized_hw or (H, W)
-            Hp, Wp = -(-Hr // 32) * 32, -(-Wr // 32) * 32
-            self.depth_map = torch.empty(S, Hp, Wp, dtype=torch.float32, device=self.device)
+        Hr, Wr = resized_hw or (H, W)
+        Hp, Wp = -(-Hr // 32) * 32, -(-Wr // 32) * 32
+        if self.depth_map is None or tuple(self.depth_map.shape) != (S, Hp, Wp):
+            self.depth_map = self.buffers.depth_map = torch.empty(S, Hp, Wp, dtype=torch.float32, device=self.device)
         self.disp2depth(raw, resized_hw, out=self.depth_map)
         self.decode_nms(cls_l, bbox_l, obj_l, (H, W))
         self.step_from_dets(self.depth_map, frame_ids)
 
     def make_frame_io(self, raw_shape, level_shapes, num_classes=1, resized_hw=None, scale_factor=(1.0, 1.0),
-                      bufs=None):
+                      bufs=None, depth_source='map'):
         """Prepare a reusable st_frame_io for inputs of the given shapes: raw
         [S,H,W] and per-level head maps [S,C,h,w].  Pointers to the per-step inputs
         are filled by ``frame_step``; everything else is bound once to the buffer
-        set ``bufs`` (default: the engine's own)."""
+        set ``bufs`` (default: the engine's own).  ``depth_source``: 'map' = K1 writes the
+        float32 depth map and K3 gathers from it; 'raw' = K3 gathers from the raw frame and no
+        map is written (resize factor 1 only); 'raw+map' = K3 from the raw frame, map written too."""
+        if depth_source not in ('map', 'raw', 'raw+map'):
+            raise ValueError(f'unknown depth_source {depth_source!r}')
         S, H, W = raw_shape
         Hr, Wr = resized_hw or (H, W)
+        if depth_source != 'map' and (Hr, Wr) != (H, W):
+            raise ValueError("depth_source='raw' needs resize factor 1 (st_box_depth_raw)")
         Hp, Wp = -(-Hr // 32) * 32, -(-Wr // 32) * 32
         own = bufs is None
         bufs = self if own else bufs
-        if bufs.depth_map is None or tuple(bufs.depth_map.shape) != (S, Hp, Wp):
+        if depth_source != 'raw' and (bufs.depth_map is None or tuple(bufs.depth_map.shape) != (S, Hp, Wp)):
             bufs.depth_map = torch.empty(S, Hp, Wp, dtype=torch.float32, device=self.device)
             if own:
                 self.buffers.depth_map = bufs.depth_map
@@ -320,7 +418,8 @@ class StereoTrackEngine:
         io.level_h, io.level_w, io.strides = (C.cast(keep[k], C.c_void_p) for k in ('lh', 'lw', 'st'))
         io.num_levels, io.num_classes, io.ori_h, io.ori_w = L, num_classes, H, W
         io.scale_w, io.scale_h = float(scale_factor[0]), float(scale_factor[1])
-        io.depth_map = bufs.depth_map.data_ptr()
+        io.depth_map = 0 if depth_source == 'raw' else bufs.depth_map.data_ptr()
+        io.depth_from_raw = int(depth_source != 'map')
         for name in ('det_boxes', 'det_scores', 'det_labels', 'det_prior', 'det_keep', 'det_counts',
                      'det_depth', 'det_scales', 'det_inflated', 'trk_boxes', 'trk_depth', 'out_scale2',
                      'out_src', 'k3_workspace',
@@ -331,7 +430,7 @@ class StereoTrackEngine:
         return io
 
     def frame_step(self, io, raw, cls_l, bbox_l, obj_l):
-        """One lockstep frame through st_frame_step (a single C call, 9 kernel launches)."""
+        """One lockstep frame through st_frame_step (a single C call, KERNELS_PER_FRAME launches)."""
         io.raw = raw.data_ptr()
         for l in range(len(cls_l)):
             io._keep['cls'][l] = cls_l[l].data_ptr()
@@ -366,7 +465,16 @@ class StereoTrackEngine:
         if m is not None:
             torch.cuda.current_stream(self.device).synchronize()
 
+    def live_counts(self):
+        """Live tracks per sequence (len(tracker.tracks)); synchronises the current stream."""
+        import numpy as np
+        n = np.zeros(self.cfg.n_seq, np.int32)
+        _lib.check(self.lib.st_read_live_counts(self._h, n.ctypes.data_as(C.c_void_p), self.cfg.n_seq,
+                                                self._stream()), 'st_read_live_counts')
+        return n
+
     def status(self):
+        """Sticky ST_STATUS_* bits per sequence; waits for all work on the device first."""
         import numpy as np
         st = np.zeros(self.cfg.n_seq, np.int32)
         _lib.check(self.lib.st_read_status(self._h, st.ctypes.data_as(C.c_void_p), self.cfg.n_seq))
@@ -427,18 +535,19 @@ class StereoTrackEngine:
 
 class FramePipeline:
     """Software pipeline over consecutive frames (st_pipeline_* of the C ABI): K1 and
-    K2 of a frame run side by side, then K3 on its detections, the tracker and the
-    deflate + K3 on its tracks, each on its own library stream, so up to five
-    consecutive frames are in different stages at once.  ``depth`` complete buffer
+    K2 of a frame run side by side, then K3 on its detections (the "pre" segment, on the ring
+    slot's own stream), the tracker (one stream, frames in order) and the deflate + K3 on its
+    tracks ("post"), so several consecutive frames are in different stages at once.  ``depth`` complete buffer
     sets are cycled; frame k uses set k % depth and its results stay readable until
     frame k + depth is submitted."""
 
-    def __init__(self, engine, raw_shape, level_shapes, depth=5, num_classes=1):
-        self.engine, self.depth = engine, depth
+    def __init__(self, engine, raw_shape, level_shapes, depth=5, num_classes=1, depth_source='map'):
+        self.engine, self.depth, self.depth_source = engine, depth, depth_source
         S = raw_shape[0]
         self.n_seq = S
         self.slots = [engine.buffers] + [FrameBuffers(S, engine.cfg.max_dets, engine.device) for _ in range(depth - 1)]
-        self.ios = [engine.make_frame_io(raw_shape, level_shapes, num_classes, bufs=None if i == 0 else b)
+        self.ios = [engine.make_frame_io(raw_shape, level_shapes, num_classes, bufs=None if i == 0 else b,
+                                         depth_source=depth_source)
                     for i, b in enumerate(self.slots)]
         self._p = C.c_void_p()
         with torch.cuda.device(engine.device):
@@ -489,6 +598,16 @@ class FramePipeline:
                                 [t.data_ptr() for t in bbox_l], [t.data_ptr() for t in obj_l],
                                 ready_event, done_event, 0 if warp is None else warp.data_ptr())
 
+    def use_graphs(self, enable=True):
+        """Replay frames as CUDA graphs (st_pipeline_use_graphs): from a slot's second use on."""
+        _lib.check(self.engine.lib.st_pipeline_use_graphs(self._p, int(bool(enable))), 'st_pipeline_use_graphs')
+
+    def stats(self):
+        """dict(graph_frames=frames replayed as graphs, captures=stream captures so far)."""
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        _lib.check(self.engine.lib.st_pipeline_stats(self._p, C.byref(a), C.byref(b)), 'st_pipeline_stats')
+        return dict(graph_frames=int(a.value), captures=int(b.value))
+
     STAGES = ('k1_disp2depth', 'k2_decode_nms', 'k3_box_depth_dets', 'k4_track_step', 'deflate_k3_tracks')
 
     def trace(self, n_frames):
@@ -520,7 +639,8 @@ class LockstepGroups:
     path.  One group per GPU is the default: the frame pipeline already overlaps the
     latency-bound stages with the bandwidth-bound ones."""
 
-    def __init__(self, n_seq, n_groups=1, device='cuda:0', depth=5, **cfg_kw):
+    def __init__(self, n_seq, n_groups=1, device='cuda:0', depth=5, depth_source='map', **cfg_kw):
+        self.depth_source = depth_source
         n_groups = max(1, min(n_groups, n_seq))
         base, extra = divmod(n_seq, n_groups)
         self.sizes = [base + (1 if g < extra else 0) for g in range(n_groups)]
@@ -532,7 +652,7 @@ class LockstepGroups:
 
     def bind(self, raw_shape, level_shapes, num_classes=1):
         _, H, W = raw_shape
-        self.pipes = [FramePipeline(e, (sz, H, W), level_shapes, self.depth, num_classes)
+        self.pipes = [FramePipeline(e, (sz, H, W), level_shapes, self.depth, num_classes, self.depth_source)
                       for e, sz in zip(self.engines, self.sizes)]
 
     def plan(self, raw, cls_l, bbox_l, obj_l, first_frame_id=0):
@@ -570,6 +690,10 @@ class LockstepGroups:
         for p in self.pipes:
             p.fork(stream)
 
+    def use_graphs(self, enable=True):
+        for p in self.pipes:
+            p.use_graphs(enable)
+
     def status(self):
         import numpy as np
         return np.concatenate([e.status() for e in self.engines])
@@ -585,4 +709,6 @@ class LockstepGroups:
 
     @property
     def kernels_per_frame(self):
-        return StereoTrackEngine.KERNELS_PER_FRAME * len(self.engines)
+        # without the depth map K1 is not launched
+        per = StereoTrackEngine.KERNELS_PER_FRAME - (1 if self.depth_source == 'raw' else 0)
+        return per * len(self.engines)

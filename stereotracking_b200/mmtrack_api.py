@@ -19,9 +19,12 @@ lockstep form is ``stereotracking_b200.engine``.
 """
 import torch
 
-from . import _lib
+from . import _lib, compat
 from .compat import MODELS, TASK_UTILS, InstanceData
 from .engine import EngineConfig, StereoTrackEngine
+
+# BaseMultiObjectTracker(mmengine BaseModel) when mmtrack is installed, a stand-in otherwise
+_ShellBase = compat.model_shell_base()
 
 
 def _mesh_affine(curr_img, prev_img, metainfo, step=16, winsize=31, ransac_thr=5.0, min_inlier_ratio=0.3):
@@ -65,14 +68,18 @@ class KalmanFilter:
     chi2inv95 = {1: 3.8415, 2: 5.9915, 3: 7.8147, 4: 9.4877, 5: 11.070, 6: 12.592, 7: 14.067, 8: 15.507, 9: 16.919}
 
     def __init__(self, center_only: bool = False, use_nsa: bool = False):
-        if use_nsa:
-            raise NotImplementedError('use_nsa=True is not configured anywhere under configs/stereo_tracking')
         self.center_only = center_only
         self.gating_threshold = self.chi2inv95[2 if center_only else 4]
         self.use_nsa = use_nsa
         self._lib = _lib.lib()
 
-    def _run(self, op, mean, cov, z):
+    def _noise_scale(self, bbox_score):
+        """kalman_filter.py:144-145: with use_nsa every measurement std is scaled by 1 - bbox_score."""
+        if not self.use_nsa:
+            return None
+        return torch.tensor([1 - bbox_score], dtype=torch.float64, device='cuda')
+
+    def _run(self, op, mean, cov, z, bbox_score=0.):
         import ctypes as C
         import numpy as np
         if not torch.cuda.is_available():
@@ -80,9 +87,11 @@ class KalmanFilter:
         m = torch.as_tensor(np.asarray(mean, np.float64).reshape(1, 8)).cuda().contiguous()
         c = torch.as_tensor(np.asarray(cov, np.float64).reshape(1, 64)).cuda().contiguous()
         zt = None if z is None else torch.as_tensor(np.asarray(z, np.float32).reshape(1, 4)).cuda().contiguous()
-        _lib.check(self._lib.st_kalman_batch(op, 1, C.c_void_p(m.data_ptr()), C.c_void_p(c.data_ptr()),
-                                             C.c_void_p(0 if zt is None else zt.data_ptr()),
-                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ns = self._noise_scale(bbox_score) if op == 2 else None
+        _lib.check(self._lib.st_kalman_batch_scored(op, 1, C.c_void_p(m.data_ptr()), C.c_void_p(c.data_ptr()),
+                                                    C.c_void_p(0 if zt is None else zt.data_ptr()),
+                                                    C.c_void_p(0 if ns is None else ns.data_ptr()),
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return m.cpu().numpy().reshape(8), c.cpu().numpy().reshape(8, 8)
 
     def initiate(self, measurement):
@@ -93,7 +102,7 @@ class KalmanFilter:
         return self._run(1, mean, covariance, None)
 
     def update(self, mean, covariance, measurement, bbox_score: float = 0.):
-        return self._run(2, mean, covariance, measurement)
+        return self._run(2, mean, covariance, measurement, bbox_score)
 
     def _states(self, mean, covariance):
         import numpy as np
@@ -108,8 +117,11 @@ class KalmanFilter:
         m, c = self._states(mean, covariance)
         pm = torch.empty(m.shape[0], 4, dtype=torch.float64, device='cuda')
         pc = torch.empty(m.shape[0], 16, dtype=torch.float64, device='cuda')
-        _lib.check(self._lib.st_kalman_project(m.shape[0], m.data_ptr(), c.data_ptr(), pm.data_ptr(), pc.data_ptr(),
-                                               torch.cuda.current_stream().cuda_stream), 'st_kalman_project')
+        ns = self._noise_scale(bbox_score)
+        _lib.check(self._lib.st_kalman_project_scored(m.shape[0], m.data_ptr(), c.data_ptr(),
+                                                      None if ns is None else ns.data_ptr(), pm.data_ptr(),
+                                                      pc.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   'st_kalman_project_scored')
         return pm.cpu().numpy().reshape(4), pc.cpu().numpy().reshape(4, 4)
 
     def gating_distance(self, mean, covariance, measurements, only_position: bool = False):
@@ -165,6 +177,7 @@ class OCSORTTracker_Disparity:
         # keep_memo: keep every frame's output rows for ``memo`` / ``get`` (base_tracker.py:120-177;
         # grows without bound like the reference's per-track lists - switch off for endless streams)
         self.keep_memo, self._frames = bool(keep_memo), []
+        self._n_live = 0          # live tracks after the last step (host copy; `empty` of base_tracker.py:39-41)
         if kwargs:
             raise TypeError(f'unexpected keyword arguments {sorted(kwargs)}')
         if momentums is not None:
@@ -208,6 +221,7 @@ class OCSORTTracker_Disparity:
     def reset(self):
         self._engine.reset()
         self._frames = []
+        self._n_live = 0
 
     # memo items in the order of the reference's update(...) call (:598-605)
     MEMO_ITEMS = ('ids', 'bboxes', 'scores', 'labels', 'scales', 'depth', 'frame_ids')
@@ -267,7 +281,7 @@ class OCSORTTracker_Disparity:
 
     @property
     def empty(self):
-        return len(self._state()['ids']) == 0
+        return self._n_live == 0
 
     @property
     def ids(self):
@@ -305,8 +319,12 @@ class OCSORTTracker_Disparity:
         eng.frame_ids.fill_(int(frame_id))
         warp = None
         if frame_id == 0:
-            self.reset_cmc()                                                   # :385-387
+            # :385-387: reset() and reset_cmc() come first, so frame 0 of every video takes the
+            # init-only branch (:391) and never reaches the estimator (the kernel resets the
+            # device state itself when it sees frame_id == 0)
+            self.reset_cmc()
             self._frames = []
+            self._n_live = 0
         if self.with_cmc:
             # the reference estimates only in the association branch (:391, :428-429)
             w = self.estimate_camera_motion(img, metainfo) if (n > 0 and not self.empty) else None
@@ -316,6 +334,7 @@ class OCSORTTracker_Disparity:
         out = eng.track_step(eng.frame_ids, eng.det_inflated, eng.det_scores, eng.det_labels, eng.det_scales,
                              eng.det_depth, eng.det_counts, warp=warp)
         m = int(out['counts'][0])
+        self._n_live = int(eng.live_counts()[0])
         status = int(eng.status()[0])
         if status:
             raise _lib.StereoTrackError(f'tracker capacity exceeded (status bits {status}); raise max_tracks / max_dets')
@@ -352,15 +371,25 @@ class OCSORTTracker(OCSORTTracker_Disparity):
         return res
 
 
-@MODELS.register_module(force=True)
-class OCSORT:
+class OCSORT(_ShellBase):
     """RGB-only model shell (mmtrack/models/mot/ocsort.py:13, predict :71-114): detector ->
-    tracker, no depth stage."""
+    tracker, no depth stage.  A ``BaseMultiObjectTracker`` like the reference class
+    (mot/ocsort.py:27-42): ``data_preprocessor`` and ``init_cfg`` go to the base model.
+    NOT registered on import: see ``register_model_shells``."""
 
     def __init__(self, detector=None, tracker=None, motion=None, data_preprocessor=None, init_cfg=None):
-        self.detector = MODELS.build(detector) if isinstance(detector, dict) else detector
-        self.motion = TASK_UTILS.build(motion) if isinstance(motion, dict) else motion
-        self.tracker = MODELS.build(tracker) if isinstance(tracker, dict) else tracker
+        super().__init__(data_preprocessor, init_cfg)
+        if detector is not None:
+            self.detector = MODELS.build(detector) if isinstance(detector, dict) else detector
+        if motion is not None:
+            self.motion = TASK_UTILS.build(motion) if isinstance(motion, dict) else motion
+        if tracker is not None:
+            self.tracker = MODELS.build(tracker) if isinstance(tracker, dict) else tracker
+
+    def loss(self, inputs, data_samples, **kwargs):                      # mot/ocsort.py:44-67
+        img = inputs['img']
+        assert img.size(1) == 1
+        return self.detector.loss(torch.squeeze(img, dim=1), data_samples, **kwargs)
 
     def predict(self, inputs, data_samples, **kwargs):
         img = inputs['img']
@@ -377,16 +406,18 @@ class OCSORT:
         return [sample]
 
 
-@MODELS.register_module(force=True)
-class OCSORT_Disparity:
+class OCSORT_Disparity(_ShellBase):
     """Model shell of the hot path: detector -> depth -> per-box depth/scale ->
     tracker -> deflate -> output depth (ocsort_disparity.py:51-111).  ``detector``
     may be any object with ``predict(data, data_samples)`` returning a list whose
     first element has ``pred_instances`` (the reference PyTorch detector stays
-    the detector; it is not part of this path)."""
+    the detector; it is not part of this path).  A ``BaseMultiObjectTracker`` like the
+    reference class (ocsort_disparity.py:15-40 via mot/ocsort.py:27-42).  NOT registered on
+    import: see ``register_model_shells``."""
 
     def __init__(self, detector=None, tracker=None, motion=None, data_preprocessor=None, init_cfg=None,
                  baseline: float = 0.25, focal_length: int = 640, depth_reducer: str = 'window'):
+        super().__init__(data_preprocessor, init_cfg)
         # depth_reducer: 'window' = extract_depth (:136-175); 'truncated_mean' | 'mean' | 'median' |
         # 'center' = what decorating extract_depth with depth_extraction_comparison.py's
         # *_decorator does in the reference's ablation runs
@@ -397,12 +428,22 @@ class OCSORT_Disparity:
         self.motion = TASK_UTILS.build(motion) if isinstance(motion, dict) else motion
         self.tracker = MODELS.build(tracker) if isinstance(tracker, dict) else tracker
         self.baseline, self.focal_length = baseline, focal_length
-        if self.tracker is not None:
+        if self.tracker is not None and hasattr(self.tracker, '_engine'):
             self.tracker._engine.cfg.baseline = float(baseline)
             self.tracker._engine.cfg.focal_length = float(focal_length)
 
+    def loss(self, inputs, data_samples, **kwargs):                      # ocsort_disparity.py:42-48
+        raise NotImplementedError('training the detector is outside this path; use the reference OCSORT_Disparity')
+
     def disp2depth(self, disp):
         return self.tracker._engine.disp_to_depth(disp.contiguous().float())
+
+    @staticmethod
+    def _depth_list(t):
+        """extract_depth returns a Python list of numpy float32 means and the int -1 for boxes
+        without a valid depth (ocsort_disparity.py:148,:168); results.csv prints them as such."""
+        import numpy as np
+        return [(-1 if v == -1 else np.float32(v)) for v in t.cpu().numpy()]
 
     def _check_center(self, eng):
         # depth_extraction_comparison.py:141 ``depth[cy, cx]``: NumPy raises when the box centre is off the map
@@ -422,12 +463,12 @@ class OCSORT_Disparity:
         infl = torch.zeros_like(b)
         d, sc, _ = eng.box_depth(depth, b, cnt, inflated_out=infl, mode=self.depth_reducer)
         self._check_center(eng)
-        values = dict(d_values=d[0, :n].tolist())
+        values = dict(d_values=self._depth_list(d[0, :n]))
         if gt_depth is not None:
             gd, _, _ = eng.box_depth(gt_depth.reshape(1, gt_depth.shape[-2], gt_depth.shape[-1]).contiguous().float(), b, cnt,
                                      mode=self.depth_reducer)
             self._check_center(eng)
-            values['gt_d_values'] = gd[0, :n].tolist()
+            values['gt_d_values'] = self._depth_list(gd[0, :n])
         pred_instances['bboxes'] = infl[0, :n].to(boxes)
         pred_instances['scales'] = sc[0, :n].to(boxes)
         pred_instances['depth'] = d[0, :n].to(boxes)
@@ -462,3 +503,13 @@ class OCSORT_Disparity:
         sample.pred_det_instances = det_results[0].pred_instances.clone()
         sample.pred_track_instances = tracks
         return [sample]
+
+
+def register_model_shells(force=True):
+    """Explicit opt-in: register the model shells ``OCSORT`` / ``OCSORT_Disparity`` under the
+    reference's type names (importing ``stereotracking_b200.mmtrack_shell`` calls this).  Importing
+    this module alone registers only the trackers and ``KalmanFilter`` - the tracker-only drop-in
+    under the reference's own model shell."""
+    MODELS.register_module(name='OCSORT', force=force, module=OCSORT)
+    MODELS.register_module(name='OCSORT_Disparity', force=force, module=OCSORT_Disparity)
+    return OCSORT, OCSORT_Disparity

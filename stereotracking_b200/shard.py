@@ -104,24 +104,34 @@ def gather_tracks(rows, dst=0, group=None):
 
 def write_mot_txt(rows, sequence, path, depth_thr=None):
     """MOTChallenge txt of one sequence as MOTDroneMetrics writes it
-    (mot_drone_metrics.py:195-207 depth-range filter ``depth_thr >= depth > 0``,
-    :231-236 line format; frame ids are 1-based)."""
+    (mot_drone_metrics.py:195-207 depth-range filter ``depth_thr >= depth > 0`` and width / height
+    as float32 differences of the float32 box, :231-236 line format; frame ids are 1-based).
+    Pinned by tests/golden/ref_writers.npz."""
     sel = rows[rows[:, 0] == sequence]
     if depth_thr is not None:
         with np.errstate(invalid='ignore'):
             sel = sel[(sel[:, 8] > 0) & (sel[:, 8] <= depth_thr)]
+    box = sel[:, 3:7].astype(np.float32)
+    w, h = box[:, 2] - box[:, 0], box[:, 3] - box[:, 1]            # float32, as the reference's tensors
     with open(path, 'wt') as f:
-        for r in sel:
+        for k, r in enumerate(sel):
             f.write('%d,%d,%.3f,%.3f,%.3f,%.3f,%.3f,-1,-1,-1\n' %
-                    (r[1] + 1, r[2], r[3], r[4], r[5] - r[3], r[6] - r[4], r[7]))
+                    (r[1] + 1, r[2], box[k, 0], box[k, 1], w[k], h[k], np.float32(r[7])))
     return len(sel)
+
+
+def _csv_depth(v):
+    """extract_depth's list entries (ocsort_disparity.py:148,:168): the int -1 for a box without a
+    valid depth, else a numpy float32."""
+    return -1 if v == -1 else np.float32(v)
 
 
 def write_results_csv(rows, sequence, path, gt_depth=None):
     """``results.csv`` of one sequence as the reference's ``@save_prediction_results``
     decorator appends it per frame (mmtrack/utils/collect_results.py:25-37): header
     frame,id,label,tl_x,tl_y,br_x,br_y,depth,gt_depth,score; ``gt_depth`` falls back to
-    the predicted depth as in ocsort_disparity.py:103-104."""
+    the predicted depth as in ocsort_disparity.py:103-104.  Pinned byte for byte by
+    tests/golden/ref_writers.npz (the reference's own decorator run on the same rows)."""
     import csv
     sel = rows[rows[:, 0] == sequence]
     with open(path, 'w', newline='') as f:
@@ -130,5 +140,5 @@ def write_results_csv(rows, sequence, path, gt_depth=None):
         for k, r in enumerate(sel):
             gd = r[8] if gt_depth is None else gt_depth[k]
             w.writerow([int(r[1]), int(r[2]), int(r[9]), np.float32(r[3]), np.float32(r[4]), np.float32(r[5]),
-                        np.float32(r[6]), np.float32(r[8]), np.float32(gd), np.float32(r[7])])
+                        np.float32(r[6]), _csv_depth(r[8]), _csv_depth(gd), np.float32(r[7])])
     return len(sel)

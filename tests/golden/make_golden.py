@@ -12,6 +12,9 @@ Outputs (small .npz files next to this script):
   ref_boxdepth_ablation.npz  the four ablation reducers of depth_extraction_comparison.py
   ref_frontend.npz    pad + HWC->CHW + TrackDataPreprocessor_Disparity_V1 lines + stack_batch on u8 images
   ref_memo_occlusion.npz  BaseTracker.memo / get while replaying ref_track_occlusion.npz
+  ref_kf_nsa.npz      KalmanFilter(use_nsa=True).project / update with bbox scores
+  ref_writers.npz     results.csv text written by the reference's own save_prediction_results
+                      decorator, and the MOT txt lines of MOTDroneMetrics, on rows of ref_track_basic.npz
   ref_track_<name>.npz  OCSORT_Disparity.predict() over whole sequences:
                       inputs (raw disparity, detections) and the reference's
                       pred_track_instances + tracker state per frame
@@ -381,6 +384,93 @@ def make_memo(ns):
     print('memo:', {k: v.shape for k, v in pack.items() if k.startswith('memo_ids')})
 
 
+def make_kf_nsa(ns):
+    """KalmanFilter(use_nsa=True) of the unmodified reference (kalman_filter.py:38,:144-145):
+    project and update with bbox scores on states of ref_kf.npz."""
+    g = np.load(os.path.join(OUT, 'ref_kf.npz'))
+    rng = np.random.default_rng(17)
+    kf = ns.KalmanFilterRaw(use_nsa=True)
+    idx = np.arange(1, len(g['op']), 4)
+    score = rng.uniform(0.05, 0.99, len(idx))
+    score[0] = 0.0
+    pm, pc, zs, um, uc = [], [], [], [], []
+    for i, sc in zip(idx, score):
+        m, c = g['mean'][i], g['cov'][i]
+        a, b = kf.project(m, c, float(sc))
+        pm.append(a); pc.append(b)
+        z = (m[:4] + rng.normal(0, [2, 2, 0.01, 1])).astype(np.float32)
+        m2, c2 = kf.update(m, c, z, float(sc))
+        zs.append(z); um.append(m2); uc.append(c2)
+    np.savez_compressed(os.path.join(OUT, 'ref_kf_nsa.npz'), idx=idx, score=score, pmean=np.stack(pm), pcov=np.stack(pc),
+                        z=np.stack(zs), umean=np.stack(um), ucov=np.stack(uc))
+    print('kf nsa:', len(idx), 'states')
+
+
+def make_writers(ns):
+    """The two output writers on rows of ref_track_basic.npz.
+    results.csv: the reference's own decorator (mmtrack/utils/collect_results.py:1-41, loaded from
+    its file; it needs only csv + os) around a predict function that returns the canned frames.
+    MOT txt: the statements of MOTDroneMetrics.process / _save_one_video_gts_preds
+    (mmtrack/evaluation/metrics/mot_drone_metrics.py:195-207,:231-236; the module itself needs
+    mmengine + trackeval, so its lines are executed here on the same torch tensors)."""
+    import importlib.util
+    import tempfile
+    spec = importlib.util.spec_from_file_location('ref_collect_results',
+                                                  os.path.join(ref_shims.REF, 'mmtrack/utils/collect_results.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(OUT, 'ref_track_basic.npz'))
+    frames = [2, 3, 10, 20, 21]
+    canned = {}
+    for f in frames:
+        m = int(g['out_count'][f])
+        depth = [(-1 if v == -1 else np.float32(v)) for v in g['out_depth'][f, :m]]     # extract_depth's list (:148,:168)
+        inst = ns.InstanceData(bboxes=torch.from_numpy(g['out_bboxes'][f, :m].copy()),
+                               instances_id=torch.from_numpy(g['out_ids'][f, :m].copy()),
+                               labels=torch.zeros(m, dtype=torch.int64),
+                               scores=torch.from_numpy(g['out_scores'][f, :m].copy()), depth=depth, gt_depth=depth)
+        canned[f] = inst
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, 'results.csv')
+
+        class Sample:
+            pass
+
+        def predict(f):
+            s = Sample()
+            s.pred_track_instances, s.frame_id = canned[f], f
+            return [s]
+
+        wrapped = mod.save_prediction_results(path)(predict)
+        for f in frames:
+            wrapped(f)
+        csv_text = open(path, 'rb').read()
+    # MOT txt, depth_thr = 50 (ignore_depth False): mot_drone_metrics.py:195-207 then :231-236
+    depth_thr, pred_tracks = 50, []
+    for f in frames:
+        pred_instances = canned[f]
+        pred_tracks.extend([
+            np.array([
+                f + 1, pred_instances['instances_id'][i].cpu(),
+                pred_instances['bboxes'][i][0].cpu(),
+                pred_instances['bboxes'][i][1].cpu(),
+                (pred_instances['bboxes'][i][2] -
+                 pred_instances['bboxes'][i][0]).cpu(),
+                (pred_instances['bboxes'][i][3] -
+                 pred_instances['bboxes'][i][1]).cpu(),
+                pred_instances['scores'][i].cpu()
+            ]) for i in range(len(pred_instances['instances_id'])) if
+            (depth_thr >= pred_instances['depth'][i] > 0)
+        ])
+    pred_tracks = np.array(pred_tracks)
+    mot_text = ''.join('%d,%d,%.3f,%.3f,%.3f,%.3f,%.3f,-1,-1,-1\n' % (
+        t[0], t[1], t[2], t[3], t[4], t[5], t[6]) for t in pred_tracks).encode()
+    np.savez_compressed(os.path.join(OUT, 'ref_writers.npz'), frames=np.asarray(frames),
+                        csv_text=np.frombuffer(csv_text, np.uint8), mot_text=np.frombuffer(mot_text, np.uint8),
+                        depth_thr=np.asarray(depth_thr))
+    print('writers:', len(csv_text), 'bytes of csv,', len(mot_text), 'bytes of MOT txt')
+
+
 def make_sequences(ns, only=None):
     scen = {
         'basic': dict(cfg=SceneConfig(160, 224, 5, 8, n_clutter=0), F=36, seed=3, miss=0.05, clutter=3, blackout=()),
@@ -428,6 +518,10 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['kf_gating']:
         make_kf_gating(ns)
         sys.exit(0)
+    if sys.argv[1:] == ['round2']:               # fixtures added in round 2 (read ref_kf.npz / ref_track_basic.npz)
+        make_kf_nsa(ns)
+        make_writers(ns)
+        sys.exit(0)
     make_kf(ns)
     make_kf_gating(ns)
     make_boxdepth(ns)
@@ -435,4 +529,6 @@ if __name__ == '__main__':
     make_frontend(ns)
     make_sequences(ns)
     make_memo(ns)
+    make_kf_nsa(ns)
+    make_writers(ns)
     print('golden fixtures written to', OUT)

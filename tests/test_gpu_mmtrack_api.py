@@ -177,6 +177,72 @@ def test_kalman_filter_project_gating_track_match_reference_fixture(api):
     assert not np.isnan(g['track_costs']).all() and np.isnan(g['track_costs']).any()
 
 
+def test_kalman_filter_use_nsa_matches_reference_fixture(api):
+    """KalmanFilter(use_nsa=True) (kalman_filter.py:38,:144-145): project / update with bbox scores
+    against the unmodified reference; with score 0 (what the OC-SORT trackers pass) it is the
+    plain filter."""
+    g = np.load(os.path.join(GOLDEN, 'ref_kf_nsa.npz'))
+    k = np.load(os.path.join(GOLDEN, 'ref_kf.npz'))
+    kf = api['compat'].TASK_UTILS.build(dict(type='KalmanFilter', use_nsa=True))
+    plain = api['compat'].TASK_UTILS.build(dict(type='KalmanFilter'))
+    assert kf.use_nsa and not plain.use_nsa
+    for n, i in enumerate(g['idx']):
+        sc = float(g['score'][n])
+        pm, pc = kf.project(k['mean'][i], k['cov'][i], sc)
+        np.testing.assert_array_equal(pm, g['pmean'][n])
+        np.testing.assert_allclose(pc, g['pcov'][n], rtol=1e-15, atol=0)
+        m, c = kf.update(k['mean'][i], k['cov'][i], g['z'][n], sc)
+        np.testing.assert_allclose(m, g['umean'][n], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(c, g['ucov'][n], rtol=1e-9, atol=1e-12)
+    m0, c0 = kf.update(k['mean'][3], k['cov'][3], g['z'][0])                 # bbox_score defaults to 0
+    m1, c1 = plain.update(k['mean'][3], k['cov'][3], g['z'][0])
+    np.testing.assert_array_equal(m0, m1)
+    np.testing.assert_array_equal(c0, c1)
+
+
+def test_cmc_state_resets_with_every_new_video(api):
+    """frame_id == 0 resets tracks AND camera-motion state before anything else
+    (ocsort_tracker_disparity.py:385-391): the second video on a tracker instance must run exactly
+    like the same video on a fresh instance - in particular no warp is estimated on its frames 0
+    and 1 (the estimator first needs a previous image from an association-branch frame)."""
+    torch, compat = api['torch'], api['compat']
+    g = np.load(os.path.join(GOLDEN, 'ref_track_cmc.npz'))
+    F = 12
+
+    def run(tracker, calls):
+        # a deterministic stand-in for the OpenCV estimator body; the bookkeeping of
+        # estimate_camera_motion (prev_cmc_img, :87-97) stays the tracker's own
+        def fake(img, prev, meta, **kw):
+            calls.append(meta['frame_id'])
+            return np.asarray([[1.01, 0.002, 1.5], [-0.002, 1.01, -0.8]], np.float32)
+        api['api']._mesh_affine, keep = fake, api['api']._mesh_affine
+        try:
+            outs = []
+            for f in range(F):
+                n = int(g['det_count'][f])
+                r = tracker._track(torch.full((1, 3, 8, 8), float(f)), dict(frame_id=f, img_shape=(8, 8)),
+                                   torch.from_numpy(g['det_boxes'][f, :n].copy()).cuda(),
+                                   torch.from_numpy(g['det_scores'][f, :n].copy()).cuda(),
+                                   torch.zeros(n, dtype=torch.int64).cuda(), torch.ones(n).cuda(), torch.ones(n).cuda())
+                outs.append((r.instances_id.cpu().numpy(), r.bboxes.cpu().numpy()))
+            return outs, tracker._engine.export_state(0)
+        finally:
+            api['api']._mesh_affine = keep
+
+    cfg = dict(TRACKER_CFG, cmc=dict(method='glme_affine'), max_dets=64, max_tracks=128)
+    reused, fresh = compat.MODELS.build(dict(cfg)), compat.MODELS.build(dict(cfg))
+    run(reused, [])                                                   # video A
+    calls_b, calls_f = [], []
+    out_b, st_b = run(reused, calls_b)                                # video B on the same instance
+    out_f, st_f = run(fresh, calls_f)                                 # video B on a fresh instance
+    assert calls_b == calls_f and 0 not in calls_b and 1 not in calls_b and 2 in calls_b
+    for (ia, ba), (ib, bb) in zip(out_b, out_f):
+        np.testing.assert_array_equal(ia, ib)
+        np.testing.assert_array_equal(ba, bb)
+    np.testing.assert_array_equal(st_b['mean'], st_f['mean'])
+    np.testing.assert_array_equal(st_b['cov'], st_f['cov'])
+
+
 def test_constructor_errors_follow_the_reference(api):
     T = api['api'].OCSORTTracker_Disparity
     with pytest.raises(ValueError):
@@ -184,8 +250,7 @@ def test_constructor_errors_follow_the_reference(api):
     assert T(cmc=dict(method='glme_affine')).with_cmc and not T().with_cmc
     with pytest.raises(AssertionError):
         T(momentums=[0.1])                                         # base_tracker.py:26-27
-    with pytest.raises(NotImplementedError):
-        api['api'].KalmanFilter(use_nsa=True)
+    assert api['api'].KalmanFilter(use_nsa=True).use_nsa            # kalman_filter.py:38
     with pytest.raises(ValueError):
         api['api'].OCSORT_Disparity(depth_reducer='mode')           # not one of depth_extraction_comparison.py's
 

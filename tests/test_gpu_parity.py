@@ -204,6 +204,100 @@ def test_k3_large_boxes_use_global_path(mods):
     np.testing.assert_allclose(sc[0].cpu().numpy(), rs, rtol=2e-6)
 
 
+def _both_k3(eng, raw, boxes, counts, with_prev=None):
+    """(map path, raw path) outputs of K3 for the same frames and boxes."""
+    depth, _, _ = eng.disp2depth(raw)
+    Hp, Wp = depth.shape[1:]
+    i1, i2 = torch.zeros_like(boxes), torch.zeros_like(boxes)
+    d1, s1, _ = eng.box_depth(depth, boxes, counts, inflated_out=i1)
+    d2, s2, _ = eng.box_depth_raw(raw, (Hp, Wp), boxes, counts, inflated_out=i2)
+    torch.cuda.synchronize()
+    return (d1, s1, i1), (d2, s2, i2), depth
+
+
+def _same_bits(a, b, n):
+    for x, y in zip(a, b):
+        x, y = x[0, :n].cpu().numpy(), y[0, :n].cpu().numpy()
+        np.testing.assert_array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
+def test_k3_raw_equals_map_path_on_reference_fixture(mods):
+    """st_box_depth_raw (codes, histograms, no depth map) against the reference's own extract_depth
+    values and bit for bit against the map path, on the 79 edge-case boxes of ref_boxdepth.npz."""
+    g = np.load(os.path.join(GOLDEN, 'ref_boxdepth.npz'))
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    n = len(g['boxes'])
+    boxes = torch.zeros(1, n + 3, 4, device='cuda')
+    boxes[0, :n] = cuda(g['boxes'])
+    counts = torch.tensor([n], dtype=torch.int32, device='cuda')
+    a, b, _ = _both_k3(eng, cuda(g['raw'][None]), boxes, counts)
+    _same_bits(a, b, n)
+    d = b[0][0, :n].cpu().numpy()
+    ok = ~np.isnan(g['d'])
+    np.testing.assert_array_equal(np.isnan(d), ~ok)
+    np.testing.assert_allclose(d[ok], g['d'][ok], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize('W,hi_code', [(1024, 3000), (1022, 3000), (1024, 20000)])
+def test_k3_raw_large_boxes_clusters_and_overflow(mods, W, hi_code):
+    """Boxes of 600 .. 200 000 pixels (the cluster histogram kernel), reaching into the pad rows /
+    columns, wider than 800 px, on a width that rules out 64-bit loads, and with codes >= 4096
+    (no histogram bin: general path) - bit-identical to the map path and equal to the oracle."""
+    rng = np.random.default_rng(8)
+    H = 250
+    raw = rng.integers(10, hi_code, (2, H, W)).astype(np.uint16)
+    raw[0, 40:200, 100:600] = 777                      # one object: a single code over 80 000 pixels
+    raw[rng.random(raw.shape) < 0.3] = 65535
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=2))
+    b = np.asarray([[3.2, 1.1, 790.5, 250.7], [100, 10, 905, 200], [0, 0, 120.5, 90.2],
+                    [500.5, 3.3, 1023.9, 255.9], [10, 10, 400, 30], [95.5, 35.2, 610.1, 210.9],
+                    [300.7, 100.2, 330.1, 121.0], [1000.2, 200.5, 1090.0, 300.0], [0, 240, 700, 256]], np.float32)
+    boxes = cuda(np.stack([b, b[::-1]]))
+    counts = torch.tensor([len(b), len(b) - 2], dtype=torch.int32, device='cuda')
+    a, r, depth = _both_k3(eng, cuda(raw), boxes, counts)
+    for s in range(2):
+        n = int(counts[s])
+        for x, y in zip(a, r):
+            np.testing.assert_array_equal(x[s, :n].cpu().numpy().view(np.uint32), y[s, :n].cpu().numpy().view(np.uint32))
+        rd, rs = mods.boxdepth.extract_depth(depth[s].cpu().numpy(), boxes[s, :n].cpu().numpy())
+        np.testing.assert_allclose(r[0][s, :n].cpu().numpy(), rd, rtol=1e-6, equal_nan=True)
+        np.testing.assert_allclose(r[1][s, :n].cpu().numpy(), rs, rtol=2e-6, equal_nan=True)
+
+
+def test_k3_raw_random_boxes_equal_map_path(mods):
+    """2 000 random boxes of all sizes over synthetic C2 frames (background ramp, objects, 5 %
+    invalid blocks): raw path == map path bit for bit, including the reuse form of the second call."""
+    cfg = mods.CONFIGS['C2']
+    fr = mods.SyntheticStereo(cfg, 2, 1, seed=77).frames(0, 1)
+    raw = fr['raw'][0].cuda().contiguous()
+    rng = np.random.default_rng(5)
+    n = 1000
+    cx, cy = rng.uniform(-20, 1300, (2, n)), rng.uniform(-20, 760, (2, n))
+    side = np.exp(rng.uniform(np.log(3), np.log(400), (2, n)))
+    asp = rng.uniform(0.5, 2.0, (2, n))
+    b = np.stack([cx - side * asp / 2, cy - side / 2, cx + side * asp / 2, cy + side / 2], -1).astype(np.float32)
+    b[:, :50] = np.floor(b[:, :50])                    # integer corners
+    boxes = cuda(b)
+    counts = torch.tensor([n, n - 7], dtype=torch.int32, device='cuda')
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=2, max_dets=n))
+    a, r, depth = _both_k3(eng, raw, boxes, counts)
+    for s in range(2):
+        m = int(counts[s])
+        for x, y in zip(a, r):
+            np.testing.assert_array_equal(x[s, :m].cpu().numpy().view(np.uint32), y[s, :m].cpu().numpy().view(np.uint32))
+    # second call of a frame: rows that came from an earlier row with the same truncated corners reuse it
+    prev_index = torch.arange(n, dtype=torch.int32, device='cuda')[None].repeat(2, 1).contiguous()
+    prev_index[:, ::3] = -1
+    jitter = boxes + torch.as_tensor(rng.uniform(-0.3, 0.3, b.shape).astype(np.float32)).cuda()
+    d3, s3, _ = eng.box_depth_raw(raw, depth.shape[1:], jitter, counts, prev_boxes=boxes, prev_index=prev_index,
+                                  prev_d=r[0])
+    d4, s4, _ = eng.box_depth(depth, jitter, counts)
+    for s in range(2):
+        m = int(counts[s])
+        np.testing.assert_array_equal(d3[s, :m].cpu().numpy().view(np.uint32), d4[s, :m].cpu().numpy().view(np.uint32))
+        np.testing.assert_array_equal(s3[s, :m].cpu().numpy().view(np.uint32), s4[s, :m].cpu().numpy().view(np.uint32))
+
+
 @pytest.mark.parametrize('mode', ['truncated_mean', 'mean', 'median', 'center'])
 def test_k3_ablation_reducers_match_reference_fixture(mods, mode):
     """depth_extraction_comparison.py's reducers: the golden values of the unmodified reference
@@ -517,6 +611,38 @@ def test_frame_pipeline_equals_sequential_steps(mods):
     done[(F - 1) % 2].synchronize()
     check(pipe2.slots[(F - 1) % 2].results(), F - 1)
     assert eng.status().max() == 0 and eng2.status().max() == 0
+    # (c) K3 gathering from the raw frame, no depth map written (st_frame_io.depth_from_raw)
+    eng3 = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S))
+    pipe3 = FramePipeline(eng3, (S, cfg.height, cfg.width), levels, depth=F, depth_source='raw')
+    assert all(b.depth_map is None for b in pipe3.slots[1:])
+    for f in range(F):
+        pipe3.submit(fid[f], raw[f], [c[f] for c in heads[0]], [c[f] for c in heads[1]], [c[f] for c in heads[2]])
+    pipe3.join()
+    torch.cuda.synchronize()
+    for f in range(F):
+        check(pipe3.slots[f].results(), f)
+    assert eng3.status().max() == 0
+    # (d) frames replayed as CUDA graphs (st_pipeline_use_graphs): a ring of 3 slots, inputs at a
+    # new address every frame (the per-slot device input table follows them), both depth sources
+    for source in ('map', 'raw'):
+        eng4 = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S))
+        pipe4 = FramePipeline(eng4, (S, cfg.height, cfg.width), levels, depth=3, depth_source=source)
+        pipe4.use_graphs(True)
+        done4 = [torch.cuda.Event() for _ in range(3)]
+        for e in done4:
+            e.record()
+        for f in range(F):
+            if f >= 3:
+                done4[f % 3].synchronize()
+                check(pipe4.slots[f % 3].results(), f - 3)
+            pipe4.submit(fid[f], raw[f], [c[f] for c in heads[0]], [c[f] for c in heads[1]], [c[f] for c in heads[2]],
+                         done_event=done4[f % 3])
+        for f in range(F - 3, F):
+            done4[f % 3].synchronize()
+            check(pipe4.slots[f % 3].results(), f)
+        st4 = pipe4.stats()
+        assert st4 == dict(graph_frames=F - 3, captures=3), st4       # first use of a slot runs uncaptured
+        assert eng4.status().max() == 0
 
 
 def test_capacity_overflow_raises_status_bits_not_silent_truncation(mods):

@@ -129,3 +129,38 @@ def test_tracker_sequence_matches_reference(name):
         lost_recovered += int((~g['out_st_tracked'][f, :k]).sum())
     if name != 'basic':
         assert lost_recovered > 0      # the scenario exercised lost tracks
+
+
+def test_writers_match_the_reference_decorator_and_metric_lines(tmp_path):
+    """shard.write_results_csv / write_mot_txt on the rows of ref_track_basic.npz against the text
+    the reference's own save_prediction_results decorator (collect_results.py:1-41) and the
+    MOTDroneMetrics statements (mot_drone_metrics.py:195-207,:231-236) produced for them."""
+    from stereotracking_b200 import shard
+    w = np.load(os.path.join(GOLDEN, 'ref_writers.npz'))
+    g = np.load(os.path.join(GOLDEN, 'ref_track_basic.npz'))
+    rows = []
+    for f in w['frames']:
+        m = int(g['out_count'][f])
+        res = [dict(instances_id=g['out_ids'][f, :m], bboxes=g['out_bboxes'][f, :m], scores=g['out_scores'][f, :m],
+                    depth=g['out_depth'][f, :m], labels=np.zeros(m, np.int64))]
+        rows.append(shard.tracks_to_rows(res, int(f), first_sequence=3))
+    rows = np.concatenate(rows)
+    shard.write_results_csv(rows, 3, str(tmp_path / 'r.csv'))
+    assert open(tmp_path / 'r.csv', 'rb').read() == bytes(w['csv_text'])
+    shard.write_mot_txt(rows, 3, str(tmp_path / 'r.txt'), depth_thr=int(w['depth_thr']))
+    assert open(tmp_path / 'r.txt', 'rb').read() == bytes(w['mot_text'])
+
+
+def test_kalman_nsa_matches_reference():
+    """KalmanFilter(use_nsa=True).project / update with bbox scores (kalman_filter.py:144-145)."""
+    from oracle import kalman
+    g = np.load(os.path.join(GOLDEN, 'ref_kf_nsa.npz'))
+    k = np.load(os.path.join(GOLDEN, 'ref_kf.npz'))
+    for n, i in enumerate(g['idx']):
+        sc = float(g['score'][n])
+        pm, pc = kalman.project(k['mean'][i], k['cov'][i], sc, use_nsa=True)
+        np.testing.assert_array_equal(pm, g['pmean'][n])
+        np.testing.assert_allclose(pc, g['pcov'][n], rtol=1e-15, atol=0)
+        m, c = kalman.update(k['mean'][i], k['cov'][i], g['z'][n], sc, use_nsa=True)
+        np.testing.assert_allclose(m, g['umean'][n], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(c, g['ucov'][n], rtol=1e-10, atol=1e-13)

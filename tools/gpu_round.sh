@@ -15,13 +15,16 @@ mkdir -p gpurun_out
 BENCH="python bench.py --steps 4 --warmup 3 --no-cpu-baseline"
 case "${1:-check}" in
   check)
-    timeout 200 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests.log 2>&1; tail -3 gpurun_out/gpu_tests.log
-    timeout 120 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
+    timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/gpu_tests.log 2>&1; tail -15 gpurun_out/gpu_tests.log
+    timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -5 gpurun_out/bench.err
     python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
 print('frames/s %.0f  ms/step %.4f  e2e %.0f  K1 frac %.3f  launches %d' % (
     d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['gpu_launches']))
+print('modes:', {k: (round(v['value']), round(v['ms_per_step'], 4), round(v['host_issue_ms_per_step'], 4)) for k, v in d['modes'].items() if isinstance(v, dict)})
+print('parity:', d.get('parity'))
+print('kernels:', {m: {k: round(v['ms'], 4) for k, v in t.items()} for m, t in d['kernels'].items()})
 print('K4 phases (slowest sequence):', d.get('k4_phase_cycles_slowest_sequence'))
 print('assignments:', d.get('assignments'))
 PY
@@ -42,7 +45,8 @@ PY
   micro)
     timeout 60 python tools/bench_k1.py > gpurun_out/k1_micro.json 2> gpurun_out/k1_micro.err; tail -2 gpurun_out/k1_micro.json
     timeout 60 python tools/bench_k1b.py > gpurun_out/k1b_micro.json 2> gpurun_out/k1b_micro.err; cat gpurun_out/k1b_micro.json
-    timeout 60 python tools/pipeline_timeline.py > gpurun_out/pipeline_timeline.txt 2>&1; tail -20 gpurun_out/pipeline_timeline.txt
+    timeout 60 python tools/pipeline_timeline.py 12 5 map > gpurun_out/pipeline_timeline_map.txt 2>&1; tail -8 gpurun_out/pipeline_timeline_map.txt
+    timeout 60 python tools/pipeline_timeline.py 12 5 raw > gpurun_out/pipeline_timeline_raw.txt 2>&1; tail -8 gpurun_out/pipeline_timeline_raw.txt
     ;;
   *) echo "unknown sub-command $1"; exit 2 ;;
 esac
