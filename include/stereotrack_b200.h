@@ -164,7 +164,7 @@ int st_decode_nms(st_handle *h, const float *const *cls_host, const float *const
  * (may be NULL). */
 int st_box_depth(const float *depth, int S, int Hp, int Wp, const float *boxes,
                  const int32_t *counts, int cap, float *d, float *scale, float *inflated,
-                 int32_t *workspace /* [4 + 6*S*cap] i32 scratch (worklists of large boxes) */,
+                 int32_t *workspace /* [8 + 6*S*cap] i32 scratch (worklists of large boxes) */,
                  void *stream);
 /* Same, for the second call of a frame (ocsort_disparity.py:100-101, on the deflated
  * track boxes): row r of `boxes` came from row prev_index[r] of prev_boxes (-1 = none),
@@ -252,7 +252,7 @@ typedef struct st_frame_io {
     int32_t *det_counts; float *det_depth; float *det_scales; float *det_inflated;
     float *trk_boxes; float *trk_depth; float *out_scale2;
     int32_t *out_src;                  /* [S,cap] detection row of every track row */
-    int32_t *k3_workspace;             /* [4 + 6*S*cap] i32 scratch of st_box_depth */
+    int32_t *k3_workspace;             /* [8 + 6*S*cap] i32 scratch of st_box_depth */
     /* outputs = pred_track_instances fields */
     float *out_boxes; float *out_scores; int64_t *out_labels; float *out_scales; float *out_depth;
     int64_t *out_ids; int32_t *out_counts;

@@ -229,7 +229,7 @@ k3_box_depth(const float *__restrict__ depth, int Hp, int Wp, const float *__res
     __shared__ float staged_all[kWarps][kStage];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = worklist[3];
-    const int32_t *list = worklist + 4 + 4 * list_cap;
+    const int32_t *list = worklist + 8 + 4 * list_cap;
     for (int idx = blockIdx.x * kWarps + warp; idx < n; idx += gridDim.x * kWarps) {
         k3_box_one(depth, Hp, Wp, boxes, list[2 * idx], list[2 * idx + 1], cap, d_out, scale_out, inflated,
                    staged_all[warp], lane);
@@ -280,7 +280,7 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
         __syncthreads();
         const int item = next_item;
         if (item >= n_work) break;
-        const int s = worklist[4 + 2 * item], bi = worklist[5 + 2 * item];
+        const int s = worklist[8 + 2 * item], bi = worklist[9 + 2 * item];
         const long long o = (long long)s * cap + bi;
         const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
         const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
@@ -338,8 +338,8 @@ k3_box_depth_table(const float *__restrict__ depth, int Hp, int Wp, const float 
             if (overflow) {
                 if (threadIdx.x == 0) {
                     const int slot = atomicAdd(&worklist[1], 1);
-                    worklist[4 + 2 * list_cap + 2 * slot] = s;
-                    worklist[5 + 2 * list_cap + 2 * slot] = bi;
+                    worklist[8 + 2 * list_cap + 2 * slot] = s;
+                    worklist[9 + 2 * list_cap + 2 * slot] = bi;
                 }
                 continue;                                // block-uniform
             }
@@ -571,7 +571,7 @@ extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, con
     if (prev_index && (!prev_boxes || !prev_d)) return ST_ERR_INVALID_ARG;
     if (S == 0) return ST_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 4, st));
+    ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 8, st));
     const int list_cap = S * cap;
     // once per device: shared-memory opt-ins, resident grid of the warp kernel
     const K3Dev *dv = g_k3dev.get([](K3Dev &v) {
@@ -597,7 +597,7 @@ extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, con
     if (st_ctx_aux(st, &aux, &ev_fork, &ev_join) != ST_OK) return ST_ERR_CUDA;
     const long long slots = (long long)S * cap;
     k3_classify<<<(int)((slots + 255) / 256), 256, 0, st>>>(S, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace,
-                                                           list_cap, prev_boxes, prev_index, prev_d, (unsigned)kSmallPix);
+                                                           list_cap, prev_boxes, prev_index, prev_d, (unsigned)kSmallPix, 0u);
     ST_CUDA_OK(cudaEventRecord(ev_fork, st));
     ST_CUDA_OK(cudaStreamWaitEvent(aux, ev_fork, 0));
     long long tgrid = (long long)dv->sms * dv->table_per_sm;
@@ -607,7 +607,7 @@ extern "C" int st_box_depth_reuse(const float *depth, int S, int Hp, int Wp, con
     MakeMapSrc mk;
     mk.depth = depth; mk.Hp = Hp; mk.Wp = Wp;
     k3_box_depth_cta<kHugeThreads, kHugeStage, MakeMapSrc><<<dv->sms, kHugeThreads, sizeof(float) * kHugeStage, aux>>>(
-        mk, Hp, Wp, boxes, cap, d, scale, inflated, workspace + 1, workspace + 4 + 2 * list_cap);
+        mk, Hp, Wp, boxes, cap, d, scale, inflated, workspace + 1, workspace + 8 + 2 * list_cap);
     ST_CUDA_OK(cudaEventRecord(ev_join, aux));
     {
         long long grid = (slots + kWarps - 1) / kWarps;

@@ -25,6 +25,7 @@
 //                       descending code order and takes ranks and window sum from the scan
 //   k3_box_depth_cta    (k3_select.cuh, RawSrc) boxes with a valid code >= 4096 (closer than
 //                       ~0.63 m at B f = 160): the general radix-select path
+#include <cstdio>
 #include <cstdlib>
 #include <cooperative_groups.h>
 #include "k3_select.cuh"
@@ -40,7 +41,6 @@ constexpr int kSmallPix = 512;           // boxes up to this many pixels: one wa
 constexpr int kBins = 4096;              // codes with a direct histogram bin
 constexpr int kHistThreads = 512;
 constexpr int kCluster = 4;
-constexpr int kBinsPerThread = kBins / kHistThreads;     // 8
 
 // MSB-first binary search on 16-bit keys staged in shared memory (one warp, no atomics): per bit
 // one pass and one REDUX.  value[k] = key of rank rank_in[k] in ascending key order, below[k] =
@@ -181,7 +181,7 @@ k3r_box_depth(MakeRawSrc mk, int Hp, int Wp, const float *__restrict__ boxes, in
     __shared__ uint16_t staged_all[kWarps][kStage];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = worklist[3];
-    const int32_t *list = worklist + 4 + 4 * list_cap;
+    const int32_t *list = worklist + 8 + 4 * list_cap;
     for (int idx = blockIdx.x * kWarps + warp; idx < n; idx += gridDim.x * kWarps) {
         const int s = list[2 * idx];
         const RawSrc src = mk(s);
@@ -206,32 +206,214 @@ __device__ __forceinline__ void load4(const RawSrc &src, bool vec_ok, int y, int
     }
 }
 
-__global__ void __launch_bounds__(kHistThreads)
+// Histogram pass over rows [r0, r1) x columns xs of one box by the kT threads of a CTA (every
+// thread must call it: the trip count is block-uniform).  Codes below kBins are counted in
+// `hist` (shared memory); returns true when this thread saw an in-box code without a bin.
+template <int kT>
+__device__ __forceinline__ bool hist_rows(const RawSrc &src, bool vec_ok, Slice xs, int r0, int r1, uint32_t *hist) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int xa = xs.lo & ~3;
+    const int g = xs.hi > xa ? (xs.hi - xa + 3) >> 2 : 0;          // 4-pixel groups per row
+    const int total = g * max(r1 - r0, 0);
+    bool ovf = false;
+    for (int base = 0; base < total; base += 4 * kT) {
+        uint32_t c[4][4];
+        int x0[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                 // four 64-bit loads in flight
+            const int q = base + u * kT + tid;
+            x0[u] = -(1 << 20);
+            c[u][0] = c[u][1] = c[u][2] = c[u][3] = 65535u;
+            if (q < total) {
+                const int ry = q / g, gx = q - ry * g;
+                x0[u] = xa + 4 * gx;
+                load4(src, vec_ok, r0 + ry, x0[u], c[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // histogram key of each pixel (none outside the box or without a bin), runs of
+            // equal keys inside the group merged; then one shared-memory atomic per distinct
+            // (key, run length) among the lanes of the warp: object pixels share one code
+            uint32_t key[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int x = x0[u] + k;
+                const bool inside = x >= xs.lo && x < xs.hi;
+                key[k] = (inside && c[u][k] < (uint32_t)kBins) ? c[u][k] : 0xffffu;
+                ovf |= inside && c[u][k] >= (uint32_t)kBins && c[u][k] != 65535u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool start = key[k] != 0xffffu && (k == 0 || key[k] != key[k - 1]);
+                if (!__any_sync(0xffffffffu, start)) continue;
+                int len = 1;
+#pragma unroll
+                for (int j = k + 1; j < 4; ++j) len += (len == j - k && key[j] == key[k]) ? 1 : 0;
+                const uint32_t tag = start ? (key[k] | ((uint32_t)len << 16)) : 0xffffffffu;
+                const unsigned peers = __match_any_sync(0xffffffffu, tag);
+                if (start && lane == __ffs(peers) - 1) atomicAdd(&hist[key[k]], (uint32_t)(len * __popc(peers)));
+            }
+        }
+    }
+    return ovf;
+}
+
+// The statistic from the complete histogram, by the kT threads of one CTA: bins in DESCENDING code
+// order = ascending depth; thread t owns positions [B t, B t + B), position p holds code kBins-1-p.
+template <int kT>
+__device__ __forceinline__ void hist_stats(const uint32_t *hist, float bf, const float *corner_sm, const int *corner_n,
+                                           int *wsum, double *dred, float *dmid_sh, float &d, float &scale) {
+    constexpr int B = kBins / kT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cnt[B];
+    float dep[B];
+    int tot = 0;
+    const int c_hi = kBins - 1 - B * tid;                           // code of this thread's first position
+#pragma unroll
+    for (int q = 0; q < B / 4; ++q) {
+        const uint4 h4 = *reinterpret_cast<const uint4 *>(&hist[c_hi - 4 * q - 3]);   // codes c_hi-4q-3 .. c_hi-4q
+        const uint32_t hv[4] = {h4.w, h4.z, h4.y, h4.x};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dep[4 * q + j] = st_code_depth((uint32_t)(c_hi - 4 * q - j), bf);
+            cnt[4 * q + j] = depth_valid(dep[4 * q + j]) ? (int)hv[j] : 0;
+            tot += cnt[4 * q + j];
+        }
+    }
+    // block-wide exclusive scan of the per-thread totals
+    int inc = tot;
+    for (int of = 1; of < 32; of <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, of);
+        if (lane >= of) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int excl = inc - tot, n = 0;
+    for (int w = 0; w < kT / 32; ++w) {
+        const int v = wsum[w];
+        if (w < warp) excl += v;
+        n += v;
+    }
+    d = -1.f; scale = 1.f;
+    if (n >= 1) {                                                   // block-uniform
+        // the median: the thread whose rank range holds n / 2
+        const int rmid = n / 2;
+        if (excl <= rmid && rmid < excl + tot) {
+            int acc = excl;
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                if (acc <= rmid && rmid < acc + cnt[j]) *dmid_sh = dep[j];
+                acc += cnt[j];
+            }
+        }
+        __syncthreads();
+        const float d_mid = *dmid_sh;
+        int k = 0;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) k += corner_mean_of(corner_sm + 4 * cc, corner_n[cc]) > d_mid;
+        const Slice seg = window_of(n, k);
+        const int m = seg.hi - seg.lo;
+        if (m <= 0) {
+            d = __int_as_float(0x7fc00000);                         // mean of empty -> NaN
+        } else {
+            double part = 0.0;
+            int acc = excl;
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const int lo = max(acc, seg.lo), hi = min(acc + cnt[j], seg.hi);
+                if (hi > lo) part += (double)dep[j] * (double)(hi - lo);
+                acc += cnt[j];
+            }
+            const double sum = block_sum(part, dred);
+            d = (float)(sum / (double)m);
+        }
+        scale = scale_of(d);
+    }
+    __syncthreads();                                                // wsum / dmid_sh are reused by the next item
+}
+
+// Medium boxes (kSmallPix < pixels <= kMediumPix): one CTA of 256 threads per box, many CTAs per SM.
+constexpr int kMedThreads = 256;
+constexpr int kMediumPix = 8192;
+
+__global__ void __launch_bounds__(kMedThreads, 4)
+k3r_box_depth_med(MakeRawSrc mk, int Hp, int Wp, const float *__restrict__ boxes, int cap,
+                  float *__restrict__ d_out, float *__restrict__ scale_out, float *__restrict__ inflated,
+                  int32_t *__restrict__ worklist, int list_cap) {
+    __shared__ __align__(16) uint32_t hist[kBins];
+    __shared__ float dmid_sh;
+    __shared__ float corner_sm[16];
+    __shared__ int corner_n[4];
+    __shared__ int wsum[kMaxCtaWarps];
+    __shared__ double dred[kMaxCtaWarps];
+    const int tid = threadIdx.x;
+    const int n_work = worklist[0];
+    const bool vec_ok = (mk.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(mk.base()) & 7u) == 0);
+    for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
+        const int s = worklist[8 + 2 * item], bi = worklist[9 + 2 * item];
+        const long long o = (long long)s * cap + bi;
+        const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
+        const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
+        const RawSrc src = mk(s);
+        const Slice ys = py_slice(b1, b3, Hp), xs = py_slice(b0, b2, Wp);
+        const long long wbox = wrap_add(b2, (long long)(0ull - (unsigned long long)b0));
+        float d = -1.f, scale = 1.f;
+        if (!(wbox > 800)) {                              // reference: d = -1, scale = 1 (:150)
+            for (int i = tid; i < kBins; i += kMedThreads) hist[i] = 0u;
+            if (tid < 16) {                               // corner patches (read after the barriers below)
+                int cy, cx, cn;
+                const bool has = corner_elem(tid >> 2, tid & 3, b0, b1, b2, b3, Hp, Wp, cy, cx, cn);
+                corner_sm[tid] = has ? src.at(cy, cx) : 0.f;
+                if ((tid & 3) == 0) corner_n[tid >> 2] = cn;
+            }
+            __syncthreads();
+            const bool ovf = hist_rows<kMedThreads>(src, vec_ok, xs, ys.lo, ys.hi, hist);
+            if (__syncthreads_or(ovf)) {                  // a valid code without a bin: general path
+                if (tid == 0) {
+                    const int slot = atomicAdd(&worklist[1], 1);
+                    worklist[8 + 2 * list_cap + 2 * slot] = s;
+                    worklist[9 + 2 * list_cap + 2 * slot] = bi;
+                }
+                continue;                                 // block-uniform
+            }
+            hist_stats<kMedThreads>(hist, src.bf, corner_sm, corner_n, wsum, dred, &dmid_sh, d, scale);
+        }
+        if (tid == 0) write_box(o, box, d, scale, d_out, scale_out, inflated);
+    }
+}
+
+// Huge boxes (> kMediumPix pixels): a cluster of kCluster CTAs per box, rows split over the CTAs,
+// histograms merged over distributed shared memory.  The huge list grows from the END of the
+// large-box list region (entry k at list_cap - 1 - k), its count is worklist[4], its cursor [2].
+__global__ void __launch_bounds__(kHistThreads, 2)
 k3r_box_depth_hist(MakeRawSrc mk, int Hp, int Wp, const float *__restrict__ boxes, int cap,
                    float *__restrict__ d_out, float *__restrict__ scale_out, float *__restrict__ inflated,
                    int32_t *__restrict__ worklist, int list_cap) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned crank = cluster.block_rank();
     __shared__ __align__(16) uint32_t hist[kBins];
-    __shared__ int next_item, overflow_sh, sel_sh;
+    __shared__ int next_item, overflow_sh;
     __shared__ float dmid_sh;
     __shared__ float corner_sm[16];
     __shared__ int corner_n[4];
     __shared__ int wsum[kMaxCtaWarps];
     __shared__ double dred[kMaxCtaWarps];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     int *leader_next = cluster.map_shared_rank(&next_item, 0);
     int *leader_ovf = cluster.map_shared_rank(&overflow_sh, 0);
-    const int n_work = worklist[0];
+    const int n_work = worklist[4];
+    if (n_work == 0) return;                              // uniform over the grid: nothing to synchronise
     const bool vec_ok = (mk.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(mk.base()) & 7u) == 0);
     while (true) {
-        // items come from a shared cursor (boxes range from 513 to 500 000+ pixels)
+        // items come from a shared cursor (boxes range from 8 193 to 500 000+ pixels)
         if (crank == 0 && tid == 0) { next_item = atomicAdd(&worklist[2], 1); overflow_sh = 0; }
         for (int i = tid; i < kBins; i += kHistThreads) hist[i] = 0u;
         cluster.sync();                                   // (A) item published, histograms cleared
         const int item = *leader_next;
         if (item >= n_work) { cluster.sync(); break; }    // nobody leaves while its shared memory may be read
-        const int s = worklist[4 + 2 * item], bi = worklist[5 + 2 * item];
+        const int e = list_cap - 1 - item;
+        const int s = worklist[8 + 2 * e], bi = worklist[9 + 2 * e];
         const long long o = (long long)s * cap + bi;
         const float4 box = reinterpret_cast<const float4 *>(boxes)[o];
         const long long b0 = trunc_i64(box.x), b1 = trunc_i64(box.y), b2 = trunc_i64(box.z), b3 = trunc_i64(box.w);
@@ -250,51 +432,7 @@ k3r_box_depth_hist(MakeRawSrc mk, int Hp, int Wp, const float *__restrict__ boxe
             const int bh = max(ys.hi - ys.lo, 0);
             const int rows_per = (bh + kCluster - 1) / kCluster;
             const int r0 = ys.lo + (int)crank * rows_per, r1 = min(r0 + rows_per, ys.hi);
-            const int xa = xs.lo & ~3;
-            const int g = xs.hi > xa ? (xs.hi - xa + 3) >> 2 : 0;      // 4-pixel groups per row
-            const int total = g * max(r1 - r0, 0);
-            bool ovf = false;
-            for (int base = 0; base < total; base += 4 * kHistThreads) {        // block-uniform trip count
-                uint32_t c[4][4];
-                int x0[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {             // four 64-bit loads in flight
-                    const int q = base + u * kHistThreads + tid;
-                    x0[u] = -1 << 20;
-                    c[u][0] = c[u][1] = c[u][2] = c[u][3] = 65535u;
-                    if (q < total) {
-                        const int ry = q / g, gx = q - ry * g;
-                        x0[u] = xa + 4 * gx;
-                        load4(src, vec_ok, r0 + ry, x0[u], c[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    // histogram key of each pixel (none outside the box or without a bin), runs of
-                    // equal keys inside the group merged; then one shared-memory atomic per distinct
-                    // (key, run length) among the lanes of the warp: object pixels share one code
-                    uint32_t key[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int x = x0[u] + k;
-                        const bool inside = x >= xs.lo && x < xs.hi;
-                        key[k] = (inside && c[u][k] < (uint32_t)kBins) ? c[u][k] : 0xffffu;
-                        ovf |= inside && c[u][k] >= (uint32_t)kBins && c[u][k] != 65535u;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const bool start = key[k] != 0xffffu && (k == 0 || key[k] != key[k - 1]);
-                        if (!__any_sync(0xffffffffu, start)) continue;
-                        int len = 1;
-#pragma unroll
-                        for (int j = k + 1; j < 4; ++j) len += (len == j - k && key[j] == key[k]) ? 1 : 0;
-                        const uint32_t tag = start ? (key[k] | ((uint32_t)len << 16)) : 0xffffffffu;
-                        const unsigned peers = __match_any_sync(0xffffffffu, tag);
-                        if (start && lane == __ffs(peers) - 1) atomicAdd(&hist[key[k]], (uint32_t)(len * __popc(peers)));
-                    }
-                }
-            }
-            if (ovf) *leader_ovf = 1;
+            if (hist_rows<kHistThreads>(src, vec_ok, xs, r0, r1, hist)) *leader_ovf = 1;
         }
         cluster.sync();                                   // (B) every CTA's histogram is complete
         if (!skip) {
@@ -316,83 +454,18 @@ k3r_box_depth_hist(MakeRawSrc mk, int Hp, int Wp, const float *__restrict__ boxe
             if (overflow_sh) {                            // a valid code without a bin: general path
                 if (tid == 0) {
                     const int slot = atomicAdd(&worklist[1], 1);
-                    worklist[4 + 2 * list_cap + 2 * slot] = s;
-                    worklist[5 + 2 * list_cap + 2 * slot] = bi;
+                    worklist[8 + 2 * list_cap + 2 * slot] = s;
+                    worklist[9 + 2 * list_cap + 2 * slot] = bi;
                 }
                 continue;                                 // block-uniform
             }
-            // bins in DESCENDING code order = ascending depth: thread t owns positions [8t, 8t+8),
-            // position p holds code kBins - 1 - p
-            int cnt[kBinsPerThread];
-            float dep[kBinsPerThread];
-            int tot = 0;
-            {
-                const int c_hi = kBins - 1 - kBinsPerThread * tid;           // code of position 8t
-                const uint4 h1 = *reinterpret_cast<const uint4 *>(&hist[c_hi - 3]);   // codes c_hi-3 .. c_hi
-                const uint4 h0 = *reinterpret_cast<const uint4 *>(&hist[c_hi - 7]);   // codes c_hi-7 .. c_hi-4
-                const uint32_t hv[kBinsPerThread] = {h1.w, h1.z, h1.y, h1.x, h0.w, h0.z, h0.y, h0.x};
-#pragma unroll
-                for (int j = 0; j < kBinsPerThread; ++j) {
-                    dep[j] = st_code_depth((uint32_t)(c_hi - j), src.bf);
-                    cnt[j] = depth_valid(dep[j]) ? (int)hv[j] : 0;
-                    tot += cnt[j];
-                }
-            }
-            // block-wide exclusive scan of the per-thread totals
-            int inc = tot;
-            for (int of = 1; of < 32; of <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, of);
-                if (lane >= of) inc += t;
-            }
-            if (lane == 31) wsum[warp] = inc;
-            __syncthreads();
-            int excl = inc - tot, n = 0;
-            for (int w = 0; w < kHistThreads / 32; ++w) {
-                const int v = wsum[w];
-                if (w < warp) excl += v;
-                n += v;
-            }
-            if (n >= 1) {
-                // the median: the thread whose rank range holds n / 2
-                const int rmid = n / 2;
-                if (excl <= rmid && rmid < excl + tot) {
-                    int acc = excl;
-#pragma unroll
-                    for (int j = 0; j < kBinsPerThread; ++j) {
-                        if (acc <= rmid && rmid < acc + cnt[j]) dmid_sh = dep[j];
-                        acc += cnt[j];
-                    }
-                }
-                __syncthreads();
-                const float d_mid = dmid_sh;
-                int k = 0;
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) k += corner_mean_of(corner_sm + 4 * cc, corner_n[cc]) > d_mid;
-                const Slice seg = window_of(n, k);
-                const int m = seg.hi - seg.lo;
-                if (m <= 0) {
-                    d = __int_as_float(0x7fc00000);       // mean of empty -> NaN
-                } else {
-                    double part = 0.0;
-                    int acc = excl;
-#pragma unroll
-                    for (int j = 0; j < kBinsPerThread; ++j) {
-                        const int lo = max(acc, seg.lo), hi = min(acc + cnt[j], seg.hi);
-                        if (hi > lo) part += (double)dep[j] * (double)(hi - lo);
-                        acc += cnt[j];
-                    }
-                    const double sum = block_sum(part, dred);
-                    d = (float)(sum / (double)m);
-                }
-                scale = scale_of(d);
-            }
-            __syncthreads();                              // wsum / dmid_sh are reused by the next item
+            hist_stats<kHistThreads>(hist, src.bf, corner_sm, corner_n, wsum, dred, &dmid_sh, d, scale);
         }
         if (tid == 0) write_box(o, box, d, scale, d_out, scale_out, inflated);
     }
 }
 
-struct K3rDev { int sms, warp_ctas, hist_clusters; };
+struct K3rDev { int sms, warp_ctas, med_ctas, hist_clusters; };
 StPerDevice<K3rDev> g_k3rdev;
 
 int launch_hist(const K3rDev *dv, cudaStream_t st, MakeRawSrc mk, int Hp, int Wp, const float *boxes, int cap, float *d,
@@ -432,7 +505,7 @@ int st_box_depth_raw_tab(const uint16_t *raw, const StFrameInputs *tab, int S, i
     if (prev_index && (!prev_boxes || !prev_d)) return ST_ERR_INVALID_ARG;
     if (S == 0) return ST_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 4, st));
+    ST_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * 8, st));
     const int list_cap = S * cap;
     const K3rDev *dv = g_k3rdev.get([](K3rDev &v) {
         v.sms = st_ctx_sms();
@@ -443,6 +516,10 @@ int st_box_depth_raw_tab(const uint16_t *raw, const StFrameInputs *tab, int S, i
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3r_box_depth, kWarps * 32, 0) != cudaSuccess || per_sm < 1)
             per_sm = 8;
         v.warp_ctas = v.sms * per_sm;
+        per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3r_box_depth_med, kMedThreads, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+        v.med_ctas = v.sms * per_sm;
         // resident clusters of the histogram kernel
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(v.sms * kCluster), 1, 1);
@@ -459,6 +536,9 @@ int st_box_depth_raw_tab(const uint16_t *raw, const StFrameInputs *tab, int S, i
         }
         if (const char *e = getenv("ST_K3R_CLUSTERS")) { const int c = atoi(e); if (c > 0 && c < clusters) clusters = c; }
         v.hist_clusters = clusters;
+        if (getenv("ST_K3R_VERBOSE"))
+            fprintf(stderr, "[st] k3r: sms %d, warp CTAs %d, medium CTAs %d, resident clusters of %d: %d\n", v.sms,
+                    v.warp_ctas, v.med_ctas, kCluster, clusters);
         return true;
     });
     if (!dv) return ST_ERR_CUDA;
@@ -469,20 +549,26 @@ int st_box_depth_raw_tab(const uint16_t *raw, const StFrameInputs *tab, int S, i
     mk.raw = raw; mk.tab = tab; mk.H = H; mk.W = W; mk.bf = st_bf(baseline, focal_length);
     const long long slots = (long long)S * cap;
     k3_classify<<<(int)((slots + 255) / 256), 256, 0, st>>>(S, Hp, Wp, boxes, counts, cap, d, scale, inflated, workspace,
-                                                           list_cap, prev_boxes, prev_index, prev_d, (unsigned)kSmallPix);
-    // fork: the large boxes (cluster kernel, then its overflow list) on the auxiliary stream,
-    // the small boxes on the caller's stream; join before returning to the caller's order
+                                                           list_cap, prev_boxes, prev_index, prev_d, (unsigned)kSmallPix,
+                                                           (unsigned)kMediumPix);
+    // fork: the medium boxes (one CTA each) on the auxiliary stream; the huge boxes (clusters), the
+    // overflow list of both and the small boxes (warps) on the caller's stream; join before returning
     ST_CUDA_OK(cudaEventRecord(ev_fork, st));
     ST_CUDA_OK(cudaStreamWaitEvent(aux, ev_fork, 0));
-    if (launch_hist(dv, aux, mk, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap) != ST_OK) return ST_ERR_CUDA;
-    k3_box_depth_cta<kHugeThreads, kHugeStage, MakeRawSrc><<<dv->sms, kHugeThreads, sizeof(float) * kHugeStage, aux>>>(
-        mk, Hp, Wp, boxes, cap, d, scale, inflated, workspace + 1, workspace + 4 + 2 * list_cap);
+    {
+        long long grid = dv->med_ctas;
+        if (grid > list_cap) grid = list_cap;
+        k3r_box_depth_med<<<(int)grid, kMedThreads, 0, aux>>>(mk, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap);
+    }
     ST_CUDA_OK(cudaEventRecord(ev_join, aux));
     {
         long long grid = (slots + kWarps - 1) / kWarps;
         if (grid > dv->warp_ctas) grid = dv->warp_ctas;
         k3r_box_depth<<<(int)grid, kWarps * 32, 0, st>>>(mk, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap);
     }
+    if (launch_hist(dv, st, mk, Hp, Wp, boxes, cap, d, scale, inflated, workspace, list_cap) != ST_OK) return ST_ERR_CUDA;
     ST_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
+    k3_box_depth_cta<kHugeThreads, kHugeStage, MakeRawSrc><<<dv->sms, kHugeThreads, sizeof(float) * kHugeStage, st>>>(
+        mk, Hp, Wp, boxes, cap, d, scale, inflated, workspace + 1, workspace + 8 + 2 * list_cap);
     return st_last_launch();
 }

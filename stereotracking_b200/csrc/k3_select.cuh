@@ -250,12 +250,15 @@ k3_box_depth_cta(MakeSrc make_src, int Hp, int Wp, const float *__restrict__ box
   }
 }
 
-// Workspace layout (int32): [0] number of large boxes, [1] number of table overflows, [2] cursor
-// of the table kernel, [3] number of small boxes, then three lists of (sequence, row) pairs with
-// list_cap = S * cap entries each: large boxes, table overflows, small boxes.
-__device__ __forceinline__ int32_t *large_list(int32_t *ws) { return ws + 4; }
-__device__ __forceinline__ int32_t *overflow_list(int32_t *ws, int list_cap) { return ws + 4 + 2 * list_cap; }
-__device__ __forceinline__ int32_t *small_list(int32_t *ws, int list_cap) { return ws + 4 + 4 * list_cap; }
+// Workspace layout (int32): [0] number of large boxes, [1] number of overflows (boxes the fast
+// large-box kernel hands to the general one), [2] work cursor of the persistent large-box kernel,
+// [3] number of small boxes, [4] number of huge boxes (raw path), [5..7] spare, then three lists of
+// (sequence, row) pairs with list_cap = S * cap entries each: large boxes (the huge ones of the raw
+// path grow from the END of this list: entry k at list_cap - 1 - k), overflows, small boxes.
+constexpr int kWsHeader = 8;
+__device__ __forceinline__ int32_t *large_list(int32_t *ws) { return ws + kWsHeader; }
+__device__ __forceinline__ int32_t *overflow_list(int32_t *ws, int list_cap) { return ws + kWsHeader + 2 * list_cap; }
+__device__ __forceinline__ int32_t *small_list(int32_t *ws, int list_cap) { return ws + kWsHeader + 4 * list_cap; }
 
 // One thread per box slot: rows that can reuse the statistic of their source row are finished
 // here; the others are sorted into the dense small-box and large-box lists, so that the warp
@@ -269,7 +272,8 @@ static __global__ void __launch_bounds__(256)
 k3_classify(int S, int Hp, int Wp, const float *__restrict__ boxes, const int32_t *__restrict__ counts, int cap,
             float *__restrict__ d_out, float *__restrict__ scale_out, float *__restrict__ inflated,
             int32_t *__restrict__ worklist, int list_cap, const float *__restrict__ prev_boxes,
-            const int32_t *__restrict__ prev_index, const float *__restrict__ prev_d, unsigned small_pix) {
+            const int32_t *__restrict__ prev_index, const float *__restrict__ prev_d, unsigned small_pix,
+            unsigned medium_pix /* 0 = no separate list of huge boxes */) {
     const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= (long long)S * cap) return;
     const int s = (int)(o / cap), bi = (int)(o - (long long)s * cap);
@@ -288,7 +292,11 @@ k3_classify(int S, int Hp, int Wp, const float *__restrict__ boxes, const int32_
     }
     const Slice ys = py_slice(b1, b3, Hp), xs = py_slice(b0, b2, Wp);
     const unsigned npix = (unsigned)max(xs.hi - xs.lo, 0) * (unsigned)max(ys.hi - ys.lo, 0);
-    if (npix > small_pix) {
+    if (medium_pix && npix > medium_pix) {
+        const int slot = list_cap - 1 - atomicAdd(&worklist[4], 1);
+        large_list(worklist)[2 * slot] = s;
+        large_list(worklist)[2 * slot + 1] = bi;
+    } else if (npix > small_pix) {
         const int slot = atomicAdd(&worklist[0], 1);
         large_list(worklist)[2 * slot] = s;
         large_list(worklist)[2 * slot + 1] = bi;

@@ -89,7 +89,7 @@ class FrameBuffers:
         self.out_scale2 = torch.zeros(S, D, **f32)
         self.out_src = torch.zeros(S, D, **i32)            # detection row of every track row
         self.frame_ids = torch.zeros(S, **i32)
-        self.k3_workspace = torch.zeros(4 + 6 * S * D, **i32)
+        self.k3_workspace = torch.zeros(8 + 6 * S * D, **i32)
         self.depth_map = None
 
     def outputs(self):
@@ -295,8 +295,8 @@ class StereoTrackEngine:
         d_out = d_out if d_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
         scale_out = scale_out if scale_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
         ws = self.k3_workspace
-        if ws.numel() < 4 + 6 * S * cap or ws.device != dev:
-            ws = self.k3_workspace = torch.zeros(4 + 6 * S * cap, dtype=torch.int32, device=dev)
+        if ws.numel() < 8 + 6 * S * cap or ws.device != dev:
+            ws = self.k3_workspace = torch.zeros(8 + 6 * S * cap, dtype=torch.int32, device=dev)
         if mode == 'window':
             _lib.check(self.lib.st_box_depth(_ptr(self._dev(depth, torch.float32)), S, Hp, Wp,
                                              _ptr(self._dev(boxes, torch.float32)),
@@ -327,8 +327,8 @@ class StereoTrackEngine:
         d_out = d_out if d_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
         scale_out = scale_out if scale_out is not None else torch.empty(S, cap, dtype=torch.float32, device=dev)
         ws = self.k3_workspace
-        if ws.numel() < 4 + 6 * S * cap or ws.device != dev:
-            ws = self.k3_workspace = torch.zeros(4 + 6 * S * cap, dtype=torch.int32, device=dev)
+        if ws.numel() < 8 + 6 * S * cap or ws.device != dev:
+            ws = self.k3_workspace = torch.zeros(8 + 6 * S * cap, dtype=torch.int32, device=dev)
         _lib.check(self.lib.st_box_depth_raw(_ptr(self._dev(raw, torch.uint16)), S, H, W, Hp, Wp, self.cfg.baseline,
                                              self.cfg.focal_length, _ptr(self._dev(boxes, torch.float32)),
                                              _ptr(self._dev(counts, torch.int32)), cap, _ptr(d_out), _ptr(scale_out),

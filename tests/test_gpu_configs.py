@@ -159,7 +159,7 @@ def test_bench_workload_c2_s64_matches_oracle(mods, depth_source):
     raw = torch.cat([p['raw'] for p in parts])
     heads = [[torch.cat([p[k][l] for p in parts]) for l in range(3)] for k in ('cls', 'bbox', 'obj')]
     del parts
-    host_raw = raw[:, check].cpu().numpy()
+    host_raw = raw.view(torch.int16)[:, check].cpu().numpy().view(np.uint16)      # no uint16 indexing kernel in torch
     host_heads = [[c[:, check].cpu().numpy() for c in hk] for hk in heads]
     fid = torch.arange(F, dtype=torch.int32, device='cuda')[:, None].repeat(1, S).contiguous()
     eng = m.StereoTrackEngine(m.EngineConfig(n_seq=S, max_dets=256, max_tracks=256, max_candidates=2048))

@@ -15,7 +15,7 @@ mkdir -p gpurun_out
 BENCH="python bench.py --steps 4 --warmup 3 --no-cpu-baseline"
 case "${1:-check}" in
   check)
-    timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/gpu_tests.log 2>&1; tail -15 gpurun_out/gpu_tests.log
+    timeout 600 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests.log 2>&1; tail -15 gpurun_out/gpu_tests.log
     timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -5 gpurun_out/bench.err
     python - <<'PY'
 import json
