@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libstereotrack_b200.so')
-SOURCES = ['st_context.cu', 'k1_disp2depth.cu', 'k1b_pack_image.cu', 'k2_decode_nms.cu', 'k3_box_depth.cu', 'k3_box_depth_raw.cu', 'k4_track.cu', 'k_pipeline.cu']
-HEADERS = ['st_common.cuh', 'kalman.cuh', 'lapjv.cuh', 'k3_common.cuh', 'k3_select.cuh', os.path.join('..', '..', 'include', 'stereotrack_b200.h')]
+SOURCES = ['st_context.cu', 'k1_disp2depth.cu', 'k1b_pack_image.cu', 'k2_decode_nms.cu', 'k3_box_depth.cu', 'k3_box_depth_raw.cu', 'k4_track.cu', 'k4_track2.cu', 'k_pipeline.cu']
+HEADERS = ['st_common.cuh', 'kalman.cuh', 'lapjv.cuh', 'k3_common.cuh', 'k3_select.cuh', 'k4_common.cuh', os.path.join('..', '..', 'include', 'stereotrack_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-fmad=false', '--extended-lambda', '-Xcompiler', '-fPIC', '-shared']
 

@@ -14,10 +14,14 @@
 // Track state lives in the handle as a structure of arrays; `order` keeps the
 // live slots in ascending-id order, which is the reference's dict order.
 #include <new>
+#include <cstdlib>
 #include <cstring>
 #include "st_common.cuh"
 #include "kalman.cuh"
 #include "lapjv.cuh"
+#include "k4_common.cuh"
+
+using namespace stk4;
 
 namespace {
 
@@ -29,16 +33,6 @@ constexpr int kThreads = ST_K4_THREADS;
 constexpr int kCostSmemFloats = 14336;
 constexpr int kWarps = kThreads / 32;
 
-// diagnostics only (st_debug_set_skip): bit0..2 skip the assignment of stage
-// 1..3, bit3 skip online smoothing, bit4 skip Kalman update, bit5 skip predict
-__device__ int g_skip = 0;
-
-struct Params {
-    int T, D;                    // capacities
-    float obj_score_thr, init_track_thr, vel_w;
-    int weight_iou, num_tentatives, vel_dt, retain;
-    double lap_half;             // (1 - match_iou_thr) / 2
-};
 
 struct Smem {                    // carved from dynamic shared memory
     stlap::Scratch lap;
@@ -65,8 +59,6 @@ struct Smem {                    // carved from dynamic shared memory
     float *in_box;               // [D,4] detection boxes
     float *in_score;             // [D]
 };
-
-__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t smem_bytes(int T, int D) {
     size_t b = stlap::scratch_bytes(T + D);
@@ -110,60 +102,6 @@ __device__ inline Smem carve(unsigned char *p, int T, int D) {
     return m;
 }
 
-__device__ __forceinline__ float sum4(const float *b) {      // torch .sum() of 4 float32
-    return __fadd_rn(__fadd_rn(__fadd_rn(b[0], b[1]), b[2]), b[3]);
-}
-
-// k_step_observation (:173-185): the observation vel_delta_t steps before the
-// newest one if it exists and is not None, else the last non-None observation
-__device__ inline const float *k_step_obs(const TrackState &st, long long g, int vel_dt) {
-    const int n = st.num_obs[g];
-    if (n > vel_dt) {
-        const int r = (n - 1 - vel_dt) % ST_RING;
-        if (st.obs_valid[g * ST_RING + r]) return st.obs_ring + (g * ST_RING + r) * 4;
-    }
-    return st.last_obs + g * 4;
-}
-
-__device__ inline void push_obs(const TrackState &st, long long g, const float *box) {
-    const int n = st.num_obs[g];
-    const int r = n % ST_RING;
-    if (box) {
-        for (int k = 0; k < 4; ++k) { st.obs_ring[(g * ST_RING + r) * 4 + k] = box[k]; st.last_obs[g * 4 + k] = box[k]; }
-        st.obs_valid[g * ST_RING + r] = 1;
-        st.miss_run[g] = 0;
-    } else {
-        st.obs_valid[g * ST_RING + r] = 0;
-        st.miss_run[g] += 1;
-    }
-    st.num_obs[g] = n + 1;
-}
-
-// vel_direction (:148-156)
-__device__ inline void vel_direction(const float *b1, const float *b2, float *out) {
-    if (sum4(b1) < 0.f || sum4(b2) < 0.f) { out[0] = -1.f; out[1] = -1.f; return; }
-    const float cx1 = __fmul_rn(__fadd_rn(b1[0], b1[2]), 0.5f), cy1 = __fmul_rn(__fadd_rn(b1[1], b1[3]), 0.5f);
-    const float cx2 = __fmul_rn(__fadd_rn(b2[0], b2[2]), 0.5f), cy2 = __fmul_rn(__fadd_rn(b2[1], b2[3]), 0.5f);
-    const float sy = __fsub_rn(cy2, cy1), sx = __fsub_rn(cx2, cx1);
-    const float norm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(sy, sy), __fmul_rn(sx, sx))), 1e-6f);
-    out[0] = __fdiv_rn(sy, norm);
-    out[1] = __fdiv_rn(sx, norm);
-}
-
-// mmdet bbox_overlaps(mode='iou', eps=1e-6) for one pair, float32
-__device__ __forceinline__ float iou_pair(const float *a, const float *b) {
-    const float a1 = __fmul_rn(__fsub_rn(a[2], a[0]), __fsub_rn(a[3], a[1]));
-    const float a2 = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
-    float w = __fsub_rn(fminf(a[2], b[2]), fmaxf(a[0], b[0]));
-    float h = __fsub_rn(fminf(a[3], b[3]), fmaxf(a[1], b[1]));
-    w = w < 0.f ? 0.f : w;           // clamp(min=0) keeps NaN
-    h = h < 0.f ? 0.f : h;
-    const float inter = __fmul_rn(w, h);
-    float uni = __fsub_rn(__fadd_rn(a1, a2), inter);
-    uni = uni < 1e-6f ? 1e-6f : uni; // torch.max(union, eps) (NaN stays NaN)
-    return __fdiv_rn(inter, uni);
-}
-
 // ordered (stable) compaction of the indices i in [0,n) with flag(i) into dst;
 // executed by warp 0, returns the count to every thread of the block via *cnt_sh
 template <typename F>
@@ -182,11 +120,6 @@ __device__ inline void compact_warp0(int n, F flag, int *dst, int *cnt_sh) {
     }
     __syncthreads();
 }
-
-struct DetView {
-    const float *boxes, *scores, *scales, *depth;
-    const int64_t *labels;
-};
 
 // one association stage: rows = slots in sm.rows[0..R), cols = input dets in
 // sm.dets[0..C).  ocm = velocity-direction term on (stage 1/2); boxes of the
@@ -685,7 +618,21 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
         stlap::count_admissible(P);
         bool ok;
         if (mode == 1) ok = stlap::solve_warp(P, sc);                 // exact emulation only
-        else {
+        else if (mode == 2 && R <= 64 && C <= 64) {
+            // component path of the round-2 tracker kernel, on one warp
+            stlap::Masks mk = stlap::carve_masks(smem_raw + ((stlap::scratch_bytes(R + C) + sizeof(int) * (2 * R + C + 4) + 15) & ~(size_t)15));
+            stlap::build_masks(P, mk);
+            stlap::prepare_components(P, sc, mk);
+            bool bad = *mk.fallback != 0;
+            for (int k = 0; !bad && k < *mk.n_comp; ++k)
+                bad = !stlap::enumerate_component(P, sc, mk.comp_rows[k], mk.comp_cols[k]);
+            ok = true;
+            if (bad) {
+                if (lane == 0) atomicAdd(fallbacks, 1);
+                __syncwarp();
+                ok = stlap::assign_warp(P, sc, nullptr);
+            }
+        } else {
             ok = R + C <= 512 && stlap::fast_assign_warp(P, sc);       // certified fast path
             if (!ok) {
                 if (lane == 0) atomicAdd(fallbacks, 1);
@@ -815,7 +762,7 @@ size_t layout(st_handle *h, unsigned char *base) {
     take(st.last_depth, c, S * T); take(st.last_label, c, S * T);
     take(h->cand_count, c, S); take(h->cand_score, c, S * N); take(h->cand_prior, c, S * N);
     take(h->cand_label, c, S * N);
-    take(h->cost, c, S * T * D);
+    take(h->cost, c, S * T * D * 3);
     return (size_t)(c - base);
 }
 
@@ -866,8 +813,14 @@ extern "C" int st_create(const st_config *cfg, st_handle **out) {
     if (cudaFuncSetAttribute(k4_track_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(k5_lapjv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(stlap::scratch_bytes(cfg->max_tracks + cfg->max_dets) +
-                                   sizeof(int) * (2 * cfg->max_tracks + cfg->max_dets + 4))) != cudaSuccess) {
+                                   sizeof(int) * (2 * cfg->max_tracks + cfg->max_dets + 4) + 16 +
+                                   stlap::masks_bytes())) != cudaSuccess) {
         cudaFree(h->all_mem); delete h; return ST_ERR_CAPACITY;
+    }
+    {
+        const char *e = getenv("ST_K4_V1");
+        h->k4_version = (e && atoi(e) != 0) || st_k4v2_configure(cfg->max_tracks, cfg->max_dets) != ST_OK ? 1 : 2;
+        cudaGetLastError();
     }
     k4_reset<<<cfg->max_sequences, 128>>>(h->st, cfg->max_tracks, nullptr);
     if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(h->all_mem); delete h; return ST_ERR_CUDA; }
@@ -979,7 +932,7 @@ extern "C" int st_debug_read_cost(st_handle *h, int seq, float *cost_host, int c
 
 extern "C" int st_debug_set_skip(int mask) {
     ST_CUDA_OK(cudaMemcpyToSymbol(g_skip, &mask, sizeof(int)));
-    return ST_OK;
+    return st_k4v2_set_skip(mask);
 }
 
 extern "C" int st_clear_status(st_handle *h, void *stream) {
@@ -1009,6 +962,10 @@ extern "C" int st_track_step(st_handle *h, int S, const int32_t *frame_ids, cons
     pr.retain = h->cfg.num_frames_retain;
     // lap.lapjv(cost_limit = 1 - match_iou_thr): Python float arithmetic on the config value
     pr.lap_half = (1.0 - h->cfg.match_iou_thr) / 2.0;
+    if (h->k4_version == 2)
+        return st_k4v2_launch(h, pr, S, frame_ids, det_boxes, det_scores, det_labels, det_scales, det_depth, det_counts,
+                              det_cap, out_boxes, out_scores, out_labels, out_scales, out_depth, out_ids, out_counts,
+                              out_src, warp, (cudaStream_t)stream);
     const size_t smem = smem_bytes(pr.T, pr.D);
     k4_track_step<<<S, kThreads, smem, (cudaStream_t)stream>>>(
         h->st, pr, frame_ids, det_boxes, det_scores, det_labels, det_scales, det_depth, det_counts, det_cap,
@@ -1094,7 +1051,8 @@ extern "C" int st_lapjv_batch(st_handle *h, int B, int R, int C, const float *co
         return ST_ERR_INVALID_ARG;
     StDeviceGuard guard(h->device);
     if (B == 0 || R + C == 0) return ST_OK;
-    k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C) + sizeof(int) * (2 * R + C + 4), (cudaStream_t)stream>>>(
+    k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C) + sizeof(int) * (2 * R + C + 4) + 16 + stlap::masks_bytes(),
+                     (cudaStream_t)stream>>>(
         R, C, cost, cost_limit / 2.0, mode, row2col, col2row, h->st.status, h->st.debug + 6);
     return st_last_launch();
 }

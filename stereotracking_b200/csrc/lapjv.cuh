@@ -99,7 +99,7 @@ __device__ __forceinline__ bool pair_less(double va, int ia, double vb, int ib) 
 // track kernel mis-executed the warp collectives of the augmentation loop on
 // inputs the stand-alone kernel solved (bisected on a B200); one
 // shared out-of-line body behaves identically at every call site.
-__device__ __noinline__ bool solve_warp(const Problem &P, Scratch &s) {
+static __device__ __noinline__ bool solve_warp(const Problem &P, Scratch &s) {
     const int lane = threadIdx.x & 31;
     const int n = P.n;
     bool ok = true;
@@ -541,7 +541,7 @@ __device__ bool hungarian_regs(const Problem &P, volatile double *u, volatile do
     return true;
 }
 
-__device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
+static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     const int lane = threadIdx.x & 31;
     const int R = P.R, C = P.C, m = R + C;
     const double half = P.half, L = 2.0 * P.half;
@@ -855,6 +855,198 @@ __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
         ++cnt;
         s.y[j] = r;
         if (r >= 0) s.x[r] = j;
+    }
+    __syncwarp();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------
+// Component path (problems with R, C <= 64).  The objective of the extended problem is
+// sum over matched pairs of (c_ij - L): only ADMISSIBLE entries (c_ij < L) can be part of an
+// optimum, so rows in different connected components of the admissible bipartite graph are
+// independent problems.  In tracking the graph is sparse: most rows are isolated pairs, the
+// rest form components of two or three tracks around the same detections (98.8 % of the
+// problems of the bench workload have only components <= 4 x 4, profiles/r01_assign_components_c2.txt).
+//   1. one warp: isolated pairs are matched, the other rows are grouped into components by
+//      closing row / column sets over the admissibility bitmasks (64-bit, REDUX per round);
+//   2. every warp of the CTA takes components: a component of <= 4 rows and <= 4 columns is
+//      solved by ENUMERATING its <= 209 partial matchings (5^rows codes spread over the lanes):
+//      the minimum is the optimum, and the runner-up being worse by more than kFastEps is the
+//      uniqueness certificate - a unique optimum is what any exact solver, including the
+//      reference's, returns;
+//   3. a larger component, a tie (duplicate boxes), a NaN or a cost within 2e-9 of L sends the
+//      whole problem to assign_warp (certified Hungarian, then the literal JV emulation), so
+//      tie-breaks still follow the reference's scan order.
+struct Masks {
+    unsigned long long *rmask;        // [64] admissible columns of every row
+    unsigned long long *cmask;        // [64] admissible rows of every column
+    unsigned long long *comp_rows;    // [64] components found by prepare_components
+    unsigned long long *comp_cols;    // [64]
+    int *n_comp;                      // [1]
+    int *fallback;                    // [1] != 0: the component path does not apply / failed
+};
+
+__host__ __device__ inline size_t masks_bytes() { return sizeof(unsigned long long) * 64 * 4 + 16; }
+
+__device__ inline Masks carve_masks(unsigned char *p) {
+    Masks m;
+    m.rmask = reinterpret_cast<unsigned long long *>(p);
+    m.cmask = m.rmask + 64;
+    m.comp_rows = m.cmask + 64;
+    m.comp_cols = m.comp_rows + 64;
+    m.n_comp = reinterpret_cast<int *>(m.comp_cols + 64);
+    m.fallback = m.n_comp + 1;
+    return m;
+}
+
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// One warp builds the bitmasks from the dense matrix (the track kernel builds them while it
+// gathers the matrix; this is for the stand-alone batch entry).
+__device__ inline void build_masks(const Problem &P, const Masks &m) {
+    const int lane = threadIdx.x & 31;
+    const double L = 2.0 * P.half;
+    for (int i = lane; i < 64; i += 32) { m.rmask[i] = 0ull; m.cmask[i] = 0ull; }
+    __syncwarp();
+    for (int i = lane; i < P.R; i += 32) {
+        unsigned long long rm = 0ull;
+        for (int j = 0; j < P.C; ++j)
+            if ((double)P.cost[(long long)i * P.C + j] < L) { rm |= 1ull << j; atomicOr(&m.cmask[j], 1ull << i); }
+        m.rmask[i] = rm;
+    }
+    __syncwarp();
+}
+
+// Step 1, by ONE warp.  Writes x / y for the isolated pairs (-1 elsewhere), the component list
+// and the fallback flag.  P.adm_misc must be filled (NaN / near-limit screens).
+__device__ inline void prepare_components(const Problem &P, Scratch &s, const Masks &m) {
+    const int lane = threadIdx.x & 31;
+    const int R = P.R, C = P.C;
+    for (int j = lane; j < C; j += 32) s.y[j] = -1;
+    __syncwarp();
+    unsigned long long active = 0ull;
+    for (int half_ = 0; half_ < 2; ++half_) {
+        const int r = lane + 32 * half_;
+        bool act = false;
+        if (r < R) {
+            const unsigned long long rm = m.rmask[r];
+            int xr = -1;
+            if (rm) {
+                const int c = __ffsll((long long)rm) - 1;
+                if ((rm & (rm - 1)) == 0ull && m.cmask[c] == (1ull << r)) { xr = c; s.y[c] = r; }   // isolated pair
+                else act = true;
+            }
+            s.x[r] = xr;
+        }
+        active |= (unsigned long long)__ballot_sync(0xffffffffu, act) << (32 * half_);
+    }
+    __syncwarp();
+    bool fb = P.adm_misc[0] != 0 || P.adm_misc[1] != 0;
+    int n = 0;
+    unsigned long long remaining = active;
+    while (remaining) {
+        unsigned long long rows = remaining & (0ull - remaining), cols = 0ull;      // lowest row of the rest
+        for (int round = 0; round < 130; ++round) {
+            unsigned long long c0 = 0ull;
+            if ((rows >> lane) & 1ull) c0 |= m.rmask[lane];
+            if ((rows >> (lane + 32)) & 1ull) c0 |= m.rmask[lane + 32];
+            const unsigned long long ncols = warp_or64(c0);
+            unsigned long long r0 = 0ull;
+            if ((ncols >> lane) & 1ull) r0 |= m.cmask[lane];
+            if ((ncols >> (lane + 32)) & 1ull) r0 |= m.cmask[lane + 32];
+            const unsigned long long nrows = warp_or64(r0) | rows;
+            const bool same = nrows == rows && ncols == cols;
+            rows = nrows; cols = ncols;
+            if (same) break;
+        }
+        if (lane == 0) { m.comp_rows[n] = rows; m.comp_cols[n] = cols; }
+        if (__popcll(rows) > 4 || __popcll(cols) > 4) fb = true;
+        ++n;
+        remaining &= ~rows;
+    }
+    if (lane == 0) { *m.n_comp = n; *m.fallback = fb ? 1 : 0; }
+    __syncwarp();
+}
+
+// Step 2, by one warp per component: enumerate the partial matchings of a component of <= 4 rows
+// and <= 4 columns.  Writes x / y of its rows and columns when the optimum is unique; returns false
+// on a tie (within kFastEps).
+__device__ inline bool enumerate_component(const Problem &P, Scratch &s, unsigned long long rows, unsigned long long cols) {
+    const int lane = threadIdx.x & 31;
+    const double L = 2.0 * P.half, INF = 1.0e300;
+    int ri[4], ci[4];
+    const int k = __popcll(rows), mcols = __popcll(cols);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ri[i] = rows ? __ffsll((long long)rows) - 1 : 0;
+        rows &= rows - 1;
+        ci[i] = cols ? __ffsll((long long)cols) - 1 : 0;
+        cols &= cols - 1;
+    }
+    double a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double v = INF;
+            if (i < k && j < mcols) {
+                const double c = (double)P.cost[(long long)ri[i] * P.C + ci[j]];
+                if (c < L) v = c - L;
+            }
+            a[i][j] = v;
+        }
+    int total = 1;
+    for (int i = 0; i < k; ++i) total *= 5;
+    double best = INF, second = INF;
+    int best_code = -1;
+    for (int code = lane; code < total; code += 32) {
+        int t = code;
+        unsigned used = 0u;
+        double obj = 0.0;
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int dgt = t % 5;
+            t /= 5;
+            if (i < k && dgt) {
+                const int j = dgt - 1;
+                double v = INF;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) v = (jj == j) ? a[i][jj] : v;
+                if ((used >> j) & 1u || !(v < INF)) ok = false;
+                used |= 1u << j;
+                obj += v;
+            }
+        }
+        if (!ok) continue;
+        if (obj < best) { second = best; best = obj; best_code = code; }
+        else if (obj < second) second = obj;
+    }
+    const double B = warp_min(best);
+    const unsigned holders = __ballot_sync(0xffffffffu, best == B);
+    const int holder = __ffs(holders) - 1;
+    const double S = warp_min(lane == holder ? second : best);
+    const bool unique = __popc(holders) == 1 && (S - B) > kFastEps;
+    if (!unique) return false;
+    const int code = __shfl_sync(0xffffffffu, best_code, holder);
+    if (lane == 0) {
+        int t = code;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int dgt = t % 5;
+            t /= 5;
+            if (i < k) {
+                int c = -1;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) c = (dgt == jj + 1) ? ci[jj] : c;
+                s.x[ri[i]] = c;
+                if (c >= 0) s.y[c] = ri[i];
+            }
+        }
     }
     __syncwarp();
     return true;

@@ -18,6 +18,7 @@
     } while (0)
 
 int st_k2_configure(int max_candidates);    // k2_decode_nms.cu
+int st_k4v2_set_skip(int mask);             // k4_track2.cu
 
 static inline int st_last_launch() {
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
@@ -69,7 +70,9 @@ struct st_handle {
     int32_t *cand_prior;    // [S, N]
     int32_t *cand_label;    // [S, N]
     // K4/K5 workspace
-    float *cost;            // [S, T*D]
+    float *cost;            // [S, 3, T*D] all-pairs OCM / OCR costs and the dense matrix of a stage, when they
+                            // do not fit the tracker kernel's shared memory
+    int k4_version;         // 2 = k4_track2.cu (default), 1 = k4_track.cu (ST_K4_V1=1, or capacities beyond v2)
     void *all_mem;          // single allocation backing everything above
     size_t all_bytes;
 };

@@ -36,6 +36,7 @@ class _Det:
 def api():
     import torch
     from stereotracking_b200 import compat, mmtrack_api
+    from stereotracking_b200 import mmtrack_shell  # noqa: F401  (opt-in: registers OCSORT / OCSORT_Disparity)
     from oracle import disparity as odisp
     return dict(torch=torch, compat=compat, api=mmtrack_api, odisp=odisp)
 

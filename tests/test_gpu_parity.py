@@ -413,6 +413,51 @@ def test_lapjv_batch_matches_oracle(mods, R, C, ties):
         assert fallbacks > 0, 'tie cases must go through the exact emulation'
 
 
+@pytest.mark.parametrize('R,C,kind', [(1, 1, 'dense'), (7, 5, 'dense'), (30, 27, 'sparse'), (64, 64, 'sparse'),
+                                      (50, 60, 'ties'), (12, 12, 'dupes'), (40, 33, 'dense')])
+def test_lapjv_component_path_matches_oracle(mods, R, C, kind):
+    """The component path of the round-2 tracker kernel (isolated pairs, connected components of the
+    admissible graph, enumeration of components <= 4 x 4 with the uniqueness certificate from the
+    same enumeration; anything else falls back to the certified Hungarian / literal JV emulation)
+    against the JV oracle: tracking-shaped sparse problems, dense ones, exact ties, duplicate rows."""
+    rng = np.random.default_rng(R * 131 + C)
+    B = 48
+    if kind == 'sparse':
+        # most rows have one admissible column of their own, a few groups of 2-4 rows share columns
+        cost = rng.uniform(0.95, 1.3, (B, R, C)).astype(np.float32)
+        for b in range(B):
+            perm = rng.permutation(C)[:min(R, C)]
+            for r, c in enumerate(perm):
+                if rng.random() < 0.85:
+                    cost[b, r, c] = rng.uniform(0.05, 0.6)
+            for _ in range(rng.integers(0, 4)):
+                rows = rng.choice(R, rng.integers(2, 5), replace=False)
+                cols = rng.choice(C, rng.integers(2, 5), replace=False)
+                cost[b][np.ix_(rows, cols)] = rng.uniform(0.1, 0.88, (len(rows), len(cols)))
+    elif kind == 'ties':
+        cost = (rng.integers(0, 5, (B, R, C)) * 0.25).astype(np.float32)
+    elif kind == 'dupes':
+        cost = rng.uniform(0.95, 1.3, (B, R, C)).astype(np.float32)
+        cost[:, 0, 0] = cost[:, 1, 0] = cost[:, 0, 1] = cost[:, 1, 1] = 0.5      # two identical tracks / detections
+        cost[:, 2, 2] = 0.3
+    else:
+        cost = rng.uniform(0, 1.3, (B, R, C)).astype(np.float32)
+        cost[:, np.arange(min(R, C)), np.arange(min(R, C))] *= 0.2
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    ref = [mods.lapjv(cost[b], 0.9) for b in range(B)]
+    x, y = eng.lapjv_batch(cuda(cost), 0.9, mode=2)
+    assert eng.status().max() == 0
+    x, y = x.cpu().numpy(), y.cpu().numpy()
+    for b in range(B):
+        np.testing.assert_array_equal(y[b], ref[b][1], err_msg=f'problem {b}')
+        np.testing.assert_array_equal(x[b], ref[b][0], err_msg=f'problem {b}')
+    fallbacks = int(eng.debug_words()[0, 6])
+    if kind == 'sparse':
+        assert fallbacks < B // 2, 'tracking-shaped problems are solved by components'
+    if kind in ('ties', 'dupes'):
+        assert fallbacks > 0, 'ties must reach the exact emulation'
+
+
 # ---------------------------------------------------------------- tracker ---------
 @pytest.mark.parametrize('name', ['basic', 'occlusion', 'stress', 'cmc', 'defaults'])
 def test_tracker_matches_reference_fixture(mods, name):
