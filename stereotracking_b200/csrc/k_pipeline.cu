@@ -90,8 +90,9 @@ extern "C" int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *s
 //         frames in flight run concurrently (each slot has its own buffers and K2 scratch)
 //   track K4/K5 on the ONE tracker stream, frames strictly in order: the only stage with
 //         cross-frame state
-//   post  deflate + K3 on the tracks, on the post stream, in frame order
-// linked by per-slot events; a slot's buffers are reused once its previous frame has left post.
+//   post  deflate + K3 on the tracks, again on the ring slot's stream (so the post segments of
+//         consecutive frames overlap too, and the slot's next frame starts after it by stream order)
+// linked by per-slot events.  The tracker stream is the only resource frames queue for.
 // Results are identical to st_frame_step: the same kernels run on the same data in the same
 // per-frame order.
 //
@@ -102,7 +103,7 @@ extern "C" int st_frame_step(st_handle *h, int S, const st_frame_io *io, void *s
 // head maps) are not baked into the graphs: the kernels read them from a per-slot device table
 // (StFrameInputs) that a one-thread kernel updates in stream order when they change, so a
 // replay on new inputs costs no graph update.  Per frame the host then issues 2 graph launches,
-// 1 kernel launch and 6 event operations instead of ~13 launches and ~25 event operations.
+// 1 kernel launch and 4 event operations instead of ~13 launches and ~25 event operations.
 constexpr int kStages = 5;             // trace stages: K1, K2, K3 on dets, tracker, post
 
 struct GraphKey {                      // everything a captured segment bakes in
@@ -118,8 +119,8 @@ struct st_pipeline {
     int skip;                          // diagnostics (ST_PIPE_SKIP): bit i = leave stage i's kernels out
     long long submitted;
     cudaStream_t *pre, *side;          // [depth]
-    cudaStream_t trk, post;
-    cudaEvent_t *ev;                   // [5][depth]: pre done, tracker done, post done, K1 fork, K1 join
+    cudaStream_t trk;
+    cudaEvent_t *ev;                   // [4][depth]: pre done, tracker done, K1 fork, K1 join
     cudaEvent_t fork_ev;
     void *scratch_mem;                 // K2 candidate scratch of every slot + the input tables
     StK2Scratch *scratch;              // [depth]
@@ -132,7 +133,8 @@ struct st_pipeline {
     GraphKey *key;                     // [depth]
     long long n_graph_frames, n_captures;
     // optional timeline (st_pipeline_trace): begin / end timing events of every stage of the
-    // first trace_cap frames submitted after tracing was switched on (those run uncaptured)
+    // first trace_cap frames submitted after tracing was switched on (a frame replayed as graphs
+    // is stamped per segment: stages 0-2 all show the whole pre segment)
     cudaEvent_t *trace_ev;             // [trace_cap][kStages][2]
     cudaEvent_t trace_origin;
     int trace_cap, trace_n;
@@ -140,7 +142,7 @@ struct st_pipeline {
 
 namespace {
 
-enum { EV_PRE = 0, EV_TRK = 1, EV_POST = 2, EV_K1F = 3, EV_K1J = 4, EV_KINDS = 5 };
+enum { EV_PRE = 0, EV_TRK = 1, EV_K1F = 2, EV_K1J = 3, EV_KINDS = 4 };
 
 void fill_inputs(const st_frame_io *io, StFrameInputs *t) {
     memset(t, 0, sizeof(*t));
@@ -215,9 +217,10 @@ int seg_pre(st_pipeline *p, int slot, int S, const st_frame_io *io, bool traced)
 
 int seg_post(st_pipeline *p, int slot, int S, const st_frame_io *io) {
     st_handle *h = p->h;
-    int rc = st_scale_boxes(io->trk_boxes, io->out_scales, io->out_counts, S, h->cfg.max_dets, 1, io->out_boxes, p->post);
+    cudaStream_t st = p->pre[slot];
+    int rc = st_scale_boxes(io->trk_boxes, io->out_scales, io->out_counts, S, h->cfg.max_dets, 1, io->out_boxes, st);
     if (rc != ST_OK) return rc;
-    return k3_on_tracks(h, S, io, p->tab_dev + slot, p->post);
+    return k3_on_tracks(h, S, io, p->tab_dev + slot, st);
 }
 
 void drop_graphs(st_pipeline *p, int slot) {
@@ -245,12 +248,12 @@ int capture(st_pipeline *p, int slot, int S, const st_frame_io *io) {
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return ST_ERR_CUDA;
     g = nullptr;
-    if (cudaStreamBeginCapture(p->post, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    if (cudaStreamBeginCapture(p->pre[slot], cudaStreamCaptureModeRelaxed) != cudaSuccess) {
         cudaGraphExecDestroy(p->g_pre[slot]);
         return ST_ERR_CUDA;
     }
     rc = seg_post(p, slot, S, io);
-    e = cudaStreamEndCapture(p->post, &g);
+    e = cudaStreamEndCapture(p->pre[slot], &g);
     if (rc == ST_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&p->g_post[slot], g, 0);
     if (g) cudaGraphDestroy(g);
     if (rc != ST_OK || e != cudaSuccess) {
@@ -306,8 +309,7 @@ extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
         ok = cudaStreamCreateWithPriority(&p->pre[i], cudaStreamNonBlocking, hi) == cudaSuccess &&
              cudaStreamCreateWithPriority(&p->side[i], cudaStreamNonBlocking, lo) == cudaSuccess;
     }
-    ok = ok && cudaStreamCreateWithPriority(&p->trk, cudaStreamNonBlocking, hi) == cudaSuccess &&
-         cudaStreamCreateWithPriority(&p->post, cudaStreamNonBlocking, hi) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&p->trk, cudaStreamNonBlocking, hi) == cudaSuccess;
     for (int i = 0; ok && i < EV_KINDS * depth; ++i)
         ok = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming) == cudaSuccess;
     // K2 candidate scratch per slot (the pre segments of frames in flight run concurrently) and
@@ -330,7 +332,6 @@ extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
         // the auxiliary streams K3 forks onto exist before anything is captured
         cudaStream_t aux; cudaEvent_t e1, e2;
         for (int i = 0; ok && i < depth; ++i) ok = st_ctx_aux(p->pre[i], &aux, &e1, &e2) == ST_OK;
-        ok = ok && st_ctx_aux(p->post, &aux, &e1, &e2) == ST_OK;
     }
     if (!ok) { st_pipeline_destroy(p); return ST_ERR_CUDA; }
     *out = p;
@@ -351,7 +352,6 @@ extern "C" int st_pipeline_destroy(st_pipeline *p) {
             if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     if (p->fork_ev) cudaEventDestroy(p->fork_ev);
     if (p->trk) cudaStreamDestroy(p->trk);
-    if (p->post) cudaStreamDestroy(p->post);
     free_trace(p);
     if (p->scratch_mem) cudaFree(p->scratch_mem);
     delete[] p->pre; delete[] p->side; delete[] p->ev; delete[] p->scratch; delete[] p->tab_host;
@@ -379,7 +379,6 @@ extern "C" int st_pipeline_fork(st_pipeline *p, void *stream) {
     ST_CUDA_OK(cudaEventRecord(p->fork_ev, (cudaStream_t)stream));
     for (int i = 0; i < p->depth; ++i) ST_CUDA_OK(cudaStreamWaitEvent(p->pre[i], p->fork_ev, 0));
     ST_CUDA_OK(cudaStreamWaitEvent(p->trk, p->fork_ev, 0));
-    ST_CUDA_OK(cudaStreamWaitEvent(p->post, p->fork_ev, 0));
     return ST_OK;
 }
 
@@ -395,7 +394,7 @@ extern "C" int st_pipeline_join(st_pipeline *p, void *stream) {
         if (join(p->pre[i]) != ST_OK) return ST_ERR_CUDA;
         if (join(p->side[i]) != ST_OK) return ST_ERR_CUDA;
     }
-    if (join(p->trk) != ST_OK || join(p->post) != ST_OK) return ST_ERR_CUDA;
+    if (join(p->trk) != ST_OK) return ST_ERR_CUDA;
     return ST_OK;
 }
 
@@ -412,8 +411,7 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     const bool traced = p->trace_ev && p->trace_n < p->trace_cap;
     cudaStream_t pre = p->pre[slot];
     int rc;
-    // the buffer set of this slot is free once its previous frame left the post segment
-    if (reused) ST_CUDA_OK(cudaStreamWaitEvent(pre, ev(EV_POST), 0));
+    // (the buffer set of this slot is free: its previous frame's post segment ran on this stream)
     if (inputs_ready) ST_CUDA_OK(cudaStreamWaitEvent(pre, (cudaEvent_t)inputs_ready, 0));
     // the slot's input table follows the frame's input pointers (stream-ordered, parameters by value)
     StFrameInputs tab;
@@ -425,7 +423,7 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     }
     // graphs from the slot's second use on: the first pass warms up every lazy initialisation
     // (opt-ins, occupancy queries, auxiliary streams) outside of a capture
-    bool graph = p->use_graphs && reused && !traced && p->skip == 0;
+    bool graph = p->use_graphs && reused && p->skip == 0;
     if (graph) {
         GraphKey k;
         fill_key(io, S, &k);
@@ -436,8 +434,14 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
         }
     }
     // ---- pre: K1 | K2 -> K3 on the detections
-    if (graph) ST_CUDA_OK(cudaGraphLaunch(p->g_pre[slot], pre));
-    else if ((rc = seg_pre(p, slot, S, io, traced)) != ST_OK) return rc;
+    if (graph) {
+        // a replayed segment is time-stamped as a whole: stages 0 and 1 carry its begin, stage 2 its end
+        if (traced)
+            for (int st_ = 0; st_ < 3; ++st_) cudaEventRecord(p->trace_ev[(p->trace_n * kStages + st_) * 2 + 0], pre);
+        ST_CUDA_OK(cudaGraphLaunch(p->g_pre[slot], pre));
+        if (traced)
+            for (int st_ = 0; st_ < 3; ++st_) cudaEventRecord(p->trace_ev[(p->trace_n * kStages + st_) * 2 + 1], pre);
+    } else if ((rc = seg_pre(p, slot, S, io, traced)) != ST_OK) return rc;
     ST_CUDA_OK(cudaEventRecord(ev(EV_PRE), pre));
     // ---- the tracker, frames strictly in order on one stream
     ST_CUDA_OK(cudaStreamWaitEvent(p->trk, ev(EV_PRE), 0));
@@ -446,14 +450,13 @@ extern "C" int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, 
     if (rc != ST_OK) return rc;
     if (traced) cudaEventRecord(p->trace_ev[(p->trace_n * kStages + 3) * 2 + 1], p->trk);
     ST_CUDA_OK(cudaEventRecord(ev(EV_TRK), p->trk));
-    // ---- post: deflate and the output depth
-    ST_CUDA_OK(cudaStreamWaitEvent(p->post, ev(EV_TRK), 0));
-    if (traced) cudaEventRecord(p->trace_ev[(p->trace_n * kStages + 4) * 2 + 0], p->post);
-    if (graph) ST_CUDA_OK(cudaGraphLaunch(p->g_post[slot], p->post));
+    // ---- post: deflate and the output depth, back on the slot's stream
+    ST_CUDA_OK(cudaStreamWaitEvent(pre, ev(EV_TRK), 0));
+    if (traced) cudaEventRecord(p->trace_ev[(p->trace_n * kStages + 4) * 2 + 0], pre);
+    if (graph) ST_CUDA_OK(cudaGraphLaunch(p->g_post[slot], pre));
     else if ((rc = seg_post(p, slot, S, io)) != ST_OK) return rc;
-    if (traced) { cudaEventRecord(p->trace_ev[(p->trace_n * kStages + 4) * 2 + 1], p->post); p->trace_n += 1; }
-    ST_CUDA_OK(cudaEventRecord(ev(EV_POST), p->post));
-    if (frame_done) ST_CUDA_OK(cudaEventRecord((cudaEvent_t)frame_done, p->post));
+    if (traced) { cudaEventRecord(p->trace_ev[(p->trace_n * kStages + 4) * 2 + 1], pre); p->trace_n += 1; }
+    if (frame_done) ST_CUDA_OK(cudaEventRecord((cudaEvent_t)frame_done, pre));
     if (graph) p->n_graph_frames += 1;
     p->submitted += 1;
     return ST_OK;

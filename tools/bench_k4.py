@@ -1,0 +1,50 @@
+"""K4 micro-benchmark at the bench workload (C2, 64 sequences): the tracker kernel alone, launches
+back to back on one stream, on the detections K2 + K3 produce for consecutive frames.
+
+    python tools/bench_k4.py [frames=40]
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from stereotracking_b200.engine import EngineConfig, StereoTrackEngine  # noqa: E402
+from stereotracking_b200.synthetic import CONFIGS, SyntheticStereo  # noqa: E402
+
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+cfg, S = CONFIGS['C2'], 64
+gen = SyntheticStereo(cfg, S, F, seed=20240604 + 1000, device='cuda')
+parts = [gen.frames(f, min(f + 2, F)) for f in range(0, F, 2)]
+raw = torch.cat([p['raw'] for p in parts])
+heads = [[torch.cat([p[k][l] for p in parts]) for l in range(3)] for k in ('cls', 'bbox', 'obj')]
+eng = StereoTrackEngine(EngineConfig(n_seq=S, max_candidates=2048))
+Hp, Wp = cfg.padded_hw
+dets = []
+for f in range(F):
+    eng.decode_nms([c[f] for c in heads[0]], [c[f] for c in heads[1]], [c[f] for c in heads[2]], (cfg.height, cfg.width))
+    eng.box_depth_raw(raw[f], (Hp, Wp), eng.det_boxes, eng.det_counts, eng.det_depth, eng.det_scales, eng.det_inflated)
+    dets.append([t.clone() for t in (eng.det_inflated, eng.det_scores, eng.det_labels, eng.det_scales, eng.det_depth,
+                                     eng.det_counts)])
+fids = [torch.full((S,), f, dtype=torch.int32, device='cuda') for f in range(F)]
+torch.cuda.synchronize()
+out = {}
+for rep in range(3):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(F + 1)]
+    ev[0].record()
+    for f in range(F):
+        eng.track_step(fids[f], *dets[f])
+        ev[f + 1].record()
+    torch.cuda.synchronize()
+    us = np.array([ev[f].elapsed_time(ev[f + 1]) * 1e3 for f in range(F)])
+    out[f'rep{rep}'] = dict(total_us_per_frame=float(ev[0].elapsed_time(ev[F]) * 1e3 / F), median_us=float(np.median(us[8:])),
+                            max_us=float(us[8:].max()))
+dbg = eng.debug_words()
+out['phase_cycles_median'] = [int(x) for x in np.median(dbg[:, 8:14], axis=0)]
+out['phase_cycles_slowest'] = [int(x) for x in dbg[int(np.argmax(dbg[:, 8:14].sum(1))), 8:14]]
+out['sum_cycles_median_max'] = [int(np.median(dbg[:, 8:14].sum(1))), int(dbg[:, 8:14].sum(1).max())]
+print(json.dumps(out))

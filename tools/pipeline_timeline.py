@@ -2,7 +2,7 @@
 every stage of a few steady-state frames, from CUDA events on the stage streams
 (st_pipeline_trace).  Shows which stage waits for what.
 
-    python tools/pipeline_timeline.py [frames=12] [depth=5] [depth_source=map|raw]
+    python tools/pipeline_timeline.py [frames=12] [depth=5] [depth_source=map|raw] [graph=0|1]
 """
 import os
 import sys
@@ -19,7 +19,8 @@ from stereotracking_b200.synthetic import CONFIGS, SyntheticStereo  # noqa: E402
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 depth = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 source = sys.argv[3] if len(sys.argv) > 3 else 'map'
-cfg, S, W = CONFIGS['C2'], 64, 8
+graph = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+cfg, S, W = CONFIGS['C2'], 64, 24
 gen = SyntheticStereo(cfg, S, W + F, seed=20240604 + 1000, device='cuda')
 parts = [gen.frames(f, min(f + 2, W + F)) for f in range(0, W + F, 2)]
 raw = torch.cat([p['raw'] for p in parts])
@@ -27,7 +28,9 @@ heads = [[torch.cat([p[k][l] for p in parts]) for l in range(3)] for k in ('cls'
 fid = torch.arange(W + F, dtype=torch.int32, device='cuda')[:, None].repeat(1, S).contiguous()
 eng = StereoTrackEngine(EngineConfig(n_seq=S, max_candidates=2048))
 pipe = FramePipeline(eng, (S, cfg.height, cfg.width), [c.shape[-2:] for c in heads[0]], depth=depth, depth_source=source)
-print(f'depth_source={source} depth={depth}')
+if graph:
+    pipe.use_graphs(True)
+print(f'depth_source={source} depth={depth} graph={graph}' + (' (stages 0-2 = the whole pre segment)' if graph else ''))
 for f in range(W + F):
     if f == W:
         pipe.trace(F)
