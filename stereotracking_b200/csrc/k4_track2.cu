@@ -147,12 +147,44 @@ __device__ __forceinline__ void mean_to_box(float cx, float cy, float a, float h
     o[0] = __fsub_rn(cx, hw); o[1] = __fsub_rn(cy, hh); o[2] = __fadd_rn(cx, hw); o[3] = __fadd_rn(cy, hh);
 }
 
+// OCM cost of (track at order position p, input detection i) exactly as the reference evaluates it
+// (:187-258): 1 - IoU (x score) + vel_consist_weight * (acos(cos) - pi/2) / pi for rows with a
+// valid velocity and k-step observation.  `lazy`: when a cheap lower bound of the angle
+// (acos(x) >= sqrt(2 - 2x) for x > 0, >= pi/2 otherwise) already puts the cost above the
+// assignment's cost limit by 1e-4, that bound is returned instead - such an entry can never be
+// matched, and only the literal JV emulation (exact ties) looks at its value: associate2
+// re-evaluates the matrix exactly before it runs that path.  *lazy_used is set when a bound was returned.
+__device__ __forceinline__ float ocm_cost(const Params &pr, const Smem &sm, int p, int i, bool lazy, double limit,
+                                          int *lazy_used) {
+    const float *db = sm.in_box + i * 4;
+    float iou = iou_pair(sm.box_ocm + p * 4, db);
+    if (pr.weight_iou) iou = __fmul_rn(iou, sm.in_score[i]);
+    float dist = __fsub_rn(1.f, iou);
+    if (!sm.valid[p]) return dist;       // the term is +-0 * weight: adding it leaves dist unchanged
+    const float kHalfPi = 1.57079637f, kPi = 3.14159274f;
+    const float dcx = __fmul_rn(__fadd_rn(db[0], db[2]), 0.5f), dcy = __fmul_rn(__fadd_rn(db[1], db[3]), 0.5f);
+    float dy = __fsub_rn(dcy, sm.kc[p * 2 + 1]), dx = __fsub_rn(dcx, sm.kc[p * 2]);
+    const float norm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx))), 1e-6f);
+    dy = __fdiv_rn(dy, norm);
+    dx = __fdiv_rn(dx, norm);
+    float cs = __fadd_rn(__fmul_rn(dy, sm.vel[p * 2]), __fmul_rn(dx, sm.vel[p * 2 + 1]));
+    cs = cs < -1.f ? -1.f : (cs > 1.f ? 1.f : cs);
+    if (lazy && pr.vel_w > 0.f) {
+        const float ang_lb = cs > 0.f ? __fsqrt_rn(__fmul_rn(2.f, __fsub_rn(1.f, cs))) : kHalfPi;
+        const float lb = dist + pr.vel_w * ((ang_lb - kHalfPi) / kPi) - 1e-5f;      // below the exact cost
+        if ((double)lb > limit + 1e-4) { *lazy_used = 1; return lb; }
+    }
+    const float ang = st_acos_f32(cs);
+    const float na = __fdiv_rn(__fsub_rn(ang, kHalfPi), kPi);
+    return __fadd_rn(dist, __fmul_rn(na, pr.vel_w));
+}
+
 // One association stage: rows = order positions rows[0..R), columns = filtered columns
 // sm.scol[0..C); `ap` = the all-pairs matrix of this stage's cost kind (leading dimension C1).
 // The sub-matrix is gathered into `dense` together with its admissible-edge statistics, solved,
 // and the matches are scattered into det_pos / det_stage / hit.
 __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *status_word, const int *rows, int R, int C,
-                           const float *ap, int C1, float *dense, int stage_code) {
+                           const float *ap, int C1, float *dense, int stage_code, bool ocm_lazy) {
     if (R == 0 || C == 0) return;           // dists.size == 0 -> nothing matched (:263-265)
     const double lap_limit = 2.0 * pr.lap_half;
     const bool small = R <= 64 && C <= 64;
@@ -201,9 +233,28 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
         }
     }
     if (need_warp_path) {                                // block-uniform
+        // certified Hungarian on one warp; without its certificate (exact ties) the literal JV emulation
         if (warp == 0) {
-            const bool ok = stlap::assign_warp(P, sm.lap, dbg + 6);
-            if (!ok && threadIdx.x == 0) atomicOr(status_word, ST_STATUS_LAP_GUARD);
+            const bool ok = P.n <= 512 && stlap::fast_assign_warp(P, sm.lap);
+            if (threadIdx.x == 0) sm.adm_misc[3] = ok ? 1 : 0;
+        }
+        __syncthreads();
+        if (sm.adm_misc[3] == 0) {
+            if (ocm_lazy) {
+                // the emulation follows the reference's scan order through EVERY entry: entries that
+                // were only bounded from below get their exact value first
+                int dummy = 0;
+                for (int e = threadIdx.x; e < R * C; e += kThreads) {
+                    const int r = e / C, j = e - r * C;
+                    dense[e] = ocm_cost(pr, sm, rows[r], sm.dets[sm.scol[j]], false, lap_limit, &dummy);
+                }
+                __syncthreads();
+            }
+            if (warp == 0) {
+                if (threadIdx.x == 0) atomicAdd(&dbg[6], 1);     // solved by the exact fallback
+                const bool ok = stlap::solve_warp(P, sm.lap);
+                if (!ok && threadIdx.x == 0) atomicOr(status_word, ST_STATUS_LAP_GUARD);
+            }
         }
     }
     __syncthreads();
@@ -235,8 +286,15 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
     const int s = blockIdx.x;
     const int T = pr.T, D = pr.D;
     int32_t *dbg = st.debug + s * ST_DEBUG_WORDS;
-    // debug words 8..13: SM cycles the last step spent in each phase (thread 0's clock)
+    // debug words 8..13: SM cycles the last step spent in each phase (thread 0's clock); 20: cycles of
+    // the whole step, 21 / 22: low 32 bits of the global nanosecond timer at the CTA's start / end
     long long t_prev = clock64();
+    const long long t_begin = t_prev;
+    if (threadIdx.x == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        dbg[21] = (int)(unsigned)ns;
+    }
 #define ST_PHASE(idx)                                                         \
     do {                                                                      \
         if (threadIdx.x == 0) {                                               \
@@ -426,42 +484,28 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
             ap_ocm = gws; ap_ocr = gws + (long long)T * D; dense_sm = sm.cost; dense_cap = sm.cost_cap;
         }
         float *dense_g = gws + 2ll * T * D;
-        const float kHalfPi = 1.57079637f, kPi = 3.14159274f;
+        const bool lazy = !((g_skip >> 6) & 1);          // diagnostics bit 6: evaluate every entry exactly
+        const double lap_limit = 2.0 * pr.lap_half;
+        int lazy_used = 0;
         for (long long e = threadIdx.x; e < A; e += kThreads) {
             const int p = (int)(e / C1), c = (int)(e - (long long)p * C1);
             const int i = sm.dets[c];
-            const float *db = sm.in_box + i * 4;
-            float iou = iou_pair(sm.box_ocm + p * 4, db);
-            float iou2 = iou_pair(sm.box_ocr + p * 4, db);
-            if (pr.weight_iou) { iou = __fmul_rn(iou, sm.in_score[i]); iou2 = __fmul_rn(iou2, sm.in_score[i]); }
-            float dist = __fsub_rn(1.f, iou);
-            if (sm.valid[p]) {
-                // (an invalid row's term is +-0 * weight: adding it leaves dist unchanged, so it is skipped)
-                const float dcx = __fmul_rn(__fadd_rn(db[0], db[2]), 0.5f), dcy = __fmul_rn(__fadd_rn(db[1], db[3]), 0.5f);
-                float dy = __fsub_rn(dcy, sm.kc[p * 2 + 1]), dx = __fsub_rn(dcx, sm.kc[p * 2]);
-                const float norm = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx))), 1e-6f);
-                dy = __fdiv_rn(dy, norm);
-                dx = __fdiv_rn(dx, norm);
-                float cs = __fadd_rn(__fmul_rn(dy, sm.vel[p * 2]), __fmul_rn(dx, sm.vel[p * 2 + 1]));
-                cs = cs < -1.f ? -1.f : (cs > 1.f ? 1.f : cs);
-                const float ang = st_acos_f32(cs);
-                const float na = __fdiv_rn(__fsub_rn(ang, kHalfPi), kPi);
-                dist = __fadd_rn(dist, __fmul_rn(na, pr.vel_w));
-            }
-            ap_ocm[e] = dist;
+            ap_ocm[e] = ocm_cost(pr, sm, p, i, lazy, lap_limit, &lazy_used);
+            float iou2 = iou_pair(sm.box_ocr + p * 4, sm.in_box + i * 4);
+            if (pr.weight_iou) iou2 = __fmul_rn(iou2, sm.in_score[i]);
             ap_ocr[e] = __fsub_rn(1.f, iou2);
         }
-        // (the first barrier inside associate2 orders these writes before the gather)
+        const bool ocm_lazy = __syncthreads_or(lazy_used) != 0;
         // ---- stage 1: confirmed tracks vs filtered dets (:448-474)
         associate2(pr, sm, dbg, &st.status[s], sm.conf, Rc, C1, ap_ocm, C1,
-                   (long long)Rc * C1 <= dense_cap ? dense_sm : dense_g, 1);
+                   (long long)Rc * C1 <= dense_cap ? dense_sm : dense_g, 1, ocm_lazy);
         ST_PHASE(9);
         // ---- stage 2: tentative tracks vs leftovers (:476-503)
         if (warp == 0) compact_warp(C1, [&](int c) { return sm.det_stage[sm.dets[c]] == 4; }, sm.scol, &sh_cnt[3]);
         __syncthreads();
         const int C2 = sh_cnt[3];
         associate2(pr, sm, dbg, &st.status[s], sm.tentl, Rt, C2, ap_ocm, C1,
-                   (long long)Rt * C2 <= dense_cap ? dense_sm : dense_g, 2);
+                   (long long)Rt * C2 <= dense_cap ? dense_sm : dense_g, 2, ocm_lazy);
         ST_PHASE(10);
         // ---- stage 3: OCR, every unmatched track's last observation (:505-569)
         if (warp == 0) compact_warp(C1, [&](int c) { return sm.det_stage[sm.dets[c]] == 4; }, sm.scol, &sh_cnt[4]);
@@ -469,7 +513,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         __syncthreads();
         const int C3 = sh_cnt[4], R3 = sh_cnt[5];
         associate2(pr, sm, dbg, &st.status[s], sm.rows, R3, C3, ap_ocr, C1,
-                   (long long)R3 * C3 <= dense_cap ? dense_sm : dense_g, 3);
+                   (long long)R3 * C3 <= dense_cap ? dense_sm : dense_g, 3, false);
         ST_PHASE(11);
         // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582): plain stores
         for (int p = threadIdx.x; p < n_live; p += kThreads)
@@ -652,6 +696,10 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
             st.n_free[s] = n_free - n_create + freed;
             st.next_id[s] = id0 + n_new;
             out_counts[s] = n_out;
+            unsigned long long ns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+            dbg[20] = (int)(clock64() - t_begin);
+            dbg[22] = (int)(unsigned)ns;
         }
     }
 #undef ST_PHASE

@@ -496,6 +496,39 @@ def test_tracker_matches_reference_fixture(mods, name):
     assert eng.status().max() == 0
 
 
+def test_tracker_exact_ties_follow_the_jv_scan_order(mods):
+    """Duplicate detections (every box twice, identical scores) and duplicate tracks make exact
+    cost ties in all three stages: the component path and the certified Hungarian must both
+    refuse them, and the literal JV emulation - run on the exactly re-evaluated matrix, not on the
+    lazily bounded one - must reproduce the oracle's tie-breaks frame after frame."""
+    from oracle.tracker import OCSortDisparityOracle
+    g = np.load(os.path.join(GOLDEN, 'ref_track_occlusion.npz'))
+    cfg = dict(mods.StereoTrackOracle.DEFAULT_TRACKER)
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1, max_dets=128, max_tracks=256))
+    ref = OCSortDisparityOracle(**cfg)
+    rows = 0
+    for f in range(30):
+        n = int(g['det_count'][f])
+        boxes = np.repeat(g['det_boxes'][f, :n], 2, axis=0).astype(np.float32)         # every detection twice
+        scores = np.repeat(g['det_scores'][f, :n], 2).astype(np.float32)
+        m = len(boxes)
+        want = ref.track(f, boxes, scores, np.zeros(m, np.int64), np.ones(m, np.float32), np.zeros(m, np.float32))
+        eng.det_inflated.zero_(); eng.det_scores.zero_(); eng.det_labels.zero_(); eng.det_depth.zero_()
+        eng.det_inflated[0, :m] = cuda(boxes)
+        eng.det_scores[0, :m] = cuda(scores)
+        eng.det_scales.fill_(1.0)
+        eng.det_counts[0] = m
+        eng.frame_ids[0] = f
+        out = eng.track_step(eng.frame_ids, eng.det_inflated, eng.det_scores, eng.det_labels, eng.det_scales,
+                             eng.det_depth, eng.det_counts)
+        k = int(out['counts'][0])
+        np.testing.assert_array_equal(out['instances_id'][0, :k].cpu().numpy(), want['instances_id'], err_msg=f'frame {f}')
+        np.testing.assert_array_equal(out['bboxes'][0, :k].cpu().numpy(), want['bboxes'])
+        rows += k
+    assert rows > 200 and eng.status().max() == 0
+    assert int(eng.debug_words()[0, 6]) > 10, 'the exact emulation must have been needed'
+
+
 def test_snapshot_resume_continues_identically(mods):
     """Checkpoint / resume: a snapshot taken at frame 20 of the occlusion fixture, restored into the
     same engine and into a fresh one, continues with the same outputs and state as the

@@ -43,6 +43,21 @@ for rep in range(3):
     us = np.array([ev[f].elapsed_time(ev[f + 1]) * 1e3 for f in range(F)])
     out[f'rep{rep}'] = dict(total_us_per_frame=float(ev[0].elapsed_time(ev[F]) * 1e3 / F), median_us=float(np.median(us[8:])),
                             max_us=float(us[8:].max()))
+# one more pass, synchronised per frame: the CTAs' own start / end stamps against the event time of the launch
+span, evt, skew, longest = [], [], [], []
+for f in range(F):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.track_step(fids[f], *dets[f])
+    e1.record()
+    torch.cuda.synchronize()
+    d = eng.debug_words().astype(np.int64)
+    st_ns, en_ns = d[:, 21] & 0xffffffff, d[:, 22] & 0xffffffff
+    span.append(float((en_ns.max() - st_ns.min()) / 1e3)); evt.append(e0.elapsed_time(e1) * 1e3)
+    skew.append(float((st_ns.max() - st_ns.min()) / 1e3)); longest.append(float((en_ns - st_ns).max() / 1e3))
+out['per_launch_us_median'] = dict(event=float(np.median(evt[8:])), first_start_to_last_end=float(np.median(span[8:])),
+                                  start_skew=float(np.median(skew[8:])), longest_cta=float(np.median(longest[8:])),
+                                  total_cycles_max_last=int(d[:, 20].max()))
 dbg = eng.debug_words()
 out['phase_cycles_median'] = [int(x) for x in np.median(dbg[:, 8:14], axis=0)]
 out['phase_cycles_slowest'] = [int(x) for x in dbg[int(np.argmax(dbg[:, 8:14].sum(1))), 8:14]]
