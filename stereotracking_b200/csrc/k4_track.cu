@@ -624,6 +624,7 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
             stlap::build_masks(P, mk);
             stlap::prepare_components(P, sc, mk);
             bool bad = *mk.fallback != 0;
+            if (!bad) bad = !stlap::solve_big_components(P, sc, mk, reinterpret_cast<unsigned char *>(mk.fallback + 3));
             for (int k = 0; !bad && k < *mk.n_comp; ++k)
                 bad = !stlap::enumerate_component(P, sc, mk.comp_rows[k], mk.comp_cols[k]);
             ok = true;
@@ -813,8 +814,8 @@ extern "C" int st_create(const st_config *cfg, st_handle **out) {
     if (cudaFuncSetAttribute(k4_track_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(k5_lapjv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(stlap::scratch_bytes(cfg->max_tracks + cfg->max_dets) +
-                                   sizeof(int) * (2 * cfg->max_tracks + cfg->max_dets + 4) + 16 +
-                                   stlap::masks_bytes())) != cudaSuccess) {
+                                   sizeof(int) * (2 * cfg->max_tracks + cfg->max_dets + 4) + 32 +
+                                   stlap::masks_bytes() + stlap::sub_bytes())) != cudaSuccess) {
         cudaFree(h->all_mem); delete h; return ST_ERR_CAPACITY;
     }
     {
@@ -1051,7 +1052,8 @@ extern "C" int st_lapjv_batch(st_handle *h, int B, int R, int C, const float *co
         return ST_ERR_INVALID_ARG;
     StDeviceGuard guard(h->device);
     if (B == 0 || R + C == 0) return ST_OK;
-    k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C) + sizeof(int) * (2 * R + C + 4) + 16 + stlap::masks_bytes(),
+    k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C) + sizeof(int) * (2 * R + C + 4) + 32 + stlap::masks_bytes() +
+                            stlap::sub_bytes(),
                      (cudaStream_t)stream>>>(
         R, C, cost, cost_limit / 2.0, mode, row2col, col2row, h->st.status, h->st.debug + 6);
     return st_last_launch();

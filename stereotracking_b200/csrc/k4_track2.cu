@@ -63,6 +63,7 @@ struct Smem {
     int *rows;                   // [T] stage-3 row -> order position
     int *conf, *tentl;           // [T] confirmed / tentative order positions (stage-1 / stage-2 rows)
     int *row_cnt, *row_adm, *col_cnt, *adm_misc;
+    unsigned char *sub;          // scratch of the sub-problem made of the larger components (lapjv.cuh)
     float *cost;                 // [cost_cap]
     int cost_cap;
 };
@@ -73,6 +74,7 @@ __host__ __device__ inline size_t smem2_fixed_bytes(int T, int D) {
     b += align16(sizeof(float) * T * 4) * 3 + align16(sizeof(float) * T * 2) * 2;
     b += align16(sizeof(float) * D * 4) + align16(sizeof(float) * D) + align16(sizeof(int) * D) * 4 + align16(D);
     b += align16(sizeof(int) * T) * 5 + align16(sizeof(int) * D) + 16;
+    b += align16(stlap::sub_bytes());
     return b;
 }
 
@@ -119,6 +121,7 @@ __device__ inline Smem carve2(unsigned char *p, int T, int D, int cost_floats) {
     m.row_adm = reinterpret_cast<int *>(take(sizeof(int) * T));
     m.col_cnt = reinterpret_cast<int *>(take(sizeof(int) * D));
     m.adm_misc = reinterpret_cast<int *>(take(16));
+    m.sub = take(stlap::sub_bytes());
     m.cost = reinterpret_cast<float *>(p);
     m.cost_cap = cost_floats;
     return m;
@@ -189,6 +192,16 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
     const double lap_limit = 2.0 * pr.lap_half;
     const bool small = R <= 64 && C <= 64;
     const int warp = threadIdx.x >> 5;
+    // debug words 14..18 (stage 1 only): cycles of gather / components / solve / fallback / scatter
+    long long t_sub = clock64();
+#define ST_SUB(idx)                                                              \
+    do {                                                                         \
+        if (threadIdx.x == 0 && stage_code == 1) {                               \
+            const long long t_now = clock64();                                   \
+            dbg[(idx)] = (int)(t_now - t_sub);                                   \
+            t_sub = t_now;                                                       \
+        }                                                                        \
+    } while (0)
     for (int r = threadIdx.x; r < R; r += kThreads) { sm.row_cnt[r] = 0; sm.row_adm[r] = -1; }
     for (int c = threadIdx.x; c < C; c += kThreads) sm.col_cnt[c] = 0;
     if (threadIdx.x < 64) { sm.masks.rmask[threadIdx.x] = 0ull; sm.masks.cmask[threadIdx.x] = 0ull; }
@@ -209,6 +222,7 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
         if (fabs((double)dist - lap_limit) <= 2.0e-9) sm.adm_misc[1] = 1;
     }
     __syncthreads();
+    ST_SUB(14);
     stlap::Problem P;
     P.cost = dense; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
     P.dbg = nullptr;                                     // no progress marks on the critical path
@@ -222,16 +236,24 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
     } else if (small) {
         if (warp == 0) stlap::prepare_components(P, sm.lap, sm.masks);
         __syncthreads();
+        ST_SUB(15);
         if (*sm.masks.fallback == 0) {
             const int n_comp = *sm.masks.n_comp;
+            const bool has_big = sm.masks.big[0] != 0ull;
             bool bad = false;
-            for (int k = warp; k < n_comp; k += kWarps)
-                bad |= !stlap::enumerate_component(P, sm.lap, sm.masks.comp_rows[k], sm.masks.comp_cols[k]);
+            // warp 0 takes the larger components as one compact sub-problem (certified Hungarian) while
+            // the other warps enumerate the small ones
+            if (warp == 0 && has_big) bad = !stlap::solve_big_components(P, sm.lap, sm.masks, sm.sub);
+            const int first = has_big ? 1 : 0, nw = kWarps - first;
+            if (warp >= first)
+                for (int k = warp - first; k < n_comp; k += nw)
+                    bad |= !stlap::enumerate_component(P, sm.lap, sm.masks.comp_rows[k], sm.masks.comp_cols[k]);
             need_warp_path = __syncthreads_or(bad) != 0;
         } else {
             need_warp_path = true;
         }
     }
+    ST_SUB(16);
     if (need_warp_path) {                                // block-uniform
         // certified Hungarian on one warp; without its certificate (exact ties) the literal JV emulation
         if (warp == 0) {
@@ -258,6 +280,7 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
         }
     }
     __syncthreads();
+    ST_SUB(17);
     // col -> row; rows >= R are the solver's dummy rows (= unmatched)
     for (int j = threadIdx.x; j < C; j += kThreads) {
         const int r = sm.lap.y[j];
@@ -269,6 +292,8 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
         }
     }
     __syncthreads();
+    ST_SUB(18);
+#undef ST_SUB
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -290,7 +315,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
     // the whole step, 21 / 22: low 32 bits of the global nanosecond timer at the CTA's start / end
     long long t_prev = clock64();
     const long long t_begin = t_prev;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && ((g_skip >> 7) & 1)) {       // diagnostics bit 7: global-timer stamps of the CTA
         unsigned long long ns;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
         dbg[21] = (int)(unsigned)ns;
@@ -496,6 +521,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
             ap_ocr[e] = __fsub_rn(1.f, iou2);
         }
         const bool ocm_lazy = __syncthreads_or(lazy_used) != 0;
+        if (threadIdx.x == 0) dbg[19] = (int)(clock64() - t_prev);      // cycles of the all-pairs pass (t_prev = end of phase 8)
         // ---- stage 1: confirmed tracks vs filtered dets (:448-474)
         associate2(pr, sm, dbg, &st.status[s], sm.conf, Rc, C1, ap_ocm, C1,
                    (long long)Rc * C1 <= dense_cap ? dense_sm : dense_g, 1, ocm_lazy);
@@ -696,10 +722,12 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
             st.n_free[s] = n_free - n_create + freed;
             st.next_id[s] = id0 + n_new;
             out_counts[s] = n_out;
-            unsigned long long ns;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
             dbg[20] = (int)(clock64() - t_begin);
-            dbg[22] = (int)(unsigned)ns;
+            if ((g_skip >> 7) & 1) {
+                unsigned long long ns;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+                dbg[22] = (int)(unsigned)ns;
+            }
         }
     }
 #undef ST_PHASE

@@ -880,13 +880,16 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
 struct Masks {
     unsigned long long *rmask;        // [64] admissible columns of every row
     unsigned long long *cmask;        // [64] admissible rows of every column
-    unsigned long long *comp_rows;    // [64] components found by prepare_components
+    unsigned long long *comp_rows;    // [64] components of <= 4 x 4 found by prepare_components
     unsigned long long *comp_cols;    // [64]
-    int *n_comp;                      // [1]
+    unsigned long long *big;          // [2] union of the rows / columns of all larger components
+    int *n_comp;                      // [1] number of small components
     int *fallback;                    // [1] != 0: the component path does not apply / failed
 };
 
-__host__ __device__ inline size_t masks_bytes() { return sizeof(unsigned long long) * 64 * 4 + 16; }
+constexpr int kSubMax = 32;           // rows / columns of the sub-problem made of the larger components
+
+__host__ __device__ inline size_t masks_bytes() { return sizeof(unsigned long long) * (64 * 4 + 2) + 16; }
 
 __device__ inline Masks carve_masks(unsigned char *p) {
     Masks m;
@@ -894,7 +897,8 @@ __device__ inline Masks carve_masks(unsigned char *p) {
     m.cmask = m.rmask + 64;
     m.comp_rows = m.cmask + 64;
     m.comp_cols = m.comp_rows + 64;
-    m.n_comp = reinterpret_cast<int *>(m.comp_cols + 64);
+    m.big = m.comp_cols + 64;
+    m.n_comp = reinterpret_cast<int *>(m.big + 2);
     m.fallback = m.n_comp + 1;
     return m;
 }
@@ -947,7 +951,7 @@ __device__ inline void prepare_components(const Problem &P, Scratch &s, const Ma
     __syncwarp();
     bool fb = P.adm_misc[0] != 0 || P.adm_misc[1] != 0;
     int n = 0;
-    unsigned long long remaining = active;
+    unsigned long long remaining = active, big_rows = 0ull, big_cols = 0ull;
     while (remaining) {
         unsigned long long rows = remaining & (0ull - remaining), cols = 0ull;      // lowest row of the rest
         for (int round = 0; round < 130; ++round) {
@@ -963,12 +967,16 @@ __device__ inline void prepare_components(const Problem &P, Scratch &s, const Ma
             rows = nrows; cols = ncols;
             if (same) break;
         }
-        if (lane == 0) { m.comp_rows[n] = rows; m.comp_cols[n] = cols; }
-        if (__popcll(rows) > 4 || __popcll(cols) > 4) fb = true;
-        ++n;
+        if (__popcll(rows) > 4 || __popcll(cols) > 4) {
+            big_rows |= rows; big_cols |= cols;           // solved together as one compact sub-problem
+        } else {
+            if (lane == 0) { m.comp_rows[n] = rows; m.comp_cols[n] = cols; }
+            ++n;
+        }
         remaining &= ~rows;
     }
-    if (lane == 0) { *m.n_comp = n; *m.fallback = fb ? 1 : 0; }
+    if (__popcll(big_rows) > kSubMax || __popcll(big_cols) > kSubMax) fb = true;
+    if (lane == 0) { *m.n_comp = n; *m.fallback = fb ? 1 : 0; m.big[0] = big_rows; m.big[1] = big_cols; }
     __syncwarp();
 }
 
@@ -1047,6 +1055,60 @@ __device__ inline bool enumerate_component(const Problem &P, Scratch &s, unsigne
                 if (c >= 0) s.y[c] = ri[i];
             }
         }
+    }
+    __syncwarp();
+    return true;
+}
+
+// The components larger than 4 x 4 (rare: crowded groups) as ONE compact sub-problem of at most
+// kSubMax x kSubMax, solved by the certified Hungarian on one warp while the other warps enumerate
+// the small components.  Rows of these components have admissible entries only in their own
+// columns, so the sub-problem's unique optimum is the restriction of the whole problem's.
+// `sub`: scratch of the sub-problem (n = 2 * kSubMax), `sub_cost` [kSubMax * kSubMax] floats,
+// `sub_idx` [4 * kSubMax + 4] ints (row / column lists and the admissible-edge statistics).
+// Writes x / y of the whole problem for its rows and columns; false = no certificate.
+__host__ __device__ inline size_t sub_bytes() {
+    return scratch_bytes(2 * kSubMax) + sizeof(float) * kSubMax * kSubMax + sizeof(int) * (5 * kSubMax + 4);
+}
+
+__device__ inline bool solve_big_components(const Problem &P, Scratch &s, const Masks &m, unsigned char *sub_mem) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long rows = m.big[0], cols = m.big[1];
+    if (!rows) return true;
+    Scratch sub = carve(sub_mem, 2 * kSubMax);
+    float *sub_cost = reinterpret_cast<float *>(sub_mem + scratch_bytes(2 * kSubMax));
+    int *lrow = reinterpret_cast<int *>(sub_cost + kSubMax * kSubMax), *lcol = lrow + kSubMax;
+    Problem Q;
+    Q.R = __popcll(rows); Q.C = __popcll(cols); Q.n = Q.R + Q.C; Q.half = P.half; Q.dbg = nullptr;
+    Q.cost = sub_cost;
+    Q.row_cnt = lcol + kSubMax; Q.row_adm = Q.row_cnt + kSubMax; Q.col_cnt = Q.row_adm + kSubMax;
+    Q.adm_misc = Q.col_cnt + kSubMax;
+    // lane l takes the l-th row and the l-th column of the sets
+    if (lane < Q.R) {
+        unsigned long long t = rows;
+        for (int k = 0; k < lane; ++k) t &= t - 1;
+        lrow[lane] = __ffsll((long long)t) - 1;
+    }
+    if (lane < Q.C) {
+        unsigned long long t = cols;
+        for (int k = 0; k < lane; ++k) t &= t - 1;
+        lcol[lane] = __ffsll((long long)t) - 1;
+    }
+    __syncwarp();
+    for (int e = lane; e < Q.R * Q.C; e += 32) {
+        const int i = e / Q.C, j = e - i * Q.C;
+        sub_cost[e] = P.cost[(long long)lrow[i] * P.C + lcol[j]];
+    }
+    __syncwarp();
+    count_admissible(Q);
+    if (!fast_assign_warp(Q, sub)) return false;
+    if (lane < Q.R) {
+        const int j = sub.x[lane];
+        s.x[lrow[lane]] = (j >= 0 && j < Q.C) ? lcol[j] : -1;
+    }
+    if (lane < Q.C) {
+        const int i = sub.y[lane];
+        s.y[lcol[lane]] = (i >= 0 && i < Q.R) ? lrow[i] : -1;
     }
     __syncwarp();
     return true;

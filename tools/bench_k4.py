@@ -45,6 +45,7 @@ for rep in range(3):
                             max_us=float(us[8:].max()))
 # one more pass, synchronised per frame: the CTAs' own start / end stamps against the event time of the launch
 span, evt, skew, longest = [], [], [], []
+eng.lib.st_debug_set_skip(128)          # diagnostics bit 7: global-timer stamps
 for f in range(F):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -58,7 +59,15 @@ for f in range(F):
 out['per_launch_us_median'] = dict(event=float(np.median(evt[8:])), first_start_to_last_end=float(np.median(span[8:])),
                                   start_skew=float(np.median(skew[8:])), longest_cta=float(np.median(longest[8:])),
                                   total_cycles_max_last=int(d[:, 20].max()))
+eng.lib.st_debug_set_skip(0)
+for f in range(F):
+    eng.track_step(fids[f], *dets[f])
+torch.cuda.synchronize()
 dbg = eng.debug_words()
+worst = int(np.argmax(dbg[:, 8:14].sum(1)))
+out['stage1_subphases'] = dict(names=['allpairs', 'gather', 'components', 'solve', 'fallback', 'scatter'],
+                               median=[int(x) for x in np.median(dbg[:, [19, 14, 15, 16, 17, 18]], axis=0)],
+                               slowest=[int(x) for x in dbg[worst, [19, 14, 15, 16, 17, 18]]])
 out['phase_cycles_median'] = [int(x) for x in np.median(dbg[:, 8:14], axis=0)]
 out['phase_cycles_slowest'] = [int(x) for x in dbg[int(np.argmax(dbg[:, 8:14].sum(1))), 8:14]]
 out['sum_cycles_median_max'] = [int(np.median(dbg[:, 8:14].sum(1))), int(dbg[:, 8:14].sum(1).max())]
