@@ -17,6 +17,10 @@ struct Params {
     float obj_score_thr, init_track_thr, vel_w;
     int weight_iou, num_tentatives, vel_dt, retain;
     double lap_half;             // (1 - match_iou_thr) / 2
+    // screen of the round-2 kernel for pairs without overlap (k4_track2.cu ocm_cost): a pair whose
+    // direction cosine is below screen_cos cannot cost less than the limit + 1e-4; such entries get
+    // `placeholder` (-2 = screen off)
+    float screen_cos, placeholder;
 };
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }

@@ -14,6 +14,7 @@
 // Track state lives in the handle as a structure of arrays; `order` keeps the
 // live slots in ascending-id order, which is the reference's dict order.
 #include <new>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include "st_common.cuh"
@@ -963,6 +964,18 @@ extern "C" int st_track_step(st_handle *h, int S, const int32_t *frame_ids, cons
     pr.retain = h->cfg.num_frames_retain;
     // lap.lapjv(cost_limit = 1 - match_iou_thr): Python float arithmetic on the config value
     pr.lap_half = (1.0 - h->cfg.match_iou_thr) / 2.0;
+    {
+        // a pair with IoU 0 costs 1 + w (angle - pi/2) / pi: above limit + 2e-4 as soon as the angle exceeds
+        // a_req, i.e. its cosine is below cos(a_req)
+        const double L = 2.0 * pr.lap_half, w = (double)pr.vel_w, pi = 3.14159265358979323846;
+        pr.screen_cos = -2.f;
+        pr.placeholder = (float)(L + 1e-3);
+        if (w > 0.0 && w < 1e6) {
+            const double a_req = pi / 2 + pi * (L + 2e-4 - 1.0) / w;
+            if (a_req <= 0.0) pr.screen_cos = 2.f;
+            else if (a_req < pi) pr.screen_cos = (float)(cos(a_req) - 1e-4);
+        }
+    }
     if (h->k4_version == 2)
         return st_k4v2_launch(h, pr, S, frame_ids, det_boxes, det_scores, det_labels, det_scales, det_depth, det_counts,
                               det_cap, out_boxes, out_scores, out_labels, out_scales, out_depth, out_ids, out_counts,

@@ -152,15 +152,38 @@ __device__ __forceinline__ void mean_to_box(float cx, float cy, float a, float h
 
 // OCM cost of (track at order position p, input detection i) exactly as the reference evaluates it
 // (:187-258): 1 - IoU (x score) + vel_consist_weight * (acos(cos) - pi/2) / pi for rows with a
-// valid velocity and k-step observation.  `lazy`: when a cheap lower bound of the angle
-// (acos(x) >= sqrt(2 - 2x) for x > 0, >= pi/2 otherwise) already puts the cost above the
-// assignment's cost limit by 1e-4, that bound is returned instead - such an entry can never be
-// matched, and only the literal JV emulation (exact ties) looks at its value: associate2
-// re-evaluates the matrix exactly before it runs that path.  *lazy_used is set when a bound was returned.
-__device__ __forceinline__ float ocm_cost(const Params &pr, const Smem &sm, int p, int i, bool lazy, double limit,
-                                          int *lazy_used) {
-    const float *db = sm.in_box + i * 4;
-    float iou = iou_pair(sm.box_ocm + p * 4, db);
+// valid velocity and k-step observation.
+// `lazy`: most pairs of a frame do not overlap at all.  For such a pair IoU is exactly 0, the cost is
+// 1 + w (angle - pi/2) / pi, and it can only come near the assignment's cost limit when the
+// detection lies almost exactly in the track's direction of motion: if the direction cosine
+// (one approximate square root, no division) is below pr.screen_cos the cost exceeds the limit by
+// more than 1e-4 whatever its last bits are, and pr.placeholder is returned instead.  Such an
+// entry can never be matched, and only the literal JV emulation (exact ties) looks at its value:
+// associate2 re-evaluates the matrix exactly before it runs that path.  *lazy_used is set when a
+// placeholder was returned.  (The all-pairs pass was issue-bound on the five IEEE divisions, two
+// square roots and the float64 acos per pair; a screened pair costs ~30 instructions.)
+__device__ __forceinline__ float ocm_cost(const Params &pr, const Smem &sm, int p, int i, bool lazy, int *lazy_used) {
+    const float *tb = sm.box_ocm + p * 4, *db = sm.in_box + i * 4;
+    if (lazy) {
+        float w = __fsub_rn(fminf(tb[2], db[2]), fmaxf(tb[0], db[0]));
+        float h = __fsub_rn(fminf(tb[3], db[3]), fmaxf(tb[1], db[1]));
+        w = w < 0.f ? 0.f : w;
+        h = h < 0.f ? 0.f : h;
+        const float inter = __fmul_rn(w, h);
+        const float a12 = __fadd_rn(__fmul_rn(__fsub_rn(tb[2], tb[0]), __fsub_rn(tb[3], tb[1])),
+                                    __fmul_rn(__fsub_rn(db[2], db[0]), __fsub_rn(db[3], db[1])));
+        const float sc = pr.weight_iou ? sm.in_score[i] : 1.f;
+        // inter == 0 with a finite union and score: IoU (x score) is exactly +-0 and 1 - it exactly 1
+        if (inter == 0.f && fabsf(a12) < 3.0e38f && fabsf(sc) < 3.0e38f) {
+            if (!sm.valid[p]) return 1.f;                 // no direction term: this IS the exact cost
+            const float dcx = __fmul_rn(__fadd_rn(db[0], db[2]), 0.5f), dcy = __fmul_rn(__fadd_rn(db[1], db[3]), 0.5f);
+            const float dy = __fsub_rn(dcy, sm.kc[p * 2 + 1]), dx = __fsub_rn(dcx, sm.kc[p * 2]);
+            const float dot = dy * sm.vel[p * 2] + dx * sm.vel[p * 2 + 1];
+            const float norm = sqrtf(dy * dy + dx * dx) + 1e-6f;
+            if (dot < pr.screen_cos * norm) { *lazy_used = 1; return pr.placeholder; }
+        }
+    }
+    float iou = iou_pair(tb, db);
     if (pr.weight_iou) iou = __fmul_rn(iou, sm.in_score[i]);
     float dist = __fsub_rn(1.f, iou);
     if (!sm.valid[p]) return dist;       // the term is +-0 * weight: adding it leaves dist unchanged
@@ -172,18 +195,15 @@ __device__ __forceinline__ float ocm_cost(const Params &pr, const Smem &sm, int 
     dx = __fdiv_rn(dx, norm);
     float cs = __fadd_rn(__fmul_rn(dy, sm.vel[p * 2]), __fmul_rn(dx, sm.vel[p * 2 + 1]));
     cs = cs < -1.f ? -1.f : (cs > 1.f ? 1.f : cs);
-    if (lazy && pr.vel_w > 0.f) {
-        const float ang_lb = cs > 0.f ? __fsqrt_rn(__fmul_rn(2.f, __fsub_rn(1.f, cs))) : kHalfPi;
-        const float lb = dist + pr.vel_w * ((ang_lb - kHalfPi) / kPi) - 1e-5f;      // below the exact cost
-        if ((double)lb > limit + 1e-4) { *lazy_used = 1; return lb; }
-    }
     const float ang = st_acos_f32(cs);
     const float na = __fdiv_rn(__fsub_rn(ang, kHalfPi), kPi);
     return __fadd_rn(dist, __fmul_rn(na, pr.vel_w));
 }
 
 // One association stage: rows = order positions rows[0..R), columns = filtered columns
-// sm.scol[0..C); `ap` = the all-pairs matrix of this stage's cost kind (leading dimension C1).
+// sm.scol[0..C); `ap` = the all-pairs OCM matrix (leading dimension C1), or nullptr for the
+// observation-centric recovery, whose cost 1 - IoU(last observation, detection) (:273-308) is
+// evaluated right here (its rows and columns are the few left over after stages 1 and 2).
 // The sub-matrix is gathered into `dense` together with its admissible-edge statistics, solved,
 // and the matches are scattered into det_pos / det_stage / hit.
 __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *status_word, const int *rows, int R, int C,
@@ -209,7 +229,14 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
     __syncthreads();
     for (int e = threadIdx.x; e < R * C; e += kThreads) {
         const int r = e / C, j = e - r * C;
-        const float dist = ap[(long long)rows[r] * C1 + sm.scol[j]];
+        float dist;
+        if (ap) dist = ap[(long long)rows[r] * C1 + sm.scol[j]];
+        else {
+            const int i = sm.dets[sm.scol[j]];
+            float iou = iou_pair(sm.box_ocr + rows[r] * 4, sm.in_box + i * 4);
+            if (pr.weight_iou) iou = __fmul_rn(iou, sm.in_score[i]);
+            dist = __fsub_rn(1.f, iou);
+        }
         dense[e] = dist;
         // admissible-edge statistics for the assignment (lapjv.cuh)
         if ((double)dist < lap_limit) {
@@ -268,7 +295,7 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
                 int dummy = 0;
                 for (int e = threadIdx.x; e < R * C; e += kThreads) {
                     const int r = e / C, j = e - r * C;
-                    dense[e] = ocm_cost(pr, sm, rows[r], sm.dets[sm.scol[j]], false, lap_limit, &dummy);
+                    dense[e] = ocm_cost(pr, sm, rows[r], sm.dets[sm.scol[j]], false, &dummy);
                 }
                 __syncthreads();
             }
@@ -301,7 +328,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
                const float *__restrict__ det_boxes, const float *__restrict__ det_scores,
                const int64_t *__restrict__ det_labels, const float *__restrict__ det_scales,
                const float *__restrict__ det_depth, const int32_t *__restrict__ det_counts, int det_cap,
-               float *cost_ws /* [S, 3, T*D]: written and re-read in this kernel: no __restrict__ */,
+               float *cost_ws /* [S, 3, T*D] (two thirds used): written and re-read in this kernel: no __restrict__ */,
                float *__restrict__ out_boxes, float *__restrict__ out_scores, int64_t *__restrict__ out_labels,
                float *__restrict__ out_scales, float *__restrict__ out_depth, int64_t *__restrict__ out_ids,
                int32_t *__restrict__ out_counts, int32_t *__restrict__ out_src_g /* may be null */,
@@ -330,7 +357,6 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
     } while (0)
     Smem sm = carve2(smem_raw, T, D, cost_floats);
     const long long sbase = (long long)s * T;
-    const int frame = frame_ids[s];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int32_t *order = st.order + sbase;
     int32_t *free_slots = st.free_slots + sbase;
@@ -340,7 +366,21 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
     const int64_t *g_labels = det_labels + (long long)s * det_cap;
     const float *g_scales = det_scales + (long long)s * det_cap;
     const float *g_depth = det_depth + (long long)s * det_cap;
+    // ---- the frame's working set: three rounds of independent loads ---------------------------
+    // round 1: everything whose address does not depend on another load - the per-sequence
+    // scalars, and speculatively this thread's `order` entry and detection row (the counts that say
+    // whether they are live arrive in the same round; a stale entry is in bounds and is dropped)
+    const int frame = frame_ids[s];
     int nd_in = det_counts[s];
+    const int n_live_g = st.n_live[s], n_free_g = st.n_free[s];
+    const long long id0_g = st.next_id[s];
+    const int slot_spec = threadIdx.x < T ? order[threadIdx.x] : 0;
+    float4 det_spec = make_float4(0.f, 0.f, 0.f, 0.f);
+    float score_spec = 0.f;
+    if (threadIdx.x < det_cap && threadIdx.x < D) {
+        det_spec = reinterpret_cast<const float4 *>(g_boxes)[threadIdx.x];
+        score_spec = g_scores[threadIdx.x];
+    }
     if (nd_in > D) {
         if (threadIdx.x == 0) atomicOr(&st.status[s], ST_STATUS_DET_OVERFLOW);
         nd_in = D;
@@ -354,18 +394,19 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         for (int i = threadIdx.x; i < T; i += kThreads) free_slots[i] = T - 1 - i;
         n_live = 0; n_free = T; id0 = 0;
     } else {
-        n_live = st.n_live[s]; n_free = st.n_free[s]; id0 = st.next_id[s];
+        n_live = n_live_g; n_free = n_free_g; id0 = id0_g;
     }
-    // ---- the frame's working set, one round of loads ------------------------------------------
     for (int i = threadIdx.x; i < nd_in; i += kThreads) {
         sm.det_pos[i] = -1;
         sm.det_stage[i] = 0;
-        const float4 b = reinterpret_cast<const float4 *>(g_boxes)[i];
+        const float4 b = i < kThreads ? det_spec : reinterpret_cast<const float4 *>(g_boxes)[i];
         sm.in_box[i * 4 + 0] = b.x; sm.in_box[i * 4 + 1] = b.y; sm.in_box[i * 4 + 2] = b.z; sm.in_box[i * 4 + 3] = b.w;
-        sm.in_score[i] = g_scores[i];
+        sm.in_score[i] = i < kThreads ? score_spec : g_scores[i];
     }
+    // rounds 2 and 3: the per-track scalars (addresses from the slot), then the two ring entries
+    // (addresses from the observation count)
     for (int p = threadIdx.x; p < n_live; p += kThreads) {
-        const int slot = order[p];
+        const int slot = p < kThreads ? slot_spec : order[p];
         const long long g = sbase + slot;
         const int n = st.num_obs[g];
         const int tent = st.tentative[g];
@@ -498,27 +539,22 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
             __syncthreads();
         }
         ST_PHASE(8);
-        // ---- all-pairs association costs: OCM (:187-258) and OCR (:273-308) for every live track
-        // against every filtered detection, float32 in the reference's evaluation order
+        // ---- all-pairs OCM costs (:187-258): every live track against every filtered detection, float32
+        // in the reference's evaluation order (stage 1 takes the confirmed rows, stage 2 the tentative ones)
         const long long A = (long long)n_live * C1;
-        float *ap_ocm, *ap_ocr, *dense_sm;
+        float *ap_ocm, *dense_sm;
         int dense_cap;
-        if (2 * A <= sm.cost_cap) {
-            ap_ocm = sm.cost; ap_ocr = sm.cost + A; dense_sm = sm.cost + 2 * A; dense_cap = sm.cost_cap - (int)(2 * A);
+        if (A <= sm.cost_cap) {
+            ap_ocm = sm.cost; dense_sm = sm.cost + A; dense_cap = sm.cost_cap - (int)A;
         } else {
-            ap_ocm = gws; ap_ocr = gws + (long long)T * D; dense_sm = sm.cost; dense_cap = sm.cost_cap;
+            ap_ocm = gws; dense_sm = sm.cost; dense_cap = sm.cost_cap;
         }
-        float *dense_g = gws + 2ll * T * D;
-        const bool lazy = !((g_skip >> 6) & 1);          // diagnostics bit 6: evaluate every entry exactly
-        const double lap_limit = 2.0 * pr.lap_half;
+        float *dense_g = gws + (long long)T * D;
+        const bool lazy = !((g_skip >> 6) & 1) && pr.screen_cos > -1.5f;   // diagnostics bit 6: evaluate every entry exactly
         int lazy_used = 0;
         for (long long e = threadIdx.x; e < A; e += kThreads) {
             const int p = (int)(e / C1), c = (int)(e - (long long)p * C1);
-            const int i = sm.dets[c];
-            ap_ocm[e] = ocm_cost(pr, sm, p, i, lazy, lap_limit, &lazy_used);
-            float iou2 = iou_pair(sm.box_ocr + p * 4, sm.in_box + i * 4);
-            if (pr.weight_iou) iou2 = __fmul_rn(iou2, sm.in_score[i]);
-            ap_ocr[e] = __fsub_rn(1.f, iou2);
+            ap_ocm[e] = ocm_cost(pr, sm, p, sm.dets[c], lazy, &lazy_used);
         }
         const bool ocm_lazy = __syncthreads_or(lazy_used) != 0;
         if (threadIdx.x == 0) dbg[19] = (int)(clock64() - t_prev);      // cycles of the all-pairs pass (t_prev = end of phase 8)
@@ -538,7 +574,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         else if (warp == 1) compact_warp(n_live, [&](int p) { return !sm.hit[p]; }, sm.rows, &sh_cnt[5]);
         __syncthreads();
         const int C3 = sh_cnt[4], R3 = sh_cnt[5];
-        associate2(pr, sm, dbg, &st.status[s], sm.rows, R3, C3, ap_ocr, C1,
+        associate2(pr, sm, dbg, &st.status[s], sm.rows, R3, C3, nullptr, C1,
                    (long long)R3 * C3 <= dense_cap ? dense_sm : dense_g, 3, false);
         ST_PHASE(11);
         // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582): plain stores

@@ -926,54 +926,87 @@ __device__ inline void build_masks(const Problem &P, const Masks &m) {
 }
 
 // Step 1, by ONE warp.  Writes x / y for the isolated pairs (-1 elsewhere), the component list
-// and the fallback flag.  P.adm_misc must be filled (NaN / near-limit screens).
+// and the fallback flag.  P.adm_misc must be filled (NaN / near-limit screens).  Components by
+// min-label propagation: every active row starts with its own index, a column takes the minimum
+// label of its rows, a row the minimum of its columns, until nothing changes (rounds ~ diameter of
+// the largest component, two rows per lane); rows with equal labels form a component.
 __device__ inline void prepare_components(const Problem &P, Scratch &s, const Masks &m) {
     const int lane = threadIdx.x & 31;
     const int R = P.R, C = P.C;
     for (int j = lane; j < C; j += 32) s.y[j] = -1;
     __syncwarp();
-    unsigned long long active = 0ull;
-    for (int half_ = 0; half_ < 2; ++half_) {
-        const int r = lane + 32 * half_;
-        bool act = false;
+    unsigned long long rm[2], cm[2];
+    int label[2];
+    bool act[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r = lane + 32 * h;
+        rm[h] = r < R ? m.rmask[r] : 0ull;
+        cm[h] = r < C ? m.cmask[r] : 0ull;            // (this lane's two columns)
+        act[h] = false;
         if (r < R) {
-            const unsigned long long rm = m.rmask[r];
             int xr = -1;
-            if (rm) {
-                const int c = __ffsll((long long)rm) - 1;
-                if ((rm & (rm - 1)) == 0ull && m.cmask[c] == (1ull << r)) { xr = c; s.y[c] = r; }   // isolated pair
-                else act = true;
+            if (rm[h]) {
+                const int c = __ffsll((long long)rm[h]) - 1;
+                if ((rm[h] & (rm[h] - 1)) == 0ull && m.cmask[c] == (1ull << r)) { xr = c; s.y[c] = r; }   // isolated pair
+                else act[h] = true;
             }
             s.x[r] = xr;
         }
-        active |= (unsigned long long)__ballot_sync(0xffffffffu, act) << (32 * half_);
+        label[h] = act[h] ? r : 64;
     }
-    __syncwarp();
     bool fb = P.adm_misc[0] != 0 || P.adm_misc[1] != 0;
-    int n = 0;
-    unsigned long long remaining = active, big_rows = 0ull, big_cols = 0ull;
-    while (remaining) {
-        unsigned long long rows = remaining & (0ull - remaining), cols = 0ull;      // lowest row of the rest
-        for (int round = 0; round < 130; ++round) {
-            unsigned long long c0 = 0ull;
-            if ((rows >> lane) & 1ull) c0 |= m.rmask[lane];
-            if ((rows >> (lane + 32)) & 1ull) c0 |= m.rmask[lane + 32];
-            const unsigned long long ncols = warp_or64(c0);
-            unsigned long long r0 = 0ull;
-            if ((ncols >> lane) & 1ull) r0 |= m.cmask[lane];
-            if ((ncols >> (lane + 32)) & 1ull) r0 |= m.cmask[lane + 32];
-            const unsigned long long nrows = warp_or64(r0) | rows;
-            const bool same = nrows == rows && ncols == cols;
-            rows = nrows; cols = ncols;
-            if (same) break;
+    // labels live in registers; a lane reads another row's / column's label by shuffle
+    int clab[2] = {64, 64};
+    for (int round = 0; round < 130; ++round) {
+        // column labels: minimum over the column's rows
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            unsigned long long t = cm[h];
+            int best = 64;
+            // all lanes step together: the shuffles need every lane, so iterate to the longest set
+            int steps = __reduce_max_sync(0xffffffffu, __popcll(t));
+            for (int k = 0; k < steps; ++k) {
+                const int r = t ? __ffsll((long long)t) - 1 : 0;
+                const int l0 = __shfl_sync(0xffffffffu, label[0], r & 31), l1 = __shfl_sync(0xffffffffu, label[1], r & 31);
+                if (t) best = min(best, r < 32 ? l0 : l1);
+                t &= t - 1;
+            }
+            clab[h] = best;
         }
+        bool changed = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            unsigned long long t = act[h] ? rm[h] : 0ull;
+            int best = label[h];
+            int steps = __reduce_max_sync(0xffffffffu, __popcll(t));
+            for (int k = 0; k < steps; ++k) {
+                const int c = t ? __ffsll((long long)t) - 1 : 0;
+                const int l0 = __shfl_sync(0xffffffffu, clab[0], c & 31), l1 = __shfl_sync(0xffffffffu, clab[1], c & 31);
+                if (t) best = min(best, c < 32 ? l0 : l1);
+                t &= t - 1;
+            }
+            if (best < label[h]) { label[h] = best; changed = true; }
+        }
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+    // roots = active rows that kept their own index; one component per root, in ascending order
+    unsigned long long roots = (unsigned long long)__ballot_sync(0xffffffffu, act[0] && label[0] == lane) |
+                               ((unsigned long long)__ballot_sync(0xffffffffu, act[1] && label[1] == lane + 32) << 32);
+    int n = 0;
+    unsigned long long big_rows = 0ull, big_cols = 0ull;
+    while (roots) {
+        const int root = __ffsll((long long)roots) - 1;
+        roots &= roots - 1;
+        const unsigned long long rows = (unsigned long long)__ballot_sync(0xffffffffu, label[0] == root) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, label[1] == root) << 32);
+        const unsigned long long cols = warp_or64((label[0] == root ? rm[0] : 0ull) | (label[1] == root ? rm[1] : 0ull));
         if (__popcll(rows) > 4 || __popcll(cols) > 4) {
             big_rows |= rows; big_cols |= cols;           // solved together as one compact sub-problem
         } else {
             if (lane == 0) { m.comp_rows[n] = rows; m.comp_cols[n] = cols; }
             ++n;
         }
-        remaining &= ~rows;
     }
     if (__popcll(big_rows) > kSubMax || __popcll(big_cols) > kSubMax) fb = true;
     if (lane == 0) { *m.n_comp = n; *m.fallback = fb ? 1 : 0; m.big[0] = big_rows; m.big[1] = big_cols; }
