@@ -456,6 +456,19 @@ def main():
         barrier()
         clock_windows.append((t0, time.perf_counter()))
         e2e_ms_reps.append(mine)
+    # the host -> device copies alone, all ranks at once (what PCIe / host memory give this many ranks):
+    # the ceiling the end-to-end number is measured against
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(s_in):
+        c0.record(s_in)
+        for f in range(W, F):
+            d_in[f % N].block.copy_(host[f].block, non_blocking=True)
+        c1.record(s_in)
+    t0 = time.perf_counter()
+    barrier()
+    clock_windows.append((t0, time.perf_counter()))
+    copy_ms = c0.elapsed_time(c1) / K
     clocks = sampler.stop(clock_windows) if rank == 0 else None      # samples of all timed regions
 
     # ---- parity of the timed workload: the oracle replays some of this rank's sequences ----------
@@ -492,7 +505,7 @@ def main():
     gathered = shard.gather_tracks(rows, dst=0)
 
     # ---- reduce over ranks ------------------------------------------------------------
-    e2e_t = torch.tensor(e2e_ms_reps, dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor(e2e_ms_reps + [copy_ms * K], dtype=torch.float64, device=dev)   # last entry: copies alone
     per_rank_e2e = [e2e_t.cpu().numpy()]
     per_rank_numa = [numa]
     bad = torch.tensor([0 if parity is None else parity['mismatches'] + (0 if modes_identical else 1)],
@@ -505,7 +518,9 @@ def main():
         dist.all_reduce(bad, op=dist.ReduceOp.SUM)
         per_rank_numa = [None] * world
         dist.all_gather_object(per_rank_numa, numa)
-    e2e_ms = float(np.median(e2e_t.cpu().numpy()))
+    e2e_all = e2e_t.cpu().numpy()
+    e2e_t, copy_only_ms = e2e_all[:-1], float(e2e_all[-1]) / K            # max over ranks of the copy-only pass
+    e2e_ms = float(np.median(e2e_t))
     frames = S * world * K
     ms_all = timing[modes[0]]['ms']
     ms_total = float(np.median(ms_all))
@@ -581,9 +596,14 @@ def main():
             cpu_baseline=cpu,
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                      ms_per_step=e2e_ms / K, h2d_copies_per_step=1, d2h_copies_per_step=G,
-                     repetitions_ms_per_step=[float(v) / K for v in e2e_t.cpu().numpy()],
-                     per_rank=[dict(rank=r, ms_per_step=float(np.median(v)) / K,
-                                    h2d_gbs=h2d / (float(np.median(v)) / K * 1e-3) / 1e9, numa=per_rank_numa[r])
+                     repetitions_ms_per_step=[float(v) / K for v in e2e_t],
+                     h2d_copy_only_ms_per_step=copy_only_ms,
+                     frac_of_copy_ceiling=copy_only_ms / (e2e_ms / K),
+                     note='h2d_copy_only: the same pinned staging records copied back to back by all ranks at once, '
+                          'nothing else running (slowest rank) - the host side ceiling of this box for this many ranks',
+                     per_rank=[dict(rank=r, ms_per_step=float(np.median(v[:-1])) / K,
+                                    h2d_gbs=h2d / (float(np.median(v[:-1])) / K * 1e-3) / 1e9,
+                                    h2d_copy_only_gbs=h2d / (float(v[-1]) / K * 1e-3) / 1e9, numa=per_rank_numa[r])
                                for r, v in enumerate(per_rank_e2e)]),
             parity=parity,
             gpu_launches=int(K * groups.kernels_per_frame), clocks=clocks,

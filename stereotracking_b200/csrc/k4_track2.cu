@@ -230,7 +230,7 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
     for (int e = threadIdx.x; e < R * C; e += kThreads) {
         const int r = e / C, j = e - r * C;
         float dist;
-        if (ap) dist = ap[(long long)rows[r] * C1 + sm.scol[j]];
+        if (ap) dist = ap[rows[r] * C1 + sm.scol[j]];
         else {
             const int i = sm.dets[sm.scol[j]];
             float iou = iou_pair(sm.box_ocr + rows[r] * 4, sm.in_box + i * 4);
@@ -261,8 +261,7 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
         for (int c = threadIdx.x; c < C; c += kThreads) sm.lap.y[c] = -1;
         need_warp_path = false;
     } else if (small) {
-        if (warp == 0) stlap::prepare_components(P, sm.lap, sm.masks);
-        __syncthreads();
+        stlap::prepare_components_block(P, sm.lap, sm.masks);     // ends with a barrier
         ST_SUB(15);
         if (*sm.masks.fallback == 0) {
             const int n_comp = *sm.masks.n_comp;
@@ -541,33 +540,33 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         ST_PHASE(8);
         // ---- all-pairs OCM costs (:187-258): every live track against every filtered detection, float32
         // in the reference's evaluation order (stage 1 takes the confirmed rows, stage 2 the tentative ones)
-        const long long A = (long long)n_live * C1;
+        const int A = n_live * C1;                       // <= T * D <= 2^20
         float *ap_ocm, *dense_sm;
         int dense_cap;
         if (A <= sm.cost_cap) {
-            ap_ocm = sm.cost; dense_sm = sm.cost + A; dense_cap = sm.cost_cap - (int)A;
+            ap_ocm = sm.cost; dense_sm = sm.cost + A; dense_cap = sm.cost_cap - A;
         } else {
             ap_ocm = gws; dense_sm = sm.cost; dense_cap = sm.cost_cap;
         }
         float *dense_g = gws + (long long)T * D;
         const bool lazy = !((g_skip >> 6) & 1) && pr.screen_cos > -1.5f;   // diagnostics bit 6: evaluate every entry exactly
         int lazy_used = 0;
-        for (long long e = threadIdx.x; e < A; e += kThreads) {
-            const int p = (int)(e / C1), c = (int)(e - (long long)p * C1);
+        for (int e = threadIdx.x; e < A; e += kThreads) {         // 32-bit index math: a 64-bit division per pair cost more than the pair
+            const int p = e / C1, c = e - p * C1;
             ap_ocm[e] = ocm_cost(pr, sm, p, sm.dets[c], lazy, &lazy_used);
         }
         const bool ocm_lazy = __syncthreads_or(lazy_used) != 0;
         if (threadIdx.x == 0) dbg[19] = (int)(clock64() - t_prev);      // cycles of the all-pairs pass (t_prev = end of phase 8)
         // ---- stage 1: confirmed tracks vs filtered dets (:448-474)
         associate2(pr, sm, dbg, &st.status[s], sm.conf, Rc, C1, ap_ocm, C1,
-                   (long long)Rc * C1 <= dense_cap ? dense_sm : dense_g, 1, ocm_lazy);
+                   Rc * C1 <= dense_cap ? dense_sm : dense_g, 1, ocm_lazy);
         ST_PHASE(9);
         // ---- stage 2: tentative tracks vs leftovers (:476-503)
         if (warp == 0) compact_warp(C1, [&](int c) { return sm.det_stage[sm.dets[c]] == 4; }, sm.scol, &sh_cnt[3]);
         __syncthreads();
         const int C2 = sh_cnt[3];
         associate2(pr, sm, dbg, &st.status[s], sm.tentl, Rt, C2, ap_ocm, C1,
-                   (long long)Rt * C2 <= dense_cap ? dense_sm : dense_g, 2, ocm_lazy);
+                   Rt * C2 <= dense_cap ? dense_sm : dense_g, 2, ocm_lazy);
         ST_PHASE(10);
         // ---- stage 3: OCR, every unmatched track's last observation (:505-569)
         if (warp == 0) compact_warp(C1, [&](int c) { return sm.det_stage[sm.dets[c]] == 4; }, sm.scol, &sh_cnt[4]);
@@ -575,7 +574,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         __syncthreads();
         const int C3 = sh_cnt[4], R3 = sh_cnt[5];
         associate2(pr, sm, dbg, &st.status[s], sm.rows, R3, C3, nullptr, C1,
-                   (long long)R3 * C3 <= dense_cap ? dense_sm : dense_g, 3, false);
+                   R3 * C3 <= dense_cap ? dense_sm : dense_g, 3, false);
         ST_PHASE(11);
         // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582): plain stores
         for (int p = threadIdx.x; p < n_live; p += kThreads)

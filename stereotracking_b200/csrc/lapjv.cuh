@@ -1013,6 +1013,71 @@ __device__ inline void prepare_components(const Problem &P, Scratch &s, const Ma
     __syncwarp();
 }
 
+// Step 1 for a whole CTA (>= 64 threads, every thread calls it; it ends with a barrier): the same
+// outputs as prepare_components.  One thread per row: the rows sharing a column with it, then the
+// transitive closure of that relation by repeated squaring on 64-bit row sets in shared memory
+// (rounds ~ log2 of the largest component), instead of a label propagation whose every step is a
+// chain of dependent shuffles on one warp.  m.comp_rows doubles as the closure's work array.
+__device__ inline void prepare_components_block(const Problem &P, Scratch &s, const Masks &m) {
+    const int t = threadIdx.x;
+    const int R = P.R, C = P.C;
+    __shared__ unsigned long long adj[64];
+    __shared__ int changed_sh;
+    for (int j = t; j < C; j += blockDim.x) s.y[j] = -1;
+    if (t == 0) { *m.n_comp = 0; m.big[0] = 0ull; m.big[1] = 0ull; *m.fallback = (P.adm_misc[0] != 0 || P.adm_misc[1] != 0) ? 1 : 0; }
+    __syncthreads();
+    bool act = false;
+    unsigned long long rm = 0ull, mine = 0ull;
+    if (t < 64) {
+        if (t < R) {
+            rm = m.rmask[t];
+            int xr = -1;
+            if (rm) {
+                const int c = __ffsll((long long)rm) - 1;
+                if ((rm & (rm - 1)) == 0ull && m.cmask[c] == (1ull << t)) { xr = c; s.y[c] = t; }   // isolated pair
+                else act = true;
+            }
+            s.x[t] = xr;
+        }
+        if (act) {                                         // rows sharing a column with this one (itself included)
+            unsigned long long q = rm;
+            while (q) { mine |= m.cmask[__ffsll((long long)q) - 1]; q &= q - 1; }
+        }
+        adj[t] = mine;
+    }
+    __syncthreads();
+    for (int round = 0; round < 7; ++round) {             // 2^7 >= 64 rows: enough for any chain
+        if (t == 0) changed_sh = 0;
+        __syncthreads();
+        unsigned long long next = mine;
+        if (t < 64 && act) {
+            unsigned long long q = mine;
+            while (q) { next |= adj[__ffsll((long long)q) - 1]; q &= q - 1; }
+            if (next != mine) changed_sh = 1;
+        }
+        __syncthreads();
+        if (t < 64) { adj[t] = next; mine = next; }
+        __syncthreads();
+        if (!changed_sh) break;
+    }
+    // the lowest row of a component publishes it
+    if (t < 64 && act && (mine & (0ull - mine)) == (1ull << t)) {
+        unsigned long long cols = 0ull, q = mine;
+        while (q) { cols |= m.rmask[__ffsll((long long)q) - 1]; q &= q - 1; }
+        if (__popcll(mine) > 4 || __popcll(cols) > 4) {
+            atomicOr(&m.big[0], mine);                     // solved together as one compact sub-problem
+            atomicOr(&m.big[1], cols);
+        } else {
+            const int k = atomicAdd(m.n_comp, 1);
+            m.comp_rows[k] = mine;
+            m.comp_cols[k] = cols;
+        }
+    }
+    __syncthreads();
+    if (t == 0 && (__popcll(m.big[0]) > kSubMax || __popcll(m.big[1]) > kSubMax)) *m.fallback = 1;
+    __syncthreads();
+}
+
 // Step 2, by one warp per component: enumerate the partial matchings of a component of <= 4 rows
 // and <= 4 columns.  Writes x / y of its rows and columns when the optimum is unique; returns false
 // on a tie (within kFastEps).
@@ -1040,8 +1105,10 @@ __device__ inline bool enumerate_component(const Problem &P, Scratch &s, unsigne
             }
             a[i][j] = v;
         }
+    // digits of a code: the option of each row, 0 = unmatched, j + 1 = column j; base = columns + 1
+    const int base = mcols + 1;
     int total = 1;
-    for (int i = 0; i < k; ++i) total *= 5;
+    for (int i = 0; i < k; ++i) total *= base;
     double best = INF, second = INF;
     int best_code = -1;
     for (int code = lane; code < total; code += 32) {
@@ -1051,8 +1118,8 @@ __device__ inline bool enumerate_component(const Problem &P, Scratch &s, unsigne
         bool ok = true;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int dgt = t % 5;
-            t /= 5;
+            const int dgt = t % base;
+            t /= base;
             if (i < k && dgt) {
                 const int j = dgt - 1;
                 double v = INF;
@@ -1078,8 +1145,8 @@ __device__ inline bool enumerate_component(const Problem &P, Scratch &s, unsigne
         int t = code;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int dgt = t % 5;
-            t /= 5;
+            const int dgt = t % base;
+            t /= base;
             if (i < k) {
                 int c = -1;
 #pragma unroll
