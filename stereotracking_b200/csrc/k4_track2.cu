@@ -263,7 +263,9 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
     } else if (small) {
         stlap::prepare_components_block(P, sm.lap, sm.masks);     // ends with a barrier
         ST_SUB(15);
-        if (*sm.masks.fallback == 0) {
+        if (*sm.masks.fallback == 0 && *sm.masks.n_comp == 0 && sm.masks.big[0] == 0ull) {
+            need_warp_path = false;                      // isolated pairs and <= 2 x 2 components only: all solved already
+        } else if (*sm.masks.fallback == 0) {
             const int n_comp = *sm.masks.n_comp;
             const bool has_big = sm.masks.big[0] != 0ull;
             bool bad = false;

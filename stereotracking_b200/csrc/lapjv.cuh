@@ -1013,8 +1013,47 @@ __device__ inline void prepare_components(const Problem &P, Scratch &s, const Ma
     __syncwarp();
 }
 
+// A component of at most 2 rows and 2 columns (four out of five components in tracking) in closed
+// form, by ONE thread: the empty matching, the up to four single pairs and the up to two pairings
+// are its seven candidates; the best wins if the runner-up is worse by more than kFastEps.
+// Writes x / y of its rows and columns; false = tie.
+__device__ inline bool solve_tiny_component(const Problem &P, Scratch &s, unsigned long long rows, unsigned long long cols) {
+    const double L = 2.0 * P.half, INF = 1.0e300;
+    const int r0 = __ffsll((long long)rows) - 1, c0 = __ffsll((long long)cols) - 1;
+    rows &= rows - 1; cols &= cols - 1;
+    const int r1 = rows ? __ffsll((long long)rows) - 1 : -1, c1 = cols ? __ffsll((long long)cols) - 1 : -1;
+    auto a = [&](int r, int c) -> double {
+        if (r < 0 || c < 0) return INF;
+        const double v = (double)P.cost[(long long)r * P.C + c];
+        return v < L ? v - L : INF;
+    };
+    const double a00 = a(r0, c0), a01 = a(r0, c1), a10 = a(r1, c0), a11 = a(r1, c1);
+    // candidate k: (value, column of r0, column of r1)
+    const double val[7] = {0.0, a00, a01, a10, a11, a00 + a11, a01 + a10};
+    double best = INF, second = INF;
+    int bk = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const double v = val[k];
+        if (!(v < INF)) continue;
+        if (v < best) { second = best; best = v; bk = k; }
+        else if (v < second) second = v;
+    }
+    if (!((second - best) > kFastEps)) return false;
+    const int x0 = (bk == 1 || bk == 5) ? c0 : ((bk == 2 || bk == 6) ? c1 : -1);
+    const int x1 = (bk == 3 || bk == 6) ? c0 : ((bk == 4 || bk == 5) ? c1 : -1);
+    s.x[r0] = x0;
+    if (x0 >= 0) s.y[x0] = r0;
+    if (r1 >= 0) {
+        s.x[r1] = x1;
+        if (x1 >= 0) s.y[x1] = r1;
+    }
+    return true;
+}
+
 // Step 1 for a whole CTA (>= 64 threads, every thread calls it; it ends with a barrier): the same
-// outputs as prepare_components.  One thread per row: the rows sharing a column with it, then the
+// outputs as prepare_components, except that components of <= 2 x 2 are solved on the spot by the
+// thread that finds them (solve_tiny_component) and do not enter the component list.  One thread per row: the rows sharing a column with it, then the
 // transitive closure of that relation by repeated squaring on 64-bit row sets in shared memory
 // (rounds ~ log2 of the largest component), instead of a label propagation whose every step is a
 // chain of dependent shuffles on one warp.  m.comp_rows doubles as the closure's work array.
@@ -1067,6 +1106,8 @@ __device__ inline void prepare_components_block(const Problem &P, Scratch &s, co
         if (__popcll(mine) > 4 || __popcll(cols) > 4) {
             atomicOr(&m.big[0], mine);                     // solved together as one compact sub-problem
             atomicOr(&m.big[1], cols);
+        } else if (__popcll(mine) <= 2 && __popcll(cols) <= 2 && *m.fallback == 0) {
+            if (!solve_tiny_component(P, s, mine, cols)) *m.fallback = 1;      // a tie: the exact path decides
         } else {
             const int k = atomicAdd(m.n_comp, 1);
             m.comp_rows[k] = mine;

@@ -126,6 +126,50 @@ def test_k2_decode_nms_matches_oracle(mods, cfg_name, S, seed):
             np.testing.assert_allclose(eng.det_boxes[s, :n].cpu().numpy(), ref['bboxes'], rtol=1e-6, atol=1e-5)
 
 
+def test_k2_matches_torchvision_batched_nms_on_the_gpu(mods):
+    """K2 directly against library code on the device (not through the oracle): the C4 stress
+    shape, ~1000 post-threshold candidates per frame.  The candidates are decoded with plain torch
+    ops as mmyolo's YOLOXBBoxCoder / filter_scores_and_topk do, then
+    torchvision.ops.batched_nms (the kernel family mmcv's batched_nms wraps) picks the keep set; K2
+    must keep the same priors in the same (descending score) order."""
+    import torchvision
+    cfg, fr = _head_case(mods, 'C4', 2, 19)
+    S = 2
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S, max_dets=1024, max_candidates=4096))
+    for f in range(fr['raw'].shape[0]):
+        cls_l = [c[f].cuda().contiguous() for c in fr['cls']]
+        box_l = [c[f].cuda().contiguous() for c in fr['bbox']]
+        obj_l = [c[f].cuda().contiguous() for c in fr['obj']]
+        eng.decode_nms(cls_l, box_l, obj_l, (cfg.height, cfg.width))
+        counts = eng.det_counts.cpu().numpy()
+        for s in range(S):
+            pri, cl, ob, bb = [], [], [], []
+            for c, b, o, st in zip(cls_l, box_l, obj_l, (8, 16, 32)):
+                h, w = c.shape[-2:]
+                ys, xs = torch.meshgrid(torch.arange(h, device='cuda'), torch.arange(w, device='cuda'), indexing='ij')
+                pri.append(torch.stack([xs.reshape(-1) * st, ys.reshape(-1) * st, torch.full((h * w,), st, device='cuda')], 1).float())
+                cl.append(c[s].permute(1, 2, 0).reshape(-1, c.shape[1]))
+                ob.append(o[s].reshape(-1))
+                bb.append(b[s].permute(1, 2, 0).reshape(-1, 4))
+            pri, cl, ob, bb = torch.cat(pri), torch.cat(cl), torch.cat(ob), torch.cat(bb)
+            score, label = (cl.double().sigmoid() * ob.double().sigmoid()[:, None]).float().max(1)
+            keep0 = torch.nonzero(score > 0.01).reshape(-1)
+            assert 600 < len(keep0) < 4096
+            cxy = bb[keep0, :2] * pri[keep0, 2:3] + pri[keep0, :2]
+            wh = bb[keep0, 2:].exp() * pri[keep0, 2:3]
+            boxes = torch.cat([cxy - wh / 2, cxy + wh / 2], 1)
+            kept = torchvision.ops.batched_nms(boxes, score[keep0], label[keep0], 0.5)
+            want_prior = keep0[kept].cpu().numpy()
+            n = int(counts[s])
+            got_prior = eng.det_prior[s, :n].cpu().numpy()
+            # torch's exp / sigmoid may differ from the correctly rounded ones in the last bit, which can
+            # flip a pair sitting exactly at IoU 0.5 or two candidates of equal score: allow at most 1 %
+            same = len(set(want_prior.tolist()) & set(got_prior.tolist()))
+            assert same >= 0.99 * max(len(want_prior), n), (same, len(want_prior), n)
+            if len(want_prior) == n and np.array_equal(np.sort(want_prior), np.sort(got_prior)):
+                np.testing.assert_array_equal(got_prior, want_prior)      # same set: then also the same order
+
+
 def test_k2_ties_multiclass_and_empty(mods):
     rng = np.random.default_rng(3)
     S, nc = 2, 3

@@ -48,5 +48,22 @@ PY
     timeout 60 python tools/pipeline_timeline.py 12 5 map > gpurun_out/pipeline_timeline_map.txt 2>&1; tail -8 gpurun_out/pipeline_timeline_map.txt
     timeout 60 python tools/pipeline_timeline.py 12 5 raw > gpurun_out/pipeline_timeline_raw.txt 2>&1; tail -8 gpurun_out/pipeline_timeline_raw.txt
     ;;
+  scale)
+    # gpurun --gpus N -- 'bash tools/gpu_round.sh scale N [extra bench flags]'
+    N="${2:?number of GPUs}"; shift 2
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29517 \
+        bench.py --gpus "$N" --no-cpu-baseline "$@" > "gpurun_out/bench_n$N.json" 2> "gpurun_out/bench_n$N.err"
+    tail -3 "gpurun_out/bench_n$N.err"
+    python - "$N" <<'PY'
+import json, sys
+n = sys.argv[1]
+d = json.loads(open(f'gpurun_out/bench_n{n}.json').read().strip().splitlines()[-1])
+print('N', d['n_gpus'], 'frames/s %.0f  ms/step %.4f  e2e %.0f (%.3f ms/step, copy-only %.3f)' % (
+    d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e']['h2d_copy_only_ms_per_step']))
+print('modes:', {k: (round(v['value']), round(v['ms_per_step'], 4), round(v['host_issue_ms_per_step'], 4)) for k, v in d['modes'].items() if isinstance(v, dict)})
+print('per rank e2e:', [(r['rank'], round(r['ms_per_step'], 3), round(r['h2d_gbs'], 1), round(r['h2d_copy_only_gbs'], 1), r['numa']) for r in d['e2e']['per_rank']])
+print('parity:', d['parity']['mismatches'], 'clocks:', d['clocks'])
+PY
+    ;;
   *) echo "unknown sub-command $1"; exit 2 ;;
 esac
