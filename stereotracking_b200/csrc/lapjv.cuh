@@ -1255,6 +1255,69 @@ __device__ inline bool solve_big_components(const Problem &P, Scratch &s, const 
     return true;
 }
 
+// The whole component path for a problem of at most 32 x 32 on ONE warp, without a block
+// barrier (stages 2 and 3 of the tracker are a handful of rows and columns; a CTA-wide barrier
+// costs more than their whole solution): `masks` must hold the admissibility bitmasks (low 32
+// bits used).  Isolated pairs, closure of the row adjacency by repeated squaring with one row
+// per lane, components of <= 2 x 2 in closed form by their root lanes, components of <= 4 x 4
+// enumerated by the warp one after the other, larger ones as the compact certified
+// sub-problem.  Returns false when the problem needs the whole-problem path (tie, NaN, ...).
+__device__ inline bool solve_small_warp(const Problem &P, Scratch &s, const Masks &m, unsigned char *sub_mem) {
+    const int lane = threadIdx.x & 31;
+    const int R = P.R, C = P.C;
+    if (lane < C) s.y[lane] = -1;
+    __syncwarp();
+    const unsigned rm = lane < R ? (unsigned)m.rmask[lane] : 0u;
+    bool act = false;
+    if (lane < R) {
+        int xr = -1;
+        if (rm) {
+            const int c = __ffs(rm) - 1;
+            if ((rm & (rm - 1)) == 0u && (unsigned)m.cmask[c] == (1u << lane)) { xr = c; s.y[c] = lane; }   // isolated pair
+            else act = true;
+        }
+        s.x[lane] = xr;
+    }
+    bool bad = P.adm_misc[0] != 0 || P.adm_misc[1] != 0;
+    // rows sharing a column with this lane's row, then the transitive closure (work array: comp_rows)
+    unsigned mine = 0u;
+    if (act) { unsigned q = rm; while (q) { mine |= (unsigned)m.cmask[__ffs(q) - 1]; q &= q - 1; } }
+    m.comp_rows[lane] = mine;
+    __syncwarp();
+    for (int round = 0; round < 6; ++round) {
+        unsigned next = mine, q = mine;
+        while (q) { next |= (unsigned)m.comp_rows[__ffs(q) - 1]; q &= q - 1; }
+        const bool changed = __any_sync(0xffffffffu, next != mine);
+        __syncwarp();
+        m.comp_rows[lane] = next;
+        mine = next;
+        __syncwarp();
+        if (!changed) break;
+    }
+    const bool root = act && (mine & (0u - mine)) == (1u << lane);
+    unsigned cols = 0u;
+    if (root) { unsigned q = mine; while (q) { cols |= (unsigned)m.rmask[__ffs(q) - 1]; q &= q - 1; } }
+    const int nr = __popc(mine), nc = __popc(cols);
+    const bool tiny = root && nr <= 2 && nc <= 2, big = root && (nr > 4 || nc > 4), mid = root && !tiny && !big;
+    if (tiny && !solve_tiny_component(P, s, mine, cols)) bad = true;
+    bad = __any_sync(0xffffffffu, bad);
+    unsigned mids = __ballot_sync(0xffffffffu, mid);
+    while (mids && !bad) {
+        const int src = __ffs(mids) - 1;
+        mids &= mids - 1;
+        const unsigned rr = __shfl_sync(0xffffffffu, mine, src), cc = __shfl_sync(0xffffffffu, cols, src);
+        if (!enumerate_component(P, s, rr, cc)) bad = true;
+    }
+    const unsigned big_rows = __reduce_or_sync(0xffffffffu, big ? mine : 0u), big_cols = __reduce_or_sync(0xffffffffu, big ? cols : 0u);
+    if (big_rows && !bad) {
+        if (lane == 0) { m.big[0] = big_rows; m.big[1] = big_cols; }
+        __syncwarp();
+        if (!solve_big_components(P, s, m, sub_mem)) bad = true;
+    }
+    __syncwarp();
+    return !bad;
+}
+
 // Fast path with certified uniqueness, else the exact emulation of the reference's solver.
 __device__ inline bool assign_warp(const Problem &P, Scratch &s, int *fallback_counter) {
     if (P.n <= 512 && fast_assign_warp(P, s)) return true;
