@@ -19,24 +19,6 @@ __device__ __forceinline__ uint2 ld_stream_u2(const uint2 *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
-// the same with an evict-first priority in L2 (ST_K1_EVICT_FIRST=1): the map is written once and read
-// by K3 at a few box positions, so it need not displace the tracker state and the raw frames from L2
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void st_stream_f4_ef(float4 *p, float4 v, uint64_t pol) {
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
-                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
-}
-__device__ __forceinline__ uint2 ld_stream_u2_ef(const uint2 *p, uint64_t pol) {
-    uint2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
-                 : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-
 // Correctly rounded float32 reciprocal of x = raw/16 + 1e-6 without the XU
 // pipe (no MUFU): integer seed + four Newton steps in FMAs.  The input domain is
 // finite (raw in [0, 65534]); tests/test_k1_reciprocal.py checks every value
@@ -115,14 +97,13 @@ __device__ __forceinline__ void convert2(uint32_t w, float2 bf2, float pad_depth
 // 5.3 TB/s; a torch copy of the same byte count takes 61.4 us, a memset of the
 // written bytes alone 36.9 us, this kernel with its loads disabled 43 us and with
 // its stores disabled 33 us.
-template <bool kDisp3, bool kMask, bool kEvictFirst = false>
+template <bool kDisp3, bool kMask>
 __global__ void __launch_bounds__(256, (kDisp3 || kMask) ? 4 : 6)
 k1_disp2depth_flat(const uint16_t *__restrict__ raw, const StFrameInputs *__restrict__ tab, int S, int H, int Hp, int Wp,
                    float *__restrict__ depth, float *__restrict__ disp3,
                    uint8_t *__restrict__ mask, float bf, unsigned total_items) {
     if (tab) raw = tab->raw;                                 // replayed frame: the input lives where the table says
     constexpr int kUnroll = (kDisp3 || kMask) ? 2 : 4;      // steps in flight: 2 x 64-bit loads each
-    const uint64_t pol = kEvictFirst ? policy_evict_first() : 0ull;
     const unsigned w4 = Wp >> 2;
     const unsigned items = (unsigned)Hp * w4, valid_items = (unsigned)H * w4;
     const unsigned stride = gridDim.x * 512u;                    // items per grid step
@@ -145,8 +126,8 @@ k1_disp2depth_flat(const uint16_t *__restrict__ raw, const StFrameInputs *__rest
             const bool live = i < total_items;
             sq[u] = s; lq[u] = li;
             v[u][0] = v[u][1] = make_uint2(0xffffffffu, 0xffffffffu);
-            if (live && li < valid_items) v[u][0] = kEvictFirst ? ld_stream_u2_ef(src, pol) : ld_stream_u2(src);
-            if (live && li + 32u < valid_items) v[u][1] = kEvictFirst ? ld_stream_u2_ef(src + 32, pol) : ld_stream_u2(src + 32);
+            if (live && li < valid_items) v[u][0] = ld_stream_u2(src);
+            if (live && li + 32u < valid_items) v[u][1] = ld_stream_u2(src + 32);
             i += stride;
             li += dr;
             src += src_step;
@@ -164,8 +145,7 @@ k1_disp2depth_flat(const uint16_t *__restrict__ raw, const StFrameInputs *__rest
                 convert2(v[u][hlf].x, bf2, pad_depth, dp[0], dz[0], mk[0], mk[1]);
                 convert2(v[u][hlf].y, bf2, pad_depth, dp[1], dz[1], mk[2], mk[3]);
                 float4 *o = reinterpret_cast<float4 *>(depth) + (size_t)iu + hlf * 32;
-                if (kEvictFirst) st_stream_f4_ef(o, make_float4(dz[0].x, dz[0].y, dz[1].x, dz[1].y), pol);
-                else st_stream_f4(o, make_float4(dz[0].x, dz[0].y, dz[1].x, dz[1].y));
+                st_stream_f4(o, make_float4(dz[0].x, dz[0].y, dz[1].x, dz[1].y));
                 if (kDisp3) {
                     const float4 d0 = make_float4(dp[0].x, dp[0].y, dp[1].x, dp[1].y);
 #pragma unroll
@@ -391,11 +371,9 @@ int st_disp2depth_tab(const uint16_t *raw, const StFrameInputs *tab, int S, int 
             if (grid > need) grid = need;
             kernel<<<(int)grid, 256, 0, st>>>(raw, tab, S, H, Hp, Wp, depth, disp3, mask, bf, (unsigned)total_items);
         };
-        static const bool evict_first = getenv("ST_K1_EVICT_FIRST") && atoi(getenv("ST_K1_EVICT_FIRST")) != 0;
         if (disp3 && mask) launch(k1_disp2depth_flat<true, true>);
         else if (disp3) launch(k1_disp2depth_flat<true, false>);
         else if (mask) launch(k1_disp2depth_flat<false, true>);
-        else if (evict_first) launch(k1_disp2depth_flat<false, false, true>);
         else launch(k1_disp2depth_flat<false, false>);
     } else if ((W % 8 == 0) && (Wp % 4 == 0) && W <= 32768 && Wp <= 65534 && ((uintptr_t)raw % 16 == 0) &&
                ((uintptr_t)depth % 16 == 0) && (!disp3 || (uintptr_t)disp3 % 16 == 0) &&

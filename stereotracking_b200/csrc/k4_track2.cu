@@ -206,7 +206,7 @@ __device__ __forceinline__ float ocm_cost(const Params &pr, const Smem &sm, int 
 // evaluated right here (its rows and columns are the few left over after stages 1 and 2).
 // The sub-matrix is gathered into `dense` together with its admissible-edge statistics, solved,
 // and the matches are scattered into det_pos / det_stage / hit.
-__device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *status_word, const int *rows, int R, int C,
+__device__ __noinline__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *status_word, const int *rows, int R, int C,
                            const float *ap, int C1, float *dense, int stage_code, bool ocm_lazy) {
     if (R == 0 || C == 0) return;           // dists.size == 0 -> nothing matched (:263-265)
     const double lap_limit = 2.0 * pr.lap_half;
@@ -228,49 +228,7 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
     P.row_cnt = sm.row_cnt; P.col_cnt = sm.col_cnt; P.row_adm = sm.row_adm; P.adm_misc = sm.adm_misc;
     const bool skip = (g_skip >> (stage_code - 1)) & 1;
     bool need_warp_path;
-    if (R <= 32 && C <= 32 && !skip) {
-        // ---- a handful of rows and columns (always so in stages 2 and 3): everything on warp 0, the
-        // other warps go straight to the barrier.  One lane per column, row by row.
-        if (warp == 0) {
-            const int lane = threadIdx.x;
-            unsigned cm = 0u;
-            bool nan = false, near = false;
-            const int sc = lane < C ? sm.scol[lane] : 0;
-            const int di = lane < C ? sm.dets[sc] : 0;
-            for (int r = 0; r < R; ++r) {
-                float dist = 0.f;
-                bool adm = false;
-                if (lane < C) {
-                    if (ap) dist = ap[rows[r] * C1 + sc];
-                    else {
-                        float iou = iou_pair(sm.box_ocr + rows[r] * 4, sm.in_box + di * 4);
-                        if (pr.weight_iou) iou = __fmul_rn(iou, sm.in_score[di]);
-                        dist = __fsub_rn(1.f, iou);
-                    }
-                    dense[r * C + lane] = dist;
-                    adm = (double)dist < lap_limit;
-                    nan |= dist != dist;
-                    near |= fabs((double)dist - lap_limit) <= 2.0e-9;
-                }
-                const unsigned rm = __ballot_sync(0xffffffffu, adm);
-                if (lane == 0) {
-                    sm.masks.rmask[r] = rm;
-                    sm.row_cnt[r] = __popc(rm);
-                    sm.row_adm[r] = rm ? 31 - __clz(rm) : -1;
-                }
-                if (adm) cm |= 1u << r;
-            }
-            if (lane < C) { sm.masks.cmask[lane] = cm; sm.col_cnt[lane] = __popc(cm); }
-            const bool any_nan = __any_sync(0xffffffffu, nan), any_near = __any_sync(0xffffffffu, near);
-            if (lane == 0) { sm.adm_misc[0] = any_nan; sm.adm_misc[1] = any_near; atomicAdd(&dbg[5], 1); }
-            __syncwarp();
-            const bool ok = stlap::solve_small_warp(P, sm.lap, sm.masks, sm.sub);
-            if (lane == 0) sm.adm_misc[2] = ok ? 0 : 1;
-        }
-        __syncthreads();
-        need_warp_path = sm.adm_misc[2] != 0;
-        ST_SUB(16);
-    } else {
+    {
     for (int r = threadIdx.x; r < R; r += kThreads) { sm.row_cnt[r] = 0; sm.row_adm[r] = -1; }
     for (int c = threadIdx.x; c < C; c += kThreads) sm.col_cnt[c] = 0;
     if (threadIdx.x < 64) { sm.masks.rmask[threadIdx.x] = 0ull; sm.masks.cmask[threadIdx.x] = 0ull; }
@@ -301,7 +259,16 @@ __device__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *st
     ST_SUB(14);
     if (threadIdx.x == 0) atomicAdd(&dbg[5], 1);        // assignments solved (fire and forget)
     need_warp_path = !small;
-    if (skip) {
+    if (!skip && R <= 32 && C <= 32) {
+        // a handful of rows and columns (always so in stages 2 and 3): the component path on warp 0
+        // alone, without block barriers; the other warps go straight to the next barrier
+        if (warp == 0) {
+            const bool ok = stlap::solve_small_warp(P, sm.lap, sm.masks, sm.sub);
+            if (threadIdx.x == 0) sm.adm_misc[2] = ok ? 0 : 1;
+        }
+        __syncthreads();
+        need_warp_path = sm.adm_misc[2] != 0;
+    } else if (skip) {
         for (int c = threadIdx.x; c < C; c += kThreads) sm.lap.y[c] = -1;
         need_warp_path = false;
     } else if (small) {
