@@ -206,7 +206,9 @@ __device__ __forceinline__ float ocm_cost(const Params &pr, const Smem &sm, int 
 // evaluated right here (its rows and columns are the few left over after stages 1 and 2).
 // The sub-matrix is gathered into `dense` together with its admissible-edge statistics, solved,
 // and the matches are scattered into det_pos / det_stage / hit.
-__device__ __noinline__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *status_word, const int *rows, int R, int C,
+// (inlined at its three call sites on purpose: out of line, the shared-memory pointers of `sm` are
+// re-read through local memory and every sub-phase ran 1.5-2x slower)
+__device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *status_word, const int *rows, int R, int C,
                            const float *ap, int C1, float *dense, int stage_code, bool ocm_lazy) {
     if (R == 0 || C == 0) return;           // dists.size == 0 -> nothing matched (:263-265)
     const double lap_limit = 2.0 * pr.lap_half;
