@@ -108,6 +108,7 @@ k2_score_compact(HeadLevels L, const StFrameInputs *__restrict__ tab, int P, int
 // memory, and the warp then scores the queue one candidate per lane.
 constexpr int kScoreWarps = 8;
 
+template <int kItems>       // 128-bit objectness loads in flight per thread
 __global__ void __launch_bounds__(kScoreWarps * 32)
 k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, int P, int num_classes, float score_thr, float logit_cut, int cap,
                     int32_t *__restrict__ cand_count, float *__restrict__ cand_score,
@@ -117,14 +118,16 @@ k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, 
     const int lane = threadIdx.x & 31;
     int32_t *queue = queue_all[threadIdx.x >> 5];
     const float screen_thr = __fmul_rn(score_thr, 0.9f);
-    // grid (ceil(items_pad / 512), S): two items per thread (both 128-bit loads issued before
-    // either is screened), all index arithmetic 32-bit (a flat 64-bit item index cost two 64-bit
-    // divisions per item and made the pass instruction-bound)
+    // grid (ceil(items_pad / (256 kItems)), S): kItems items per thread (all 128-bit loads issued
+    // before any is screened; 2 at the bench size, where the pass is launch-latency-bound and more
+    // CTAs start sooner, 4 for large batches, where CTA turnover set the pace), all index arithmetic
+    // 32-bit (a flat 64-bit item index cost two 64-bit divisions per item and made the pass
+    // instruction-bound)
     const int s = blockIdx.y;
-    float4 o4s[2];
+    float4 o4s[kItems];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int j = (blockIdx.x * 2 + u) * blockDim.x + threadIdx.x;
+    for (int u = 0; u < kItems; ++u) {
+        const int j = (blockIdx.x * kItems + u) * blockDim.x + threadIdx.x;
         o4s[u] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
         if (j < P4) {
             const int l = level_of(L, j * 4);
@@ -134,8 +137,8 @@ k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, 
         }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-    const int j = (blockIdx.x * 2 + u) * blockDim.x + threadIdx.x;
+    for (int u = 0; u < kItems; ++u) {
+    const int j = (blockIdx.x * kItems + u) * blockDim.x + threadIdx.x;
     unsigned keep = 0u;                                  // priors of this item that survive the screen
     const int p0 = j * 4;
     if (j < P4) {
@@ -471,8 +474,13 @@ int st_decode_nms_ws(st_handle *h, const float *const *cls_host, const float *co
                ((uintptr_t)obj_host[l] % 16 == 0);
     if (vec4) {
         const int items_pad = ((P >> 2) + 31) & ~31;
-        k2_score_compact_v4<<<dim3((items_pad + kScoreWarps * 64 - 1) / (kScoreWarps * 64), S), kScoreWarps * 32, 0, st>>>(
-            L, tab, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
+        const bool big = (long long)items_pad * S >= (1ll << 21);          // >= 8 M priors per call
+        if (big)
+            k2_score_compact_v4<4><<<dim3((items_pad + kScoreWarps * 128 - 1) / (kScoreWarps * 128), S), kScoreWarps * 32, 0, st>>>(
+                L, tab, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
+        else
+            k2_score_compact_v4<2><<<dim3((items_pad + kScoreWarps * 64 - 1) / (kScoreWarps * 64), S), kScoreWarps * 32, 0, st>>>(
+                L, tab, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
     } else {
         k2_score_compact<<<dim3((P + 255) / 256, S), 256, 0, st>>>(
             L, tab, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
