@@ -14,6 +14,7 @@
 // were three more launches, 95 us of mostly launch and dependent-load latency for
 // ~200 candidates per frame.)
 #include <cmath>
+#include <cstdlib>
 #include "st_common.cuh"
 
 namespace {
@@ -474,7 +475,8 @@ int st_decode_nms_ws(st_handle *h, const float *const *cls_host, const float *co
                ((uintptr_t)obj_host[l] % 16 == 0);
     if (vec4) {
         const int items_pad = ((P >> 2) + 31) & ~31;
-        const bool big = (long long)items_pad * S >= (1ll << 21);          // >= 8 M priors per call
+        bool big = (long long)items_pad * S >= (1ll << 21);                // >= 8 M priors per call
+        if (const char *e = getenv("ST_K2_ITEMS")) big = atoi(e) >= 4;      // tuning aid
         if (big)
             k2_score_compact_v4<4><<<dim3((items_pad + kScoreWarps * 128 - 1) / (kScoreWarps * 128), S), kScoreWarps * 32, 0, st>>>(
                 L, tab, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
