@@ -109,7 +109,12 @@ k2_score_compact(HeadLevels L, const StFrameInputs *__restrict__ tab, int P, int
 // memory, and the warp then scores the queue one candidate per lane.
 constexpr int kScoreWarps = 8;
 
-template <int kItems>       // 128-bit objectness loads in flight per thread
+// kPersist: a resident grid walks the tiles (512 priors x kItems of one sequence each) and loads
+// the NEXT tile's objectness words before it screens the current one, so the 128-bit loads of two
+// tiles are in flight per thread and no CTA launch sits between them.  Used for large batches
+// (the one-shot grid turned 43 k CTAs of 8 KB each over at 2048 x 1080p: CTA turnover, not DRAM, set
+// the pace); at the bench size the pass is launch-latency-bound and the one-shot grid starts sooner.
+template <int kItems, bool kPersist>       // kItems: 128-bit objectness loads per thread and tile
 __global__ void __launch_bounds__(kScoreWarps * 32)
 k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, int P, int num_classes, float score_thr, float logit_cut, int cap,
                     int32_t *__restrict__ cand_count, float *__restrict__ cand_score,
@@ -119,27 +124,34 @@ k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, 
     const int lane = threadIdx.x & 31;
     int32_t *queue = queue_all[threadIdx.x >> 5];
     const float screen_thr = __fmul_rn(score_thr, 0.9f);
-    // grid (ceil(items_pad / (256 kItems)), S): kItems items per thread (all 128-bit loads issued
-    // before any is screened; 2 at the bench size, where the pass is launch-latency-bound and more
-    // CTAs start sooner, 4 for large batches, where CTA turnover set the pace), all index arithmetic
-    // 32-bit (a flat 64-bit item index cost two 64-bit divisions per item and made the pass
-    // instruction-bound)
-    const int s = blockIdx.y;
-    float4 o4s[kItems];
+    // tiles: (ceil(items_pad / (256 kItems)) per sequence) x S; all index arithmetic 32-bit (a flat
+    // 64-bit item index cost two 64-bit divisions per item and made the pass instruction-bound)
+    const int tiles_per_seq = kPersist ? (((P4 + 31) & ~31) + kScoreWarps * 32 * kItems - 1) / (kScoreWarps * 32 * kItems) : (int)gridDim.x;
+    const int total_tiles = tiles_per_seq * S;
+    int tile = kPersist ? (int)blockIdx.x : (int)(blockIdx.y * gridDim.x + blockIdx.x);
+    auto load_tile = [&](int t, float4 (&o)[kItems]) {
+        const int s_ = t / tiles_per_seq, jt = t - s_ * tiles_per_seq;
 #pragma unroll
-    for (int u = 0; u < kItems; ++u) {
-        const int j = (blockIdx.x * kItems + u) * blockDim.x + threadIdx.x;
-        o4s[u] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
-        if (j < P4) {
-            const int l = level_of(L, j * 4);
-            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                         : "=f"(o4s[u].x), "=f"(o4s[u].y), "=f"(o4s[u].z), "=f"(o4s[u].w)
-                         : "l"(K2_OBJ(l) + (long long)s * L.h[l] * L.w[l] + (j * 4 - L.prior_off[l])));
+        for (int u = 0; u < kItems; ++u) {
+            const int j = (jt * kItems + u) * blockDim.x + threadIdx.x;
+            o[u] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
+            if (j < P4) {
+                const int l = level_of(L, j * 4);
+                asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(o[u].x), "=f"(o[u].y), "=f"(o[u].z), "=f"(o[u].w)
+                             : "l"(K2_OBJ(l) + (long long)s_ * L.h[l] * L.w[l] + (j * 4 - L.prior_off[l])));
+            }
         }
-    }
+    };
+    float4 o4s[kItems], nxt[kItems];
+    if (tile < total_tiles) load_tile(tile, o4s);
+    while (tile < total_tiles) {
+    const int next_tile = kPersist ? tile + (int)gridDim.x : total_tiles;
+    if (kPersist && next_tile < total_tiles) load_tile(next_tile, nxt);
+    const int s = tile / tiles_per_seq, jt0 = tile - s * tiles_per_seq;
 #pragma unroll
     for (int u = 0; u < kItems; ++u) {
-    const int j = (blockIdx.x * kItems + u) * blockDim.x + threadIdx.x;
+    const int j = (jt0 * kItems + u) * blockDim.x + threadIdx.x;
     unsigned keep = 0u;                                  // priors of this item that survive the screen
     const int p0 = j * 4;
     if (j < P4) {
@@ -212,6 +224,12 @@ k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, 
         }
     }
     __syncwarp();
+    }
+    tile = next_tile;
+    if (kPersist) {
+#pragma unroll
+        for (int u = 0; u < kItems; ++u) o4s[u] = nxt[u];
+    }
     }
 }
 
@@ -475,14 +493,25 @@ int st_decode_nms_ws(st_handle *h, const float *const *cls_host, const float *co
                ((uintptr_t)obj_host[l] % 16 == 0);
     if (vec4) {
         const int items_pad = ((P >> 2) + 31) & ~31;
-        bool big = (long long)items_pad * S >= (1ll << 21);                // >= 8 M priors per call
-        if (const char *e = getenv("ST_K2_ITEMS")) big = atoi(e) >= 4;      // tuning aid
-        if (big)
-            k2_score_compact_v4<4><<<dim3((items_pad + kScoreWarps * 128 - 1) / (kScoreWarps * 128), S), kScoreWarps * 32, 0, st>>>(
+        const int tiles = (items_pad + kScoreWarps * 64 - 1) / (kScoreWarps * 64);
+        bool persist = (long long)tiles * S >= 8192;                        // >= 16 M priors per call
+        if (const char *e = getenv("ST_K2_PERSIST")) persist = atoi(e) != 0;   // tuning aid
+        if (persist) {
+            struct Dev { int grid; };
+            static StPerDevice<Dev> per_device;
+            const Dev *dv = per_device.get([](Dev &v) {
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_score_compact_v4<2, true>, kScoreWarps * 32, 0) != cudaSuccess || per_sm < 1)
+                    per_sm = 4;
+                v.grid = st_ctx_sms() * per_sm;
+                return true;
+            });
+            k2_score_compact_v4<2, true><<<dv ? dv->grid : 592, kScoreWarps * 32, 0, st>>>(
                 L, tab, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
-        else
-            k2_score_compact_v4<2><<<dim3((items_pad + kScoreWarps * 64 - 1) / (kScoreWarps * 64), S), kScoreWarps * 32, 0, st>>>(
+        } else {
+            k2_score_compact_v4<2, false><<<dim3(tiles, S), kScoreWarps * 32, 0, st>>>(
                 L, tab, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
+        }
     } else {
         k2_score_compact<<<dim3((P + 255) / 256, S), 256, 0, st>>>(
             L, tab, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);

@@ -209,10 +209,14 @@ __device__ __forceinline__ float ocm_cost(const Params &pr, const Smem &sm, int 
 // (inlined at its three call sites on purpose: out of line, the shared-memory pointers of `sm` are
 // re-read through local memory and every sub-phase ran 1.5-2x slower)
 __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *status_word, const int *rows, int R, int C,
-                           const float *ap, int C1, float *dense, int stage_code, bool ocm_lazy) {
+                           const float *ap, int C1, float *dense, int stage_code, bool ocm_lazy,
+                           unsigned char *wide_mem /* room for the 256-bit component path, or null */) {
     if (R == 0 || C == 0) return;           // dists.size == 0 -> nothing matched (:263-265)
     const double lap_limit = 2.0 * pr.lap_half;
     const bool small = R <= 64 && C <= 64;
+    const bool wide = !small && wide_mem != nullptr && R <= stlap::kWideMax && C <= stlap::kWideMax;
+    stlap::WideMasks wm;
+    if (wide) wm = stlap::carve_wide(wide_mem);
     const int warp = threadIdx.x >> 5;
     // debug words 14..18 (stage 1 only): cycles of gather / components / solve / fallback / scatter
     long long t_sub = clock64();
@@ -234,6 +238,8 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
     for (int r = threadIdx.x; r < R; r += kThreads) { sm.row_cnt[r] = 0; sm.row_adm[r] = -1; }
     for (int c = threadIdx.x; c < C; c += kThreads) sm.col_cnt[c] = 0;
     if (threadIdx.x < 64) { sm.masks.rmask[threadIdx.x] = 0ull; sm.masks.cmask[threadIdx.x] = 0ull; }
+    if (wide)
+        for (int i = threadIdx.x; i < 2 * stlap::kWideMax * stlap::kWideWords; i += kThreads) wm.rmask[i] = 0ull;   // rmask and cmask
     if (threadIdx.x == 0) { sm.adm_misc[0] = 0; sm.adm_misc[1] = 0; *sm.masks.fallback = 0; *sm.masks.n_comp = 0; }
     __syncthreads();
     for (int e = threadIdx.x; e < R * C; e += kThreads) {
@@ -253,6 +259,10 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
             atomicAdd(&sm.col_cnt[j], 1);
             sm.row_adm[r] = j;
             if (small) { atomicOr(&sm.masks.rmask[r], 1ull << j); atomicOr(&sm.masks.cmask[j], 1ull << r); }
+            else if (wide) {
+                atomicOr(&wm.rmask[r * stlap::kWideWords + (j >> 6)], 1ull << (j & 63));
+                atomicOr(&wm.cmask[j * stlap::kWideWords + (r >> 6)], 1ull << (r & 63));
+            }
         }
         if (dist != dist) sm.adm_misc[0] = 1;
         if (fabs((double)dist - lap_limit) <= 2.0e-9) sm.adm_misc[1] = 1;
@@ -290,6 +300,31 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
                 for (int k = warp - first; k < n_comp; k += nw)
                     bad |= !stlap::enumerate_component(P, sm.lap, sm.masks.comp_rows[k], sm.masks.comp_cols[k]);
             need_warp_path = __syncthreads_or(bad) != 0;
+        } else {
+            need_warp_path = true;
+        }
+    } else if (wide) {
+        // a hundred or two rows and columns: the same component path on 256-bit sets
+        stlap::prepare_components_wide(P, sm.lap, wm, sm.sub);        // ends with a barrier
+        ST_SUB(15);
+        if (*wm.fallback == 0) {
+            const int n_comp = min(*wm.n_comp, stlap::kWideComps);
+            const int nR = (int)wm.big[0], nC = (int)wm.big[1];
+            const bool has_big = nR > 0;
+            if (n_comp == 0 && !has_big) {
+                need_warp_path = false;
+            } else {
+                bool bad = false;
+                if (warp == 0 && has_big) bad = !stlap::solve_sub_problem(P, sm.lap, sm.sub, nR, nC);
+                const int first = has_big ? 1 : 0, nw = kWarps - first;
+                if (warp >= first)
+                    for (int k = warp - first; k < n_comp; k += nw) {
+                        const int *rec = wm.comp + k * 10;
+                        const int ri[4] = {rec[2], rec[3], rec[4], rec[5]}, ci[4] = {rec[6], rec[7], rec[8], rec[9]};
+                        bad |= !stlap::enumerate_idx(P, sm.lap, ri, ci, rec[0], rec[1]);
+                    }
+                need_warp_path = __syncthreads_or(bad) != 0;
+            }
         } else {
             need_warp_path = true;
         }
@@ -559,10 +594,19 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         const int A = n_live * C1;                       // <= T * D <= 2^20
         float *ap_ocm, *dense_sm;
         int dense_cap;
-        if (A <= sm.cost_cap) {
-            ap_ocm = sm.cost; dense_sm = sm.cost + A; dense_cap = sm.cost_cap - A;
+        // crowded sequences (more than 64 rows or columns in some stage) take the tail of the cost region
+        // for the 256-bit component sets; their matrices then mostly live in the global workspace
+        const int wide_floats = (int)((stlap::wide_bytes() + 15) / 16 * 4);
+        unsigned char *wide_mem = nullptr;
+        int cost_avail = sm.cost_cap;
+        if ((n_live > 64 || C1 > 64) && sm.cost_cap >= wide_floats) {
+            cost_avail = sm.cost_cap - wide_floats;
+            wide_mem = reinterpret_cast<unsigned char *>(sm.cost + cost_avail);
+        }
+        if (A <= cost_avail) {
+            ap_ocm = sm.cost; dense_sm = sm.cost + A; dense_cap = cost_avail - A;
         } else {
-            ap_ocm = gws; dense_sm = sm.cost; dense_cap = sm.cost_cap;
+            ap_ocm = gws; dense_sm = sm.cost; dense_cap = cost_avail;
         }
         float *dense_g = gws + (long long)T * D;
         const bool lazy = !((g_skip >> 6) & 1) && pr.screen_cos > -1.5f;   // diagnostics bit 6: evaluate every entry exactly
@@ -575,14 +619,14 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         if (threadIdx.x == 0) dbg[19] = (int)(clock64() - t_prev);      // cycles of the all-pairs pass (t_prev = end of phase 8)
         // ---- stage 1: confirmed tracks vs filtered dets (:448-474)
         associate2(pr, sm, dbg, &st.status[s], sm.conf, Rc, C1, ap_ocm, C1,
-                   Rc * C1 <= dense_cap ? dense_sm : dense_g, 1, ocm_lazy);
+                   Rc * C1 <= dense_cap ? dense_sm : dense_g, 1, ocm_lazy, wide_mem);
         ST_PHASE(9);
         // ---- stage 2: tentative tracks vs leftovers (:476-503)
         if (warp == 0) compact_warp(C1, [&](int c) { return sm.det_stage[sm.dets[c]] == 4; }, sm.scol, &sh_cnt[3]);
         __syncthreads();
         const int C2 = sh_cnt[3];
         associate2(pr, sm, dbg, &st.status[s], sm.tentl, Rt, C2, ap_ocm, C1,
-                   Rt * C2 <= dense_cap ? dense_sm : dense_g, 2, ocm_lazy);
+                   Rt * C2 <= dense_cap ? dense_sm : dense_g, 2, ocm_lazy, wide_mem);
         ST_PHASE(10);
         // ---- stage 3: OCR, every unmatched track's last observation (:505-569)
         if (warp == 0) compact_warp(C1, [&](int c) { return sm.det_stage[sm.dets[c]] == 4; }, sm.scol, &sh_cnt[4]);
@@ -590,7 +634,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         __syncthreads();
         const int C3 = sh_cnt[4], R3 = sh_cnt[5];
         associate2(pr, sm, dbg, &st.status[s], sm.rows, R3, C3, nullptr, C1,
-                   R3 * C3 <= dense_cap ? dense_sm : dense_g, 3, false);
+                   R3 * C3 <= dense_cap ? dense_sm : dense_g, 3, false, wide_mem);
         ST_PHASE(11);
         // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582): plain stores
         for (int p = threadIdx.x; p < n_live; p += kThreads)

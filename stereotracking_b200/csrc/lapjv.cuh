@@ -1017,11 +1017,18 @@ __device__ inline void prepare_components(const Problem &P, Scratch &s, const Ma
 // form, by ONE thread: the empty matching, the up to four single pairs and the up to two pairings
 // are its seven candidates; the best wins if the runner-up is worse by more than kFastEps.
 // Writes x / y of its rows and columns; false = tie.
+__device__ inline bool solve_tiny_idx(const Problem &P, Scratch &s, int r0, int r1, int c0, int c1);
+
 __device__ inline bool solve_tiny_component(const Problem &P, Scratch &s, unsigned long long rows, unsigned long long cols) {
-    const double L = 2.0 * P.half, INF = 1.0e300;
     const int r0 = __ffsll((long long)rows) - 1, c0 = __ffsll((long long)cols) - 1;
     rows &= rows - 1; cols &= cols - 1;
     const int r1 = rows ? __ffsll((long long)rows) - 1 : -1, c1 = cols ? __ffsll((long long)cols) - 1 : -1;
+    return solve_tiny_idx(P, s, r0, r1, c0, c1);
+}
+
+// rows r0 (, r1) and columns c0 (, c1); -1 = absent
+__device__ inline bool solve_tiny_idx(const Problem &P, Scratch &s, int r0, int r1, int c0, int c1) {
+    const double L = 2.0 * P.half, INF = 1.0e300;
     auto a = [&](int r, int c) -> double {
         if (r < 0 || c < 0) return INF;
         const double v = (double)P.cost[(long long)r * P.C + c];
@@ -1122,9 +1129,9 @@ __device__ inline void prepare_components_block(const Problem &P, Scratch &s, co
 // Step 2, by one warp per component: enumerate the partial matchings of a component of <= 4 rows
 // and <= 4 columns.  Writes x / y of its rows and columns when the optimum is unique; returns false
 // on a tie (within kFastEps).
+__device__ inline bool enumerate_idx(const Problem &P, Scratch &s, const int (&ri)[4], const int (&ci)[4], int k, int mcols);
+
 __device__ inline bool enumerate_component(const Problem &P, Scratch &s, unsigned long long rows, unsigned long long cols) {
-    const int lane = threadIdx.x & 31;
-    const double L = 2.0 * P.half, INF = 1.0e300;
     int ri[4], ci[4];
     const int k = __popcll(rows), mcols = __popcll(cols);
 #pragma unroll
@@ -1134,6 +1141,13 @@ __device__ inline bool enumerate_component(const Problem &P, Scratch &s, unsigne
         ci[i] = cols ? __ffsll((long long)cols) - 1 : 0;
         cols &= cols - 1;
     }
+    return enumerate_idx(P, s, ri, ci, k, mcols);
+}
+
+// the same for a component given by its row / column indices (k <= 4 rows, mcols <= 4 columns)
+__device__ inline bool enumerate_idx(const Problem &P, Scratch &s, const int (&ri)[4], const int (&ci)[4], int k, int mcols) {
+    const int lane = threadIdx.x & 31;
+    const double L = 2.0 * P.half, INF = 1.0e300;
     double a[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -1212,30 +1226,41 @@ __host__ __device__ inline size_t sub_bytes() {
     return scratch_bytes(2 * kSubMax) + sizeof(float) * kSubMax * kSubMax + sizeof(int) * (5 * kSubMax + 4);
 }
 
+__device__ inline bool solve_sub_problem(const Problem &P, Scratch &s, unsigned char *sub_mem, int nR, int nC);
+
 __device__ inline bool solve_big_components(const Problem &P, Scratch &s, const Masks &m, unsigned char *sub_mem) {
     const int lane = threadIdx.x & 31;
     unsigned long long rows = m.big[0], cols = m.big[1];
     if (!rows) return true;
-    Scratch sub = carve(sub_mem, 2 * kSubMax);
     float *sub_cost = reinterpret_cast<float *>(sub_mem + scratch_bytes(2 * kSubMax));
     int *lrow = reinterpret_cast<int *>(sub_cost + kSubMax * kSubMax), *lcol = lrow + kSubMax;
-    Problem Q;
-    Q.R = __popcll(rows); Q.C = __popcll(cols); Q.n = Q.R + Q.C; Q.half = P.half; Q.dbg = nullptr;
-    Q.cost = sub_cost;
-    Q.row_cnt = lcol + kSubMax; Q.row_adm = Q.row_cnt + kSubMax; Q.col_cnt = Q.row_adm + kSubMax;
-    Q.adm_misc = Q.col_cnt + kSubMax;
+    const int nR = __popcll(rows), nC = __popcll(cols);
     // lane l takes the l-th row and the l-th column of the sets
-    if (lane < Q.R) {
+    if (lane < nR) {
         unsigned long long t = rows;
         for (int k = 0; k < lane; ++k) t &= t - 1;
         lrow[lane] = __ffsll((long long)t) - 1;
     }
-    if (lane < Q.C) {
+    if (lane < nC) {
         unsigned long long t = cols;
         for (int k = 0; k < lane; ++k) t &= t - 1;
         lcol[lane] = __ffsll((long long)t) - 1;
     }
     __syncwarp();
+    return solve_sub_problem(P, s, sub_mem, nR, nC);
+}
+
+// the sub-problem of the rows lrow[0..nR) x columns lcol[0..nC) already listed in sub_mem
+__device__ inline bool solve_sub_problem(const Problem &P, Scratch &s, unsigned char *sub_mem, int nR, int nC) {
+    const int lane = threadIdx.x & 31;
+    Scratch sub = carve(sub_mem, 2 * kSubMax);
+    float *sub_cost = reinterpret_cast<float *>(sub_mem + scratch_bytes(2 * kSubMax));
+    int *lrow = reinterpret_cast<int *>(sub_cost + kSubMax * kSubMax), *lcol = lrow + kSubMax;
+    Problem Q;
+    Q.R = nR; Q.C = nC; Q.n = Q.R + Q.C; Q.half = P.half; Q.dbg = nullptr;
+    Q.cost = sub_cost;
+    Q.row_cnt = lcol + kSubMax; Q.row_adm = Q.row_cnt + kSubMax; Q.col_cnt = Q.row_adm + kSubMax;
+    Q.adm_misc = Q.col_cnt + kSubMax;
     for (int e = lane; e < Q.R * Q.C; e += 32) {
         const int i = e / Q.C, j = e - i * Q.C;
         sub_cost[e] = P.cost[(long long)lrow[i] * P.C + lcol[j]];
@@ -1316,6 +1341,175 @@ __device__ inline bool solve_small_warp(const Problem &P, Scratch &s, const Mask
     }
     __syncwarp();
     return !bad;
+}
+
+// ---------------------------------------------------------------------------------
+// Component path for problems of up to 256 x 256 (a hundred or two tracks and detections per
+// sequence: 1080p scenes, the stress workload with ~1000 candidates), by a whole CTA: the same
+// steps as prepare_components_block on 256-bit row / column sets (four 64-bit words, one row
+// per thread).  Components of <= 2 x 2 are solved by the thread that finds them, components up
+// to 4 x 4 are listed by their row / column indices for the enumeration, all larger ones
+// together are listed as the sub-problem of solve_sub_problem (at most kSubMax rows / columns,
+// else the stage falls back to the single-warp path on the whole problem).
+constexpr int kWideMax = 256, kWideWords = kWideMax / 64, kWideComps = 128;
+
+struct WideMasks {
+    unsigned long long *rmask, *cmask, *adj;      // [256][4] each
+    int *comp;                                    // [kWideComps][10]: k, m, rows[4], cols[4]
+    unsigned long long *big;                      // [8]: rows[4], cols[4] of the larger components
+    int *n_comp, *fallback;
+};
+
+__host__ __device__ inline size_t wide_bytes() {
+    return sizeof(unsigned long long) * (3 * kWideMax * kWideWords + 8) + sizeof(int) * (kWideComps * 10 + 4);
+}
+
+__device__ inline WideMasks carve_wide(unsigned char *p) {
+    WideMasks m;
+    m.rmask = reinterpret_cast<unsigned long long *>(p);
+    m.cmask = m.rmask + kWideMax * kWideWords;
+    m.adj = m.cmask + kWideMax * kWideWords;
+    m.big = m.adj + kWideMax * kWideWords;
+    m.comp = reinterpret_cast<int *>(m.big + 8);
+    m.n_comp = m.comp + kWideComps * 10;
+    m.fallback = m.n_comp + 1;
+    return m;
+}
+
+// every thread of the CTA (>= 256 threads) calls it; ends with a barrier.  m.rmask / m.cmask hold the
+// admissibility bits; sub_mem receives the row / column lists of the larger components.
+__device__ inline void prepare_components_wide(const Problem &P, Scratch &s, const WideMasks &m, unsigned char *sub_mem) {
+    const int t = threadIdx.x;
+    const int R = P.R, C = P.C;
+    __shared__ int changed_w;
+    for (int j = t; j < C; j += blockDim.x) s.y[j] = -1;
+    if (t < 8) m.big[t] = 0ull;
+    if (t == 0) { *m.n_comp = 0; *m.fallback = (P.adm_misc[0] != 0 || P.adm_misc[1] != 0) ? 1 : 0; }
+    __syncthreads();
+    bool act = false;
+    unsigned long long rm[kWideWords] = {0ull, 0ull, 0ull, 0ull}, mine[kWideWords] = {0ull, 0ull, 0ull, 0ull};
+    auto popc4 = [](const unsigned long long *w) { return __popcll(w[0]) + __popcll(w[1]) + __popcll(w[2]) + __popcll(w[3]); };
+    auto first4 = [](const unsigned long long *w) {
+        for (int q = 0; q < kWideWords; ++q) if (w[q]) return q * 64 + __ffsll((long long)w[q]) - 1;
+        return -1;
+    };
+    if (t < kWideMax) {
+        if (t < R) {
+#pragma unroll
+            for (int q = 0; q < kWideWords; ++q) rm[q] = m.rmask[t * kWideWords + q];
+            int xr = -1;
+            const int n_adm = popc4(rm);
+            if (n_adm) {
+                const int c = first4(rm);
+                const unsigned long long *cm = m.cmask + c * kWideWords;
+                bool only_me = n_adm == 1;
+#pragma unroll
+                for (int q = 0; q < kWideWords; ++q) only_me = only_me && cm[q] == ((t >> 6) == q ? 1ull << (t & 63) : 0ull);
+                if (only_me) { xr = c; s.y[c] = t; }                   // isolated pair
+                else act = true;
+            }
+            s.x[t] = xr;
+        }
+        if (act)
+#pragma unroll
+            for (int q = 0; q < kWideWords; ++q) {
+                unsigned long long w = rm[q];
+                while (w) {
+                    const int c = q * 64 + __ffsll((long long)w) - 1;
+                    w &= w - 1;
+#pragma unroll
+                    for (int z = 0; z < kWideWords; ++z) mine[z] |= m.cmask[c * kWideWords + z];
+                }
+            }
+#pragma unroll
+        for (int q = 0; q < kWideWords; ++q) m.adj[t * kWideWords + q] = mine[q];
+    }
+    __syncthreads();
+    for (int round = 0; round < 9; ++round) {              // 2^9 > 256 rows
+        if (t == 0) changed_w = 0;
+        __syncthreads();
+        unsigned long long next[kWideWords] = {mine[0], mine[1], mine[2], mine[3]};
+        if (t < kWideMax && act) {
+#pragma unroll
+            for (int q = 0; q < kWideWords; ++q) {
+                unsigned long long w = mine[q];
+                while (w) {
+                    const int r = q * 64 + __ffsll((long long)w) - 1;
+                    w &= w - 1;
+#pragma unroll
+                    for (int z = 0; z < kWideWords; ++z) next[z] |= m.adj[r * kWideWords + z];
+                }
+            }
+            if (next[0] != mine[0] || next[1] != mine[1] || next[2] != mine[2] || next[3] != mine[3]) changed_w = 1;
+        }
+        __syncthreads();
+        if (t < kWideMax) {
+#pragma unroll
+            for (int q = 0; q < kWideWords; ++q) { m.adj[t * kWideWords + q] = next[q]; mine[q] = next[q]; }
+        }
+        __syncthreads();
+        if (!changed_w) break;
+    }
+    // the lowest row of a component publishes it
+    if (t < kWideMax && act && first4(mine) == t) {
+        unsigned long long cols[kWideWords] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+        for (int q = 0; q < kWideWords; ++q) {
+            unsigned long long w = mine[q];
+            while (w) {
+                const int r = q * 64 + __ffsll((long long)w) - 1;
+                w &= w - 1;
+#pragma unroll
+                for (int z = 0; z < kWideWords; ++z) cols[z] |= m.rmask[r * kWideWords + z];
+            }
+        }
+        const int nr = popc4(mine), nc = popc4(cols);
+        if (nr > 4 || nc > 4) {
+#pragma unroll
+            for (int q = 0; q < kWideWords; ++q) { atomicOr(&m.big[q], mine[q]); atomicOr(&m.big[4 + q], cols[q]); }
+        } else {
+            int ri[4] = {-1, -1, -1, -1}, ci[4] = {-1, -1, -1, -1};
+            {
+                int k = 0;
+#pragma unroll
+                for (int q = 0; q < kWideWords; ++q) { unsigned long long w = mine[q]; while (w && k < 4) { ri[k++] = q * 64 + __ffsll((long long)w) - 1; w &= w - 1; } }
+                k = 0;
+#pragma unroll
+                for (int q = 0; q < kWideWords; ++q) { unsigned long long w = cols[q]; while (w && k < 4) { ci[k++] = q * 64 + __ffsll((long long)w) - 1; w &= w - 1; } }
+            }
+            if (nr <= 2 && nc <= 2) {
+                if (*m.fallback == 0 && !solve_tiny_idx(P, s, ri[0], ri[1], ci[0], ci[1])) *m.fallback = 1;
+            } else {
+                const int k = atomicAdd(m.n_comp, 1);
+                if (k < kWideComps) {
+                    int *rec = m.comp + k * 10;
+                    rec[0] = nr; rec[1] = nc;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { rec[2 + q] = ri[q] < 0 ? 0 : ri[q]; rec[6 + q] = ci[q] < 0 ? 0 : ci[q]; }
+                } else {
+                    *m.fallback = 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // the larger components as index lists for solve_sub_problem (thread 0; they are few)
+    if (t == 0) {
+        const int nR = __popcll(m.big[0]) + __popcll(m.big[1]) + __popcll(m.big[2]) + __popcll(m.big[3]);
+        const int nC = __popcll(m.big[4]) + __popcll(m.big[5]) + __popcll(m.big[6]) + __popcll(m.big[7]);
+        if (nR > kSubMax || nC > kSubMax) *m.fallback = 1;
+        else if (nR > 0) {
+            float *sub_cost = reinterpret_cast<float *>(sub_mem + scratch_bytes(2 * kSubMax));
+            int *lrow = reinterpret_cast<int *>(sub_cost + kSubMax * kSubMax), *lcol = lrow + kSubMax;
+            int k = 0;
+            for (int q = 0; q < kWideWords; ++q) { unsigned long long w = m.big[q]; while (w) { lrow[k++] = q * 64 + __ffsll((long long)w) - 1; w &= w - 1; } }
+            k = 0;
+            for (int q = 0; q < kWideWords; ++q) { unsigned long long w = m.big[4 + q]; while (w) { lcol[k++] = q * 64 + __ffsll((long long)w) - 1; w &= w - 1; } }
+        }
+        m.big[0] = (unsigned long long)nR;                 // handed to the caller: number of rows / columns listed
+        m.big[1] = (unsigned long long)nC;
+    }
+    __syncthreads();
 }
 
 // Fast path with certified uniqueness, else the exact emulation of the reference's solver.
