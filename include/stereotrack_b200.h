@@ -135,6 +135,14 @@ int st_disp2depth(const uint16_t *raw, int S, int H, int W, int Hr, int Wr, int 
 int st_pack_image(const uint8_t *img, int S, int H, int W, int Hp, int Wp,
                   const uint8_t *pad_val_host, const float *mean_host, const float *std_host,
                   int swap_rb, float *out, void *stream);
+/* The same with the image branch of Resize_Disparity in front, for a resize factor != 1
+ * (transforms_disparity.py:128 -> mmdet Resize._resize_img -> mmcv.imrescale, 'bilinear', cv2 backend =
+ * cv2.resize INTER_LINEAR on the u8 image; a downscale by exactly 2 is OpenCV's 2 x 2 box average):
+ * img [S,H,W,3] u8 -> bilinear to Hr x Wr (bit-exact, 11-bit fixed-point taps) -> pad to Hp x Wp ->
+ * out [S,3,Hp,Wp] f32.  Hr == H and Wr == W is exactly the entry above. */
+int st_resize_pack_image(const uint8_t *img, int S, int H, int W, int Hr, int Wr, int Hp, int Wp,
+                         const uint8_t *pad_val_host, const float *mean_host, const float *std_host,
+                         int swap_rb, float *out, void *stream);
 
 /* disp2depth of OCSORT_Disparity (ocsort_disparity.py:132-134) on an already
  * post-processed float disparity (`disp_postp[:, 0:1]`), n contiguous elements. */

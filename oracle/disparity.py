@@ -51,6 +51,56 @@ def nearest_resize(img, new_h, new_w):
     return img[nearest_index(new_h, h)][:, nearest_index(new_w, w)]
 
 
+def _linear_coeffs(dst_n, src_n):
+    """cv2.resize(INTER_LINEAR) on 8-bit images, one axis: source index and the two 11-bit
+    fixed-point weights of every destination index (OpenCV imgproc resize.cpp, resize():
+    fx = (float)((dx + 0.5) * scale - 0.5), floor, weights saturate_cast<short>(w * 2048) with
+    round-half-even).  ``clamp`` = the horizontal pass's border rule (index clamped, weight
+    moved to the first tap); the vertical pass keeps the weights and clamps the ROW indices."""
+    scale = 1.0 / (dst_n / float(src_n))
+    f = ((np.arange(dst_n, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+    i0 = np.floor(f).astype(np.int64)
+    f = (f - i0.astype(np.float32)).astype(np.float32)
+    return i0, f
+
+
+def bilinear_resize_u8(img, new_h, new_w):
+    """The image branch of Resize_Disparity (transforms_disparity.py:24-26 -> mmdet Resize._resize_img
+    -> mmcv.imrescale(..., interpolation='bilinear', backend='cv2') == cv2.resize(INTER_LINEAR)) for an
+    8-bit [H,W,C] image, restated bit-exactly: horizontal pass to 11-bit fixed point, vertical pass
+    ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2 >> 2.  A downscale by exactly 2 in both axes
+    is the 2x2 box average (OpenCV switches INTER_LINEAR to INTER_AREA there).  Pinned against
+    cv2.resize by tests/golden/make_golden.py (ref_resize_bilinear.npz) and, where cv2 is importable,
+    tests/test_oracle_crosscheck.py."""
+    img = np.asarray(img, np.uint8)
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[:, :, None]
+    h, w = img.shape[:2]
+    if (new_h, new_w) == (h, w):
+        out = img.copy()
+    elif h == 2 * new_h and w == 2 * new_w:
+        a = img.astype(np.int32)
+        out = ((a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    else:
+        sx, fx = _linear_coeffs(new_w, w)
+        lo, hi = sx < 0, sx >= w - 1
+        fx = np.where(lo | hi, np.float32(0), fx).astype(np.float32)
+        sx = np.clip(sx, 0, w - 1)
+        a0 = np.rint((np.float32(1) - fx) * np.float32(2048)).astype(np.int32)
+        a1 = np.rint(fx * np.float32(2048)).astype(np.int32)
+        sx1 = np.minimum(sx + 1, w - 1)                 # weight 0 where sx is the last column
+        src = img.astype(np.int32)
+        rows = src[:, sx] * a0[None, :, None] + src[:, sx1] * a1[None, :, None]        # [h, new_w, C]
+        sy, fy = _linear_coeffs(new_h, h)
+        b0 = np.rint((np.float32(1) - fy) * np.float32(2048)).astype(np.int32)
+        b1 = np.rint(fy * np.float32(2048)).astype(np.int32)
+        r0 = rows[np.clip(sy, 0, h - 1)]
+        r1 = rows[np.clip(sy + 1, 0, h - 1)]
+        out = ((((b0[:, None, None] * (r0 >> 4)) >> 16) + ((b1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2).astype(np.uint8)
+    return out[:, :, 0] if squeeze else out
+
+
 def pad_to_divisor(img, divisor=32, value=0):
     """transforms_disparity.py:177-194: bottom/right constant pad."""
     h, w = img.shape[:2]
@@ -87,8 +137,9 @@ def preprocess(raw_u16, img_scale=None, size_divisor=32, baseline=0.25,
                 depth=disp2depth(disp, baseline, focal_length))
 
 
-def pack_image(img, size_divisor=32, pad_val=(114, 114, 114), mean=None, std=None, swap_rb=False):
-    """The RGB half of the detector input at resize factor 1: Pad_Disparity._pad_img
+def pack_image(img, size_divisor=32, pad_val=(114, 114, 114), mean=None, std=None, swap_rb=False, img_scale=None):
+    """The RGB half of the detector input: Resize_Disparity's image branch when ``img_scale`` is
+    given (keep_ratio; bilinear_resize_u8 to rescale_size), Pad_Disparity._pad_img
     (transforms_disparity.py:243 -> mmdet Pad: bottom/right pad of the HWC u8 image to a multiple
     of ``size_divisor`` with pad_val['img']), PackTrackInputs_Disparity HWC -> CHW
     (formatting_disparity.py:166-176), TrackDataPreprocessor_Disparity_V1.forward
@@ -96,6 +147,8 @@ def pack_image(img, size_divisor=32, pad_val=(114, 114, 114), mean=None, std=Non
     mean / std in the swapped order, stack_batch (already at the padded size).
     img [H,W,3] u8 -> [3,H',W'] float32."""
     img = np.asarray(img, np.uint8)
+    if img_scale is not None:
+        img = bilinear_resize_u8(img, *rescale_size(img.shape[0], img.shape[1], img_scale))
     H, W = img.shape[:2]
     Hp = -(-H // size_divisor) * size_divisor
     Wp = -(-W // size_divisor) * size_divisor

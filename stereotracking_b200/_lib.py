@@ -66,6 +66,7 @@ _SIGNATURES = {
     'st_box_depth': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
     'st_scale_boxes': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     'st_pack_image': (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
+    'st_resize_pack_image': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     'st_box_depth_mode': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     'st_box_depth_reuse': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'st_box_depth_raw': (_I, [_P, _I, _I, _I, _I, _I, C.c_float, C.c_float, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),

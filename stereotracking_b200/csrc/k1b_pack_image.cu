@@ -9,6 +9,10 @@
 //                                 (data_preprocessor_disparity_v1.py:38-52, utils/misc.py:13-64)
 // so that a frame crosses PCIe as 3 bytes per pixel instead of 12.  Pure streaming:
 // 3*H*W bytes read, 12*Hp*Wp bytes written per frame; HBM-bound.
+// At a resize factor != 1 (st_resize_pack_image) the same launch first applies the image branch of
+// Resize_Disparity (transforms_disparity.py:128 -> mmdet Resize._resize_img -> mmcv.imrescale
+// 'bilinear' / cv2 = cv2.resize INTER_LINEAR on the u8 image): 11-bit fixed-point taps, the
+// horizontal pass before the vertical one, bit-exact against OpenCV (tests: ref_resize_bilinear.npz).
 #include "st_common.cuh"
 
 namespace {
@@ -87,6 +91,82 @@ k1b_pack_image_generic(const unsigned char *__restrict__ img, long long n_out, i
     }
 }
 
+// ---- bilinear resize + pad + pack ------------------------------------------------------------
+struct ResizeParams {
+    int H, W, Hr, Wr, Hp, Wp;
+    double scale_x, scale_y;      // 1 / (dst / src), as OpenCV evaluates it
+    int area2;                    // downscale by exactly 2 in both axes: OpenCV's 2 x 2 box average
+};
+
+// source index and the two fixed-point weights of destination index d (OpenCV resize(): the float
+// offset is the double expression rounded to float; weights = round-half-even of w * 2048)
+__device__ __forceinline__ void linear_taps(int d, double scale, int &i0, int &w0, int &w1, int clamp_n) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int i = (int)floorf(f);
+    f = __fsub_rn(f, (float)i);
+    if (clamp_n > 0) {            // horizontal pass: border columns take the whole weight
+        if (i < 0) { f = 0.f; i = 0; }
+        if (i >= clamp_n - 1) { f = 0.f; i = clamp_n - 1; }
+    }
+    i0 = i;
+    w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+// kPx output pixels per thread (4: 128-bit stores, needs Wp % 4 == 0 and a 16-byte aligned out).
+template <int kPx>
+__global__ void __launch_bounds__(256)
+k1b_resize_pack(const unsigned char *__restrict__ img, ResizeParams r, PackParams p, float *__restrict__ out) {
+    const unsigned wq = (unsigned)r.Wp / kPx, n_items = wq * (unsigned)r.Hp;
+    const long long plane = (long long)r.Hp * r.Wp;
+    const long long s = blockIdx.y;
+    const unsigned char *__restrict__ src = img + s * r.H * r.W * 3;
+    for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+        const int y = (int)(it / wq);
+        const int x0 = (int)(it - (unsigned)y * wq) * kPx;
+        int sy = 0, b0 = 0, b1 = 0, r0 = 0, r1 = 0;
+        if (y < r.Hr) {
+            if (r.area2) { r0 = 2 * y; r1 = 2 * y + 1; }
+            else {
+                linear_taps(y, r.scale_y, sy, b0, b1, 0);
+                r0 = min(max(sy, 0), r.H - 1);            // the vertical pass clamps the ROWS, not the weights
+                r1 = min(max(sy + 1, 0), r.H - 1);
+            }
+        }
+        float v[3][kPx];
+#pragma unroll
+        for (int px = 0; px < kPx; ++px) {
+            const int x = x0 + px;
+            unsigned b[3] = {p.pad[0], p.pad[1], p.pad[2]};
+            if (y < r.Hr && x < r.Wr) {
+                int c0, a0 = 0, a1 = 0;
+                if (r.area2) c0 = 2 * x;
+                else linear_taps(x, r.scale_x, c0, a0, a1, r.W);
+                const int c1 = r.area2 ? c0 + 1 : min(c0 + 1, r.W - 1);
+                const unsigned char *p00 = src + ((long long)r0 * r.W + c0) * 3, *p01 = src + ((long long)r0 * r.W + c1) * 3;
+                const unsigned char *p10 = src + ((long long)r1 * r.W + c0) * 3, *p11 = src + ((long long)r1 * r.W + c1) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (r.area2) b[c] = ((unsigned)p00[c] + p01[c] + p10[c] + p11[c] + 2u) >> 2;
+                    else {
+                        const int h0 = p00[c] * a0 + p01[c] * a1, h1 = p10[c] * a0 + p11[c] * a1;
+                        b[c] = (unsigned)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c][px] = convert(b[c], p.swap_rb ? 2 - c : c, p);
+        }
+        float *dst = out + s * 3 * plane + (long long)y * r.Wp + x0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int co = p.swap_rb ? 2 - c : c;
+            if (kPx == 4) *reinterpret_cast<float4 *>(dst + co * plane) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+            else dst[co * plane] = v[c][0];
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int st_pack_image(const uint8_t *img, int S, int H, int W, int Hp, int Wp,
@@ -132,5 +212,38 @@ extern "C" int st_pack_image(const uint8_t *img, int S, int H, int W, int Hp, in
         if (grid > (long long)sms * 8) grid = (long long)sms * 8;
         k1b_pack_image_generic<<<(int)grid, 256, 0, st>>>(img, n_out, H, W, Hp, Wp, p, out);
     }
+    return st_last_launch();
+}
+
+extern "C" int st_resize_pack_image(const uint8_t *img, int S, int H, int W, int Hr, int Wr, int Hp, int Wp,
+                                    const uint8_t *pad_val_host, const float *mean_host, const float *std_host,
+                                    int swap_rb, float *out, void *stream) {
+    if (Hr == H && Wr == W) return st_pack_image(img, S, H, W, Hp, Wp, pad_val_host, mean_host, std_host, swap_rb, out, stream);
+    if (!img || !out || S < 0 || S > 65535 || H < 1 || W < 1 || Hr < 1 || Wr < 1 || Hp < Hr || Wp < Wr ||
+        (long long)Hp * Wp >= (1ll << 31) || (long long)H * W * 3 >= (1ll << 40) || ((mean_host == nullptr) != (std_host == nullptr)))
+        return ST_ERR_INVALID_ARG;
+    if (S == 0) return ST_OK;
+    PackParams p;
+    for (int c = 0; c < 3; ++c) {
+        p.pad[c] = pad_val_host ? pad_val_host[c] : 0;
+        p.mean[c] = mean_host ? mean_host[c] : 0.f;
+        p.std[c] = std_host ? std_host[c] : 1.f;
+    }
+    p.swap_rb = swap_rb != 0;
+    p.normalise = mean_host != nullptr;
+    ResizeParams r;
+    r.H = H; r.W = W; r.Hr = Hr; r.Wr = Wr; r.Hp = Hp; r.Wp = Wp;
+    r.scale_x = 1.0 / ((double)Wr / (double)W);
+    r.scale_y = 1.0 / ((double)Hr / (double)H);
+    r.area2 = (H == 2 * Hr && W == 2 * Wr) ? 1 : 0;
+    const int sms = st_ctx_sms();
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (Wp % 4 == 0) && ((uintptr_t)out % 16 == 0);
+    const long long per_seq = (long long)Hp * (vec ? Wp / 4 : Wp);
+    long long gx = (per_seq + 255) / 256;
+    const long long share = (long long)sms * 8 / S > 0 ? (long long)sms * 8 / S : 1;
+    if (gx > share) gx = share;
+    if (vec) k1b_resize_pack<4><<<dim3((unsigned)gx, (unsigned)S), 256, 0, st>>>(img, r, p, out);
+    else k1b_resize_pack<1><<<dim3((unsigned)gx, (unsigned)S), 256, 0, st>>>(img, r, p, out);
     return st_last_launch();
 }

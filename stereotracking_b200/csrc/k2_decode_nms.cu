@@ -96,74 +96,76 @@ k2_score_compact(HeadLevels L, const StFrameInputs *__restrict__ tab, int P, int
     }
 }
 
-// Vectorised form (every level's h*w a multiple of 4, 16-byte aligned maps): a work item
-// is 4 consecutive priors of one level of one sequence; the objectness logits are streamed
-// with 128-bit loads, and the class logits of an item are only fetched when one of its
-// objectness logits is above the cut (~1 % of the items), so the pass reads 4 bytes per
-// prior instead of 8.  A warp's 32 items belong to one sequence, so candidates are appended
-// with one atomic per warp.
-// The exact score needs float64 exp (correctly rounded sigmoid).  Evaluated where the
-// logits are found it ran at 1/32 lane efficiency in two of three warps (14 us for 5 MB);
-// so the streaming phase only screens - logit cut, then the product of fast-math sigmoids
-// against 0.9 * thr (their error is < 1e-5 relative) - and queues the survivors in shared
-// memory, and the warp then scores the queue one candidate per lane.
+// Vectorised form (every level's h*w a multiple of 4, 16-byte aligned maps): the objectness logits
+// are streamed with 128-bit loads, and the class logits of a word are only fetched when one of its
+// objectness logits is above the cut (~1 % of the words), so the pass reads 4 bytes per prior
+// instead of 8.
+// The exact score needs float64 exp (correctly rounded sigmoid).  Evaluated where the logits are
+// found it ran at 1/32 lane efficiency in two of three warps (14 us for 5 MB); so the streaming
+// phase only screens - logit cut, then the product of fast-math sigmoids against 0.9 * thr (their
+// error is < 1e-5 relative) - and queues the survivors in shared memory, and the warp then scores
+// the queue one candidate per lane.
+// (History: a tiled form - a work item = 4 priors of one level of one sequence, per-item level and
+// sequence arithmetic, 2 loads per thread - reached 0.41-0.47 of the copy peak at 512-2048 x 1080p,
+// its persistent double-buffered variant less; profiles/r02_k2_score_variants.txt.)
 constexpr int kScoreWarps = 8;
 
-// kPersist: a resident grid walks the tiles (512 priors x kItems of one sequence each) and loads
-// the NEXT tile's objectness words before it screens the current one, so the 128-bit loads of two
-// tiles are in flight per thread and no CTA launch sits between them.  Used for large batches
-// (the one-shot grid turned 43 k CTAs of 8 KB each over at 2048 x 1080p: CTA turnover, not DRAM, set
-// the pace); at the bench size the pass is launch-latency-bound and the one-shot grid starts sooner.
-template <int kItems, bool kPersist>       // kItems: 128-bit objectness loads per thread and tile
+// The objectness map of a level is ONE contiguous array [S, h*w] over
+// all sequences, so the streaming part is a flat walk over S*h*w/4 128-bit words per level with no
+// per-item level / sequence arithmetic: a tile is 256 * kItems consecutive words of one level
+// (block-uniform pointer and level), a thread issues its kItems loads, takes the maximum of each
+// word and leaves when no lane of its warp saw a logit above the cut - the case for nearly every
+// warp.  Only warps with a hit compute (sequence, prior) = divmod(element, h*w), fetch the class
+// logits, screen and score as above.  A warp's words may straddle two sequences: candidates are
+// appended with one atomic per (warp, sequence) via match_any.
+struct FlatTiles { int first[ST_MAX_LEVELS + 1]; };
+
+template <int kItems>
 __global__ void __launch_bounds__(kScoreWarps * 32)
-k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, int P, int num_classes, float score_thr, float logit_cut, int cap,
-                    int32_t *__restrict__ cand_count, float *__restrict__ cand_score,
-                    int32_t *__restrict__ cand_prior, int32_t *__restrict__ cand_label) {
-    __shared__ int32_t queue_all[kScoreWarps][128];
-    const int P4 = P >> 2;
+k2_score_flat(HeadLevels L, const StFrameInputs *__restrict__ tab, FlatTiles ft, int S, int num_classes, float score_thr, float logit_cut,
+              int cap, int32_t *__restrict__ cand_count, float *__restrict__ cand_score, int32_t *__restrict__ cand_prior,
+              int32_t *__restrict__ cand_label) {
+    __shared__ int32_t queue_all[kScoreWarps][128 * kItems];
     const int lane = threadIdx.x & 31;
-    int32_t *queue = queue_all[threadIdx.x >> 5];
-    const float screen_thr = __fmul_rn(score_thr, 0.9f);
-    // tiles: (ceil(items_pad / (256 kItems)) per sequence) x S; all index arithmetic 32-bit (a flat
-    // 64-bit item index cost two 64-bit divisions per item and made the pass instruction-bound)
-    const int tiles_per_seq = kPersist ? (((P4 + 31) & ~31) + kScoreWarps * 32 * kItems - 1) / (kScoreWarps * 32 * kItems) : (int)gridDim.x;
-    const int total_tiles = tiles_per_seq * S;
-    int tile = kPersist ? (int)blockIdx.x : (int)(blockIdx.y * gridDim.x + blockIdx.x);
-    auto load_tile = [&](int t, float4 (&o)[kItems]) {
-        const int s_ = t / tiles_per_seq, jt = t - s_ * tiles_per_seq;
-#pragma unroll
-        for (int u = 0; u < kItems; ++u) {
-            const int j = (jt * kItems + u) * blockDim.x + threadIdx.x;
-            o[u] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
-            if (j < P4) {
-                const int l = level_of(L, j * 4);
-                asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                             : "=f"(o[u].x), "=f"(o[u].y), "=f"(o[u].z), "=f"(o[u].w)
-                             : "l"(K2_OBJ(l) + (long long)s_ * L.h[l] * L.w[l] + (j * 4 - L.prior_off[l])));
-            }
-        }
-    };
-    float4 o4s[kItems], nxt[kItems];
-    if (tile < total_tiles) load_tile(tile, o4s);
-    while (tile < total_tiles) {
-    const int next_tile = kPersist ? tile + (int)gridDim.x : total_tiles;
-    if (kPersist && next_tile < total_tiles) load_tile(next_tile, nxt);
-    const int s = tile / tiles_per_seq, jt0 = tile - s * tiles_per_seq;
+    int l = 0;
+    while (l + 1 < L.n && (int)blockIdx.x >= ft.first[l + 1]) ++l;          // block-uniform
+    const int hw = L.h[l] * L.w[l];
+    const int n4 = (int)(((long long)S * hw) >> 2);
+    const float *__restrict__ obj = K2_OBJ(l);
+    const int i0 = ((int)blockIdx.x - ft.first[l]) * (kScoreWarps * 32 * kItems) + threadIdx.x;
+    float4 o4s[kItems];
+    bool hit = false;
 #pragma unroll
     for (int u = 0; u < kItems; ++u) {
-    const int j = (jt0 * kItems + u) * blockDim.x + threadIdx.x;
-    unsigned keep = 0u;                                  // priors of this item that survive the screen
-    const int p0 = j * 4;
-    if (j < P4) {
-        const int l = level_of(L, p0);
-        const int q = p0 - L.prior_off[l];
-        const long long hw = (long long)L.h[l] * L.w[l];
+        const int i = i0 + u * (kScoreWarps * 32);
+        o4s[u] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
+        if (i < n4)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(o4s[u].x), "=f"(o4s[u].y), "=f"(o4s[u].z), "=f"(o4s[u].w)
+                         : "l"(obj + (long long)i * 4));
+    }
+#pragma unroll
+    for (int u = 0; u < kItems; ++u)       // fmaxf drops NaN: a NaN logit is never above the cut, as in the exact test
+        hit = hit || fmaxf(fmaxf(o4s[u].x, o4s[u].y), fmaxf(o4s[u].z, o4s[u].w)) > logit_cut;
+    if (!__any_sync(0xffffffffu, hit)) return;
+    // ---- a lane of this warp saw a logit above the cut (everything below is fully unrolled: the loaded
+    // words stay in registers) ----
+    int32_t *queue = queue_all[threadIdx.x >> 5];
+    const float screen_thr = __fmul_rn(score_thr, 0.9f);
+    const float *__restrict__ cls = K2_CLS(l);
+    const int p_off = L.prior_off[l];
+    // screen: bit 4u+k = prior k of word u survives the logit cut and the fast-math product test
+    unsigned keep = 0u;
+#pragma unroll
+    for (int u = 0; u < kItems; ++u) {
         const float4 o4 = o4s[u];
         const float lo[4] = {o4.x, o4.y, o4.z, o4.w};
         if (lo[0] > logit_cut || lo[1] > logit_cut || lo[2] > logit_cut || lo[3] > logit_cut) {
-            float mc[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};     // max class logit
+            const int e0 = (i0 + u * (kScoreWarps * 32)) * 4;               // element of the level's [S, hw] array
+            const int s = e0 / hw, q = e0 - s * hw;                         // hw % 4 == 0: the word lies in one sequence
+            float mc[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};         // max class logit
             for (int c = 0; c < num_classes; ++c) {
-                const float4 c4 = *reinterpret_cast<const float4 *>(K2_CLS(l) + ((long long)s * num_classes + c) * hw + q);
+                const float4 c4 = *reinterpret_cast<const float4 *>(cls + ((long long)s * num_classes + c) * hw + q);
                 mc[0] = fmaxf(mc[0], c4.x); mc[1] = fmaxf(mc[1], c4.y);
                 mc[2] = fmaxf(mc[2], c4.z); mc[3] = fmaxf(mc[3], c4.w);
             }
@@ -171,37 +173,46 @@ k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, 
             for (int k = 0; k < 4; ++k) {
                 if (!(lo[k] > logit_cut) || !(mc[k] > logit_cut)) continue;
                 const float approx = __fdividef(1.0f, (1.0f + __expf(-lo[k])) * (1.0f + __expf(-mc[k])));
-                if (!(approx < screen_thr)) keep |= 1u << k;           // NaN logits stay in and fail exactly
+                if (!(approx < screen_thr)) keep |= 1u << (4 * u + k);     // NaN class logits stay in and fail exactly
             }
         }
     }
-    // queue the survivors of the warp's 128 priors
-    int n_q = 0;
+    // one queue for the warp's survivors: exclusive prefix of the per-lane counts
+    const int mine = __popc(keep);
+    int incl = mine;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const bool f = (keep >> k) & 1u;
-        const unsigned b = __ballot_sync(0xffffffffu, f);
-        if (f) queue[n_q + __popc(b & ((1u << lane) - 1u))] = p0 + k;
-        n_q += __popc(b);
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
     }
-    if (n_q == 0) continue;                              // warp-uniform
+    const int n_q = __shfl_sync(0xffffffffu, incl, 31);
+    if (n_q == 0) return;
+    {
+        int pos = incl - mine;
+        unsigned kb = keep;
+        while (kb) {
+            const int b = __ffs(kb) - 1;
+            kb &= kb - 1;
+            queue[pos++] = (i0 + (b >> 2) * (kScoreWarps * 32)) * 4 + (b & 3);
+        }
+    }
     __syncwarp();
     // exact scores, one candidate per lane
     for (int c0 = 0; c0 < n_q; c0 += 32) {
         const bool have = c0 + lane < n_q;
         bool pass = false;
         float score = 0.f;
-        int label = 0, p = 0;
+        int label = 0, p = 0, s = -1;
         if (have) {
-            p = queue[c0 + lane];
-            const int l = level_of(L, p);
-            const int q = p - L.prior_off[l];
-            const long long hw = (long long)L.h[l] * L.w[l];
-            const float so = st_sigmoid_f32(K2_OBJ(l)[(long long)s * hw + q]);
+            const int e = queue[c0 + lane];
+            s = e / hw;
+            const int q = e - s * hw;
+            p = p_off + q;
+            const float so = st_sigmoid_f32(obj[e]);
             // scores = sigmoid(cls) * sigmoid(obj); max over classes, first max wins
             float best = -1.f;
             for (int c = 0; c < num_classes; ++c) {
-                const float lc = K2_CLS(l)[((long long)s * num_classes + c) * hw + q];
+                const float lc = cls[((long long)s * num_classes + c) * hw + q];
                 if (!(lc > logit_cut)) continue;
                 const float v = __fmul_rn(st_sigmoid_f32(lc), so);
                 if (v > best) { best = v; label = c; }
@@ -211,25 +222,19 @@ k2_score_compact_v4(HeadLevels L, const StFrameInputs *__restrict__ tab, int S, 
         }
         const unsigned ballot = __ballot_sync(0xffffffffu, pass);
         if (ballot == 0) continue;
-        int base = 0;
-        if (lane == (__ffs(ballot) - 1)) base = atomicAdd(&cand_count[s], __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
         if (pass) {
-            const int pos = base + __popc(ballot & ((1u << lane) - 1u));
+            const unsigned peers = __match_any_sync(ballot, s);            // the passing lanes of the same sequence
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&cand_count[s], __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const int pos = base + __popc(peers & ((1u << lane) - 1u));
             if (pos < cap) {
                 cand_score[(long long)s * cap + pos] = score;
                 cand_prior[(long long)s * cap + pos] = p;
                 cand_label[(long long)s * cap + pos] = label;
             }
         }
-    }
-    __syncwarp();
-    }
-    tile = next_tile;
-    if (kPersist) {
-#pragma unroll
-        for (int u = 0; u < kItems; ++u) o4s[u] = nxt[u];
-    }
     }
 }
 
@@ -491,27 +496,27 @@ int st_decode_nms_ws(st_handle *h, const float *const *cls_host, const float *co
     for (int l = 0; l < num_levels; ++l)
         vec4 = vec4 && (level_h_host[l] * level_w_host[l]) % 4 == 0 && ((uintptr_t)cls_host[l] % 16 == 0) &&
                ((uintptr_t)obj_host[l] % 16 == 0);
-    if (vec4) {
-        const int items_pad = ((P >> 2) + 31) & ~31;
-        const int tiles = (items_pad + kScoreWarps * 64 - 1) / (kScoreWarps * 64);
-        bool persist = (long long)tiles * S >= 8192;                        // >= 16 M priors per call
-        if (const char *e = getenv("ST_K2_PERSIST")) persist = atoi(e) != 0;   // tuning aid
-        if (persist) {
-            struct Dev { int grid; };
-            static StPerDevice<Dev> per_device;
-            const Dev *dv = per_device.get([](Dev &v) {
-                int per_sm = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_score_compact_v4<2, true>, kScoreWarps * 32, 0) != cudaSuccess || per_sm < 1)
-                    per_sm = 4;
-                v.grid = st_ctx_sms() * per_sm;
-                return true;
-            });
-            k2_score_compact_v4<2, true><<<dv ? dv->grid : 592, kScoreWarps * 32, 0, st>>>(
-                L, tab, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
-        } else {
-            k2_score_compact_v4<2, false><<<dim3(tiles, S), kScoreWarps * 32, 0, st>>>(
-                L, tab, S, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);
+    bool flat = vec4;
+    for (int l = 0; l < num_levels; ++l) flat = flat && (long long)S * level_h_host[l] * level_w_host[l] < (1ll << 31);
+    if (flat) {
+        // 128-bit loads per thread: enough CTAs for every SM at the bench size, 32 KB per CTA in flight once
+        // the pass is bandwidth-bound (2048 x 1080p, kernel alone: 85.5 / 65.0 / 53.1 us with 2 / 4 / 8)
+        static const int forced = [] { const char *e = getenv("ST_K2_ITEMS"); return e ? atoi(e) : 0; }();
+        const long long words = ((long long)S * P) >> 2;
+        const int items = forced ? forced : (words < (1ll << 20) ? 2 : (words < (1ll << 22) ? 4 : 8));
+        FlatTiles ft;
+        int n_tiles = 0;
+        const int per_tile = kScoreWarps * 32 * (items == 2 ? 2 : items == 8 ? 8 : 4);
+        for (int l = 0; l < num_levels; ++l) {
+            ft.first[l] = n_tiles;
+            const long long n4 = ((long long)S * level_h_host[l] * level_w_host[l]) >> 2;
+            n_tiles += (int)((n4 + per_tile - 1) / per_tile);
         }
+        ft.first[num_levels] = n_tiles;
+#define K2_FLAT(IT) k2_score_flat<IT><<<n_tiles, kScoreWarps * 32, 0, st>>>(L, tab, ft, S, num_classes, h->cfg.score_thr, logit_cut, cap, \
+                                                                            ws->count, ws->score, ws->prior, ws->label)
+        if (items == 2) K2_FLAT(2); else if (items == 8) K2_FLAT(8); else K2_FLAT(4);
+#undef K2_FLAT
     } else {
         k2_score_compact<<<dim3((P + 255) / 256, S), 256, 0, st>>>(
             L, tab, P, num_classes, h->cfg.score_thr, logit_cut, cap, ws->count, ws->score, ws->prior, ws->label);

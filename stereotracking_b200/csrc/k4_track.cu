@@ -201,6 +201,7 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
         stlap::Problem P;
         P.cost = cost; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
         P.dbg = st.debug + (sbase / pr.T) * ST_DEBUG_WORDS;
+        P.why = nullptr;
         P.row_cnt = sm.row_cnt; P.col_cnt = sm.col_cnt; P.row_adm = sm.row_adm; P.adm_misc = sm.adm_misc;
         P.mark(0, stage_code); P.mark(1, R); P.mark(2, C);
         // debug words 5/6: assignments solved / solved by the exact fallback (this handle's lifetime)
@@ -613,6 +614,7 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
     stlap::Problem P;
     P.cost = cost + (long long)b * R * C; P.R = R; P.C = C; P.n = R + C; P.half = half;
     P.dbg = nullptr;
+    P.why = nullptr;
     int *stats = reinterpret_cast<int *>(smem_raw + stlap::scratch_bytes(R + C));
     P.row_cnt = stats; P.row_adm = stats + R; P.col_cnt = stats + 2 * R; P.adm_misc = stats + 2 * R + C;
     if (R > 0 && C > 0) {

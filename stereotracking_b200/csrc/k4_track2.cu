@@ -231,6 +231,7 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
     stlap::Problem P;
     P.cost = dense; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
     P.dbg = nullptr;                                     // no progress marks on the critical path
+    P.why = stage_code == 1 ? dbg + 24 : nullptr;        // debug words 24..31: the whole-problem fast path of stage 1
     P.row_cnt = sm.row_cnt; P.col_cnt = sm.col_cnt; P.row_adm = sm.row_adm; P.adm_misc = sm.adm_misc;
     const bool skip = (g_skip >> (stage_code - 1)) & 1;
     bool need_warp_path;

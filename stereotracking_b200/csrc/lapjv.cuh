@@ -56,6 +56,9 @@ struct Problem {
     int R, C, n;
     double half;          // cost_limit / 2
     int *dbg;             // optional [8] progress words (global), may be null
+    int *why;             // optional [8] diagnostics of fast_assign_warp (global), may be null: [0] code of the
+                          // last refusal, [1] refusals, [2..4] cycles of start / search / certificate of the last
+                          // call, [5] rows searched, [6] active rows, [7] tight arcs
     // Admissible-edge statistics of the fast path (cost < L = 2 * half): number of
     // admissible entries per row / column, one admissible column of each row, and
     // adm_misc[0] != 0 when the matrix holds a NaN, adm_misc[1] != 0 when a cost lies within
@@ -462,6 +465,7 @@ __device__ bool hungarian_regs(const Problem &P, volatile double *u, volatile do
     for (int k = 0; k < KC; ++k) vv[k] = 0.0;
     for (int t = 0; t < n_active; ++t) {
         const int row = active[t];
+        if (row < 0) continue;                     // matched by the greedy start
         double minv[KC];
         int way[KC];
         unsigned used = 0u;
@@ -550,6 +554,12 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
     volatile int *p = s.x, *way = s.y, *active = s.free_rows;
     volatile unsigned char *used = s.unique;
     const double INF = 1.0e300;
+    const long long t_f0 = clock64();
+#define ST_REFUSE(code)                                                                     \
+    do {                                                                                    \
+        if (P.why && lane == 0) { P.why[0] = (code); atomicAdd(&P.why[1], 1); }             \
+        return false;                                                                       \
+    } while (0)
     // ---- row pruning, NaN screen, isolated pairs ----------------------------------------
     // Rows without an admissible entry (cost < L) can never be matched: u_i = L/2.
     // A row whose only admissible column has no other admissible row is matched
@@ -557,13 +567,20 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
     // reaches when it inserts that row first (every other entry of the row and of
     // the column costs at least the dummy).  In tracking most pairs are of this
     // kind, so the shortest-path search runs only for the crowded remainder.
-    if (P.adm_misc[0] || P.adm_misc[1]) return false;      // NaN, or a cost within 2e-9 of L (tie with the dummies)
-    for (int j = lane; j < m; j += 32) { v[j] = 0.0; p[j] = -1; }
+    if (P.adm_misc[0] || P.adm_misc[1]) ST_REFUSE(1);      // NaN, or a cost within 2e-9 of L (tie with the dummies)
+    for (int j = lane; j < m; j += 32) { v[j] = 0.0; p[j] = -1; way[j] = 0x7fffffff; }
     __syncwarp();
+    // Greedy start for the remaining rows: u_i = the row's smallest reduced entry (duals stay feasible:
+    // v = 0, every entry of the row >= u_i, the dummy costs half > u_i) and the row takes that column
+    // unless a lower row wants it too (way[] collects the lowest claimant).  Only the rows that lose
+    // a claim go through the shortest-path search - in a crowd nearly every track still has "its"
+    // detection.  `active` lists every non-isolated row with admissible entries (the certificate scans
+    // them all); rows matched by the greedy start are stored as ~row and skipped by the search.
     int n_active = 0;
     for (int i0 = 0; i0 < R; i0 += 32) {
         const int i = i0 + lane;
         bool act = false;
+        int best_j = -1;
         if (i < R) {
             const int cnt = P.row_cnt[i];
             double ui = half;
@@ -573,15 +590,29 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
                 ui = (double)P.cost[(long long)i * C + j] - half;
             } else if (cnt > 0) {
                 act = true;
-                ui = 0.0;
+                float bc = 3.0e38f;
+                const float *crow = P.cost + (long long)i * C;
+                for (int j = 0; j < C; ++j) { const float c = crow[j]; if (c < bc) { bc = c; best_j = j; } }
+                ui = (double)bc - half;
+                atomicMin(const_cast<int *>(way) + best_j, i);
             }
             u[i] = ui;
         }
         const unsigned mb = __ballot_sync(0xffffffffu, act);
-        if (act) active[n_active + __popc(mb & ((1u << lane) - 1u))] = i;
+        if (act) active[n_active + __popc(mb & ((1u << lane) - 1u))] = i | (best_j << 16);
         n_active += __popc(mb);
     }
     __syncwarp();
+    int n_search = 0;
+    for (int t = lane; t < n_active; t += 32) {
+        const int packed = active[t], i = packed & 0xffff, j = packed >> 16;
+        const bool won = way[j] == i;
+        if (won) p[j] = i;
+        active[t] = won ? ~i : i;
+        n_search += won ? 0 : 1;
+    }
+    __syncwarp();
+    const int n_search_total = __reduce_add_sync(0xffffffffu, n_search);
     // a(i, j): real column -> c_ij - half ; own dummy column C+i -> half ; else INF
     auto a = [&](int i, int j) -> double {
         if (j < C) return (double)P.cost[(long long)i * C + j] - half;
@@ -596,18 +627,19 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
         else if (C <= 64) ok = hungarian_regs<2>(P, u, v, p, way, active, n_active);
         else if (C <= 128) ok = hungarian_regs<4>(P, u, v, p, way, active, n_active);
         else ok = hungarian_regs<8>(P, u, v, p, way, active, n_active);
-        if (!ok) return false;
+        if (!ok) ST_REFUSE(2);
         solved = true;
     }
     if (!solved) {
     for (int t = 0; t < n_active; ++t) {
         const int row = active[t];
+        if (row < 0) continue;                     // matched by the greedy start
         for (int j = lane; j < m; j += 32) { minv[j] = INF; used[j] = 0; }
         __syncwarp();
         int j0 = m;                       // virtual start column holding `row`
         int guard = 0;
         while (true) {
-            if (++guard > m + 2) return false;
+            if (++guard > m + 2) ST_REFUSE(3);
             if (j0 < m && lane == 0) used[j0] = 1;
             __syncwarp();
             const int i0 = j0 == m ? row : p[j0];
@@ -632,7 +664,7 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
                 const int oj = __shfl_xor_sync(0xffffffffu, j1, o);
                 if (pair_less(od, oj, delta, j1)) { delta = od; j1 = oj; }
             }
-            if (j1 < 0 || !(delta < INF)) return false;
+            if (j1 < 0 || !(delta < INF)) ST_REFUSE(4);
             __syncwarp();
             // dual update: visited columns (and the virtual one) move with their rows
             for (int j = lane; j < m; j += 32) {
@@ -686,7 +718,7 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
     // stepping through the columns together (cost ~ C steps per 32 rows).
     if (n_active * ((C + 31) / 32) * 2 < C) {
         for (int t = 0; t < n_active; ++t) {
-            const int i = active[t];
+            const int i = active[t] < 0 ? ~active[t] : active[t];
             const double ui = u[i];
             const float hu = (float)(half + ui);
             const int si = sigma[i];
@@ -706,7 +738,7 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
     for (int t0 = 0; t0 < n_active; t0 += 32) {
         const int t = t0 + lane;
         const bool hv = t < n_active;
-        const int i = hv ? active[t] : 0;
+        const int i = hv ? (active[t] < 0 ? ~active[t] : active[t]) : 0;
         const double ui = hv ? u[i] : 0.0;
         const float hu = (float)(half + ui);
         const int si = hv ? sigma[i] : -1;
@@ -749,7 +781,7 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
         if (tight && pos < m) { arc_from[pos] = from; arc_to[pos] = C + i; }
         n_arcs += __popc(tb);
     }
-    if (n_arcs > m) return false;                       // more tight edges than the list holds
+    if (n_arcs > m) ST_REFUSE(5);                       // more tight edges than the list holds
     __syncwarp();
     const long long t_c1 = clock64();
     long long t_c2 = t_c1;
@@ -791,7 +823,7 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
             if (!__any_sync(0xffffffffu, drop)) break;
         }
         unsure |= alive;
-        if (__any_sync(0xffffffffu, unsure)) return false;
+        if (__any_sync(0xffffffffu, unsure)) ST_REFUSE(6);
     } else if (n_arcs > 0) {
         // column flags live where the row potentials were (no longer needed)
         volatile unsigned char *assigned = reinterpret_cast<volatile unsigned char *>(s.cols);
@@ -831,9 +863,13 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
             if (!__any_sync(0xffffffffu, changed)) break;
         }
         for (int j = lane; j < m; j += 32) unsure |= alive[j] != 0;    // survivors lie on a cycle
-        if (__any_sync(0xffffffffu, unsure)) return false;
+        if (__any_sync(0xffffffffu, unsure)) ST_REFUSE(7);
     }
     __syncwarp();
+    if (P.why && lane == 0) {
+        P.why[2] = (int)(t_h0 - t_f0); P.why[3] = (int)(t_h1 - t_h0); P.why[4] = (int)(clock64() - t_h1);
+        P.why[5] = n_search_total; P.why[6] = n_active; P.why[7] = n_arcs;
+    }
     // diagnostics (debug words 14 / 15): cycles of the search and of the certificate, last call
     if (P.dbg && lane == 0 && P.dbg[0] == 1) {          // stage 1 of the track step only
         P.dbg[14] = (int)(t_h1 - t_h0); P.dbg[15] = (int)(clock64() - t_h1);
@@ -859,6 +895,7 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
     __syncwarp();
     return true;
 }
+#undef ST_REFUSE
 
 // ---------------------------------------------------------------------------------
 // Component path (problems with R, C <= 64).  The objective of the extended problem is
@@ -1257,7 +1294,7 @@ __device__ inline bool solve_sub_problem(const Problem &P, Scratch &s, unsigned 
     float *sub_cost = reinterpret_cast<float *>(sub_mem + scratch_bytes(2 * kSubMax));
     int *lrow = reinterpret_cast<int *>(sub_cost + kSubMax * kSubMax), *lcol = lrow + kSubMax;
     Problem Q;
-    Q.R = nR; Q.C = nC; Q.n = Q.R + Q.C; Q.half = P.half; Q.dbg = nullptr;
+    Q.R = nR; Q.C = nC; Q.n = Q.R + Q.C; Q.half = P.half; Q.dbg = nullptr; Q.why = nullptr;
     Q.cost = sub_cost;
     Q.row_cnt = lcol + kSubMax; Q.row_adm = Q.row_cnt + kSubMax; Q.col_cnt = Q.row_adm + kSubMax;
     Q.adm_misc = Q.col_cnt + kSubMax;

@@ -232,24 +232,26 @@ class StereoTrackEngine:
         return depth, disp3, mask
 
     def pack_image(self, img, size_divisor=32, pad_val=(114, 114, 114), mean=None, std=None, swap_rb=False,
-                   out=None):
-        """K1b: u8 frames [S,H,W,3] (device) -> the detector's float32 input [S,3,H',W'] (pad with
-        ``pad_val`` to a multiple of ``size_divisor``, HWC->CHW, optional channel swap and
-        (img - mean) / std; see st_pack_image)."""
+                   out=None, resized_hw=None):
+        """K1b: u8 frames [S,H,W,3] (device) -> the detector's float32 input [S,3,H',W'] (optional
+        bilinear resize to ``resized_hw`` as cv2.resize INTER_LINEAR does it, pad with ``pad_val`` to a
+        multiple of ``size_divisor``, HWC->CHW, optional channel swap and (img - mean) / std; see
+        st_pack_image / st_resize_pack_image)."""
         import ctypes
         S, H, W, ch = img.shape
         if ch != 3 or img.dtype != torch.uint8:
             raise ValueError('img must be [S,H,W,3] uint8')
         if (mean is None) != (std is None):
             raise AssertionError('mean and std should be both None or tuple')      # data_preprocessor.py:65-66
-        Hp = -(-H // size_divisor) * size_divisor if size_divisor > 1 else H
-        Wp = -(-W // size_divisor) * size_divisor if size_divisor > 1 else W
+        Hr, Wr = resized_hw or (H, W)
+        Hp = -(-Hr // size_divisor) * size_divisor if size_divisor > 1 else Hr
+        Wp = -(-Wr // size_divisor) * size_divisor if size_divisor > 1 else Wr
         out = out if out is not None else torch.empty(S, 3, Hp, Wp, dtype=torch.float32, device=img.device)
         pad = (ctypes.c_uint8 * 3)(*[int(v) for v in pad_val])
         m = (ctypes.c_float * 3)(*mean) if mean is not None else None
         sd = (ctypes.c_float * 3)(*std) if std is not None else None
-        _lib.check(self.lib.st_pack_image(_ptr(img.contiguous()), S, H, W, Hp, Wp, pad, m, sd, int(bool(swap_rb)),
-                                          _ptr(out), self._stream()), 'st_pack_image')
+        _lib.check(self.lib.st_resize_pack_image(_ptr(img.contiguous()), S, H, W, Hr, Wr, Hp, Wp, pad, m, sd,
+                                                 int(bool(swap_rb)), _ptr(out), self._stream()), 'st_resize_pack_image')
         return out
 
     def disp_to_depth(self, disp, out=None):

@@ -471,6 +471,33 @@ def make_writers(ns):
     print('writers:', len(csv_text), 'bytes of csv,', len(mot_text), 'bytes of MOT txt')
 
 
+def make_resize(ns):
+    """Image branch of Resize_Disparity at a resize factor != 1 (transforms_disparity.py:128 runs mmdet's
+    Resize._resize_img: ``mmcv.imrescale(img, scale, interpolation='bilinear', return_scale=True,
+    backend='cv2')``).  mmdet / mmcv are third-party and absent; their two steps are executed here as
+    they are written there: new size = int(side * factor + 0.5) with factor = min(long / max(h, w),
+    short / min(h, w)) (mmcv rescale_size), then ``cv2.resize(img, (w, h), interpolation=cv2.INTER_LINEAR)``
+    with the OpenCV of this image (the library the reference itself calls)."""
+    import cv2
+    rng = np.random.default_rng(31)
+    out = {}
+    cases = dict(down=((54, 96), (36, 64)), up=((45, 80), (72, 128)), half=((64, 96), (32, 48)),
+                 odd=((37, 53), (50, 90)), tall=((80, 30), (64, 64)))
+    for tag, ((H, W), scale) in cases.items():
+        img = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+        if tag == 'odd':                                  # smooth content too, not only noise
+            yy, xx = np.mgrid[0:H, 0:W]
+            img = np.stack([(xx * 255 // (W - 1)), (yy * 255 // (H - 1)), ((xx + yy) % 256)], -1).astype(np.uint8)
+        factor = min(max(scale) / max(H, W), min(scale) / min(H, W))
+        nw, nh = int(W * float(factor) + 0.5), int(H * float(factor) + 0.5)
+        res = cv2.resize(img, (nw, nh), dst=None, interpolation=cv2.INTER_LINEAR)
+        out[f'img_{tag}'] = img
+        out[f'scale_{tag}'] = np.asarray(scale, np.int64)
+        out[f'out_{tag}'] = res
+    np.savez_compressed(os.path.join(OUT, 'ref_resize_bilinear.npz'), **out)
+    print('resize:', {k: v.shape for k, v in out.items() if k.startswith('out_')})
+
+
 def make_sequences(ns, only=None):
     scen = {
         'basic': dict(cfg=SceneConfig(160, 224, 5, 8, n_clutter=0), F=36, seed=3, miss=0.05, clutter=3, blackout=()),
@@ -521,6 +548,7 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['round2']:               # fixtures added in round 2 (read ref_kf.npz / ref_track_basic.npz)
         make_kf_nsa(ns)
         make_writers(ns)
+        make_resize(ns)
         sys.exit(0)
     make_kf(ns)
     make_kf_gating(ns)
@@ -531,4 +559,5 @@ if __name__ == '__main__':
     make_memo(ns)
     make_kf_nsa(ns)
     make_writers(ns)
+    make_resize(ns)
     print('golden fixtures written to', OUT)

@@ -96,6 +96,39 @@ def test_k1b_pack_image_bit_exact(mods):
     assert eng.lib.st_pack_image(None, 1, 8, 8, 8, 8, None, None, None, 0, out.data_ptr(), None) != 0
 
 
+def test_k1b_resize_pack_bit_exact(mods):
+    """Resize factor != 1: the image branch of Resize_Disparity (cv2.resize INTER_LINEAR through mmcv.imrescale)
+    fused in front of pad + pack - OpenCV-generated vectors, then a 1080p -> 720p batch, an upscale, the exact
+    2 x downscale (OpenCV's box average) and an unaligned output width against the oracle."""
+    g = np.load(os.path.join(GOLDEN, 'ref_resize_bilinear.npz'))
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    norm = dict(mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375), swap_rb=True)
+    for tag in ('down', 'up', 'half', 'odd', 'tall'):
+        img, scale, ref = g[f'img_{tag}'], tuple(int(v) for v in g[f'scale_{tag}']), g[f'out_{tag}']
+        hw = mods.disparity.rescale_size(img.shape[0], img.shape[1], scale)
+        assert hw == ref.shape[:2]
+        np.testing.assert_array_equal(eng.pack_image(cuda(img[None]), resized_hw=hw)[0].cpu().numpy(),
+                                      mods.disparity.pack_image(ref))
+        np.testing.assert_array_equal(eng.pack_image(cuda(img[None]), resized_hw=hw, **norm)[0].cpu().numpy(),
+                                      mods.disparity.pack_image(ref, **norm))
+        # no pad, any width: one output pixel per thread
+        got = eng.pack_image(cuda(img[None]), resized_hw=hw, size_divisor=1)[0].cpu().numpy()
+        np.testing.assert_array_equal(got, ref.transpose(2, 0, 1).astype(np.float32))
+    rng = np.random.default_rng(37)
+    big = rng.integers(0, 256, (3, 1080, 1920, 3)).astype(np.uint8)
+    for scale in ((720, 1280), (540, 960), (1200, 2200)):
+        hw = mods.disparity.rescale_size(1080, 1920, scale)
+        out = eng.pack_image(cuda(big), resized_hw=hw, **norm)
+        for s in (0, 2):
+            np.testing.assert_array_equal(out[s].cpu().numpy(), mods.disparity.pack_image(big[s], img_scale=scale, **norm))
+    same = eng.pack_image(cuda(big), resized_hw=(1080, 1920))                 # factor 1 = st_pack_image
+    np.testing.assert_array_equal(same[1].cpu().numpy(), mods.disparity.pack_image(big[1]))
+    out = torch.empty(1, 3, 32, 32, device='cuda')
+    img = cuda(big[:1, :40, :40].copy())
+    assert eng.lib.st_resize_pack_image(img.data_ptr(), 1, 40, 40, 0, 20, 32, 32, None, None, None, 0, out.data_ptr(), None) != 0
+    assert eng.lib.st_resize_pack_image(img.data_ptr(), 1, 40, 40, 33, 20, 32, 32, None, None, None, 0, out.data_ptr(), None) != 0
+
+
 def _head_case(mods, cfg_name, S, seed, frames=2):
     cfg = mods.CONFIGS[cfg_name]
     gen = mods.SyntheticStereo(cfg, S, frames, seed=seed)

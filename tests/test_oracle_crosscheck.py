@@ -94,6 +94,21 @@ def test_nearest_resize_matches_opencv():
         np.testing.assert_array_equal(disparity.nearest_resize(img, nh, nw), ref)
 
 
+def test_bilinear_resize_matches_opencv():
+    """bilinear_resize_u8 = cv2.resize(INTER_LINEAR) on 8-bit images, any size pair (including the exact
+    2 x downscale, where OpenCV switches to the box average, and 1-pixel sides)."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(5)
+    shapes = [((1080, 1920), (720, 1280)), ((720, 1280), (1080, 1920)), ((480, 640), (240, 320)), ((100, 100), (50, 100)),
+              ((9, 7), (1, 1)), ((1, 1), (4, 4)), ((2, 2), (1, 1)), ((300, 400), (100, 133)), ((64, 64), (63, 65))]
+    shapes += [((int(rng.integers(1, 150)), int(rng.integers(1, 150))), (int(rng.integers(1, 200)), int(rng.integers(1, 200))))
+               for _ in range(25)]
+    for (h, w), (nh, nw) in shapes:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(disparity.bilinear_resize_u8(img, nh, nw),
+                                      cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR), err_msg=str(((h, w), (nh, nw))))
+
+
 def test_preprocess_shapes_and_invalid():
     raw = np.full((720, 1280), 160, np.uint16)
     raw[:10] = 65535

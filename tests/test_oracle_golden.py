@@ -68,6 +68,20 @@ def test_pack_image_matches_reference_lines():
     assert (g['out_plain_a'][:, 40:, :] == 114).all() and (g['out_plain_a'][:, :, 52:] == 114).all()
 
 
+def test_bilinear_resize_matches_opencv_vectors():
+    """Resize_Disparity's image branch (mmcv.imrescale 'bilinear' = cv2.resize INTER_LINEAR), bit-exact, and
+    the packed detector input behind it."""
+    g = np.load(os.path.join(GOLDEN, 'ref_resize_bilinear.npz'))
+    for tag in ('down', 'up', 'half', 'odd', 'tall'):
+        img, scale, ref = g[f'img_{tag}'], tuple(int(v) for v in g[f'scale_{tag}']), g[f'out_{tag}']
+        nh, nw = disparity.rescale_size(img.shape[0], img.shape[1], scale)
+        assert (nh, nw) == ref.shape[:2], tag
+        np.testing.assert_array_equal(disparity.bilinear_resize_u8(img, nh, nw), ref)
+        np.testing.assert_array_equal(disparity.pack_image(img, img_scale=scale), disparity.pack_image(ref))
+    one = g['img_down'][:, :, 0]
+    np.testing.assert_array_equal(disparity.bilinear_resize_u8(one, 36, 64), g['out_down'][:, :, 0])
+
+
 @pytest.mark.parametrize('mode', boxdepth.ABLATION_MODES)
 def test_boxdepth_ablation_matches_reference(mode):
     """The four reducers of depth_extraction_comparison.py, box by box (center raises

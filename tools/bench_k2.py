@@ -52,7 +52,11 @@ def run(name, S, hw, reps=30, with_objects=False):
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'big':          # one case, for an ncu capture
+        run('C3 512 x 1920x1080, background only', 512, (1088, 1920), reps=12)
+        sys.exit(0)
     run('C2 64 x 1280x720, background only', 64, (736, 1280))
     run('C2 64 x 1280x720, ~300 candidates', 64, (736, 1280), with_objects=True)
+    run('C3 256 x 1920x1080, background only', 256, (1088, 1920))
     run('C3 512 x 1920x1080, background only', 512, (1088, 1920))
     run('2048 x 1920x1080, background only', 2048, (1088, 1920), reps=10)
