@@ -253,6 +253,8 @@ def main():
     level_hw = [c.shape[-2:] for c in cls]
     caps = CAPS.get(args.workload, CAPS['C2'])
     eng = StereoTrackEngine(EngineConfig(n_seq=S, **caps), device=dev)
+    if os.environ.get('ST_K4_SKIP'):                       # diagnostics only (st_debug_set_skip bits)
+        eng.lib.st_debug_set_skip(int(os.environ['ST_K4_SKIP']))
     eng.make_frame_io(raw.shape[1:], level_hw)      # allocates eng.depth_map
     stream = torch.cuda.current_stream(dev)
     modes = [args.depth_source, 'map' if args.depth_source == 'raw' else 'raw']

@@ -201,7 +201,7 @@ __device__ void associate(const TrackState &st, const Params &pr, Smem &sm, long
         stlap::Problem P;
         P.cost = cost; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
         P.dbg = st.debug + (sbase / pr.T) * ST_DEBUG_WORDS;
-        P.why = nullptr;
+        P.why = nullptr; P.no_greedy = 0;
         P.row_cnt = sm.row_cnt; P.col_cnt = sm.col_cnt; P.row_adm = sm.row_adm; P.adm_misc = sm.adm_misc;
         P.mark(0, stage_code); P.mark(1, R); P.mark(2, C);
         // debug words 5/6: assignments solved / solved by the exact fallback (this handle's lifetime)
@@ -614,7 +614,7 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
     stlap::Problem P;
     P.cost = cost + (long long)b * R * C; P.R = R; P.C = C; P.n = R + C; P.half = half;
     P.dbg = nullptr;
-    P.why = nullptr;
+    P.why = nullptr; P.no_greedy = 0;
     int *stats = reinterpret_cast<int *>(smem_raw + stlap::scratch_bytes(R + C));
     P.row_cnt = stats; P.row_adm = stats + R; P.col_cnt = stats + 2 * R; P.adm_misc = stats + 2 * R + C;
     if (R > 0 && C > 0) {
@@ -929,7 +929,10 @@ extern "C" int st_debug_read_cost(st_handle *h, int seq, float *cost_host, int c
     if (!h || !cost_host || seq < 0 || seq >= h->cfg.max_sequences) return ST_ERR_INVALID_ARG;
     StDeviceGuard guard(h->device);
     ST_CUDA_OK(cudaDeviceSynchronize());
-    ST_CUDA_OK(cudaMemcpy(cost_host, h->cost + (size_t)seq * h->cfg.max_tracks * h->cfg.max_dets,
+    // round-2 kernel: the third slot of the sequence's workspace (a stage-1 matrix the certified paths refused,
+    // kept when diagnostics bit 9 is set); round-1 kernel: the mirror of the last matrix (bit 6)
+    const size_t slot = h->k4_version == 2 ? (size_t)seq * 3 + 2 : (size_t)seq;
+    ST_CUDA_OK(cudaMemcpy(cost_host, h->cost + slot * h->cfg.max_tracks * h->cfg.max_dets,
                           sizeof(float) * count, cudaMemcpyDeviceToHost));
     return ST_OK;
 }

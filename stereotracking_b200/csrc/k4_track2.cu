@@ -162,6 +162,29 @@ __device__ __forceinline__ void mean_to_box(float cx, float cy, float a, float h
 // associate2 re-evaluates the matrix exactly before it runs that path.  *lazy_used is set when a
 // placeholder was returned.  (The all-pairs pass was issue-bound on the five IEEE divisions, two
 // square roots and the float64 acos per pair; a screened pair costs ~30 instructions.)
+// The screen of ocm_cost alone: returns false and the final value (1 or the placeholder) for a pair the lazy
+// rule settles, true when the pair needs the full evaluation.
+__device__ __forceinline__ bool ocm_screen(const Params &pr, const Smem &sm, int p, int i, float *val, int *lazy_used) {
+    const float *tb = sm.box_ocm + p * 4, *db = sm.in_box + i * 4;
+    float w = __fsub_rn(fminf(tb[2], db[2]), fmaxf(tb[0], db[0]));
+    float h = __fsub_rn(fminf(tb[3], db[3]), fmaxf(tb[1], db[1]));
+    w = w < 0.f ? 0.f : w;
+    h = h < 0.f ? 0.f : h;
+    const float inter = __fmul_rn(w, h);
+    const float a12 = __fadd_rn(__fmul_rn(__fsub_rn(tb[2], tb[0]), __fsub_rn(tb[3], tb[1])),
+                                __fmul_rn(__fsub_rn(db[2], db[0]), __fsub_rn(db[3], db[1])));
+    const float sc = pr.weight_iou ? sm.in_score[i] : 1.f;
+    if (inter == 0.f && fabsf(a12) < 3.0e38f && fabsf(sc) < 3.0e38f) {
+        if (!sm.valid[p]) { *val = 1.f; return false; }
+        const float dcx = __fmul_rn(__fadd_rn(db[0], db[2]), 0.5f), dcy = __fmul_rn(__fadd_rn(db[1], db[3]), 0.5f);
+        const float dy = __fsub_rn(dcy, sm.kc[p * 2 + 1]), dx = __fsub_rn(dcx, sm.kc[p * 2]);
+        const float dot = dy * sm.vel[p * 2] + dx * sm.vel[p * 2 + 1];
+        const float norm = sqrtf(dy * dy + dx * dx) + 1e-6f;
+        if (dot < pr.screen_cos * norm) { *lazy_used = 1; *val = pr.placeholder; return false; }
+    }
+    return true;
+}
+
 __device__ __forceinline__ float ocm_cost(const Params &pr, const Smem &sm, int p, int i, bool lazy, int *lazy_used) {
     const float *tb = sm.box_ocm + p * 4, *db = sm.in_box + i * 4;
     if (lazy) {
@@ -210,13 +233,11 @@ __device__ __forceinline__ float ocm_cost(const Params &pr, const Smem &sm, int 
 // re-read through local memory and every sub-phase ran 1.5-2x slower)
 __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *dbg, int32_t *status_word, const int *rows, int R, int C,
                            const float *ap, int C1, float *dense, int stage_code, bool ocm_lazy,
-                           unsigned char *wide_mem /* room for the 256-bit component path, or null */) {
+                           float *dump = nullptr /* diagnostics: receives the matrix of a refused stage-1 problem */) {
     if (R == 0 || C == 0) return;           // dists.size == 0 -> nothing matched (:263-265)
     const double lap_limit = 2.0 * pr.lap_half;
     const bool small = R <= 64 && C <= 64;
-    const bool wide = !small && wide_mem != nullptr && R <= stlap::kWideMax && C <= stlap::kWideMax;
-    stlap::WideMasks wm;
-    if (wide) wm = stlap::carve_wide(wide_mem);
+    __shared__ int sp_hdr[4];                            // sparse path: nR, nC, E, verdict
     const int warp = threadIdx.x >> 5;
     // debug words 14..18 (stage 1 only): cycles of gather / components / solve / fallback / scatter
     long long t_sub = clock64();
@@ -231,16 +252,15 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
     stlap::Problem P;
     P.cost = dense; P.R = R; P.C = C; P.n = R + C; P.half = pr.lap_half;
     P.dbg = nullptr;                                     // no progress marks on the critical path
+    P.no_greedy = (g_skip >> 8) & 1;                     // diagnostics bit 8
     P.why = stage_code == 1 ? dbg + 24 : nullptr;        // debug words 24..31: the whole-problem fast path of stage 1
     P.row_cnt = sm.row_cnt; P.col_cnt = sm.col_cnt; P.row_adm = sm.row_adm; P.adm_misc = sm.adm_misc;
     const bool skip = (g_skip >> (stage_code - 1)) & 1;
-    bool need_warp_path;
+    bool need_warp_path, sparse_refused = false;
     {
     for (int r = threadIdx.x; r < R; r += kThreads) { sm.row_cnt[r] = 0; sm.row_adm[r] = -1; }
     for (int c = threadIdx.x; c < C; c += kThreads) sm.col_cnt[c] = 0;
     if (threadIdx.x < 64) { sm.masks.rmask[threadIdx.x] = 0ull; sm.masks.cmask[threadIdx.x] = 0ull; }
-    if (wide)
-        for (int i = threadIdx.x; i < 2 * stlap::kWideMax * stlap::kWideWords; i += kThreads) wm.rmask[i] = 0ull;   // rmask and cmask
     if (threadIdx.x == 0) { sm.adm_misc[0] = 0; sm.adm_misc[1] = 0; *sm.masks.fallback = 0; *sm.masks.n_comp = 0; }
     __syncthreads();
     for (int e = threadIdx.x; e < R * C; e += kThreads) {
@@ -260,10 +280,6 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
             atomicAdd(&sm.col_cnt[j], 1);
             sm.row_adm[r] = j;
             if (small) { atomicOr(&sm.masks.rmask[r], 1ull << j); atomicOr(&sm.masks.cmask[j], 1ull << r); }
-            else if (wide) {
-                atomicOr(&wm.rmask[r * stlap::kWideWords + (j >> 6)], 1ull << (j & 63));
-                atomicOr(&wm.cmask[j * stlap::kWideWords + (r >> 6)], 1ull << (r & 63));
-            }
         }
         if (dist != dist) sm.adm_misc[0] = 1;
         if (fabs((double)dist - lap_limit) <= 2.0e-9) sm.adm_misc[1] = 1;
@@ -304,38 +320,93 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
         } else {
             need_warp_path = true;
         }
-    } else if (wide) {
-        // a hundred or two rows and columns: the same component path on 256-bit sets
-        stlap::prepare_components_wide(P, sm.lap, wm, sm.sub);        // ends with a barrier
-        ST_SUB(15);
-        if (*wm.fallback == 0) {
-            const int n_comp = min(*wm.n_comp, stlap::kWideComps);
-            const int nR = (int)wm.big[0], nC = (int)wm.big[1];
-            const bool has_big = nR > 0;
-            if (n_comp == 0 && !has_big) {
-                need_warp_path = false;
-            } else {
-                bool bad = false;
-                if (warp == 0 && has_big) bad = !stlap::solve_sub_problem(P, sm.lap, sm.sub, nR, nC);
-                const int first = has_big ? 1 : 0, nw = kWarps - first;
-                if (warp >= first)
-                    for (int k = warp - first; k < n_comp; k += nw) {
-                        const int *rec = wm.comp + k * 10;
-                        const int ri[4] = {rec[2], rec[3], rec[4], rec[5]}, ci[4] = {rec[6], rec[7], rec[8], rec[9]};
-                        bad |= !stlap::enumerate_idx(P, sm.lap, ri, ci, rec[0], rec[1]);
+    } else {
+        // crowded or wide problems: the sparse certified solver on the admissible edges (lapjv.cuh)
+        int verdict = 8;                                 // 8 = does not fit the arena
+        if (sm.adm_misc[0] == 0 && sm.adm_misc[1] == 0) {
+            // arena: the part of the whole-problem scratch in front of x / y (v, d, cols, pred: 24 bytes per node)
+            unsigned char *arena = reinterpret_cast<unsigned char *>(const_cast<double *>(sm.lap.v));
+            const size_t arena_bytes = (size_t)24 * (pr.T + pr.D);
+            int *rmap = reinterpret_cast<int *>(arena), *cmap = rmap + R, *rlist = cmap + C, *clist = rlist + R;
+            for (int r = threadIdx.x; r < R; r += kThreads) sm.lap.x[r] = -1;
+            for (int c = threadIdx.x; c < C; c += kThreads) sm.lap.y[c] = -1;
+            if (warp == 0) {
+                compact_warp(R, [&](int r) { return sm.row_cnt[r] > 0; }, rlist, &sp_hdr[0]);
+                __syncwarp();
+                for (int k = threadIdx.x; k < sp_hdr[0]; k += 32) rmap[rlist[k]] = k;
+            } else if (warp == 1) {
+                compact_warp(C, [&](int c) { return sm.col_cnt[c] > 0; }, clist, &sp_hdr[1]);
+                __syncwarp();
+                for (int k = threadIdx.x & 31; k < sp_hdr[1]; k += 32) cmap[clist[k]] = k;
+            }
+            __syncthreads();
+            const int nR = sp_hdr[0], nC = sp_hdr[1];
+            size_t at = ((size_t)8 * (R + C) + 15) & ~(size_t)15;
+            int *cursor = reinterpret_cast<int *>(arena + at); at += ((size_t)4 * nR + 15) & ~(size_t)15;
+            unsigned short *off = reinterpret_cast<unsigned short *>(arena + at); at += ((size_t)2 * (nR + 1) + 15) & ~(size_t)15;
+            // edge offsets: exclusive prefix of the admissible counts of the kept rows (warp 0)
+            if (warp == 0 && at <= arena_bytes) {
+                const int lane = threadIdx.x;
+                int run = 0;
+                for (int k0 = 0; k0 < nR; k0 += 32) {
+                    const int k = k0 + lane;
+                    const int cnt = k < nR ? sm.row_cnt[rlist[k]] : 0;
+                    int incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+                    if (k < nR) { off[k] = (unsigned short)min(run + incl - cnt, 65535); cursor[k] = run + incl - cnt; }
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) { off[nR] = (unsigned short)min(run, 65535); sp_hdr[2] = run; }
+            }
+            __syncthreads();
+            const int E = sp_hdr[2];
+            unsigned short *erow = reinterpret_cast<unsigned short *>(arena + at); at += ((size_t)2 * E + 15) & ~(size_t)15;
+            unsigned short *ecol = reinterpret_cast<unsigned short *>(arena + at); at += ((size_t)2 * E + 15) & ~(size_t)15;
+            float *ecost = reinterpret_cast<float *>(arena + at); at += ((size_t)4 * E + 15) & ~(size_t)15;
+            const bool fits = at + stlap::sparse_state_bytes(nR, nC) <= arena_bytes && E < 65535 && nR + nC <= 512;
+            if (fits) {
+                // the admissible entries of the matrix, grouped by row (order inside a row does not matter)
+                for (int e = threadIdx.x; e < R * C; e += kThreads) {
+                    const float dist = dense[e];
+                    if ((double)dist < lap_limit) {
+                        const int r = e / C, j = e - r * C;
+                        const int k = atomicAdd(&cursor[rmap[r]], 1);
+                        erow[k] = (unsigned short)rmap[r]; ecol[k] = (unsigned short)cmap[j]; ecost[k] = dist;
                     }
-                need_warp_path = __syncthreads_or(bad) != 0;
+                }
+                __syncthreads();
+                ST_SUB(15);
+                if (warp == 0) {
+                    stlap::Sparse q;
+                    q.nR = nR; q.nC = nC; q.E = E; q.half = pr.lap_half;
+                    q.off = off; q.erow = erow; q.ecol = ecol; q.ecost = ecost;
+                    q.why = stage_code == 1 ? dbg + 24 : nullptr;
+                    stlap::sparse_carve_state(q, arena + at);
+                    const int code = nR == 0 ? 0 : stlap::sparse_assign_warp(q);
+                    if (code == 0)
+                        for (int j = threadIdx.x; j < nC; j += 32) {
+                            const int rr = q.p[j];
+                            if (rr >= 0) { sm.lap.y[clist[j]] = rlist[rr]; sm.lap.x[rlist[rr]] = clist[j]; }
+                        }
+                    else if (q.why && threadIdx.x == 0) { q.why[0] = code; atomicAdd(&q.why[1], 1); }
+                    if (threadIdx.x == 0) sp_hdr[3] = code;
+                }
+                __syncthreads();
+                verdict = sp_hdr[3];
             }
         } else {
-            need_warp_path = true;
+            verdict = 1;                                 // NaN / a cost within 2e-9 of the limit: the exact path decides
         }
+        need_warp_path = verdict != 0;
+        sparse_refused = verdict == 1 || verdict == 6 || verdict == 7;   // the dense certified path would refuse as well
     }
     ST_SUB(16);
     }
     if (need_warp_path) {                                // block-uniform
         // certified Hungarian on one warp; without its certificate (exact ties) the literal JV emulation
         if (warp == 0) {
-            const bool ok = P.n <= 512 && stlap::fast_assign_warp(P, sm.lap);
+            const bool ok = !sparse_refused && P.n <= 512 && stlap::fast_assign_warp(P, sm.lap);
             if (threadIdx.x == 0) sm.adm_misc[3] = ok ? 1 : 0;
         }
         __syncthreads();
@@ -349,6 +420,10 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
                     dense[e] = ocm_cost(pr, sm, rows[r], sm.dets[sm.scol[j]], false, &dummy);
                 }
                 __syncthreads();
+            }
+            if (dump) {                                  // diagnostics bit 9: keep the refused matrix for st_debug_read_cost
+                for (int e = threadIdx.x; e < R * C; e += kThreads) dump[e] = dense[e];
+                if (threadIdx.x == 0) { dbg[23] = stage_code; dbg[26] = R; dbg[27] = C; }
             }
             if (warp == 0) {
                 if (threadIdx.x == 0) atomicAdd(&dbg[6], 1);     // solved by the exact fallback
@@ -385,7 +460,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
                int32_t *__restrict__ out_counts, int32_t *__restrict__ out_src_g /* may be null */,
                const float *__restrict__ cmc_warp /* [S,6] camera-motion affine, may be null */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int sh_cnt[8];
+    __shared__ int sh_cnt[8];                            // [6]: pairs queued for the full OCM evaluation
     const int s = blockIdx.x;
     const int T = pr.T, D = pr.D;
     int32_t *dbg = st.debug + s * ST_DEBUG_WORDS;
@@ -595,15 +670,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         const int A = n_live * C1;                       // <= T * D <= 2^20
         float *ap_ocm, *dense_sm;
         int dense_cap;
-        // crowded sequences (more than 64 rows or columns in some stage) take the tail of the cost region
-        // for the 256-bit component sets; their matrices then mostly live in the global workspace
-        const int wide_floats = (int)((stlap::wide_bytes() + 15) / 16 * 4);
-        unsigned char *wide_mem = nullptr;
-        int cost_avail = sm.cost_cap;
-        if ((n_live > 64 || C1 > 64) && sm.cost_cap >= wide_floats) {
-            cost_avail = sm.cost_cap - wide_floats;
-            wide_mem = reinterpret_cast<unsigned char *>(sm.cost + cost_avail);
-        }
+        const int cost_avail = sm.cost_cap;
         if (A <= cost_avail) {
             ap_ocm = sm.cost; dense_sm = sm.cost + A; dense_cap = cost_avail - A;
         } else {
@@ -612,22 +679,57 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         float *dense_g = gws + (long long)T * D;
         const bool lazy = !((g_skip >> 6) & 1) && pr.screen_cos > -1.5f;   // diagnostics bit 6: evaluate every entry exactly
         int lazy_used = 0;
-        for (int e = threadIdx.x; e < A; e += kThreads) {         // 32-bit index math: a 64-bit division per pair cost more than the pair
-            const int p = e / C1, c = e - p * C1;
-            ap_ocm[e] = ocm_cost(pr, sm, p, sm.dets[c], lazy, &lazy_used);
+        // Two passes: the screen settles the pairs that do not overlap (nearly all of them) and queues the rest;
+        // the full evaluation (five IEEE divisions, two square roots, a float64 acos) then runs with every lane
+        // busy - evaluated in place, one overlapping pair per warp held the other 31 lanes for ~1 200 cycles.
+        // The queue borrows the room of the stage's dense matrix; what does not fit is evaluated in place.
+        int *queue = reinterpret_cast<int *>(dense_sm);
+        const int queue_cap = lazy ? dense_cap : 0;
+        if (threadIdx.x == 0) sh_cnt[6] = 0;
+        __syncthreads();
+        for (int e0 = warp * 32; e0 < A; e0 += kThreads) {        // 32-bit index math: a 64-bit division per pair cost more than the pair
+            const int e = e0 + (threadIdx.x & 31);
+            bool need = false;
+            int p = 0, c = 0;
+            if (e < A) {
+                p = e / C1; c = e - p * C1;
+                float val = 0.f;
+                need = !lazy || ocm_screen(pr, sm, p, sm.dets[c], &val, &lazy_used);
+                if (!need) ap_ocm[e] = val;
+            }
+            const unsigned mb = __ballot_sync(0xffffffffu, need);
+            if (mb == 0u) continue;
+            int base = 0;
+            if ((threadIdx.x & 31) == 0) base = atomicAdd(&sh_cnt[6], __popc(mb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (need) {
+                const int pos = base + __popc(mb & ((1u << (threadIdx.x & 31)) - 1u));
+                if (pos < queue_cap) queue[pos] = e;
+                else ap_ocm[e] = ocm_cost(pr, sm, p, sm.dets[c], false, &lazy_used);
+            }
+        }
+        __syncthreads();
+        {
+            const int n_queued = min(sh_cnt[6], queue_cap);
+            int unused = 0;
+            for (int k = threadIdx.x; k < n_queued; k += kThreads) {
+                const int e = queue[k], p = e / C1, c = e - p * C1;
+                ap_ocm[e] = ocm_cost(pr, sm, p, sm.dets[c], false, &unused);
+            }
         }
         const bool ocm_lazy = __syncthreads_or(lazy_used) != 0;
         if (threadIdx.x == 0) dbg[19] = (int)(clock64() - t_prev);      // cycles of the all-pairs pass (t_prev = end of phase 8)
         // ---- stage 1: confirmed tracks vs filtered dets (:448-474)
         associate2(pr, sm, dbg, &st.status[s], sm.conf, Rc, C1, ap_ocm, C1,
-                   Rc * C1 <= dense_cap ? dense_sm : dense_g, 1, ocm_lazy, wide_mem);
+                   Rc * C1 <= dense_cap ? dense_sm : dense_g, 1, ocm_lazy,
+                   ((g_skip >> 9) & 1) ? gws + 2ll * T * D : nullptr);
         ST_PHASE(9);
         // ---- stage 2: tentative tracks vs leftovers (:476-503)
         if (warp == 0) compact_warp(C1, [&](int c) { return sm.det_stage[sm.dets[c]] == 4; }, sm.scol, &sh_cnt[3]);
         __syncthreads();
         const int C2 = sh_cnt[3];
         associate2(pr, sm, dbg, &st.status[s], sm.tentl, Rt, C2, ap_ocm, C1,
-                   Rt * C2 <= dense_cap ? dense_sm : dense_g, 2, ocm_lazy, wide_mem);
+                   Rt * C2 <= dense_cap ? dense_sm : dense_g, 2, ocm_lazy, ((g_skip >> 9) & 1) ? gws + 2ll * T * D : nullptr);
         ST_PHASE(10);
         // ---- stage 3: OCR, every unmatched track's last observation (:505-569)
         if (warp == 0) compact_warp(C1, [&](int c) { return sm.det_stage[sm.dets[c]] == 4; }, sm.scol, &sh_cnt[4]);
@@ -635,7 +737,7 @@ k4_track_step2(TrackState st, Params pr, int cost_floats, const int32_t *__restr
         __syncthreads();
         const int C3 = sh_cnt[4], R3 = sh_cnt[5];
         associate2(pr, sm, dbg, &st.status[s], sm.rows, R3, C3, nullptr, C1,
-                   R3 * C3 <= dense_cap ? dense_sm : dense_g, 3, false, wide_mem);
+                   R3 * C3 <= dense_cap ? dense_sm : dense_g, 3, false, ((g_skip >> 9) & 1) ? gws + 2ll * T * D : nullptr);
         ST_PHASE(11);
         // ---- unmatched tracks: tracked = False, obs.append(None) (:579-582): plain stores
         for (int p = threadIdx.x; p < n_live; p += kThreads)

@@ -56,6 +56,7 @@ struct Problem {
     int R, C, n;
     double half;          // cost_limit / 2
     int *dbg;             // optional [8] progress words (global), may be null
+    int no_greedy;        // diagnostics: != 0 = every non-isolated row goes through the search (no greedy start)
     int *why;             // optional [8] diagnostics of fast_assign_warp (global), may be null: [0] code of the
                           // last refusal, [1] refusals, [2..4] cycles of start / search / certificate of the last
                           // call, [5] rows searched, [6] active rows, [7] tight arcs
@@ -545,6 +546,99 @@ __device__ bool hungarian_regs(const Problem &P, volatile double *u, volatile do
     return true;
 }
 
+// Uniqueness analysis of an optimal assignment from its tight non-matching edges, given as arcs
+// sigma(i) -> j over the column nodes [0, m) (real columns < C, then the private dummy column C + i of
+// row i): p[j] = row of real column j or -1, sigma[i] = column node of row i, vnode(j) = potential of
+// column node j (0 for dummies), flags = 4 m bytes of scratch.  Returns 0 when no equal-cost
+// alternative exists, else the refusal code (6 / 7): (1) a free column is reachable from a column that
+// can be vacated at no cost, or (2) the arcs hold a directed cycle.  One warp.
+template <typename VNode>
+__device__ inline int arcs_unique(int C, int m, int n_arcs, const volatile int *arc_from, const volatile int *arc_to,
+                                  const volatile int *p, const volatile int *sigma, VNode vnode,
+                                  volatile unsigned char *flags, long long *t_mid) {
+    const int lane = threadIdx.x & 31;
+    if (n_arcs > 0 && n_arcs <= 32) {
+        // few arcs (the usual case): one arc per lane, fixpoints by shuffles, no shared memory.
+        // `from` is always an assigned column (sigma of a row); only columns that occur in arcs matter.
+        __syncwarp();
+        const bool have = lane < n_arcs;
+        const int from = have ? arc_from[lane] : -1, to = have ? arc_to[lane] : -2;
+        bool to_assigned = false, from_vac = false;
+        if (have) {
+            to_assigned = to < C ? p[to] >= 0 : sigma[to - C] == to;
+            from_vac = vnode(from) >= -kFastEps;                 // may be vacated at no cost
+        }
+        // (1) a free column reachable from a vacatable one
+        bool reach = have && !to_assigned;
+        for (int round = 0; round <= n_arcs; ++round) {
+            bool changed = false;
+            for (int k = 0; k < n_arcs; ++k) {
+                const int f = __shfl_sync(0xffffffffu, from, k);
+                const bool r = __shfl_sync(0xffffffffu, (int)reach, k) != 0;
+                if (have && !reach && r && f == to) { reach = true; changed = true; }
+            }
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        if (t_mid) *t_mid = clock64();
+        bool unsure = reach && from_vac;
+        // (2) a directed cycle: an arc stays alive while its head has an alive outgoing arc
+        bool alive = have && to_assigned;
+        for (int round = 0; round <= n_arcs; ++round) {
+            bool has_next = false;
+            for (int k = 0; k < n_arcs; ++k) {
+                const int f = __shfl_sync(0xffffffffu, from, k);
+                const bool al = __shfl_sync(0xffffffffu, (int)alive, k) != 0;
+                has_next |= al && f == to;
+            }
+            const bool drop = alive && !has_next;
+            if (drop) alive = false;
+            if (!__any_sync(0xffffffffu, drop)) break;
+        }
+        unsure |= alive;
+        if (__any_sync(0xffffffffu, unsure)) return 6;
+    } else if (n_arcs > 0) {
+        volatile unsigned char *assigned = flags;
+        volatile unsigned char *reach = assigned + m, *alive = assigned + 2 * m, *has_out = assigned + 3 * m;
+        bool vac_l[16];
+        int cnt = 0;
+        for (int j = lane; j < m; j += 32, ++cnt) {
+            const bool asg = j < C ? p[j] >= 0 : sigma[j - C] == j;
+            if (cnt < 16) vac_l[cnt] = asg && vnode(j) >= -kFastEps;     // may be vacated at no cost
+            assigned[j] = asg; reach[j] = !asg; alive[j] = asg;
+        }
+        __syncwarp();
+        // (1) columns from which a free column is reachable along arcs
+        for (int round = 0; round <= m; ++round) {
+            bool changed = false;
+            for (int k = lane; k < n_arcs; k += 32)
+                if (reach[arc_to[k]] && !reach[arc_from[k]]) { reach[arc_from[k]] = 1; changed = true; }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        if (t_mid) *t_mid = clock64();
+        bool unsure = false;
+        cnt = 0;
+        for (int j = lane; j < m; j += 32, ++cnt)
+            if (cnt < 16 && vac_l[cnt] && reach[j]) unsure = true;   // a free re-routing exists
+        // (2) directed cycle among assigned columns (peel columns without live successors)
+        for (int round = 0; round <= m; ++round) {
+            for (int j = lane; j < m; j += 32) has_out[j] = 0;
+            __syncwarp();
+            for (int k = lane; k < n_arcs; k += 32)
+                if (alive[arc_from[k]] && alive[arc_to[k]]) has_out[arc_from[k]] = 1;
+            __syncwarp();
+            bool changed = false;
+            for (int j = lane; j < m; j += 32)
+                if (alive[j] && !has_out[j]) { alive[j] = 0; changed = true; }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        for (int j = lane; j < m; j += 32) unsure |= alive[j] != 0;    // survivors lie on a cycle
+        if (__any_sync(0xffffffffu, unsure)) return 7;
+    }
+    return 0;
+}
+
 static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &s) {
     const int lane = threadIdx.x & 31;
     const int R = P.R, C = P.C, m = R + C;
@@ -593,7 +687,7 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
                 float bc = 3.0e38f;
                 const float *crow = P.cost + (long long)i * C;
                 for (int j = 0; j < C; ++j) { const float c = crow[j]; if (c < bc) { bc = c; best_j = j; } }
-                ui = (double)bc - half;
+                ui = P.no_greedy ? 0.0 : (double)bc - half;
                 atomicMin(const_cast<int *>(way) + best_j, i);
             }
             u[i] = ui;
@@ -606,7 +700,7 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
     int n_search = 0;
     for (int t = lane; t < n_active; t += 32) {
         const int packed = active[t], i = packed & 0xffff, j = packed >> 16;
-        const bool won = way[j] == i;
+        const bool won = way[j] == i && !P.no_greedy;
         if (won) p[j] = i;
         active[t] = won ? ~i : i;
         n_search += won ? 0 : 1;
@@ -785,85 +879,10 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
     __syncwarp();
     const long long t_c1 = clock64();
     long long t_c2 = t_c1;
-    if (n_arcs > 0 && n_arcs <= 32) {
-        // few arcs (the usual case): one arc per lane, fixpoints by shuffles, no shared memory.
-        // `from` is always an assigned column (sigma of a row); only columns that occur in arcs matter.
-        __syncwarp();
-        const bool have = lane < n_arcs;
-        const int from = have ? arc_from[lane] : -1, to = have ? arc_to[lane] : -2;
-        bool to_assigned = false, from_vac = false;
-        if (have) {
-            to_assigned = to < C ? p[to] >= 0 : sigma[to - C] == to;
-            from_vac = v[from] >= -kFastEps;                     // may be vacated at no cost
-        }
-        // (1) a free column reachable from a vacatable one
-        bool reach = have && !to_assigned;
-        for (int round = 0; round <= n_arcs; ++round) {
-            bool changed = false;
-            for (int k = 0; k < n_arcs; ++k) {
-                const int f = __shfl_sync(0xffffffffu, from, k);
-                const bool r = __shfl_sync(0xffffffffu, (int)reach, k) != 0;
-                if (have && !reach && r && f == to) { reach = true; changed = true; }
-            }
-            if (!__any_sync(0xffffffffu, changed)) break;
-        }
-        t_c2 = clock64();
-        bool unsure = reach && from_vac;
-        // (2) a directed cycle: an arc stays alive while its head has an alive outgoing arc
-        bool alive = have && to_assigned;
-        for (int round = 0; round <= n_arcs; ++round) {
-            bool has_next = false;
-            for (int k = 0; k < n_arcs; ++k) {
-                const int f = __shfl_sync(0xffffffffu, from, k);
-                const bool al = __shfl_sync(0xffffffffu, (int)alive, k) != 0;
-                has_next |= al && f == to;
-            }
-            const bool drop = alive && !has_next;
-            if (drop) alive = false;
-            if (!__any_sync(0xffffffffu, drop)) break;
-        }
-        unsure |= alive;
-        if (__any_sync(0xffffffffu, unsure)) ST_REFUSE(6);
-    } else if (n_arcs > 0) {
-        // column flags live where the row potentials were (no longer needed)
-        volatile unsigned char *assigned = reinterpret_cast<volatile unsigned char *>(s.cols);
-        volatile unsigned char *reach = assigned + m, *alive = assigned + 2 * m, *has_out = assigned + 3 * m;
-        bool vac_l[16];
-        int cnt = 0;
-        for (int j = lane; j < m; j += 32, ++cnt) {
-            const bool asg = j < C ? p[j] >= 0 : sigma[j - C] == j;
-            if (cnt < 16) vac_l[cnt] = asg && v[j] >= -kFastEps;     // may be vacated at no cost
-            assigned[j] = asg; reach[j] = !asg; alive[j] = asg;
-        }
-        __syncwarp();
-        // (1) columns from which a free column is reachable along arcs
-        for (int round = 0; round <= m; ++round) {
-            bool changed = false;
-            for (int k = lane; k < n_arcs; k += 32)
-                if (reach[arc_to[k]] && !reach[arc_from[k]]) { reach[arc_from[k]] = 1; changed = true; }
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, changed)) break;
-        }
-        t_c2 = clock64();
-        bool unsure = false;
-        cnt = 0;
-        for (int j = lane; j < m; j += 32, ++cnt)
-            if (cnt < 16 && vac_l[cnt] && reach[j]) unsure = true;   // a free re-routing exists
-        // (2) directed cycle among assigned columns (peel columns without live successors)
-        for (int round = 0; round <= m; ++round) {
-            for (int j = lane; j < m; j += 32) has_out[j] = 0;
-            __syncwarp();
-            for (int k = lane; k < n_arcs; k += 32)
-                if (alive[arc_from[k]] && alive[arc_to[k]]) has_out[arc_from[k]] = 1;
-            __syncwarp();
-            bool changed = false;
-            for (int j = lane; j < m; j += 32)
-                if (alive[j] && !has_out[j]) { alive[j] = 0; changed = true; }
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, changed)) break;
-        }
-        for (int j = lane; j < m; j += 32) unsure |= alive[j] != 0;    // survivors lie on a cycle
-        if (__any_sync(0xffffffffu, unsure)) ST_REFUSE(7);
+    {
+        const int verdict = arcs_unique(C, m, n_arcs, arc_from, arc_to, p, sigma, [&](int j) { return (double)v[j]; },
+                                        reinterpret_cast<volatile unsigned char *>(s.cols), &t_c2);
+        if (verdict) ST_REFUSE(verdict);
     }
     __syncwarp();
     if (P.why && lane == 0) {
@@ -896,6 +915,228 @@ static __device__ __noinline__ bool fast_assign_warp(const Problem &P, Scratch &
     return true;
 }
 #undef ST_REFUSE
+
+// ---------------------------------------------------------------------------------
+// Sparse certified solver (crowded or wide problems: more than 64 rows or columns).
+// Only ADMISSIBLE entries (cost < L) can be part of an optimum, and during the shortest-path search a
+// non-admissible real column never beats the private dummy of the same row (its slack is
+// c - L/2 - u_i - v_j >= L/2 - u_i because v_j <= 0, with equality excluded by the 2e-9 screen), so the
+// whole method runs on the admissible edges alone: rows / columns without admissible entries are
+// dropped, the rest is renumbered compactly (nR rows, nC columns) and the edges are held as a CSR list
+// (a hundred tracks in a crowd have ~4 admissible detections each: ~600 edges instead of a
+// 170 x 240 matrix in global memory).
+//   start:   u_i = the row's smallest reduced entry; the row takes that column unless a lower row wants
+//            it too (isolated pairs are the trivial case) - feasible duals, v = 0;
+//   search:  the rows that lost a claim, one after the other, Hungarian shortest-path search with the
+//            same rules as hungarian_regs (row's own dummy tracked as one scalar, real columns win
+//            ties against dummies, lowest column index among equal slacks); the per-column state
+//            lives in shared memory and only the columns touched by the search (the frontier, a
+//            handful) are scanned and updated per step;
+//   certificate: tight non-matching admissible edges + the dummy edge of every matched row -> arcs ->
+//            arcs_unique (non-admissible edges are never tight: slack >= c - L > 2e-9).
+// One warp.  Results in COMPACT numbering: p[j] = row of column j or -1.  Returns 0, or a refusal code.
+struct Sparse {
+    int nR, nC, E;
+    double half;
+    const unsigned short *off;       // [nR + 1]
+    const unsigned short *erow;      // [E] row of every edge
+    const unsigned short *ecol;      // [E] column of every edge
+    const float *ecost;              // [E]
+    // state (shared memory)
+    volatile double *u;              // [nR]
+    volatile double *v, *minv;       // [nC]
+    volatile int *p, *way;           // [nC]
+    volatile unsigned short *fcol;   // [nC] frontier of the current search
+    volatile unsigned char *used;    // [nC]
+    volatile int *freel;             // [nR] rows to search
+    volatile int *sigma;             // [nR]
+    volatile int *arc_from, *arc_to; // [nR + nC]
+    volatile unsigned char *flags;   // [4 (nR + nC)]
+    int *why;                        // optional diagnostics as Problem::why
+};
+
+__host__ __device__ inline size_t sparse_state_bytes(int nR, int nC) {
+    size_t b = sizeof(double) * (size_t)(nR + 2 * nC) + sizeof(int) * (size_t)(2 * nC + 2 * nR + 2 * (nR + nC));
+    b += sizeof(unsigned short) * (size_t)nC + (size_t)nC + 4 * (size_t)(nR + nC);
+    return (b + 15) & ~(size_t)15;
+}
+
+// carves the state arrays of q (nR, nC set) out of mem (sparse_state_bytes(nR, nC) bytes, 8-byte aligned)
+__device__ inline void sparse_carve_state(Sparse &q, unsigned char *mem) {
+    q.u = reinterpret_cast<volatile double *>(mem); mem += sizeof(double) * q.nR;
+    q.v = reinterpret_cast<volatile double *>(mem); mem += sizeof(double) * q.nC;
+    q.minv = reinterpret_cast<volatile double *>(mem); mem += sizeof(double) * q.nC;
+    q.p = reinterpret_cast<volatile int *>(mem); mem += sizeof(int) * q.nC;
+    q.way = reinterpret_cast<volatile int *>(mem); mem += sizeof(int) * q.nC;
+    q.freel = reinterpret_cast<volatile int *>(mem); mem += sizeof(int) * q.nR;
+    q.sigma = reinterpret_cast<volatile int *>(mem); mem += sizeof(int) * q.nR;
+    q.arc_from = reinterpret_cast<volatile int *>(mem); mem += sizeof(int) * (q.nR + q.nC);
+    q.arc_to = reinterpret_cast<volatile int *>(mem); mem += sizeof(int) * (q.nR + q.nC);
+    q.fcol = reinterpret_cast<volatile unsigned short *>(mem); mem += sizeof(unsigned short) * q.nC;
+    q.used = mem; mem += q.nC;
+    q.flags = mem;
+}
+
+static __device__ __noinline__ int sparse_assign_warp(const Sparse &q) {
+    const int lane = threadIdx.x & 31;
+    const int nR = q.nR, nC = q.nC, m = nR + nC;
+    const double half = q.half, INF = 1.0e300;
+    const int VIRT = 1 << 30;
+    const long long t0 = clock64();
+    for (int j = lane; j < nC; j += 32) { q.v[j] = 0.0; q.minv[j] = INF; q.p[j] = -1; q.way[j] = 0x7fffffff; q.used[j] = 0; }
+    __syncwarp();
+    // ---- greedy start ----
+    for (int i = lane; i < nR; i += 32) {
+        float bc = 3.0e38f;
+        int bj = 0x7fffffff;
+        for (int e = q.off[i]; e < q.off[i + 1]; ++e) {
+            const float c = q.ecost[e];
+            const int j = q.ecol[e];
+            if (c < bc || (c == bc && j < bj)) { bc = c; bj = j; }
+        }
+        q.u[i] = (double)bc - half;
+        q.sigma[i] = bj;                                   // the wanted column, until the certificate
+        atomicMin(const_cast<int *>(q.way) + bj, i);
+    }
+    __syncwarp();
+    int n_free = 0;
+    for (int i0 = 0; i0 < nR; i0 += 32) {
+        const int i = i0 + lane;
+        bool lost = false;
+        if (i < nR) {
+            const int j = q.sigma[i];
+            if (q.way[j] == i) q.p[j] = i; else lost = true;
+        }
+        const unsigned mb = __ballot_sync(0xffffffffu, lost);
+        if (lost) q.freel[n_free + __popc(mb & ((1u << lane) - 1u))] = i;
+        n_free += __popc(mb);
+    }
+    __syncwarp();
+    const long long t1 = clock64();
+    // ---- shortest-path searches for the rows that lost their claim ----
+    for (int t = 0; t < n_free; ++t) {
+        const int row = q.freel[t];
+        int n_f = 0;
+        int j0 = VIRT, i0 = row;
+        double dmin = half - q.u[row];                     // the new row's own dummy
+        int drow = row, dcol = VIRT;
+        bool to_dummy = false;
+        int guard = 0;
+        while (true) {
+            if (++guard > m + 2) return 2;
+            const double ui0 = q.u[i0];
+            // relax the admissible edges of i0
+            const int e0 = q.off[i0], e1 = q.off[i0 + 1];
+            for (int eb = e0; eb < e1; eb += 32) {
+                const int e = eb + lane;
+                bool fresh = false;
+                int j = 0;
+                if (e < e1) {
+                    j = q.ecol[e];
+                    if (!q.used[j]) {
+                        const double cur = ((double)q.ecost[e] - half) - ui0 - q.v[j];
+                        const double mv = q.minv[j];
+                        fresh = !(mv < INF);
+                        if (cur < mv) { q.minv[j] = cur; q.way[j] = j0; }
+                    }
+                }
+                const unsigned fb = __ballot_sync(0xffffffffu, fresh);
+                if (fresh) q.fcol[n_f + __popc(fb & ((1u << lane) - 1u))] = (unsigned short)j;
+                n_f += __popc(fb);
+            }
+            __syncwarp();
+            // the closest unvisited column of the frontier (lowest index among equals)
+            double best = INF;
+            int bj = -1;
+            for (int f = lane; f < n_f; f += 32) {
+                const int j = q.fcol[f];
+                if (q.used[j]) continue;
+                const double mv = q.minv[j];
+                if (mv < best || (mv == best && j < bj)) { best = mv; bj = j; }
+            }
+            warp_argmin(best, bj);
+            to_dummy = bj < 0 || dmin < best;
+            const double delta = to_dummy ? dmin : best;
+            if (!(delta < INF)) return 4;
+            // dual update (only frontier columns have state)
+            for (int f = lane; f < n_f; f += 32) {
+                const int j = q.fcol[f];
+                if (q.used[j]) { q.u[q.p[j]] += delta; q.v[j] -= delta; }
+                else q.minv[j] -= delta;
+            }
+            if (lane == 0) q.u[row] += delta;
+            dmin -= delta;
+            __syncwarp();
+            if (to_dummy) break;
+            j0 = bj;
+            if (lane == 0) q.used[j0] = 1;
+            __syncwarp();
+            i0 = q.p[j0];
+            if (i0 < 0) break;                             // free real column: augment
+            const double cand = half - q.u[i0];
+            if (cand < dmin) { dmin = cand; drow = i0; dcol = j0; }
+        }
+        (void)drow;
+        if (lane == 0) {
+            int jc = to_dummy ? dcol : j0;                 // column that receives a new row (VIRT: none)
+            int steps = 0;
+            while (jc != VIRT && steps++ <= m) {
+                const int jp = q.way[jc];
+                q.p[jc] = jp == VIRT ? row : q.p[jp];
+                jc = jp;
+            }
+        }
+        __syncwarp();
+        for (int f = lane; f < n_f; f += 32) { const int j = q.fcol[f]; q.minv[j] = INF; q.used[j] = 0; }
+        __syncwarp();
+    }
+    const long long t2 = clock64();
+    // ---- uniqueness certificate ----
+    for (int i = lane; i < nR; i += 32) q.sigma[i] = nC + i;
+    __syncwarp();
+    for (int j = lane; j < nC; j += 32) { const int r = q.p[j]; if (r >= 0) q.sigma[r] = j; }
+    __syncwarp();
+    int n_arcs = 0;
+    for (int eb = 0; eb < q.E; eb += 32) {
+        const int e = eb + lane;
+        bool tight = false;
+        int from = 0, to = 0;
+        if (e < q.E) {
+            const int i = q.erow[e];
+            to = q.ecol[e];
+            from = q.sigma[i];
+            tight = to != from && ((double)q.ecost[e] - half) - q.u[i] - q.v[to] <= kFastEps;
+        }
+        const unsigned tb = __ballot_sync(0xffffffffu, tight);
+        if (tb == 0u) continue;
+        const int pos = n_arcs + __popc(tb & ((1u << lane) - 1u));
+        if (tight && pos < m) { q.arc_from[pos] = from; q.arc_to[pos] = to; }
+        n_arcs += __popc(tb);
+    }
+    for (int i0 = 0; i0 < nR; i0 += 32) {                  // the dummy edge of every matched row
+        const int i = i0 + lane;
+        bool tight = false;
+        int from = 0;
+        if (i < nR) {
+            from = q.sigma[i];
+            if (from != nC + i) tight = half - q.u[i] <= kFastEps;
+        }
+        const unsigned tb = __ballot_sync(0xffffffffu, tight);
+        const int pos = n_arcs + __popc(tb & ((1u << lane) - 1u));
+        if (tight && pos < m) { q.arc_from[pos] = from; q.arc_to[pos] = nC + i; }
+        n_arcs += __popc(tb);
+    }
+    if (n_arcs > m) return 5;
+    __syncwarp();
+    const int verdict = arcs_unique(nC, m, n_arcs, q.arc_from, q.arc_to, q.p, q.sigma,
+                                    [&](int j) { return j < nC ? (double)q.v[j] : 0.0; }, q.flags, (long long *)nullptr);
+    if (q.why && lane == 0) {
+        q.why[2] = (int)(t1 - t0); q.why[3] = (int)(t2 - t1); q.why[4] = (int)(clock64() - t2);
+        q.why[5] = n_free; q.why[6] = nR; q.why[7] = n_arcs;
+    }
+    __syncwarp();
+    return verdict;
+}
 
 // ---------------------------------------------------------------------------------
 // Component path (problems with R, C <= 64).  The objective of the extended problem is
@@ -1294,7 +1535,7 @@ __device__ inline bool solve_sub_problem(const Problem &P, Scratch &s, unsigned 
     float *sub_cost = reinterpret_cast<float *>(sub_mem + scratch_bytes(2 * kSubMax));
     int *lrow = reinterpret_cast<int *>(sub_cost + kSubMax * kSubMax), *lcol = lrow + kSubMax;
     Problem Q;
-    Q.R = nR; Q.C = nC; Q.n = Q.R + Q.C; Q.half = P.half; Q.dbg = nullptr; Q.why = nullptr;
+    Q.R = nR; Q.C = nC; Q.n = Q.R + Q.C; Q.half = P.half; Q.dbg = nullptr; Q.why = nullptr; Q.no_greedy = P.no_greedy;
     Q.cost = sub_cost;
     Q.row_cnt = lcol + kSubMax; Q.row_adm = Q.row_cnt + kSubMax; Q.col_cnt = Q.row_adm + kSubMax;
     Q.adm_misc = Q.col_cnt + kSubMax;
@@ -1378,175 +1619,6 @@ __device__ inline bool solve_small_warp(const Problem &P, Scratch &s, const Mask
     }
     __syncwarp();
     return !bad;
-}
-
-// ---------------------------------------------------------------------------------
-// Component path for problems of up to 256 x 256 (a hundred or two tracks and detections per
-// sequence: 1080p scenes, the stress workload with ~1000 candidates), by a whole CTA: the same
-// steps as prepare_components_block on 256-bit row / column sets (four 64-bit words, one row
-// per thread).  Components of <= 2 x 2 are solved by the thread that finds them, components up
-// to 4 x 4 are listed by their row / column indices for the enumeration, all larger ones
-// together are listed as the sub-problem of solve_sub_problem (at most kSubMax rows / columns,
-// else the stage falls back to the single-warp path on the whole problem).
-constexpr int kWideMax = 256, kWideWords = kWideMax / 64, kWideComps = 128;
-
-struct WideMasks {
-    unsigned long long *rmask, *cmask, *adj;      // [256][4] each
-    int *comp;                                    // [kWideComps][10]: k, m, rows[4], cols[4]
-    unsigned long long *big;                      // [8]: rows[4], cols[4] of the larger components
-    int *n_comp, *fallback;
-};
-
-__host__ __device__ inline size_t wide_bytes() {
-    return sizeof(unsigned long long) * (3 * kWideMax * kWideWords + 8) + sizeof(int) * (kWideComps * 10 + 4);
-}
-
-__device__ inline WideMasks carve_wide(unsigned char *p) {
-    WideMasks m;
-    m.rmask = reinterpret_cast<unsigned long long *>(p);
-    m.cmask = m.rmask + kWideMax * kWideWords;
-    m.adj = m.cmask + kWideMax * kWideWords;
-    m.big = m.adj + kWideMax * kWideWords;
-    m.comp = reinterpret_cast<int *>(m.big + 8);
-    m.n_comp = m.comp + kWideComps * 10;
-    m.fallback = m.n_comp + 1;
-    return m;
-}
-
-// every thread of the CTA (>= 256 threads) calls it; ends with a barrier.  m.rmask / m.cmask hold the
-// admissibility bits; sub_mem receives the row / column lists of the larger components.
-__device__ inline void prepare_components_wide(const Problem &P, Scratch &s, const WideMasks &m, unsigned char *sub_mem) {
-    const int t = threadIdx.x;
-    const int R = P.R, C = P.C;
-    __shared__ int changed_w;
-    for (int j = t; j < C; j += blockDim.x) s.y[j] = -1;
-    if (t < 8) m.big[t] = 0ull;
-    if (t == 0) { *m.n_comp = 0; *m.fallback = (P.adm_misc[0] != 0 || P.adm_misc[1] != 0) ? 1 : 0; }
-    __syncthreads();
-    bool act = false;
-    unsigned long long rm[kWideWords] = {0ull, 0ull, 0ull, 0ull}, mine[kWideWords] = {0ull, 0ull, 0ull, 0ull};
-    auto popc4 = [](const unsigned long long *w) { return __popcll(w[0]) + __popcll(w[1]) + __popcll(w[2]) + __popcll(w[3]); };
-    auto first4 = [](const unsigned long long *w) {
-        for (int q = 0; q < kWideWords; ++q) if (w[q]) return q * 64 + __ffsll((long long)w[q]) - 1;
-        return -1;
-    };
-    if (t < kWideMax) {
-        if (t < R) {
-#pragma unroll
-            for (int q = 0; q < kWideWords; ++q) rm[q] = m.rmask[t * kWideWords + q];
-            int xr = -1;
-            const int n_adm = popc4(rm);
-            if (n_adm) {
-                const int c = first4(rm);
-                const unsigned long long *cm = m.cmask + c * kWideWords;
-                bool only_me = n_adm == 1;
-#pragma unroll
-                for (int q = 0; q < kWideWords; ++q) only_me = only_me && cm[q] == ((t >> 6) == q ? 1ull << (t & 63) : 0ull);
-                if (only_me) { xr = c; s.y[c] = t; }                   // isolated pair
-                else act = true;
-            }
-            s.x[t] = xr;
-        }
-        if (act)
-#pragma unroll
-            for (int q = 0; q < kWideWords; ++q) {
-                unsigned long long w = rm[q];
-                while (w) {
-                    const int c = q * 64 + __ffsll((long long)w) - 1;
-                    w &= w - 1;
-#pragma unroll
-                    for (int z = 0; z < kWideWords; ++z) mine[z] |= m.cmask[c * kWideWords + z];
-                }
-            }
-#pragma unroll
-        for (int q = 0; q < kWideWords; ++q) m.adj[t * kWideWords + q] = mine[q];
-    }
-    __syncthreads();
-    for (int round = 0; round < 9; ++round) {              // 2^9 > 256 rows
-        if (t == 0) changed_w = 0;
-        __syncthreads();
-        unsigned long long next[kWideWords] = {mine[0], mine[1], mine[2], mine[3]};
-        if (t < kWideMax && act) {
-#pragma unroll
-            for (int q = 0; q < kWideWords; ++q) {
-                unsigned long long w = mine[q];
-                while (w) {
-                    const int r = q * 64 + __ffsll((long long)w) - 1;
-                    w &= w - 1;
-#pragma unroll
-                    for (int z = 0; z < kWideWords; ++z) next[z] |= m.adj[r * kWideWords + z];
-                }
-            }
-            if (next[0] != mine[0] || next[1] != mine[1] || next[2] != mine[2] || next[3] != mine[3]) changed_w = 1;
-        }
-        __syncthreads();
-        if (t < kWideMax) {
-#pragma unroll
-            for (int q = 0; q < kWideWords; ++q) { m.adj[t * kWideWords + q] = next[q]; mine[q] = next[q]; }
-        }
-        __syncthreads();
-        if (!changed_w) break;
-    }
-    // the lowest row of a component publishes it
-    if (t < kWideMax && act && first4(mine) == t) {
-        unsigned long long cols[kWideWords] = {0ull, 0ull, 0ull, 0ull};
-#pragma unroll
-        for (int q = 0; q < kWideWords; ++q) {
-            unsigned long long w = mine[q];
-            while (w) {
-                const int r = q * 64 + __ffsll((long long)w) - 1;
-                w &= w - 1;
-#pragma unroll
-                for (int z = 0; z < kWideWords; ++z) cols[z] |= m.rmask[r * kWideWords + z];
-            }
-        }
-        const int nr = popc4(mine), nc = popc4(cols);
-        if (nr > 4 || nc > 4) {
-#pragma unroll
-            for (int q = 0; q < kWideWords; ++q) { atomicOr(&m.big[q], mine[q]); atomicOr(&m.big[4 + q], cols[q]); }
-        } else {
-            int ri[4] = {-1, -1, -1, -1}, ci[4] = {-1, -1, -1, -1};
-            {
-                int k = 0;
-#pragma unroll
-                for (int q = 0; q < kWideWords; ++q) { unsigned long long w = mine[q]; while (w && k < 4) { ri[k++] = q * 64 + __ffsll((long long)w) - 1; w &= w - 1; } }
-                k = 0;
-#pragma unroll
-                for (int q = 0; q < kWideWords; ++q) { unsigned long long w = cols[q]; while (w && k < 4) { ci[k++] = q * 64 + __ffsll((long long)w) - 1; w &= w - 1; } }
-            }
-            if (nr <= 2 && nc <= 2) {
-                if (*m.fallback == 0 && !solve_tiny_idx(P, s, ri[0], ri[1], ci[0], ci[1])) *m.fallback = 1;
-            } else {
-                const int k = atomicAdd(m.n_comp, 1);
-                if (k < kWideComps) {
-                    int *rec = m.comp + k * 10;
-                    rec[0] = nr; rec[1] = nc;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { rec[2 + q] = ri[q] < 0 ? 0 : ri[q]; rec[6 + q] = ci[q] < 0 ? 0 : ci[q]; }
-                } else {
-                    *m.fallback = 1;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // the larger components as index lists for solve_sub_problem (thread 0; they are few)
-    if (t == 0) {
-        const int nR = __popcll(m.big[0]) + __popcll(m.big[1]) + __popcll(m.big[2]) + __popcll(m.big[3]);
-        const int nC = __popcll(m.big[4]) + __popcll(m.big[5]) + __popcll(m.big[6]) + __popcll(m.big[7]);
-        if (nR > kSubMax || nC > kSubMax) *m.fallback = 1;
-        else if (nR > 0) {
-            float *sub_cost = reinterpret_cast<float *>(sub_mem + scratch_bytes(2 * kSubMax));
-            int *lrow = reinterpret_cast<int *>(sub_cost + kSubMax * kSubMax), *lcol = lrow + kSubMax;
-            int k = 0;
-            for (int q = 0; q < kWideWords; ++q) { unsigned long long w = m.big[q]; while (w) { lrow[k++] = q * 64 + __ffsll((long long)w) - 1; w &= w - 1; } }
-            k = 0;
-            for (int q = 0; q < kWideWords; ++q) { unsigned long long w = m.big[4 + q]; while (w) { lcol[k++] = q * 64 + __ffsll((long long)w) - 1; w &= w - 1; } }
-        }
-        m.big[0] = (unsigned long long)nR;                 // handed to the caller: number of rows / columns listed
-        m.big[1] = (unsigned long long)nC;
-    }
-    __syncthreads();
 }
 
 // Fast path with certified uniqueness, else the exact emulation of the reference's solver.

@@ -62,7 +62,7 @@ for f in range(F):
 out['per_launch_us_median'] = dict(event=float(np.median(evt[8:])), first_start_to_last_end=float(np.median(span[8:])),
                                   start_skew=float(np.median(skew[8:])), longest_cta=float(np.median(longest[8:])),
                                   total_cycles_max_last=int(d[:, 20].max()))
-eng.lib.st_debug_set_skip(0)
+eng.lib.st_debug_set_skip(int(os.environ.get('ST_K4_SKIP', '0')))
 worst_frames = []
 refusals, last_cnt = {}, None
 for f in range(F):
