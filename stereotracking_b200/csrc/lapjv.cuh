@@ -1286,7 +1286,6 @@ __device__ inline void prepare_components(const Problem &P, Scratch &s, const Ma
             ++n;
         }
     }
-    if (__popcll(big_rows) > kSubMax || __popcll(big_cols) > kSubMax) fb = true;
     if (lane == 0) { *m.n_comp = n; *m.fallback = fb ? 1 : 0; m.big[0] = big_rows; m.big[1] = big_cols; }
     __syncwarp();
 }
@@ -1400,7 +1399,6 @@ __device__ inline void prepare_components_block(const Problem &P, Scratch &s, co
         }
     }
     __syncthreads();
-    if (t == 0 && (__popcll(m.big[0]) > kSubMax || __popcll(m.big[1]) > kSubMax)) *m.fallback = 1;
     __syncthreads();
 }
 
@@ -1493,66 +1491,94 @@ __device__ inline bool enumerate_idx(const Problem &P, Scratch &s, const int (&r
     return true;
 }
 
-// The components larger than 4 x 4 (rare: crowded groups) as ONE compact sub-problem of at most
-// kSubMax x kSubMax, solved by the certified Hungarian on one warp while the other warps enumerate
-// the small components.  Rows of these components have admissible entries only in their own
-// columns, so the sub-problem's unique optimum is the restriction of the whole problem's.
-// `sub`: scratch of the sub-problem (n = 2 * kSubMax), `sub_cost` [kSubMax * kSubMax] floats,
-// `sub_idx` [4 * kSubMax + 4] ints (row / column lists and the admissible-edge statistics).
-// Writes x / y of the whole problem for its rows and columns; false = no certificate.
+// The components larger than 4 x 4 (crowded groups) together as ONE sub-problem for the sparse certified
+// solver on one warp, while the other warps enumerate the small components.  Rows of these components
+// have admissible entries only in their own columns, so the sub-problem's unique optimum is the
+// restriction of the whole problem's.  The edge list comes straight from the 64-bit admissibility masks
+// (at most kSubEdges edges, else the whole-problem path); `sub_mem` (sub_bytes()) holds the CSR arrays,
+// the compact -> whole index lists and the solver's state.  Writes x / y of the whole problem for its
+// rows and columns; false = no certificate.
+// (Round 2 first copied a dense <= 32 x 32 sub-matrix and ran the dense certified Hungarian on it: ~20 k
+// cycles for a component of 5-9 tracks, most of them in the admissible-edge statistics, the per-column
+// state set-up and the certificate's column walk of the dense form.)
 __host__ __device__ inline size_t sub_bytes() {
     return scratch_bytes(2 * kSubMax) + sizeof(float) * kSubMax * kSubMax + sizeof(int) * (5 * kSubMax + 4);
 }
 
-__device__ inline bool solve_sub_problem(const Problem &P, Scratch &s, unsigned char *sub_mem, int nR, int nC);
+constexpr int kSubEdges = 256;         // admissible edges the sub-problem of the larger components may hold
+constexpr size_t kSubFront = 144 + 2 * 2 * kSubEdges + 4 * kSubEdges + 128;     // off | erow | ecol | ecost | lrow, lcol
 
 __device__ inline bool solve_big_components(const Problem &P, Scratch &s, const Masks &m, unsigned char *sub_mem) {
+    static_assert(kSubFront % 16 == 0, "state must start 16-byte aligned");
     const int lane = threadIdx.x & 31;
-    unsigned long long rows = m.big[0], cols = m.big[1];
+    const unsigned long long rows = m.big[0], cols = m.big[1];
     if (!rows) return true;
-    float *sub_cost = reinterpret_cast<float *>(sub_mem + scratch_bytes(2 * kSubMax));
-    int *lrow = reinterpret_cast<int *>(sub_cost + kSubMax * kSubMax), *lcol = lrow + kSubMax;
     const int nR = __popcll(rows), nC = __popcll(cols);
-    // lane l takes the l-th row and the l-th column of the sets
-    if (lane < nR) {
-        unsigned long long t = rows;
-        for (int k = 0; k < lane; ++k) t &= t - 1;
-        lrow[lane] = __ffsll((long long)t) - 1;
+    if (kSubFront + sparse_state_bytes(nR, nC) > sub_bytes()) return false;
+    unsigned short *off = reinterpret_cast<unsigned short *>(sub_mem);
+    unsigned short *erow = off + 72, *ecol = erow + kSubEdges;
+    float *ecost = reinterpret_cast<float *>(ecol + kSubEdges);
+    unsigned char *lrow = reinterpret_cast<unsigned char *>(ecost + kSubEdges), *lcol = lrow + 64;
+    // compact numbering: the k-th set bit of `rows` / `cols`; lane l takes rows l and l + 32
+    int gr[2] = {0, 0}, deg[2] = {0, 0};
+    unsigned long long adj[2] = {0ull, 0ull};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < nR) {
+            unsigned long long t = rows;
+            for (int q = 0; q < k; ++q) t &= t - 1;
+            gr[h] = __ffsll((long long)t) - 1;
+            adj[h] = m.rmask[gr[h]] & cols;
+            deg[h] = __popcll(adj[h]);
+            lrow[k] = (unsigned char)gr[h];
+        }
+        if (k < nC) {
+            unsigned long long t = cols;
+            for (int q = 0; q < k; ++q) t &= t - 1;
+            lcol[k] = (unsigned char)(__ffsll((long long)t) - 1);
+        }
     }
-    if (lane < nC) {
-        unsigned long long t = cols;
-        for (int k = 0; k < lane; ++k) t &= t - 1;
-        lcol[lane] = __ffsll((long long)t) - 1;
+    int run = 0, first[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int incl = deg[h];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+        first[h] = run + incl - deg[h];
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
+    const int E = run;
+    if (E > kSubEdges) return false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < nR) {
+            off[k] = (unsigned short)first[h];
+            unsigned long long a = adj[h];
+            int e = first[h];
+            while (a) {
+                const int j = __ffsll((long long)a) - 1;
+                a &= a - 1;
+                erow[e] = (unsigned short)k;
+                ecol[e] = (unsigned short)__popcll(cols & ((1ull << j) - 1ull));
+                ecost[e] = P.cost[(long long)gr[h] * P.C + j];
+                ++e;
+            }
+            s.x[gr[h]] = -1;
+        }
+    }
+    if (lane == 0) off[nR] = (unsigned short)E;
     __syncwarp();
-    return solve_sub_problem(P, s, sub_mem, nR, nC);
-}
-
-// the sub-problem of the rows lrow[0..nR) x columns lcol[0..nC) already listed in sub_mem
-__device__ inline bool solve_sub_problem(const Problem &P, Scratch &s, unsigned char *sub_mem, int nR, int nC) {
-    const int lane = threadIdx.x & 31;
-    Scratch sub = carve(sub_mem, 2 * kSubMax);
-    float *sub_cost = reinterpret_cast<float *>(sub_mem + scratch_bytes(2 * kSubMax));
-    int *lrow = reinterpret_cast<int *>(sub_cost + kSubMax * kSubMax), *lcol = lrow + kSubMax;
-    Problem Q;
-    Q.R = nR; Q.C = nC; Q.n = Q.R + Q.C; Q.half = P.half; Q.dbg = nullptr; Q.why = nullptr; Q.no_greedy = P.no_greedy;
-    Q.cost = sub_cost;
-    Q.row_cnt = lcol + kSubMax; Q.row_adm = Q.row_cnt + kSubMax; Q.col_cnt = Q.row_adm + kSubMax;
-    Q.adm_misc = Q.col_cnt + kSubMax;
-    for (int e = lane; e < Q.R * Q.C; e += 32) {
-        const int i = e / Q.C, j = e - i * Q.C;
-        sub_cost[e] = P.cost[(long long)lrow[i] * P.C + lcol[j]];
-    }
-    __syncwarp();
-    count_admissible(Q);
-    if (!fast_assign_warp(Q, sub)) return false;
-    if (lane < Q.R) {
-        const int j = sub.x[lane];
-        s.x[lrow[lane]] = (j >= 0 && j < Q.C) ? lcol[j] : -1;
-    }
-    if (lane < Q.C) {
-        const int i = sub.y[lane];
-        s.y[lcol[lane]] = (i >= 0 && i < Q.R) ? lrow[i] : -1;
+    Sparse q;
+    q.nR = nR; q.nC = nC; q.E = E; q.half = P.half;
+    q.off = off; q.erow = erow; q.ecol = ecol; q.ecost = ecost; q.why = P.why;
+    sparse_carve_state(q, sub_mem + kSubFront);
+    if (sparse_assign_warp(q) != 0) return false;
+    for (int j = lane; j < nC; j += 32) {
+        const int r = q.p[j];
+        s.y[lcol[j]] = r >= 0 ? (int)lrow[r] : -1;
+        if (r >= 0) s.x[lrow[r]] = lcol[j];
     }
     __syncwarp();
     return true;
