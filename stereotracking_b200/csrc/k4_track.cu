@@ -636,6 +636,16 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
                 __syncwarp();
                 ok = stlap::assign_warp(P, sc, nullptr);
             }
+        } else if (mode == 2) {
+            // crowded / wide problems: the sparse certified solver of the round-2 tracker kernel
+            __shared__ int hdr[4];
+            const int verdict = stlap::sparse_assign_block(P, sc, (size_t)24 * (R + C), hdr, nullptr);
+            ok = true;
+            if (verdict != 0) {
+                if (lane == 0) atomicAdd(fallbacks, 1);
+                __syncwarp();
+                ok = (verdict == 1 || verdict == 6 || verdict == 7) ? stlap::solve_warp(P, sc) : stlap::assign_warp(P, sc, nullptr);
+            }
         } else {
             ok = R + C <= 512 && stlap::fast_assign_warp(P, sc);       // certified fast path
             if (!ok) {

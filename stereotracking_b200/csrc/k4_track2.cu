@@ -321,83 +321,11 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
             need_warp_path = true;
         }
     } else {
-        // crowded or wide problems: the sparse certified solver on the admissible edges (lapjv.cuh)
-        int verdict = 8;                                 // 8 = does not fit the arena
-        if (sm.adm_misc[0] == 0 && sm.adm_misc[1] == 0) {
-            // arena: the part of the whole-problem scratch in front of x / y (v, d, cols, pred: 24 bytes per node)
-            unsigned char *arena = reinterpret_cast<unsigned char *>(const_cast<double *>(sm.lap.v));
-            const size_t arena_bytes = (size_t)24 * (pr.T + pr.D);
-            int *rmap = reinterpret_cast<int *>(arena), *cmap = rmap + R, *rlist = cmap + C, *clist = rlist + R;
-            for (int r = threadIdx.x; r < R; r += kThreads) sm.lap.x[r] = -1;
-            for (int c = threadIdx.x; c < C; c += kThreads) sm.lap.y[c] = -1;
-            if (warp == 0) {
-                compact_warp(R, [&](int r) { return sm.row_cnt[r] > 0; }, rlist, &sp_hdr[0]);
-                __syncwarp();
-                for (int k = threadIdx.x; k < sp_hdr[0]; k += 32) rmap[rlist[k]] = k;
-            } else if (warp == 1) {
-                compact_warp(C, [&](int c) { return sm.col_cnt[c] > 0; }, clist, &sp_hdr[1]);
-                __syncwarp();
-                for (int k = threadIdx.x & 31; k < sp_hdr[1]; k += 32) cmap[clist[k]] = k;
-            }
-            __syncthreads();
-            const int nR = sp_hdr[0], nC = sp_hdr[1];
-            size_t at = ((size_t)8 * (R + C) + 15) & ~(size_t)15;
-            int *cursor = reinterpret_cast<int *>(arena + at); at += ((size_t)4 * nR + 15) & ~(size_t)15;
-            unsigned short *off = reinterpret_cast<unsigned short *>(arena + at); at += ((size_t)2 * (nR + 1) + 15) & ~(size_t)15;
-            // edge offsets: exclusive prefix of the admissible counts of the kept rows (warp 0)
-            if (warp == 0 && at <= arena_bytes) {
-                const int lane = threadIdx.x;
-                int run = 0;
-                for (int k0 = 0; k0 < nR; k0 += 32) {
-                    const int k = k0 + lane;
-                    const int cnt = k < nR ? sm.row_cnt[rlist[k]] : 0;
-                    int incl = cnt;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
-                    if (k < nR) { off[k] = (unsigned short)min(run + incl - cnt, 65535); cursor[k] = run + incl - cnt; }
-                    run += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (lane == 0) { off[nR] = (unsigned short)min(run, 65535); sp_hdr[2] = run; }
-            }
-            __syncthreads();
-            const int E = sp_hdr[2];
-            unsigned short *erow = reinterpret_cast<unsigned short *>(arena + at); at += ((size_t)2 * E + 15) & ~(size_t)15;
-            unsigned short *ecol = reinterpret_cast<unsigned short *>(arena + at); at += ((size_t)2 * E + 15) & ~(size_t)15;
-            float *ecost = reinterpret_cast<float *>(arena + at); at += ((size_t)4 * E + 15) & ~(size_t)15;
-            const bool fits = at + stlap::sparse_state_bytes(nR, nC) <= arena_bytes && E < 65535 && nR + nC <= 512;
-            if (fits) {
-                // the admissible entries of the matrix, grouped by row (order inside a row does not matter)
-                for (int e = threadIdx.x; e < R * C; e += kThreads) {
-                    const float dist = dense[e];
-                    if ((double)dist < lap_limit) {
-                        const int r = e / C, j = e - r * C;
-                        const int k = atomicAdd(&cursor[rmap[r]], 1);
-                        erow[k] = (unsigned short)rmap[r]; ecol[k] = (unsigned short)cmap[j]; ecost[k] = dist;
-                    }
-                }
-                __syncthreads();
-                ST_SUB(15);
-                if (warp == 0) {
-                    stlap::Sparse q;
-                    q.nR = nR; q.nC = nC; q.E = E; q.half = pr.lap_half;
-                    q.off = off; q.erow = erow; q.ecol = ecol; q.ecost = ecost;
-                    q.why = stage_code == 1 ? dbg + 24 : nullptr;
-                    stlap::sparse_carve_state(q, arena + at);
-                    const int code = nR == 0 ? 0 : stlap::sparse_assign_warp(q);
-                    if (code == 0)
-                        for (int j = threadIdx.x; j < nC; j += 32) {
-                            const int rr = q.p[j];
-                            if (rr >= 0) { sm.lap.y[clist[j]] = rlist[rr]; sm.lap.x[rlist[rr]] = clist[j]; }
-                        }
-                    else if (q.why && threadIdx.x == 0) { q.why[0] = code; atomicAdd(&q.why[1], 1); }
-                    if (threadIdx.x == 0) sp_hdr[3] = code;
-                }
-                __syncthreads();
-                verdict = sp_hdr[3];
-            }
-        } else {
-            verdict = 1;                                 // NaN / a cost within 2e-9 of the limit: the exact path decides
-        }
+        // crowded or wide problems: the sparse certified solver on the admissible edges (lapjv.cuh); its arena is
+        // the part of the whole-problem scratch in front of x / y (v, d, cols, pred: 24 bytes per node)
+        const int verdict = stlap::sparse_assign_block(P, sm.lap, (size_t)24 * (pr.T + pr.D), sp_hdr,
+                                                       stage_code == 1 ? dbg + 24 : nullptr);
+        ST_SUB(15);
         need_warp_path = verdict != 0;
         sparse_refused = verdict == 1 || verdict == 6 || verdict == 7;   // the dense certified path would refuse as well
     }

@@ -1138,6 +1138,103 @@ static __device__ __noinline__ int sparse_assign_warp(const Sparse &q) {
     return verdict;
 }
 
+// The sparse solver for a whole problem, called by EVERY thread of the CTA (blockDim.x a multiple of 32;
+// a one-warp CTA works too): drops the rows / columns without admissible entries, builds the CSR edge
+// list from the dense matrix (P.row_cnt / col_cnt / adm_misc must be filled), runs sparse_assign_warp on
+// warp 0 and writes x / y of the whole problem.  Everything lives in the part of the whole-problem
+// scratch in front of x / y (v, d, cols, pred: `arena_bytes` = 24 bytes per node of its capacity).
+// hdr: 4 ints of shared memory.  Returns the block-uniform verdict: 0 = solved with certificate,
+// 1 / 6 / 7 = the dense certified path would refuse as well (NaN, near-limit cost, equal-cost
+// alternative), 8 = does not fit, other = a guard.
+template <typename F>
+__device__ __forceinline__ int compact_by_warp(int n, F flag, int *dst) {
+    const int lane = threadIdx.x & 31;
+    int total = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool f = i < n && flag(i);
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (f) dst[total + __popc(b & ((1u << lane) - 1u))] = i;
+        total += __popc(b);
+    }
+    __syncwarp();
+    return total;
+}
+
+__device__ __forceinline__ int sparse_assign_block(const Problem &P, Scratch &s, size_t arena_bytes, int *hdr, int *why) {
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int R = P.R, C = P.C;
+    const double L = 2.0 * P.half;
+    if (P.adm_misc[0] != 0 || P.adm_misc[1] != 0) return 1;
+    size_t at = ((size_t)8 * (R + C) + 15) & ~(size_t)15;
+    if (at > arena_bytes) return 8;
+    unsigned char *arena = reinterpret_cast<unsigned char *>(const_cast<double *>(s.v));
+    int *rmap = reinterpret_cast<int *>(arena), *cmap = rmap + R, *rlist = cmap + C, *clist = rlist + R;
+    for (int r = tid; r < R; r += nthr) s.x[r] = -1;
+    for (int c = tid; c < C; c += nthr) s.y[c] = -1;
+    if (warp == 0) {
+        const int n = compact_by_warp(R, [&](int r) { return P.row_cnt[r] > 0; }, rlist);
+        for (int k = lane; k < n; k += 32) rmap[rlist[k]] = k;
+        if (lane == 0) hdr[0] = n;
+    }
+    if (warp == (nthr > 32 ? 1 : 0)) {
+        const int n = compact_by_warp(C, [&](int c) { return P.col_cnt[c] > 0; }, clist);
+        for (int k = lane; k < n; k += 32) cmap[clist[k]] = k;
+        if (lane == 0) hdr[1] = n;
+    }
+    __syncthreads();
+    const int nR = hdr[0], nC = hdr[1];
+    int *cursor = reinterpret_cast<int *>(arena + at); at += ((size_t)4 * nR + 15) & ~(size_t)15;
+    unsigned short *off = reinterpret_cast<unsigned short *>(arena + at); at += ((size_t)2 * (nR + 1) + 15) & ~(size_t)15;
+    // edge offsets: exclusive prefix of the admissible counts of the kept rows (warp 0)
+    if (warp == 0 && at <= arena_bytes) {
+        int run = 0;
+        for (int k0 = 0; k0 < nR; k0 += 32) {
+            const int k = k0 + lane;
+            const int cnt = k < nR ? P.row_cnt[rlist[k]] : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+            if (k < nR) { off[k] = (unsigned short)min(run + incl - cnt, 65535); cursor[k] = run + incl - cnt; }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) { off[nR] = (unsigned short)min(run, 65535); hdr[2] = run; }
+    }
+    __syncthreads();
+    if (at > arena_bytes) return 8;
+    const int E = hdr[2];
+    unsigned short *erow = reinterpret_cast<unsigned short *>(arena + at); at += ((size_t)2 * E + 15) & ~(size_t)15;
+    unsigned short *ecol = reinterpret_cast<unsigned short *>(arena + at); at += ((size_t)2 * E + 15) & ~(size_t)15;
+    float *ecost = reinterpret_cast<float *>(arena + at); at += ((size_t)4 * E + 15) & ~(size_t)15;
+    if (at + sparse_state_bytes(nR, nC) > arena_bytes || E >= 65535 || nR + nC > 512) return 8;
+    // the admissible entries of the matrix, grouped by row (the order inside a row does not matter)
+    for (int e = tid; e < R * C; e += nthr) {
+        const float dist = P.cost[e];
+        if ((double)dist < L) {
+            const int r = e / C, j = e - r * C;
+            const int k = atomicAdd(&cursor[rmap[r]], 1);
+            erow[k] = (unsigned short)rmap[r]; ecol[k] = (unsigned short)cmap[j]; ecost[k] = dist;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        Sparse q;
+        q.nR = nR; q.nC = nC; q.E = E; q.half = P.half;
+        q.off = off; q.erow = erow; q.ecol = ecol; q.ecost = ecost; q.why = why;
+        sparse_carve_state(q, arena + at);
+        const int code = nR == 0 ? 0 : sparse_assign_warp(q);
+        if (code == 0)
+            for (int j = lane; j < nC; j += 32) {
+                const int rr = q.p[j];
+                if (rr >= 0) { s.y[clist[j]] = rlist[rr]; s.x[rlist[rr]] = clist[j]; }
+            }
+        else if (why && lane == 0) { why[0] = code; atomicAdd(&why[1], 1); }
+        if (lane == 0) hdr[3] = code;
+    }
+    __syncthreads();
+    return hdr[3];
+}
+
 // ---------------------------------------------------------------------------------
 // Component path (problems with R, C <= 64).  The objective of the extended problem is
 // sum over matched pairs of (c_ij - L): only ADMISSIBLE entries (c_ij < L) can be part of an

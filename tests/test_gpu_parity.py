@@ -491,12 +491,15 @@ def test_lapjv_batch_matches_oracle(mods, R, C, ties):
 
 
 @pytest.mark.parametrize('R,C,kind', [(1, 1, 'dense'), (7, 5, 'dense'), (30, 27, 'sparse'), (64, 64, 'sparse'),
-                                      (50, 60, 'ties'), (12, 12, 'dupes'), (40, 33, 'dense')])
+                                      (50, 60, 'ties'), (12, 12, 'dupes'), (40, 33, 'dense'),
+                                      (170, 240, 'crowd'), (70, 300, 'crowd'), (150, 120, 'crowd_ties'), (90, 40, 'crowd')])
 def test_lapjv_component_path_matches_oracle(mods, R, C, kind):
     """The component path of the round-2 tracker kernel (isolated pairs, connected components of the
     admissible graph, enumeration of components <= 4 x 4 with the uniqueness certificate from the
     same enumeration; anything else falls back to the certified Hungarian / literal JV emulation)
-    against the JV oracle: tracking-shaped sparse problems, dense ones, exact ties, duplicate rows."""
+    against the JV oracle: tracking-shaped sparse problems, dense ones, exact ties, duplicate rows; and,
+    beyond 64 rows or columns, the sparse certified solver on the admissible edges: crowds whose rows
+    chain into components of a hundred tracks, with and without exact ties."""
     rng = np.random.default_rng(R * 131 + C)
     B = 48
     if kind == 'sparse':
@@ -511,6 +514,24 @@ def test_lapjv_component_path_matches_oracle(mods, R, C, kind):
                 rows = rng.choice(R, rng.integers(2, 5), replace=False)
                 cols = rng.choice(C, rng.integers(2, 5), replace=False)
                 cost[b][np.ix_(rows, cols)] = rng.uniform(0.1, 0.88, (len(rows), len(cols)))
+    elif kind in ('crowd', 'crowd_ties'):
+        B = 24
+        cost = rng.uniform(0.95, 1.3, (B, R, C)).astype(np.float32)
+        n = min(R, C)
+        for b in range(B):
+            perm = rng.permutation(C)[:n]
+            rows = rng.permutation(R)[:n]
+            for k in range(n):
+                if rng.random() < 0.9:
+                    cost[b, rows[k], perm[k]] = rng.uniform(0.05, 0.6)
+                if k + 1 < n and rng.random() < 0.6:                    # neighbours overlap: long chains
+                    cost[b, rows[k], perm[k + 1]] = rng.uniform(0.3, 0.89)
+                if k > 0 and rng.random() < 0.3:
+                    cost[b, rows[k], perm[k - 1]] = rng.uniform(0.3, 0.89)
+            extra = rng.integers(0, R * C, 40)
+            cost[b].reshape(-1)[extra] = rng.uniform(0.5, 0.89, 40)
+            if kind == 'crowd_ties' and b % 2 == 0:                      # two tracks over the same two detections
+                cost[b][np.ix_(rows[:2], perm[:2])] = 0.5
     elif kind == 'ties':
         cost = (rng.integers(0, 5, (B, R, C)) * 0.25).astype(np.float32)
     elif kind == 'dupes':
@@ -531,7 +552,9 @@ def test_lapjv_component_path_matches_oracle(mods, R, C, kind):
     fallbacks = int(eng.debug_words()[0, 6])
     if kind == 'sparse':
         assert fallbacks < B, 'tracking-shaped problems without a large component are solved by enumeration'
-    if kind in ('ties', 'dupes'):
+    if kind == 'crowd':
+        assert fallbacks == 0, 'tie-free crowds are certified by the sparse solver'
+    if kind in ('ties', 'dupes', 'crowd_ties'):
         assert fallbacks > 0, 'ties must reach the exact emulation'
 
 
