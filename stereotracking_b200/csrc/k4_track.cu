@@ -605,17 +605,19 @@ __global__ void k4_reset(TrackState st, int T, const uint8_t *__restrict__ mask)
 }
 
 __global__ void __launch_bounds__(32)
-k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mode,
+k5_lapjv_batch(int R, int C, int n_alloc /* nodes the scratch is sized for: the handle's max_tracks + max_dets, as in the
+                                             tracker kernel, so that the sparse path finds the same arena */,
+               const float *__restrict__ cost, double half, int mode,
                int32_t *__restrict__ row2col, int32_t *__restrict__ col2row, int32_t *__restrict__ status,
                int32_t *__restrict__ fallbacks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, lane = threadIdx.x;
-    stlap::Scratch sc = stlap::carve(smem_raw, R + C);
+    stlap::Scratch sc = stlap::carve(smem_raw, n_alloc);
     stlap::Problem P;
     P.cost = cost + (long long)b * R * C; P.R = R; P.C = C; P.n = R + C; P.half = half;
     P.dbg = nullptr;
     P.why = nullptr; P.no_greedy = 0;
-    int *stats = reinterpret_cast<int *>(smem_raw + stlap::scratch_bytes(R + C));
+    int *stats = reinterpret_cast<int *>(smem_raw + stlap::scratch_bytes(n_alloc));
     P.row_cnt = stats; P.row_adm = stats + R; P.col_cnt = stats + 2 * R; P.adm_misc = stats + 2 * R + C;
     if (R > 0 && C > 0) {
         stlap::count_admissible(P);
@@ -623,7 +625,7 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
         if (mode == 1) ok = stlap::solve_warp(P, sc);                 // exact emulation only
         else if (mode == 2 && R <= 64 && C <= 64) {
             // component path of the round-2 tracker kernel, on one warp
-            stlap::Masks mk = stlap::carve_masks(smem_raw + ((stlap::scratch_bytes(R + C) + sizeof(int) * (2 * R + C + 4) + 15) & ~(size_t)15));
+            stlap::Masks mk = stlap::carve_masks(smem_raw + ((stlap::scratch_bytes(n_alloc) + sizeof(int) * (2 * R + C + 4) + 15) & ~(size_t)15));
             stlap::build_masks(P, mk);
             stlap::prepare_components(P, sc, mk);
             bool bad = *mk.fallback != 0;
@@ -639,7 +641,7 @@ k5_lapjv_batch(int R, int C, const float *__restrict__ cost, double half, int mo
         } else if (mode == 2) {
             // crowded / wide problems: the sparse certified solver of the round-2 tracker kernel
             __shared__ int hdr[4];
-            const int verdict = stlap::sparse_assign_block(P, sc, (size_t)24 * (R + C), hdr, nullptr);
+            const int verdict = stlap::sparse_assign_block(P, sc, (size_t)24 * n_alloc, hdr, nullptr);
             ok = true;
             if (verdict != 0) {
                 if (lane == 0) atomicAdd(fallbacks, 1);
@@ -1080,9 +1082,10 @@ extern "C" int st_lapjv_batch(st_handle *h, int B, int R, int C, const float *co
         return ST_ERR_INVALID_ARG;
     StDeviceGuard guard(h->device);
     if (B == 0 || R + C == 0) return ST_OK;
-    k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(R + C) + sizeof(int) * (2 * R + C + 4) + 32 + stlap::masks_bytes() +
+    const int n_alloc = h->cfg.max_tracks + h->cfg.max_dets;
+    k5_lapjv_batch<<<B, 32, stlap::scratch_bytes(n_alloc) + sizeof(int) * (2 * R + C + 4) + 32 + stlap::masks_bytes() +
                             stlap::sub_bytes(),
                      (cudaStream_t)stream>>>(
-        R, C, cost, cost_limit / 2.0, mode, row2col, col2row, h->st.status, h->st.debug + 6);
+        R, C, n_alloc, cost, cost_limit / 2.0, mode, row2col, col2row, h->st.status, h->st.debug + 6);
     return st_last_launch();
 }

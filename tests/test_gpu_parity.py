@@ -541,7 +541,9 @@ def test_lapjv_component_path_matches_oracle(mods, R, C, kind):
     else:
         cost = rng.uniform(0, 1.3, (B, R, C)).astype(np.float32)
         cost[:, np.arange(min(R, C)), np.arange(min(R, C))] *= 0.2
-    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1))
+    # the sparse path finds its arena in the scratch sized for the handle's capacities, as in the tracker kernel
+    caps = dict(max_tracks=512, max_dets=512) if kind.startswith('crowd') else {}
+    eng = mods.StereoTrackEngine(mods.EngineConfig(n_seq=1, **caps))
     ref = [mods.lapjv(cost[b], 0.9) for b in range(B)]
     x, y = eng.lapjv_batch(cuda(cost), 0.9, mode=2)
     assert eng.status().max() == 0
