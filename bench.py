@@ -563,8 +563,10 @@ def main():
             cpu = dict(value=fps, unit=UNIT, cores=used, kind='port', single_core=single,
                        sample=f'first {n_seqs} sequences x {fsub} frames of this workload, oracle (NumPy/C port of '
                               f'the reference tracker path), one process per core')
+        trk_sms, other_sms = groups.pipes[0].partition()
         config.update(depth_source=modes[0], cuda_graph=bool(args.graph), value_repetitions=int(len(ms_all)),
-                      e2e_repetitions=int(len(e2e_ms_reps)))
+                      e2e_repetitions=int(len(e2e_ms_reps)),
+                      sm_partition=dict(tracker_sms=trk_sms, other_sms=other_sms) if trk_sms else None)
         other = modes[1]
         oms = float(np.median(timing[other]['ms']))
         line = dict(

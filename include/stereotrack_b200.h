@@ -297,6 +297,12 @@ int st_pipeline_submit(st_pipeline *p, int S, const st_frame_io *io, void *input
  * results; st_pipeline_stats reports how many frames were replayed and how many captures ran. */
 int st_pipeline_use_graphs(st_pipeline *p, int enable);
 int st_pipeline_stats(st_pipeline *p, long long *graph_frames, long long *captures);
+/* SM partition of the pipeline (environment ST_PIPE_PARTITION=1 at st_pipeline_create, while max_sequences is at
+ * most ~55 % of the SMs): the tracker stream runs in a green context that owns tracker_sms SMs - one tracker CTA
+ * per sequence, one SM each -, every other stream of the pipeline in a second one with the remaining SMs, so the
+ * latency-bound tracker never shares an SM with the streaming stages of the neighbouring frames.  Both are 0
+ * when the pipeline is not partitioned (switched off, driver without green contexts, too many sequences). */
+int st_pipeline_partition(st_pipeline *p, int *tracker_sms, int *other_sms);
 /* the pipeline's streams start after the work already queued on `stream` */
 int st_pipeline_fork(st_pipeline *p, void *stream);
 /* `stream` waits for every frame submitted so far */

@@ -77,6 +77,7 @@ _SIGNATURES = {
     'st_pipeline_submit': (_I, [_P, _I, C.POINTER(StFrameIO), _P, _P]),
     'st_pipeline_use_graphs': (_I, [_P, _I]),
     'st_pipeline_stats': (_I, [_P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    'st_pipeline_partition': (_I, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'st_pipeline_fork': (_I, [_P, _P]),
     'st_pipeline_join': (_I, [_P, _P]),
     'st_pipeline_trace': (_I, [_P, _I]),

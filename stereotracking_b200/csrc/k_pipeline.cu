@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <cuda.h>
 #include "st_common.cuh"
 
 namespace {
@@ -119,7 +120,13 @@ struct st_pipeline {
     int skip;                          // diagnostics (ST_PIPE_SKIP): bit i = leave stage i's kernels out
     long long submitted;
     cudaStream_t *pre, *side;          // [depth]
+    cudaStream_t *aux;                 // [depth] K3's auxiliary stream of every slot when the SMs are partitioned
     cudaStream_t trk;
+    // SM partition (green contexts, ST_PIPE_PARTITION): the tracker stream owns trk_sms SMs, every other
+    // stream of the pipeline the rest, so that the latency-bound tracker CTAs never share an SM with the
+    // streaming stages of the neighbouring frames
+    void *green_trk, *green_rest;
+    int trk_sms, rest_sms;
     cudaEvent_t *ev;                   // [4][depth]: pre done, tracker done, K1 fork, K1 join
     cudaEvent_t fork_ev;
     void *scratch_mem;                 // K2 candidate scratch of every slot + the input tables
@@ -274,6 +281,64 @@ void free_trace(st_pipeline *p) {
     p->trace_ev = nullptr;
 }
 
+// ---- SM partition through green contexts (driver entry points fetched at run time: no libcuda link) ----
+struct GreenApi {
+    decltype(&cuDeviceGet) deviceGet;
+    decltype(&cuDeviceGetDevResource) getDevResource;
+    decltype(&cuDevSmResourceSplitByCount) splitByCount;
+    decltype(&cuDevResourceGenerateDesc) generateDesc;
+    decltype(&cuGreenCtxCreate) ctxCreate;
+    decltype(&cuGreenCtxDestroy) ctxDestroy;
+    decltype(&cuGreenCtxStreamCreate) streamCreate;
+    bool ok;
+};
+
+const GreenApi &green_api() {
+    static const GreenApi api = [] {
+        GreenApi a;
+        memset(&a, 0, sizeof(a));
+        auto get = [](const char *name, void **f) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *f;
+        };
+        a.ok = get("cuDeviceGet", (void **)&a.deviceGet) && get("cuDeviceGetDevResource", (void **)&a.getDevResource) &&
+               get("cuDevSmResourceSplitByCount", (void **)&a.splitByCount) &&
+               get("cuDevResourceGenerateDesc", (void **)&a.generateDesc) && get("cuGreenCtxCreate", (void **)&a.ctxCreate) &&
+               get("cuGreenCtxDestroy", (void **)&a.ctxDestroy) && get("cuGreenCtxStreamCreate", (void **)&a.streamCreate);
+        cudaGetLastError();
+        return a;
+    }();
+    return api;
+}
+
+// two green contexts on `device`: at least `want` SMs for the tracker, the remainder for everything else
+bool partition_create(int device, int want, st_pipeline *p) {
+    const GreenApi &a = green_api();
+    if (!a.ok) return false;
+    CUdevice dev;
+    CUdevResource all, part, rest;
+    unsigned groups = 1;
+    if (a.deviceGet(&dev, device) != CUDA_SUCCESS || a.getDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS ||
+        a.splitByCount(&part, &groups, &all, &rest, 0, (unsigned)want) != CUDA_SUCCESS || groups != 1 || rest.sm.smCount < 16)
+        return false;
+    CUdevResourceDesc d_trk, d_rest;
+    CUgreenCtx g_trk = nullptr, g_rest = nullptr;
+    if (a.generateDesc(&d_trk, &part, 1) != CUDA_SUCCESS || a.generateDesc(&d_rest, &rest, 1) != CUDA_SUCCESS ||
+        a.ctxCreate(&g_trk, d_trk, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS)
+        return false;
+    if (a.ctxCreate(&g_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { a.ctxDestroy(g_trk); return false; }
+    p->green_trk = g_trk; p->green_rest = g_rest;
+    p->trk_sms = (int)part.sm.smCount; p->rest_sms = (int)rest.sm.smCount;
+    return true;
+}
+
+bool partition_stream(void *green, int priority, cudaStream_t *s) {
+    CUstream cs = nullptr;
+    if (green_api().streamCreate(&cs, (CUgreenCtx)green, CU_STREAM_NON_BLOCKING, priority) != CUDA_SUCCESS) return false;
+    *s = (cudaStream_t)cs;
+    return true;
+}
+
 }  // namespace
 
 extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
@@ -286,6 +351,7 @@ extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
     { const char *e = getenv("ST_PIPE_SKIP"); p->skip = e ? atoi(e) : 0; }
     p->pre = new (std::nothrow) cudaStream_t[depth]();
     p->side = new (std::nothrow) cudaStream_t[depth]();
+    p->aux = new (std::nothrow) cudaStream_t[depth]();
     p->ev = new (std::nothrow) cudaEvent_t[EV_KINDS * depth]();
     p->scratch = new (std::nothrow) StK2Scratch[depth]();
     p->tab_host = new (std::nothrow) StFrameInputs[depth]();
@@ -294,7 +360,7 @@ extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
     p->g_post = new (std::nothrow) cudaGraphExec_t[depth]();
     p->have_graph = new (std::nothrow) bool[depth]();
     p->key = new (std::nothrow) GraphKey[depth]();
-    bool ok = p->pre && p->side && p->ev && p->scratch && p->tab_host && p->tab_valid && p->g_pre && p->g_post &&
+    bool ok = p->pre && p->side && p->aux && p->ev && p->scratch && p->tab_host && p->tab_valid && p->g_pre && p->g_post &&
               p->have_graph && p->key;
     ok = ok && cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming) == cudaSuccess;
     // Stream priorities: K1 (bandwidth-bound, fills every SM for its whole duration) on the lowest
@@ -305,11 +371,24 @@ extern "C" int st_pipeline_create(st_handle *h, int depth, st_pipeline **out) {
     const char *pe = getenv("ST_PIPE_PRIO");
     const int prio_mode = pe ? atoi(pe) : 2;
     const int hi = prio_mode ? prio_hi : 0, lo = prio_mode ? prio_lo : 0;
-    for (int i = 0; ok && i < depth; ++i) {
-        ok = cudaStreamCreateWithPriority(&p->pre[i], cudaStreamNonBlocking, hi) == cudaSuccess &&
-             cudaStreamCreateWithPriority(&p->side[i], cudaStreamNonBlocking, lo) == cudaSuccess;
+    // SM partition: one tracker CTA per sequence, one SM each; worth it while that leaves most of the device to
+    // the other stages (ST_PIPE_PARTITION=0 / 1 forces it off / on)
+    {
+        const char *ge = getenv("ST_PIPE_PARTITION");
+        const int want = (h->cfg.max_sequences + 7) & ~7;
+        const bool wanted = ge ? atoi(ge) != 0 : false;
+        if (ok && wanted && want * 20 <= st_ctx_sms() * 11) partition_create(h->device, want, p);
     }
-    ok = ok && cudaStreamCreateWithPriority(&p->trk, cudaStreamNonBlocking, hi) == cudaSuccess;
+    for (int i = 0; ok && i < depth; ++i) {
+        if (p->green_rest)
+            ok = partition_stream(p->green_rest, hi, &p->pre[i]) && partition_stream(p->green_rest, lo, &p->side[i]) &&
+                 partition_stream(p->green_rest, hi, &p->aux[i]) && st_ctx_set_aux(p->pre[i], p->aux[i]) == ST_OK;
+        else
+            ok = cudaStreamCreateWithPriority(&p->pre[i], cudaStreamNonBlocking, hi) == cudaSuccess &&
+                 cudaStreamCreateWithPriority(&p->side[i], cudaStreamNonBlocking, lo) == cudaSuccess;
+    }
+    if (p->green_trk) ok = ok && partition_stream(p->green_trk, hi, &p->trk);
+    else ok = ok && cudaStreamCreateWithPriority(&p->trk, cudaStreamNonBlocking, hi) == cudaSuccess;
     for (int i = 0; ok && i < EV_KINDS * depth; ++i)
         ok = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming) == cudaSuccess;
     // K2 candidate scratch per slot (the pre segments of frames in flight run concurrently) and
@@ -344,6 +423,10 @@ extern "C" int st_pipeline_destroy(st_pipeline *p) {
     cudaDeviceSynchronize();
     for (int i = 0; i < p->depth; ++i) {
         if (p->have_graph) drop_graphs(p, i);
+        if (p->aux && p->aux[i]) {                       // partitioned: the pairing dies with the streams
+            if (p->pre && p->pre[i]) st_ctx_drop_aux(p->pre[i]);
+            cudaStreamDestroy(p->aux[i]);
+        }
         if (p->pre && p->pre[i]) cudaStreamDestroy(p->pre[i]);
         if (p->side && p->side[i]) cudaStreamDestroy(p->side[i]);
     }
@@ -352,9 +435,11 @@ extern "C" int st_pipeline_destroy(st_pipeline *p) {
             if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     if (p->fork_ev) cudaEventDestroy(p->fork_ev);
     if (p->trk) cudaStreamDestroy(p->trk);
+    if (p->green_trk) green_api().ctxDestroy((CUgreenCtx)p->green_trk);
+    if (p->green_rest) green_api().ctxDestroy((CUgreenCtx)p->green_rest);
     free_trace(p);
     if (p->scratch_mem) cudaFree(p->scratch_mem);
-    delete[] p->pre; delete[] p->side; delete[] p->ev; delete[] p->scratch; delete[] p->tab_host;
+    delete[] p->pre; delete[] p->side; delete[] p->aux; delete[] p->ev; delete[] p->scratch; delete[] p->tab_host;
     delete[] p->tab_valid; delete[] p->g_pre; delete[] p->g_post; delete[] p->have_graph; delete[] p->key;
     delete p;
     return ST_OK;
@@ -363,6 +448,13 @@ extern "C" int st_pipeline_destroy(st_pipeline *p) {
 extern "C" int st_pipeline_use_graphs(st_pipeline *p, int enable) {
     if (!p) return ST_ERR_INVALID_ARG;
     p->use_graphs = enable != 0;
+    return ST_OK;
+}
+
+extern "C" int st_pipeline_partition(st_pipeline *p, int *tracker_sms, int *other_sms) {
+    if (!p || !tracker_sms || !other_sms) return ST_ERR_INVALID_ARG;
+    *tracker_sms = p->green_trk ? p->trk_sms : 0;
+    *other_sms = p->green_trk ? p->rest_sms : 0;
     return ST_OK;
 }
 

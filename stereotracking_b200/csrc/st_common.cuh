@@ -139,6 +139,8 @@ int st_ctx_sms();                            // SM count of the current device
 // fork / join helper: the auxiliary stream paired with `caller` (created at first use, same
 // priority) and two events of the device's ring
 int st_ctx_aux(cudaStream_t caller, cudaStream_t *aux, cudaEvent_t *ev_fork, cudaEvent_t *ev_join);
+int st_ctx_set_aux(cudaStream_t caller, cudaStream_t aux);
+void st_ctx_drop_aux(cudaStream_t caller);
 
 // Lazily initialised per-device values of one translation unit (occupancy-derived grids,
 // shared-memory opt-ins): init(T&) -> bool runs once per device under the mutex; a failed

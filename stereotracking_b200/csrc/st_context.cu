@@ -68,3 +68,23 @@ int st_ctx_aux(cudaStream_t caller, cudaStream_t *aux, cudaEvent_t *ev_fork, cud
     *ev_join = c->ev[c->ev_next++ % StDeviceCtx::kEvents];
     return ST_OK;
 }
+
+// Pairs `caller` with an auxiliary stream the caller created itself (the frame pipeline creates its streams
+// inside an SM partition and wants K3's forked kernels to stay there).  Must run before the first
+// st_ctx_aux(caller, ...); an existing pairing is kept and ST_ERR_INVALID_ARG returned.
+int st_ctx_set_aux(cudaStream_t caller, cudaStream_t aux) {
+    StDeviceCtx *c = st_ctx();
+    if (!c) return ST_ERR_CUDA;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (c->aux.find(caller) != c->aux.end()) return ST_ERR_INVALID_ARG;
+    c->aux.emplace(caller, aux);
+    return ST_OK;
+}
+
+// Forgets the pairing of `caller` (its streams are about to be destroyed; a later stream may reuse the handle).
+void st_ctx_drop_aux(cudaStream_t caller) {
+    StDeviceCtx *c = st_ctx();
+    if (!c) return;
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->aux.erase(caller);
+}

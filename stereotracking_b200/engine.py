@@ -604,6 +604,12 @@ class FramePipeline:
         """Replay frames as CUDA graphs (st_pipeline_use_graphs): from a slot's second use on."""
         _lib.check(self.engine.lib.st_pipeline_use_graphs(self._p, int(bool(enable))), 'st_pipeline_use_graphs')
 
+    def partition(self):
+        """(tracker SMs, other SMs) of the pipeline's SM partition, (0, 0) when not partitioned (st_pipeline_partition)."""
+        a, b = C.c_int(0), C.c_int(0)
+        _lib.check(self.engine.lib.st_pipeline_partition(self._p, C.byref(a), C.byref(b)), 'st_pipeline_partition')
+        return a.value, b.value
+
     def stats(self):
         """dict(graph_frames=frames replayed as graphs, captures=stream captures so far)."""
         a, b = C.c_longlong(0), C.c_longlong(0)

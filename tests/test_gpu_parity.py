@@ -823,6 +823,27 @@ def test_frame_pipeline_equals_sequential_steps(mods):
         st4 = pipe4.stats()
         assert st4 == dict(graph_frames=F - 3, captures=3), st4       # first use of a slot runs uncaptured
         assert eng4.status().max() == 0
+    # (e) SM partition (ST_PIPE_PARTITION=1 at pipeline creation): the tracker stream in a green context of its own,
+    # every other stream in a second one, frames replayed as graphs; results unchanged
+    os.environ['ST_PIPE_PARTITION'] = '1'
+    try:
+        eng5 = mods.StereoTrackEngine(mods.EngineConfig(n_seq=S))
+        pipe5 = FramePipeline(eng5, (S, cfg.height, cfg.width), levels, depth=F, depth_source='raw')
+    finally:
+        del os.environ['ST_PIPE_PARTITION']
+    trk_sms, other_sms = pipe5.partition()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert (trk_sms, other_sms) == (0, 0) or (trk_sms >= S and trk_sms + other_sms == sms), (trk_sms, other_sms)
+    assert pipe3.partition() == (0, 0)
+    pipe5.use_graphs(True)
+    for f in range(F):
+        pipe5.submit(fid[f], raw[f], [c[f] for c in heads[0]], [c[f] for c in heads[1]], [c[f] for c in heads[2]])
+    pipe5.join()
+    torch.cuda.synchronize()
+    for f in range(F):
+        check(pipe5.slots[f].results(), f)
+    assert eng5.status().max() == 0
+    del pipe5, eng5
 
 
 def test_capacity_overflow_raises_status_bits_not_silent_truncation(mods):
