@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define ST_ABI_VERSION 6
+#define ST_ABI_VERSION 7
 
 enum {
     ST_OK = 0,

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libstereotrack_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ST_STATUS = dict(CAND_OVERFLOW=1, DET_OVERFLOW=2, TRACK_OVERFLOW=4, LAP_GUARD=8)
 

@@ -10,25 +10,10 @@ timeout 200 $B > gpurun_out/plain.log 2>&1 || { echo 'plain bench failed'; tail 
 timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active \
     --clock-control none -k 'regex:^k[0-9]' -c 1200 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 python tools/ncu_summary.py gpurun_out/launches.csv | tee gpurun_out/launch_summary.txt
-# 2. K2 score pass alone, 2 and 4 loads in flight
-for it in 2 4; do
-  ST_K2_ITEMS=$it timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum --clock-control none -k 'regex:k2_score' --csv \
-      --log-file gpurun_out/k2_score_items$it.csv python tools/bench_k2.py > gpurun_out/ncu_k2_$it.log 2>&1
-  python - $it <<'PY'
-import csv, sys, collections
-it = sys.argv[1]
-rows = [r for r in csv.reader(open(f'gpurun_out/k2_score_items{it}.csv')) if len(r) > 5]
-h = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
-hdr = rows[h]; gi, mi, vi, ui = hdr.index('Grid Size'), hdr.index('Metric Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
-per = collections.defaultdict(list)
-for r in rows[h + 1:]:
-    if r[mi] == 'gpu__time_duration.sum':
-        per[r[gi]].append(float(r[vi].replace(',', '')) * {'ns': 1e-3, 'us': 1, 'ms': 1e3}[r[ui]])
-for g, v in per.items():
-    v.sort()
-    print(f'k2_score items={it} grid {g}: n={len(v)} median {v[len(v) // 2]:.1f} us')
-PY
-done
+# 2. K2 score pass alone (per-case medians: tools/k2_cases.py)
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum --clock-control none -k 'regex:k2_score' --csv \
+    --log-file gpurun_out/k2_score_shipped.csv python tools/bench_k2.py > gpurun_out/ncu_k2.log 2>&1
+python tools/k2_cases.py gpurun_out/k2_score_shipped.csv | tee gpurun_out/k2_score_cases.txt
 # 3. --set full captures of the kernels this round changed (one launch each, steady state)
 full() {  # name regex skip command...
   local name=$1 re=$2 skip=$3; shift 3
@@ -42,4 +27,5 @@ full k3r_box_depth_hist k3r_box_depth_hist 20 python tools/bench_k3.py 6 20
 full k3r_box_depth_warp 'k3r_box_depth\(' 20 python tools/bench_k3.py 6 20
 full k1b_pack_image_v4 k1b_pack_image_v4 5 python tools/bench_k1b.py
 full k1_disp2depth_flat k1_disp2depth_flat 10 python tools/bench_k1.py
+full k2_score_flat k2_score_flat 8 python tools/bench_k2.py big
 python tools/ncu_hot_lines.py gpurun_out/full_k4_track_step2.ncu-rep k4_track_step2 k4_track2 40 > gpurun_out/k4_hot_lines.txt 2>&1; head -5 gpurun_out/k4_hot_lines.txt
