@@ -263,6 +263,7 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
     if (threadIdx.x < 64) { sm.masks.rmask[threadIdx.x] = 0ull; sm.masks.cmask[threadIdx.x] = 0ull; }
     if (threadIdx.x == 0) { sm.adm_misc[0] = 0; sm.adm_misc[1] = 0; *sm.masks.fallback = 0; *sm.masks.n_comp = 0; }
     __syncthreads();
+    bool any_edge = false;                               // an admissible entry, a NaN or a cost at the limit
     for (int e = threadIdx.x; e < R * C; e += kThreads) {
         const int r = e / C, j = e - r * C;
         float dist;
@@ -280,13 +281,17 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
             atomicAdd(&sm.col_cnt[j], 1);
             sm.row_adm[r] = j;
             if (small) { atomicOr(&sm.masks.rmask[r], 1ull << j); atomicOr(&sm.masks.cmask[j], 1ull << r); }
+            any_edge = true;
         }
-        if (dist != dist) sm.adm_misc[0] = 1;
-        if (fabs((double)dist - lap_limit) <= 2.0e-9) sm.adm_misc[1] = 1;
+        if (dist != dist) { sm.adm_misc[0] = 1; any_edge = true; }
+        if (fabs((double)dist - lap_limit) <= 2.0e-9) { sm.adm_misc[1] = 1; any_edge = true; }
     }
-    __syncthreads();
+    const bool nothing = __syncthreads_or(any_edge) == 0;
     ST_SUB(14);
     if (threadIdx.x == 0) atomicAdd(&dbg[5], 1);        // assignments solved (fire and forget)
+    // every cost is above the limit by more than 2e-9 (the usual case in stage 3: what could be matched was matched
+    // in stage 1): the reference's solver leaves every row and column unmatched, and so does this stage
+    if (nothing && !dump) return;
     need_warp_path = !small;
     if (!skip && R <= 32 && C <= 32) {
         // a handful of rows and columns (always so in stages 2 and 3): the component path on warp 0
