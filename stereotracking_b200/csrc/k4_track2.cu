@@ -311,13 +311,21 @@ __device__ __forceinline__ void associate2(const Params &pr, Smem &sm, int32_t *
         if (*sm.masks.fallback == 0 && *sm.masks.n_comp == 0 && sm.masks.big[0] == 0ull) {
             need_warp_path = false;                      // isolated pairs and <= 2 x 2 components only: all solved already
         } else if (*sm.masks.fallback == 0) {
-            const int n_comp = *sm.masks.n_comp;
-            const bool has_big = sm.masks.big[0] != 0ull;
+            const int n_comp = *sm.masks.n_comp, n_big = sm.masks.n_comp[2];
             bool bad = false;
-            // warp 0 takes the larger components as one compact sub-problem (certified Hungarian) while
-            // the other warps enumerate the small ones
-            if (warp == 0 && has_big) bad = !stlap::solve_big_components(P, sm.lap, sm.masks, sm.sub);
-            const int first = has_big ? 1 : 0, nw = kWarps - first;
+            // the larger components (crowded groups) each go to the sparse certified solver on a warp of their own, as
+            // many at a time as there is scratch for: sm.sub, then pieces of the whole-problem scratch in front of
+            // x / y (unused on this path); the other warps enumerate the small components meanwhile
+            const size_t piece = (stlap::sub_bytes() + 15) & ~(size_t)15;
+            const int n_slots = 1 + min(3, (int)(((size_t)24 * (pr.T + pr.D)) / piece));
+            const int n_par = min(n_big, n_slots);
+            if (warp < n_par) {
+                unsigned char *mem = warp == 0 ? sm.sub
+                                               : reinterpret_cast<unsigned char *>(const_cast<double *>(sm.lap.v)) + (warp - 1) * piece;
+                for (int k = warp; k < n_big; k += n_par)
+                    bad |= !stlap::solve_component_sparse(P, sm.lap, sm.masks, sm.masks.comp_rows[63 - k], sm.masks.comp_cols[63 - k], mem);
+            }
+            const int first = n_par, nw = kWarps - first;
             if (warp >= first)
                 for (int k = warp - first; k < n_comp; k += nw)
                     bad |= !stlap::enumerate_component(P, sm.lap, sm.masks.comp_rows[k], sm.masks.comp_cols[k]);

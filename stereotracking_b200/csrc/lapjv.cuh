@@ -1258,7 +1258,8 @@ struct Masks {
     unsigned long long *comp_rows;    // [64] components of <= 4 x 4 found by prepare_components
     unsigned long long *comp_cols;    // [64]
     unsigned long long *big;          // [2] union of the rows / columns of all larger components
-    int *n_comp;                      // [1] number of small components
+    int *n_comp;                      // [0] number of small components; [2] number of larger ones (block version:
+                                      //     listed one by one in comp_rows / comp_cols[63 - k])
     int *fallback;                    // [1] != 0: the component path does not apply / failed
 };
 
@@ -1444,7 +1445,10 @@ __device__ inline void prepare_components_block(const Problem &P, Scratch &s, co
     __shared__ unsigned long long adj[64];
     __shared__ int changed_sh;
     for (int j = t; j < C; j += blockDim.x) s.y[j] = -1;
-    if (t == 0) { *m.n_comp = 0; m.big[0] = 0ull; m.big[1] = 0ull; *m.fallback = (P.adm_misc[0] != 0 || P.adm_misc[1] != 0) ? 1 : 0; }
+    if (t == 0) {
+        *m.n_comp = 0; m.n_comp[2] = 0; m.big[0] = 0ull; m.big[1] = 0ull;
+        *m.fallback = (P.adm_misc[0] != 0 || P.adm_misc[1] != 0) ? 1 : 0;
+    }
     __syncthreads();
     bool act = false;
     unsigned long long rm = 0ull, mine = 0ull;
@@ -1485,8 +1489,11 @@ __device__ inline void prepare_components_block(const Problem &P, Scratch &s, co
         unsigned long long cols = 0ull, q = mine;
         while (q) { cols |= m.rmask[__ffsll((long long)q) - 1]; q &= q - 1; }
         if (__popcll(mine) > 4 || __popcll(cols) > 4) {
-            atomicOr(&m.big[0], mine);                     // solved together as one compact sub-problem
+            atomicOr(&m.big[0], mine);                     // the union, for a caller that solves them as one sub-problem
             atomicOr(&m.big[1], cols);
+            const int kb = atomicAdd(m.n_comp + 2, 1);     // and one by one, from the end of the component list
+            m.comp_rows[63 - kb] = mine;                   // (components have distinct rows: small + larger ones <= 64)
+            m.comp_cols[63 - kb] = cols;
         } else if (__popcll(mine) <= 2 && __popcll(cols) <= 2 && *m.fallback == 0) {
             if (!solve_tiny_component(P, s, mine, cols)) *m.fallback = 1;      // a tie: the exact path decides
         } else {
@@ -1605,10 +1612,18 @@ __host__ __device__ inline size_t sub_bytes() {
 constexpr int kSubEdges = 256;         // admissible edges the sub-problem of the larger components may hold
 constexpr size_t kSubFront = 144 + 2 * 2 * kSubEdges + 4 * kSubEdges + 128;     // off | erow | ecol | ecost | lrow, lcol
 
+__device__ inline bool solve_component_sparse(const Problem &P, Scratch &s, const Masks &m, unsigned long long rows,
+                                              unsigned long long cols, unsigned char *sub_mem);
+
 __device__ inline bool solve_big_components(const Problem &P, Scratch &s, const Masks &m, unsigned char *sub_mem) {
+    return solve_component_sparse(P, s, m, m.big[0], m.big[1], sub_mem);
+}
+
+// one component (or a union of components) given by its row / column sets; sub_mem: sub_bytes() of scratch
+__device__ inline bool solve_component_sparse(const Problem &P, Scratch &s, const Masks &m, unsigned long long rows,
+                                              unsigned long long cols, unsigned char *sub_mem) {
     static_assert(kSubFront % 16 == 0, "state must start 16-byte aligned");
     const int lane = threadIdx.x & 31;
-    const unsigned long long rows = m.big[0], cols = m.big[1];
     if (!rows) return true;
     const int nR = __popcll(rows), nC = __popcll(cols);
     if (kSubFront + sparse_state_bytes(nR, nC) > sub_bytes()) return false;
